@@ -1,0 +1,236 @@
+/*
+ * irt_b200.h -- C ABI of the B200-native hot path of interactive-rate-tendons.
+ *
+ * The reference (Kuntz-Lab/interactive-rate-tendons) has no C ABI or plugin loader; its
+ * "operator API" for this path is a pair of C++ virtual interfaces plus the value types they
+ * exchange.  Every entry point below names the reference interface it
+ * replaces (file:line relative to /root/reference/cpp/src/).  INTEGRATION.md shows the
+ * reference-side C++ glue a maintainer would add.
+ *
+ * Conventions
+ *   - plain C: opaque handles, POD structs, pointers + sizes; no exceptions cross the boundary.
+ *   - every call returns an irt_status (0 = OK).  irt_last_error(ctx) has the detail string.
+ *   - "host" entry points take HOST pointers and copy H2D/D2H internally;
+ *     "_dev" entry points take DEVICE pointers (cudaMalloc'ed or torch tensors' data_ptr())
+ *     and a cudaStream_t passed as void* (NULL = the context's own stream); they are
+ *     asynchronous with respect to the host.
+ *   - there is NO CPU fallback: without a CUDA device irt_ctx_create fails with
+ *     IRT_ERR_NO_DEVICE and nothing else can be called.
+ *   - per-item problems (non-convergence, limits, ...) are NOT errors: they are reported in a
+ *     per-item uint32 flag word (IRT_FLAG_*), mirroring TendonResult::converged
+ *     (tendon/TendonRobot.cpp:470-474) and AbstractValidityChecker::is_valid_shape
+ *     (motion-planning/AbstractValidityChecker.cpp:99-114).
+ *
+ * Data layouts
+ *   state    double[S], S = N + [rotation] + [retraction]   (tendon/TendonRobot.h:60-64)
+ *   points   double[n][cap_pts][3], first npts[i] rows valid (TendonResult::p)
+ *   R        double[n][cap_pts][9] column-major               (TendonResult::R, Eigen storage)
+ *   voxel block  uint64, bit = x*16 + y*4 + z                 (collision/VoxelOctree.cpp:1501-1503)
+ *   block key    uint32 Morton code with x as the most significant bit of every 3-bit group:
+ *                exactly the reference's octant order (collision/detail/TreeNode.h:66-68), so a
+ *                key-sorted list is VoxelOctree::visit_leaves order and 8 consecutive keys are
+ *                one 2x2x2 group of leaf blocks = one 512-bit super-block.
+ *   set store    CSR: offsets uint64[n+1], keys uint32[nb], bits uint64[nb], key-sorted per set
+ *   verdicts     uint32 words, bit (i % 32) of word (i / 32) = set i collides with the environment
+ */
+#ifndef IRT_B200_H
+#define IRT_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define IRT_MAX_TENDONS 12
+#define IRT_MAX_COEF 8
+#define IRT_ABI_VERSION 1
+
+typedef enum irt_status {
+  IRT_OK = 0,
+  IRT_ERR_NO_DEVICE = 1,        /* no CUDA device / driver: there is no CPU fallback */
+  IRT_ERR_INVALID_ARGUMENT = 2, /* std::invalid_argument in the reference (wrong state size,
+                                   grid size mismatch, dL too coarse for the grid) */
+  IRT_ERR_OUT_OF_RANGE = 3,     /* std::out_of_range (tau / tendon count mismatch) */
+  IRT_ERR_CUDA = 4,             /* a CUDA runtime call or kernel failed */
+  IRT_ERR_UNSUPPORTED = 5,      /* routing the reference itself cannot handle */
+  IRT_ERR_CAPACITY = 6,         /* an output buffer / per-set capacity is too small */
+  IRT_ERR_DOMAIN = 7            /* std::domain_error: point outside the voxel grid */
+} irt_status;
+
+/* per-item flag word */
+#define IRT_FLAG_NONCONVERGED 1u   /* TendonResult::converged == false */
+#define IRT_FLAG_LENGTH_LIMIT 2u   /* !is_within_length_limits (tendon/TendonRobot.h:262-278) */
+#define IRT_FLAG_SELF_COLLISION 4u /* collides_self (collision/collision.cpp:6-46) */
+#define IRT_FLAG_OUT_OF_DOMAIN 8u  /* find_cell would throw std::domain_error */
+#define IRT_FLAG_PARTIAL 16u       /* edge: PartialVoxelization::is_fully_valid == false */
+#define IRT_FLAG_BAD_STATE 32u     /* retraction < 0 or NaN: outside the reference's state space */
+#define IRT_FLAG_CAPACITY 64u      /* per-item scratch capacity exceeded (result incomplete) */
+
+typedef struct irt_ctx irt_ctx;
+typedef struct irt_robot irt_robot;
+typedef struct irt_env irt_env;
+typedef struct irt_setstore irt_setstore;
+
+/* POD mirror of tendon::TendonRobot (tendon/TendonRobot.h:52-58), BackboneSpecs
+ * (tendon/BackboneSpecs.h:15-21) and TendonSpecs (tendon/TendonSpecs.h:24-30). */
+typedef struct irt_robot_desc {
+  double r;
+  double L, dL, ro, ri, E, nu;
+  double residual_threshold;
+  int32_t n_tendons;
+  int32_t n_c;  /* theta-polynomial length (all tendons share tendon 0's, get_r_info.h:34-39) */
+  int32_t n_d;  /* rho-polynomial length */
+  int32_t enable_rotation;
+  int32_t enable_retraction;
+  int32_t _pad;
+  double C[IRT_MAX_TENDONS * IRT_MAX_COEF]; /* row-major [tendon][coef] */
+  double D[IRT_MAX_TENDONS * IRT_MAX_COEF];
+  double max_tension[IRT_MAX_TENDONS];
+  double min_length[IRT_MAX_TENDONS];
+  double max_length[IRT_MAX_TENDONS];
+} irt_robot_desc;
+
+/* Voxel grid geometry: VoxelOctree limits (collision/VoxelOctree.h:310-329) and
+ * VoxelEnvironment::inv_rotation (motion-planning/VoxelEnvironment.cpp:129-131). */
+typedef struct irt_grid {
+  int32_t Ng; /* voxels per axis, power of two in [4, 512] (VoxelOctree.cpp:83-116) */
+  int32_t _pad;
+  double lim[6];     /* xmin,xmax,ymin,ymax,zmin,zmax */
+  double inv_rot[9]; /* row-major */
+} irt_grid;
+
+/* OMPL space constants fixed by Problem::create_space_information
+ * (motion-planning/Problem.cpp:101-163, Problem.h:59-63). */
+typedef struct irt_space {
+  double min_tension_change;    /* default 0.02 */
+  double min_rotation_change;   /* default 0.01 */
+  double min_retraction_change; /* default 1e-4 */
+} irt_space;
+
+/* optional FK outputs; NULL members are skipped.  Host or device pointers depending on the
+ * entry point.  Mirrors tendon::TendonResult (tendon/TendonResult.h:17-28). */
+typedef struct irt_fk_outputs {
+  double *p;       /* [n][cap_pts][3] */
+  double *R;       /* [n][cap_pts][9] column-major */
+  double *t;       /* [n][cap_pts] */
+  int32_t *npts;   /* [n] */
+  double *L;       /* [n] */
+  double *L_i;     /* [n][N] */
+  double *tip;     /* [n][3]  == p[npts-1] */
+  double *uv;      /* [n][12]: u_i, u_f, v_i, v_f */
+  uint32_t *flags; /* [n] IRT_FLAG_NONCONVERGED | LENGTH_LIMIT | SELF_COLLISION | BAD_STATE */
+  int32_t *iters;  /* [n] fixed-point iterations (solve_initial_bending.cpp:41-70) */
+  int32_t *nsteps; /* [n] RK4 steps taken */
+} irt_fk_outputs;
+
+/* ---- context ------------------------------------------------------------------------- */
+int irt_abi_version(void);
+const char *irt_status_string(int status);
+int irt_ctx_create(int device, irt_ctx **out);
+void irt_ctx_destroy(irt_ctx *ctx);
+const char *irt_last_error(const irt_ctx *ctx);
+int irt_ctx_device(const irt_ctx *ctx);
+int irt_ctx_synchronize(irt_ctx *ctx);
+/* kernels launched by this context since creation (bench.py "gpu_launches") */
+int64_t irt_ctx_launch_count(const irt_ctx *ctx);
+/* measured FP64 DFMA-chain peak of this device in FLOP/s (roofline denominator for K1) */
+int irt_measure_fp64_peak(irt_ctx *ctx, double *flops_per_s);
+
+/* ---- robot: replaces tendon::TendonRobot (tendon/TendonRobot.h:52-355) ------------------ */
+int irt_robot_create(irt_ctx *ctx, const irt_robot_desc *desc, irt_robot **out);
+void irt_robot_destroy(irt_robot *rb);
+int irt_robot_state_size(const irt_robot *rb); /* TendonRobot::state_size, TendonRobot.h:60-64 */
+int irt_robot_max_points(const irt_robot *rb); /* len(t_range(0, L, dL)), TendonRobot.cpp:69-84 */
+
+/* K1: TendonRobot::shape(state) for n states (tendon/TendonRobot.h:105-131 ->
+ * tension_shape TendonRobot.cpp:325-500), plus the validity epilogue
+ * AbstractValidityChecker::is_valid_shape (AbstractValidityChecker.cpp:99-114) when
+ * out->flags != NULL.  Replaces the OpenMP loops apps/estimate_length_discretization.cpp:62-71
+ * and apps/roadmap2samples.cpp:64-78.
+ * IRT_ERR_INVALID_ARGUMENT if state_size != irt_robot_state_size (TendonRobot.h:107-109),
+ * IRT_ERR_CAPACITY if cap_pts < irt_robot_max_points. */
+int irt_fk_batch(irt_ctx *ctx, const irt_robot *rb, const double *states, int state_size,
+                 int64_t n, int cap_pts, const irt_fk_outputs *out);
+int irt_fk_batch_dev(irt_ctx *ctx, const irt_robot *rb, const double *d_states, int state_size,
+                     int64_t n, int cap_pts, const irt_fk_outputs *d_out, void *stream);
+/* TendonRobot::home_shape(state).L_i (tendon/TendonRobot.cpp:249-314), host arrays */
+int irt_home_lengths_batch(irt_ctx *ctx, const irt_robot *rb, const double *states,
+                           int state_size, int64_t n, double *L_i);
+
+/* ---- environment: replaces the obstacle collision::VoxelOctree each validator copies at
+ * construction (AbstractVoxelValidityChecker.h:22-25,64; AbstractVoxelMotionValidator.h:191) */
+int irt_env_create(irt_ctx *ctx, const irt_grid *grid, irt_env **out);
+void irt_env_destroy(irt_env *env);
+/* dense upload: blocks[Nb^3] indexed by Morton key */
+int irt_env_update(irt_ctx *ctx, irt_env *env, const uint64_t *blocks);
+int irt_env_update_dev(irt_ctx *ctx, irt_env *env, const uint64_t *d_blocks, void *stream);
+/* sparse upload from VoxelOctree::visit_leaves output: (bx,by,bz) uint8 triples + bits */
+int irt_env_update_sparse(irt_ctx *ctx, irt_env *env, const uint8_t *bxyz,
+                          const uint64_t *bits, int64_t nblocks);
+int64_t irt_env_nblocks(irt_ctx *ctx, const irt_env *env); /* VoxelOctree::nblocks */
+
+/* ---- set store: replaces vertexVoxelsProperty_/edgeVoxelsProperty_
+ * (std::shared_ptr<VoxelOctree> per vertex/edge, VoxelCachedLazyPRM.h:141,165-179) ------- */
+int irt_setstore_create(irt_ctx *ctx, const irt_grid *grid, irt_setstore **out);
+void irt_setstore_destroy(irt_setstore *s);
+int64_t irt_setstore_num_sets(const irt_setstore *s);
+int64_t irt_setstore_num_blocks(const irt_setstore *s);
+/* import/export the CSR (host arrays); the .rmp record list {u8 bx,u8 by,u8 bz,u64 bits}
+ * (VoxelCachedLazyPRM.cpp:1091-1095) converts 1:1 with irt_morton_key / irt_morton_decode */
+int irt_setstore_import(irt_ctx *ctx, irt_setstore *s, int64_t n_sets, const uint64_t *offsets,
+                        const uint32_t *keys, const uint64_t *bits);
+int irt_setstore_export(irt_ctx *ctx, const irt_setstore *s, uint64_t *offsets, uint32_t *keys,
+                        uint64_t *bits);
+/* device views (valid until the store is next modified) */
+int irt_setstore_device_ptrs(const irt_setstore *s, const uint64_t **d_offsets,
+                             const uint32_t **d_keys, const uint64_t **d_bits);
+uint32_t irt_morton_key(int bx, int by, int bz, int Nb);
+void irt_morton_decode(uint32_t key, int Nb, int *bx, int *by, int *bz);
+
+/* K1+K2 (vertex mode): VoxelCachedLazyPRM::precomputeVertexVoxelCache /
+ * voxelizeVertex (VoxelCachedLazyPRM.cpp:1687-1712,2803-2837): FK + is_valid_shape +
+ * VoxelBackboneValidityChecker::voxelize_impl (VoxelBackboneValidityChecker.h:49-57).
+ * Replaces the store content with n sets (an invalid shape gets an empty set and its flags).
+ * tips (optional, [n][3]) = fk_shape.p.back(). */
+int irt_voxelize_vertices(irt_ctx *ctx, const irt_robot *rb, const double *states,
+                          int state_size, int64_t n, irt_setstore *store, uint32_t *flags,
+                          double *tips);
+/* K1+K2 (edge mode): VoxelCachedLazyPRM::precomputeEdgeVoxelCache / voxelizeEdge
+ * (VoxelCachedLazyPRM.cpp:1736-1782,2879-2902) -> AbstractVoxelMotionValidator::voxelize
+ * (AbstractVoxelMotionValidator.h:98-107) -> VoxelBackboneMotionValidator::generic_voxelize
+ * (VoxelBackboneMotionValidator.cpp:41-74) -> VoxelEnvironment::voxelize_valid_backbone_motion
+ * (VoxelEnvironment.cpp:207-444).  a,b: [n][S] endpoint states.  Outputs (optional):
+ * flags (IRT_FLAG_PARTIAL = !is_fully_valid), t_last = PartialVoxelization::t,
+ * nsamples = FK evaluations spent on the edge. */
+int irt_voxelize_edges(irt_ctx *ctx, const irt_robot *rb, const irt_space *space,
+                       const double *a, const double *b, int state_size, int64_t n,
+                       irt_setstore *store, uint32_t *flags, double *t_last, int32_t *nsamples);
+/* OMPL StateSpace::validSegmentCount for the compound space of Problem.cpp:101-163 (host) */
+uint32_t irt_valid_segment_count(const irt_robot_desc *desc, const irt_space *space,
+                                 const double *a, const double *b);
+
+/* K3: VoxelOctree::collides(other) (collision/VoxelOctree.cpp:973-978) of every cached set in
+ * [begin,end) against the environment; the batch form of computeVertexValidity /
+ * computeEdgeValidity with warm caches (VoxelCachedLazyPRM.cpp:2607-2631) as driven by
+ * precomputeVertexValidity / precomputeEdgeValidity (:1563-1647).
+ * verdict_words: uint32[(end-begin+31)/32], bit i-begin set <=> set i collides.
+ * IRT_ERR_INVALID_ARGUMENT if the grids' Ng differ (VoxelOctree.cpp:46-53). */
+int irt_check_sets(irt_ctx *ctx, const irt_setstore *store, const irt_env *env, int64_t begin,
+                   int64_t end, uint32_t *verdict_words);
+int irt_check_sets_dev(irt_ctx *ctx, const irt_setstore *store, const irt_env *env,
+                       int64_t begin, int64_t end, uint32_t *d_verdict_words, void *stream);
+/* the popcount side of K3 over the same range: stats[0] = sum over leaves of
+ * popcount(set_bits & env_bits) (colliding voxels), stats[1] = number of leaves that hit.
+ * Not part of the reference API (its collides() stops at the first hit); used as a
+ * size-independent checksum and for reporting. */
+int irt_check_sets_popcount(irt_ctx *ctx, const irt_setstore *store, const irt_env *env,
+                            int64_t begin, int64_t end, uint64_t *stats);
+/* algorithmic bytes one irt_check_sets call over [begin,end) moves:
+ * sum(12*nb + 8) + 8*Nb^3 + ceil(n/8) */
+int64_t irt_check_sets_algorithmic_bytes(const irt_setstore *store, int64_t begin, int64_t end);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* IRT_B200_H */

@@ -1,0 +1,111 @@
+// common.cuh -- shared declarations of the sm_100a hot-path library (libirt_b200.so).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <atomic>
+#include <cstdio>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/irt_b200.h"
+
+#define IRT_CAP_PTS_MAX 512  // upper bound on backbone points per shape (L/dL + 2)
+
+struct irt_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  int sm_count = 148;
+  std::string last_error;
+  std::atomic<int64_t> launches{0};
+  std::mutex mu;
+  // growable device scratch owned by the context (never shrinks)
+  void *scratch = nullptr;
+  size_t scratch_bytes = 0;
+};
+
+// device-resident robot constants (passed to kernels by value)
+struct RobotDev {
+  double Kse[3], Kbt[3], KseInv[3], KbtInv[3];
+  double L, dL, r, residual_threshold;
+  double C[IRT_MAX_TENDONS * IRT_MAX_COEF];
+  double D[IRT_MAX_TENDONS * IRT_MAX_COEF];
+  double home_factor[IRT_MAX_TENDONS];  // L_i^home = (L - s) * home_factor  (TendonRobot.cpp:281-310)
+  double min_length[IRT_MAX_TENDONS], max_length[IRT_MAX_TENDONS];
+  int n_tendons, n_c, n_d, enable_rotation, enable_retraction;
+  int Kfull;          // number of grid nodes for s = 0, excluding the start point
+  int n_table;        // 2*Kfull - 1 entries: idx(node i) = 2i, idx(mid of step i -> i-1) = 2i - 1
+  int n_head;         // no-retraction robots: tabulated first-gap stages (<= 4 entries)
+  double head_h[2];   // no-retraction robots: first-gap step sizes (h[1] = 0 if one step)
+  const double *table;  // device: [n_table][N][6] = rx, ry, rdx, rdy, rddx, rddy
+  const double *head;   // device: [4][N][6]
+  const double *node_t; // device: [Kfull] canonical node times L - i*dL
+};
+
+struct irt_robot {
+  irt_ctx *ctx = nullptr;
+  irt_robot_desc desc;
+  RobotDev dev;
+  int state_size = 0;
+  int max_points = 0;
+  double *d_table = nullptr;
+  double *d_head = nullptr;
+  double *d_node_t = nullptr;
+  std::vector<double> node_t;
+};
+
+struct GridDev {
+  int Ng, Nb, levels;       // Nb = Ng/4, levels = log2(Nb)
+  double lo[3], hi[3], d[3], inv_d[3];
+  double inv_rot[9];
+  int identity_rot;
+};
+
+struct irt_env {
+  irt_ctx *ctx = nullptr;
+  irt_grid grid;
+  GridDev gd;
+  uint64_t *d_blocks = nullptr;  // [Nb^3] Morton-ordered dense leaf blocks
+  uint32_t *d_occ = nullptr;     // [Nb^3/32] leaf-occupancy bitmap (bit = block non-empty)
+  int64_t n_blocks_total = 0;
+};
+
+struct irt_setstore {
+  irt_ctx *ctx = nullptr;
+  irt_grid grid;
+  GridDev gd;
+  int64_t n_sets = 0, n_blocks = 0;
+  uint64_t *d_offsets = nullptr;  // [n_sets + 1]
+  uint32_t *d_keys = nullptr;     // [n_blocks]
+  uint64_t *d_bits = nullptr;     // [n_blocks]
+  size_t cap_sets = 0, cap_blocks = 0;
+  uint32_t *d_chunk_set = nullptr;  // [n_blocks/128 + 1] id of the set holding leaf 128*c
+  size_t cap_chunks = 0;
+};
+
+int irt_fail(irt_ctx *ctx, int status, const char *fmt, ...);
+GridDev make_grid_dev(const irt_grid &g);
+int grid_check(irt_ctx *ctx, const irt_grid *g);
+void *ctx_scratch(irt_ctx *ctx, size_t bytes);  // nullptr on failure
+
+#define IRT_CUDA(ctx, call)                                                             \
+  do {                                                                                  \
+    cudaError_t _e = (call);                                                            \
+    if (_e != cudaSuccess)                                                              \
+      return irt_fail((ctx), IRT_ERR_CUDA, "%s failed: %s (%s:%d)", #call,              \
+                      cudaGetErrorString(_e), __FILE__, __LINE__);                      \
+  } while (0)
+
+#define IRT_LAUNCHED(ctx) ((ctx)->launches.fetch_add(1, std::memory_order_relaxed))
+
+// internal cross-file entry points
+int setstore_reserve(irt_ctx *ctx, irt_setstore *s, int64_t n_sets, int64_t n_blocks);
+int setstore_finalize(irt_ctx *ctx, irt_setstore *s, int64_t n_sets, int64_t n_blocks,
+                      cudaStream_t st);
+int fk_launch(irt_ctx *ctx, const irt_robot *rb, const double *d_states, int64_t n, int cap_pts,
+              const irt_fk_outputs &o, const int32_t *d_perm, cudaStream_t st);
+int self_collision_launch(irt_ctx *ctx, const irt_robot *rb, const double *d_p,
+                          const int32_t *d_npts, int64_t n, int cap_pts, uint32_t *d_flags,
+                          cudaStream_t st);

@@ -1,0 +1,617 @@
+// fk.cu -- K1 `fk_rk4_fp64`: batched forward kinematics of tendon robots on sm_100a.
+//
+// Replaces TendonRobot::shape -> tension_shape (tendon/TendonRobot.cpp:325-500):
+//   solve_initial_bending (tendon/solve_initial_bending.cpp:15-73), RK4 over t_range
+//   (TendonRobot.cpp:69-84,458-462) of tendon_deriv (tendon/tendon_deriv.cpp:95-178), the
+//   convergence flag (TendonRobot.cpp:188-217,470-474), rotate_z (TendonResult.cpp:13-18) and
+//   the length-limit part of is_valid_shape (AbstractValidityChecker.cpp:99-114).
+//
+// Design (B200-first, not a translation):
+//   * one configuration per thread; the whole ODE state lives in registers.
+//   * the routing r, r', r'' of every tendon at every RK4 stage time is state-independent
+//     because the arclength grid is anchored at L (TendonRobot.cpp:69-84): it is tabulated once
+//     per robot on the host (the sin/cos of get_r_info.cpp:133-134 never run in the hot loop)
+//     and staged in shared memory; a warp walks the table in lock-step so every read is a
+//     broadcast.  Only the irregular first gap next to the retracted base is evaluated per thread.
+//   * the per-tendon 3x3 blocks are accumulated in outer-product form
+//       A_i = c3 (s2 I - q q^T),  B_i = c3 (s2 r^ - m q^T),  G_i = B_i^T,
+//       H_i = c3 (s2 (|r|^2 I - r r^T) - m m^T),   m = r x q, c3 = tau / sigma^3,
+//     (algebraically identical to tendon_deriv.cpp:136-157) and the 6x6 system is solved by a
+//     symmetric Schur complement (same block elimination as linsubsolve2, tendon_deriv.cpp:60-87)
+//     using adjugates, so a derivative evaluation needs 2 reciprocals and N+1 rsqrt only.
+//   * configurations are bucketed by node count (retraction) so warps stay converged.
+#include <cmath>
+#include <limits>
+
+#include "common.cuh"
+
+namespace {
+
+constexpr int FK_THREADS = 128;
+
+__device__ __forceinline__ double rcp_fast(double x) { return 1.0 / x; }
+
+// routing at arbitrary t, per thread (only used inside the irregular first gap)
+template <int NT>
+__device__ __noinline__ void routing_eval(const RobotDev &rb, double t, double *out) {
+  const int Na = rb.n_c, Nm = rb.n_d;
+  const int Ns = Na > Nm ? Na : Nm;
+  double S[IRT_MAX_COEF], Sd[IRT_MAX_COEF], Sdd[IRT_MAX_COEF];
+  S[0] = 1; Sd[0] = 0; Sdd[0] = 0;
+  if (Ns >= 2) { S[1] = t; Sd[1] = 1; Sdd[1] = 0; }
+  for (int i = 2; i < Ns; i++) {
+    S[i] = t * S[i - 1];
+    Sd[i] = i * S[i - 1];
+    Sdd[i] = i * (i - 1) * S[i - 2];
+  }
+  for (int j = 0; j < NT; j++) {
+    const double *C = rb.C + j * IRT_MAX_COEF, *D = rb.D + j * IRT_MAX_COEF;
+    double th = 0, th1 = 0, th2 = 0, rho = 0, rho1 = 0, rho2 = 0;
+    for (int i = 0; i < Na; i++) { th += C[i] * S[i]; th1 += C[i] * Sd[i]; th2 += C[i] * Sdd[i]; }
+    for (int i = 0; i < Nm; i++) { rho += D[i] * S[i]; rho1 += D[i] * Sd[i]; rho2 += D[i] * Sdd[i]; }
+    double s, c;
+    sincos(th, &s, &c);
+    double *o = out + 6 * j;
+    o[0] = rho * s;
+    o[1] = rho * c;
+    o[2] = rho1 * s + rho * (c * th1);
+    o[3] = rho1 * c + rho * (-s * th1);
+    o[4] = ((rho2 * s + (2 * rho1) * (c * th1)) - rho * (s * th1 * th1)) + rho * (c * th2);
+    o[5] = ((rho2 * c + (2 * rho1) * (-s * th1)) - rho * (c * th1 * th1)) + rho * (-s * th2);
+  }
+}
+
+// (v', u', sigma_i) at one RK4 stage.  rt: [NT][6] routing (shared table or local array).
+template <int NT>
+__device__ __forceinline__ void vu_dot(const double *__restrict__ rt, const double (&tau)[NT],
+                                       const double (&Kse)[3], const double (&Kbt)[3],
+                                       const double (&v)[3], const double (&u)[3],
+                                       double (&vd)[3], double (&ud)[3], double (&sig)[NT]) {
+  // symmetric A (00,01,02,11,12,22), full B (row-major), symmetric H, a, b
+  double a00 = 0, a01 = 0, a02 = 0, a11 = 0, a12 = 0, a22 = 0;
+  double b00 = 0, b01 = 0, b02 = 0, b10 = 0, b11 = 0, b12 = 0, b20 = 0, b21 = 0, b22 = 0;
+  double h00 = 0, h01 = 0, h02 = 0, h11 = 0, h12 = 0, h22 = 0;
+  double av0 = 0, av1 = 0, av2 = 0, bv0 = 0, bv1 = 0, bv2 = 0;
+  double esum = 0, erx = 0, ery = 0, exx = 0, eyy = 0, exy = 0;
+#pragma unroll
+  for (int j = 0; j < NT; j++) {
+    const double rx = rt[6 * j + 0], ry = rt[6 * j + 1];
+    const double dx = rt[6 * j + 2], dy = rt[6 * j + 3];
+    const double ddx = rt[6 * j + 4], ddy = rt[6 * j + 5];
+    // q = u x r + r' + v        (r_z = r'_z = r''_z = 0)
+    const double qx = fma(-u[2], ry, dx + v[0]);
+    const double qy = fma(u[2], rx, dy + v[1]);
+    const double qz = fma(u[0], ry, fma(-u[1], rx, v[2]));
+    const double s2 = fma(qx, qx, fma(qy, qy, qz * qz));
+    const double rs = rsqrt(s2);
+    sig[j] = s2 * rs;
+    const double e = tau[j] * rs;        // tau / sigma
+    const double c3 = e * (rs * rs);     // tau / sigma^3
+    const double mx = ry * qz, my = -rx * qz, mz = fma(rx, qy, -ry * qx);  // m = r x q
+    const double cqx = c3 * qx, cqy = c3 * qy, cqz = c3 * qz;
+    const double cmx = c3 * mx, cmy = c3 * my, cmz = c3 * mz;
+    a00 = fma(-cqx, qx, a00); a01 = fma(-cqx, qy, a01); a02 = fma(-cqx, qz, a02);
+    a11 = fma(-cqy, qy, a11); a12 = fma(-cqy, qz, a12); a22 = fma(-cqz, qz, a22);
+    esum += e;
+    b00 = fma(-cmx, qx, b00); b01 = fma(-cmx, qy, b01); b02 = fma(-cmx, qz, b02);
+    b10 = fma(-cmy, qx, b10); b11 = fma(-cmy, qy, b11); b12 = fma(-cmy, qz, b12);
+    b20 = fma(-cmz, qx, b20); b21 = fma(-cmz, qy, b21); b22 = fma(-cmz, qz, b22);
+    const double erxj = e * rx, eryj = e * ry;
+    erx += erxj; ery += eryj;
+    h00 = fma(-cmx, mx, h00); h01 = fma(-cmx, my, h01); h02 = fma(-cmx, mz, h02);
+    h11 = fma(-cmy, my, h11); h12 = fma(-cmy, mz, h12); h22 = fma(-cmz, mz, h22);
+    exx = fma(erxj, rx, exx); eyy = fma(eryj, ry, eyy); exy = fma(erxj, ry, exy);
+    // w = u x (q + r') + r''
+    const double gx = qx + dx, gy = qy + dy, gz = qz;
+    const double wx = fma(u[1], gz, fma(-u[2], gy, ddx));
+    const double wy = fma(u[2], gx, fma(-u[0], gz, ddy));
+    const double wz = fma(u[0], gy, -u[1] * gx);
+    const double qw = fma(qx, wx, fma(qy, wy, qz * wz));
+    // a_i = A_i w = e w - c3 q (q.w)
+    const double ax = fma(e, wx, -cqx * qw), ay = fma(e, wy, -cqy * qw), az = fma(e, wz, -cqz * qw);
+    av0 += ax; av1 += ay; av2 += az;
+    // b_i = r x a_i
+    bv0 = fma(ry, az, bv0); bv1 = fma(-rx, az, bv1); bv2 += fma(rx, ay, -ry * ax);
+  }
+  // A += (sum e) I + K_se ;  B += sum e r^ ;  H += sum e (|r|^2 I - r r^T) + K_bt
+  a00 += esum + Kse[0]; a11 += esum + Kse[1]; a22 += esum + Kse[2];
+  b02 += ery; b12 -= erx; b20 -= ery; b21 += erx;
+  h00 += eyy + Kbt[0]; h11 += exx + Kbt[1]; h22 += (exx + eyy) + Kbt[2]; h01 -= exy;
+
+  // right-hand sides (tendon_deriv.cpp:159-161), K diagonal
+  const double kv0 = Kse[0] * v[0], kv1 = Kse[1] * v[1], kv2 = Kse[2] * (v[2] - 1.0);
+  const double ku0 = Kbt[0] * u[0], ku1 = Kbt[1] * u[1], ku2 = Kbt[2] * u[2];
+  // c = -u x Ku - v x Kv - b ; d = -u x Kv - a
+  const double c0 = -(fma(u[1], ku2, -u[2] * ku1)) - (fma(v[1], kv2, -v[2] * kv1)) - bv0;
+  const double c1 = -(fma(u[2], ku0, -u[0] * ku2)) - (fma(v[2], kv0, -v[0] * kv2)) - bv1;
+  const double c2 = -(fma(u[0], ku1, -u[1] * ku0)) - (fma(v[0], kv1, -v[1] * kv0)) - bv2;
+  const double d0 = -(fma(u[1], kv2, -u[2] * kv1)) - av0;
+  const double d1 = -(fma(u[2], kv0, -u[0] * kv2)) - av1;
+  const double d2 = -(fma(u[0], kv1, -u[1] * kv0)) - av2;
+
+  // solve [[A, B^T],[B, H]] [v'; u'] = [d; c]:  adjugate of symmetric A
+  const double C00 = fma(a11, a22, -a12 * a12), C01 = fma(a02, a12, -a01 * a22),
+               C02 = fma(a01, a12, -a02 * a11), C11 = fma(a00, a22, -a02 * a02),
+               C12 = fma(a01, a02, -a00 * a12), C22 = fma(a00, a11, -a01 * a01);
+  const double detA = fma(a00, C00, fma(a01, C01, a02 * C02));
+  const double idA = rcp_fast(detA);
+  // Y = adj(A) B^T (unscaled):  Y[i][j] = sum_k C[i][k] B[j][k]
+  const double y00 = fma(C00, b00, fma(C01, b01, C02 * b02));
+  const double y01 = fma(C00, b10, fma(C01, b11, C02 * b12));
+  const double y02 = fma(C00, b20, fma(C01, b21, C02 * b22));
+  const double y10 = fma(C01, b00, fma(C11, b01, C12 * b02));
+  const double y11 = fma(C01, b10, fma(C11, b11, C12 * b12));
+  const double y12 = fma(C01, b20, fma(C11, b21, C12 * b22));
+  const double y20 = fma(C02, b00, fma(C12, b01, C22 * b02));
+  const double y21 = fma(C02, b10, fma(C12, b11, C22 * b12));
+  const double y22 = fma(C02, b20, fma(C12, b21, C22 * b22));
+  // S = H - idA * B Y   (symmetric)
+  const double s00 = fma(-idA, fma(b00, y00, fma(b01, y10, b02 * y20)), h00);
+  const double s01 = fma(-idA, fma(b00, y01, fma(b01, y11, b02 * y21)), h01);
+  const double s02 = fma(-idA, fma(b00, y02, fma(b01, y12, b02 * y22)), h02);
+  const double s11 = fma(-idA, fma(b10, y01, fma(b11, y11, b12 * y21)), h11);
+  const double s12 = fma(-idA, fma(b10, y02, fma(b11, y12, b12 * y22)), h12);
+  const double s22 = fma(-idA, fma(b20, y02, fma(b21, y12, b22 * y22)), h22);
+  // z = A^-1 d
+  const double z0 = idA * fma(C00, d0, fma(C01, d1, C02 * d2));
+  const double z1 = idA * fma(C01, d0, fma(C11, d1, C12 * d2));
+  const double z2 = idA * fma(C02, d0, fma(C12, d1, C22 * d2));
+  // y = c - B z
+  const double r0 = c0 - fma(b00, z0, fma(b01, z1, b02 * z2));
+  const double r1 = c1 - fma(b10, z0, fma(b11, z1, b12 * z2));
+  const double r2 = c2 - fma(b20, z0, fma(b21, z1, b22 * z2));
+  // u' = S^-1 y
+  const double T00 = fma(s11, s22, -s12 * s12), T01 = fma(s02, s12, -s01 * s22),
+               T02 = fma(s01, s12, -s02 * s11), T11 = fma(s00, s22, -s02 * s02),
+               T12 = fma(s01, s02, -s00 * s12), T22 = fma(s00, s11, -s01 * s01);
+  const double detS = fma(s00, T00, fma(s01, T01, s02 * T02));
+  const double idS = rcp_fast(detS);
+  ud[0] = idS * fma(T00, r0, fma(T01, r1, T02 * r2));
+  ud[1] = idS * fma(T01, r0, fma(T11, r1, T12 * r2));
+  ud[2] = idS * fma(T02, r0, fma(T12, r1, T22 * r2));
+  // v' = z - idA * Y u'
+  vd[0] = fma(-idA, fma(y00, ud[0], fma(y01, ud[1], y02 * ud[2])), z0);
+  vd[1] = fma(-idA, fma(y10, ud[0], fma(y11, ud[1], y12 * ud[2])), z1);
+  vd[2] = fma(-idA, fma(y20, ud[0], fma(y21, ud[1], y22 * ud[2])), z2);
+}
+
+template <int NT>
+struct FkState {
+  double p[3];
+  double R[9];  // column-major (R[i + 3 j]) like Eigen
+  double v[3], u[3];
+  double Lb;
+  double Li[NT];
+};
+
+// one classic RK4 step of size h; rt0/rt1/rt2 = routing at t, t+h/2, t+h
+template <int NT>
+__device__ __forceinline__ void rk4_step(FkState<NT> &x, const double (&tau)[NT],
+                                         const double (&Kse)[3], const double (&Kbt)[3], double h,
+                                         const double *__restrict__ rt0,
+                                         const double *__restrict__ rt1,
+                                         const double *__restrict__ rt2) {
+  const double hh = 0.5 * h, w1 = h * (1.0 / 6.0), w2 = h * (1.0 / 3.0);
+  double sv[3], su[3], sR[9];      // stage values
+  double aR[9], av[3], au[3];      // sum of weighted slopes (k1 + 2 k2 + 2 k3 + k4)
+  double vd[3], ud[3], sig[NT], Rd[9];
+#pragma unroll
+  for (int i = 0; i < 3; i++) { sv[i] = x.v[i]; su[i] = x.u[i]; }
+#pragma unroll
+  for (int i = 0; i < 9; i++) sR[i] = x.R[i];
+
+#pragma unroll
+  for (int stage = 0; stage < 4; stage++) {
+    const double *rt = (stage == 0) ? rt0 : ((stage == 3) ? rt2 : rt1);
+    const double wq = (stage == 0 || stage == 3) ? w1 : w2;    // quadrature weight
+    const double wk = (stage == 0 || stage == 3) ? 1.0 : 2.0;  // slope weight in a*
+    vu_dot<NT>(rt, tau, Kse, Kbt, sv, su, vd, ud, sig);
+    // p' = R v ; L' = |v| ; L_i' = sigma_i : pure quadratures, accumulate in place
+#pragma unroll
+    for (int i = 0; i < 3; i++)
+      x.p[i] = fma(wq, fma(sR[i], sv[0], fma(sR[i + 3], sv[1], sR[i + 6] * sv[2])), x.p[i]);
+    x.Lb = fma(wq, sqrt(fma(sv[0], sv[0], fma(sv[1], sv[1], sv[2] * sv[2]))), x.Lb);
+#pragma unroll
+    for (int j = 0; j < NT; j++) x.Li[j] = fma(wq, sig[j], x.Li[j]);
+    // R' = R u^
+#pragma unroll
+    for (int i = 0; i < 3; i++) {
+      Rd[i] = fma(sR[i + 3], su[2], -sR[i + 6] * su[1]);
+      Rd[i + 3] = fma(sR[i + 6], su[0], -sR[i] * su[2]);
+      Rd[i + 6] = fma(sR[i], su[1], -sR[i + 3] * su[0]);
+    }
+    if (stage == 0) {
+#pragma unroll
+      for (int i = 0; i < 9; i++) aR[i] = Rd[i];
+#pragma unroll
+      for (int i = 0; i < 3; i++) { av[i] = vd[i]; au[i] = ud[i]; }
+    } else {
+#pragma unroll
+      for (int i = 0; i < 9; i++) aR[i] = fma(wk, Rd[i], aR[i]);
+#pragma unroll
+      for (int i = 0; i < 3; i++) { av[i] = fma(wk, vd[i], av[i]); au[i] = fma(wk, ud[i], au[i]); }
+    }
+    if (stage < 3) {
+      const double a = (stage == 2) ? h : hh;
+#pragma unroll
+      for (int i = 0; i < 9; i++) sR[i] = fma(a, Rd[i], x.R[i]);
+#pragma unroll
+      for (int i = 0; i < 3; i++) { sv[i] = fma(a, vd[i], x.v[i]); su[i] = fma(a, ud[i], x.u[i]); }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 9; i++) x.R[i] = fma(w1, aR[i], x.R[i]);
+#pragma unroll
+  for (int i = 0; i < 3; i++) { x.v[i] = fma(w1, av[i], x.v[i]); x.u[i] = fma(w1, au[i], x.u[i]); }
+}
+
+struct RotZ {
+  double c, s;
+  int on;
+};
+
+template <int NT>
+__device__ __forceinline__ void emit_node(const irt_fk_outputs &o, int64_t cfg, int cap_pts, int k,
+                                          double t, const FkState<NT> &x, const RotZ &rz) {
+  const int64_t row = cfg * cap_pts + k;
+  double px = x.p[0], py = x.p[1];
+  if (rz.on) {
+    px = rz.c * x.p[0] - rz.s * x.p[1];
+    py = rz.s * x.p[0] + rz.c * x.p[1];
+  }
+  if (o.p) {
+    double *dst = o.p + row * 3;
+    dst[0] = px; dst[1] = py; dst[2] = x.p[2];
+  }
+  if (o.t) o.t[row] = t;
+  if (o.R) {
+    double *dst = o.R + row * 9;
+#pragma unroll
+    for (int j = 0; j < 3; j++) {
+      double r0 = x.R[3 * j], r1 = x.R[3 * j + 1];
+      if (rz.on) {
+        dst[3 * j] = rz.c * r0 - rz.s * r1;
+        dst[3 * j + 1] = rz.s * r0 + rz.c * r1;
+      } else {
+        dst[3 * j] = r0;
+        dst[3 * j + 1] = r1;
+      }
+      dst[3 * j + 2] = x.R[3 * j + 2];
+    }
+  }
+}
+
+template <int NT, bool RETRACT>
+__global__ void __launch_bounds__(FK_THREADS, 2)
+fk_rk4_fp64_kernel(const RobotDev rb, const double *__restrict__ states, int state_size, int64_t n,
+                   int cap_pts, const irt_fk_outputs o, const int32_t *__restrict__ perm) {
+  extern __shared__ double smem[];
+  double *tab = smem;                                // [n_table][NT][6]
+  double *head = smem + (size_t)rb.n_table * NT * 6; // [4][NT][6]
+  for (int i = threadIdx.x; i < rb.n_table * NT * 6; i += blockDim.x) tab[i] = rb.table[i];
+  for (int i = threadIdx.x; i < 4 * NT * 6; i += blockDim.x) head[i] = rb.head[i];
+  __syncthreads();
+
+  const int64_t gi = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const bool in_range = gi < n;
+  const int64_t cfg = in_range ? (perm ? (int64_t)perm[gi] : gi) : 0;
+  const double *st = states + cfg * state_size;
+
+  double tau[NT];
+#pragma unroll
+  for (int j = 0; j < NT; j++) tau[j] = in_range ? st[j] : 0.0;
+  RotZ rz{1.0, 0.0, 0};
+  if (rb.enable_rotation) {
+    rz.on = 1;
+    sincos(in_range ? st[NT] : 0.0, &rz.s, &rz.c);
+  }
+  double s_start = 0.0;
+  if (RETRACT) s_start = in_range ? st[state_size - 1] : 0.0;
+  const double Kse[3] = {rb.Kse[0], rb.Kse[1], rb.Kse[2]};
+  const double Kbt[3] = {rb.Kbt[0], rb.Kbt[1], rb.Kbt[2]};
+
+  uint32_t flags = 0;
+  bool active = in_range;
+  if (RETRACT && !(s_start >= 0.0)) {  // s < 0 or NaN: outside the reference's state space
+    flags |= IRT_FLAG_BAD_STATE;
+    active = false;
+  }
+  if (s_start > rb.L) s_start = rb.L;  // TendonRobot.cpp:359
+
+  // number of nodes K: util::range's accumulation (vector_ops.h:67-75), bit-for-bit
+  int K = 0;
+  if (active) {
+    if (RETRACT) {
+      const double lim = rb.L - (rb.dL / 2);
+      for (double pacc = s_start; pacc <= lim; pacc += rb.dL) K++;
+      if (K > rb.Kfull) K = rb.Kfull;
+    } else {
+      K = rb.Kfull;
+    }
+  }
+  const bool degenerate = active && (s_start == rb.L);  // TendonRobot.cpp:361-372
+
+  FkState<NT> x;
+#pragma unroll
+  for (int i = 0; i < 3; i++) { x.p[i] = 0; x.v[i] = 0; x.u[i] = 0; }
+#pragma unroll
+  for (int i = 0; i < 9; i++) x.R[i] = 0;
+  x.R[0] = x.R[4] = x.R[8] = 1.0;
+  x.v[2] = 1.0;
+  x.Lb = 0;
+#pragma unroll
+  for (int j = 0; j < NT; j++) x.Li[j] = 0;
+
+  int iters = 0, nsteps = 0;
+  double u0[3] = {0, 0, 0}, v0[3] = {0, 0, 1};
+  double rt_local[NT * 6];
+  const bool run = active && !degenerate;
+  // L - dL/2 < s < L: the grid is the single point {s} (K == 0), nothing to integrate
+  const bool integ = run && K >= 1;
+
+  if (run) {
+    // ---- initial condition: solve_initial_bending.cpp:15-73 ------------------------------
+    const double *rt_s;
+    if (RETRACT) {
+      routing_eval<NT>(rb, s_start, rt_local);
+      rt_s = rt_local;
+    } else {
+      rt_s = head;
+    }
+    double v[3] = {0, 0, 1}, u[3] = {0, 0, 0};
+    for (iters = 0; iters < 1000; ++iters) {
+      double Ft[3] = {0, 0, 0}, Lt[3] = {0, 0, 0};
+#pragma unroll
+      for (int k = 0; k < NT; k++) {
+        const double rx = rt_s[6 * k], ry = rt_s[6 * k + 1], dx = rt_s[6 * k + 2], dy = rt_s[6 * k + 3];
+        double qx = (-u[2] * ry + dx) + v[0];
+        double qy = (u[2] * rx + dy) + v[1];
+        double qz = (-u[1] * rx + u[0] * ry) + v[2];
+        const double nrm = sqrt(qx * qx + qy * qy + qz * qz);
+        qx /= nrm; qy /= nrm; qz /= nrm;
+        Ft[0] -= tau[k] * qx; Ft[1] -= tau[k] * qy; Ft[2] -= tau[k] * qz;
+        // r^ q = r x q = (ry qz, -rx qz, rx qy - ry qx)
+        Lt[0] -= tau[k] * (ry * qz); Lt[1] -= tau[k] * (-rx * qz); Lt[2] -= tau[k] * (rx * qy - ry * qx);
+      }
+      const double n0 = Kse[0] * v[0], n1 = Kse[1] * v[1], n2 = Kse[2] * (v[2] - 1.0);
+      const double m0 = Kbt[0] * u[0], m1 = Kbt[1] * u[1], m2 = Kbt[2] * u[2];
+      const double residual =
+          sqrt(((n0 - Ft[0]) * (n0 - Ft[0]) + (n1 - Ft[1]) * (n1 - Ft[1]) + (n2 - Ft[2]) * (n2 - Ft[2])) +
+               ((m0 - Lt[0]) * (m0 - Lt[0]) + (m1 - Lt[1]) * (m1 - Lt[1]) + (m2 - Lt[2]) * (m2 - Lt[2])));
+      if (residual < rb.residual_threshold) break;
+      const double vn0 = rb.KseInv[0] * Ft[0], vn1 = rb.KseInv[1] * Ft[1], vn2 = rb.KseInv[2] * Ft[2] + 1.0;
+      const double un0 = rb.KbtInv[0] * Lt[0], un1 = rb.KbtInv[1] * Lt[1], un2 = rb.KbtInv[2] * Lt[2];
+      const double dv = sqrt((vn0 - v[0]) * (vn0 - v[0]) + (vn1 - v[1]) * (vn1 - v[1]) + (vn2 - v[2]) * (vn2 - v[2]));
+      const double du = sqrt((un0 - u[0]) * (un0 - u[0]) + (un1 - u[1]) * (un1 - u[1]) + (un2 - u[2]) * (un2 - u[2]));
+      const double nv = sqrt(v[0] * v[0] + v[1] * v[1] + v[2] * v[2]);
+      const double nu = sqrt(u[0] * u[0] + u[1] * u[1] + u[2] * u[2]);
+      if (dv < 1e-9 * nv && du < 1e-9 * nu) break;
+      v[0] = vn0; v[1] = vn1; v[2] = vn2;
+      u[0] = un0; u[1] = un1; u[2] = un2;
+    }
+#pragma unroll
+    for (int i = 0; i < 3; i++) { x.v[i] = v0[i] = v[i]; x.u[i] = u0[i] = u[i]; }
+
+    // ---- convergence flag: calc_point_forces at the base, R = I (TendonRobot.cpp:188-217) --
+    {
+      double Ft[3] = {0, 0, 0}, Lt[3] = {0, 0, 0};
+#pragma unroll
+      for (int k = 0; k < NT; k++) {
+        const double rx = rt_s[6 * k], ry = rt_s[6 * k + 1], dx = rt_s[6 * k + 2], dy = rt_s[6 * k + 3];
+        double qx = (-u[2] * ry + dx) + v[0];
+        double qy = (u[2] * rx + dy) + v[1];
+        double qz = (u[0] * ry - u[1] * rx) + v[2];
+        const double nrm = sqrt(qx * qx + qy * qy + qz * qz);
+        const double fx = -tau[k] * (qx / nrm), fy = -tau[k] * (qy / nrm), fz = -tau[k] * (qz / nrm);
+        Ft[0] += fx; Ft[1] += fy; Ft[2] += fz;
+        Lt[0] += ry * fz; Lt[1] += -rx * fz; Lt[2] += rx * fy - ry * fx;
+      }
+      const double e0 = Kse[0] * v[0] - Ft[0], e1 = Kse[1] * v[1] - Ft[1], e2 = Kse[2] * (v[2] - 1.0) - Ft[2];
+      const double g0 = Kbt[0] * u[0] - Lt[0], g1 = Kbt[1] * u[1] - Lt[1], g2 = Kbt[2] * u[2] - Lt[2];
+      const double resid = sqrt((e0 * e0 + e1 * e1 + e2 * e2) + (g0 * g0 + g1 * g1 + g2 * g2));
+      if (!(resid <= rb.residual_threshold)) flags |= IRT_FLAG_NONCONVERGED;
+    }
+  }
+
+  // ---- integrate_times(runge_kutta4) over the grid {s} U {node K-1 .. node 0} --------------
+  if (run) emit_node<NT>(o, cfg, cap_pts, 0, s_start, x, rz);
+  if (integ) {
+    // irregular first gap: s -> node K-1 in one or two steps (h = min(dL, t_next - t))
+    if (RETRACT) {
+      const double eps = 2.220446049250313e-16;
+      const double t1 = rb.node_t[K - 1];
+      double tc = s_start;
+      double h = fmin(rb.dL, t1 - tc);
+      double rt_mid[NT * 6];
+      routing_eval<NT>(rb, tc + 0.5 * h, rt_mid);
+      if (t1 - (tc + h) > eps) {
+        double rt_end[NT * 6];
+        routing_eval<NT>(rb, tc + h, rt_end);
+        rk4_step<NT>(x, tau, Kse, Kbt, h, rt_local, rt_mid, rt_end);
+        nsteps++;
+        tc += h;
+        h = fmin(rb.dL, t1 - tc);
+        routing_eval<NT>(rb, tc + 0.5 * h, rt_mid);
+        rk4_step<NT>(x, tau, Kse, Kbt, h, rt_end, rt_mid, tab + (size_t)(2 * (K - 1)) * NT * 6);
+        nsteps++;
+      } else {
+        rk4_step<NT>(x, tau, Kse, Kbt, h, rt_local, rt_mid, tab + (size_t)(2 * (K - 1)) * NT * 6);
+        nsteps++;
+      }
+    } else {
+      const double *end = tab + (size_t)(2 * (K - 1)) * NT * 6;
+      if (rb.n_head == 4) {
+        rk4_step<NT>(x, tau, Kse, Kbt, rb.head_h[0], head, head + NT * 6, head + 2 * NT * 6);
+        rk4_step<NT>(x, tau, Kse, Kbt, rb.head_h[1], head + 2 * NT * 6, head + 3 * NT * 6, end);
+        nsteps += 2;
+      } else {
+        rk4_step<NT>(x, tau, Kse, Kbt, rb.head_h[0], head, head + NT * 6, end);
+        nsteps++;
+      }
+    }
+    emit_node<NT>(o, cfg, cap_pts, 1, rb.node_t[K - 1], x, rz);
+  }
+  // regular steps node q -> node q-1, the warp walks the table in lock-step
+  {
+    int qtop = integ ? (K - 1) : 0;
+    int qmax = qtop;
+    if (RETRACT) qmax = __reduce_max_sync(0xffffffffu, qtop);
+    for (int q = qmax; q >= 1; q--) {
+      if (q <= qtop) {
+        const double *e0 = tab + (size_t)(2 * q) * NT * 6;
+        rk4_step<NT>(x, tau, Kse, Kbt, rb.dL, e0, e0 - NT * 6, e0 - 2 * NT * 6);
+        nsteps++;
+        emit_node<NT>(o, cfg, cap_pts, K - q + 1, rb.node_t[q - 1], x, rz);
+      }
+    }
+  }
+
+  if (!in_range) return;
+  int npts = 0;
+  if (degenerate) {
+    npts = 1;
+    emit_node<NT>(o, cfg, cap_pts, 0, s_start, x, rz);  // p = 0, R = I, v = e3, u = 0
+  } else if (run) {
+    npts = K + 1;
+  }
+  // length limits: is_within_length_limits(calc_dl(home.L_i, L_i)) -- TendonRobot.h:247-278
+  if (active) {
+    double sh = s_start < 0.0 ? 0.0 : s_start;  // home_shape clamps both ends
+    const double Lhome = degenerate ? 0.0 : (rb.L - sh);
+#pragma unroll
+    for (int j = 0; j < NT; j++) {
+      const double dl = Lhome * rb.home_factor[j] - x.Li[j];
+      if (dl < rb.min_length[j] || rb.max_length[j] < dl) flags |= IRT_FLAG_LENGTH_LIMIT;
+    }
+  }
+  if (o.npts) o.npts[cfg] = npts;
+  if (o.L) o.L[cfg] = x.Lb;
+  if (o.L_i) {
+#pragma unroll
+    for (int j = 0; j < NT; j++) o.L_i[cfg * NT + j] = x.Li[j];
+  }
+  if (o.tip) {
+    double px = x.p[0], py = x.p[1];
+    if (rz.on) { px = rz.c * x.p[0] - rz.s * x.p[1]; py = rz.s * x.p[0] + rz.c * x.p[1]; }
+    o.tip[cfg * 3] = px; o.tip[cfg * 3 + 1] = py; o.tip[cfg * 3 + 2] = x.p[2];
+  }
+  if (o.uv) {
+    double *d = o.uv + cfg * 12;
+#pragma unroll
+    for (int i = 0; i < 3; i++) { d[i] = u0[i]; d[3 + i] = x.u[i]; d[6 + i] = v0[i]; d[9 + i] = x.v[i]; }
+  }
+  if (o.flags) o.flags[cfg] = flags;
+  if (o.iters) o.iters[cfg] = iters;
+  if (o.nsteps) o.nsteps[cfg] = nsteps;
+}
+
+// ---- bucket configurations by node count (descending) so warps stay converged --------------
+__global__ void fk_count_nodes_kernel(const RobotDev rb, const double *__restrict__ states,
+                                      int state_size, int64_t n, int32_t *__restrict__ keys,
+                                      int32_t *__restrict__ hist) {
+  extern __shared__ int32_t sh[];
+  const int nb = rb.Kfull + 1;
+  for (int i = threadIdx.x; i < nb; i += blockDim.x) sh[i] = 0;
+  __syncthreads();
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) {
+    double s = states[i * state_size + state_size - 1];
+    int K = 0;
+    if (s >= 0.0 && s < rb.L) {
+      const double lim = rb.L - (rb.dL / 2);
+      for (double p = s; p <= lim; p += rb.dL) K++;
+      if (K > rb.Kfull) K = rb.Kfull;
+    }
+    keys[i] = K;
+    atomicAdd(&sh[K], 1);
+  }
+  __syncthreads();
+  for (int k = threadIdx.x; k < nb; k += blockDim.x)
+    if (sh[k]) atomicAdd(&hist[k], sh[k]);
+}
+
+__global__ void fk_bucket_scan_kernel(int32_t *hist, int nb) {
+  // exclusive scan in DESCENDING key order; hist[k] becomes the first slot of bucket k
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    int32_t acc = 0;
+    for (int k = nb - 1; k >= 0; k--) {
+      int32_t c = hist[k];
+      hist[k] = acc;
+      acc += c;
+    }
+  }
+}
+
+__global__ void fk_bucket_scatter_kernel(const int32_t *__restrict__ keys, int64_t n,
+                                         int32_t *__restrict__ cursor, int32_t *__restrict__ perm) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) {
+    int32_t pos = atomicAdd(&cursor[keys[i]], 1);
+    perm[pos] = (int32_t)i;
+  }
+}
+
+template <int NT>
+int launch_nt(irt_ctx *ctx, const irt_robot *rb, const double *d_states, int64_t n, int cap_pts,
+              const irt_fk_outputs &o, const int32_t *d_perm, cudaStream_t st) {
+  const RobotDev &d = rb->dev;
+  size_t smem = ((size_t)d.n_table + 4) * NT * 6 * sizeof(double);
+  const int64_t blocks = (n + FK_THREADS - 1) / FK_THREADS;
+  if (d.enable_retraction) {
+    auto k = fk_rk4_fp64_kernel<NT, true>;
+    IRT_CUDA(ctx, cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k<<<(unsigned)blocks, FK_THREADS, smem, st>>>(d, d_states, rb->state_size, n, cap_pts, o, d_perm);
+  } else {
+    auto k = fk_rk4_fp64_kernel<NT, false>;
+    IRT_CUDA(ctx, cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k<<<(unsigned)blocks, FK_THREADS, smem, st>>>(d, d_states, rb->state_size, n, cap_pts, o, d_perm);
+  }
+  IRT_LAUNCHED(ctx);
+  IRT_CUDA(ctx, cudaGetLastError());
+  return IRT_OK;
+}
+
+}  // namespace
+
+// d_perm == nullptr: when retraction is enabled a bucket permutation is built in ctx scratch.
+int fk_launch(irt_ctx *ctx, const irt_robot *rb, const double *d_states, int64_t n, int cap_pts,
+              const irt_fk_outputs &o, const int32_t *d_perm, cudaStream_t st) {
+  if (n <= 0) return IRT_OK;
+  if (n > 0x7fffffffLL) return irt_fail(ctx, IRT_ERR_INVALID_ARGUMENT, "batch too large");
+  const RobotDev &d = rb->dev;
+  size_t smem = ((size_t)d.n_table + 4) * d.n_tendons * 6 * sizeof(double);
+  if (smem > 200 * 1024)
+    return irt_fail(ctx, IRT_ERR_CAPACITY, "routing table (%zu B) exceeds shared memory", smem);
+  if (d.enable_retraction && !d_perm) {
+    const int nb = d.Kfull + 1;
+    size_t bytes = (size_t)n * 4 * 2 + (size_t)nb * 4 + 256;
+    char *scr = (char *)ctx_scratch(ctx, bytes);
+    if (!scr) return irt_fail(ctx, IRT_ERR_CUDA, "scratch alloc of %zu bytes failed", bytes);
+    int32_t *keys = (int32_t *)scr;
+    int32_t *perm = keys + n;
+    int32_t *hist = perm + n;
+    IRT_CUDA(ctx, cudaMemsetAsync(hist, 0, (size_t)nb * 4, st));
+    const int T = 256;
+    const unsigned B = (unsigned)((n + T - 1) / T);
+    fk_count_nodes_kernel<<<B, T, nb * sizeof(int32_t), st>>>(d, d_states, rb->state_size, n, keys, hist);
+    IRT_LAUNCHED(ctx);
+    fk_bucket_scan_kernel<<<1, 32, 0, st>>>(hist, nb);
+    IRT_LAUNCHED(ctx);
+    fk_bucket_scatter_kernel<<<B, T, 0, st>>>(keys, n, hist, perm);
+    IRT_LAUNCHED(ctx);
+    IRT_CUDA(ctx, cudaGetLastError());
+    d_perm = perm;
+  }
+  switch (d.n_tendons) {
+    case 1: return launch_nt<1>(ctx, rb, d_states, n, cap_pts, o, d_perm, st);
+    case 2: return launch_nt<2>(ctx, rb, d_states, n, cap_pts, o, d_perm, st);
+    case 3: return launch_nt<3>(ctx, rb, d_states, n, cap_pts, o, d_perm, st);
+    case 4: return launch_nt<4>(ctx, rb, d_states, n, cap_pts, o, d_perm, st);
+    case 5: return launch_nt<5>(ctx, rb, d_states, n, cap_pts, o, d_perm, st);
+    case 6: return launch_nt<6>(ctx, rb, d_states, n, cap_pts, o, d_perm, st);
+    case 8: return launch_nt<8>(ctx, rb, d_states, n, cap_pts, o, d_perm, st);
+    default:
+      return irt_fail(ctx, IRT_ERR_UNSUPPORTED,
+                      "no fk kernel instantiated for %d tendons (have 1-6, 8)", d.n_tendons);
+  }
+}

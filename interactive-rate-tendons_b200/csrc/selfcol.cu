@@ -1,0 +1,188 @@
+// selfcol.cu -- validity epilogue of K1: collision::collides_self(CapsuleSequence)
+// (collision/collision.cpp:6-46) with closest_st_segment (collision_primitives.cpp:10-102)
+// and the capsule/sphere tests of collision.hxx:65-68,102-108.
+//
+// One warp per shape.  The O(P^2) capsule-pair loop of the reference is pruned by an exact
+// (conservative) two-level test: chunks of 8 consecutive capsules get a bounding sphere; only
+// chunk pairs whose spheres come within 2r (+margin) have their 64 capsule pairs examined
+// with the reference's arithmetic.  The verdict (any pair collides) is unchanged.
+#include "common.cuh"
+
+namespace {
+
+constexpr int SC_WARPS = 4;
+constexpr int SC_CHUNK = 8;
+
+struct P3 {
+  double x, y, z;
+};
+__device__ __forceinline__ P3 sub3(const P3 &a, const P3 &b) { return {a.x - b.x, a.y - b.y, a.z - b.z}; }
+__device__ __forceinline__ double dot3(const P3 &a, const P3 &b) { return (a.x * b.x + a.y * b.y) + a.z * b.z; }
+__device__ __forceinline__ double bound01(double t) { return fmax(0.0, fmin(1.0, t)); }
+
+// closest_st_segment -- collision/collision_primitives.cpp:10-102
+__device__ void closest_st(const P3 &A, const P3 &B, const P3 &C, const P3 &D, double &s, double &t) {
+  const double eps = 2.220446049250313e-16;
+  const double eps2 = eps * eps;
+  const P3 AB = sub3(B, A), CD = sub3(D, C);
+  const double a = dot3(AB, AB), c = dot3(CD, CD);
+  if (a <= eps2) {
+    s = 0.0;
+    t = (c <= eps2) ? 0.0 : bound01(dot3(CD, sub3(A, C)) / c);
+    return;
+  }
+  if (c <= eps2) {
+    s = bound01(dot3(AB, sub3(C, A)) / a);
+    t = 0.0;
+    return;
+  }
+  const P3 AC = sub3(C, A);
+  const double b = dot3(AB, CD), d = dot3(AC, AB), e = dot3(AC, CD);
+  const double denom = fmax(0.0, a * c - b * b);
+  if (denom <= eps2) {
+    double tt = dot3(CD, sub3(A, C)) / c;
+    if (0.0 <= tt && tt <= 1.0) { s = 0.0; t = tt; return; }
+    tt = dot3(CD, sub3(B, C)) / c;
+    if (0.0 <= tt && tt <= 1.0) { s = 1.0; t = tt; return; }
+    double ss = dot3(AB, sub3(C, A)) / a;
+    if (0.0 <= ss && ss <= 1.0) { s = ss; t = 0.0; return; }
+    const P3 AD = sub3(D, A), BC = sub3(C, B), BD = sub3(D, B);
+    const double ac2 = dot3(AC, AC), ad2 = dot3(AD, AD), bc2 = dot3(BC, BC), bd2 = dot3(BD, BD);
+    if (ac2 <= ad2 && ac2 <= bc2 && ac2 <= bd2) { s = 0.0; t = 0.0; return; }
+    if (ad2 <= bc2 && ad2 <= bd2) { s = 0.0; t = 1.0; return; }
+    if (bc2 <= bd2) { s = 1.0; t = 0.0; return; }
+    s = 1.0; t = 1.0;
+    return;
+  }
+  const double ss = (c * d - b * e) / denom;
+  const double tt = (b * d - a * e) / denom;
+  if (0.0 <= tt && tt <= 1.0) { s = bound01(ss); t = tt; return; }
+  if (tt < 0.0) { s = bound01(-c / a); t = 0.0; return; }
+  s = bound01((b - c) / a);
+  t = 1.0;
+}
+
+// collides(Capsule, Capsule) -- collision/collision.hxx:102-108
+__device__ bool capsules_collide(const P3 &a0, const P3 &a1, const P3 &b0, const P3 &b1, double rr) {
+  double s, t;
+  closest_st(a0, a1, b0, b1, s, t);
+  const P3 dA = sub3(a1, a0), dB = sub3(b1, b0);
+  const P3 c1 = {a0.x + dA.x * s, a0.y + dA.y * s, a0.z + dA.z * s};
+  const P3 c2 = {b0.x + dB.x * t, b0.y + dB.y * t, b0.z + dB.z * t};
+  const P3 diff = sub3(c1, c2);
+  return dot3(diff, diff) <= (rr * rr);
+}
+
+__global__ void __launch_bounds__(SC_WARPS * 32)
+self_collision_kernel(const double *__restrict__ p, const int32_t *__restrict__ npts, int64_t n,
+                      int cap_pts, double r, uint32_t *__restrict__ flags) {
+  extern __shared__ double sm[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // per warp: xyz[cap*3], acc[cap], chunk centre xyz + radius [4 * nchunk_max]
+  const int nchunk_max = (cap_pts + SC_CHUNK - 1) / SC_CHUNK;
+  double *base = sm + (size_t)warp * ((size_t)cap_pts * 4 + (size_t)nchunk_max * 4);
+  double *px = base, *acc = base + (size_t)cap_pts * 3, *ch = acc + cap_pts;
+  const double dist_to_consider = 3.0 * r;
+  const double rr = r + r;
+
+  for (int64_t shape = (int64_t)blockIdx.x * SC_WARPS + warp; shape < n;
+       shape += (int64_t)gridDim.x * SC_WARPS) {
+    const int N = npts[shape];
+    __syncwarp();
+    if (N <= 2) continue;  // collision.cpp:14
+    const double *src = p + shape * (int64_t)cap_pts * 3;
+    for (int i = lane; i < N * 3; i += 32) px[i] = src[i];
+    __syncwarp();
+    // accumulated L2 distances, summed in the reference's order (collision.cpp:22-29)
+    for (int i = lane; i < N; i += 32) {
+      double len = 0.0;
+      if (i > 0) {
+        const double dx = px[3 * i] - px[3 * i - 3], dy = px[3 * i + 1] - px[3 * i - 2],
+                     dz = px[3 * i + 2] - px[3 * i - 1];
+        len = sqrt((dx * dx + dy * dy) + dz * dz);
+      }
+      acc[i] = len;
+    }
+    __syncwarp();
+    if (lane == 0) {
+      double dsum = 0.0;
+      for (int i = 0; i < N; i++) { dsum += acc[i]; acc[i] = dsum; }
+    }
+    __syncwarp();
+    // chunk bounding spheres over capsules [c*8, c*8+8) i.e. points [c*8, min(c*8+8, N-1)]
+    const int ncap = N - 1;
+    const int nchunk = (ncap + SC_CHUNK - 1) / SC_CHUNK;
+    for (int c = lane; c < nchunk; c += 32) {
+      const int i0 = c * SC_CHUNK, i1 = min(i0 + SC_CHUNK, ncap);  // points i0..i1 inclusive
+      const int im = (i0 + i1) >> 1;
+      const double cx = px[3 * im], cy = px[3 * im + 1], cz = px[3 * im + 2];
+      double rad2 = 0.0;
+      for (int i = i0; i <= i1; i++) {
+        const double dx = px[3 * i] - cx, dy = px[3 * i + 1] - cy, dz = px[3 * i + 2] - cz;
+        rad2 = fmax(rad2, (dx * dx + dy * dy) + dz * dz);
+      }
+      ch[4 * c] = cx; ch[4 * c + 1] = cy; ch[4 * c + 2] = cz; ch[4 * c + 3] = sqrt(rad2);
+    }
+    __syncwarp();
+    bool hit = false;
+    const int npairs = nchunk * nchunk;
+    for (int base_pair = 0; base_pair < npairs && !hit; base_pair += 32) {
+      const int pair = base_pair + lane;
+      bool near = false;
+      int ca = 0, cb = 0;
+      if (pair < npairs) {
+        ca = pair / nchunk; cb = pair - ca * nchunk;
+        if (cb >= ca) {
+          const double dx = ch[4 * ca] - ch[4 * cb], dy = ch[4 * ca + 1] - ch[4 * cb + 1],
+                       dz = ch[4 * ca + 2] - ch[4 * cb + 2];
+          const double reach = (ch[4 * ca + 3] + ch[4 * cb + 3] + rr) * (1.0 + 1e-9) + 1e-12;
+          near = ((dx * dx + dy * dy) + dz * dz) <= reach * reach;
+        }
+      }
+      unsigned m = __ballot_sync(0xffffffffu, near);
+      while (m && !hit) {
+        const int src_lane = __ffs(m) - 1;
+        m &= m - 1;
+        const int a0 = __shfl_sync(0xffffffffu, ca, src_lane) * SC_CHUNK;
+        const int b0 = __shfl_sync(0xffffffffu, cb, src_lane) * SC_CHUNK;
+        bool h = false;
+        for (int k = lane; k < SC_CHUNK * SC_CHUNK; k += 32) {
+          const int a = a0 + (k >> 3), b = b0 + (k & 7);
+          // loop bounds of collision.cpp:35-36: a < N-3, a+2 <= b < N-1
+          if (a < N - 3 && b >= a + 2 && b < N - 1) {
+            if (!(acc[b] - acc[a + 1] < dist_to_consider)) {
+              const P3 A0 = {px[3 * a], px[3 * a + 1], px[3 * a + 2]};
+              const P3 A1 = {px[3 * a + 3], px[3 * a + 4], px[3 * a + 5]};
+              const P3 B0 = {px[3 * b], px[3 * b + 1], px[3 * b + 2]};
+              const P3 B1 = {px[3 * b + 3], px[3 * b + 4], px[3 * b + 5]};
+              if (capsules_collide(A0, A1, B0, B1, rr)) h = true;
+            }
+          }
+        }
+        hit = __any_sync(0xffffffffu, h);
+      }
+    }
+    if (hit && lane == 0) flags[shape] |= IRT_FLAG_SELF_COLLISION;
+  }
+}
+
+}  // namespace
+
+int self_collision_launch(irt_ctx *ctx, const irt_robot *rb, const double *d_p,
+                          const int32_t *d_npts, int64_t n, int cap_pts, uint32_t *d_flags,
+                          cudaStream_t st) {
+  if (n <= 0) return IRT_OK;
+  const int nchunk_max = (cap_pts + SC_CHUNK - 1) / SC_CHUNK;
+  size_t smem = (size_t)SC_WARPS * ((size_t)cap_pts * 4 + (size_t)nchunk_max * 4) * sizeof(double);
+  if (smem > 200 * 1024) return irt_fail(ctx, IRT_ERR_CAPACITY, "cap_pts=%d too large", cap_pts);
+  IRT_CUDA(ctx, cudaFuncSetAttribute(self_collision_kernel,
+                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int64_t blocks = (n + SC_WARPS - 1) / SC_WARPS;
+  const int64_t max_blocks = (int64_t)ctx->sm_count * 16;
+  if (blocks > max_blocks) blocks = max_blocks;
+  self_collision_kernel<<<(unsigned)blocks, SC_WARPS * 32, smem, st>>>(d_p, d_npts, n, cap_pts,
+                                                                      rb->dev.r, d_flags);
+  IRT_LAUNCHED(ctx);
+  IRT_CUDA(ctx, cudaGetLastError());
+  return IRT_OK;
+}

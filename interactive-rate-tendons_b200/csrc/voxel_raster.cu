@@ -1,0 +1,878 @@
+// voxel_raster.cu -- K2 `swept_voxel_raster`: backbone polyline -> sparse voxel block sets,
+// for roadmap vertices (one FK sample per set) and edges (adaptive swept volume).
+//
+// Replaces, behind the same results:
+//   VoxelOctree::add_line / add_piecewise_line      collision/VoxelOctree.cpp:325-432
+//   segment_aabox_intersect                         collision/collision_primitives.h:62-85
+//   VoxelBackboneValidityChecker::voxelize_impl     motion-planning/VoxelBackboneValidityChecker.h:49-57
+//   VoxelEnvironment::voxelize_valid_backbone_motion motion-planning/VoxelEnvironment.cpp:207-444
+//   VoxelBackboneMotionValidator::generic_voxelize  motion-planning/VoxelBackboneMotionValidator.cpp:41-74
+//
+// B200-first structure (not a translation of the reference's per-edge LIFO loop):
+//   * the bisection of ALL edges of a chunk runs level-synchronously: every round interpolates the
+//     midpoints of all open intervals, runs ONE batched K1 launch (+ validity epilogue) over them,
+//     then one warp per interval evaluates should_subdivide (VoxelEnvironment.cpp:304-341).  The
+//     sample set this produces below the first invalid t equals the reference's depth-first
+//     order exactly (DESIGN.md "level-synchronous bisection" has the argument).
+//   * rasterisation: one warp per set; lanes take polyline segments, run the reference's voxel
+//     traversal literally (same operation order, this file is compiled with -fmad=false so no
+//     contraction changes a cell index) and OR cell bits into a shared-memory hash keyed by the
+//     Morton block key; the table is then rank-sorted by key, which is the reference's
+//     visit_leaves order, and written as {u32 key, u64 bits} records (8 consecutive keys = one
+//     512-bit 2x2x2 super-block).  Two passes (count, exclusive scan, emit) give an exact CSR
+//     without per-set capacity slots.
+#include <cmath>
+#include <cstring>
+#include <vector>
+
+#include "common.cuh"
+
+namespace {
+
+constexpr int RS_WARPS = 4;
+constexpr int RS_HASH = 1024;        // hash entries per warp (power of two)
+constexpr uint32_t RS_EMPTY = 0xffffffffu;
+constexpr int RS_WARP_BYTES = RS_HASH * 18 + 16;
+constexpr int RS_SMEM = RS_WARPS * RS_WARP_BYTES;
+constexpr uint32_t INVALID_MASK = IRT_FLAG_NONCONVERGED | IRT_FLAG_LENGTH_LIMIT |
+                                  IRT_FLAG_SELF_COLLISION | IRT_FLAG_BAD_STATE;
+
+struct D3 {
+  double x, y, z;
+};
+
+__device__ __forceinline__ uint32_t spread3(uint32_t x) {
+  x = (x | (x << 16)) & 0x030000FFu;
+  x = (x | (x << 8)) & 0x0300F00Fu;
+  x = (x | (x << 4)) & 0x030C30C3u;
+  x = (x | (x << 2)) & 0x09249249u;
+  return x;
+}
+// x is the most significant bit of each 3-bit group: child index 4*x + 2*y + z (TreeNode.h:66-68)
+__device__ __forceinline__ uint32_t morton_key(uint32_t bx, uint32_t by, uint32_t bz) {
+  return (spread3(bx) << 2) | (spread3(by) << 1) | spread3(bz);
+}
+
+__device__ __forceinline__ D3 rotate_pt(const GridDev &g, const double *p) {
+  if (g.identity_rot) return {p[0], p[1], p[2]};
+  // Eigen 3x3 * 3x1: (m0*b0 + m1*b1) + m2*b2
+  return {(g.inv_rot[0] * p[0] + g.inv_rot[1] * p[1]) + g.inv_rot[2] * p[2],
+          (g.inv_rot[3] * p[0] + g.inv_rot[4] * p[1]) + g.inv_rot[5] * p[2],
+          (g.inv_rot[6] * p[0] + g.inv_rot[7] * p[1]) + g.inv_rot[8] * p[2]};
+}
+
+struct WarpHash {
+  uint32_t *keys;   // [RS_HASH]
+  unsigned long long *bits;  // [RS_HASH]
+  uint32_t *overflow;
+};
+
+__device__ __forceinline__ void hash_insert(const WarpHash &h, uint32_t key, unsigned long long mask) {
+  uint32_t slot = (key * 2654435761u) >> (32 - 10);  // RS_HASH == 1 << 10
+  for (int probe = 0; probe < RS_HASH; probe++) {
+    const uint32_t old = atomicCAS(&h.keys[slot], RS_EMPTY, key);
+    if (old == RS_EMPTY || old == key) {
+      atomicOr(&h.bits[slot], mask);
+      return;
+    }
+    slot = (slot + 1) & (RS_HASH - 1);
+  }
+  *h.overflow = 1u;
+}
+
+// VoxelOctree::set_cell(ix,iy,iz,true) -- collision/VoxelOctree.cpp:262-272,1501-1503
+__device__ __forceinline__ void set_cell(const WarpHash &h, int ix, int iy, int iz) {
+  const uint32_t key = morton_key((uint32_t)ix >> 2, (uint32_t)iy >> 2, (uint32_t)iz >> 2);
+  const unsigned long long mask = 1ull << ((ix & 3) * 16 + (iy & 3) * 4 + (iz & 3));
+  hash_insert(h, key, mask);
+}
+
+// collision/collision_primitives.h:62-85, literal operation order
+__device__ bool segment_aabox_intersect(const D3 &A, const D3 &B, const D3 &C, const D3 &D) {
+  const D3 AB = {B.x - A.x, B.y - A.y, B.z - A.z};
+  const double len = sqrt((AB.x * AB.x + AB.y * AB.y) + AB.z * AB.z) / 2;
+  const double l2 = 2 * len;
+  const D3 U = {AB.x / l2, AB.y / l2, AB.z / l2};
+  const D3 Uabs = {fabs(U.x), fabs(U.y), fabs(U.z)};
+  const D3 P = {(A.x + B.x) / 2 - (D.x + C.x) / 2, (A.y + B.y) / 2 - (D.y + C.y) / 2,
+                (A.z + B.z) / 2 - (D.z + C.z) / 2};
+  const D3 ext = {fabs(D.x - C.x) / 2, fabs(D.y - C.y) / 2, fabs(D.z - C.z) / 2};
+  const D3 UxP = {fabs(U.y * P.z - U.z * P.y), fabs(U.z * P.x - U.x * P.z), fabs(U.x * P.y - U.y * P.x)};
+  const D3 Pabs = {fabs(P.x), fabs(P.y), fabs(P.z)};
+  const bool separated = Pabs.x > ext.x + len * Uabs.x || Pabs.y > ext.y + len * Uabs.y ||
+                         Pabs.z > ext.z + len * Uabs.z ||
+                         UxP.x > ext.y * Uabs.z + ext.z * Uabs.y ||
+                         UxP.y > ext.z * Uabs.x + ext.x * Uabs.z ||
+                         UxP.z > ext.x * Uabs.y + ext.y * Uabs.x;
+  return !separated;
+}
+
+// VoxelOctree::add_line -- collision/VoxelOctree.cpp:325-426, reproduced literally including the
+// "voxel index times metric cell size" initial error (:371-373) and the overshoot past B (:423-424).
+__device__ void add_line(const GridDev &g, const WarpHash &h, const D3 &a, const D3 &b) {
+  const D3 ll = {g.lo[0], g.lo[1], g.lo[2]}, ur = {g.hi[0], g.hi[1], g.hi[2]};
+  if (!segment_aabox_intersect(a, b, ll, ur)) return;
+  const D3 A = {(a.x - ll.x) * g.inv_d[0], (a.y - ll.y) * g.inv_d[1], (a.z - ll.z) * g.inv_d[2]};
+  const D3 B = {(b.x - ll.x) * g.inv_d[0], (b.y - ll.y) * g.inv_d[1], (b.z - ll.z) * g.inv_d[2]};
+  const int Axi = (int)A.x - (A.x < 0), Ayi = (int)A.y - (A.y < 0), Azi = (int)A.z - (A.z < 0);
+  const int Bxi = (int)B.x - (B.x < 0), Byi = (int)B.y - (B.y < 0), Bzi = (int)B.z - (B.z < 0);
+  const int N = g.Ng;
+#define IDX_IN(v) (0 <= (v) && (v) < N)
+#define VOX_IN(x, y, z) (IDX_IN(x) && IDX_IN(y) && IDX_IN(z))
+  bool entered = VOX_IN(Axi, Ayi, Azi);
+  if (entered) set_cell(h, Axi, Ayi, Azi);
+  if (VOX_IN(Bxi, Byi, Bzi)) set_cell(h, Bxi, Byi, Bzi);
+  D3 U = {B.x - A.x, B.y - A.y, B.z - A.z};
+  {
+    const double z = (U.x * U.x + U.y * U.y) + U.z * U.z;  // Eigen normalized()
+    if (z > 0.0) {
+      const double n = sqrt(z);
+      U.x /= n; U.y /= n; U.z /= n;
+    }
+  }
+  const int step_x = 1 - 2 * (U.x < 0), step_y = 1 - 2 * (U.y < 0), step_z = 1 - 2 * (U.z < 0);
+  const double ex = fabs(A.x - (Axi + step_x) * g.d[0]);
+  const double ey = fabs(A.y - (Ayi + step_y) * g.d[1]);
+  const double ez = fabs(A.z - (Azi + step_z) * g.d[2]);
+  const double ux = fabs(U.x), uy = fabs(U.y), uz = fabs(U.z);
+  const double threshold = 1e-10;
+  const double tx_delta = (ux > threshold) ? 1 / ux : 1 / threshold;
+  const double ty_delta = (uy > threshold) ? 1 / uy : 1 / threshold;
+  const double tz_delta = (uz > threshold) ? 1 / uz : 1 / threshold;
+  double tx = fabs(ex * tx_delta), ty = fabs(ey * ty_delta), tz = fabs(ez * tz_delta);
+  int xi = Axi, yi = Ayi, zi = Azi;
+  while (step_x * (Bxi - xi) >= 0 && step_y * (Byi - yi) >= 0 && step_z * (Bzi - zi) >= 0) {
+    const bool tx_is_min = (tx < ty) && (tx < tz);
+    const bool ty_is_min = !(tx < ty) && (ty < tz);
+    if (tx_is_min) {
+      xi += step_x;
+      if (entered && !IDX_IN(xi)) break;
+      tx += tx_delta;
+    } else if (ty_is_min) {
+      yi += step_y;
+      if (entered && !IDX_IN(yi)) break;
+      ty += ty_delta;
+    } else {
+      zi += step_z;
+      if (entered && !IDX_IN(zi)) break;
+      tz += tz_delta;
+    }
+    if (!entered && VOX_IN(xi, yi, zi)) entered = true;
+    if (entered) set_cell(h, xi, yi, zi);
+  }
+#undef IDX_IN
+#undef VOX_IN
+}
+
+// One warp per set.  A set is a linked list of FK samples (set_head / sample_next); a sample is
+// included iff t < tlimit[set] (edges) -- vertices have a single sample and no limit.
+// EMIT=false: counts[set] = #occupied leaf blocks, optional t_last[set].
+// EMIT=true : writes keys/bits at offsets[set], key-sorted.
+template <bool EMIT>
+__global__ void __launch_bounds__(RS_WARPS * 32)
+swept_voxel_raster_kernel(const GridDev g, const double *__restrict__ pts,
+                          const int32_t *__restrict__ npts, int cap_pts,
+                          const int32_t *__restrict__ set_head, const int32_t *__restrict__ sample_next,
+                          const double *__restrict__ sample_t, const double *__restrict__ tlimit,
+                          int64_t nsets, uint32_t *__restrict__ counts, double *__restrict__ t_last,
+                          int32_t *__restrict__ nsamples, const uint64_t *__restrict__ offsets,
+                          uint32_t *__restrict__ out_keys, uint64_t *__restrict__ out_bits,
+                          uint32_t *__restrict__ set_flags) {
+  extern __shared__ unsigned long long rs_smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // per warp: bits u64[H] | keys u32[H] | dense keys u32[H] | dense slots u16[H] | overflow
+  unsigned char *wbase = reinterpret_cast<unsigned char *>(rs_smem) + (size_t)warp * RS_WARP_BYTES;
+  WarpHash h;
+  h.bits = reinterpret_cast<unsigned long long *>(wbase);
+  h.keys = reinterpret_cast<uint32_t *>(wbase + RS_HASH * 8);
+  uint32_t *dk = reinterpret_cast<uint32_t *>(wbase + RS_HASH * 12);
+  uint16_t *ds = reinterpret_cast<uint16_t *>(wbase + RS_HASH * 16);
+  h.overflow = reinterpret_cast<uint32_t *>(wbase + RS_HASH * 18);
+
+  for (int64_t set = (int64_t)blockIdx.x * RS_WARPS + warp; set < nsets;
+       set += (int64_t)gridDim.x * RS_WARPS) {
+    for (int i = lane; i < RS_HASH; i += 32) { h.keys[i] = RS_EMPTY; h.bits[i] = 0ull; }
+    if (lane == 0) *h.overflow = 0u;
+    __syncwarp();
+    const double lim = tlimit ? tlimit[set] : 0.0;
+    double tl = 0.0;
+    int ns = 0;
+    for (int smp = set_head[set]; smp >= 0; smp = sample_next ? sample_next[smp] : -1) {
+      ns++;
+      if (tlimit) {
+        const double t = sample_t[smp];
+        if (!(t < lim)) continue;  // VoxelEnvironment.cpp:409
+        if (tl < t) tl = t;        // :419-422 last valid t
+      }
+      const int P = npts[smp];
+      const double *sp = pts + (int64_t)smp * cap_pts * 3;
+      for (int i = 1 + lane; i < P; i += 32) {  // add_piecewise_line: segments (i-1, i)
+        const D3 a = rotate_pt(g, sp + 3 * (i - 1));
+        const D3 b = rotate_pt(g, sp + 3 * i);
+        add_line(g, h, a, b);
+      }
+    }
+    __syncwarp();
+    // compact the occupied entries (ballot prefix), then rank-sort them by key
+    int cnt = 0;
+    for (int j0 = 0; j0 < RS_HASH; j0 += 32) {
+      const uint32_t k = h.keys[j0 + lane];
+      const unsigned m = __ballot_sync(0xffffffffu, k != RS_EMPTY);
+      if (EMIT && k != RS_EMPTY) {
+        const int pos = cnt + __popc(m & ((1u << lane) - 1u));
+        dk[pos] = k;
+        ds[pos] = (uint16_t)(j0 + lane);
+      }
+      cnt += __popc(m);
+    }
+    __syncwarp();
+    if (!EMIT) {
+      if (lane == 0) {
+        counts[set] = (uint32_t)cnt;
+        if (t_last) t_last[set] = tl;
+        if (nsamples) nsamples[set] = ns;
+        if (*h.overflow && set_flags) set_flags[set] |= IRT_FLAG_CAPACITY;
+      }
+    } else {
+      const uint64_t base = offsets[set];
+      for (int i = lane; i < cnt; i += 32) {
+        const uint32_t k = dk[i];
+        int rank = 0;
+        for (int j = 0; j < cnt; j++) rank += (dk[j] < k);
+        out_keys[base + rank] = k;
+        out_bits[base + rank] = h.bits[ds[i]];
+      }
+    }
+    __syncwarp();
+  }
+}
+
+// ---- exclusive scan: uint32 counts -> uint64 offsets (n+1 entries) ------------------------
+constexpr int SCAN_T = 256, SCAN_ITEMS = 8, SCAN_TILE = SCAN_T * SCAN_ITEMS;
+
+__global__ void scan_tile_sums_kernel(const uint32_t *__restrict__ in, int64_t n,
+                                      uint64_t *__restrict__ tile_sums) {
+  __shared__ uint64_t sh[SCAN_T / 32];
+  const int64_t base = (int64_t)blockIdx.x * SCAN_TILE;
+  uint64_t s = 0;
+  for (int k = 0; k < SCAN_ITEMS; k++) {
+    const int64_t i = base + (int64_t)k * SCAN_T + threadIdx.x;
+    if (i < n) s += in[i];
+  }
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    uint64_t t = 0;
+    for (int w = 0; w < SCAN_T / 32; w++) t += sh[w];
+    tile_sums[blockIdx.x] = t;
+  }
+}
+
+__global__ void scan_tile_offsets_kernel(uint64_t *tile_sums, int64_t ntiles, uint64_t *total) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    uint64_t acc = 0;
+    for (int64_t i = 0; i < ntiles; i++) {
+      const uint64_t c = tile_sums[i];
+      tile_sums[i] = acc;
+      acc += c;
+    }
+    *total = acc;
+  }
+}
+
+__global__ void scan_apply_kernel(const uint32_t *__restrict__ in, int64_t n,
+                                  const uint64_t *__restrict__ tile_sums,
+                                  const uint64_t *__restrict__ total, uint64_t *__restrict__ out) {
+  // thread t owns SCAN_ITEMS consecutive items of the tile
+  __shared__ uint64_t sh[SCAN_T];
+  const int64_t base = (int64_t)blockIdx.x * SCAN_TILE + (int64_t)threadIdx.x * SCAN_ITEMS;
+  uint32_t v[SCAN_ITEMS];
+  uint64_t s = 0;
+  for (int k = 0; k < SCAN_ITEMS; k++) {
+    v[k] = (base + k < n) ? in[base + k] : 0u;
+    s += v[k];
+  }
+  sh[threadIdx.x] = s;
+  __syncthreads();
+  for (int o = 1; o < SCAN_T; o <<= 1) {  // Hillis-Steele inclusive scan of the thread sums
+    uint64_t add = (threadIdx.x >= o) ? sh[threadIdx.x - o] : 0;
+    __syncthreads();
+    sh[threadIdx.x] += add;
+    __syncthreads();
+  }
+  uint64_t acc = tile_sums[blockIdx.x] + sh[threadIdx.x] - s;
+  for (int k = 0; k < SCAN_ITEMS; k++) {
+    if (base + k < n) out[base + k] = acc;
+    acc += v[k];
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) out[n] = *total;
+}
+
+// offsets[0..n] from counts[0..n); returns total on the host
+int exclusive_scan(irt_ctx *ctx, const uint32_t *d_counts, int64_t n, uint64_t *d_offsets,
+                   uint64_t *d_tmp /* ntiles + 1 */, uint64_t *h_total, cudaStream_t st) {
+  const int64_t ntiles = (n + SCAN_TILE - 1) / SCAN_TILE;
+  scan_tile_sums_kernel<<<(unsigned)ntiles, SCAN_T, 0, st>>>(d_counts, n, d_tmp);
+  scan_tile_offsets_kernel<<<1, 32, 0, st>>>(d_tmp, ntiles, d_tmp + ntiles);
+  scan_apply_kernel<<<(unsigned)ntiles, SCAN_T, 0, st>>>(d_counts, n, d_tmp, d_tmp + ntiles, d_offsets);
+  ctx->launches.fetch_add(3);
+  IRT_CUDA(ctx, cudaGetLastError());
+  IRT_CUDA(ctx, cudaMemcpyAsync(h_total, d_tmp + ntiles, 8, cudaMemcpyDeviceToHost, st));
+  IRT_CUDA(ctx, cudaStreamSynchronize(st));
+  return IRT_OK;
+}
+
+// ---- vertex mode helpers --------------------------------------------------------------------
+__global__ void vertex_heads_kernel(const uint32_t *__restrict__ flags, int64_t n,
+                                    int32_t *__restrict__ heads) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) heads[i] = (flags[i] & INVALID_MASK) ? -1 : (int32_t)i;
+}
+
+// ---- edge mode: level-synchronous bisection -----------------------------------------------------
+struct Interval {
+  int32_t edge, ia, ib;
+};
+struct Pending {
+  int32_t edge, ia, im, ib;
+};
+
+struct EdgePool {
+  // per edge
+  const double *a, *b;        // [E][S]
+  const double *thr;          // [E] rel_threshold
+  unsigned long long *first_invalid;  // [E] double bits (positive -> uint order == double order)
+  int32_t *head;              // [E]
+  uint32_t *eflags;           // [E]
+  // per sample
+  int32_t *s_edge, *s_next, *s_npts;
+  uint32_t *s_flags;
+  double *s_t, *s_state, *s_p;
+  int32_t cap_samples;
+  int S, N, enable_rotation, enable_retraction, cap_pts;
+};
+
+__global__ void edge_init_kernel(EdgePool P, int32_t E) {
+  const int32_t e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= E) return;
+  const int32_t i0 = 2 * e, i1 = 2 * e + 1;
+  P.s_edge[i0] = e; P.s_edge[i1] = e;
+  P.s_t[i0] = 0.0; P.s_t[i1] = 1.0;
+  for (int k = 0; k < P.S; k++) {
+    P.s_state[(int64_t)i0 * P.S + k] = P.a[(int64_t)e * P.S + k];
+    P.s_state[(int64_t)i1 * P.S + k] = P.b[(int64_t)e * P.S + k];
+  }
+  P.s_next[i0] = -1;
+  P.s_next[i1] = i0;
+  P.head[e] = i1;
+  P.first_invalid[e] = (unsigned long long)__double_as_longlong(10.0);  // VoxelEnvironment.cpp:261
+  P.eflags[e] = 0u;
+}
+
+// after FK: invalid samples lower first_invalid_t of their edge (VoxelEnvironment.cpp:266-268)
+__global__ void edge_mark_kernel(EdgePool P, int32_t lo, int32_t hi) {
+  const int32_t i = lo + blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= hi) return;
+  if (P.s_flags[i] & INVALID_MASK)
+    atomicMin(&P.first_invalid[P.s_edge[i]], (unsigned long long)__double_as_longlong(P.s_t[i]));
+}
+
+// OMPL compound interpolate restated (RealVector linear, SO2 shortest arc + wrap), the `interp`
+// lambda of VoxelBackboneMotionValidator.cpp:58-66
+__device__ void interpolate_state(const EdgePool &P, const double *a, const double *b, double t,
+                                  double *out) {
+  const double pi = 3.14159265358979323846;
+  for (int i = 0; i < P.N; i++) out[i] = a[i] + (b[i] - a[i]) * t;
+  int idx = P.N;
+  if (P.enable_rotation) {
+    double diff = b[idx] - a[idx];
+    if (fabs(diff) <= pi) {
+      out[idx] = a[idx] + diff * t;
+    } else {
+      if (diff > 0.0) diff = 2.0 * pi - diff;
+      else diff = -2.0 * pi - diff;
+      double v = a[idx] - diff * t;
+      if (v > pi) v -= 2.0 * pi;
+      else if (v < -pi) v += 2.0 * pi;
+      out[idx] = v;
+    }
+    idx++;
+  }
+  if (P.enable_retraction) out[idx] = a[idx] + (b[idx] - a[idx]) * t;
+}
+
+// one thread per open interval: VoxelEnvironment.cpp:369-384
+__global__ void edge_split_kernel(EdgePool P, const Interval *__restrict__ cur, int32_t ncur,
+                                  int32_t *__restrict__ n_samples, Pending *__restrict__ pend,
+                                  int32_t *__restrict__ n_pend) {
+  const int32_t q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= ncur) return;
+  const Interval iv = cur[q];
+  const double ta = P.s_t[iv.ia], tb = P.s_t[iv.ib];
+  if ((tb - ta) <= P.thr[iv.edge]) return;
+  const double fi = __longlong_as_double((long long)P.first_invalid[iv.edge]);
+  if (fi <= ta) return;
+  const int32_t m = atomicAdd(n_samples, 1);
+  if (m >= P.cap_samples) {
+    atomicOr(&P.eflags[iv.edge], IRT_FLAG_CAPACITY);
+    return;
+  }
+  const double tm = (ta + tb) / 2;
+  P.s_edge[m] = iv.edge;
+  P.s_t[m] = tm;
+  interpolate_state(P, P.a + (int64_t)iv.edge * P.S, P.b + (int64_t)iv.edge * P.S, tm,
+                    P.s_state + (int64_t)m * P.S);
+  P.s_next[m] = atomicExch(&P.head[iv.edge], m);
+  const int32_t k = atomicAdd(n_pend, 1);
+  pend[k] = Pending{iv.edge, iv.ia, m, iv.ib};
+}
+
+// find_cell -- collision/VoxelOctree.cpp:309-317 (+domain_check :1511-1521); false = domain error
+__device__ __forceinline__ bool find_cell(const GridDev &g, const D3 &p, long long *c) {
+  if (p.x < g.lo[0] || g.hi[0] < p.x) return false;
+  if (p.y < g.lo[1] || g.hi[1] < p.y) return false;
+  if (p.z < g.lo[2] || g.hi[2] < p.z) return false;
+  c[0] = (long long)((p.x - g.lo[0]) / g.d[0]);
+  c[1] = (long long)((p.y - g.lo[1]) / g.d[1]);
+  c[2] = (long long)((p.z - g.lo[2]) / g.d[2]);
+  return true;
+}
+
+// should_subdivide(a, b) -- VoxelEnvironment.cpp:304-341, warp-cooperative (lanes over points,
+// scanned from the tip like the reference so the first event found is the same one)
+__device__ bool should_subdivide(const GridDev &g, const EdgePool &P, int32_t ia, int32_t ib,
+                                 int32_t edge, int lane) {
+  if (P.s_flags[ia] & INVALID_MASK) return false;
+  const int na = P.s_npts[ia], nb = P.s_npts[ib];
+  if (na + 1 < nb || na > nb + 1) return true;
+  const int Pn = min(na, nb);
+  const double *pa = P.s_p + (int64_t)ia * P.cap_pts * 3, *pb = P.s_p + (int64_t)ib * P.cap_pts * 3;
+  for (int top = Pn - 1; top >= 0; top -= 32) {
+    const int i = top - lane;
+    int ev = 0;  // 1 = far apart, 2 = domain error
+    if (i >= 0) {
+      long long s[3], e[3];
+      const D3 qa = rotate_pt(g, pa + 3 * i), qb = rotate_pt(g, pb + 3 * i);
+      if (!find_cell(g, qa, s) || !find_cell(g, qb, e)) {
+        ev = 2;
+      } else {
+        const long long dx = llabs(s[0] - e[0]), dy = llabs(s[1] - e[1]), dz = llabs(s[2] - e[2]);
+        if (dx > 1 || dy > 1 || dz > 1) ev = 1;
+      }
+    }
+    const unsigned m = __ballot_sync(0xffffffffu, ev != 0);
+    if (m) {
+      const int first = __ffs(m) - 1;  // lane 0 holds the highest index
+      const int fev = __shfl_sync(0xffffffffu, ev, first);
+      if (fev == 2) {
+        if (lane == 0) atomicOr(&P.eflags[edge], IRT_FLAG_OUT_OF_DOMAIN);
+        return false;
+      }
+      return true;
+    }
+  }
+  return false;
+}
+
+// one warp per candidate: round 0 tests (2e, 2e+1); later rounds test both halves of a bisected
+// interval (VoxelEnvironment.cpp:350-353,386-397)
+__global__ void edge_subdivide_kernel(const GridDev g, EdgePool P, const Pending *__restrict__ pend,
+                                      int32_t npend, int32_t E_round0, Interval *__restrict__ next,
+                                      int32_t *__restrict__ n_next, int32_t cap_next) {
+  const int lane = threadIdx.x & 31;
+  const int32_t w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int32_t total = pend ? npend : E_round0;
+  if (w >= total) return;
+  if (!pend) {
+    const int32_t e = w;
+    if (should_subdivide(g, P, 2 * e, 2 * e + 1, e, lane) && lane == 0) {
+      const int32_t k = atomicAdd(n_next, 1);
+      if (k < cap_next) next[k] = Interval{e, 2 * e, 2 * e + 1};
+      else atomicOr(&P.eflags[e], IRT_FLAG_CAPACITY);
+    }
+    return;
+  }
+  const Pending pd = pend[w];
+  const bool distal = should_subdivide(g, P, pd.im, pd.ib, pd.edge, lane);
+  const bool proximal = should_subdivide(g, P, pd.ia, pd.im, pd.edge, lane);
+  if (lane == 0) {
+    if (distal) {
+      const int32_t k = atomicAdd(n_next, 1);
+      if (k < cap_next) next[k] = Interval{pd.edge, pd.im, pd.ib};
+      else atomicOr(&P.eflags[pd.edge], IRT_FLAG_CAPACITY);
+    }
+    if (proximal) {
+      const int32_t k = atomicAdd(n_next, 1);
+      if (k < cap_next) next[k] = Interval{pd.edge, pd.ia, pd.im};
+      else atomicOr(&P.eflags[pd.edge], IRT_FLAG_CAPACITY);
+    }
+  }
+}
+
+__global__ void edge_finish_kernel(EdgePool P, int32_t E, double *__restrict__ tlimit,
+                                   uint32_t *__restrict__ flags_out) {
+  const int32_t e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= E) return;
+  const double fi = __longlong_as_double((long long)P.first_invalid[e]);
+  tlimit[e] = fi;
+  uint32_t f = P.eflags[e];
+  if (!(5.0 < fi)) f |= IRT_FLAG_PARTIAL;  // VoxelEnvironment.cpp:438
+  flags_out[e] = f;
+}
+
+struct DevMem {
+  std::vector<void *> ptrs;
+  ~DevMem() {
+    for (void *p : ptrs) cudaFree(p);
+  }
+  template <typename T>
+  bool alloc(T **out, size_t count) {
+    void *p = nullptr;
+    if (cudaMalloc(&p, (count ? count : 1) * sizeof(T)) != cudaSuccess) return false;
+    ptrs.push_back(p);
+    *out = (T *)p;
+    return true;
+  }
+};
+
+int raster_to_store(irt_ctx *ctx, const GridDev &g, const double *d_pts, const int32_t *d_npts,
+                    int cap_pts, const int32_t *d_heads, const int32_t *d_next, const double *d_st,
+                    const double *d_tlimit, int64_t nsets, double *d_tlast, int32_t *d_nsamples,
+                    uint32_t *d_setflags, uint32_t *d_counts, uint64_t *d_scan_tmp,
+                    irt_setstore *store, int64_t set_off, uint64_t *d_offsets_tmp,
+                    uint64_t *total_out, cudaStream_t st);
+
+}  // namespace
+
+namespace {
+
+// counts -> offsets -> emit into a temporary CSR (d_offsets_tmp / store arrays at set_off)
+int raster_to_store(irt_ctx *ctx, const GridDev &g, const double *d_pts, const int32_t *d_npts,
+                    int cap_pts, const int32_t *d_heads, const int32_t *d_next, const double *d_st,
+                    const double *d_tlimit, int64_t nsets, double *d_tlast, int32_t *d_nsamples,
+                    uint32_t *d_setflags, uint32_t *d_counts, uint64_t *d_scan_tmp,
+                    irt_setstore *store, int64_t set_off, uint64_t *d_offsets_tmp,
+                    uint64_t *total_out, cudaStream_t st) {
+  (void)set_off;
+  int64_t blocks = (nsets + RS_WARPS - 1) / RS_WARPS;
+  const int64_t max_blocks = (int64_t)ctx->sm_count * 8;
+  if (blocks > max_blocks) blocks = max_blocks;
+  IRT_CUDA(ctx, cudaFuncSetAttribute(swept_voxel_raster_kernel<false>,
+                                     cudaFuncAttributeMaxDynamicSharedMemorySize, RS_SMEM));
+  IRT_CUDA(ctx, cudaFuncSetAttribute(swept_voxel_raster_kernel<true>,
+                                     cudaFuncAttributeMaxDynamicSharedMemorySize, RS_SMEM));
+  swept_voxel_raster_kernel<false><<<(unsigned)blocks, RS_WARPS * 32, RS_SMEM, st>>>(
+      g, d_pts, d_npts, cap_pts, d_heads, d_next, d_st, d_tlimit, nsets, d_counts, d_tlast,
+      d_nsamples, nullptr, nullptr, nullptr, d_setflags);
+  IRT_LAUNCHED(ctx);
+  IRT_CUDA(ctx, cudaGetLastError());
+  uint64_t total = 0;
+  int rc = exclusive_scan(ctx, d_counts, nsets, d_offsets_tmp, d_scan_tmp, &total, st);
+  if (rc) return rc;
+  *total_out = total;
+  (void)store;
+  return IRT_OK;
+}
+
+}  // namespace
+
+// ===============================================================================================
+// C ABI
+// ===============================================================================================
+extern "C" {
+
+uint32_t irt_valid_segment_count(const irt_robot_desc *rb, const irt_space *sp, const double *a,
+                                 const double *b) {
+  // OMPL 1.5 documented behaviour: StateSpace::validSegmentCount = ceil(distance /
+  // longestValidSegment), longestValidSegment = maximumExtent * fraction (fractions set in
+  // motion-planning/Problem.cpp:118-144); CompoundStateSpace takes the max over subspaces.
+  const int N = rb->n_tendons;
+  double ext2 = 0;
+  for (int i = 0; i < N; i++) ext2 += rb->max_tension[i] * rb->max_tension[i];
+  const double tendon_extent = std::sqrt(ext2);
+  const double len_t = tendon_extent * (sp->min_tension_change / tendon_extent);
+  double d2 = 0;
+  for (int i = 0; i < N; i++) d2 += (a[i] - b[i]) * (a[i] - b[i]);
+  unsigned sc = (unsigned)std::ceil(std::sqrt(d2) / len_t);
+  int idx = N;
+  if (rb->enable_rotation) {
+    const double len_r = M_PI * (sp->min_rotation_change / (2 * M_PI));
+    double d = std::fabs(a[idx] - b[idx]);
+    d = (d > M_PI) ? 2.0 * M_PI - d : d;
+    unsigned c = (unsigned)std::ceil(d / len_r);
+    if (c > sc) sc = c;
+    idx++;
+  }
+  if (rb->enable_retraction) {
+    const double len_s = rb->L * std::fmin(0.01, sp->min_retraction_change / rb->L);
+    double d = std::sqrt((a[idx] - b[idx]) * (a[idx] - b[idx]));
+    unsigned c = (unsigned)std::ceil(d / len_s);
+    if (c > sc) sc = c;
+  }
+  return sc;
+}
+
+int irt_voxelize_vertices(irt_ctx *ctx, const irt_robot *rb, const double *states, int state_size,
+                          int64_t n, irt_setstore *store, uint32_t *flags, double *tips) {
+  if (!ctx || !rb || !store || n < 0 || (n > 0 && !states)) return IRT_ERR_INVALID_ARGUMENT;
+  if (state_size != rb->state_size)
+    return irt_fail(ctx, IRT_ERR_INVALID_ARGUMENT, "State is not the right size (%d != %d)",
+                    state_size, rb->state_size);
+  const GridDev &g = store->gd;
+  // VoxelBackboneValidityChecker ctor: dL must not exceed the largest voxel side (.h:37-45)
+  const double dmax = std::fmax(g.d[0], std::fmax(g.d[1], g.d[2]));
+  if (rb->desc.dL > dmax)
+    return irt_fail(ctx, IRT_ERR_INVALID_ARGUMENT,
+                    "robot.specs.dL is larger than expected by VoxelBackboneValidityChecker (%g > %g)",
+                    rb->desc.dL, dmax);
+  IRT_CUDA(ctx, cudaSetDevice(ctx->device));
+  cudaStream_t st = ctx->stream;
+  if (n == 0) {
+    int rc = setstore_reserve(ctx, store, 0, 0);
+    if (rc) return rc;
+    IRT_CUDA(ctx, cudaMemsetAsync(store->d_offsets, 0, 8, st));
+    return setstore_finalize(ctx, store, 0, 0, st);
+  }
+  const int cap = rb->max_points;
+  DevMem mem;
+  double *d_states, *d_p, *d_tip;
+  int32_t *d_npts, *d_heads;
+  uint32_t *d_flags, *d_counts;
+  uint64_t *d_scan_tmp;
+  const int64_t ntiles = (n + SCAN_TILE - 1) / SCAN_TILE;
+  if (!mem.alloc(&d_states, (size_t)n * state_size) || !mem.alloc(&d_p, (size_t)n * cap * 3) ||
+      !mem.alloc(&d_tip, (size_t)n * 3) || !mem.alloc(&d_npts, (size_t)n) ||
+      !mem.alloc(&d_heads, (size_t)n) || !mem.alloc(&d_flags, (size_t)n) ||
+      !mem.alloc(&d_counts, (size_t)n) || !mem.alloc(&d_scan_tmp, (size_t)ntiles + 2))
+    return irt_fail(ctx, IRT_ERR_CUDA, "device allocation failed (n=%lld)", (long long)n);
+  IRT_CUDA(ctx, cudaMemcpyAsync(d_states, states, (size_t)n * state_size * 8, cudaMemcpyHostToDevice, st));
+  irt_fk_outputs o;
+  std::memset(&o, 0, sizeof(o));
+  o.p = d_p; o.npts = d_npts; o.flags = d_flags; o.tip = d_tip;
+  int rc = fk_launch(ctx, rb, d_states, n, cap, o, nullptr, st);
+  if (rc) return rc;
+  rc = self_collision_launch(ctx, rb, d_p, d_npts, n, cap, d_flags, st);
+  if (rc) return rc;
+  const int T = 256;
+  vertex_heads_kernel<<<(unsigned)((n + T - 1) / T), T, 0, st>>>(d_flags, n, d_heads);
+  IRT_LAUNCHED(ctx);
+  rc = setstore_reserve(ctx, store, n, 0);
+  if (rc) return rc;
+  uint64_t total = 0;
+  rc = raster_to_store(ctx, g, d_p, d_npts, cap, d_heads, nullptr, nullptr, nullptr, n, nullptr,
+                       nullptr, d_flags, d_counts, d_scan_tmp, store, 0, store->d_offsets, &total, st);
+  if (rc) return rc;
+  rc = setstore_reserve(ctx, store, n, (int64_t)total);  // offsets buffer is kept (cap_sets ok)
+  if (rc) return rc;
+  int64_t blocks = (n + RS_WARPS - 1) / RS_WARPS;
+  const int64_t max_blocks = (int64_t)ctx->sm_count * 8;
+  if (blocks > max_blocks) blocks = max_blocks;
+  swept_voxel_raster_kernel<true><<<(unsigned)blocks, RS_WARPS * 32, RS_SMEM, st>>>(
+      g, d_p, d_npts, cap, d_heads, nullptr, nullptr, nullptr, n, nullptr, nullptr, nullptr,
+      store->d_offsets, store->d_keys, store->d_bits, nullptr);
+  IRT_LAUNCHED(ctx);
+  IRT_CUDA(ctx, cudaGetLastError());
+  rc = setstore_finalize(ctx, store, n, (int64_t)total, st);
+  if (rc) return rc;
+  if (flags) IRT_CUDA(ctx, cudaMemcpyAsync(flags, d_flags, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
+  if (tips) IRT_CUDA(ctx, cudaMemcpyAsync(tips, d_tip, (size_t)n * 24, cudaMemcpyDeviceToHost, st));
+  IRT_CUDA(ctx, cudaStreamSynchronize(st));
+  return IRT_OK;
+}
+
+int irt_voxelize_edges(irt_ctx *ctx, const irt_robot *rb, const irt_space *space, const double *a,
+                       const double *b, int state_size, int64_t n, irt_setstore *store,
+                       uint32_t *flags, double *t_last, int32_t *nsamples) {
+  if (!ctx || !rb || !space || !store || n < 0 || (n > 0 && (!a || !b)))
+    return IRT_ERR_INVALID_ARGUMENT;
+  if (state_size != rb->state_size)
+    return irt_fail(ctx, IRT_ERR_INVALID_ARGUMENT, "State is not the right size (%d != %d)",
+                    state_size, rb->state_size);
+  const GridDev &g = store->gd;
+  const double dmax = std::fmax(g.d[0], std::fmax(g.d[1], g.d[2]));
+  if (rb->desc.dL > dmax)
+    return irt_fail(ctx, IRT_ERR_INVALID_ARGUMENT,
+                    "robot.specs.dL is larger than expected by VoxelBackboneValidityChecker (%g > %g)",
+                    rb->desc.dL, dmax);
+  IRT_CUDA(ctx, cudaSetDevice(ctx->device));
+  cudaStream_t st = ctx->stream;
+  const int S = state_size, cap = rb->max_points;
+  if (n == 0) {
+    int rc = setstore_reserve(ctx, store, 0, 0);
+    if (rc) return rc;
+    IRT_CUDA(ctx, cudaMemsetAsync(store->d_offsets, 0, 8, st));
+    return setstore_finalize(ctx, store, 0, 0, st);
+  }
+  if (n > (int64_t)0x3fffffff) return irt_fail(ctx, IRT_ERR_INVALID_ARGUMENT, "too many edges");
+
+  // chunk sizing: a sample costs cap*24 + S*8 + 40 bytes; budget ~6 GiB or 40% of free memory
+  size_t free_b = 0, total_b = 0;
+  IRT_CUDA(ctx, cudaMemGetInfo(&free_b, &total_b));
+  const size_t per_sample = (size_t)cap * 24 + (size_t)S * 8 + 40;
+  size_t budget = (size_t)6 << 30;
+  if (budget > free_b * 2 / 5) budget = free_b * 2 / 5;
+  int64_t cap_samples = (int64_t)(budget / per_sample);
+  if (cap_samples > 0x3fffffff) cap_samples = 0x3fffffff;
+  int64_t chunk = cap_samples / 48;
+  if (chunk < 256) { chunk = 256; if (cap_samples < chunk * 8) cap_samples = chunk * 8; }
+  if (chunk > n) { chunk = n; }
+
+  // host: rel_threshold = 1 / validSegmentCount  (VoxelBackboneMotionValidator.cpp:55-56)
+  std::vector<double> h_thr((size_t)n);
+  for (int64_t i = 0; i < n; i++)
+    h_thr[i] = 1.0 / double(irt_valid_segment_count(&rb->desc, space, a + i * S, b + i * S));
+
+  DevMem mem;
+  EdgePool P;
+  std::memset(&P, 0, sizeof(P));
+  double *d_a, *d_b, *d_thr, *d_tlimit, *d_tlast;
+  int32_t *d_nsamp_set;
+  uint32_t *d_flags_out, *d_counts;
+  Interval *d_q0, *d_q1;
+  Pending *d_pend;
+  int32_t *d_counters;  // [0] n_samples, [1] n_pend, [2] n_q0, [3] n_q1
+  uint64_t *d_scan_tmp, *d_off_chunk;
+  const int64_t ntiles = (chunk + SCAN_TILE - 1) / SCAN_TILE;
+  bool ok = mem.alloc(&d_a, (size_t)chunk * S) && mem.alloc(&d_b, (size_t)chunk * S) &&
+            mem.alloc(&d_thr, (size_t)chunk) && mem.alloc(&d_tlimit, (size_t)chunk) &&
+            mem.alloc(&d_tlast, (size_t)chunk) && mem.alloc(&d_nsamp_set, (size_t)chunk) &&
+            mem.alloc(&d_flags_out, (size_t)chunk) && mem.alloc(&d_counts, (size_t)chunk) &&
+            mem.alloc(&P.first_invalid, (size_t)chunk) && mem.alloc(&P.head, (size_t)chunk) &&
+            mem.alloc(&P.eflags, (size_t)chunk) && mem.alloc(&P.s_edge, (size_t)cap_samples) &&
+            mem.alloc(&P.s_next, (size_t)cap_samples) && mem.alloc(&P.s_npts, (size_t)cap_samples) &&
+            mem.alloc(&P.s_flags, (size_t)cap_samples) && mem.alloc(&P.s_t, (size_t)cap_samples) &&
+            mem.alloc(&P.s_state, (size_t)cap_samples * S) &&
+            mem.alloc(&P.s_p, (size_t)cap_samples * cap * 3) &&
+            mem.alloc(&d_q0, (size_t)cap_samples) && mem.alloc(&d_q1, (size_t)cap_samples) &&
+            mem.alloc(&d_pend, (size_t)cap_samples) && mem.alloc(&d_counters, 8) &&
+            mem.alloc(&d_scan_tmp, (size_t)ntiles + 2) && mem.alloc(&d_off_chunk, (size_t)chunk + 1);
+  if (!ok) return irt_fail(ctx, IRT_ERR_CUDA, "edge pool allocation failed (%lld samples)", (long long)cap_samples);
+  P.a = d_a; P.b = d_b; P.thr = d_thr;
+  P.cap_samples = (int32_t)cap_samples;
+  P.S = S; P.N = rb->desc.n_tendons; P.cap_pts = cap;
+  P.enable_rotation = rb->desc.enable_rotation ? 1 : 0;
+  P.enable_retraction = rb->desc.enable_retraction ? 1 : 0;
+
+  // per-chunk CSR pieces are gathered on the host side of the store (device-to-device appends)
+  std::vector<uint64_t> h_offsets((size_t)n + 1, 0);
+  struct Piece { uint32_t *keys; uint64_t *bits; uint64_t count; };
+  std::vector<Piece> pieces;
+  DevMem piece_mem;
+  uint64_t grand_total = 0;
+  const int T = 256;
+
+  for (int64_t off = 0; off < n; off += chunk) {
+    const int32_t E = (int32_t)((n - off < chunk) ? (n - off) : chunk);
+    IRT_CUDA(ctx, cudaMemcpyAsync(d_a, a + off * S, (size_t)E * S * 8, cudaMemcpyHostToDevice, st));
+    IRT_CUDA(ctx, cudaMemcpyAsync(d_b, b + off * S, (size_t)E * S * 8, cudaMemcpyHostToDevice, st));
+    IRT_CUDA(ctx, cudaMemcpyAsync(d_thr, h_thr.data() + off, (size_t)E * 8, cudaMemcpyHostToDevice, st));
+    IRT_CUDA(ctx, cudaMemsetAsync(d_counters, 0, 32, st));
+    edge_init_kernel<<<(E + T - 1) / T, T, 0, st>>>(P, E);
+    IRT_LAUNCHED(ctx);
+    int32_t n_samples = 2 * E;
+    IRT_CUDA(ctx, cudaMemcpyAsync(d_counters, &n_samples, 4, cudaMemcpyHostToDevice, st));
+
+    auto run_fk = [&](int32_t lo, int32_t hi) -> int {
+      if (hi <= lo) return IRT_OK;
+      irt_fk_outputs o;
+      std::memset(&o, 0, sizeof(o));
+      o.p = P.s_p + (int64_t)lo * cap * 3;
+      o.npts = P.s_npts + lo;
+      o.flags = P.s_flags + lo;
+      int r = fk_launch(ctx, rb, P.s_state + (int64_t)lo * S, hi - lo, cap, o, nullptr, st);
+      if (r) return r;
+      r = self_collision_launch(ctx, rb, o.p, o.npts, hi - lo, cap, o.flags, st);
+      if (r) return r;
+      edge_mark_kernel<<<(hi - lo + T - 1) / T, T, 0, st>>>(P, lo, hi);
+      IRT_LAUNCHED(ctx);
+      return IRT_OK;
+    };
+    int rc = run_fk(0, n_samples);
+    if (rc) return rc;
+    Interval *cur = d_q0, *nxt = d_q1;
+    int32_t *n_cur = d_counters + 2, *n_nxt = d_counters + 3;
+    {
+      const int64_t threads = (int64_t)E * 32;
+      edge_subdivide_kernel<<<(unsigned)((threads + T - 1) / T), T, 0, st>>>(
+          g, P, nullptr, 0, E, cur, n_cur, (int32_t)cap_samples);
+      IRT_LAUNCHED(ctx);
+    }
+    for (int round = 0; round < 64; round++) {
+      int32_t h_cnt[4];
+      IRT_CUDA(ctx, cudaMemcpyAsync(h_cnt, d_counters, 16, cudaMemcpyDeviceToHost, st));
+      IRT_CUDA(ctx, cudaStreamSynchronize(st));
+      const int32_t ncur = std::min(*(cur == d_q0 ? &h_cnt[2] : &h_cnt[3]), (int32_t)cap_samples);
+      if (ncur == 0) break;
+      const int32_t s_lo = std::min(h_cnt[0], (int32_t)cap_samples);
+      IRT_CUDA(ctx, cudaMemsetAsync(d_counters + 1, 0, 4, st));  // n_pend
+      IRT_CUDA(ctx, cudaMemsetAsync(n_nxt, 0, 4, st));
+      edge_split_kernel<<<(ncur + T - 1) / T, T, 0, st>>>(P, cur, ncur, d_counters, d_pend, d_counters + 1);
+      IRT_LAUNCHED(ctx);
+      IRT_CUDA(ctx, cudaMemcpyAsync(h_cnt, d_counters, 8, cudaMemcpyDeviceToHost, st));
+      IRT_CUDA(ctx, cudaStreamSynchronize(st));
+      const int32_t s_hi = std::min(h_cnt[0], (int32_t)cap_samples);
+      const int32_t npend = h_cnt[1];
+      if (h_cnt[0] > (int32_t)cap_samples) {  // keep the counter in range
+        int32_t capv = (int32_t)cap_samples;
+        IRT_CUDA(ctx, cudaMemcpyAsync(d_counters, &capv, 4, cudaMemcpyHostToDevice, st));
+      }
+      rc = run_fk(s_lo, s_hi);
+      if (rc) return rc;
+      if (npend > 0) {
+        const int64_t threads = (int64_t)npend * 32;
+        edge_subdivide_kernel<<<(unsigned)((threads + T - 1) / T), T, 0, st>>>(
+            g, P, d_pend, npend, 0, nxt, n_nxt, (int32_t)cap_samples);
+        IRT_LAUNCHED(ctx);
+      }
+      std::swap(cur, nxt);
+      std::swap(n_cur, n_nxt);
+    }
+    edge_finish_kernel<<<(E + T - 1) / T, T, 0, st>>>(P, E, d_tlimit, d_flags_out);
+    IRT_LAUNCHED(ctx);
+    // rasterise every sample below the first invalid t (VoxelEnvironment.cpp:406-422)
+    uint64_t total = 0;
+    rc = raster_to_store(ctx, g, P.s_p, P.s_npts, cap, P.head, P.s_next, P.s_t, d_tlimit, E, d_tlast,
+                         d_nsamp_set, d_flags_out, d_counts, d_scan_tmp, store, 0, d_off_chunk, &total, st);
+    if (rc) return rc;
+    Piece pc{nullptr, nullptr, total};
+    if (!piece_mem.alloc(&pc.keys, (size_t)total + 4) || !piece_mem.alloc(&pc.bits, (size_t)total + 4))
+      return irt_fail(ctx, IRT_ERR_CUDA, "piece allocation failed");
+    int64_t blocks = ((int64_t)E + RS_WARPS - 1) / RS_WARPS;
+    const int64_t max_blocks = (int64_t)ctx->sm_count * 8;
+    if (blocks > max_blocks) blocks = max_blocks;
+    swept_voxel_raster_kernel<true><<<(unsigned)blocks, RS_WARPS * 32, RS_SMEM, st>>>(
+        g, P.s_p, P.s_npts, cap, P.head, P.s_next, P.s_t, d_tlimit, E, nullptr, nullptr, nullptr,
+        d_off_chunk, pc.keys, pc.bits, nullptr);
+    IRT_LAUNCHED(ctx);
+    IRT_CUDA(ctx, cudaGetLastError());
+    pieces.push_back(pc);
+    // chunk offsets -> host (rebased), per-edge outputs -> host
+    std::vector<uint64_t> h_off((size_t)E + 1);
+    IRT_CUDA(ctx, cudaMemcpyAsync(h_off.data(), d_off_chunk, ((size_t)E + 1) * 8, cudaMemcpyDeviceToHost, st));
+    if (flags) IRT_CUDA(ctx, cudaMemcpyAsync(flags + off, d_flags_out, (size_t)E * 4, cudaMemcpyDeviceToHost, st));
+    if (t_last) IRT_CUDA(ctx, cudaMemcpyAsync(t_last + off, d_tlast, (size_t)E * 8, cudaMemcpyDeviceToHost, st));
+    if (nsamples) IRT_CUDA(ctx, cudaMemcpyAsync(nsamples + off, d_nsamp_set, (size_t)E * 4, cudaMemcpyDeviceToHost, st));
+    IRT_CUDA(ctx, cudaStreamSynchronize(st));
+    for (int32_t e = 0; e <= E; e++) h_offsets[(size_t)off + e] = grand_total + h_off[e];
+    grand_total += total;
+  }
+  // assemble the store
+  int rc = setstore_reserve(ctx, store, n, (int64_t)grand_total);
+  if (rc) return rc;
+  IRT_CUDA(ctx, cudaMemcpyAsync(store->d_offsets, h_offsets.data(), ((size_t)n + 1) * 8, cudaMemcpyHostToDevice, st));
+  uint64_t pos = 0;
+  for (const Piece &pc : pieces) {
+    if (pc.count) {
+      IRT_CUDA(ctx, cudaMemcpyAsync(store->d_keys + pos, pc.keys, (size_t)pc.count * 4, cudaMemcpyDeviceToDevice, st));
+      IRT_CUDA(ctx, cudaMemcpyAsync(store->d_bits + pos, pc.bits, (size_t)pc.count * 8, cudaMemcpyDeviceToDevice, st));
+    }
+    pos += pc.count;
+  }
+  rc = setstore_finalize(ctx, store, n, (int64_t)grand_total, st);
+  if (rc) return rc;
+  IRT_CUDA(ctx, cudaStreamSynchronize(st));
+  return IRT_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,26 @@
+import os
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
+
+
+@pytest.fixture(scope="session")
+def orc():
+    """canonical CPU oracle (test infrastructure)"""
+    from oracle.oracle import Oracle, build
+    build()
+    return Oracle("canonical")
+
+
+@pytest.fixture(scope="session")
+def wl():
+    import irt_b200.workloads as w
+    return w
