@@ -1,0 +1,462 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the CPU oracle on identical
+seeded inputs.  Bars (BASELINE.json north_star): backbone points within 1e-9 relative;
+flags, voxel sets and collision verdicts bit-exact (flips counted and required to be zero here).
+"""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+FK_REL_TOL = 1e-9  # relative to the backbone length L (north_star tolerance)
+
+
+@pytest.fixture(scope="module")
+def irt():
+    import irt_b200
+    return irt_b200
+
+
+@pytest.fixture(scope="module")
+def ctx(irt):
+    return irt.Context(0)
+
+
+def _fk_compare(irt, ctx, orc, spec, states, want_all=False):
+    rb = irt.Robot(ctx, spec)
+    want = ("p", "R", "t", "npts", "L", "L_i", "tip", "uv", "flags", "iters", "nsteps") if want_all \
+        else ("p", "npts", "L_i", "tip", "flags")
+    out = rb.shape_batch(states, want=want)
+    ref = orc.fk_batch(orc.robot(spec), states, rb.max_points)
+    assert np.array_equal(out["npts"], ref["npts"])
+    L = spec["L"]
+    err = np.abs(out["p"] - ref["p"]).max() / L
+    assert err < FK_REL_TOL, "backbone points differ by %g L" % err
+    assert np.abs(out["L_i"] - ref["L_i"]).max() / L < FK_REL_TOL
+    assert np.abs(out["tip"] - ref["tip"]).max() / L < FK_REL_TOL
+    assert np.array_equal(out["flags"], ref["flags"])
+    if want_all:
+        assert np.array_equal(out["iters"], ref["iters"])
+        assert np.array_equal(out["nsteps"], ref["nsteps"])
+    return rb, out, ref
+
+
+@pytest.mark.parametrize("robot,dL,rot", [("a", 0.005, False), ("a", 0.003, False),
+                                          ("b", 0.005, False), ("b", 0.003, False),
+                                          ("b", 0.005, True)])
+def test_fk_parity(irt, ctx, orc, wl, robot, dL, rot):
+    spec = wl.robot_a(dL) if robot == "a" else wl.robot_b(dL, rotation=rot)
+    states = wl.sample_states(spec, 3000, stream=31)
+    _fk_compare(irt, ctx, orc, spec, states, want_all=True)
+
+
+def test_fk_full_tendon_result(irt, ctx, orc, wl):
+    """every TendonResult member (t, p, R, L, L_i, u_i, u_f, v_i, v_f, converged)"""
+    spec = wl.robot_b(0.005, rotation=True)
+    states = wl.sample_states(spec, 64, stream=32)
+    rb = irt.Robot(ctx, spec)
+    out = rb.shape_batch(states, want=("p", "R", "t", "npts", "L", "L_i", "uv", "flags"))
+    orb = orc.robot(spec)
+    for i in range(64):
+        s = orc.shape(orb, states[i])
+        n = len(s["t"])
+        assert out["npts"][i] == n
+        assert np.allclose(out["t"][i, :n], s["t"], atol=1e-15)
+        assert np.abs(out["p"][i, :n] - s["p"]).max() < FK_REL_TOL * spec["L"]
+        assert np.abs(out["R"][i, :n] - s["R"]).max() < 1e-9
+        assert abs(out["L"][i] - s["L"]) < FK_REL_TOL * spec["L"]
+        uv = out["uv"][i]
+        for got, want in ((uv[0:3], s["u_i"]), (uv[3:6], s["u_f"]), (uv[6:9], s["v_i"]), (uv[9:12], s["v_f"])):
+            assert np.allclose(got, want, rtol=1e-9, atol=1e-10)
+        assert bool(out["flags"][i] & irt.FLAG_NONCONVERGED) == (not s["converged"])
+        assert np.all(out["p"][i, n:] == 0)  # padding rows are zero
+
+
+def test_fk_other_tendon_counts(irt, ctx, orc, wl):
+    """1, 2, 3, 5 and 8 tendons, mixed straight / helical / quadratic routing"""
+    base = wl.robot_b(0.005)
+    for n_t in (1, 2, 3, 5, 8):
+        spec = dict(base)
+        spec["C"] = [[0.4 * k, (-1) ** k * 9.0, 20.0 * (k % 2)] for k in range(n_t)]
+        spec["D"] = [[0.008 + 0.0005 * k, 0.01 * (k % 3)] for k in range(n_t)]
+        spec["max_tension"] = [20.0] * n_t
+        spec["min_length"] = [-1.0] * n_t   # general routing: home lengths are unsupported
+        spec["max_length"] = [1.0] * n_t    # (reference UB), keep the limits out of play
+        states = wl.sample_states(spec, 300, stream=33 + n_t)
+        rb = irt.Robot(ctx, spec)
+        out = rb.shape_batch(states, want=("p", "npts", "L_i"))
+        ref = orc.fk_batch(orc.robot(spec), states, rb.max_points)
+        assert np.array_equal(out["npts"], ref["npts"])
+        assert np.abs(out["p"] - ref["p"]).max() < FK_REL_TOL * spec["L"]
+        assert np.abs(out["L_i"] - ref["L_i"]).max() < FK_REL_TOL * spec["L"]
+
+
+def test_fk_edge_cases(irt, ctx, orc, wl):
+    spec = wl.robot_b(0.005)
+    rb = irt.Robot(ctx, spec)
+    L = spec["L"]
+    tau = [3.0, 7.5, 1.0, 0.0, 12.0, 4.0]
+    # s == L, s > L, K == 0 (L - dL/2 < s < L), exact node, two-step and one-step first gaps, s = 0
+    ss = [L, L + 0.05, 0.199, 0.1975, 0.195, 0.0131, 0.0169, 0.0, 1e-300]
+    states = np.array([tau + [s] for s in ss])
+    _fk_compare(irt, ctx, orc, spec, states, want_all=True)
+    out = rb.shape_batch(states, want=("p", "npts", "flags"))
+    assert out["npts"][0] == 1 and out["npts"][1] == 1 and out["npts"][2] == 1
+    # negative retraction / NaN: outside the reference's state space -> BAD_STATE, no points
+    bad = rb.shape_batch(np.array([tau + [-0.01], tau + [float("nan")]]), want=("p", "npts", "flags"))
+    assert np.all(bad["flags"] & irt.FLAG_BAD_STATE) and np.all(bad["npts"] == 0)
+    # zero tension
+    z = rb.shape_batch(np.array([[0.0] * 6 + [0.05]]), want=("p", "npts", "t"))
+    n = z["npts"][0]
+    assert np.all(z["p"][0, :n, :2] == 0) and np.allclose(z["p"][0, :n, 2], z["t"][0, :n] - 0.05, atol=1e-15)
+    # empty batch
+    e = rb.shape_batch(np.zeros((0, 7)))
+    assert e["p"].shape[0] == 0
+    # error convention (TendonRobot.h:107-109 -> std::invalid_argument)
+    with pytest.raises(irt.IrtError) as ei:
+        rb.shape_batch(np.zeros((4, 6)))
+    assert ei.value.status == irt.IRT_ERR_INVALID_ARGUMENT
+    with pytest.raises(irt.IrtError) as ei:
+        rb.shape_batch(np.zeros((4, 7)), cap_pts=8)
+    assert ei.value.status == irt.IRT_ERR_CAPACITY
+
+
+def test_fk_self_collision_and_limits(irt, ctx, orc, wl):
+    """a softer backbone curls enough to self-collide; flags must agree bit for bit"""
+    spec = wl.robot_a(0.005)
+    spec["E"] = 1.0e6
+    states = wl.sample_states(spec, 4000, stream=35)
+    rb, out, ref = _fk_compare(irt, ctx, orc, spec, states)
+    assert (ref["flags"] & irt.FLAG_SELF_COLLISION).sum() > 20, "fixture must exercise self-collision"
+    assert (ref["flags"] & irt.FLAG_LENGTH_LIMIT).sum() > 20
+    spec = wl.robot_b(0.003)
+    spec["E"] = 1.4e6  # also exercises non-convergence and the 1000-iteration cap
+    states = wl.sample_states(spec, 4000, stream=36)
+    _, _, ref = _fk_compare(irt, ctx, orc, spec, states, want_all=True)
+    assert (ref["flags"] & irt.FLAG_NONCONVERGED).sum() > 50 and ref["iters"].max() == 1000
+
+
+def test_fk_device_resident_matches_host_api(irt, ctx, wl):
+    torch = pytest.importorskip("torch")
+    spec = wl.robot_b(0.005)
+    rb = irt.Robot(ctx, spec)
+    n = 5000
+    states = wl.sample_states(spec, n, stream=37)
+    host = rb.shape_batch(states, want=("p", "npts", "flags"))
+    d_states = torch.from_numpy(states).cuda()
+    d = dict(p=torch.zeros(n, rb.max_points, 3, dtype=torch.float64, device="cuda"),
+             npts=torch.zeros(n, dtype=torch.int32, device="cuda"),
+             flags=torch.zeros(n, dtype=torch.int32, device="cuda"))
+    rb.shape_batch_dev(d_states, n, d)
+    ctx.synchronize()
+    assert np.array_equal(d["p"].cpu().numpy(), host["p"])
+    assert np.array_equal(d["npts"].cpu().numpy(), host["npts"])
+    assert np.array_equal(d["flags"].cpu().numpy().view(np.uint32), host["flags"])
+
+
+# ---------------------------------------------------------------------------------------------
+# K2 vertex mode
+# ---------------------------------------------------------------------------------------------
+def _csr_flips(got, want):
+    """number of differing voxels between two CSR stores (0 when bit-exact)"""
+    go, gk, gb = got
+    wo, wk, wb = want
+    if np.array_equal(go, wo) and np.array_equal(gk, wk) and np.array_equal(gb, wb):
+        return 0
+    flips = 0
+    for i in range(len(wo) - 1):
+        a = dict(zip(gk[int(go[i]):int(go[i + 1])].tolist(), gb[int(go[i]):int(go[i + 1])].tolist()))
+        b = dict(zip(wk[int(wo[i]):int(wo[i + 1])].tolist(), wb[int(wo[i]):int(wo[i + 1])].tolist()))
+        for k in set(a) | set(b):
+            flips += bin(a.get(k, 0) ^ b.get(k, 0)).count("1")
+    return max(flips, 1)
+
+
+@pytest.mark.parametrize("robot,rotated", [("a", False), ("b", False), ("b", True)])
+def test_vertex_voxel_sets_bit_exact(irt, ctx, orc, wl, robot, rotated):
+    spec = wl.robot_a(0.003) if robot == "a" else wl.robot_b(0.003)
+    g = wl.workspace_grid(spec)
+    inv_rot = np.eye(3)
+    if rotated:
+        c, s = np.cos(0.3), np.sin(0.3)
+        inv_rot = np.array([[c, 0, s], [0, 1, 0], [-s, 0, c]]) @ np.array([[1, 0, 0], [0, c, -s], [0, s, c]])
+    states = wl.sample_states(spec, 3000, stream=41)
+    rb = irt.Robot(ctx, spec)
+    store = irt.SetStore(ctx, irt.make_grid(g["Ng"], g["lim"], inv_rot))
+    flags, tips = store.voxelize_vertices(rb, states)
+    ogrid = orc.grid(g["Ng"], g["lim"], inv_rot)
+    ostore, oflags = orc.voxelize_vertices_batch(orc.robot(spec), ogrid, states)
+    assert np.array_equal(flags, oflags)
+    assert _csr_flips(store.export_csr(), ostore.export()) == 0
+    ref = orc.fk_batch(orc.robot(spec), states, rb.max_points, want_p=False)
+    assert np.abs(tips - ref["tip"]).max() < FK_REL_TOL * spec["L"]
+    assert store.num_sets == 3000 and store.num_blocks == int(ostore.export()[0][-1])
+
+
+def test_vertex_voxel_sets_invalid_and_empty(irt, ctx, orc, wl):
+    spec = wl.robot_a(0.003)
+    spec["E"] = 1.0e6  # many invalid shapes -> empty sets + flags
+    g = wl.workspace_grid(spec)
+    grid = irt.make_grid(g["Ng"], g["lim"])
+    states = wl.sample_states(spec, 1500, stream=42)
+    rb = irt.Robot(ctx, spec)
+    store = irt.SetStore(ctx, grid)
+    flags, _ = store.voxelize_vertices(rb, states)
+    ostore, oflags = orc.voxelize_vertices_batch(orc.robot(spec), orc.grid(g["Ng"], g["lim"]), states)
+    assert np.array_equal(flags, oflags) and (flags != 0).sum() > 50
+    assert _csr_flips(store.export_csr(), ostore.export()) == 0
+    off = store.export_csr()[0]
+    assert np.all((off[1:] - off[:-1])[flags != 0] == 0)
+    # empty batch
+    store.voxelize_vertices(rb, np.zeros((0, 4)))
+    assert store.num_sets == 0 and store.num_blocks == 0
+    # dL coarser than the voxels: VoxelBackboneValidityChecker ctor throws std::invalid_argument
+    coarse = irt.Robot(ctx, wl.robot_a(0.005))
+    with pytest.raises(irt.IrtError) as ei:
+        store.voxelize_vertices(coarse, wl.sample_states(wl.robot_a(0.005), 4))
+    assert ei.value.status == irt.IRT_ERR_INVALID_ARGUMENT
+
+
+# ---------------------------------------------------------------------------------------------
+# K2 edge mode
+# ---------------------------------------------------------------------------------------------
+def _edges(wl, spec, n_vertices, k, stream, max_edges):
+    states = wl.sample_states(spec, n_vertices, stream=stream)
+    pairs = wl.knn_edges(spec, states, k=k)[:max_edges]
+    return states[pairs[:, 0]].copy(), states[pairs[:, 1]].copy()
+
+
+@pytest.mark.parametrize("robot", ["a", "b", "brot"])
+def test_edge_swept_volumes_bit_exact(irt, ctx, orc, wl, robot):
+    spec = {"a": wl.robot_a(0.003), "b": wl.robot_b(0.003), "brot": wl.robot_b(0.003, rotation=True)}[robot]
+    g = wl.workspace_grid(spec)
+    a, b = _edges(wl, spec, 400, 4, 51, 600)
+    rb = irt.Robot(ctx, spec)
+    store = irt.SetStore(ctx, irt.make_grid(g["Ng"], g["lim"]))
+    info = store.voxelize_edges(rb, irt.make_space(), a, b)
+    ostore, oinfo = orc.voxelize_edges_batch(orc.robot(spec), orc.grid(g["Ng"], g["lim"]), orc.space(), a, b)
+    assert np.array_equal(info["flags"], oinfo["flags"])
+    assert np.array_equal(info["t_last"], oinfo["t_last"])
+    fully = (oinfo["flags"] & irt.FLAG_PARTIAL) == 0
+    # below the first invalid t the sample set equals the reference's depth-first one, so for
+    # fully valid edges even the FK-sample count must agree
+    assert np.array_equal(info["nsamples"][fully], oinfo["nsamples"][fully])
+    assert _csr_flips(store.export_csr(), ostore.export()) == 0
+    assert info["nsamples"].mean() > 2.5, "fixture must exercise the bisection"
+
+
+def test_edge_partial_validity(irt, ctx, orc, wl):
+    """edges that run into invalid configurations: PARTIAL flag, t_last and the voxels of the
+    valid prefix agree with the reference's LIFO order"""
+    spec = wl.robot_a(0.003)
+    spec["E"] = 1.4e6
+    g = wl.workspace_grid(spec)
+    a, b = _edges(wl, spec, 300, 4, 52, 500)
+    rb = irt.Robot(ctx, spec)
+    store = irt.SetStore(ctx, irt.make_grid(g["Ng"], g["lim"]))
+    info = store.voxelize_edges(rb, irt.make_space(), a, b)
+    ostore, oinfo = orc.voxelize_edges_batch(orc.robot(spec), orc.grid(g["Ng"], g["lim"]), orc.space(), a, b)
+    assert (oinfo["flags"] & irt.FLAG_PARTIAL).sum() > 20, "fixture must contain partial edges"
+    assert np.array_equal(info["flags"], oinfo["flags"])
+    assert np.array_equal(info["t_last"], oinfo["t_last"])
+    assert _csr_flips(store.export_csr(), ostore.export()) == 0
+    assert np.all(info["nsamples"] >= oinfo["nsamples"])  # level-synchronous order may add samples past t*
+
+
+def test_edge_degenerate_inputs(irt, ctx, orc, wl):
+    spec = wl.robot_b(0.003)
+    g = wl.workspace_grid(spec)
+    rb = irt.Robot(ctx, spec)
+    store = irt.SetStore(ctx, irt.make_grid(g["Ng"], g["lim"]))
+    x = wl.sample_states(spec, 3, stream=53)
+    a = np.stack([x[0], x[1], x[2]])
+    b = np.stack([x[0], x[1] + 1e-9, x[2]])  # identical endpoints: nseg = 0 -> threshold = inf
+    info = store.voxelize_edges(rb, irt.make_space(), a, b)
+    ostore, oinfo = orc.voxelize_edges_batch(orc.robot(spec), orc.grid(g["Ng"], g["lim"]), orc.space(), a, b)
+    assert np.array_equal(info["nsamples"], oinfo["nsamples"]) and np.all(info["nsamples"] == 2)
+    assert _csr_flips(store.export_csr(), ostore.export()) == 0
+    store.voxelize_edges(rb, irt.make_space(), np.zeros((0, 7)), np.zeros((0, 7)))
+    assert store.num_sets == 0
+    assert rb.valid_segment_count(irt.make_space(), x[0], x[1]) == orc.valid_segment_count(
+        orc.robot(spec), orc.space(), x[0], x[1])
+
+
+# ---------------------------------------------------------------------------------------------
+# K3
+# ---------------------------------------------------------------------------------------------
+def _oracle_env(orc, wl, ogrid, env_blocks, Nb):
+    oenv = orc.octree(ogrid)
+    nz = np.nonzero(env_blocks)[0]
+    bx, by, bz = wl.morton_decode(nz.astype(np.uint32), Nb)
+    for x, y, z, k in zip(bx.tolist(), by.tolist(), bz.tolist(), nz.tolist()):
+        oenv.set_block(x, y, z, int(env_blocks[k]))
+    return oenv
+
+
+def test_check_sets_vs_tree_recursion(irt, ctx, orc, wl):
+    spec = wl.robot_b(0.003)
+    g = wl.workspace_grid(spec)
+    Nb = g["Ng"] // 4
+    grid = irt.make_grid(g["Ng"], g["lim"])
+    ogrid = orc.grid(g["Ng"], g["lim"])
+    states = wl.sample_states(spec, 6000, stream=61)
+    ostore, _ = orc.voxelize_vertices_batch(orc.robot(spec), ogrid, states)
+    env_blocks = wl.dense_to_morton_blocks(wl.lung_like_env_dense(spec, g))
+    frac = np.count_nonzero(env_blocks) / env_blocks.size
+    assert 0.005 < frac < 0.2
+    oenv = _oracle_env(orc, wl, ogrid, env_blocks, Nb)
+    want = orc.check_sets_batch(ostore, oenv).astype(bool)
+    assert 0.02 < want.mean() < 0.98, "fixture must mix colliding and free sets"
+    # device store imported from the oracle's CSR (the .rmp-style import path)
+    store = irt.SetStore(ctx, grid)
+    off, keys, bits = ostore.export()
+    store.import_csr(off, keys, bits)
+    env = irt.Env(ctx, grid)
+    env.update(env_blocks)
+    assert env.nblocks() == np.count_nonzero(env_blocks) == oenv.nblocks()
+    got = store.check(env)
+    assert np.array_equal(got, want)
+    # ragged sub-ranges (heads/tails not multiple of 4 leaves or 32 sets)
+    for lo, hi in ((0, 1), (1, 2), (5, 37), (33, 4097), (5999, 6000), (100, 100)):
+        assert np.array_equal(store.check(env, lo, hi), want[lo:hi])
+    # popcount checksum against numpy
+    vox, hits = store.popcount(env)
+    x = bits & env_blocks[keys]
+    assert hits == int(np.count_nonzero(x))
+    assert vox == int(sum(bin(int(v)).count("1") for v in x[x != 0]))
+    # round trip
+    o2, k2, b2 = store.export_csr()
+    assert np.array_equal(o2, off) and np.array_equal(k2, keys) and np.array_equal(b2, bits)
+    # sparse environment upload (visit_leaves style) gives the same verdicts
+    bxyz, ebits = oenv.export()
+    env2 = irt.Env(ctx, grid)
+    env2.update_sparse(bxyz, ebits)
+    assert np.array_equal(store.check(env2), want)
+    # algorithmic bytes formula of SURVEY 8(d)
+    assert store.algorithmic_bytes() == 12 * len(keys) + 8 * 6000 + 8 * Nb ** 3 + (6000 + 7) // 8
+
+
+def test_check_sets_edge_cases(irt, ctx, wl):
+    g = dict(Ng=16, lim=[0, 1, 0, 1, 0, 1])
+    grid = irt.make_grid(g["Ng"], g["lim"])
+    store = irt.SetStore(ctx, grid)
+    env = irt.Env(ctx, grid)
+    Nb = 4
+    blocks = np.zeros(Nb ** 3, dtype=np.uint64)
+    blocks[5] = 1 << 63
+    blocks[63] = 1
+    env.update(blocks)
+    # sets: empty, hit on high bit, miss on same block, hit in last block, empty, zero-bits leaf
+    off = np.array([0, 0, 1, 2, 4, 4, 5], dtype=np.uint64)
+    keys = np.array([5, 5, 10, 63, 63], dtype=np.uint32)
+    bits = np.array([1 << 63, 1 << 62, 7, 3, 0], dtype=np.uint64)
+    store.import_csr(off, keys, bits)
+    assert store.check(env).tolist() == [False, True, False, True, False, False]
+    env.update(np.zeros(Nb ** 3, dtype=np.uint64))
+    assert not store.check(env).any()
+    env.update(np.full(Nb ** 3, 2 ** 64 - 1, dtype=np.uint64))
+    assert store.check(env).tolist() == [False, True, True, True, False, False]
+    # empty store
+    store.import_csr(np.zeros(1, dtype=np.uint64), np.zeros(0, dtype=np.uint32), np.zeros(0, dtype=np.uint64))
+    assert store.check(env).size == 0
+    # grid-size mismatch -> std::invalid_argument (VoxelOctree.cpp:46-53)
+    env32 = irt.Env(ctx, irt.make_grid(32, g["lim"]))
+    store.import_csr(off, keys, bits)
+    with pytest.raises(irt.IrtError) as ei:
+        store.check(env32)
+    assert ei.value.status == irt.IRT_ERR_INVALID_ARGUMENT
+    # key outside the grid is rejected at import
+    with pytest.raises(irt.IrtError):
+        store.import_csr(np.array([0, 1], dtype=np.uint64), np.array([64], dtype=np.uint32),
+                         np.array([1], dtype=np.uint64))
+
+
+def test_check_sets_other_grid_sizes(irt, ctx, wl):
+    """Ng = 4 (single leaf) up to 512 (occupancy bitmap too large for shared memory)"""
+    rng = np.random.default_rng(7)
+    for Ng in (4, 8, 64, 256, 512):
+        Nb = Ng // 4
+        grid = irt.make_grid(Ng, [0, 1, 0, 1, 0, 1])
+        nkeys = Nb ** 3
+        env_blocks = np.zeros(nkeys, dtype=np.uint64)
+        occ = rng.choice(nkeys, size=max(1, nkeys // 20), replace=False)
+        env_blocks[occ] = rng.integers(1, 2 ** 63, size=len(occ), dtype=np.uint64)
+        n_sets = 500
+        sizes = rng.integers(0, min(30, nkeys) + 1, size=n_sets)
+        off = np.concatenate([[0], np.cumsum(sizes)]).astype(np.uint64)
+        keys = np.concatenate([np.sort(rng.choice(nkeys, size=s, replace=False)) for s in sizes] + [np.zeros(0, dtype=np.int64)]).astype(np.uint32)
+        bits = rng.integers(1, 2 ** 63, size=len(keys), dtype=np.uint64)
+        want = np.array([np.any(bits[int(off[i]):int(off[i + 1])] & env_blocks[keys[int(off[i]):int(off[i + 1])]])
+                         for i in range(n_sets)])
+        store = irt.SetStore(ctx, grid)
+        store.import_csr(off, keys, bits)
+        env = irt.Env(ctx, grid)
+        env.update(env_blocks)
+        assert np.array_equal(store.check(env), want), Ng
+
+
+# ---------------------------------------------------------------------------------------------
+# size-independent properties at BASELINE.json's full sizes
+# ---------------------------------------------------------------------------------------------
+def test_full_size_fk_properties(irt, ctx, wl):
+    """1M configurations (config C2): rotation equivariance and zero-tension home shape"""
+    spec = wl.robot_b(0.005, rotation=True)
+    rb = irt.Robot(ctx, spec)
+    n = 1 << 20
+    st = wl.sample_states(spec, n, stream=71)
+    st0 = st.copy()
+    st0[:, 6] = 0.0
+    a = rb.shape_batch(st, want=("tip", "npts", "L_i"))
+    b = rb.shape_batch(st0, want=("tip", "npts", "L_i"))
+    c, s = np.cos(st[:, 6]), np.sin(st[:, 6])
+    rot = np.stack([c * b["tip"][:, 0] - s * b["tip"][:, 1], s * b["tip"][:, 0] + c * b["tip"][:, 1], b["tip"][:, 2]], axis=1)
+    assert np.abs(a["tip"] - rot).max() < 1e-12
+    assert np.array_equal(a["npts"], b["npts"]) and np.array_equal(a["L_i"], b["L_i"])
+    # tip never farther than the unretracted length; node count follows the retraction
+    assert np.all(np.linalg.norm(a["tip"], axis=1) <= spec["L"] - st[:, 7] + 1e-9)
+    k = np.floor((spec["L"] - st[:, 7]) / spec["dL"] - 0.5).astype(int) + 2
+    assert np.abs(a["npts"] - k).max() <= 1
+    z = st.copy()
+    z[:, :6] = 0.0
+    h = rb.shape_batch(z, want=("tip", "L_i", "npts"))
+    m = h["npts"] > 1  # L - dL/2 < s < L gives the reference's single-point grid {s}: nothing integrated
+    assert np.abs(np.linalg.norm(h["tip"], axis=1) - (spec["L"] - st[:, 7]))[m].max() < 1e-12
+    assert np.abs(h["L_i"] - rb.home_lengths(z))[m].max() < 1e-12
+    assert np.all(h["tip"][~m] == 0)
+
+
+def test_full_size_check_properties(irt, ctx, wl):
+    """10M synthetic sets (config C4 scale): monotonicity in the environment, idempotence,
+    all-ones / all-zeros environments, checksum of checksums"""
+    rng = np.random.default_rng(8)
+    Ng, Nb = 128, 32
+    grid = irt.make_grid(Ng, [-0.21, 0.21] * 3)
+    n_sets = 2_000_000
+    sizes = rng.integers(5, 60, size=n_sets)
+    off = np.concatenate([[0], np.cumsum(sizes)]).astype(np.uint64)
+    nb = int(off[-1])
+    keys = rng.integers(0, Nb ** 3, size=nb, dtype=np.uint32)
+    bits = rng.integers(1, 2 ** 63, size=nb, dtype=np.uint64)
+    store = irt.SetStore(ctx, grid)
+    store.import_csr(off, keys, bits)
+    env = irt.Env(ctx, grid)
+    e1 = np.zeros(Nb ** 3, dtype=np.uint64)
+    occ = rng.choice(Nb ** 3, size=Nb ** 3 // 25, replace=False)
+    e1[occ] = rng.integers(1, 2 ** 62, size=len(occ), dtype=np.uint64)
+    e2 = e1.copy()
+    more = rng.choice(Nb ** 3, size=Nb ** 3 // 25, replace=False)
+    e2[more] |= rng.integers(1, 2 ** 62, size=len(more), dtype=np.uint64)
+    env.update(e1)
+    v1 = store.check(env)
+    assert np.array_equal(v1, store.check(env))            # idempotent
+    vox, hits = store.popcount(env)
+    x = bits & e1[keys]
+    assert hits == int(np.count_nonzero(x))                 # checksum of checksums
+    seg = np.add.reduceat((x != 0).astype(np.int64), off[:-1].astype(np.int64))
+    assert np.array_equal(v1, seg > 0)
+    env.update(e2)
+    v2 = store.check(env)
+    assert np.all(v2 | ~v1)                                 # env1 subset env2 -> v1 implies v2
+    env.update(np.zeros(Nb ** 3, dtype=np.uint64))
+    assert not store.check(env).any()
+    env.update(np.full(Nb ** 3, 2 ** 64 - 1, dtype=np.uint64))
+    assert store.check(env).all()
