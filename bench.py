@@ -1,0 +1,409 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the B200-native interactive-rate-tendons hot path.
+
+  python bench.py --gpus N --steps K --warmup W            (this repo's CUDA path)
+  python bench.py --impl reference --gpus N --steps K ...   (the reference algorithm on host cores)
+
+A "step" is one pass of batched forward kinematics over config C2 of BASELINE.json
+(6-tendon helical robot with retraction, 1M configurations per GPU) with inputs resident in
+HBM.  The same run also measures the roadmap voxel check (K3) over a roadmap built with the
+real pipeline, the end-to-end FK rate through the host-pointer C ABI, and the CPU baseline
+(the oracle restatement of the reference, timed on this box's host cores).
+Prints ONE JSON line on rank 0.
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+N_CONFIGS = 1_000_000          # config C2: 1M FK per GPU
+DL = 0.005
+WORKLOAD = "C2: 6-tendon helical robot, retraction (RetractionSampler), dL=0.005, 1M configs/GPU"
+
+
+def flops_per_shape(n_tendons, mean_steps, mean_iters):
+    """F_shape = n_steps * (4 * (346 + 162 N) + 13 (19 + N)) + iters * (30 + 46 N)"""
+    N = n_tendons
+    return mean_steps * (4 * (346 + 162 * N) + 13 * (19 + N)) + mean_iters * (30 + 46 * N)
+
+
+class ClockSampler(threading.Thread):
+    """samples SM clock and throttle reasons during the timed region (pynvml)"""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.stop_flag, self.samples, self.reasons = index, False, [], set()
+        self.max_mhz = None
+        self.ok = False
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.ok = True
+        except Exception:
+            self.ok = False
+
+    def run(self):
+        if not self.ok:
+            return
+        nv = self.nv
+        names = {
+            getattr(nv, "nvmlClocksThrottleReasonHwSlowdown", 0x8): "hw_slowdown",
+            getattr(nv, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40): "hw_thermal_slowdown",
+            getattr(nv, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20): "sw_thermal_slowdown",
+            getattr(nv, "nvmlClocksThrottleReasonSwPowerCap", 0x4): "sw_power_cap",
+        }
+        while not self.stop_flag:
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, name in names.items():
+                    if r & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(0.02)
+
+    def result(self):
+        if not self.ok or not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": ["unavailable"]}
+        return {"sm_mhz": float(np.median(self.samples)), "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons)}
+
+
+def cpu_fk_rate(spec, n_tendons, seconds, threads=None, stream=900):
+    """oracle (restatement of the reference CPU path, -O3 -march=native -fopenmp) timed on a
+    bounded sample of the SAME workload; loop shape = apps/estimate_length_discretization.cpp:62-71"""
+    from oracle.oracle import Oracle, build
+    import irt_b200.workloads as wl
+    build()
+    orc = Oracle("fast")
+    rb = orc.robot(spec)
+    nt = threads or orc.max_threads()
+    batch = 20000
+    done, t0 = 0, time.perf_counter()
+    cap = len(orc.t_range(0.0, spec["L"], spec["dL"]))
+    k = 0
+    while True:
+        st = wl.sample_states(spec, batch, stream=stream + k)
+        orc.fk_batch(rb, st, cap, nthreads=nt)
+        done += batch
+        k += 1
+        el = time.perf_counter() - t0
+        if el >= seconds:
+            break
+    return done / el, nt, done, el
+
+
+def knn_edges_gpu(torch, states_np, spec, k, device):
+    """undirected k-nearest-neighbour edges under the compound-space metric of Problem.cpp:118-141
+    (exact, brute force on the GPU with torch: benchmark INPUT generation, not the hot path)."""
+    import irt_b200.workloads as wl
+    w = wl.space_weights(spec)
+    N = len(spec["C"])
+    x = torch.from_numpy(states_np).to(device)
+    tau = x[:, :N].float()
+    ret = x[:, -1].float() if spec["enable_retraction"] else None
+    sq = (tau * tau).sum(1)
+    n = x.shape[0]
+    out = []
+    blk = max(256, min(8192, (1 << 31) // max(n, 1)))
+    for s in range(0, n, blk):
+        e = min(n, s + blk)
+        d2 = sq[s:e, None] + sq[None, :] - 2.0 * tau[s:e] @ tau.T
+        d = d2.clamp_min_(0).sqrt_()
+        if ret is not None:
+            d += w["w_ret"] * (ret[s:e, None] - ret[None, :]).abs()
+        d[torch.arange(e - s, device=device), torch.arange(s, e, device=device)] = float("inf")
+        nb = torch.topk(d, k, dim=1, largest=False).indices
+        src = torch.arange(s, e, device=device).repeat_interleave(k)
+        out.append(torch.stack([src, nb.reshape(-1)], dim=1))
+    pr = torch.cat(out, 0)
+    pr = torch.sort(pr, dim=1).values
+    pr = torch.unique(pr, dim=0)
+    return pr.cpu().numpy().astype(np.int64)
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the reference's own CPU implementation of the path.  The reference cannot
+    be compiled in this image (Eigen3/Boost.odeint/OMPL/FCL/ITK absent), so this arm times the
+    oracle port (line-for-line restatement) with all host threads, on bounded samples."""
+    if rank != 0:
+        return
+    import irt_b200.workloads as wl
+    spec = wl.robot_b(DL)
+    per_step = max(2.0, min(20.0, 120.0 / max(1, args.steps + args.warmup)))
+    rates = []
+    for i in range(args.warmup + args.steps):
+        r, nt, done, el = cpu_fk_rate(spec, 6, per_step, stream=1000 + 10 * i)
+        if i >= args.warmup:
+            rates.append((r, done, el))
+    value = float(np.mean([r for r, _, _ in rates]))
+    done = int(np.mean([d for _, d, _ in rates]))
+    line = {
+        "impl": "reference", "metric": "fk_shapes_per_s", "value": value, "unit": "shapes/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * float(np.mean([e for _, _, e in rates])),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic",
+        "config": {"workload": WORKLOAD, "n_configs_per_step": done,
+                   "note": "bounded sample of the same workload per step"},
+        "cpu_baseline": {"value": value, "unit": "shapes/s", "cores": nt, "kind": "port",
+                         "sample": "%d configs per step (~%.0f s), OpenMP over configs" % (done, per_step)},
+        "e2e": {"value": value, "unit": "shapes/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--roadmap-vertices", type=int, default=100_000,
+                    help="vertices of the roadmap used for the K3 sweep (k=10 nearest-neighbour edges)")
+    ap.add_argument("--cpu-seconds", type=float, default=12.0)
+    ap.add_argument("--skip-roadmap", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+    args.warmup = max(args.warmup, 3)
+
+    import torch
+    import torch.distributed as dist
+    import irt_b200
+    import irt_b200.workloads as wl
+    from irt_b200.roadmap import VoxelCachedLazyPRM, shard_words, gather_verdict_words
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def sum_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
+
+    ctx = irt_b200.Context(local_rank)
+    stream = torch.cuda.current_stream(dev)
+    sptr = stream.cuda_stream
+    fp64_peak = ctx.fp64_peak()
+
+    # ---------------- K1: batched FK, config C2 ----------------------------------------------
+    spec = wl.robot_b(DL)
+    rb = irt_b200.Robot(ctx, spec)
+    n = N_CONFIGS
+    states = wl.sample_states(spec, n, stream=100 + rank)
+    d_states = torch.from_numpy(states).to(dev)
+    cap = rb.max_points
+    outs = dict(p=torch.zeros(n, cap, 3, dtype=torch.float64, device=dev),
+                npts=torch.zeros(n, dtype=torch.int32, device=dev),
+                L=torch.zeros(n, dtype=torch.float64, device=dev),
+                L_i=torch.zeros(n, rb.n_tendons, dtype=torch.float64, device=dev),
+                iters=torch.zeros(n, dtype=torch.int32, device=dev),
+                nsteps=torch.zeros(n, dtype=torch.int32, device=dev))
+    flush = torch.empty(512 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
+
+    def fk_step():
+        rb.shape_batch_dev(d_states, n, outs, stream=sptr)
+
+    for _ in range(args.warmup):
+        flush.zero_()
+        fk_step()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    launches0 = ctx.launch_count()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    t_wall0 = time.perf_counter()
+    for a, b in ev:
+        flush.zero_()            # L2 flush between timed iterations (outside the event pair)
+        a.record(stream)
+        fk_step()
+        b.record(stream)
+    barrier()
+    t_wall = time.perf_counter() - t_wall0
+    launches = ctx.launch_count() - launches0
+    sampler.stop_flag = True
+    sampler.join()
+    ms_local = float(np.mean([a.elapsed_time(b) for a, b in ev]))
+    ms = max_over_ranks(ms_local)
+    value = world * n / (ms * 1e-3)
+    mean_steps = float(outs["nsteps"].double().mean().item())
+    mean_iters = float(outs["iters"].double().mean().item())
+    fshape = flops_per_shape(rb.n_tendons, mean_steps, mean_iters)
+    achieved = n * fshape / (ms_local * 1e-3) / 1e12
+    prof = {}
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            prof = json.load(f)
+    except Exception:
+        pass
+    roofline = {"bound": "fp64", "kernel": "fk_rk4_fp64_kernel<6,true>", "achieved": achieved,
+                "peak": fp64_peak / 1e12, "unit": "TFLOP/s", "frac": achieved / (fp64_peak / 1e12),
+                "traffic": prof.get("fk_dram_bytes_per_launch"),
+                "peak_source": "live DFMA-chain probe on this GPU (MEASURED_PEAKS.json has no FP64 entry)",
+                "flop_per_shape": fshape, "mean_rk4_steps": mean_steps, "mean_fixed_point_iters": mean_iters,
+                "note": "duration = whole step (3 bucket-sort launches + the RK4 kernel)"}
+
+    # ---------------- e2e: host-pointer C ABI, pinned buffers, H2D + D2H inside ----------------
+    h_states = torch.from_numpy(states).pin_memory()
+    h_out = dict(p=torch.zeros(n, cap, 3, dtype=torch.float64).pin_memory(),
+                 npts=torch.zeros(n, dtype=torch.int32).pin_memory(),
+                 L=torch.zeros(n, dtype=torch.float64).pin_memory(),
+                 L_i=torch.zeros(n, rb.n_tendons, dtype=torch.float64).pin_memory())
+    o = irt_b200.FkOutputs()
+    for kname, t in h_out.items():
+        setattr(o, kname, t.data_ptr())
+    import ctypes as C
+
+    def e2e_step():
+        ctx.check(ctx.L.irt_fk_batch(ctx.h, rb.h, C.c_void_p(h_states.data_ptr()), rb.state_size, n, cap, C.byref(o)))
+
+    e2e_step()
+    barrier()
+    e2e_steps = max(2, min(args.steps, 5))
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        e2e_step()
+    barrier()
+    e2e_s = max_over_ranks((time.perf_counter() - t0) / e2e_steps)
+    h2d = n * rb.state_size * 8
+    d2h = n * (cap * 24 + 4 + 8 + rb.n_tendons * 8)
+    e2e = {"value": world * n / e2e_s, "unit": "shapes/s", "h2d_bytes_per_step": h2d,
+           "d2h_bytes_per_step": d2h, "ms_per_step": e2e_s * 1e3,
+           "api": "irt_fk_batch (host pointers, pinned), outputs p/npts/L/L_i"}
+    # parity spot check of the timed outputs against each other (device path == host path)
+    same = bool(torch.equal(h_out["npts"], outs["npts"].cpu()))
+
+    # ---------------- K3: roadmap voxel check ---------------------------------------------------
+    edge_check = None
+    if not args.skip_roadmap:
+        spec3 = wl.robot_b(0.003)
+        rb3 = irt_b200.Robot(ctx, spec3)
+        g = wl.workspace_grid(spec3)
+        grid = irt_b200.make_grid(g["Ng"], g["lim"], g["inv_rot"])
+        prm = VoxelCachedLazyPRM(ctx, rb3, grid, rank=rank, world=world, dist=dist if world > 1 else None)
+        nv = args.roadmap_vertices
+        t_build0 = time.perf_counter()
+        prm.createRoadmap(nv, lambda cnt, rnd: wl.sample_states(spec3, cnt, stream=200 + rnd),
+                          lambda st: knn_edges_gpu(torch, st, spec3, 10, dev))
+        t_sample = time.perf_counter() - t_build0
+        t1 = time.perf_counter()
+        prm.precomputeVertexVoxelCache()
+        t_vvox = time.perf_counter() - t1
+        t1 = time.perf_counter()
+        einfo = prm.precomputeEdgeVoxelCache()
+        t_evox = time.perf_counter() - t1
+        env_blocks = wl.dense_to_morton_blocks(wl.lung_like_env_dense(spec3, g))
+        prm.setEnvironment(env_blocks)
+        ne = len(prm.edges)
+        lo, hi = prm.shard(ne)
+        w = shard_words(ne, world)
+        d_words = torch.zeros(max(w, 1), dtype=torch.int32, device=dev)
+
+        def k3_step():
+            if hi > lo:
+                prm.edge_store.check_dev(prm.env, d_words, 0, hi - lo, stream=sptr)
+            return gather_verdict_words(d_words, dist if world > 1 else None)
+
+        for _ in range(args.warmup):
+            flush.zero_()
+            k3_step()
+        barrier()
+        ev3 = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+        for a, b in ev3:
+            flush.zero_()
+            a.record(stream)
+            k3_step()
+            b.record(stream)
+        barrier()
+        ms3_local = float(np.mean([a.elapsed_time(b) for a, b in ev3]))
+        ms3 = max_over_ranks(ms3_local)
+        alg_bytes = prm.edge_store.algorithmic_bytes() if hi > lo else 0
+        hbm_peak = 6552.0
+        try:
+            with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+                hbm_peak = float(json.load(f)["hbm_gbs"])
+            hbm_src = "MEASURED_PEAKS.json hbm_gbs (of measured)"
+        except Exception:
+            hbm_peak, hbm_src = 6650.0, "fallback 6.65 TB/s (of fallback)"
+        ach3 = alg_bytes / (ms3_local * 1e-3) / 1e9
+        nblk = prm.edge_store.num_blocks
+        edge_check = {
+            "metric": "roadmap_voxel_edge_checks_per_s", "value": ne / (ms3 * 1e-3), "unit": "edges/s",
+            "ms_per_sweep": ms3, "scaling": "strong", "n_vertices": len(prm.states), "n_edges": ne,
+            "edges_this_rank": hi - lo, "blocks_per_edge": nblk / max(1, hi - lo),
+            "fk_samples_per_edge": float(np.mean(einfo["nsamples"])) if hi > lo else None,
+            "collision_fraction": None,
+            "build_s": {"sample_valid_vertices_and_knn": t_sample, "vertex_voxel_cache": t_vvox,
+                        "edge_voxel_cache": t_evox,
+                        "edges_per_s_K1K2": (hi - lo) / t_evox if t_evox > 0 else None},
+            "roofline": {"bound": "hbm", "kernel": "voxel_and_popc_kernel", "achieved": ach3, "peak": hbm_peak,
+                         "unit": "GB/s", "frac": ach3 / hbm_peak, "traffic": prof.get("k3_dram_bytes_per_launch"),
+                         "peak_source": hbm_src, "algorithmic_bytes": alg_bytes,
+                         "note": "duration includes the verdict memset and (N>1) the NCCL all_gather"},
+        }
+        verd = prm.precomputeEdgeValidity()
+        edge_check["collision_fraction"] = float(1.0 - verd.mean())
+
+    # ---------------- CPU baseline (rank 0 at N=1 only) ------------------------------------------
+    cpu = None
+    if rank == 0 and world == 1 and args.cpu_seconds > 0:
+        rate, nt, done, el = cpu_fk_rate(spec, rb.n_tendons, args.cpu_seconds)
+        cpu = {"value": rate, "unit": "shapes/s", "cores": nt, "kind": "port",
+               "sample": "%d configs of the same workload in %.1f s (oracle -O3 -march=native -fopenmp)" % (done, el)}
+
+    if rank == 0:
+        line = {
+            "metric": "fk_shapes_per_s", "value": value, "unit": "shapes/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "n_configs_per_gpu": n, "state_size": rb.state_size,
+                       "max_points": cap, "seed": wl.SEED,
+                       "l2": "512 MB flush write between timed steps; outputs (%.0f MB) exceed L2" % (n * cap * 24 / 1e6),
+                       "outputs": "p, npts, L, L_i (+iters, nsteps)"},
+            "clocks": sampler.result(), "e2e": e2e, "gpu_launches": int(launches),
+            "roofline": roofline, "cpu_baseline": cpu, "edge_check": edge_check,
+            "wall_s_timed_region": t_wall, "host_vs_device_path_equal": same,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -17,6 +17,7 @@
 struct irt_ctx {
   int device = 0;
   cudaStream_t stream = nullptr;
+  cudaStream_t copy_stream = nullptr;  // D2H of finished chunks overlaps the next chunk's kernels
   int sm_count = 148;
   std::string last_error;
   std::atomic<int64_t> launches{0};

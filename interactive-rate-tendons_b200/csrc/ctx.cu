@@ -63,7 +63,8 @@ int irt_ctx_create(int device, irt_ctx **out) {
   ctx->device = device;
   cudaDeviceProp prop;
   if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) ctx->sm_count = prop.multiProcessorCount;
-  if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) {
+  if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking) != cudaSuccess) {
     delete ctx;
     return IRT_ERR_CUDA;
   }
@@ -76,6 +77,7 @@ void irt_ctx_destroy(irt_ctx *ctx) {
   cudaSetDevice(ctx->device);
   if (ctx->scratch) cudaFree(ctx->scratch);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
+  if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
   delete ctx;
 }
 

@@ -53,66 +53,85 @@ int irt_fk_batch(irt_ctx *ctx, const irt_robot *rb, const double *states, int st
   if (rc) return rc;
   if (n == 0) return IRT_OK;
   IRT_CUDA(ctx, cudaSetDevice(ctx->device));
-  cudaStream_t st = ctx->stream;
+  cudaStream_t st = ctx->stream, cs = ctx->copy_stream;
   const int N = rb->desc.n_tendons;
-  // chunk so that device staging stays bounded (<= ~2 GiB of points per chunk)
-  const int64_t per_cfg = (int64_t)cap_pts * (3 + (out->R ? 9 : 0) + (out->t ? 1 : 0)) * 8 + 256;
-  int64_t chunk = (int64_t)(2048LL << 20) / per_cfg;
-  if (chunk < 1024) chunk = 1024;
+  // Chunked, double-buffered pipeline: the D2H copy of chunk c (copy stream) overlaps the
+  // kernels of chunk c+1 (compute stream).  With pinned host buffers the copies are truly
+  // asynchronous; with pageable buffers the runtime stages them and the overlap is partial.
+  int64_t chunk = 96 * 1024;
   if (chunk > n) chunk = n;
   const bool need_p = out->p || out->flags;
-  DevBuf d_states, d_p, d_R, d_t, d_npts, d_L, d_Li, d_tip, d_uv, d_flags, d_iters, d_nsteps;
-  bool ok = d_states.alloc((size_t)chunk * state_size * 8);
-  if (need_p) ok = ok && d_p.alloc((size_t)chunk * cap_pts * 24);
-  if (out->R) ok = ok && d_R.alloc((size_t)chunk * cap_pts * 72);
-  if (out->t) ok = ok && d_t.alloc((size_t)chunk * cap_pts * 8);
-  ok = ok && d_npts.alloc((size_t)chunk * 4);
-  if (out->L) ok = ok && d_L.alloc((size_t)chunk * 8);
-  if (out->L_i) ok = ok && d_Li.alloc((size_t)chunk * N * 8);
-  if (out->tip) ok = ok && d_tip.alloc((size_t)chunk * 24);
-  if (out->uv) ok = ok && d_uv.alloc((size_t)chunk * 96);
-  if (out->flags) ok = ok && d_flags.alloc((size_t)chunk * 4);
-  if (out->iters) ok = ok && d_iters.alloc((size_t)chunk * 4);
-  if (out->nsteps) ok = ok && d_nsteps.alloc((size_t)chunk * 4);
-  if (!ok) return irt_fail(ctx, IRT_ERR_CUDA, "device staging allocation failed");
-
-  for (int64_t off = 0; off < n; off += chunk) {
+  struct Stage {
+    DevBuf states, p, R, t, npts, L, Li, tip, uv, flags, iters, nsteps;
+    cudaEvent_t computed = nullptr, copied = nullptr;
+    ~Stage() {
+      if (computed) cudaEventDestroy(computed);
+      if (copied) cudaEventDestroy(copied);
+    }
+  } stage[2];
+  const int nstage = (n > chunk) ? 2 : 1;
+  for (int b = 0; b < nstage; b++) {
+    Stage &s = stage[b];
+    bool ok = s.states.alloc((size_t)chunk * state_size * 8);
+    if (need_p) ok = ok && s.p.alloc((size_t)chunk * cap_pts * 24);
+    if (out->R) ok = ok && s.R.alloc((size_t)chunk * cap_pts * 72);
+    if (out->t) ok = ok && s.t.alloc((size_t)chunk * cap_pts * 8);
+    ok = ok && s.npts.alloc((size_t)chunk * 4);
+    if (out->L) ok = ok && s.L.alloc((size_t)chunk * 8);
+    if (out->L_i) ok = ok && s.Li.alloc((size_t)chunk * N * 8);
+    if (out->tip) ok = ok && s.tip.alloc((size_t)chunk * 24);
+    if (out->uv) ok = ok && s.uv.alloc((size_t)chunk * 96);
+    if (out->flags) ok = ok && s.flags.alloc((size_t)chunk * 4);
+    if (out->iters) ok = ok && s.iters.alloc((size_t)chunk * 4);
+    if (out->nsteps) ok = ok && s.nsteps.alloc((size_t)chunk * 4);
+    if (!ok) return irt_fail(ctx, IRT_ERR_CUDA, "device staging allocation failed");
+    IRT_CUDA(ctx, cudaEventCreateWithFlags(&s.computed, cudaEventDisableTiming));
+    IRT_CUDA(ctx, cudaEventCreateWithFlags(&s.copied, cudaEventDisableTiming));
+  }
+  int64_t c = 0;
+  for (int64_t off = 0; off < n; off += chunk, c++) {
+    Stage &s = stage[c % nstage];
     const int64_t m = (n - off < chunk) ? (n - off) : chunk;
-    IRT_CUDA(ctx, cudaMemcpyAsync(d_states.p, states + off * state_size, (size_t)m * state_size * 8,
+    if (c >= nstage) IRT_CUDA(ctx, cudaStreamWaitEvent(st, s.copied, 0));  // buffers free again
+    IRT_CUDA(ctx, cudaMemcpyAsync(s.states.p, states + off * state_size, (size_t)m * state_size * 8,
                                   cudaMemcpyHostToDevice, st));
     irt_fk_outputs o;
     std::memset(&o, 0, sizeof(o));
-    o.p = (double *)d_p.p; o.R = (double *)d_R.p; o.t = (double *)d_t.p;
-    o.npts = (int32_t *)d_npts.p; o.L = (double *)d_L.p; o.L_i = (double *)d_Li.p;
-    o.tip = (double *)d_tip.p; o.uv = (double *)d_uv.p; o.flags = (uint32_t *)d_flags.p;
-    o.iters = (int32_t *)d_iters.p; o.nsteps = (int32_t *)d_nsteps.p;
+    o.p = (double *)s.p.p; o.R = (double *)s.R.p; o.t = (double *)s.t.p;
+    o.npts = (int32_t *)s.npts.p; o.L = (double *)s.L.p; o.L_i = (double *)s.Li.p;
+    o.tip = (double *)s.tip.p; o.uv = (double *)s.uv.p; o.flags = (uint32_t *)s.flags.p;
+    o.iters = (int32_t *)s.iters.p; o.nsteps = (int32_t *)s.nsteps.p;
     // rows beyond npts[i] are returned as zeros (deterministic padding)
     if (o.p) IRT_CUDA(ctx, cudaMemsetAsync(o.p, 0, (size_t)m * cap_pts * 24, st));
     if (o.R) IRT_CUDA(ctx, cudaMemsetAsync(o.R, 0, (size_t)m * cap_pts * 72, st));
     if (o.t) IRT_CUDA(ctx, cudaMemsetAsync(o.t, 0, (size_t)m * cap_pts * 8, st));
-    rc = fk_launch(ctx, rb, (const double *)d_states.p, m, cap_pts, o, nullptr, st);
+    rc = fk_launch(ctx, rb, (const double *)s.states.p, m, cap_pts, o, nullptr, st);
     if (rc) return rc;
     if (o.flags) {
       rc = self_collision_launch(ctx, rb, o.p, o.npts, m, cap_pts, o.flags, st);
       if (rc) return rc;
     }
+    IRT_CUDA(ctx, cudaEventRecord(s.computed, st));
+    IRT_CUDA(ctx, cudaStreamWaitEvent(cs, s.computed, 0));
 #define D2H(dst, src, bytes_per)                                                               \
   if (dst) IRT_CUDA(ctx, cudaMemcpyAsync((char *)(dst) + (size_t)off * (bytes_per), (src),      \
-                                         (size_t)m * (bytes_per), cudaMemcpyDeviceToHost, st))
-    D2H(out->p, d_p.p, (size_t)cap_pts * 24);
-    D2H(out->R, d_R.p, (size_t)cap_pts * 72);
-    D2H(out->t, d_t.p, (size_t)cap_pts * 8);
-    D2H(out->npts, d_npts.p, 4);
-    D2H(out->L, d_L.p, 8);
-    D2H(out->L_i, d_Li.p, (size_t)N * 8);
-    D2H(out->tip, d_tip.p, 24);
-    D2H(out->uv, d_uv.p, 96);
-    D2H(out->flags, d_flags.p, 4);
-    D2H(out->iters, d_iters.p, 4);
-    D2H(out->nsteps, d_nsteps.p, 4);
+                                         (size_t)m * (bytes_per), cudaMemcpyDeviceToHost, cs))
+    D2H(out->p, s.p.p, (size_t)cap_pts * 24);
+    D2H(out->R, s.R.p, (size_t)cap_pts * 72);
+    D2H(out->t, s.t.p, (size_t)cap_pts * 8);
+    D2H(out->npts, s.npts.p, 4);
+    D2H(out->L, s.L.p, 8);
+    D2H(out->L_i, s.Li.p, (size_t)N * 8);
+    D2H(out->tip, s.tip.p, 24);
+    D2H(out->uv, s.uv.p, 96);
+    D2H(out->flags, s.flags.p, 4);
+    D2H(out->iters, s.iters.p, 4);
+    D2H(out->nsteps, s.nsteps.p, 4);
 #undef D2H
-    IRT_CUDA(ctx, cudaStreamSynchronize(st));
+    IRT_CUDA(ctx, cudaEventRecord(s.copied, cs));
   }
+  IRT_CUDA(ctx, cudaStreamSynchronize(st));
+  IRT_CUDA(ctx, cudaStreamSynchronize(cs));
   return IRT_OK;
 }
 
