@@ -218,8 +218,12 @@ def main():
         return float(t.item())
 
     ctx = irt_b200.Context(local_rank)
-    stream = torch.cuda.current_stream(dev)
+    # a real (non-legacy) stream: the library treats a NULL stream as "use the context's own",
+    # and torch.cuda.Event only sees work on the stream it is recorded on
+    stream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(stream)
     sptr = stream.cuda_stream
+    assert sptr != 0
     fp64_peak = ctx.fp64_peak()
 
     # ---------------- K1: batched FK, config C2 ----------------------------------------------

@@ -82,8 +82,6 @@ struct irt_setstore {
   uint32_t *d_keys = nullptr;     // [n_blocks]
   uint64_t *d_bits = nullptr;     // [n_blocks]
   size_t cap_sets = 0, cap_blocks = 0;
-  uint32_t *d_chunk_set = nullptr;  // [n_blocks/128 + 1] id of the set holding leaf 128*c
-  size_t cap_chunks = 0;
 };
 
 int irt_fail(irt_ctx *ctx, int status, const char *fmt, ...);

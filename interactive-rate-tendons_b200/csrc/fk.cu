@@ -184,27 +184,29 @@ struct FkState {
   double Li[NT];
 };
 
-// one classic RK4 step of size h; rt0/rt1/rt2 = routing at t, t+h/2, t+h
+// one classic RK4 step of size h; rt0/rt1/rt2 = routing at t, t+h/2, t+h.
+// The four stages are a real loop (not unrolled): the hot loop body is ONE copy of vu_dot, which
+// keeps the instruction footprint inside the SM's instruction cache.
 template <int NT>
 __device__ __forceinline__ void rk4_step(FkState<NT> &x, const double (&tau)[NT],
                                          const double (&Kse)[3], const double (&Kbt)[3], double h,
-                                         const double *__restrict__ rt0,
-                                         const double *__restrict__ rt1,
-                                         const double *__restrict__ rt2) {
+                                         const double *rt0, const double *rt1, const double *rt2) {
   const double hh = 0.5 * h, w1 = h * (1.0 / 6.0), w2 = h * (1.0 / 3.0);
   double sv[3], su[3], sR[9];      // stage values
-  double aR[9], av[3], au[3];      // sum of weighted slopes (k1 + 2 k2 + 2 k3 + k4)
+  double aR[9], av[3], au[3];      // k1 + 2 k2 + 2 k3 + k4
   double vd[3], ud[3], sig[NT], Rd[9];
 #pragma unroll
-  for (int i = 0; i < 3; i++) { sv[i] = x.v[i]; su[i] = x.u[i]; }
+  for (int i = 0; i < 3; i++) { sv[i] = x.v[i]; su[i] = x.u[i]; av[i] = 0.0; au[i] = 0.0; }
 #pragma unroll
-  for (int i = 0; i < 9; i++) sR[i] = x.R[i];
+  for (int i = 0; i < 9; i++) { sR[i] = x.R[i]; aR[i] = 0.0; }
 
-#pragma unroll
+#pragma unroll 1
   for (int stage = 0; stage < 4; stage++) {
+    const bool outer = (stage == 0) || (stage == 3);
     const double *rt = (stage == 0) ? rt0 : ((stage == 3) ? rt2 : rt1);
-    const double wq = (stage == 0 || stage == 3) ? w1 : w2;    // quadrature weight
-    const double wk = (stage == 0 || stage == 3) ? 1.0 : 2.0;  // slope weight in a*
+    const double wq = outer ? w1 : w2;     // quadrature weight
+    const double wk = outer ? 1.0 : 2.0;   // slope weight
+    const double a = (stage == 2) ? h : hh;
     vu_dot<NT>(rt, tau, Kse, Kbt, sv, su, vd, ud, sig);
     // p' = R v ; L' = |v| ; L_i' = sigma_i : pure quadratures, accumulate in place
 #pragma unroll
@@ -220,23 +222,12 @@ __device__ __forceinline__ void rk4_step(FkState<NT> &x, const double (&tau)[NT]
       Rd[i + 3] = fma(sR[i + 6], su[0], -sR[i] * su[2]);
       Rd[i + 6] = fma(sR[i], su[1], -sR[i + 3] * su[0]);
     }
-    if (stage == 0) {
 #pragma unroll
-      for (int i = 0; i < 9; i++) aR[i] = Rd[i];
+    for (int i = 0; i < 9; i++) { aR[i] = fma(wk, Rd[i], aR[i]); sR[i] = fma(a, Rd[i], x.R[i]); }
 #pragma unroll
-      for (int i = 0; i < 3; i++) { av[i] = vd[i]; au[i] = ud[i]; }
-    } else {
-#pragma unroll
-      for (int i = 0; i < 9; i++) aR[i] = fma(wk, Rd[i], aR[i]);
-#pragma unroll
-      for (int i = 0; i < 3; i++) { av[i] = fma(wk, vd[i], av[i]); au[i] = fma(wk, ud[i], au[i]); }
-    }
-    if (stage < 3) {
-      const double a = (stage == 2) ? h : hh;
-#pragma unroll
-      for (int i = 0; i < 9; i++) sR[i] = fma(a, Rd[i], x.R[i]);
-#pragma unroll
-      for (int i = 0; i < 3; i++) { sv[i] = fma(a, vd[i], x.v[i]); su[i] = fma(a, ud[i], x.u[i]); }
+    for (int i = 0; i < 3; i++) {
+      av[i] = fma(wk, vd[i], av[i]); au[i] = fma(wk, ud[i], au[i]);
+      sv[i] = fma(a, vd[i], x.v[i]); su[i] = fma(a, ud[i], x.u[i]);
     }
   }
 #pragma unroll
@@ -414,55 +405,67 @@ fk_rk4_fp64_kernel(const RobotDev rb, const double *__restrict__ states, int sta
   }
 
   // ---- integrate_times(runge_kutta4) over the grid {s} U {node K-1 .. node 0} --------------
+  // Head: the irregular first gap s -> node K-1 takes one or two steps (h = min(dL, t_next - t),
+  // repeated while t_next - t > eps).  Then the regular steps node q -> node q-1.  All steps run
+  // through ONE rk4_step call site in a loop that is end-aligned across the warp, so that every
+  // lane is at the same regular step q in the same iteration (table reads are broadcasts).
   if (run) emit_node<NT>(o, cfg, cap_pts, 0, s_start, x, rz);
+  int nhead = 0;
+  double hh0 = 0.0, hh1 = 0.0;
+  const double *hd0 = head, *hd1 = head + NT * 6, *hd2 = head + 2 * NT * 6, *hd3 = head + 3 * NT * 6;
+  double rt_h1[NT * 6], rt_h2[NT * 6], rt_h3[NT * 6];
   if (integ) {
-    // irregular first gap: s -> node K-1 in one or two steps (h = min(dL, t_next - t))
     if (RETRACT) {
       const double eps = 2.220446049250313e-16;
       const double t1 = rb.node_t[K - 1];
-      double tc = s_start;
-      double h = fmin(rb.dL, t1 - tc);
-      double rt_mid[NT * 6];
-      routing_eval<NT>(rb, tc + 0.5 * h, rt_mid);
-      if (t1 - (tc + h) > eps) {
-        double rt_end[NT * 6];
-        routing_eval<NT>(rb, tc + h, rt_end);
-        rk4_step<NT>(x, tau, Kse, Kbt, h, rt_local, rt_mid, rt_end);
-        nsteps++;
-        tc += h;
-        h = fmin(rb.dL, t1 - tc);
-        routing_eval<NT>(rb, tc + 0.5 * h, rt_mid);
-        rk4_step<NT>(x, tau, Kse, Kbt, h, rt_end, rt_mid, tab + (size_t)(2 * (K - 1)) * NT * 6);
-        nsteps++;
-      } else {
-        rk4_step<NT>(x, tau, Kse, Kbt, h, rt_local, rt_mid, tab + (size_t)(2 * (K - 1)) * NT * 6);
-        nsteps++;
+      hh0 = fmin(rb.dL, t1 - s_start);
+      routing_eval<NT>(rb, s_start + 0.5 * hh0, rt_h1);
+      nhead = 1;
+      if (t1 - (s_start + hh0) > eps) {
+        const double tc = s_start + hh0;
+        hh1 = fmin(rb.dL, t1 - tc);
+        routing_eval<NT>(rb, tc, rt_h2);
+        routing_eval<NT>(rb, tc + 0.5 * hh1, rt_h3);
+        nhead = 2;
       }
+      hd0 = rt_local; hd1 = rt_h1; hd2 = rt_h2; hd3 = rt_h3;
     } else {
-      const double *end = tab + (size_t)(2 * (K - 1)) * NT * 6;
-      if (rb.n_head == 4) {
-        rk4_step<NT>(x, tau, Kse, Kbt, rb.head_h[0], head, head + NT * 6, head + 2 * NT * 6);
-        rk4_step<NT>(x, tau, Kse, Kbt, rb.head_h[1], head + 2 * NT * 6, head + 3 * NT * 6, end);
-        nsteps += 2;
-      } else {
-        rk4_step<NT>(x, tau, Kse, Kbt, rb.head_h[0], head, head + NT * 6, end);
-        nsteps++;
-      }
+      nhead = (rb.n_head == 4) ? 2 : 1;
+      hh0 = rb.head_h[0];
+      hh1 = rb.head_h[1];
     }
-    emit_node<NT>(o, cfg, cap_pts, 1, rb.node_t[K - 1], x, rz);
   }
-  // regular steps node q -> node q-1, the warp walks the table in lock-step
   {
-    int qtop = integ ? (K - 1) : 0;
-    int qmax = qtop;
-    if (RETRACT) qmax = __reduce_max_sync(0xffffffffu, qtop);
-    for (int q = qmax; q >= 1; q--) {
-      if (q <= qtop) {
-        const double *e0 = tab + (size_t)(2 * q) * NT * 6;
-        rk4_step<NT>(x, tau, Kse, Kbt, rb.dL, e0, e0 - NT * 6, e0 - 2 * NT * 6);
-        nsteps++;
-        emit_node<NT>(o, cfg, cap_pts, K - q + 1, rb.node_t[q - 1], x, rz);
+    const int T = integ ? (K - 1 + nhead) : 0;
+    int Tmax = T;
+    if (RETRACT) Tmax = __reduce_max_sync(0xffffffffu, T);
+    nsteps = T;
+#pragma unroll 1
+    for (int j = 0; j < Tmax; j++) {
+      const int q = Tmax - j;  // regular step q: node q -> node q-1 (1 <= q <= K-1)
+      if (!integ || q > K - 1 + nhead) continue;
+      const double *p0, *p1, *p2;
+      double h;
+      int emit_idx;
+      if (q <= K - 1) {
+        p0 = tab + (size_t)(2 * q) * NT * 6;
+        p1 = p0 - NT * 6;
+        p2 = p0 - 2 * NT * 6;
+        h = rb.dL;
+        emit_idx = K - q + 1;
+      } else if (q == K) {  // the head step that lands on node K-1
+        p0 = (nhead == 2) ? hd2 : hd0;
+        p1 = (nhead == 2) ? hd3 : hd1;
+        p2 = tab + (size_t)(2 * (K - 1)) * NT * 6;
+        h = (nhead == 2) ? hh1 : hh0;
+        emit_idx = 1;
+      } else {  // q == K + 1: first of two head steps, lands between grid points (not observed)
+        p0 = hd0; p1 = hd1; p2 = hd2;
+        h = hh0;
+        emit_idx = -1;
       }
+      rk4_step<NT>(x, tau, Kse, Kbt, h, p0, p1, p2);
+      if (emit_idx >= 0) emit_node<NT>(o, cfg, cap_pts, emit_idx, rb.node_t[K - emit_idx], x, rz);
     }
   }
 

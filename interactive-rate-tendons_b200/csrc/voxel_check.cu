@@ -12,9 +12,12 @@
 //                the role of the octree's "null child" early-out.
 //   set store    CSR, structure-of-arrays: keys uint32[nb], bits uint64[nb], offsets uint64[n+1];
 //                12 bytes per occupied leaf block = the algorithmic traffic of SURVEY 8(d).
-// K3 streams keys/bits with 128-bit loads, fully coalesced, flat over all leaves of the range
-// (no per-set divergence); a leaf that intersects the environment locates its set through a
-// per-128-leaf "first set" table and ORs one bit into the verdict bitmask.
+// K3: one warp per tile of 32 consecutive sets = one uint32 verdict word.  The tile's leaves
+// are one contiguous CSR range; lanes stream it with 128-bit loads (uint4 of keys + 2 x
+// ulonglong2 of bits per lane and iteration, two iterations in flight), test
+// `bits & env[key]` behind the occupancy bitmap, and a leaf that hits is attributed to its set
+// by a warp broadcast against the 32 set offsets the lanes hold in registers.  The word is
+// produced by one __ballot_sync: no atomics, no memset, no per-set divergence.
 #include <cstring>
 #include <vector>
 
@@ -23,7 +26,6 @@
 namespace {
 
 constexpr int K3_THREADS = 256;
-constexpr int K3_CHUNK = 128;  // leaves per entry of the chunk -> first-set table
 
 __global__ void env_build_occ_kernel(const uint64_t *__restrict__ blocks, int64_t nblk,
                                      uint32_t *__restrict__ occ) {
@@ -58,25 +60,12 @@ __global__ void count_nonzero_kernel(const uint64_t *__restrict__ blocks, int64_
   if ((threadIdx.x & 31) == 0 && m) atomicAdd(out, (unsigned long long)__popc(m));
 }
 
-// chunk c (leaves [c*128, c*128+128)) -> id of the set containing leaf c*128
-__global__ void build_chunk_table_kernel(const uint64_t *__restrict__ offsets, int64_t n_sets,
-                                         int64_t n_chunks, uint32_t *__restrict__ chunk_set) {
-  const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (s >= n_sets) return;
-  const uint64_t lo = offsets[s], hi = offsets[s + 1];
-  if (hi == lo) return;
-  // chunk starts c*128 with lo <= c*128 < hi
-  int64_t c0 = (int64_t)((lo + K3_CHUNK - 1) / K3_CHUNK);
-  for (int64_t c = c0; c < n_chunks && (uint64_t)c * K3_CHUNK < hi; c++) chunk_set[c] = (uint32_t)s;
-}
-
-// K3.  One thread per 4 consecutive leaves per iteration (uint4 keys + 2 x ulonglong2 bits).
+// K3 `voxel_and_popc`
 template <bool OCC_SMEM, bool STATS>
 __global__ void __launch_bounds__(K3_THREADS)
 voxel_and_popc_kernel(const uint32_t *__restrict__ keys, const uint64_t *__restrict__ bits,
-                      const uint64_t *__restrict__ offsets, const uint32_t *__restrict__ chunk_set,
-                      const uint64_t *__restrict__ env, const uint32_t *__restrict__ occ,
-                      int occ_words, int64_t leaf_begin, int64_t leaf_end, int64_t set_begin,
+                      const uint64_t *__restrict__ offsets, const uint64_t *__restrict__ env,
+                      const uint32_t *__restrict__ occ, int occ_words, int64_t set_begin,
                       int64_t set_end, uint32_t *__restrict__ verdict,
                       unsigned long long *__restrict__ stats) {
   extern __shared__ uint32_t s_occ[];
@@ -85,51 +74,79 @@ voxel_and_popc_kernel(const uint32_t *__restrict__ keys, const uint64_t *__restr
     __syncthreads();
   }
   const uint32_t *occp = OCC_SMEM ? s_occ : occ;
-  const int64_t q_begin = leaf_begin >> 2, q_end = (leaf_end + 3) >> 2;  // quads of 4 leaves
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  const int64_t ntiles = (set_end - set_begin + 31) >> 5;
   unsigned long long vox = 0, hits = 0;
-  for (int64_t q = q_begin + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < q_end;
-       q += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t j0 = q << 2;
-    uint32_t k[4];
-    uint64_t b[4];
-    if (j0 >= leaf_begin && j0 + 4 <= leaf_end) {
-      const uint4 kk = __ldcs(reinterpret_cast<const uint4 *>(keys + j0));
-      const ulonglong2 b01 = __ldcs(reinterpret_cast<const ulonglong2 *>(bits + j0));
-      const ulonglong2 b23 = __ldcs(reinterpret_cast<const ulonglong2 *>(bits + j0 + 2));
-      k[0] = kk.x; k[1] = kk.y; k[2] = kk.z; k[3] = kk.w;
-      b[0] = b01.x; b[1] = b01.y; b[2] = b23.x; b[3] = b23.y;
-    } else {  // ragged head / tail of the range
+
+  for (int64_t tile = warp; tile < ntiles; tile += nwarps) {
+    const int64_t s0 = set_begin + (tile << 5);
+    const int64_t sl = s0 + lane;
+    // lane l owns set s0+l: leaves [lo, hi)
+    uint64_t lo = 0, hi = 0;
+    if (sl < set_end) { lo = offsets[sl]; hi = offsets[sl + 1]; }
+    const uint64_t t_lo = __shfl_sync(0xffffffffu, lo, 0);
+    const int last = (int)min((int64_t)31, set_end - 1 - s0);
+    const uint64_t t_hi = __shfl_sync(0xffffffffu, hi, last);
+    bool mine = false;  // verdict of the set this lane owns
+
+    auto process = [&](int64_t j0, const uint4 &kk, const ulonglong2 &b01, const ulonglong2 &b23) {
+      const uint32_t k[4] = {kk.x, kk.y, kk.z, kk.w};
+      const uint64_t b[4] = {b01.x, b01.y, b23.x, b23.y};
+      uint32_t hitmask = 0;
 #pragma unroll
       for (int e = 0; e < 4; e++) {
-        const int64_t j = j0 + e;
-        const bool in = (j >= leaf_begin && j < leaf_end);
-        k[e] = in ? keys[j] : 0u;
-        b[e] = in ? bits[j] : 0ull;
+        const uint64_t j = (uint64_t)(j0 + e);
+        if (j < t_lo || j >= t_hi || b[e] == 0ull) continue;
+        if (!((occp[k[e] >> 5] >> (k[e] & 31)) & 1u)) continue;  // empty environment leaf
+        const uint64_t x = b[e] & env[k[e]];
+        if (x == 0ull) continue;
+        hitmask |= 1u << e;
+        if (STATS) { vox += (unsigned long long)__popcll(x); hits++; }
       }
-    }
+      // attribute hits to sets: broadcast the position of each hitting lane's leaves
+      unsigned m = __ballot_sync(0xffffffffu, hitmask != 0);
+      while (m) {
+        const int src = __ffs(m) - 1;
+        m &= m - 1;
+        const int64_t jj = __shfl_sync(0xffffffffu, j0, src);
+        const uint32_t hm = __shfl_sync(0xffffffffu, hitmask, src);
 #pragma unroll
-    for (int e = 0; e < 4; e++) {
-      if (b[e] == 0ull) continue;
-      if (!((occp[k[e] >> 5] >> (k[e] & 31)) & 1u)) continue;  // empty environment leaf
-      const uint64_t x = b[e] & env[k[e]];
-      if (x == 0ull) continue;
-      if (STATS) { vox += (unsigned long long)__popcll(x); hits++; }
-      // locate the set of leaf j: chunk table, then a short forward scan of the offsets
-      const int64_t j = j0 + e;
-      int64_t s = (int64_t)chunk_set[j / K3_CHUNK];
-      if (s < set_begin) s = set_begin;
-      while (s + 1 < set_end && offsets[s + 1] <= (uint64_t)j) s++;
-      const int64_t rel = s - set_begin;
-      const uint32_t bit = 1u << (rel & 31);
-      if (!(verdict[rel >> 5] & bit)) atomicOr(&verdict[rel >> 5], bit);
+        for (int e = 0; e < 4; e++)
+          if (((hm >> e) & 1u) && lo <= (uint64_t)(jj + e) && (uint64_t)(jj + e) < hi) mine = true;
+      }
+    };
+
+    // flat walk over the tile's leaves in 16-byte aligned quads, two iterations in flight
+    const int64_t q_begin = (int64_t)(t_lo >> 2), q_end = (int64_t)((t_hi + 3) >> 2);
+    for (int64_t qbase = q_begin; qbase < q_end; qbase += 64) {  // warp-uniform trip count
+      const int64_t qa = qbase + lane, qb = qa + 32;
+      uint4 ka = make_uint4(0, 0, 0, 0), kb = ka;
+      ulonglong2 a01 = make_ulonglong2(0, 0), a23 = a01, b01 = a01, b23 = a01;
+      const bool va = qa < q_end, vb = qb < q_end;
+      if (va) {
+        ka = __ldcs(reinterpret_cast<const uint4 *>(keys) + qa);
+        a01 = __ldcs(reinterpret_cast<const ulonglong2 *>(bits) + 2 * qa);
+        a23 = __ldcs(reinterpret_cast<const ulonglong2 *>(bits) + 2 * qa + 1);
+      }
+      if (vb) {
+        kb = __ldcs(reinterpret_cast<const uint4 *>(keys) + qb);
+        b01 = __ldcs(reinterpret_cast<const ulonglong2 *>(bits) + 2 * qb);
+        b23 = __ldcs(reinterpret_cast<const ulonglong2 *>(bits) + 2 * qb + 1);
+      }
+      if (__any_sync(0xffffffffu, va)) process(qa << 2, ka, a01, a23);
+      if (__any_sync(0xffffffffu, vb)) process(qb << 2, kb, b01, b23);
     }
+    const unsigned word = __ballot_sync(0xffffffffu, mine);
+    if (lane == 0) verdict[tile] = word;
   }
   if (STATS) {
     for (int o = 16; o > 0; o >>= 1) {
       vox += __shfl_down_sync(0xffffffffu, vox, o);
       hits += __shfl_down_sync(0xffffffffu, hits, o);
     }
-    if ((threadIdx.x & 31) == 0 && (vox | hits)) {
+    if (lane == 0 && (vox | hits)) {
       atomicAdd(&stats[0], vox);
       atomicAdd(&stats[1], hits);
     }
@@ -164,25 +181,9 @@ int setstore_reserve(irt_ctx *ctx, irt_setstore *s, int64_t n_sets, int64_t n_bl
 
 int setstore_finalize(irt_ctx *ctx, irt_setstore *s, int64_t n_sets, int64_t n_blocks,
                       cudaStream_t st) {
+  (void)ctx; (void)st;
   s->n_sets = n_sets;
   s->n_blocks = n_blocks;
-  irt_setstore &a = *s;
-  const int64_t n_chunks = (n_blocks + K3_CHUNK - 1) / K3_CHUNK + 1;
-  if ((size_t)n_chunks > a.cap_chunks) {
-    if (a.d_chunk_set) cudaFree(a.d_chunk_set);
-    a.d_chunk_set = nullptr;
-    a.cap_chunks = 0;
-    IRT_CUDA(ctx, cudaMalloc(&a.d_chunk_set, (size_t)n_chunks * 4));
-    a.cap_chunks = (size_t)n_chunks;
-  }
-  IRT_CUDA(ctx, cudaMemsetAsync(a.d_chunk_set, 0, (size_t)n_chunks * 4, st));
-  if (n_sets > 0) {
-    const int T = 256;
-    build_chunk_table_kernel<<<(unsigned)((n_sets + T - 1) / T), T, 0, st>>>(s->d_offsets, n_sets,
-                                                                           n_chunks, a.d_chunk_set);
-    IRT_LAUNCHED(ctx);
-    IRT_CUDA(ctx, cudaGetLastError());
-  }
   return IRT_OK;
 }
 
@@ -313,7 +314,6 @@ int irt_setstore_create(irt_ctx *ctx, const irt_grid *grid, irt_setstore **out) 
 void irt_setstore_destroy(irt_setstore *s) {
   if (!s) return;
   cudaSetDevice(s->ctx->device);
-  if (s->d_chunk_set) cudaFree(s->d_chunk_set);
   if (s->d_offsets) cudaFree(s->d_offsets);
   if (s->d_keys) cudaFree(s->d_keys);
   if (s->d_bits) cudaFree(s->d_bits);
@@ -390,21 +390,14 @@ static int check_sets_impl(irt_ctx *ctx, const irt_setstore *store, const irt_en
                     (long long)begin, (long long)end, (long long)store->n_sets);
   const int64_t n = end - begin;
   if (n == 0) return IRT_OK;
-  IRT_CUDA(ctx, cudaMemsetAsync(d_verdict, 0, (size_t)((n + 31) / 32) * 4, st));
-  // leaf range of the set range (known on the host for a whole-store sweep, else two 8-byte reads)
-  uint64_t lr[2] = {0, (uint64_t)store->n_blocks};
-  if (begin != 0 || end != store->n_sets) {
-    IRT_CUDA(ctx, cudaMemcpyAsync(&lr[0], store->d_offsets + begin, 8, cudaMemcpyDeviceToHost, st));
-    IRT_CUDA(ctx, cudaMemcpyAsync(&lr[1], store->d_offsets + end, 8, cudaMemcpyDeviceToHost, st));
-    IRT_CUDA(ctx, cudaStreamSynchronize(st));
+  if (store->n_blocks == 0) {
+    IRT_CUDA(ctx, cudaMemsetAsync(d_verdict, 0, (size_t)((n + 31) / 32) * 4, st));
+    return IRT_OK;
   }
-  const int64_t leaf_begin = (int64_t)lr[0], leaf_end = (int64_t)lr[1];
-  if (leaf_end == leaf_begin) return IRT_OK;
-  const irt_setstore &a = *store;
   const int occ_words = (int)((env->n_blocks_total + 31) / 32);
   const bool occ_smem = (size_t)occ_words * 4 <= 64 * 1024;
-  const int64_t quads = ((leaf_end + 3) >> 2) - (leaf_begin >> 2);
-  int64_t blocks = (quads + K3_THREADS - 1) / K3_THREADS;
+  const int64_t ntiles = (n + 31) / 32;
+  int64_t blocks = (ntiles * 32 + K3_THREADS - 1) / K3_THREADS;
   const int64_t max_blocks = (int64_t)ctx->sm_count * 8;  // 8 resident CTAs of 256 threads per SM
   if (blocks > max_blocks) blocks = max_blocks;
   const size_t smem = occ_smem ? (size_t)occ_words * 4 : 0;
@@ -413,9 +406,9 @@ static int check_sets_impl(irt_ctx *ctx, const irt_setstore *store, const irt_en
     auto kfn = voxel_and_popc_kernel<OS, ST>;                                                      \
     if (smem > 48 * 1024)                                                                          \
       IRT_CUDA(ctx, cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-    kfn<<<(unsigned)blocks, K3_THREADS, smem, st>>>(                                               \
-        store->d_keys, store->d_bits, store->d_offsets, a.d_chunk_set, env->d_blocks, env->d_occ,  \
-        occ_words, leaf_begin, leaf_end, begin, end, d_verdict, d_stats);                          \
+    kfn<<<(unsigned)blocks, K3_THREADS, smem, st>>>(store->d_keys, store->d_bits, store->d_offsets, \
+                                                    env->d_blocks, env->d_occ, occ_words, begin,   \
+                                                    end, d_verdict, d_stats);                      \
   } while (0)
   if (occ_smem) {
     if (d_stats) K3_LAUNCH(true, true); else K3_LAUNCH(true, false);

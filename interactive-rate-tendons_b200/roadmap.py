@@ -143,6 +143,8 @@ class VoxelCachedLazyPRM:
         if hi > lo:
             stream = torch.cuda.current_stream(dev).cuda_stream if use_cuda else None
             store.check_dev(self.env, words, 0, hi - lo, stream=stream)
+            if not stream:  # legacy default stream: the library ran on its own stream
+                self.ctx.synchronize()
         allw = gather_verdict_words(words, self.dist)
         collides = assemble_verdicts(allw.cpu().numpy().view(np.uint32), n_total, self.world)
         return collides

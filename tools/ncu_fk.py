@@ -1,0 +1,42 @@
+"""small single-purpose drivers for ncu captures (one kernel each)"""
+import sys, os
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np, torch
+import irt_b200, irt_b200.workloads as wl
+
+which = sys.argv[1] if len(sys.argv) > 1 else "fk"
+ctx = irt_b200.Context(0)
+if which == "fk":
+    spec = wl.robot_b(0.005)
+    rb = irt_b200.Robot(ctx, spec)
+    n = 1_000_000
+    st = torch.from_numpy(wl.sample_states(spec, n, stream=100)).cuda()
+    outs = dict(p=torch.zeros(n, rb.max_points, 3, dtype=torch.float64, device="cuda"),
+                npts=torch.zeros(n, dtype=torch.int32, device="cuda"),
+                L=torch.zeros(n, dtype=torch.float64, device="cuda"),
+                L_i=torch.zeros(n, 6, dtype=torch.float64, device="cuda"))
+    for _ in range(3):
+        rb.shape_batch_dev(st, n, outs)
+        ctx.synchronize()
+else:
+    rng = np.random.default_rng(8)
+    Ng, Nb = 128, 32
+    grid = irt_b200.make_grid(Ng, [-0.21, 0.21] * 3)
+    n_sets = 4_000_000
+    sizes = rng.integers(20, 60, size=n_sets)
+    off = np.concatenate([[0], np.cumsum(sizes)]).astype(np.uint64)
+    nb = int(off[-1])
+    # clustered keys like a real swept volume: consecutive morton keys around a random start
+    starts = rng.integers(0, Nb ** 3 - 64, size=n_sets)
+    keys = (np.repeat(starts, sizes) + (np.arange(nb) - np.repeat(off[:-1].astype(np.int64), sizes))).astype(np.uint32)
+    bits = rng.integers(1, 2 ** 63, size=nb, dtype=np.uint64)
+    store = irt_b200.SetStore(ctx, grid); store.import_csr(off, keys, bits)
+    env = irt_b200.Env(ctx, grid)
+    e1 = np.zeros(Nb ** 3, dtype=np.uint64)
+    occ = rng.choice(Nb ** 3, size=Nb ** 3 // 25, replace=False)
+    e1[occ] = rng.integers(1, 2 ** 62, size=len(occ), dtype=np.uint64)
+    env.update(e1)
+    words = torch.zeros((n_sets + 31) // 32, dtype=torch.int32, device="cuda")
+    for _ in range(3):
+        store.check_dev(env, words); ctx.synchronize()
+    print("alg bytes", store.algorithmic_bytes(), "collide frac", irt_b200.unpack_verdicts(words.cpu().numpy().view(np.uint32), n_sets).mean())
