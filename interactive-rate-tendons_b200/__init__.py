@@ -20,7 +20,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libirt_b200.so")
+LIB_PATH = os.environ.get("IRT_B200_LIB", os.path.join(_HERE, "libirt_b200.so"))
 
 MAX_TENDONS = 12
 MAX_COEF = 8

@@ -27,37 +27,49 @@
 
 namespace {
 
-constexpr int FK_THREADS = 128;
+#ifndef FK_THREADS_PER_BLOCK
+#define FK_THREADS_PER_BLOCK 128
+#endif
+#ifndef FK_MIN_BLOCKS
+#define FK_MIN_BLOCKS 2
+#endif
+constexpr int FK_THREADS = FK_THREADS_PER_BLOCK;
 
 __device__ __forceinline__ double rcp_fast(double x) { return 1.0 / x; }
 
-// routing at arbitrary t, per thread (only used inside the irregular first gap)
+// routing at arbitrary t, per thread (only used inside the irregular first gap); same
+// power-sum form as get_poly_vecs / get_r_info2 (tendon/get_r_info.cpp:17-40,105-144), with the
+// coefficient loops fully unrolled so S, S', S'' stay in registers
 template <int NT>
-__device__ __noinline__ void routing_eval(const RobotDev &rb, double t, double *out) {
+__device__ __forceinline__ void routing_eval(const RobotDev &rb, double t, double *out) {
   const int Na = rb.n_c, Nm = rb.n_d;
-  const int Ns = Na > Nm ? Na : Nm;
   double S[IRT_MAX_COEF], Sd[IRT_MAX_COEF], Sdd[IRT_MAX_COEF];
   S[0] = 1; Sd[0] = 0; Sdd[0] = 0;
-  if (Ns >= 2) { S[1] = t; Sd[1] = 1; Sdd[1] = 0; }
-  for (int i = 2; i < Ns; i++) {
+  S[1] = t; Sd[1] = 1; Sdd[1] = 0;
+#pragma unroll
+  for (int i = 2; i < IRT_MAX_COEF; i++) {
     S[i] = t * S[i - 1];
     Sd[i] = i * S[i - 1];
     Sdd[i] = i * (i - 1) * S[i - 2];
   }
+#pragma unroll 1
   for (int j = 0; j < NT; j++) {
     const double *C = rb.C + j * IRT_MAX_COEF, *D = rb.D + j * IRT_MAX_COEF;
     double th = 0, th1 = 0, th2 = 0, rho = 0, rho1 = 0, rho2 = 0;
-    for (int i = 0; i < Na; i++) { th += C[i] * S[i]; th1 += C[i] * Sd[i]; th2 += C[i] * Sdd[i]; }
-    for (int i = 0; i < Nm; i++) { rho += D[i] * S[i]; rho1 += D[i] * Sd[i]; rho2 += D[i] * Sdd[i]; }
-    double s, c;
-    sincos(th, &s, &c);
+#pragma unroll
+    for (int i = 0; i < IRT_MAX_COEF; i++) {
+      if (i < Na) { th += C[i] * S[i]; th1 += C[i] * Sd[i]; th2 += C[i] * Sdd[i]; }
+      if (i < Nm) { rho += D[i] * S[i]; rho1 += D[i] * Sd[i]; rho2 += D[i] * Sdd[i]; }
+    }
+    double sn, cs;
+    sincos(th, &sn, &cs);
     double *o = out + 6 * j;
-    o[0] = rho * s;
-    o[1] = rho * c;
-    o[2] = rho1 * s + rho * (c * th1);
-    o[3] = rho1 * c + rho * (-s * th1);
-    o[4] = ((rho2 * s + (2 * rho1) * (c * th1)) - rho * (s * th1 * th1)) + rho * (c * th2);
-    o[5] = ((rho2 * c + (2 * rho1) * (-s * th1)) - rho * (c * th1 * th1)) + rho * (-s * th2);
+    o[0] = rho * sn;
+    o[1] = rho * cs;
+    o[2] = rho1 * sn + rho * (cs * th1);
+    o[3] = rho1 * cs + rho * (-sn * th1);
+    o[4] = ((rho2 * sn + (2 * rho1) * (cs * th1)) - rho * (sn * th1 * th1)) + rho * (cs * th2);
+    o[5] = ((rho2 * cs + (2 * rho1) * (-sn * th1)) - rho * (cs * th1 * th1)) + rho * (-sn * th2);
   }
 }
 
@@ -273,7 +285,7 @@ __device__ __forceinline__ void emit_node(const irt_fk_outputs &o, int64_t cfg, 
 }
 
 template <int NT, bool RETRACT>
-__global__ void __launch_bounds__(FK_THREADS, 2)
+__global__ void __launch_bounds__(FK_THREADS, FK_MIN_BLOCKS)
 fk_rk4_fp64_kernel(const RobotDev rb, const double *__restrict__ states, int state_size, int64_t n,
                    int cap_pts, const irt_fk_outputs o, const int32_t *__restrict__ perm) {
   extern __shared__ double smem[];
@@ -350,33 +362,37 @@ fk_rk4_fp64_kernel(const RobotDev rb, const double *__restrict__ states, int sta
       rt_s = head;
     }
     double v[3] = {0, 0, 1}, u[3] = {0, 0, 0};
+    // Same iteration as the reference; the unit vectors use rsqrt and the three exit tests
+    // compare squares (residual < thr <=> residual^2 < thr^2, |dv| < 1e-9 |v| <=> |dv|^2 <
+    // 1e-18 |v|^2), which keeps FP64 divisions and square roots out of the loop.
+    const double thr2 = rb.residual_threshold * rb.residual_threshold;
     for (iters = 0; iters < 1000; ++iters) {
-      double Ft[3] = {0, 0, 0}, Lt[3] = {0, 0, 0};
+      double Ft0 = 0, Ft1 = 0, Ft2 = 0, Lt0 = 0, Lt1 = 0, Lt2 = 0;
 #pragma unroll
       for (int k = 0; k < NT; k++) {
         const double rx = rt_s[6 * k], ry = rt_s[6 * k + 1], dx = rt_s[6 * k + 2], dy = rt_s[6 * k + 3];
-        double qx = (-u[2] * ry + dx) + v[0];
-        double qy = (u[2] * rx + dy) + v[1];
-        double qz = (-u[1] * rx + u[0] * ry) + v[2];
-        const double nrm = sqrt(qx * qx + qy * qy + qz * qz);
-        qx /= nrm; qy /= nrm; qz /= nrm;
-        Ft[0] -= tau[k] * qx; Ft[1] -= tau[k] * qy; Ft[2] -= tau[k] * qz;
-        // r^ q = r x q = (ry qz, -rx qz, rx qy - ry qx)
-        Lt[0] -= tau[k] * (ry * qz); Lt[1] -= tau[k] * (-rx * qz); Lt[2] -= tau[k] * (rx * qy - ry * qx);
+        const double qx = fma(-u[2], ry, dx + v[0]);
+        const double qy = fma(u[2], rx, dy + v[1]);
+        const double qz = fma(u[0], ry, fma(-u[1], rx, v[2]));
+        const double tr = tau[k] * rsqrt(fma(qx, qx, fma(qy, qy, qz * qz)));
+        const double fx = tr * qx, fy = tr * qy, fz = tr * qz;  // tau * unit(q)
+        Ft0 -= fx; Ft1 -= fy; Ft2 -= fz;
+        Lt0 = fma(-ry, fz, Lt0); Lt1 = fma(rx, fz, Lt1); Lt2 -= fma(rx, fy, -ry * fx);
       }
-      const double n0 = Kse[0] * v[0], n1 = Kse[1] * v[1], n2 = Kse[2] * (v[2] - 1.0);
-      const double m0 = Kbt[0] * u[0], m1 = Kbt[1] * u[1], m2 = Kbt[2] * u[2];
-      const double residual =
-          sqrt(((n0 - Ft[0]) * (n0 - Ft[0]) + (n1 - Ft[1]) * (n1 - Ft[1]) + (n2 - Ft[2]) * (n2 - Ft[2])) +
-               ((m0 - Lt[0]) * (m0 - Lt[0]) + (m1 - Lt[1]) * (m1 - Lt[1]) + (m2 - Lt[2]) * (m2 - Lt[2])));
-      if (residual < rb.residual_threshold) break;
-      const double vn0 = rb.KseInv[0] * Ft[0], vn1 = rb.KseInv[1] * Ft[1], vn2 = rb.KseInv[2] * Ft[2] + 1.0;
-      const double un0 = rb.KbtInv[0] * Lt[0], un1 = rb.KbtInv[1] * Lt[1], un2 = rb.KbtInv[2] * Lt[2];
-      const double dv = sqrt((vn0 - v[0]) * (vn0 - v[0]) + (vn1 - v[1]) * (vn1 - v[1]) + (vn2 - v[2]) * (vn2 - v[2]));
-      const double du = sqrt((un0 - u[0]) * (un0 - u[0]) + (un1 - u[1]) * (un1 - u[1]) + (un2 - u[2]) * (un2 - u[2]));
-      const double nv = sqrt(v[0] * v[0] + v[1] * v[1] + v[2] * v[2]);
-      const double nu = sqrt(u[0] * u[0] + u[1] * u[1] + u[2] * u[2]);
-      if (dv < 1e-9 * nv && du < 1e-9 * nu) break;
+      const double e0 = fma(Kse[0], v[0], -Ft0), e1 = fma(Kse[1], v[1], -Ft1),
+                   e2 = fma(Kse[2], v[2] - 1.0, -Ft2);
+      const double g0 = fma(Kbt[0], u[0], -Lt0), g1 = fma(Kbt[1], u[1], -Lt1),
+                   g2 = fma(Kbt[2], u[2], -Lt2);
+      const double res2 = fma(e0, e0, fma(e1, e1, e2 * e2)) + fma(g0, g0, fma(g1, g1, g2 * g2));
+      if (res2 < thr2) break;
+      const double vn0 = rb.KseInv[0] * Ft0, vn1 = rb.KseInv[1] * Ft1, vn2 = fma(rb.KseInv[2], Ft2, 1.0);
+      const double un0 = rb.KbtInv[0] * Lt0, un1 = rb.KbtInv[1] * Lt1, un2 = rb.KbtInv[2] * Lt2;
+      const double a0 = vn0 - v[0], a1 = vn1 - v[1], a2 = vn2 - v[2];
+      const double b0 = un0 - u[0], b1 = un1 - u[1], b2 = un2 - u[2];
+      const double dv2 = fma(a0, a0, fma(a1, a1, a2 * a2)), du2 = fma(b0, b0, fma(b1, b1, b2 * b2));
+      const double nv2 = fma(v[0], v[0], fma(v[1], v[1], v[2] * v[2]));
+      const double nu2 = fma(u[0], u[0], fma(u[1], u[1], u[2] * u[2]));
+      if (dv2 < 1e-18 * nv2 && du2 < 1e-18 * nu2) break;
       v[0] = vn0; v[1] = vn1; v[2] = vn2;
       u[0] = un0; u[1] = un1; u[2] = un2;
     }
@@ -414,7 +430,11 @@ fk_rk4_fp64_kernel(const RobotDev rb, const double *__restrict__ states, int sta
   double hh0 = 0.0, hh1 = 0.0;
   const double *hd0 = head, *hd1 = head + NT * 6, *hd2 = head + 2 * NT * 6, *hd3 = head + 3 * NT * 6;
   double rt_h1[NT * 6], rt_h2[NT * 6], rt_h3[NT * 6];
+#ifdef EXP_NO_HEAD
+  if (false) {
+#else
   if (integ) {
+#endif
     if (RETRACT) {
       const double eps = 2.220446049250313e-16;
       const double t1 = rb.node_t[K - 1];
@@ -443,7 +463,11 @@ fk_rk4_fp64_kernel(const RobotDev rb, const double *__restrict__ states, int sta
 #pragma unroll 1
     for (int j = 0; j < Tmax; j++) {
       const int q = Tmax - j;  // regular step q: node q -> node q-1 (1 <= q <= K-1)
+#ifdef EXP_NO_HEAD
+      if (!integ || q > K - 1) continue;
+#else
       if (!integ || q > K - 1 + nhead) continue;
+#endif
       const double *p0, *p1, *p2;
       double h;
       int emit_idx;
@@ -513,20 +537,27 @@ __global__ void fk_count_nodes_kernel(const RobotDev rb, const double *__restric
                                       int state_size, int64_t n, int32_t *__restrict__ keys,
                                       int32_t *__restrict__ hist) {
   extern __shared__ int32_t sh[];
-  const int nb = rb.Kfull + 1;
+  const int nb = rb.Kfull + 2;
   for (int i = threadIdx.x; i < nb; i += blockDim.x) sh[i] = 0;
   __syncthreads();
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) {
+    // bucket key = number of RK4 steps the configuration will take (K - 1 regular + 1 or 2 head)
     double s = states[i * state_size + state_size - 1];
-    int K = 0;
+    int T = 0;
     if (s >= 0.0 && s < rb.L) {
+      int K = 0;
       const double lim = rb.L - (rb.dL / 2);
       for (double p = s; p <= lim; p += rb.dL) K++;
       if (K > rb.Kfull) K = rb.Kfull;
+      if (K >= 1) {
+        const double t1 = rb.node_t[K - 1];
+        const double h0 = fmin(rb.dL, t1 - s);
+        T = K - 1 + ((t1 - (s + h0) > 2.220446049250313e-16) ? 2 : 1);
+      }
     }
-    keys[i] = K;
-    atomicAdd(&sh[K], 1);
+    keys[i] = T;
+    atomicAdd(&sh[T], 1);
   }
   __syncthreads();
   for (int k = threadIdx.x; k < nb; k += blockDim.x)
@@ -586,7 +617,7 @@ int fk_launch(irt_ctx *ctx, const irt_robot *rb, const double *d_states, int64_t
   if (smem > 200 * 1024)
     return irt_fail(ctx, IRT_ERR_CAPACITY, "routing table (%zu B) exceeds shared memory", smem);
   if (d.enable_retraction && !d_perm) {
-    const int nb = d.Kfull + 1;
+    const int nb = d.Kfull + 2;
     size_t bytes = (size_t)n * 4 * 2 + (size_t)nb * 4 + 256;
     char *scr = (char *)ctx_scratch(ctx, bytes);
     if (!scr) return irt_fail(ctx, IRT_ERR_CUDA, "scratch alloc of %zu bytes failed", bytes);
