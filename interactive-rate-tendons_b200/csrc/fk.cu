@@ -35,7 +35,36 @@ namespace {
 #endif
 constexpr int FK_THREADS = FK_THREADS_PER_BLOCK;
 
+#ifndef FK_FAST_PRIMS
+#define FK_FAST_PRIMS 1
+#endif
+#if FK_FAST_PRIMS
+// Branch-free reciprocal / reciprocal square root: the hardware FP64 seed (MUFU.RCP64H /
+// MUFU.RSQ64H, ~20 bits) refined by two Newton steps (relative error ~1e-16, not correctly
+// rounded).  Unlike the library routines they contain no special-case branches, so the compiler
+// can interleave the dependency chains of different tendons.  Valid for normal, finite inputs
+// (here: |q|^2 ~ 1 and determinants of positive-definite stiffness blocks).
+__device__ __forceinline__ double rcp_fast(double x) {
+  double y;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+  double e = fma(-x, y, 1.0);
+  y = fma(y, e, y);
+  e = fma(-x, y, 1.0);
+  return fma(y, e, y);
+}
+__device__ __forceinline__ double rsqrt_fast(double x) {
+  double y;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+  const double hx = 0.5 * x;
+  double e = fma(-hx * y, y, 0.5);
+  y = fma(y, e, y);
+  e = fma(-hx * y, y, 0.5);
+  return fma(y, e, y);
+}
+#else
 __device__ __forceinline__ double rcp_fast(double x) { return 1.0 / x; }
+__device__ __forceinline__ double rsqrt_fast(double x) { return rsqrt(x); }
+#endif
 
 // routing at arbitrary t, per thread (only used inside the irregular first gap); same
 // power-sum form as get_poly_vecs / get_r_info2 (tendon/get_r_info.cpp:17-40,105-144), with the
@@ -95,7 +124,7 @@ __device__ __forceinline__ void vu_dot(const double *__restrict__ rt, const doub
     const double qy = fma(u[2], rx, dy + v[1]);
     const double qz = fma(u[0], ry, fma(-u[1], rx, v[2]));
     const double s2 = fma(qx, qx, fma(qy, qy, qz * qz));
-    const double rs = rsqrt(s2);
+    const double rs = rsqrt_fast(s2);
     sig[j] = s2 * rs;
     const double e = tau[j] * rs;        // tau / sigma
     const double c3 = e * (rs * rs);     // tau / sigma^3
@@ -187,13 +216,41 @@ __device__ __forceinline__ void vu_dot(const double *__restrict__ rt, const doub
   vd[2] = fma(-idA, fma(y20, ud[0], fma(y21, ud[1], y22 * ud[2])), z2);
 }
 
+// FK_SMEM_ACC: the pure quadratures (L, L_i and optionally p) are only touched once per RK4
+// stage; keeping them in per-thread shared-memory slots (stride = block size, conflict-free)
+// frees registers for the scheduler.
+#ifndef FK_SMEM_ACC
+#define FK_SMEM_ACC 0
+#endif
 template <int NT>
 struct FkState {
-  double p[3];
   double R[9];  // column-major (R[i + 3 j]) like Eigen
   double v[3], u[3];
+#if FK_SMEM_ACC >= 2
+  double *sm;   // slots: [0..2] p, [3] L, [4..4+NT) L_i
+  __device__ __forceinline__ double &P(int i) { return sm[i * FK_THREADS]; }
+  __device__ __forceinline__ const double &P(int i) const { return sm[i * FK_THREADS]; }
+#else
+  double p[3];
+  __device__ __forceinline__ double &P(int i) { return p[i]; }
+  __device__ __forceinline__ const double &P(int i) const { return p[i]; }
+#endif
+#if FK_SMEM_ACC >= 1
+#if FK_SMEM_ACC == 1
+  double *sm;
+#endif
+  __device__ __forceinline__ double &LB() { return sm[3 * FK_THREADS]; }
+  __device__ __forceinline__ const double &LB() const { return sm[3 * FK_THREADS]; }
+  __device__ __forceinline__ double &LI(int j) { return sm[(4 + j) * FK_THREADS]; }
+  __device__ __forceinline__ const double &LI(int j) const { return sm[(4 + j) * FK_THREADS]; }
+#else
   double Lb;
   double Li[NT];
+  __device__ __forceinline__ double &LB() { return Lb; }
+  __device__ __forceinline__ const double &LB() const { return Lb; }
+  __device__ __forceinline__ double &LI(int j) { return Li[j]; }
+  __device__ __forceinline__ const double &LI(int j) const { return Li[j]; }
+#endif
 };
 
 // one classic RK4 step of size h; rt0/rt1/rt2 = routing at t, t+h/2, t+h.
@@ -223,10 +280,17 @@ __device__ __forceinline__ void rk4_step(FkState<NT> &x, const double (&tau)[NT]
     // p' = R v ; L' = |v| ; L_i' = sigma_i : pure quadratures, accumulate in place
 #pragma unroll
     for (int i = 0; i < 3; i++)
-      x.p[i] = fma(wq, fma(sR[i], sv[0], fma(sR[i + 3], sv[1], sR[i + 6] * sv[2])), x.p[i]);
-    x.Lb = fma(wq, sqrt(fma(sv[0], sv[0], fma(sv[1], sv[1], sv[2] * sv[2]))), x.Lb);
+      x.P(i) = fma(wq, fma(sR[i], sv[0], fma(sR[i + 3], sv[1], sR[i + 6] * sv[2])), x.P(i));
+    {
+      const double vv = fma(sv[0], sv[0], fma(sv[1], sv[1], sv[2] * sv[2]));
+#if FK_FAST_PRIMS
+      x.LB() = fma(wq, vv * rsqrt_fast(vv), x.LB());
+#else
+      x.LB() = fma(wq, sqrt(vv), x.LB());
+#endif
+    }
 #pragma unroll
-    for (int j = 0; j < NT; j++) x.Li[j] = fma(wq, sig[j], x.Li[j]);
+    for (int j = 0; j < NT; j++) x.LI(j) = fma(wq, sig[j], x.LI(j));
     // R' = R u^
 #pragma unroll
     for (int i = 0; i < 3; i++) {
@@ -257,14 +321,15 @@ template <int NT>
 __device__ __forceinline__ void emit_node(const irt_fk_outputs &o, int64_t cfg, int cap_pts, int k,
                                           double t, const FkState<NT> &x, const RotZ &rz) {
   const int64_t row = cfg * cap_pts + k;
-  double px = x.p[0], py = x.p[1];
+  const double p0 = x.P(0), p1 = x.P(1), p2 = x.P(2);
+  double px = p0, py = p1;
   if (rz.on) {
-    px = rz.c * x.p[0] - rz.s * x.p[1];
-    py = rz.s * x.p[0] + rz.c * x.p[1];
+    px = rz.c * p0 - rz.s * p1;
+    py = rz.s * p0 + rz.c * p1;
   }
   if (o.p) {
     double *dst = o.p + row * 3;
-    dst[0] = px; dst[1] = py; dst[2] = x.p[2];
+    dst[0] = px; dst[1] = py; dst[2] = p2;
   }
   if (o.t) o.t[row] = t;
   if (o.R) {
@@ -291,6 +356,9 @@ fk_rk4_fp64_kernel(const RobotDev rb, const double *__restrict__ states, int sta
   extern __shared__ double smem[];
   double *tab = smem;                                // [n_table][NT][6]
   double *head = smem + (size_t)rb.n_table * NT * 6; // [4][NT][6]
+#if FK_SMEM_ACC >= 1
+  double *acc_smem = head + 4 * NT * 6;              // [4 + NT][FK_THREADS]
+#endif
   for (int i = threadIdx.x; i < rb.n_table * NT * 6; i += blockDim.x) tab[i] = rb.table[i];
   for (int i = threadIdx.x; i < 4 * NT * 6; i += blockDim.x) head[i] = rb.head[i];
   __syncthreads();
@@ -335,15 +403,18 @@ fk_rk4_fp64_kernel(const RobotDev rb, const double *__restrict__ states, int sta
   const bool degenerate = active && (s_start == rb.L);  // TendonRobot.cpp:361-372
 
   FkState<NT> x;
+#if FK_SMEM_ACC >= 1
+  x.sm = acc_smem + threadIdx.x;
+#endif
 #pragma unroll
-  for (int i = 0; i < 3; i++) { x.p[i] = 0; x.v[i] = 0; x.u[i] = 0; }
+  for (int i = 0; i < 3; i++) { x.P(i) = 0; x.v[i] = 0; x.u[i] = 0; }
 #pragma unroll
   for (int i = 0; i < 9; i++) x.R[i] = 0;
   x.R[0] = x.R[4] = x.R[8] = 1.0;
   x.v[2] = 1.0;
-  x.Lb = 0;
+  x.LB() = 0;
 #pragma unroll
-  for (int j = 0; j < NT; j++) x.Li[j] = 0;
+  for (int j = 0; j < NT; j++) x.LI(j) = 0;
 
   int iters = 0, nsteps = 0;
   double u0[3] = {0, 0, 0}, v0[3] = {0, 0, 1};
@@ -374,7 +445,7 @@ fk_rk4_fp64_kernel(const RobotDev rb, const double *__restrict__ states, int sta
         const double qx = fma(-u[2], ry, dx + v[0]);
         const double qy = fma(u[2], rx, dy + v[1]);
         const double qz = fma(u[0], ry, fma(-u[1], rx, v[2]));
-        const double tr = tau[k] * rsqrt(fma(qx, qx, fma(qy, qy, qz * qz)));
+        const double tr = tau[k] * rsqrt_fast(fma(qx, qx, fma(qy, qy, qz * qz)));
         const double fx = tr * qx, fy = tr * qy, fz = tr * qz;  // tau * unit(q)
         Ft0 -= fx; Ft1 -= fy; Ft2 -= fz;
         Lt0 = fma(-ry, fz, Lt0); Lt1 = fma(rx, fz, Lt1); Lt2 -= fma(rx, fy, -ry * fx);
@@ -507,20 +578,21 @@ fk_rk4_fp64_kernel(const RobotDev rb, const double *__restrict__ states, int sta
     const double Lhome = degenerate ? 0.0 : (rb.L - sh);
 #pragma unroll
     for (int j = 0; j < NT; j++) {
-      const double dl = Lhome * rb.home_factor[j] - x.Li[j];
+      const double dl = Lhome * rb.home_factor[j] - x.LI(j);
       if (dl < rb.min_length[j] || rb.max_length[j] < dl) flags |= IRT_FLAG_LENGTH_LIMIT;
     }
   }
   if (o.npts) o.npts[cfg] = npts;
-  if (o.L) o.L[cfg] = x.Lb;
+  if (o.L) o.L[cfg] = x.LB();
   if (o.L_i) {
 #pragma unroll
-    for (int j = 0; j < NT; j++) o.L_i[cfg * NT + j] = x.Li[j];
+    for (int j = 0; j < NT; j++) o.L_i[cfg * NT + j] = x.LI(j);
   }
   if (o.tip) {
-    double px = x.p[0], py = x.p[1];
-    if (rz.on) { px = rz.c * x.p[0] - rz.s * x.p[1]; py = rz.s * x.p[0] + rz.c * x.p[1]; }
-    o.tip[cfg * 3] = px; o.tip[cfg * 3 + 1] = py; o.tip[cfg * 3 + 2] = x.p[2];
+    const double p0 = x.P(0), p1 = x.P(1), p2 = x.P(2);
+    double px = p0, py = p1;
+    if (rz.on) { px = rz.c * p0 - rz.s * p1; py = rz.s * p0 + rz.c * p1; }
+    o.tip[cfg * 3] = px; o.tip[cfg * 3 + 1] = py; o.tip[cfg * 3 + 2] = p2;
   }
   if (o.uv) {
     double *d = o.uv + cfg * 12;
@@ -590,6 +662,9 @@ int launch_nt(irt_ctx *ctx, const irt_robot *rb, const double *d_states, int64_t
               const irt_fk_outputs &o, const int32_t *d_perm, cudaStream_t st) {
   const RobotDev &d = rb->dev;
   size_t smem = ((size_t)d.n_table + 4) * NT * 6 * sizeof(double);
+#if FK_SMEM_ACC >= 1
+  smem += (size_t)(4 + NT) * FK_THREADS * sizeof(double);
+#endif
   const int64_t blocks = (n + FK_THREADS - 1) / FK_THREADS;
   if (d.enable_retraction) {
     auto k = fk_rk4_fp64_kernel<NT, true>;
