@@ -196,6 +196,12 @@ void irt_morton_decode(uint32_t key, int Nb, int *bx, int *by, int *bz);
 int irt_voxelize_vertices(irt_ctx *ctx, const irt_robot *rb, const double *states,
                           int state_size, int64_t n, irt_setstore *store, uint32_t *flags,
                           double *tips);
+/* K2 on given shapes: AbstractVoxelValidityChecker::voxelize(const TendonResult&)
+ * (AbstractVoxelValidityChecker.h:33-41 -> VoxelBackboneValidityChecker::voxelize_impl,
+ * VoxelBackboneValidityChecker.h:49-57): rotate_points + add_piecewise_line of n already computed
+ * backbones p[n][cap_pts][3] (host), npts[n].  Replaces the store content with n sets. */
+int irt_voxelize_shapes(irt_ctx *ctx, const double *p, const int32_t *npts, int cap_pts, int64_t n,
+                        irt_setstore *store);
 /* K1+K2 (edge mode): VoxelCachedLazyPRM::precomputeEdgeVoxelCache / voxelizeEdge
  * (VoxelCachedLazyPRM.cpp:1736-1782,2879-2902) -> AbstractVoxelMotionValidator::voxelize
  * (AbstractVoxelMotionValidator.h:98-107) -> VoxelBackboneMotionValidator::generic_voxelize

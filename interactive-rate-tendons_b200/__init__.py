@@ -87,7 +87,7 @@ ABI_SYMBOLS = [
     "irt_setstore_create", "irt_setstore_destroy", "irt_setstore_num_sets",
     "irt_setstore_num_blocks", "irt_setstore_import", "irt_setstore_export",
     "irt_setstore_device_ptrs", "irt_morton_key", "irt_morton_decode",
-    "irt_voxelize_vertices", "irt_voxelize_edges", "irt_valid_segment_count",
+    "irt_voxelize_vertices", "irt_voxelize_shapes", "irt_voxelize_edges", "irt_valid_segment_count",
     "irt_check_sets", "irt_check_sets_dev", "irt_check_sets_popcount",
     "irt_check_sets_algorithmic_bytes",
 ]
@@ -139,6 +139,7 @@ def lib():
         "irt_morton_key": (u32, [i32, i32, i32, i32]),
         "irt_morton_decode": (None, [u32, i32, C.POINTER(i32), C.POINTER(i32), C.POINTER(i32)]),
         "irt_voxelize_vertices": (i32, [vp, vp, vp, i32, i64, vp, vp, vp]),
+        "irt_voxelize_shapes": (i32, [vp, vp, vp, i32, i64, vp]),
         "irt_voxelize_edges": (i32, [vp, vp, C.POINTER(Space), vp, vp, i32, i64, vp, vp, vp, vp]),
         "irt_valid_segment_count": (u32, [C.POINTER(RobotDesc), C.POINTER(Space), vp, vp]),
         "irt_check_sets": (i32, [vp, vp, vp, i64, i64, vp]),
@@ -413,6 +414,12 @@ class SetStore:
         self.ctx.check(self.ctx.L.irt_voxelize_vertices(self.ctx.h, robot.h, _ptr(states), S, n, self.h,
                                                         _ptr(flags), _ptr(tips)))
         return flags, tips
+
+    def voxelize_shapes(self, p, npts):
+        """AbstractVoxelValidityChecker::voxelize for already computed backbones p[n][cap][3]."""
+        p, npts = _np(p, np.float64), _np(npts, np.int32)
+        n, cap = p.shape[0], p.shape[1]
+        self.ctx.check(self.ctx.L.irt_voxelize_shapes(self.ctx.h, _ptr(p), _ptr(npts), cap, n, self.h))
 
     def voxelize_edges(self, robot, space, a, b):
         """precomputeEdgeVoxelCache: swept volume of every edge a[i] -> b[i].

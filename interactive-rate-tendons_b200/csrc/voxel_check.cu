@@ -83,43 +83,52 @@ voxel_and_popc_kernel(const uint32_t *__restrict__ keys, const uint64_t *__restr
   for (int64_t tile = warp; tile < ntiles; tile += nwarps) {
     const int64_t s0 = set_begin + (tile << 5);
     const int64_t sl = s0 + lane;
-    // lane l owns set s0+l: leaves [lo, hi)
+    // lane l owns set s0+l: leaves [lo, hi), kept as 32-bit positions relative to the tile
     uint64_t lo = 0, hi = 0;
     if (sl < set_end) { lo = offsets[sl]; hi = offsets[sl + 1]; }
     const uint64_t t_lo = __shfl_sync(0xffffffffu, lo, 0);
     const int last = (int)min((int64_t)31, set_end - 1 - s0);
     const uint64_t t_hi = __shfl_sync(0xffffffffu, hi, last);
-    bool mine = false;  // verdict of the set this lane owns
+    const uint32_t tile_n = (uint32_t)(t_hi - t_lo);
+    const uint32_t rlo = (sl < set_end) ? (uint32_t)(lo - t_lo) : tile_n;  // ascending over lanes
+    uint32_t own = 0;  // bit l set: set s0+l collides (as discovered by this lane)
 
-    auto process = [&](int64_t j0, const uint4 &kk, const ulonglong2 &b01, const ulonglong2 &b23) {
+    // position of the first leaf of this lane's quad relative to the tile start (may be < 0)
+    const int64_t q_begin = (int64_t)(t_lo >> 2), q_end = (int64_t)((t_hi + 3) >> 2);
+    const int32_t head = (int32_t)((q_begin << 2) - (int64_t)t_lo);  // in (-4, 0]
+
+    auto process = [&](int32_t r0, const uint4 &kk, const ulonglong2 &b01, const ulonglong2 &b23) {
       const uint32_t k[4] = {kk.x, kk.y, kk.z, kk.w};
       const uint64_t b[4] = {b01.x, b01.y, b23.x, b23.y};
       uint32_t hitmask = 0;
 #pragma unroll
       for (int e = 0; e < 4; e++) {
-        const uint64_t j = (uint64_t)(j0 + e);
-        if (j < t_lo || j >= t_hi || b[e] == 0ull) continue;
+        const uint32_t r = (uint32_t)(r0 + e);                    // negative wraps to huge: out of range
+        if (r >= tile_n || b[e] == 0ull) continue;
         if (!((occp[k[e] >> 5] >> (k[e] & 31)) & 1u)) continue;  // empty environment leaf
         const uint64_t x = b[e] & env[k[e]];
         if (x == 0ull) continue;
         hitmask |= 1u << e;
         if (STATS) { vox += (unsigned long long)__popcll(x); hits++; }
       }
-      // attribute hits to sets: broadcast the position of each hitting lane's leaves
-      unsigned m = __ballot_sync(0xffffffffu, hitmask != 0);
-      while (m) {
-        const int src = __ffs(m) - 1;
-        m &= m - 1;
-        const int64_t jj = __shfl_sync(0xffffffffu, j0, src);
-        const uint32_t hm = __shfl_sync(0xffffffffu, hitmask, src);
+      // attribute hits to sets: every lane binary-searches the 32 set starts held across the warp
+      if (__any_sync(0xffffffffu, hitmask != 0)) {
 #pragma unroll
-        for (int e = 0; e < 4; e++)
-          if (((hm >> e) & 1u) && lo <= (uint64_t)(jj + e) && (uint64_t)(jj + e) < hi) mine = true;
+        for (int e = 0; e < 4; e++) {
+          if (!__any_sync(0xffffffffu, (hitmask >> e) & 1u)) continue;
+          const uint32_t r = (uint32_t)(r0 + e);
+          int o = 0;
+#pragma unroll
+          for (int step = 16; step > 0; step >>= 1) {
+            const uint32_t v = __shfl_sync(0xffffffffu, rlo, (o + step) & 31);
+            if (v <= r) o += step;  // o + step <= 31 always holds here
+          }
+          if ((hitmask >> e) & 1u) own |= 1u << o;
+        }
       }
     };
 
     // flat walk over the tile's leaves in 16-byte aligned quads, two iterations in flight
-    const int64_t q_begin = (int64_t)(t_lo >> 2), q_end = (int64_t)((t_hi + 3) >> 2);
     for (int64_t qbase = q_begin; qbase < q_end; qbase += 64) {  // warp-uniform trip count
       const int64_t qa = qbase + lane, qb = qa + 32;
       uint4 ka = make_uint4(0, 0, 0, 0), kb = ka;
@@ -135,10 +144,11 @@ voxel_and_popc_kernel(const uint32_t *__restrict__ keys, const uint64_t *__restr
         b01 = __ldcs(reinterpret_cast<const ulonglong2 *>(bits) + 2 * qb);
         b23 = __ldcs(reinterpret_cast<const ulonglong2 *>(bits) + 2 * qb + 1);
       }
-      if (__any_sync(0xffffffffu, va)) process(qa << 2, ka, a01, a23);
-      if (__any_sync(0xffffffffu, vb)) process(qb << 2, kb, b01, b23);
+      const int32_t ra = head + (int32_t)((qa - q_begin) << 2);
+      process(ra, ka, a01, a23);
+      if (qbase + 32 < q_end) process(ra + 128, kb, b01, b23);
     }
-    const unsigned word = __ballot_sync(0xffffffffu, mine);
+    const unsigned word = __reduce_or_sync(0xffffffffu, own);
     if (lane == 0) verdict[tile] = word;
   }
   if (STATS) {

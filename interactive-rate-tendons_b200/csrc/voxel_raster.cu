@@ -681,6 +681,58 @@ int irt_voxelize_vertices(irt_ctx *ctx, const irt_robot *rb, const double *state
   return IRT_OK;
 }
 
+int irt_voxelize_shapes(irt_ctx *ctx, const double *p, const int32_t *npts, int cap_pts, int64_t n,
+                        irt_setstore *store) {
+  if (!ctx || !store || n < 0 || cap_pts < 1 || (n > 0 && (!p || !npts))) return IRT_ERR_INVALID_ARGUMENT;
+  for (int64_t i = 0; i < n; i++)
+    if (npts[i] < 0 || npts[i] > cap_pts) return irt_fail(ctx, IRT_ERR_INVALID_ARGUMENT, "npts[%lld] out of range", (long long)i);
+  IRT_CUDA(ctx, cudaSetDevice(ctx->device));
+  cudaStream_t st = ctx->stream;
+  const GridDev &g = store->gd;
+  if (n == 0) {
+    int rc = setstore_reserve(ctx, store, 0, 0);
+    if (rc) return rc;
+    IRT_CUDA(ctx, cudaMemsetAsync(store->d_offsets, 0, 8, st));
+    return setstore_finalize(ctx, store, 0, 0, st);
+  }
+  DevMem mem;
+  double *d_p;
+  int32_t *d_npts, *d_heads;
+  uint32_t *d_flags, *d_counts;
+  uint64_t *d_scan_tmp;
+  const int64_t ntiles = (n + SCAN_TILE - 1) / SCAN_TILE;
+  if (!mem.alloc(&d_p, (size_t)n * cap_pts * 3) || !mem.alloc(&d_npts, (size_t)n) ||
+      !mem.alloc(&d_heads, (size_t)n) || !mem.alloc(&d_flags, (size_t)n) ||
+      !mem.alloc(&d_counts, (size_t)n) || !mem.alloc(&d_scan_tmp, (size_t)ntiles + 2))
+    return irt_fail(ctx, IRT_ERR_CUDA, "device allocation failed");
+  IRT_CUDA(ctx, cudaMemcpyAsync(d_p, p, (size_t)n * cap_pts * 24, cudaMemcpyHostToDevice, st));
+  IRT_CUDA(ctx, cudaMemcpyAsync(d_npts, npts, (size_t)n * 4, cudaMemcpyHostToDevice, st));
+  IRT_CUDA(ctx, cudaMemsetAsync(d_flags, 0, (size_t)n * 4, st));
+  const int T = 256;
+  vertex_heads_kernel<<<(unsigned)((n + T - 1) / T), T, 0, st>>>(d_flags, n, d_heads);
+  IRT_LAUNCHED(ctx);
+  int rc = setstore_reserve(ctx, store, n, 0);
+  if (rc) return rc;
+  uint64_t total = 0;
+  rc = raster_to_store(ctx, g, d_p, d_npts, cap_pts, d_heads, nullptr, nullptr, nullptr, n, nullptr,
+                       nullptr, d_flags, d_counts, d_scan_tmp, store, 0, store->d_offsets, &total, st);
+  if (rc) return rc;
+  rc = setstore_reserve(ctx, store, n, (int64_t)total);
+  if (rc) return rc;
+  int64_t blocks = (n + RS_WARPS - 1) / RS_WARPS;
+  const int64_t max_blocks = (int64_t)ctx->sm_count * 8;
+  if (blocks > max_blocks) blocks = max_blocks;
+  swept_voxel_raster_kernel<true><<<(unsigned)blocks, RS_WARPS * 32, RS_SMEM, st>>>(
+      g, d_p, d_npts, cap_pts, d_heads, nullptr, nullptr, nullptr, n, nullptr, nullptr, nullptr,
+      store->d_offsets, store->d_keys, store->d_bits, nullptr);
+  IRT_LAUNCHED(ctx);
+  IRT_CUDA(ctx, cudaGetLastError());
+  rc = setstore_finalize(ctx, store, n, (int64_t)total, st);
+  if (rc) return rc;
+  IRT_CUDA(ctx, cudaStreamSynchronize(st));
+  return IRT_OK;
+}
+
 int irt_voxelize_edges(irt_ctx *ctx, const irt_robot *rb, const irt_space *space, const double *a,
                        const double *b, int state_size, int64_t n, irt_setstore *store,
                        uint32_t *flags, double *t_last, int32_t *nsamples) {

@@ -1,0 +1,652 @@
+// irt_host.hpp -- C++ host mirror of the reference's operator interface for the hot path,
+// implemented entirely on top of the C ABI (include/irt_b200.h -> libirt_b200.so, CUDA sm_100a).
+//
+// Same class names, member names, argument meaning and error behaviour as the reference so that
+// planner code above the boundary (VoxelCachedLazyPRM's batch loops, apps) reads unchanged:
+//
+//   tendon::BackboneSpecs / TendonSpecs / TendonResult / TendonRobot
+//        tendon/BackboneSpecs.h:15-21, TendonSpecs.h:24-40, TendonResult.h:17-40, TendonRobot.h:52-355
+//   collision::VoxelOctree                          collision/VoxelOctree.h:68-330 (value type: block
+//        storage + set algebra; voxelisation and collides() run on the GPU)
+//   motion_planning::VoxelEnvironment, VoxelBackboneValidityChecker, VoxelBackboneMotionValidator
+//        motion-planning/VoxelEnvironment.h:137-167, AbstractVoxelValidityChecker.h:33-52,
+//        AbstractVoxelMotionValidator.h:98-135
+//   motion_planning::VoxelCachedLazyPRM (batch entry points only)
+//        motion-planning/VoxelCachedLazyPRM.h:495-520, .cpp:1563-1782
+//
+// Status codes are translated back into the reference's exception types:
+//   IRT_ERR_INVALID_ARGUMENT -> std::invalid_argument   IRT_ERR_OUT_OF_RANGE -> std::out_of_range
+//   IRT_ERR_DOMAIN -> std::domain_error                 everything else -> std::runtime_error
+// There is no CPU fallback: without a CUDA device the Context constructor throws.
+#pragma once
+
+#include <array>
+#include <cmath>
+#include <cstdint>
+#include <cstring>
+#include <functional>
+#include <map>
+#include <memory>
+#include <stdexcept>
+#include <string>
+#include <tuple>
+#include <utility>
+#include <vector>
+
+#include "../../include/irt_b200.h"
+
+namespace irt {
+
+inline void check(irt_ctx *ctx, int rc) {
+  if (rc == IRT_OK) return;
+  std::string msg = std::string(irt_status_string(rc)) + ": " + (ctx ? irt_last_error(ctx) : "");
+  switch (rc) {
+    case IRT_ERR_INVALID_ARGUMENT: throw std::invalid_argument(msg);
+    case IRT_ERR_OUT_OF_RANGE: throw std::out_of_range(msg);
+    case IRT_ERR_DOMAIN: throw std::domain_error(msg);
+    default: throw std::runtime_error(msg);
+  }
+}
+
+/// one CUDA device + stream; shared by every mirrored object
+class Context {
+public:
+  explicit Context(int device = 0) {
+    int rc = irt_ctx_create(device, &ctx_);
+    if (rc != IRT_OK) throw std::runtime_error(std::string("irt_b200: ") + irt_status_string(rc));
+  }
+  ~Context() { irt_ctx_destroy(ctx_); }
+  Context(const Context &) = delete;
+  Context &operator=(const Context &) = delete;
+  irt_ctx *get() const { return ctx_; }
+  static std::shared_ptr<Context> &global() {
+    static std::shared_ptr<Context> g;
+    if (!g) g = std::make_shared<Context>(0);
+    return g;
+  }
+
+private:
+  irt_ctx *ctx_ = nullptr;
+};
+
+}  // namespace irt
+
+namespace collision {
+using Point = std::array<double, 3>;
+}
+
+namespace tendon {
+
+struct BackboneSpecs {  // tendon/BackboneSpecs.h:15-21
+  double L = 0.2, dL = 0.005, ro = 0.01, ri = 0.0, E = 2.1e6, nu = 0.3;
+};
+
+struct TendonSpecs {  // tendon/TendonSpecs.h:24-40
+  std::vector<double> C, D;
+  double max_tension = 20.0, min_length = -0.015, max_length = 0.035;
+  static size_t poly_degree(const std::vector<double> &c, double eps) {  // TendonSpecs.cpp:17-25
+    if (c.empty()) return 0;
+    for (size_t i = c.size() - 1; i > 0; i--)
+      if (std::abs(c[i]) > eps) return i;
+    return 0;
+  }
+  size_t r_degree(double eps = 0.0) const { return poly_degree(D, eps); }
+  size_t theta_degree(double eps = 0.0) const { return poly_degree(C, eps); }
+  bool is_straight(double eps = 0.0) const { return r_degree(eps) == 0 && theta_degree(eps) == 0; }
+  bool is_helix(double eps = 0.0) const { return r_degree(eps) == 0 && theta_degree(eps) == 1; }
+};
+
+struct TendonResult {  // tendon/TendonResult.h:17-40
+  std::vector<double> t;
+  std::vector<collision::Point> p;
+  std::vector<std::array<double, 9>> R;  // column-major 3x3, like Eigen::Matrix3d storage
+  double L = 0.0;
+  std::vector<double> L_i;
+  std::array<double, 3> u_i{0, 0, 0}, u_f{0, 0, 0}, v_i{0, 0, 1}, v_f{0, 0, 1};
+  bool converged = true;
+  /// device-computed validity word of this shape (IRT_FLAG_*); not a reference member
+  uint32_t flags = 0;
+
+  void rotate_z(double theta) {  // tendon/TendonResult.cpp:13-18
+    const double c = std::cos(theta), s = std::sin(theta);
+    for (auto &q : p) q = {c * q[0] - s * q[1], s * q[0] + c * q[1], q[2]};
+    for (auto &m : R)
+      for (int j = 0; j < 3; j++) {
+        const double a = m[3 * j], b = m[3 * j + 1];
+        m[3 * j] = c * a - s * b;
+        m[3 * j + 1] = s * a + c * b;
+      }
+  }
+};
+
+struct TendonRobot {  // tendon/TendonRobot.h:52-355
+  double r = 0.015;
+  BackboneSpecs specs{};
+  std::vector<TendonSpecs> tendons;
+  bool enable_rotation = false, enable_retraction = false;
+  double residual_threshold = 5e-6;
+
+  size_t state_size() const { return tendons.size() + (enable_rotation ? 1 : 0) + (enable_retraction ? 1 : 0); }
+
+  irt_robot_desc desc() const {
+    irt_robot_desc d;
+    std::memset(&d, 0, sizeof(d));
+    d.r = r; d.L = specs.L; d.dL = specs.dL; d.ro = specs.ro; d.ri = specs.ri; d.E = specs.E; d.nu = specs.nu;
+    d.residual_threshold = residual_threshold;
+    if (tendons.size() > IRT_MAX_TENDONS) throw std::out_of_range("too many tendons");
+    d.n_tendons = (int32_t)tendons.size();
+    d.n_c = tendons.empty() ? 0 : (int32_t)tendons[0].C.size();
+    d.n_d = tendons.empty() ? 0 : (int32_t)tendons[0].D.size();
+    if (d.n_c > IRT_MAX_COEF || d.n_d > IRT_MAX_COEF) throw std::out_of_range("too many coefficients");
+    for (size_t j = 0; j < tendons.size(); j++) {
+      // get_r_info.h:34-39: every tendon is evaluated with tendon 0's coefficient counts
+      for (int i = 0; i < d.n_c && i < (int)tendons[j].C.size(); i++) d.C[j * IRT_MAX_COEF + i] = tendons[j].C[i];
+      for (int i = 0; i < d.n_d && i < (int)tendons[j].D.size(); i++) d.D[j * IRT_MAX_COEF + i] = tendons[j].D[i];
+      d.max_tension[j] = tendons[j].max_tension;
+      d.min_length[j] = tendons[j].min_length;
+      d.max_length[j] = tendons[j].max_length;
+    }
+    d.enable_rotation = enable_rotation ? 1 : 0;
+    d.enable_retraction = enable_retraction ? 1 : 0;
+    return d;
+  }
+
+  /// device handle (robot constants + routing tables), rebuilt when the description changes
+  irt_robot *handle() const {
+    irt_robot_desc d = desc();
+    if (!dev_ || std::memcmp(&d, &cached_, sizeof(d)) != 0) {
+      ctx_ = irt::Context::global();
+      irt_robot *h = nullptr;
+      irt::check(ctx_->get(), irt_robot_create(ctx_->get(), &d, &h));
+      dev_ = std::shared_ptr<irt_robot>(h, [](irt_robot *x) { irt_robot_destroy(x); });
+      cached_ = d;
+    }
+    return dev_.get();
+  }
+  irt_ctx *ctx() const { handle(); return ctx_->get(); }
+
+  /// TendonRobot::shape for a batch (the OpenMP loops of apps/estimate_length_discretization.cpp:62-71)
+  std::vector<TendonResult> shape_batch(const std::vector<std::vector<double>> &states) const {
+    const size_t S = state_size(), n = states.size(), N = tendons.size();
+    for (auto &s : states)
+      if (s.size() != S) throw std::invalid_argument("State is not the right size");  // TendonRobot.h:107-109
+    irt_robot *h = handle();
+    const int cap = irt_robot_max_points(h);
+    std::vector<double> flat(n * S), p(n * cap * 3), R(n * cap * 9), t(n * cap), L(n), Li(n * N), uv(n * 12);
+    std::vector<int32_t> npts(n);
+    std::vector<uint32_t> flags(n);
+    for (size_t i = 0; i < n; i++) std::copy(states[i].begin(), states[i].end(), flat.begin() + i * S);
+    irt_fk_outputs o;
+    std::memset(&o, 0, sizeof(o));
+    o.p = p.data(); o.R = R.data(); o.t = t.data(); o.npts = npts.data(); o.L = L.data();
+    o.L_i = Li.data(); o.uv = uv.data(); o.flags = flags.data();
+    irt::check(ctx_->get(), irt_fk_batch(ctx_->get(), h, flat.data(), (int)S, (int64_t)n, cap, &o));
+    std::vector<TendonResult> out(n);
+    for (size_t i = 0; i < n; i++) {
+      TendonResult &r = out[i];
+      const int m = npts[i];
+      r.t.assign(t.begin() + i * cap, t.begin() + i * cap + m);
+      r.p.resize(m); r.R.resize(m);
+      for (int k = 0; k < m; k++) {
+        std::memcpy(r.p[k].data(), &p[(i * cap + k) * 3], 24);
+        std::memcpy(r.R[k].data(), &R[(i * cap + k) * 9], 72);
+      }
+      r.L = L[i];
+      r.L_i.assign(Li.begin() + i * N, Li.begin() + (i + 1) * N);
+      for (int c = 0; c < 3; c++) {
+        r.u_i[c] = uv[i * 12 + c]; r.u_f[c] = uv[i * 12 + 3 + c];
+        r.v_i[c] = uv[i * 12 + 6 + c]; r.v_f[c] = uv[i * 12 + 9 + c];
+      }
+      r.flags = flags[i];
+      r.converged = !(flags[i] & IRT_FLAG_NONCONVERGED);
+    }
+    return out;
+  }
+
+  TendonResult shape(const std::vector<double> &state) const { return shape_batch({state})[0]; }
+  TendonResult shape(const std::vector<double> &tau, double rotation, double retraction) const {
+    if (tau.size() != tendons.size()) throw std::out_of_range("tendons and tau are not the same length");
+    std::vector<double> st(tau);
+    if (enable_rotation) st.push_back(rotation);
+    if (enable_retraction) st.push_back(retraction);
+    return shape(st);
+  }
+  std::vector<collision::Point> forward_kinematics(const std::vector<double> &state) const { return shape(state).p; }
+
+  /// home_shape (tendon/TendonRobot.cpp:249-314): straight backbone, closed-form tendon lengths
+  TendonResult home_shape(double s_start = 0) const {
+    if (s_start < 0.0) s_start = 0.0;
+    if (s_start > specs.L) s_start = specs.L;
+    std::vector<double> st(state_size(), 0.0);
+    const bool had_ret = enable_retraction;
+    TendonResult res;
+    if (had_ret) {
+      st.back() = s_start;
+      res = shape(st);  // zero tension == home shape
+    } else {
+      TendonRobot tmp = *this;
+      tmp.enable_retraction = true;
+      tmp.dev_.reset();
+      st.push_back(s_start);
+      res = tmp.shape(st);
+    }
+    std::vector<double> home(tendons.size());
+    std::vector<double> one(state_size(), 0.0);
+    if (enable_retraction) one.back() = s_start;
+    irt::check(ctx(), irt_home_lengths_batch(ctx(), handle(), one.data(), (int)state_size(), 1, home.data()));
+    if (!enable_retraction)
+      for (auto &h : home) h *= (s_start == specs.L) ? 0.0 : (specs.L - s_start) / specs.L;
+    res.L_i = home;
+    return res;
+  }
+  TendonResult home_shape(const std::vector<double> &state) const {
+    return home_shape(enable_retraction ? state.back() : 0.0);
+  }
+
+  std::vector<double> calc_dl(const std::vector<double> &home_l, const std::vector<double> &other_l) const {
+    if (home_l.size() != other_l.size()) throw std::out_of_range("vector size mismatch");
+    std::vector<double> dl(home_l.size());
+    for (size_t i = 0; i < dl.size(); i++) dl[i] = home_l[i] - other_l[i];
+    return dl;
+  }
+  bool is_within_length_limits(const std::vector<double> &dl) const {
+    if (dl.size() != tendons.size()) throw std::out_of_range("length mismatch");
+    for (size_t i = 0; i < dl.size(); i++)
+      if (dl[i] < tendons[i].min_length || tendons[i].max_length < dl[i]) return false;
+    return true;
+  }
+  bool is_within_length_limits(const std::vector<double> &home_l, const std::vector<double> &other_l) const {
+    return is_within_length_limits(calc_dl(home_l, other_l));
+  }
+  /// collides_self of a shape computed by this robot (device verdict carried in TendonResult::flags)
+  bool collides_self(const TendonResult &shape_) const { return (shape_.flags & IRT_FLAG_SELF_COLLISION) != 0; }
+  bool is_valid(const std::vector<double> &state, const TendonResult &, const TendonResult &shape_) const {
+    if (shape_.flags & IRT_FLAG_LENGTH_LIMIT) return false;
+    for (size_t i = 0; i < tendons.size(); i++)
+      if (state[i] < 0.0 || tendons[i].max_tension < state[i]) return false;
+    return !collides_self(shape_);
+  }
+
+private:
+  mutable std::shared_ptr<irt::Context> ctx_;
+  mutable std::shared_ptr<irt_robot> dev_;
+  mutable irt_robot_desc cached_;
+};
+
+}  // namespace tendon
+
+namespace collision {
+
+/// Value-type mirror of collision::VoxelOctree: the sparse set of occupied 4x4x4 leaf blocks.
+/// Storage is a key-ordered map (Morton key == the reference's visit_leaves order); the heavy
+/// operations (voxelising shapes, collides) go through the C ABI.
+class VoxelOctree {
+public:
+  using BlockType = uint64_t;
+  using ConstBlockVisitor = std::function<void(size_t, size_t, size_t, uint64_t)>;
+
+  explicit VoxelOctree(size_t Ndim = 4) : N_(Ndim) {
+    // collision/VoxelOctree.cpp:83-116
+    if (Ndim < 4 || Ndim > 512 || (Ndim & (Ndim - 1)))
+      throw std::invalid_argument("unsupported voxel dimension: " + std::to_string(Ndim));
+    set_xlim(0.0, 1.0); set_ylim(0.0, 1.0); set_zlim(0.0, 1.0);
+  }
+  size_t Nx() const { return N_; }
+  size_t Ny() const { return N_; }
+  size_t Nz() const { return N_; }
+  size_t Nbx() const { return N_ / 4; }
+  void set_xlim(double a, double b) { lim_check(a, b); lim_[0] = a; lim_[1] = b; }
+  void set_ylim(double a, double b) { lim_check(a, b); lim_[2] = a; lim_[3] = b; }
+  void set_zlim(double a, double b) { lim_check(a, b); lim_[4] = a; lim_[5] = b; }
+  std::pair<double, double> xlim() const { return {lim_[0], lim_[1]}; }
+  std::pair<double, double> ylim() const { return {lim_[2], lim_[3]}; }
+  std::pair<double, double> zlim() const { return {lim_[4], lim_[5]}; }
+  double dx() const { return (lim_[1] - lim_[0]) / N_; }
+  double dy() const { return (lim_[3] - lim_[2]) / N_; }
+  double dz() const { return (lim_[5] - lim_[4]) / N_; }
+  void copy_limits(const VoxelOctree &o) { lim_ = o.lim_; }
+  VoxelOctree empty_copy() const { VoxelOctree c(N_); c.lim_ = lim_; return c; }
+  bool is_empty() const { return blocks_.empty(); }
+  size_t nblocks() const { return blocks_.size(); }
+  size_t ncells() const {
+    size_t c = 0;
+    for (auto &kv : blocks_) c += (size_t)__builtin_popcountll(kv.second);
+    return c;
+  }
+  uint64_t block(size_t bx, size_t by, size_t bz) const {
+    auto it = blocks_.find(key(bx, by, bz));
+    return it == blocks_.end() ? 0 : it->second;
+  }
+  void set_block(size_t bx, size_t by, size_t bz, uint64_t v) {
+    if (v) blocks_[key(bx, by, bz)] = v; else blocks_.erase(key(bx, by, bz));
+  }
+  uint64_t union_block(size_t bx, size_t by, size_t bz, uint64_t v) {
+    uint64_t old = block(bx, by, bz);
+    if (v) blocks_[key(bx, by, bz)] = old | v;
+    return old;
+  }
+  bool cell(size_t ix, size_t iy, size_t iz) const {
+    return (block(ix / 4, iy / 4, iz / 4) >> ((ix % 4) * 16 + (iy % 4) * 4 + (iz % 4))) & 1u;
+  }
+  void add_voxels(const VoxelOctree &o) {
+    check_dims(o);
+    for (auto &kv : o.blocks_) blocks_[kv.first] |= kv.second;
+  }
+  void visit_leaves(const ConstBlockVisitor &f) const {
+    for (auto &kv : blocks_) {
+      int bx, by, bz;
+      irt_morton_decode(kv.first, (int)(N_ / 4), &bx, &by, &bz);
+      f((size_t)bx, (size_t)by, (size_t)bz, kv.second);
+    }
+  }
+  bool operator==(const VoxelOctree &o) const { return N_ == o.N_ && lim_ == o.lim_ && blocks_ == o.blocks_; }
+
+  irt_grid grid(const std::array<double, 9> &inv_rot = {1, 0, 0, 0, 1, 0, 0, 0, 1}) const {
+    irt_grid g;
+    std::memset(&g, 0, sizeof(g));
+    g.Ng = (int32_t)N_;
+    for (int i = 0; i < 6; i++) g.lim[i] = lim_[i];
+    for (int i = 0; i < 9; i++) g.inv_rot[i] = inv_rot[i];
+    return g;
+  }
+
+  /// voxels of a backbone polyline: add_piecewise_line (collision/VoxelOctree.cpp:428-432), on the GPU
+  void add_piecewise_line(const std::vector<Point> &line) {
+    auto ctx = irt::Context::global();
+    irt_grid g = grid();
+    irt_setstore *st = nullptr;
+    irt::check(ctx->get(), irt_setstore_create(ctx->get(), &g, &st));
+    std::shared_ptr<irt_setstore> guard(st, [](irt_setstore *x) { irt_setstore_destroy(x); });
+    int32_t n = (int32_t)line.size();
+    std::vector<double> flat(3 * std::max<size_t>(1, line.size()));
+    for (size_t i = 0; i < line.size(); i++) std::memcpy(&flat[3 * i], line[i].data(), 24);
+    irt::check(ctx->get(), irt_voxelize_shapes(ctx->get(), flat.data(), &n, std::max(1, (int)line.size()), 1, st));
+    merge_store(ctx->get(), st, 0);
+  }
+
+  /// collides(other): VoxelOctree.cpp:973-978, K3 on the GPU (this = environment, other = set)
+  bool collides(const VoxelOctree &other) const {
+    check_dims(other);  // std::invalid_argument on mismatch (VoxelOctree.cpp:46-53)
+    auto ctx = irt::Context::global();
+    irt_grid g = grid();
+    irt_env *env = nullptr;
+    irt::check(ctx->get(), irt_env_create(ctx->get(), &g, &env));
+    std::shared_ptr<irt_env> eg(env, [](irt_env *x) { irt_env_destroy(x); });
+    upload_env(ctx->get(), env);
+    irt_setstore *st = nullptr;
+    irt::check(ctx->get(), irt_setstore_create(ctx->get(), &g, &st));
+    std::shared_ptr<irt_setstore> sg(st, [](irt_setstore *x) { irt_setstore_destroy(x); });
+    other.to_store(ctx->get(), st);
+    uint32_t word = 0;
+    irt::check(ctx->get(), irt_check_sets(ctx->get(), st, env, 0, 1, &word));
+    return word & 1u;
+  }
+
+  // ---- helpers used by the validators ------------------------------------------------------
+  void upload_env(irt_ctx *ctx, irt_env *env) const {
+    std::vector<uint8_t> xyz(3 * blocks_.size() + 3);
+    std::vector<uint64_t> bits(blocks_.size() + 1);
+    size_t i = 0;
+    for (auto &kv : blocks_) {
+      int bx, by, bz;
+      irt_morton_decode(kv.first, (int)(N_ / 4), &bx, &by, &bz);
+      xyz[3 * i] = (uint8_t)bx; xyz[3 * i + 1] = (uint8_t)by; xyz[3 * i + 2] = (uint8_t)bz;
+      bits[i++] = kv.second;
+    }
+    irt::check(ctx, irt_env_update_sparse(ctx, env, xyz.data(), bits.data(), (int64_t)blocks_.size()));
+  }
+  void to_store(irt_ctx *ctx, irt_setstore *st) const {
+    std::vector<uint64_t> off{0, (uint64_t)blocks_.size()}, bits;
+    std::vector<uint32_t> keys;
+    for (auto &kv : blocks_) { keys.push_back(kv.first); bits.push_back(kv.second); }
+    keys.push_back(0); bits.push_back(0);
+    irt::check(ctx, irt_setstore_import(ctx, st, 1, off.data(), keys.data(), bits.data()));
+  }
+  /// OR set `i` of a device store into this octree
+  void merge_store(irt_ctx *ctx, irt_setstore *st, int64_t i) {
+    const int64_t n = irt_setstore_num_sets(st), nb = irt_setstore_num_blocks(st);
+    std::vector<uint64_t> off(n + 1), bits(nb + 1);
+    std::vector<uint32_t> keys(nb + 1);
+    irt::check(ctx, irt_setstore_export(ctx, st, off.data(), keys.data(), bits.data()));
+    for (uint64_t j = off[i]; j < off[i + 1]; j++) blocks_[keys[j]] |= bits[j];
+  }
+  static VoxelOctree from_store(irt_ctx *ctx, irt_setstore *st, int64_t i, const VoxelOctree &like) {
+    VoxelOctree v = like.empty_copy();
+    v.merge_store(ctx, st, i);
+    return v;
+  }
+
+private:
+  static void lim_check(double a, double b) {
+    if (a >= b) throw std::length_error("limits must be positive in size");  // VoxelOctree.cpp:152-177
+  }
+  void check_dims(const VoxelOctree &o) const {
+    if (N_ != o.N_)
+      throw std::invalid_argument("voxel dimension mismatch (" + std::to_string(N_) + " != " + std::to_string(o.N_) + ")");
+  }
+  uint32_t key(size_t bx, size_t by, size_t bz) const { return irt_morton_key((int)bx, (int)by, (int)bz, (int)(N_ / 4)); }
+  size_t N_;
+  std::array<double, 6> lim_{};
+  std::map<uint32_t, uint64_t> blocks_;
+};
+
+}  // namespace collision
+
+namespace motion_planning {
+
+/// the part of VoxelEnvironment the hot path uses: inv_rotation + PartialVoxelization
+struct VoxelEnvironment {
+  std::array<double, 9> inv_rotation{1, 0, 0, 0, 1, 0, 0, 0, 1};  // row-major
+  struct PartialVoxelization {  // VoxelEnvironment.h:137-143
+    bool is_fully_valid = false;
+    double t = 0.0;
+    std::vector<double> last_valid;
+    std::vector<collision::Point> last_backbone;
+    collision::VoxelOctree voxels;
+  };
+};
+
+/// AbstractVoxelValidityChecker / VoxelBackboneValidityChecker (AbstractVoxelValidityChecker.h:17-65,
+/// VoxelBackboneValidityChecker.h:20-57) without the OMPL base class
+class VoxelBackboneValidityChecker {
+public:
+  VoxelBackboneValidityChecker(const tendon::TendonRobot &robot, const VoxelEnvironment &venv,
+                               collision::VoxelOctree voxels)
+      : robot_(robot), venv_(venv), voxels_(std::move(voxels)) {
+    const double mx = std::max({voxels_.dx(), voxels_.dy(), voxels_.dz()});
+    if (robot.specs.dL > mx)  // VoxelBackboneValidityChecker.h:37-45
+      throw std::invalid_argument("robot.specs.dL is larger than expected by VoxelBackboneValidityChecker");
+    home_ = robot.home_shape();
+  }
+  std::pair<tendon::TendonResult, tendon::TendonResult> fk(const std::vector<double> &state) const {
+    return {robot_.shape(state), robot_.enable_retraction ? robot_.home_shape(state) : home_};
+  }
+  bool is_valid_shape(const tendon::TendonResult &fk_shape, const tendon::TendonResult &home_shape) const {
+    if (!fk_shape.converged || !home_shape.converged) return false;  // AbstractValidityChecker.cpp:99-114
+    if (!robot_.is_within_length_limits(robot_.calc_dl(home_shape.L_i, fk_shape.L_i))) return false;
+    return !robot_.collides_self(fk_shape);
+  }
+  collision::VoxelOctree voxelize(const tendon::TendonResult &fk_shape) const {
+    auto ctx = irt::Context::global();
+    irt_grid g = voxels_.grid(venv_.inv_rotation);
+    irt_setstore *st = nullptr;
+    irt::check(ctx->get(), irt_setstore_create(ctx->get(), &g, &st));
+    std::shared_ptr<irt_setstore> guard(st, [](irt_setstore *x) { irt_setstore_destroy(x); });
+    int32_t n = (int32_t)fk_shape.p.size();
+    std::vector<double> flat(3 * std::max<size_t>(1, fk_shape.p.size()));
+    for (size_t i = 0; i < fk_shape.p.size(); i++) std::memcpy(&flat[3 * i], fk_shape.p[i].data(), 24);
+    irt::check(ctx->get(), irt_voxelize_shapes(ctx->get(), flat.data(), &n, std::max(1, n), 1, st));
+    return collision::VoxelOctree::from_store(ctx->get(), st, 0, voxels_);
+  }
+  bool collides(const collision::VoxelOctree &v) const { return voxels_.collides(v); }
+  const collision::VoxelOctree &voxels() const { return voxels_; }
+  const tendon::TendonRobot &robot() const { return robot_; }
+  const VoxelEnvironment &venv() const { return venv_; }
+
+private:
+  const tendon::TendonRobot &robot_;
+  const VoxelEnvironment &venv_;
+  collision::VoxelOctree voxels_;
+  tendon::TendonResult home_;
+};
+
+/// AbstractVoxelMotionValidator / VoxelBackboneMotionValidator (AbstractVoxelMotionValidator.h:32-193,
+/// VoxelBackboneMotionValidator.cpp:19-91); the OMPL space constants come from irt_space
+class VoxelBackboneMotionValidator {
+public:
+  using PartialVoxelization = VoxelEnvironment::PartialVoxelization;
+  VoxelBackboneMotionValidator(const tendon::TendonRobot &robot, const VoxelEnvironment &venv,
+                               collision::VoxelOctree voxels, irt_space space = {0.02, 0.01, 0.0001})
+      : robot_(robot), venv_(venv), voxels_(std::move(voxels)), space_(space) {}
+
+  PartialVoxelization voxelize(const std::vector<double> &a, const std::vector<double> &b) const {
+    const size_t S = robot_.state_size();
+    if (a.size() != S || b.size() != S) throw std::invalid_argument("start and end are different sizes");
+    irt_ctx *ctx = robot_.ctx();
+    irt_grid g = voxels_.grid(venv_.inv_rotation);
+    irt_setstore *st = nullptr;
+    irt::check(ctx, irt_setstore_create(ctx, &g, &st));
+    std::shared_ptr<irt_setstore> guard(st, [](irt_setstore *x) { irt_setstore_destroy(x); });
+    uint32_t flags = 0;
+    double t_last = 0.0;
+    int32_t ns = 0;
+    irt::check(ctx, irt_voxelize_edges(ctx, robot_.handle(), &space_, a.data(), b.data(), (int)S, 1, st, &flags,
+                                       &t_last, &ns));
+    if (flags & IRT_FLAG_OUT_OF_DOMAIN) throw std::domain_error("point is out of the voxel dimensions");
+    PartialVoxelization pv;
+    pv.is_fully_valid = !(flags & IRT_FLAG_PARTIAL);
+    if (!pv.is_fully_valid) num_voxelize_errors_++;  // AbstractVoxelMotionValidator.h:105
+    pv.t = t_last;
+    pv.last_valid = interpolate(a, b, t_last);
+    pv.last_backbone = robot_.shape(pv.last_valid).p;
+    pv.voxels = collision::VoxelOctree::from_store(ctx, st, 0, voxels_);
+    return pv;
+  }
+  bool collides(const collision::VoxelOctree &swept) const { return voxels_.collides(swept); }
+  size_t num_voxelize_errors() const { return num_voxelize_errors_; }
+  uint32_t valid_segment_count(const std::vector<double> &a, const std::vector<double> &b) const {
+    irt_robot_desc d = robot_.desc();
+    return irt_valid_segment_count(&d, &space_, a.data(), b.data());
+  }
+  /// OMPL compound interpolate restated (RealVector linear, SO2 shortest arc + wrap)
+  std::vector<double> interpolate(const std::vector<double> &a, const std::vector<double> &b, double t) const {
+    std::vector<double> out(a.size());
+    const size_t N = robot_.tendons.size();
+    for (size_t i = 0; i < a.size(); i++) out[i] = a[i] + (b[i] - a[i]) * t;
+    if (robot_.enable_rotation) {
+      double diff = b[N] - a[N];
+      if (std::fabs(diff) > M_PI) {
+        diff = (diff > 0.0) ? 2.0 * M_PI - diff : -2.0 * M_PI - diff;
+        double v = a[N] - diff * t;
+        if (v > M_PI) v -= 2.0 * M_PI; else if (v < -M_PI) v += 2.0 * M_PI;
+        out[N] = v;
+      }
+    }
+    return out;
+  }
+
+private:
+  const tendon::TendonRobot &robot_;
+  const VoxelEnvironment &venv_;
+  collision::VoxelOctree voxels_;
+  irt_space space_;
+  mutable size_t num_voxelize_errors_ = 0;
+};
+
+/// batch entry points of VoxelCachedLazyPRM (VoxelCachedLazyPRM.h:495-520): the graph lives in
+/// (states, edges); the voxel caches live on the device; validity words mirror
+/// vertexValidityProperty_ / edgeValidityProperty_ (VALIDITY_UNKNOWN = 0, VALIDITY_TRUE = 1).
+class VoxelCachedLazyPRM {
+public:
+  static constexpr unsigned VALIDITY_UNKNOWN = 0, VALIDITY_TRUE = 1;  // VoxelCachedLazyPRM.h:598-601
+  VoxelCachedLazyPRM(const tendon::TendonRobot &robot, const VoxelEnvironment &venv,
+                     const collision::VoxelOctree &env_voxels, irt_space space = {0.02, 0.01, 0.0001})
+      : robot_(robot), venv_(venv), env_voxels_(env_voxels), space_(space) {
+    ctx_ = robot.ctx();
+    irt_grid g = env_voxels_.grid(venv_.inv_rotation);
+    irt::check(ctx_, irt_setstore_create(ctx_, &g, &vstore_));
+    irt::check(ctx_, irt_setstore_create(ctx_, &g, &estore_));
+    irt::check(ctx_, irt_env_create(ctx_, &g, &env_));
+    env_voxels_.upload_env(ctx_, env_);
+  }
+  ~VoxelCachedLazyPRM() {
+    irt_setstore_destroy(vstore_); irt_setstore_destroy(estore_); irt_env_destroy(env_);
+  }
+  void setRoadmap(std::vector<std::vector<double>> states, std::vector<std::pair<size_t, size_t>> edges) {
+    states_ = std::move(states); edges_ = std::move(edges);
+    vflags_.clear(); eflags_.clear();
+    clearValidity();
+  }
+  void precomputeVertexVoxelCache() {  // .cpp:1687-1734
+    const size_t S = robot_.state_size(), n = states_.size();
+    std::vector<double> flat(n * S);
+    for (size_t i = 0; i < n; i++) std::copy(states_[i].begin(), states_[i].end(), flat.begin() + i * S);
+    vflags_.assign(n, 0); tips_.assign(3 * n, 0.0);
+    irt::check(ctx_, irt_voxelize_vertices(ctx_, robot_.handle(), flat.data(), (int)S, (int64_t)n, vstore_,
+                                           vflags_.data(), tips_.data()));
+  }
+  void precomputeEdgeVoxelCache() {  // .cpp:1736-1782
+    const size_t S = robot_.state_size(), n = edges_.size();
+    std::vector<double> a(n * S), b(n * S);
+    for (size_t i = 0; i < n; i++) {
+      std::copy(states_[edges_[i].first].begin(), states_[edges_[i].first].end(), a.begin() + i * S);
+      std::copy(states_[edges_[i].second].begin(), states_[edges_[i].second].end(), b.begin() + i * S);
+    }
+    eflags_.assign(n, 0);
+    irt::check(ctx_, irt_voxelize_edges(ctx_, robot_.handle(), &space_, a.data(), b.data(), (int)S, (int64_t)n,
+                                        estore_, eflags_.data(), nullptr, nullptr));
+  }
+  void precomputeVoxelCache() { precomputeVertexVoxelCache(); precomputeEdgeVoxelCache(); }
+  void precomputeVertexValidity() {  // .cpp:1563-1598 with warm caches
+    if (vflags_.size() != states_.size()) precomputeVertexVoxelCache();
+    sweep(vstore_, vflags_, IRT_FLAG_NONCONVERGED | IRT_FLAG_LENGTH_LIMIT | IRT_FLAG_SELF_COLLISION | IRT_FLAG_BAD_STATE,
+          vertex_validity_);
+  }
+  void precomputeEdgeValidity() {  // .cpp:1600-1647
+    if (eflags_.size() != edges_.size()) precomputeEdgeVoxelCache();
+    sweep(estore_, eflags_, IRT_FLAG_PARTIAL, edge_validity_);
+  }
+  void precomputeValidity() { precomputeVertexValidity(); precomputeEdgeValidity(); }
+  void clearValidity() {  // .cpp:1656-1663
+    vertex_validity_.assign(states_.size(), VALIDITY_UNKNOWN);
+    edge_validity_.assign(edges_.size(), VALIDITY_UNKNOWN);
+  }
+  /// environment replacement (the reference rebuilds its validators, Problem.h:175-216)
+  void setEnvironment(const collision::VoxelOctree &env_voxels) {
+    env_voxels_ = env_voxels;
+    env_voxels_.upload_env(ctx_, env_);
+    clearValidity();
+  }
+  const std::vector<unsigned> &vertexValidity() const { return vertex_validity_; }
+  const std::vector<unsigned> &edgeValidity() const { return edge_validity_; }
+  collision::VoxelOctree vertexVoxels(size_t i) const { return collision::VoxelOctree::from_store(ctx_, vstore_, (int64_t)i, env_voxels_); }
+  collision::VoxelOctree edgeVoxels(size_t i) const { return collision::VoxelOctree::from_store(ctx_, estore_, (int64_t)i, env_voxels_); }
+  const std::vector<uint32_t> &vertexFlags() const { return vflags_; }
+  const std::vector<uint32_t> &edgeFlags() const { return eflags_; }
+
+private:
+  void sweep(irt_setstore *st, const std::vector<uint32_t> &flags, uint32_t mask, std::vector<unsigned> &validity) {
+    const int64_t n = irt_setstore_num_sets(st);
+    std::vector<uint32_t> words((n + 31) / 32 + 1, 0);
+    if (n > 0) irt::check(ctx_, irt_check_sets(ctx_, st, env_, 0, n, words.data()));
+    validity.assign(n, VALIDITY_UNKNOWN);
+    for (int64_t i = 0; i < n; i++) {
+      const bool hit = (words[i >> 5] >> (i & 31)) & 1u;
+      if (!hit && !(flags[i] & mask)) validity[i] = VALIDITY_TRUE;
+    }
+  }
+  const tendon::TendonRobot &robot_;
+  const VoxelEnvironment &venv_;
+  collision::VoxelOctree env_voxels_;
+  irt_space space_;
+  irt_ctx *ctx_ = nullptr;
+  irt_setstore *vstore_ = nullptr, *estore_ = nullptr;
+  irt_env *env_ = nullptr;
+  std::vector<std::vector<double>> states_;
+  std::vector<std::pair<size_t, size_t>> edges_;
+  std::vector<uint32_t> vflags_, eflags_;
+  std::vector<double> tips_;
+  std::vector<unsigned> vertex_validity_, edge_validity_;
+};
+
+}  // namespace motion_planning

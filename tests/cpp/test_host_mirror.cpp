@@ -1,0 +1,205 @@
+// Parity test of the C++ host mirror (interactive-rate-tendons_b200/host/irt_host.hpp) against
+// the CPU oracle, written the way a reference-side test would read.  Built and run by
+// tests/test_gpu_host_cpp.py on the GPU box.  The oracle is linked here as the checker only.
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <random>
+#include <vector>
+
+#include "../../interactive-rate-tendons_b200/host/irt_host.hpp"
+#include "../../oracle/tendon_oracle.h"
+
+static int failures = 0;
+#define CHECK(cond)                                                         \
+  do {                                                                      \
+    if (!(cond)) {                                                          \
+      std::printf("FAIL %s:%d: %s\n", __FILE__, __LINE__, #cond);           \
+      failures++;                                                           \
+    }                                                                       \
+  } while (0)
+
+static orc_robot to_orc(const tendon::TendonRobot &rb) {
+  irt_robot_desc d = rb.desc();
+  orc_robot o;
+  static_assert(sizeof(orc_robot) == sizeof(irt_robot_desc), "POD mirrors must match");
+  std::memcpy(&o, &d, sizeof(o));
+  return o;
+}
+
+int main() {
+  // Robot B: 6 helical tendons, retraction + rotation
+  tendon::TendonRobot robot;
+  robot.specs.dL = 0.003;
+  robot.enable_retraction = true;
+  robot.enable_rotation = true;
+  for (int k = 0; k < 6; k++) {
+    tendon::TendonSpecs t;
+    t.C = {k * M_PI / 3, (k % 2 ? -1.0 : 1.0) * 2 * M_PI / robot.specs.L};
+    t.D = {0.01};
+    robot.tendons.push_back(t);
+  }
+  CHECK(robot.state_size() == 8);
+  CHECK(robot.tendons[0].is_helix() && !robot.tendons[0].is_straight());
+  orc_robot orb = to_orc(robot);
+
+  std::mt19937_64 gen(20220801);
+  std::uniform_real_distribution<double> U(0.0, 1.0);
+  auto sample = [&]() {
+    std::vector<double> s(8);
+    for (int i = 0; i < 6; i++) s[i] = 20.0 * U(gen);
+    s[6] = -M_PI + 2 * M_PI * U(gen);
+    s[7] = robot.specs.L - robot.specs.L * std::cbrt(U(gen));
+    return s;
+  };
+
+  // ---- TendonRobot::shape / forward_kinematics ------------------------------------------
+  std::vector<std::vector<double>> states;
+  for (int i = 0; i < 200; i++) states.push_back(sample());
+  auto shapes = robot.shape_batch(states);
+  double worst = 0;
+  for (size_t i = 0; i < states.size(); i++) {
+    std::vector<double> t(512), p(512 * 3), R(512 * 9);
+    orc_fk_out fo;
+    int n = orc_shape(&orb, states[i].data(), 512, t.data(), p.data(), R.data(), &fo);
+    CHECK(n == (int)shapes[i].p.size());
+    CHECK(shapes[i].converged == (fo.converged != 0));
+    for (int k = 0; k < n; k++) {
+      for (int c = 0; c < 3; c++) worst = std::max(worst, std::fabs(shapes[i].p[k][c] - p[3 * k + c]));
+      for (int c = 0; c < 9; c++) worst = std::max(worst, std::fabs(shapes[i].R[k][c] - R[9 * k + c]));
+      CHECK(std::fabs(shapes[i].t[k] - t[k]) < 1e-15);
+    }
+    for (int j = 0; j < 6; j++) worst = std::max(worst, std::fabs(shapes[i].L_i[j] - fo.L_i[j]));
+    uint32_t want = orc_validity_flags(&orb, states[i].data(), &fo, p.data());
+    CHECK(shapes[i].flags == want);
+  }
+  std::printf("shape: max abs diff %.3g\n", worst);
+  CHECK(worst < 1e-9 * robot.specs.L);
+  CHECK(robot.forward_kinematics(states[0]).size() == shapes[0].p.size());
+  // home shape and length limits
+  {
+    auto home = robot.home_shape(states[3]);
+    std::vector<double> want(6);
+    orc_home_lengths(&orb, states[3][7], want.data());
+    for (int j = 0; j < 6; j++) CHECK(std::fabs(home.L_i[j] - want[j]) < 1e-15);
+    CHECK(std::fabs(home.p.back()[2] - (robot.specs.L - states[3][7])) < 1e-12);
+    auto dl = robot.calc_dl(home.L_i, shapes[3].L_i);
+    CHECK(robot.is_within_length_limits(dl) == !(shapes[3].flags & IRT_FLAG_LENGTH_LIMIT));
+  }
+  // error convention: wrong state size -> std::invalid_argument (TendonRobot.h:107-109)
+  try { robot.shape(std::vector<double>(5, 0.0)); CHECK(false); } catch (const std::invalid_argument &) {}
+
+  // ---- VoxelOctree value type + validators ----------------------------------------------------
+  collision::VoxelOctree env_vox(128);
+  env_vox.set_xlim(-0.21, 0.21); env_vox.set_ylim(-0.21, 0.21); env_vox.set_zlim(-0.21, 0.21);
+  orc_grid og;
+  std::memset(&og, 0, sizeof(og));
+  og.Ng = 128;
+  for (int a = 0; a < 3; a++) { og.lim[2 * a] = -0.21; og.lim[2 * a + 1] = 0.21; }
+  og.inv_rot[0] = og.inv_rot[4] = og.inv_rot[8] = 1;
+  orc_octree *oenv = orc_octree_new(&og);
+  {  // obstacle: a sphere off to the side
+    double c[3] = {0.05, 0.02, 0.12};
+    orc_octree_add_sphere(oenv, c, 0.03);
+    std::vector<uint8_t> xyz(3 * 4096);
+    std::vector<uint64_t> bits(4096);
+    int64_t nb = orc_octree_export(oenv, 4096, xyz.data(), bits.data());
+    for (int64_t i = 0; i < nb; i++) env_vox.set_block(xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2], bits[i]);
+    CHECK((int64_t)env_vox.nblocks() == nb && (int64_t)env_vox.ncells() == orc_octree_ncells(oenv));
+  }
+  try { collision::VoxelOctree bad(100); CHECK(false); } catch (const std::invalid_argument &) {}
+  try { collision::VoxelOctree(64).collides(env_vox); CHECK(false); } catch (const std::invalid_argument &) {}
+
+  motion_planning::VoxelEnvironment venv;
+  motion_planning::VoxelBackboneValidityChecker checker(robot, venv, env_vox);
+  motion_planning::VoxelBackboneMotionValidator validator(robot, venv, env_vox);
+  int n_collide = 0;
+  for (int i = 0; i < 40; i++) {
+    auto [fk_shape, home_shape] = checker.fk(states[i]);
+    bool valid = checker.is_valid_shape(fk_shape, home_shape);
+    CHECK(valid == (shapes[i].flags == 0));
+    auto vox = checker.voxelize(fk_shape);
+    orc_octree *ov = orc_octree_new(&og);
+    std::vector<double> flat(3 * fk_shape.p.size());
+    for (size_t k = 0; k < fk_shape.p.size(); k++) std::memcpy(&flat[3 * k], fk_shape.p[k].data(), 24);
+    orc_voxelize_shape(&og, flat.data(), (int)fk_shape.p.size(), ov);
+    CHECK((int64_t)vox.nblocks() == orc_octree_nblocks(ov) && (int64_t)vox.ncells() == orc_octree_ncells(ov));
+    vox.visit_leaves([&](size_t bx, size_t by, size_t bz, uint64_t b) { CHECK(orc_octree_block(ov, bx, by, bz) == b); });
+    bool hit = checker.collides(vox);
+    CHECK(hit == (orc_octree_collides(oenv, ov) == 1));
+    n_collide += hit;
+    orc_octree_free(ov);
+  }
+  std::printf("vertex checks: %d/40 collide\n", n_collide);
+  {  // dL too coarse for the grid -> std::invalid_argument (VoxelBackboneValidityChecker.h:37-45)
+    tendon::TendonRobot coarse = robot;
+    coarse.specs.dL = 0.005;
+    try { motion_planning::VoxelBackboneValidityChecker c2(coarse, venv, env_vox); CHECK(false); }
+    catch (const std::invalid_argument &) {}
+  }
+  // swept volumes: PartialVoxelization vs the oracle's LIFO restatement
+  orc_space osp{0.02, 0.01, 0.0001};
+  for (int i = 0; i < 12; i++) {
+    std::vector<double> a = states[2 * i], b = states[2 * i];
+    for (int k = 0; k < 8; k++) b[k] = a[k] + 0.1 * (states[2 * i + 1][k] - a[k]);
+    auto pv = validator.voxelize(a, b);
+    orc_octree *ov = orc_octree_new(&og);
+    orc_edge_out info;
+    orc_voxelize_edge(&orb, &og, &osp, a.data(), b.data(), nullptr, ov, &info);
+    CHECK(pv.is_fully_valid == (info.is_fully_valid != 0));
+    CHECK(pv.t == info.t);
+    for (int k = 0; k < 8; k++) CHECK(std::fabs(pv.last_valid[k] - info.last_valid[k]) < 1e-15);
+    CHECK((int64_t)pv.voxels.nblocks() == orc_octree_nblocks(ov) && (int64_t)pv.voxels.ncells() == orc_octree_ncells(ov));
+    pv.voxels.visit_leaves([&](size_t bx, size_t by, size_t bz, uint64_t bb) { CHECK(orc_octree_block(ov, bx, by, bz) == bb); });
+    CHECK(validator.collides(pv.voxels) == (orc_octree_collides(oenv, ov) == 1));
+    CHECK(validator.valid_segment_count(a, b) == orc_valid_segment_count(&orb, &osp, a.data(), b.data()));
+    orc_octree_free(ov);
+  }
+
+  // ---- VoxelCachedLazyPRM batch entry points --------------------------------------------------
+  motion_planning::VoxelCachedLazyPRM prm(robot, venv, env_vox);
+  std::vector<std::vector<double>> verts(states.begin(), states.begin() + 64);
+  std::vector<std::pair<size_t, size_t>> edges;
+  for (size_t i = 0; i + 1 < verts.size(); i++) {
+    // short edges: move 5% of the way to the next sample so most stay valid
+    edges.emplace_back(i, i + 1);
+  }
+  for (size_t i = 0; i + 1 < verts.size(); i += 2)
+    for (int k = 0; k < 8; k++) verts[i + 1][k] = verts[i][k] + 0.05 * (verts[i + 1][k] - verts[i][k]);
+  prm.setRoadmap(verts, edges);
+  prm.precomputeVoxelCache();
+  prm.precomputeValidity();
+  for (size_t i = 0; i < verts.size(); i++) {
+    std::vector<double> t(512), p(512 * 3);
+    orc_fk_out fo;
+    int n = orc_shape(&orb, verts[i].data(), 512, t.data(), p.data(), nullptr, &fo);
+    uint32_t f = orc_validity_flags(&orb, verts[i].data(), &fo, p.data());
+    orc_octree *ov = orc_octree_new(&og);
+    if (f == 0) orc_voxelize_shape(&og, p.data(), n, ov);
+    bool ok = (f == 0) && orc_octree_collides(oenv, ov) != 1;
+    CHECK(prm.vertexValidity()[i] == (ok ? 1u : 0u));
+    orc_octree_free(ov);
+  }
+  int valid_edges = 0;
+  for (size_t i = 0; i < edges.size(); i++) {
+    orc_octree *ov = orc_octree_new(&og);
+    orc_edge_out info;
+    orc_voxelize_edge(&orb, &og, &osp, verts[edges[i].first].data(), verts[edges[i].second].data(), nullptr, ov, &info);
+    bool ok = info.is_fully_valid && orc_octree_collides(oenv, ov) != 1;
+    CHECK(prm.edgeValidity()[i] == (ok ? 1u : 0u));
+    valid_edges += ok;
+    orc_octree_free(ov);
+  }
+  std::printf("roadmap: %d/%zu edges valid\n", valid_edges, edges.size());
+  prm.clearValidity();
+  for (auto v : prm.edgeValidity()) CHECK(v == 0);
+  // environment swap: empty environment -> everything with a valid shape becomes valid
+  prm.setEnvironment(env_vox.empty_copy());
+  prm.precomputeVertexValidity();
+  for (size_t i = 0; i < verts.size(); i++) CHECK(prm.vertexValidity()[i] == ((prm.vertexFlags()[i] & 39u) == 0 ? 1u : 0u));
+
+  orc_octree_free(oenv);
+  std::printf(failures ? "FAILED (%d)\n" : "host mirror ok\n", failures);
+  return failures ? 1 : 0;
+}
