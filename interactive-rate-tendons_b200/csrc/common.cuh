@@ -25,6 +25,10 @@ struct irt_ctx {
   // growable device scratch owned by the context (never shrinks)
   void *scratch = nullptr;
   size_t scratch_bytes = 0;
+  // second grow-only arena for the K2 pipelines (sample pools, raster slots); kept across calls so
+  // repeated roadmap builds do not pay cudaMalloc/cudaFree of multi-GB pools
+  void *arena = nullptr;
+  size_t arena_bytes = 0;
 };
 
 // device-resident robot constants (passed to kernels by value)
@@ -88,6 +92,9 @@ int irt_fail(irt_ctx *ctx, int status, const char *fmt, ...);
 GridDev make_grid_dev(const irt_grid &g);
 int grid_check(irt_ctx *ctx, const irt_grid *g);
 void *ctx_scratch(irt_ctx *ctx, size_t bytes);  // nullptr on failure
+void *ctx_arena(irt_ctx *ctx, size_t bytes);    // nullptr on failure
+int setstore_grow_blocks(irt_ctx *ctx, irt_setstore *s, int64_t need_blocks, int64_t keep_blocks,
+                         cudaStream_t st);
 
 #define IRT_CUDA(ctx, call)                                                             \
   do {                                                                                  \

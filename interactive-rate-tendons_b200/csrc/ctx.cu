@@ -33,6 +33,16 @@ void *ctx_scratch(irt_ctx *ctx, size_t bytes) {
   return ctx->scratch;
 }
 
+void *ctx_arena(irt_ctx *ctx, size_t bytes) {
+  if (bytes <= ctx->arena_bytes) return ctx->arena;
+  if (ctx->arena) cudaFree(ctx->arena);
+  ctx->arena = nullptr;
+  ctx->arena_bytes = 0;
+  if (cudaMalloc(&ctx->arena, bytes) != cudaSuccess) return nullptr;
+  ctx->arena_bytes = bytes;
+  return ctx->arena;
+}
+
 extern "C" {
 
 int irt_abi_version(void) { return IRT_ABI_VERSION; }
@@ -76,6 +86,7 @@ void irt_ctx_destroy(irt_ctx *ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
   if (ctx->scratch) cudaFree(ctx->scratch);
+  if (ctx->arena) cudaFree(ctx->arena);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
   if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
   delete ctx;

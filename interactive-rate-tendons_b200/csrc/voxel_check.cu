@@ -189,6 +189,29 @@ int setstore_reserve(irt_ctx *ctx, irt_setstore *s, int64_t n_sets, int64_t n_bl
   return ensure_store_capacity(ctx, s, n_sets, n_blocks);
 }
 
+// content-preserving growth of the keys/bits arrays (amortised x1.5)
+int setstore_grow_blocks(irt_ctx *ctx, irt_setstore *s, int64_t need_blocks, int64_t keep_blocks,
+                         cudaStream_t st) {
+  if ((size_t)need_blocks + 4 <= s->cap_blocks) return IRT_OK;
+  size_t cap = s->cap_blocks + s->cap_blocks / 2;
+  if (cap < (size_t)need_blocks + 4) cap = (size_t)need_blocks + 4;
+  uint32_t *nk = nullptr;
+  uint64_t *nb = nullptr;
+  IRT_CUDA(ctx, cudaMalloc(&nk, cap * 4));
+  IRT_CUDA(ctx, cudaMalloc(&nb, cap * 8));
+  if (keep_blocks > 0) {
+    IRT_CUDA(ctx, cudaMemcpyAsync(nk, s->d_keys, (size_t)keep_blocks * 4, cudaMemcpyDeviceToDevice, st));
+    IRT_CUDA(ctx, cudaMemcpyAsync(nb, s->d_bits, (size_t)keep_blocks * 8, cudaMemcpyDeviceToDevice, st));
+    IRT_CUDA(ctx, cudaStreamSynchronize(st));
+  }
+  if (s->d_keys) cudaFree(s->d_keys);
+  if (s->d_bits) cudaFree(s->d_bits);
+  s->d_keys = nk;
+  s->d_bits = nb;
+  s->cap_blocks = cap;
+  return IRT_OK;
+}
+
 int setstore_finalize(irt_ctx *ctx, irt_setstore *s, int64_t n_sets, int64_t n_blocks,
                       cudaStream_t st) {
   (void)ctx; (void)st;

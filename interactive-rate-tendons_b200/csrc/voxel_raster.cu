@@ -25,9 +25,28 @@
 #include <cstring>
 #include <vector>
 
+#include <chrono>
+
 #include "common.cuh"
 
 namespace {
+
+// IRT_B200_TRACE=1: per-phase wall-clock of the K2 host pipeline (synchronising; debugging only)
+struct Trace {
+  bool on;
+  cudaStream_t st;
+  std::chrono::steady_clock::time_point t0;
+  explicit Trace(cudaStream_t s) : on(getenv("IRT_B200_TRACE") != nullptr), st(s), t0(std::chrono::steady_clock::now()) {}
+  void point(const char *name, long long count = -1) {
+    if (!on) return;
+    cudaStreamSynchronize(st);
+    auto t1 = std::chrono::steady_clock::now();
+    std::fprintf(stderr, "[irt trace] %-28s %9.3f ms", name, std::chrono::duration<double, std::milli>(t1 - t0).count());
+    if (count >= 0) std::fprintf(stderr, "  (%lld)", count);
+    std::fprintf(stderr, "\n");
+    t0 = std::chrono::steady_clock::now();
+  }
+};
 
 constexpr int RS_WARPS = 4;
 constexpr int RS_HASH = 1024;        // hash entries per warp (power of two)
@@ -64,6 +83,8 @@ __device__ __forceinline__ D3 rotate_pt(const GridDev &g, const double *p) {
 struct WarpHash {
   uint32_t *keys;   // [RS_HASH]
   unsigned long long *bits;  // [RS_HASH]
+  uint16_t *list;   // [RS_HASH] slots in insertion order (dense list of the occupied entries)
+  uint32_t *count;  // number of occupied entries
   uint32_t *overflow;
 };
 
@@ -71,6 +92,7 @@ __device__ __forceinline__ void hash_insert(const WarpHash &h, uint32_t key, uns
   uint32_t slot = (key * 2654435761u) >> (32 - 10);  // RS_HASH == 1 << 10
   for (int probe = 0; probe < RS_HASH; probe++) {
     const uint32_t old = atomicCAS(&h.keys[slot], RS_EMPTY, key);
+    if (old == RS_EMPTY) h.list[atomicAdd(h.count, 1u)] = (uint16_t)slot;
     if (old == RS_EMPTY || old == key) {
       atomicOr(&h.bits[slot], mask);
       return;
@@ -166,34 +188,36 @@ __device__ void add_line(const GridDev &g, const WarpHash &h, const D3 &a, const
 
 // One warp per set.  A set is a linked list of FK samples (set_head / sample_next); a sample is
 // included iff t < tlimit[set] (edges) -- vertices have a single sample and no limit.
-// EMIT=false: counts[set] = #occupied leaf blocks, optional t_last[set].
-// EMIT=true : writes keys/bits at offsets[set], key-sorted.
-template <bool EMIT>
+// Output: the set's occupied leaf blocks, key-sorted, in its slot of capacity RS_HASH
+// (slot_keys / slot_bits), counts[set], optional t_last / nsamples.  A gather kernel then packs
+// the slots into the CSR at the scanned offsets.  Per-set cost is proportional to the number of
+// occupied blocks: occupied hash slots are kept in an append list, so neither the compaction nor
+// the clean-up ever scans the whole table.
 __global__ void __launch_bounds__(RS_WARPS * 32)
 swept_voxel_raster_kernel(const GridDev g, const double *__restrict__ pts,
                           const int32_t *__restrict__ npts, int cap_pts,
                           const int32_t *__restrict__ set_head, const int32_t *__restrict__ sample_next,
                           const double *__restrict__ sample_t, const double *__restrict__ tlimit,
                           int64_t nsets, uint32_t *__restrict__ counts, double *__restrict__ t_last,
-                          int32_t *__restrict__ nsamples, const uint64_t *__restrict__ offsets,
-                          uint32_t *__restrict__ out_keys, uint64_t *__restrict__ out_bits,
-                          uint32_t *__restrict__ set_flags) {
+                          int32_t *__restrict__ nsamples, uint32_t *__restrict__ slot_keys,
+                          uint64_t *__restrict__ slot_bits, uint32_t *__restrict__ set_flags) {
   extern __shared__ unsigned long long rs_smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  // per warp: bits u64[H] | keys u32[H] | dense keys u32[H] | dense slots u16[H] | overflow
+  // per warp: bits u64[H] | keys u32[H] | dense keys u32[H] | list u16[H] | count, overflow
   unsigned char *wbase = reinterpret_cast<unsigned char *>(rs_smem) + (size_t)warp * RS_WARP_BYTES;
   WarpHash h;
   h.bits = reinterpret_cast<unsigned long long *>(wbase);
   h.keys = reinterpret_cast<uint32_t *>(wbase + RS_HASH * 8);
   uint32_t *dk = reinterpret_cast<uint32_t *>(wbase + RS_HASH * 12);
-  uint16_t *ds = reinterpret_cast<uint16_t *>(wbase + RS_HASH * 16);
-  h.overflow = reinterpret_cast<uint32_t *>(wbase + RS_HASH * 18);
+  h.list = reinterpret_cast<uint16_t *>(wbase + RS_HASH * 16);
+  h.count = reinterpret_cast<uint32_t *>(wbase + RS_HASH * 18);
+  h.overflow = h.count + 1;
+  for (int i = lane; i < RS_HASH; i += 32) { h.keys[i] = RS_EMPTY; h.bits[i] = 0ull; }
+  if (lane == 0) { *h.count = 0u; *h.overflow = 0u; }
+  __syncwarp();
 
   for (int64_t set = (int64_t)blockIdx.x * RS_WARPS + warp; set < nsets;
        set += (int64_t)gridDim.x * RS_WARPS) {
-    for (int i = lane; i < RS_HASH; i += 32) { h.keys[i] = RS_EMPTY; h.bits[i] = 0ull; }
-    if (lane == 0) *h.overflow = 0u;
-    __syncwarp();
     const double lim = tlimit ? tlimit[set] : 0.0;
     double tl = 0.0;
     int ns = 0;
@@ -213,37 +237,49 @@ swept_voxel_raster_kernel(const GridDev g, const double *__restrict__ pts,
       }
     }
     __syncwarp();
-    // compact the occupied entries (ballot prefix), then rank-sort them by key
-    int cnt = 0;
-    for (int j0 = 0; j0 < RS_HASH; j0 += 32) {
-      const uint32_t k = h.keys[j0 + lane];
-      const unsigned m = __ballot_sync(0xffffffffu, k != RS_EMPTY);
-      if (EMIT && k != RS_EMPTY) {
-        const int pos = cnt + __popc(m & ((1u << lane) - 1u));
-        dk[pos] = k;
-        ds[pos] = (uint16_t)(j0 + lane);
-      }
-      cnt += __popc(m);
+    const int cnt = (int)min(*h.count, (uint32_t)RS_HASH);
+    for (int i = lane; i < cnt; i += 32) dk[i] = h.keys[h.list[i]];
+    __syncwarp();
+    // rank sort by key == the reference's visit_leaves order
+    uint32_t *sk = slot_keys + set * RS_HASH;
+    uint64_t *sb = slot_bits + set * RS_HASH;
+    for (int i = lane; i < cnt; i += 32) {
+      const uint32_t k = dk[i];
+      int rank = 0;
+      for (int j = 0; j < cnt; j++) rank += (dk[j] < k);
+      sk[rank] = k;
+      sb[rank] = h.bits[h.list[i]];
+    }
+    if (lane == 0) {
+      counts[set] = (uint32_t)cnt;
+      if (t_last) t_last[set] = tl;
+      if (nsamples) nsamples[set] = ns;
+      if (*h.overflow && set_flags) set_flags[set] |= IRT_FLAG_CAPACITY;
     }
     __syncwarp();
-    if (!EMIT) {
-      if (lane == 0) {
-        counts[set] = (uint32_t)cnt;
-        if (t_last) t_last[set] = tl;
-        if (nsamples) nsamples[set] = ns;
-        if (*h.overflow && set_flags) set_flags[set] |= IRT_FLAG_CAPACITY;
-      }
-    } else {
-      const uint64_t base = offsets[set];
-      for (int i = lane; i < cnt; i += 32) {
-        const uint32_t k = dk[i];
-        int rank = 0;
-        for (int j = 0; j < cnt; j++) rank += (dk[j] < k);
-        out_keys[base + rank] = k;
-        out_bits[base + rank] = h.bits[ds[i]];
-      }
+    for (int i = lane; i < cnt; i += 32) {  // clean only what was used
+      const int sl = h.list[i];
+      h.keys[sl] = RS_EMPTY;
+      h.bits[sl] = 0ull;
     }
     __syncwarp();
+    if (lane == 0) { *h.count = 0u; *h.overflow = 0u; }
+    __syncwarp();
+  }
+}
+
+// pack the slots into the CSR: one warp per set, coalesced copies
+__global__ void raster_gather_kernel(const uint32_t *__restrict__ slot_keys, const uint64_t *__restrict__ slot_bits,
+                                     const uint32_t *__restrict__ counts, const uint64_t *__restrict__ offsets,
+                                     int64_t nsets, uint32_t *__restrict__ out_keys, uint64_t *__restrict__ out_bits) {
+  const int lane = threadIdx.x & 31;
+  const int64_t set = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (set >= nsets) return;
+  const uint32_t n = counts[set];
+  const uint64_t base = offsets[set];
+  for (uint32_t i = lane; i < n; i += 32) {
+    out_keys[base + i] = slot_keys[set * RS_HASH + i];
+    out_bits[base + i] = slot_bits[set * RS_HASH + i];
   }
 }
 
@@ -283,7 +319,8 @@ __global__ void scan_tile_offsets_kernel(uint64_t *tile_sums, int64_t ntiles, ui
 
 __global__ void scan_apply_kernel(const uint32_t *__restrict__ in, int64_t n,
                                   const uint64_t *__restrict__ tile_sums,
-                                  const uint64_t *__restrict__ total, uint64_t *__restrict__ out) {
+                                  const uint64_t *__restrict__ total, uint64_t base_off,
+                                  uint64_t *__restrict__ out) {
   // thread t owns SCAN_ITEMS consecutive items of the tile
   __shared__ uint64_t sh[SCAN_T];
   const int64_t base = (int64_t)blockIdx.x * SCAN_TILE + (int64_t)threadIdx.x * SCAN_ITEMS;
@@ -301,21 +338,22 @@ __global__ void scan_apply_kernel(const uint32_t *__restrict__ in, int64_t n,
     sh[threadIdx.x] += add;
     __syncthreads();
   }
-  uint64_t acc = tile_sums[blockIdx.x] + sh[threadIdx.x] - s;
+  uint64_t acc = base_off + tile_sums[blockIdx.x] + sh[threadIdx.x] - s;
   for (int k = 0; k < SCAN_ITEMS; k++) {
     if (base + k < n) out[base + k] = acc;
     acc += v[k];
   }
-  if (blockIdx.x == 0 && threadIdx.x == 0) out[n] = *total;
+  if (blockIdx.x == 0 && threadIdx.x == 0) out[n] = base_off + *total;
 }
 
-// offsets[0..n] from counts[0..n); returns total on the host
-int exclusive_scan(irt_ctx *ctx, const uint32_t *d_counts, int64_t n, uint64_t *d_offsets,
-                   uint64_t *d_tmp /* ntiles + 1 */, uint64_t *h_total, cudaStream_t st) {
+// offsets[0..n] = base_off + exclusive scan of counts[0..n); returns the chunk total on the host
+int exclusive_scan(irt_ctx *ctx, const uint32_t *d_counts, int64_t n, uint64_t base_off,
+                   uint64_t *d_offsets, uint64_t *d_tmp /* ntiles + 1 */, uint64_t *h_total,
+                   cudaStream_t st) {
   const int64_t ntiles = (n + SCAN_TILE - 1) / SCAN_TILE;
   scan_tile_sums_kernel<<<(unsigned)ntiles, SCAN_T, 0, st>>>(d_counts, n, d_tmp);
   scan_tile_offsets_kernel<<<1, 32, 0, st>>>(d_tmp, ntiles, d_tmp + ntiles);
-  scan_apply_kernel<<<(unsigned)ntiles, SCAN_T, 0, st>>>(d_counts, n, d_tmp, d_tmp + ntiles, d_offsets);
+  scan_apply_kernel<<<(unsigned)ntiles, SCAN_T, 0, st>>>(d_counts, n, d_tmp, d_tmp + ntiles, base_off, d_offsets);
   ctx->launches.fetch_add(3);
   IRT_CUDA(ctx, cudaGetLastError());
   IRT_CUDA(ctx, cudaMemcpyAsync(h_total, d_tmp + ntiles, 8, cudaMemcpyDeviceToHost, st));
@@ -521,57 +559,83 @@ __global__ void edge_finish_kernel(EdgePool P, int32_t E, double *__restrict__ t
   flags_out[e] = f;
 }
 
-struct DevMem {
-  std::vector<void *> ptrs;
-  ~DevMem() {
-    for (void *p : ptrs) cudaFree(p);
-  }
+// bump allocator over the context's grow-only K2 arena.  Layouts are described once by a
+// lambda and run twice: a dry run to size the arena, then the real carve-up.
+struct Arena {
+  char *base = nullptr;
+  size_t cap = 0, used = 0;
+  bool dry = true;
   template <typename T>
   bool alloc(T **out, size_t count) {
-    void *p = nullptr;
-    if (cudaMalloc(&p, (count ? count : 1) * sizeof(T)) != cudaSuccess) return false;
-    ptrs.push_back(p);
-    *out = (T *)p;
+    const size_t bytes = ((count ? count : 1) * sizeof(T) + 255) & ~(size_t)255;
+    if (dry) { *out = nullptr; used += bytes; return true; }
+    if (used + bytes > cap) return false;
+    *out = reinterpret_cast<T *>(base + used);
+    used += bytes;
     return true;
   }
 };
+template <typename F>
+int arena_layout(irt_ctx *ctx, const F &layout) {
+  Arena dry;
+  layout(dry);
+  char *base = (char *)ctx_arena(ctx, dry.used);
+  if (!base) return irt_fail(ctx, IRT_ERR_CUDA, "K2 arena allocation of %zu bytes failed", dry.used);
+  Arena real;
+  real.base = base; real.cap = dry.used; real.dry = false;
+  if (!layout(real)) return irt_fail(ctx, IRT_ERR_CUDA, "K2 arena layout failed");
+  return IRT_OK;
+}
 
-int raster_to_store(irt_ctx *ctx, const GridDev &g, const double *d_pts, const int32_t *d_npts,
-                    int cap_pts, const int32_t *d_heads, const int32_t *d_next, const double *d_st,
-                    const double *d_tlimit, int64_t nsets, double *d_tlast, int32_t *d_nsamples,
-                    uint32_t *d_setflags, uint32_t *d_counts, uint64_t *d_scan_tmp,
-                    irt_setstore *store, int64_t set_off, uint64_t *d_offsets_tmp,
-                    uint64_t *total_out, cudaStream_t st);
+constexpr int64_t RS_CHUNK_SETS = 65536;  // sets rasterised per launch (slot scratch = 12 KiB per set)
 
-}  // namespace
+struct RasterScratch {
+  uint32_t *slot_keys = nullptr;
+  uint64_t *slot_bits = nullptr;
+  uint32_t *counts = nullptr;
+  uint64_t *scan_tmp = nullptr;
+  template <typename A>
+  bool layout(A &a, int64_t chunk) {
+    const int64_t ntiles = (chunk + SCAN_TILE - 1) / SCAN_TILE;
+    return a.alloc(&slot_keys, (size_t)chunk * RS_HASH) && a.alloc(&slot_bits, (size_t)chunk * RS_HASH) &&
+           a.alloc(&counts, (size_t)chunk) && a.alloc(&scan_tmp, (size_t)ntiles + 2);
+  }
+};
 
-namespace {
-
-// counts -> offsets -> emit into a temporary CSR (d_offsets_tmp / store arrays at set_off)
-int raster_to_store(irt_ctx *ctx, const GridDev &g, const double *d_pts, const int32_t *d_npts,
-                    int cap_pts, const int32_t *d_heads, const int32_t *d_next, const double *d_st,
-                    const double *d_tlimit, int64_t nsets, double *d_tlast, int32_t *d_nsamples,
-                    uint32_t *d_setflags, uint32_t *d_counts, uint64_t *d_scan_tmp,
-                    irt_setstore *store, int64_t set_off, uint64_t *d_offsets_tmp,
-                    uint64_t *total_out, cudaStream_t st) {
-  (void)set_off;
-  int64_t blocks = (nsets + RS_WARPS - 1) / RS_WARPS;
-  const int64_t max_blocks = (int64_t)ctx->sm_count * 8;
-  if (blocks > max_blocks) blocks = max_blocks;
-  IRT_CUDA(ctx, cudaFuncSetAttribute(swept_voxel_raster_kernel<false>,
-                                     cudaFuncAttributeMaxDynamicSharedMemorySize, RS_SMEM));
-  IRT_CUDA(ctx, cudaFuncSetAttribute(swept_voxel_raster_kernel<true>,
-                                     cudaFuncAttributeMaxDynamicSharedMemorySize, RS_SMEM));
-  swept_voxel_raster_kernel<false><<<(unsigned)blocks, RS_WARPS * 32, RS_SMEM, st>>>(
-      g, d_pts, d_npts, cap_pts, d_heads, d_next, d_st, d_tlimit, nsets, d_counts, d_tlast,
-      d_nsamples, nullptr, nullptr, nullptr, d_setflags);
-  IRT_LAUNCHED(ctx);
-  IRT_CUDA(ctx, cudaGetLastError());
-  uint64_t total = 0;
-  int rc = exclusive_scan(ctx, d_counts, nsets, d_offsets_tmp, d_scan_tmp, &total, st);
-  if (rc) return rc;
-  *total_out = total;
-  (void)store;
+// Rasterise sets [0, nsets) of one sample pool and APPEND them to the store: the sets become
+// store sets [set_base, set_base + nsets) and their leaves start at leaf_base.
+int raster_append(irt_ctx *ctx, const GridDev &g, const double *d_pts, const int32_t *d_npts,
+                  int cap_pts, const int32_t *d_heads, const int32_t *d_next, const double *d_st,
+                  const double *d_tlimit, int64_t nsets, double *d_tlast, int32_t *d_nsamples,
+                  uint32_t *d_setflags, RasterScratch &rs, irt_setstore *store, int64_t set_base,
+                  uint64_t leaf_base, uint64_t *leaf_total_out, cudaStream_t st) {
+  IRT_CUDA(ctx, cudaFuncSetAttribute(swept_voxel_raster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     RS_SMEM));
+  uint64_t running = leaf_base;
+  for (int64_t c0 = 0; c0 < nsets; c0 += RS_CHUNK_SETS) {
+    const int64_t m = (nsets - c0 < RS_CHUNK_SETS) ? (nsets - c0) : RS_CHUNK_SETS;
+    int64_t blocks = (m + RS_WARPS - 1) / RS_WARPS;
+    const int64_t max_blocks = (int64_t)ctx->sm_count * 8;
+    if (blocks > max_blocks) blocks = max_blocks;
+    swept_voxel_raster_kernel<<<(unsigned)blocks, RS_WARPS * 32, RS_SMEM, st>>>(
+        g, d_pts, d_npts, cap_pts, d_heads + c0, d_next, d_st, d_tlimit ? d_tlimit + c0 : nullptr, m, rs.counts,
+        d_tlast ? d_tlast + c0 : nullptr, d_nsamples ? d_nsamples + c0 : nullptr, rs.slot_keys, rs.slot_bits,
+        d_setflags ? d_setflags + c0 : nullptr);
+    IRT_LAUNCHED(ctx);
+    IRT_CUDA(ctx, cudaGetLastError());
+    uint64_t total = 0;
+    int rc = exclusive_scan(ctx, rs.counts, m, running, store->d_offsets + set_base + c0, rs.scan_tmp, &total, st);
+    if (rc) return rc;
+    rc = setstore_grow_blocks(ctx, store, (int64_t)(running + total), (int64_t)running, st);
+    if (rc) return rc;
+    const int T = 256;
+    raster_gather_kernel<<<(unsigned)((m * 32 + T - 1) / T), T, 0, st>>>(
+        rs.slot_keys, rs.slot_bits, rs.counts, store->d_offsets + set_base + c0, m, store->d_keys, store->d_bits);
+    IRT_LAUNCHED(ctx);
+    IRT_CUDA(ctx, cudaGetLastError());
+    running += total;
+  }
+  *leaf_total_out = running - leaf_base;
   return IRT_OK;
 }
 
@@ -613,6 +677,23 @@ uint32_t irt_valid_segment_count(const irt_robot_desc *rb, const irt_space *sp, 
   return sc;
 }
 
+static int store_begin(irt_ctx *ctx, irt_setstore *store, int64_t n, int64_t est_blocks, cudaStream_t st) {
+  int rc = setstore_reserve(ctx, store, n, est_blocks);
+  if (rc) return rc;
+  if (n == 0) IRT_CUDA(ctx, cudaMemsetAsync(store->d_offsets, 0, 8, st));
+  return IRT_OK;
+}
+
+static int check_dl_vs_grid(irt_ctx *ctx, const irt_robot *rb, const GridDev &g) {
+  // VoxelBackboneValidityChecker ctor: dL must not exceed the largest voxel side (.h:37-45)
+  const double dmax = std::fmax(g.d[0], std::fmax(g.d[1], g.d[2]));
+  if (rb->desc.dL > dmax)
+    return irt_fail(ctx, IRT_ERR_INVALID_ARGUMENT,
+                    "robot.specs.dL is larger than expected by VoxelBackboneValidityChecker (%g > %g)",
+                    rb->desc.dL, dmax);
+  return IRT_OK;
+}
+
 int irt_voxelize_vertices(irt_ctx *ctx, const irt_robot *rb, const double *states, int state_size,
                           int64_t n, irt_setstore *store, uint32_t *flags, double *tips) {
   if (!ctx || !rb || !store || n < 0 || (n > 0 && !states)) return IRT_ERR_INVALID_ARGUMENT;
@@ -620,117 +701,92 @@ int irt_voxelize_vertices(irt_ctx *ctx, const irt_robot *rb, const double *state
     return irt_fail(ctx, IRT_ERR_INVALID_ARGUMENT, "State is not the right size (%d != %d)",
                     state_size, rb->state_size);
   const GridDev &g = store->gd;
-  // VoxelBackboneValidityChecker ctor: dL must not exceed the largest voxel side (.h:37-45)
-  const double dmax = std::fmax(g.d[0], std::fmax(g.d[1], g.d[2]));
-  if (rb->desc.dL > dmax)
-    return irt_fail(ctx, IRT_ERR_INVALID_ARGUMENT,
-                    "robot.specs.dL is larger than expected by VoxelBackboneValidityChecker (%g > %g)",
-                    rb->desc.dL, dmax);
+  int rc = check_dl_vs_grid(ctx, rb, g);
+  if (rc) return rc;
   IRT_CUDA(ctx, cudaSetDevice(ctx->device));
   cudaStream_t st = ctx->stream;
-  if (n == 0) {
-    int rc = setstore_reserve(ctx, store, 0, 0);
-    if (rc) return rc;
-    IRT_CUDA(ctx, cudaMemsetAsync(store->d_offsets, 0, 8, st));
-    return setstore_finalize(ctx, store, 0, 0, st);
-  }
-  const int cap = rb->max_points;
-  DevMem mem;
-  double *d_states, *d_p, *d_tip;
-  int32_t *d_npts, *d_heads;
-  uint32_t *d_flags, *d_counts;
-  uint64_t *d_scan_tmp;
-  const int64_t ntiles = (n + SCAN_TILE - 1) / SCAN_TILE;
-  if (!mem.alloc(&d_states, (size_t)n * state_size) || !mem.alloc(&d_p, (size_t)n * cap * 3) ||
-      !mem.alloc(&d_tip, (size_t)n * 3) || !mem.alloc(&d_npts, (size_t)n) ||
-      !mem.alloc(&d_heads, (size_t)n) || !mem.alloc(&d_flags, (size_t)n) ||
-      !mem.alloc(&d_counts, (size_t)n) || !mem.alloc(&d_scan_tmp, (size_t)ntiles + 2))
-    return irt_fail(ctx, IRT_ERR_CUDA, "device allocation failed (n=%lld)", (long long)n);
-  IRT_CUDA(ctx, cudaMemcpyAsync(d_states, states, (size_t)n * state_size * 8, cudaMemcpyHostToDevice, st));
-  irt_fk_outputs o;
-  std::memset(&o, 0, sizeof(o));
-  o.p = d_p; o.npts = d_npts; o.flags = d_flags; o.tip = d_tip;
-  int rc = fk_launch(ctx, rb, d_states, n, cap, o, nullptr, st);
+  rc = store_begin(ctx, store, n, n * 24, st);
   if (rc) return rc;
-  rc = self_collision_launch(ctx, rb, d_p, d_npts, n, cap, d_flags, st);
+  if (n == 0) return setstore_finalize(ctx, store, 0, 0, st);
+  const int cap = rb->max_points, S = state_size;
+  const int64_t chunk = std::min<int64_t>(n, 262144);
+  double *d_states = nullptr, *d_p = nullptr, *d_tip = nullptr;
+  int32_t *d_npts = nullptr, *d_heads = nullptr;
+  uint32_t *d_flags = nullptr;
+  RasterScratch rs;
+  rc = arena_layout(ctx, [&](Arena &a) {
+    return a.alloc(&d_states, (size_t)chunk * S) && a.alloc(&d_p, (size_t)chunk * cap * 3) &&
+           a.alloc(&d_tip, (size_t)chunk * 3) && a.alloc(&d_npts, (size_t)chunk) &&
+           a.alloc(&d_heads, (size_t)chunk) && a.alloc(&d_flags, (size_t)chunk) &&
+           rs.layout(a, std::min<int64_t>(chunk, RS_CHUNK_SETS));
+  });
   if (rc) return rc;
+  uint64_t running = 0;
   const int T = 256;
-  vertex_heads_kernel<<<(unsigned)((n + T - 1) / T), T, 0, st>>>(d_flags, n, d_heads);
-  IRT_LAUNCHED(ctx);
-  rc = setstore_reserve(ctx, store, n, 0);
-  if (rc) return rc;
-  uint64_t total = 0;
-  rc = raster_to_store(ctx, g, d_p, d_npts, cap, d_heads, nullptr, nullptr, nullptr, n, nullptr,
-                       nullptr, d_flags, d_counts, d_scan_tmp, store, 0, store->d_offsets, &total, st);
-  if (rc) return rc;
-  rc = setstore_reserve(ctx, store, n, (int64_t)total);  // offsets buffer is kept (cap_sets ok)
-  if (rc) return rc;
-  int64_t blocks = (n + RS_WARPS - 1) / RS_WARPS;
-  const int64_t max_blocks = (int64_t)ctx->sm_count * 8;
-  if (blocks > max_blocks) blocks = max_blocks;
-  swept_voxel_raster_kernel<true><<<(unsigned)blocks, RS_WARPS * 32, RS_SMEM, st>>>(
-      g, d_p, d_npts, cap, d_heads, nullptr, nullptr, nullptr, n, nullptr, nullptr, nullptr,
-      store->d_offsets, store->d_keys, store->d_bits, nullptr);
-  IRT_LAUNCHED(ctx);
-  IRT_CUDA(ctx, cudaGetLastError());
-  rc = setstore_finalize(ctx, store, n, (int64_t)total, st);
-  if (rc) return rc;
-  if (flags) IRT_CUDA(ctx, cudaMemcpyAsync(flags, d_flags, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
-  if (tips) IRT_CUDA(ctx, cudaMemcpyAsync(tips, d_tip, (size_t)n * 24, cudaMemcpyDeviceToHost, st));
-  IRT_CUDA(ctx, cudaStreamSynchronize(st));
-  return IRT_OK;
+  for (int64_t off = 0; off < n; off += chunk) {
+    const int64_t m = std::min<int64_t>(chunk, n - off);
+    IRT_CUDA(ctx, cudaMemcpyAsync(d_states, states + off * S, (size_t)m * S * 8, cudaMemcpyHostToDevice, st));
+    irt_fk_outputs o;
+    std::memset(&o, 0, sizeof(o));
+    o.p = d_p; o.npts = d_npts; o.flags = d_flags; o.tip = d_tip;
+    rc = fk_launch(ctx, rb, d_states, m, cap, o, nullptr, st);
+    if (rc) return rc;
+    rc = self_collision_launch(ctx, rb, d_p, d_npts, m, cap, d_flags, st);
+    if (rc) return rc;
+    vertex_heads_kernel<<<(unsigned)((m + T - 1) / T), T, 0, st>>>(d_flags, m, d_heads);
+    IRT_LAUNCHED(ctx);
+    uint64_t total = 0;
+    rc = raster_append(ctx, g, d_p, d_npts, cap, d_heads, nullptr, nullptr, nullptr, m, nullptr, nullptr,
+                       d_flags, rs, store, off, running, &total, st);
+    if (rc) return rc;
+    running += total;
+    if (flags) IRT_CUDA(ctx, cudaMemcpyAsync(flags + off, d_flags, (size_t)m * 4, cudaMemcpyDeviceToHost, st));
+    if (tips) IRT_CUDA(ctx, cudaMemcpyAsync(tips + off * 3, d_tip, (size_t)m * 24, cudaMemcpyDeviceToHost, st));
+    IRT_CUDA(ctx, cudaStreamSynchronize(st));
+  }
+  return setstore_finalize(ctx, store, n, (int64_t)running, st);
 }
 
 int irt_voxelize_shapes(irt_ctx *ctx, const double *p, const int32_t *npts, int cap_pts, int64_t n,
                         irt_setstore *store) {
   if (!ctx || !store || n < 0 || cap_pts < 1 || (n > 0 && (!p || !npts))) return IRT_ERR_INVALID_ARGUMENT;
   for (int64_t i = 0; i < n; i++)
-    if (npts[i] < 0 || npts[i] > cap_pts) return irt_fail(ctx, IRT_ERR_INVALID_ARGUMENT, "npts[%lld] out of range", (long long)i);
+    if (npts[i] < 0 || npts[i] > cap_pts)
+      return irt_fail(ctx, IRT_ERR_INVALID_ARGUMENT, "npts[%lld] out of range", (long long)i);
   IRT_CUDA(ctx, cudaSetDevice(ctx->device));
   cudaStream_t st = ctx->stream;
   const GridDev &g = store->gd;
-  if (n == 0) {
-    int rc = setstore_reserve(ctx, store, 0, 0);
-    if (rc) return rc;
-    IRT_CUDA(ctx, cudaMemsetAsync(store->d_offsets, 0, 8, st));
-    return setstore_finalize(ctx, store, 0, 0, st);
-  }
-  DevMem mem;
-  double *d_p;
-  int32_t *d_npts, *d_heads;
-  uint32_t *d_flags, *d_counts;
-  uint64_t *d_scan_tmp;
-  const int64_t ntiles = (n + SCAN_TILE - 1) / SCAN_TILE;
-  if (!mem.alloc(&d_p, (size_t)n * cap_pts * 3) || !mem.alloc(&d_npts, (size_t)n) ||
-      !mem.alloc(&d_heads, (size_t)n) || !mem.alloc(&d_flags, (size_t)n) ||
-      !mem.alloc(&d_counts, (size_t)n) || !mem.alloc(&d_scan_tmp, (size_t)ntiles + 2))
-    return irt_fail(ctx, IRT_ERR_CUDA, "device allocation failed");
-  IRT_CUDA(ctx, cudaMemcpyAsync(d_p, p, (size_t)n * cap_pts * 24, cudaMemcpyHostToDevice, st));
-  IRT_CUDA(ctx, cudaMemcpyAsync(d_npts, npts, (size_t)n * 4, cudaMemcpyHostToDevice, st));
-  IRT_CUDA(ctx, cudaMemsetAsync(d_flags, 0, (size_t)n * 4, st));
+  int rc = store_begin(ctx, store, n, n * 24, st);
+  if (rc) return rc;
+  if (n == 0) return setstore_finalize(ctx, store, 0, 0, st);
+  const int64_t chunk = std::min<int64_t>(n, 262144);
+  double *d_p = nullptr;
+  int32_t *d_npts = nullptr, *d_heads = nullptr;
+  uint32_t *d_flags = nullptr;
+  RasterScratch rs;
+  rc = arena_layout(ctx, [&](Arena &a) {
+    return a.alloc(&d_p, (size_t)chunk * cap_pts * 3) && a.alloc(&d_npts, (size_t)chunk) &&
+           a.alloc(&d_heads, (size_t)chunk) && a.alloc(&d_flags, (size_t)chunk) &&
+           rs.layout(a, std::min<int64_t>(chunk, RS_CHUNK_SETS));
+  });
+  if (rc) return rc;
+  uint64_t running = 0;
   const int T = 256;
-  vertex_heads_kernel<<<(unsigned)((n + T - 1) / T), T, 0, st>>>(d_flags, n, d_heads);
-  IRT_LAUNCHED(ctx);
-  int rc = setstore_reserve(ctx, store, n, 0);
-  if (rc) return rc;
-  uint64_t total = 0;
-  rc = raster_to_store(ctx, g, d_p, d_npts, cap_pts, d_heads, nullptr, nullptr, nullptr, n, nullptr,
-                       nullptr, d_flags, d_counts, d_scan_tmp, store, 0, store->d_offsets, &total, st);
-  if (rc) return rc;
-  rc = setstore_reserve(ctx, store, n, (int64_t)total);
-  if (rc) return rc;
-  int64_t blocks = (n + RS_WARPS - 1) / RS_WARPS;
-  const int64_t max_blocks = (int64_t)ctx->sm_count * 8;
-  if (blocks > max_blocks) blocks = max_blocks;
-  swept_voxel_raster_kernel<true><<<(unsigned)blocks, RS_WARPS * 32, RS_SMEM, st>>>(
-      g, d_p, d_npts, cap_pts, d_heads, nullptr, nullptr, nullptr, n, nullptr, nullptr, nullptr,
-      store->d_offsets, store->d_keys, store->d_bits, nullptr);
-  IRT_LAUNCHED(ctx);
-  IRT_CUDA(ctx, cudaGetLastError());
-  rc = setstore_finalize(ctx, store, n, (int64_t)total, st);
-  if (rc) return rc;
-  IRT_CUDA(ctx, cudaStreamSynchronize(st));
-  return IRT_OK;
+  for (int64_t off = 0; off < n; off += chunk) {
+    const int64_t m = std::min<int64_t>(chunk, n - off);
+    IRT_CUDA(ctx, cudaMemcpyAsync(d_p, p + off * cap_pts * 3, (size_t)m * cap_pts * 24, cudaMemcpyHostToDevice, st));
+    IRT_CUDA(ctx, cudaMemcpyAsync(d_npts, npts + off, (size_t)m * 4, cudaMemcpyHostToDevice, st));
+    IRT_CUDA(ctx, cudaMemsetAsync(d_flags, 0, (size_t)m * 4, st));
+    vertex_heads_kernel<<<(unsigned)((m + T - 1) / T), T, 0, st>>>(d_flags, m, d_heads);
+    IRT_LAUNCHED(ctx);
+    uint64_t total = 0;
+    rc = raster_append(ctx, g, d_p, d_npts, cap_pts, d_heads, nullptr, nullptr, nullptr, m, nullptr, nullptr,
+                       d_flags, rs, store, off, running, &total, st);
+    if (rc) return rc;
+    running += total;
+    IRT_CUDA(ctx, cudaStreamSynchronize(st));
+  }
+  return setstore_finalize(ctx, store, n, (int64_t)running, st);
 }
 
 int irt_voxelize_edges(irt_ctx *ctx, const irt_robot *rb, const irt_space *space, const double *a,
@@ -742,78 +798,69 @@ int irt_voxelize_edges(irt_ctx *ctx, const irt_robot *rb, const irt_space *space
     return irt_fail(ctx, IRT_ERR_INVALID_ARGUMENT, "State is not the right size (%d != %d)",
                     state_size, rb->state_size);
   const GridDev &g = store->gd;
-  const double dmax = std::fmax(g.d[0], std::fmax(g.d[1], g.d[2]));
-  if (rb->desc.dL > dmax)
-    return irt_fail(ctx, IRT_ERR_INVALID_ARGUMENT,
-                    "robot.specs.dL is larger than expected by VoxelBackboneValidityChecker (%g > %g)",
-                    rb->desc.dL, dmax);
+  int rc = check_dl_vs_grid(ctx, rb, g);
+  if (rc) return rc;
   IRT_CUDA(ctx, cudaSetDevice(ctx->device));
   cudaStream_t st = ctx->stream;
   const int S = state_size, cap = rb->max_points;
-  if (n == 0) {
-    int rc = setstore_reserve(ctx, store, 0, 0);
-    if (rc) return rc;
-    IRT_CUDA(ctx, cudaMemsetAsync(store->d_offsets, 0, 8, st));
-    return setstore_finalize(ctx, store, 0, 0, st);
-  }
   if (n > (int64_t)0x3fffffff) return irt_fail(ctx, IRT_ERR_INVALID_ARGUMENT, "too many edges");
+  rc = store_begin(ctx, store, n, n * 32, st);
+  if (rc) return rc;
+  if (n == 0) return setstore_finalize(ctx, store, 0, 0, st);
+  Trace tr(st);
 
-  // chunk sizing: a sample costs cap*24 + S*8 + 40 bytes; budget ~6 GiB or 40% of free memory
+  // chunk sizing: a sample costs cap*24 + S*8 + 72 bytes; budget ~6 GiB or 40% of free memory
   size_t free_b = 0, total_b = 0;
   IRT_CUDA(ctx, cudaMemGetInfo(&free_b, &total_b));
-  const size_t per_sample = (size_t)cap * 24 + (size_t)S * 8 + 40;
+  free_b += ctx->arena_bytes;  // the arena is ours to reuse
+  const size_t per_sample = (size_t)cap * 24 + (size_t)S * 8 + 72;
   size_t budget = (size_t)6 << 30;
   if (budget > free_b * 2 / 5) budget = free_b * 2 / 5;
   int64_t cap_samples = (int64_t)(budget / per_sample);
   if (cap_samples > 0x3fffffff) cap_samples = 0x3fffffff;
   int64_t chunk = cap_samples / 48;
   if (chunk < 256) { chunk = 256; if (cap_samples < chunk * 8) cap_samples = chunk * 8; }
-  if (chunk > n) { chunk = n; }
+  if (chunk > n) {
+    chunk = n;
+    cap_samples = std::min<int64_t>(cap_samples, std::max<int64_t>(chunk * 64, 4096));
+  }
 
   // host: rel_threshold = 1 / validSegmentCount  (VoxelBackboneMotionValidator.cpp:55-56)
   std::vector<double> h_thr((size_t)n);
   for (int64_t i = 0; i < n; i++)
     h_thr[i] = 1.0 / double(irt_valid_segment_count(&rb->desc, space, a + i * S, b + i * S));
 
-  DevMem mem;
   EdgePool P;
   std::memset(&P, 0, sizeof(P));
-  double *d_a, *d_b, *d_thr, *d_tlimit, *d_tlast;
-  int32_t *d_nsamp_set;
-  uint32_t *d_flags_out, *d_counts;
-  Interval *d_q0, *d_q1;
-  Pending *d_pend;
-  int32_t *d_counters;  // [0] n_samples, [1] n_pend, [2] n_q0, [3] n_q1
-  uint64_t *d_scan_tmp, *d_off_chunk;
-  const int64_t ntiles = (chunk + SCAN_TILE - 1) / SCAN_TILE;
-  bool ok = mem.alloc(&d_a, (size_t)chunk * S) && mem.alloc(&d_b, (size_t)chunk * S) &&
-            mem.alloc(&d_thr, (size_t)chunk) && mem.alloc(&d_tlimit, (size_t)chunk) &&
-            mem.alloc(&d_tlast, (size_t)chunk) && mem.alloc(&d_nsamp_set, (size_t)chunk) &&
-            mem.alloc(&d_flags_out, (size_t)chunk) && mem.alloc(&d_counts, (size_t)chunk) &&
-            mem.alloc(&P.first_invalid, (size_t)chunk) && mem.alloc(&P.head, (size_t)chunk) &&
-            mem.alloc(&P.eflags, (size_t)chunk) && mem.alloc(&P.s_edge, (size_t)cap_samples) &&
-            mem.alloc(&P.s_next, (size_t)cap_samples) && mem.alloc(&P.s_npts, (size_t)cap_samples) &&
-            mem.alloc(&P.s_flags, (size_t)cap_samples) && mem.alloc(&P.s_t, (size_t)cap_samples) &&
-            mem.alloc(&P.s_state, (size_t)cap_samples * S) &&
-            mem.alloc(&P.s_p, (size_t)cap_samples * cap * 3) &&
-            mem.alloc(&d_q0, (size_t)cap_samples) && mem.alloc(&d_q1, (size_t)cap_samples) &&
-            mem.alloc(&d_pend, (size_t)cap_samples) && mem.alloc(&d_counters, 8) &&
-            mem.alloc(&d_scan_tmp, (size_t)ntiles + 2) && mem.alloc(&d_off_chunk, (size_t)chunk + 1);
-  if (!ok) return irt_fail(ctx, IRT_ERR_CUDA, "edge pool allocation failed (%lld samples)", (long long)cap_samples);
+  double *d_a = nullptr, *d_b = nullptr, *d_thr = nullptr, *d_tlimit = nullptr, *d_tlast = nullptr;
+  int32_t *d_nsamp_set = nullptr, *d_counters = nullptr;
+  uint32_t *d_flags_out = nullptr;
+  Interval *d_q0 = nullptr, *d_q1 = nullptr;
+  Pending *d_pend = nullptr;
+  RasterScratch rs;
+  rc = arena_layout(ctx, [&](Arena &A) {
+    return A.alloc(&d_a, (size_t)chunk * S) && A.alloc(&d_b, (size_t)chunk * S) &&
+           A.alloc(&d_thr, (size_t)chunk) && A.alloc(&d_tlimit, (size_t)chunk) &&
+           A.alloc(&d_tlast, (size_t)chunk) && A.alloc(&d_nsamp_set, (size_t)chunk) &&
+           A.alloc(&d_flags_out, (size_t)chunk) && A.alloc(&P.first_invalid, (size_t)chunk) &&
+           A.alloc(&P.head, (size_t)chunk) && A.alloc(&P.eflags, (size_t)chunk) &&
+           A.alloc(&P.s_edge, (size_t)cap_samples) && A.alloc(&P.s_next, (size_t)cap_samples) &&
+           A.alloc(&P.s_npts, (size_t)cap_samples) && A.alloc(&P.s_flags, (size_t)cap_samples) &&
+           A.alloc(&P.s_t, (size_t)cap_samples) && A.alloc(&P.s_state, (size_t)cap_samples * S) &&
+           A.alloc(&P.s_p, (size_t)cap_samples * cap * 3) && A.alloc(&d_q0, (size_t)cap_samples) &&
+           A.alloc(&d_q1, (size_t)cap_samples) && A.alloc(&d_pend, (size_t)cap_samples) &&
+           A.alloc(&d_counters, 8) && rs.layout(A, std::min<int64_t>(chunk, RS_CHUNK_SETS));
+  });
+  if (rc) return rc;
+  tr.point("thr + pool layout", cap_samples);
   P.a = d_a; P.b = d_b; P.thr = d_thr;
   P.cap_samples = (int32_t)cap_samples;
   P.S = S; P.N = rb->desc.n_tendons; P.cap_pts = cap;
   P.enable_rotation = rb->desc.enable_rotation ? 1 : 0;
   P.enable_retraction = rb->desc.enable_retraction ? 1 : 0;
 
-  // per-chunk CSR pieces are gathered on the host side of the store (device-to-device appends)
-  std::vector<uint64_t> h_offsets((size_t)n + 1, 0);
-  struct Piece { uint32_t *keys; uint64_t *bits; uint64_t count; };
-  std::vector<Piece> pieces;
-  DevMem piece_mem;
   uint64_t grand_total = 0;
   const int T = 256;
-
   for (int64_t off = 0; off < n; off += chunk) {
     const int32_t E = (int32_t)((n - off < chunk) ? (n - off) : chunk);
     IRT_CUDA(ctx, cudaMemcpyAsync(d_a, a + off * S, (size_t)E * S * 8, cudaMemcpyHostToDevice, st));
@@ -840,8 +887,10 @@ int irt_voxelize_edges(irt_ctx *ctx, const irt_robot *rb, const irt_space *space
       IRT_LAUNCHED(ctx);
       return IRT_OK;
     };
-    int rc = run_fk(0, n_samples);
+    tr.point("h2d + init");
+    rc = run_fk(0, n_samples);
     if (rc) return rc;
+    tr.point("round 0 fk", n_samples);
     Interval *cur = d_q0, *nxt = d_q1;
     int32_t *n_cur = d_counters + 2, *n_nxt = d_counters + 3;
     {
@@ -879,52 +928,26 @@ int irt_voxelize_edges(irt_ctx *ctx, const irt_robot *rb, const irt_space *space
       }
       std::swap(cur, nxt);
       std::swap(n_cur, n_nxt);
+      tr.point("bisection round", s_hi - s_lo);
     }
     edge_finish_kernel<<<(E + T - 1) / T, T, 0, st>>>(P, E, d_tlimit, d_flags_out);
     IRT_LAUNCHED(ctx);
     // rasterise every sample below the first invalid t (VoxelEnvironment.cpp:406-422)
     uint64_t total = 0;
-    rc = raster_to_store(ctx, g, P.s_p, P.s_npts, cap, P.head, P.s_next, P.s_t, d_tlimit, E, d_tlast,
-                         d_nsamp_set, d_flags_out, d_counts, d_scan_tmp, store, 0, d_off_chunk, &total, st);
+    rc = raster_append(ctx, g, P.s_p, P.s_npts, cap, P.head, P.s_next, P.s_t, d_tlimit, E, d_tlast,
+                       d_nsamp_set, d_flags_out, rs, store, off, grand_total, &total, st);
     if (rc) return rc;
-    Piece pc{nullptr, nullptr, total};
-    if (!piece_mem.alloc(&pc.keys, (size_t)total + 4) || !piece_mem.alloc(&pc.bits, (size_t)total + 4))
-      return irt_fail(ctx, IRT_ERR_CUDA, "piece allocation failed");
-    int64_t blocks = ((int64_t)E + RS_WARPS - 1) / RS_WARPS;
-    const int64_t max_blocks = (int64_t)ctx->sm_count * 8;
-    if (blocks > max_blocks) blocks = max_blocks;
-    swept_voxel_raster_kernel<true><<<(unsigned)blocks, RS_WARPS * 32, RS_SMEM, st>>>(
-        g, P.s_p, P.s_npts, cap, P.head, P.s_next, P.s_t, d_tlimit, E, nullptr, nullptr, nullptr,
-        d_off_chunk, pc.keys, pc.bits, nullptr);
-    IRT_LAUNCHED(ctx);
-    IRT_CUDA(ctx, cudaGetLastError());
-    pieces.push_back(pc);
-    // chunk offsets -> host (rebased), per-edge outputs -> host
-    std::vector<uint64_t> h_off((size_t)E + 1);
-    IRT_CUDA(ctx, cudaMemcpyAsync(h_off.data(), d_off_chunk, ((size_t)E + 1) * 8, cudaMemcpyDeviceToHost, st));
+    tr.point("raster + scan + gather", (long long)total);
     if (flags) IRT_CUDA(ctx, cudaMemcpyAsync(flags + off, d_flags_out, (size_t)E * 4, cudaMemcpyDeviceToHost, st));
     if (t_last) IRT_CUDA(ctx, cudaMemcpyAsync(t_last + off, d_tlast, (size_t)E * 8, cudaMemcpyDeviceToHost, st));
     if (nsamples) IRT_CUDA(ctx, cudaMemcpyAsync(nsamples + off, d_nsamp_set, (size_t)E * 4, cudaMemcpyDeviceToHost, st));
     IRT_CUDA(ctx, cudaStreamSynchronize(st));
-    for (int32_t e = 0; e <= E; e++) h_offsets[(size_t)off + e] = grand_total + h_off[e];
     grand_total += total;
-  }
-  // assemble the store
-  int rc = setstore_reserve(ctx, store, n, (int64_t)grand_total);
-  if (rc) return rc;
-  IRT_CUDA(ctx, cudaMemcpyAsync(store->d_offsets, h_offsets.data(), ((size_t)n + 1) * 8, cudaMemcpyHostToDevice, st));
-  uint64_t pos = 0;
-  for (const Piece &pc : pieces) {
-    if (pc.count) {
-      IRT_CUDA(ctx, cudaMemcpyAsync(store->d_keys + pos, pc.keys, (size_t)pc.count * 4, cudaMemcpyDeviceToDevice, st));
-      IRT_CUDA(ctx, cudaMemcpyAsync(store->d_bits + pos, pc.bits, (size_t)pc.count * 8, cudaMemcpyDeviceToDevice, st));
-    }
-    pos += pc.count;
+    tr.point("chunk d2h");
   }
   rc = setstore_finalize(ctx, store, n, (int64_t)grand_total, st);
-  if (rc) return rc;
-  IRT_CUDA(ctx, cudaStreamSynchronize(st));
-  return IRT_OK;
+  tr.point("finalize");
+  return rc;
 }
 
 }  // extern "C"
