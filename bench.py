@@ -382,7 +382,9 @@ def main():
                          "note": "duration includes the verdict memset and (N>1) the NCCL all_gather"},
         }
         verd = prm.precomputeEdgeValidity()
-        edge_check["collision_fraction"] = float(1.0 - verd.mean())
+        edge_check["valid_edge_fraction"] = float(verd.mean())
+        lo_w = irt_b200.unpack_verdicts(d_words.cpu().numpy().view(np.uint32), hi - lo) if hi > lo else np.zeros(0)
+        edge_check["collision_fraction"] = float(lo_w.mean()) if hi > lo else None
 
     # ---------------- CPU baseline (rank 0 at N=1 only) ------------------------------------------
     cpu = None

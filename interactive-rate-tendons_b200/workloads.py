@@ -141,10 +141,11 @@ def lung_like_capsules(rb, stream=7, generations=4):
     return [c for c in caps if np.linalg.norm(c[1]) < 1.2 * L]
 
 
-def lung_like_env_dense(rb, grid, stream=7, shell_voxels=2):
+def lung_like_env_dense(rb, grid, stream=7, shell_voxels=2, radius_scale=4.0):
     """Dense boolean obstacle array [Ng,Ng,Ng] (x,y,z): a shell of `shell_voxels` voxels
     around the airway tree (distance in (r_airway, r_airway + shell*dx]) clipped to the
-    workspace ball, with the base hole left open."""
+    workspace ball, with the base hole left open.  `radius_scale` widens the airways; 4.0 gives
+    ~2.6 % occupied leaf blocks at 128^3 and about half of random configurations colliding."""
     Ng = grid["Ng"]
     lim = grid["lim"]
     dx = (lim[1] - lim[0]) / Ng
@@ -156,7 +157,7 @@ def lung_like_env_dense(rb, grid, stream=7, shell_voxels=2):
         ab = b - a
         t = np.clip(((P - a) @ ab) / max(ab @ ab, 1e-30), 0.0, 1.0)
         c = a + t[:, None] * ab
-        dist = np.minimum(dist, np.linalg.norm(P - c, axis=1) - rad)
+        dist = np.minimum(dist, np.linalg.norm(P - c, axis=1) - rad * radius_scale)
     shell = (dist > 0.0) & (dist <= shell_voxels * dx)
     inside_ball = np.linalg.norm(P, axis=1) <= rb["L"] * 1.02
     occ = shell & inside_ball
