@@ -29,6 +29,10 @@ struct irt_ctx {
   // repeated roadmap builds do not pay cudaMalloc/cudaFree of multi-GB pools
   void *arena = nullptr;
   size_t arena_bytes = 0;
+  // staging for the host-pointer FK entry point (two pipeline stages), also grow-only
+  void *io = nullptr;
+  size_t io_bytes = 0;
+  cudaEvent_t ev_computed[2] = {nullptr, nullptr}, ev_copied[2] = {nullptr, nullptr};
 };
 
 // device-resident robot constants (passed to kernels by value)
@@ -93,6 +97,7 @@ GridDev make_grid_dev(const irt_grid &g);
 int grid_check(irt_ctx *ctx, const irt_grid *g);
 void *ctx_scratch(irt_ctx *ctx, size_t bytes);  // nullptr on failure
 void *ctx_arena(irt_ctx *ctx, size_t bytes);    // nullptr on failure
+void *ctx_io(irt_ctx *ctx, size_t bytes);       // nullptr on failure
 int setstore_grow_blocks(irt_ctx *ctx, irt_setstore *s, int64_t need_blocks, int64_t keep_blocks,
                          cudaStream_t st);
 

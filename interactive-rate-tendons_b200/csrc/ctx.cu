@@ -43,6 +43,16 @@ void *ctx_arena(irt_ctx *ctx, size_t bytes) {
   return ctx->arena;
 }
 
+void *ctx_io(irt_ctx *ctx, size_t bytes) {
+  if (bytes <= ctx->io_bytes) return ctx->io;
+  if (ctx->io) cudaFree(ctx->io);
+  ctx->io = nullptr;
+  ctx->io_bytes = 0;
+  if (cudaMalloc(&ctx->io, bytes) != cudaSuccess) return nullptr;
+  ctx->io_bytes = bytes;
+  return ctx->io;
+}
+
 extern "C" {
 
 int irt_abi_version(void) { return IRT_ABI_VERSION; }
@@ -78,6 +88,10 @@ int irt_ctx_create(int device, irt_ctx **out) {
     delete ctx;
     return IRT_ERR_CUDA;
   }
+  for (int b = 0; b < 2; b++) {
+    cudaEventCreateWithFlags(&ctx->ev_computed[b], cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&ctx->ev_copied[b], cudaEventDisableTiming);
+  }
   *out = ctx;
   return IRT_OK;
 }
@@ -87,6 +101,11 @@ void irt_ctx_destroy(irt_ctx *ctx) {
   cudaSetDevice(ctx->device);
   if (ctx->scratch) cudaFree(ctx->scratch);
   if (ctx->arena) cudaFree(ctx->arena);
+  if (ctx->io) cudaFree(ctx->io);
+  for (int b = 0; b < 2; b++) {
+    if (ctx->ev_computed[b]) cudaEventDestroy(ctx->ev_computed[b]);
+    if (ctx->ev_copied[b]) cudaEventDestroy(ctx->ev_copied[b]);
+  }
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
   if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
   delete ctx;

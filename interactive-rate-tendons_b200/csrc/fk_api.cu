@@ -62,50 +62,62 @@ int irt_fk_batch(irt_ctx *ctx, const irt_robot *rb, const double *states, int st
   if (chunk > n) chunk = n;
   const bool need_p = out->p || out->flags;
   struct Stage {
-    DevBuf states, p, R, t, npts, L, Li, tip, uv, flags, iters, nsteps;
-    cudaEvent_t computed = nullptr, copied = nullptr;
-    ~Stage() {
-      if (computed) cudaEventDestroy(computed);
-      if (copied) cudaEventDestroy(copied);
-    }
+    double *states, *p, *R, *t, *L, *Li, *tip, *uv;
+    int32_t *npts, *iters, *nsteps;
+    uint32_t *flags;
+    cudaEvent_t computed, copied;
   } stage[2];
+  std::memset(stage, 0, sizeof(stage));
   const int nstage = (n > chunk) ? 2 : 1;
-  for (int b = 0; b < nstage; b++) {
-    Stage &s = stage[b];
-    bool ok = s.states.alloc((size_t)chunk * state_size * 8);
-    if (need_p) ok = ok && s.p.alloc((size_t)chunk * cap_pts * 24);
-    if (out->R) ok = ok && s.R.alloc((size_t)chunk * cap_pts * 72);
-    if (out->t) ok = ok && s.t.alloc((size_t)chunk * cap_pts * 8);
-    ok = ok && s.npts.alloc((size_t)chunk * 4);
-    if (out->L) ok = ok && s.L.alloc((size_t)chunk * 8);
-    if (out->L_i) ok = ok && s.Li.alloc((size_t)chunk * N * 8);
-    if (out->tip) ok = ok && s.tip.alloc((size_t)chunk * 24);
-    if (out->uv) ok = ok && s.uv.alloc((size_t)chunk * 96);
-    if (out->flags) ok = ok && s.flags.alloc((size_t)chunk * 4);
-    if (out->iters) ok = ok && s.iters.alloc((size_t)chunk * 4);
-    if (out->nsteps) ok = ok && s.nsteps.alloc((size_t)chunk * 4);
-    if (!ok) return irt_fail(ctx, IRT_ERR_CUDA, "device staging allocation failed");
-    IRT_CUDA(ctx, cudaEventCreateWithFlags(&s.computed, cudaEventDisableTiming));
-    IRT_CUDA(ctx, cudaEventCreateWithFlags(&s.copied, cudaEventDisableTiming));
+  {  // carve both stages out of the context's grow-only staging buffer (no per-call cudaMalloc)
+    auto carve = [&](char *base, size_t *total) {
+      size_t used = 0;
+      auto take = [&](size_t bytes) -> char * {
+        char *ptr = base ? base + used : nullptr;
+        used += (bytes + 255) & ~(size_t)255;
+        return ptr;
+      };
+      for (int b = 0; b < nstage; b++) {
+        Stage &s = stage[b];
+        s.states = (double *)take((size_t)chunk * state_size * 8);
+        s.p = need_p ? (double *)take((size_t)chunk * cap_pts * 24) : nullptr;
+        s.R = out->R ? (double *)take((size_t)chunk * cap_pts * 72) : nullptr;
+        s.t = out->t ? (double *)take((size_t)chunk * cap_pts * 8) : nullptr;
+        s.npts = (int32_t *)take((size_t)chunk * 4);
+        s.L = out->L ? (double *)take((size_t)chunk * 8) : nullptr;
+        s.Li = out->L_i ? (double *)take((size_t)chunk * N * 8) : nullptr;
+        s.tip = out->tip ? (double *)take((size_t)chunk * 24) : nullptr;
+        s.uv = out->uv ? (double *)take((size_t)chunk * 96) : nullptr;
+        s.flags = out->flags ? (uint32_t *)take((size_t)chunk * 4) : nullptr;
+        s.iters = out->iters ? (int32_t *)take((size_t)chunk * 4) : nullptr;
+        s.nsteps = out->nsteps ? (int32_t *)take((size_t)chunk * 4) : nullptr;
+        s.computed = ctx->ev_computed[b];
+        s.copied = ctx->ev_copied[b];
+      }
+      *total = used;
+    };
+    size_t total = 0;
+    carve(nullptr, &total);
+    char *base = (char *)ctx_io(ctx, total);
+    if (!base) return irt_fail(ctx, IRT_ERR_CUDA, "device staging allocation of %zu bytes failed", total);
+    carve(base, &total);
   }
   int64_t c = 0;
   for (int64_t off = 0; off < n; off += chunk, c++) {
     Stage &s = stage[c % nstage];
     const int64_t m = (n - off < chunk) ? (n - off) : chunk;
     if (c >= nstage) IRT_CUDA(ctx, cudaStreamWaitEvent(st, s.copied, 0));  // buffers free again
-    IRT_CUDA(ctx, cudaMemcpyAsync(s.states.p, states + off * state_size, (size_t)m * state_size * 8,
+    IRT_CUDA(ctx, cudaMemcpyAsync(s.states, states + off * state_size, (size_t)m * state_size * 8,
                                   cudaMemcpyHostToDevice, st));
     irt_fk_outputs o;
     std::memset(&o, 0, sizeof(o));
-    o.p = (double *)s.p.p; o.R = (double *)s.R.p; o.t = (double *)s.t.p;
-    o.npts = (int32_t *)s.npts.p; o.L = (double *)s.L.p; o.L_i = (double *)s.Li.p;
-    o.tip = (double *)s.tip.p; o.uv = (double *)s.uv.p; o.flags = (uint32_t *)s.flags.p;
-    o.iters = (int32_t *)s.iters.p; o.nsteps = (int32_t *)s.nsteps.p;
+    o.p = s.p; o.R = s.R; o.t = s.t; o.npts = s.npts; o.L = s.L; o.L_i = s.Li;
+    o.tip = s.tip; o.uv = s.uv; o.flags = s.flags; o.iters = s.iters; o.nsteps = s.nsteps;
     // rows beyond npts[i] are returned as zeros (deterministic padding)
     if (o.p) IRT_CUDA(ctx, cudaMemsetAsync(o.p, 0, (size_t)m * cap_pts * 24, st));
     if (o.R) IRT_CUDA(ctx, cudaMemsetAsync(o.R, 0, (size_t)m * cap_pts * 72, st));
     if (o.t) IRT_CUDA(ctx, cudaMemsetAsync(o.t, 0, (size_t)m * cap_pts * 8, st));
-    rc = fk_launch(ctx, rb, (const double *)s.states.p, m, cap_pts, o, nullptr, st);
+    rc = fk_launch(ctx, rb, s.states, m, cap_pts, o, nullptr, st);
     if (rc) return rc;
     if (o.flags) {
       rc = self_collision_launch(ctx, rb, o.p, o.npts, m, cap_pts, o.flags, st);
@@ -116,17 +128,17 @@ int irt_fk_batch(irt_ctx *ctx, const irt_robot *rb, const double *states, int st
 #define D2H(dst, src, bytes_per)                                                               \
   if (dst) IRT_CUDA(ctx, cudaMemcpyAsync((char *)(dst) + (size_t)off * (bytes_per), (src),      \
                                          (size_t)m * (bytes_per), cudaMemcpyDeviceToHost, cs))
-    D2H(out->p, s.p.p, (size_t)cap_pts * 24);
-    D2H(out->R, s.R.p, (size_t)cap_pts * 72);
-    D2H(out->t, s.t.p, (size_t)cap_pts * 8);
-    D2H(out->npts, s.npts.p, 4);
-    D2H(out->L, s.L.p, 8);
-    D2H(out->L_i, s.Li.p, (size_t)N * 8);
-    D2H(out->tip, s.tip.p, 24);
-    D2H(out->uv, s.uv.p, 96);
-    D2H(out->flags, s.flags.p, 4);
-    D2H(out->iters, s.iters.p, 4);
-    D2H(out->nsteps, s.nsteps.p, 4);
+    D2H(out->p, s.p, (size_t)cap_pts * 24);
+    D2H(out->R, s.R, (size_t)cap_pts * 72);
+    D2H(out->t, s.t, (size_t)cap_pts * 8);
+    D2H(out->npts, s.npts, 4);
+    D2H(out->L, s.L, 8);
+    D2H(out->L_i, s.Li, (size_t)N * 8);
+    D2H(out->tip, s.tip, 24);
+    D2H(out->uv, s.uv, 96);
+    D2H(out->flags, s.flags, 4);
+    D2H(out->iters, s.iters, 4);
+    D2H(out->nsteps, s.nsteps, 4);
 #undef D2H
     IRT_CUDA(ctx, cudaEventRecord(s.copied, cs));
   }

@@ -111,19 +111,34 @@ voxel_and_popc_kernel(const uint32_t *__restrict__ keys, const uint64_t *__restr
         hitmask |= 1u << e;
         if (STATS) { vox += (unsigned long long)__popcll(x); hits++; }
       }
-      // attribute hits to sets: every lane binary-searches the 32 set starts held across the warp
+      // attribute hits to sets: every lane binary-searches (5 shuffles) the 32 set starts held
+      // across the warp for the owner of its first in-range leaf; the other three leaves of the
+      // quad have the same owner unless a set boundary falls inside the quad (rare: then those
+      // leaves are searched individually, warp-uniformly).
       if (__any_sync(0xffffffffu, hitmask != 0)) {
+        const uint32_t rf = (r0 < 0) ? 0u : (uint32_t)r0;  // first leaf of the quad inside the tile
+        int o = 0;
 #pragma unroll
-        for (int e = 0; e < 4; e++) {
-          if (!__any_sync(0xffffffffu, (hitmask >> e) & 1u)) continue;
-          const uint32_t r = (uint32_t)(r0 + e);
-          int o = 0;
+        for (int step = 16; step > 0; step >>= 1) {
+          const uint32_t v = __shfl_sync(0xffffffffu, rlo, (o + step) & 31);
+          if (v <= rf) o += step;  // o + step <= 31 always holds here
+        }
+        const uint32_t nxt = __shfl_sync(0xffffffffu, rlo, (o + 1) & 31);
+        const uint32_t next_start = (o == 31) ? tile_n : nxt;  // start of the next set's leaves
+        const bool straddles = hitmask != 0 && (uint32_t)(r0 + 3) >= next_start;
+        if (hitmask != 0 && !straddles) own |= 1u << o;
+        if (__any_sync(0xffffffffu, straddles)) {
 #pragma unroll
-          for (int step = 16; step > 0; step >>= 1) {
-            const uint32_t v = __shfl_sync(0xffffffffu, rlo, (o + step) & 31);
-            if (v <= r) o += step;  // o + step <= 31 always holds here
+          for (int e = 0; e < 4; e++) {
+            const uint32_t r = (uint32_t)(r0 + e);
+            int oe = 0;
+#pragma unroll
+            for (int step = 16; step > 0; step >>= 1) {
+              const uint32_t v = __shfl_sync(0xffffffffu, rlo, (oe + step) & 31);
+              if (v <= r) oe += step;
+            }
+            if (straddles && ((hitmask >> e) & 1u)) own |= 1u << oe;
           }
-          if ((hitmask >> e) & 1u) own |= 1u << o;
         }
       }
     };
