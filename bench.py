@@ -89,7 +89,13 @@ def cpu_fk_rate(spec, n_tendons, seconds, threads=None, stream=900):
     build()
     orc = Oracle("fast")
     rb = orc.robot(spec)
-    nt = threads or orc.max_threads()
+    # all host threads this process may use (torchrun exports OMP_NUM_THREADS=1; the explicit
+    # num_threads clause of the oracle's OpenMP loops overrides it)
+    try:
+        avail = len(os.sched_getaffinity(0))
+    except Exception:
+        avail = os.cpu_count() or 1
+    nt = threads or max(avail, orc.max_threads())
     batch = 20000
     done, t0 = 0, time.perf_counter()
     cap = len(orc.t_range(0.0, spec["L"], spec["dL"]))
@@ -381,6 +387,45 @@ def main():
                          "peak_source": hbm_src, "algorithmic_bytes": alg_bytes,
                          "note": "duration includes the verdict memset and (N>1) the NCCL all_gather"},
         }
+        # ---- C5: interactive replanning tick = env change + upload + vertex sweep + edge sweep + gather
+        nvt = len(prm.states)
+        vlo, vhi = prm.shard(nvt)
+        d_vwords = torch.zeros(max(shard_words(nvt, world), 1), dtype=torch.int32, device=dev)
+        rng_t = np.random.default_rng(wl.SEED + 5)
+        tick_envs = []
+        for _ in range(4):  # pre-generate the changed environments (host side of the tick is the upload)
+            c = rng_t.uniform(-0.1, 0.1, 3) + np.array([0.0, 0.0, 0.1])
+            tick_envs.append(torch.from_numpy(wl.toggle_blob(env_blocks, g, c, rng_t.uniform(0.005, 0.015)).view(np.int64)).pin_memory())
+        d_env = torch.zeros(env_blocks.size, dtype=torch.int64, device=dev)
+
+        def tick(i):
+            d_env.copy_(tick_envs[i % len(tick_envs)], non_blocking=True)   # H2D 256 KiB
+            prm.env.update_dev(d_env, stream=sptr)
+            if vhi > vlo:
+                prm.vertex_store.check_dev(prm.env, d_vwords, 0, vhi - vlo, stream=sptr)
+            if hi > lo:
+                prm.edge_store.check_dev(prm.env, d_words, 0, hi - lo, stream=sptr)
+            gather_verdict_words(d_vwords, dist if world > 1 else None)
+            return gather_verdict_words(d_words, dist if world > 1 else None)
+
+        for i in range(args.warmup):
+            tick(i)
+        barrier()
+        ta, tb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        n_ticks = max(args.steps, 10)
+        ta.record(stream)
+        for i in range(n_ticks):
+            tick(i)
+        tb.record(stream)
+        barrier()
+        ms_tick = max_over_ranks(ta.elapsed_time(tb) / n_ticks)
+        edge_check["replanning_tick"] = {
+            "ms_per_tick": ms_tick, "ticks_per_s": 1e3 / ms_tick,
+            "what": "C5: H2D of a changed 128^3 environment (256 KiB) + occupancy rebuild + K3 over all vertices "
+                    "and edges of this rank + verdict all_gather"}
+        prm.setEnvironment(env_blocks)
+        k3_step()
+        torch.cuda.synchronize()
         verd = prm.precomputeEdgeValidity()
         edge_check["valid_edge_fraction"] = float(verd.mean())
         lo_w = irt_b200.unpack_verdicts(d_words.cpu().numpy().view(np.uint32), hi - lo) if hi > lo else np.zeros(0)
