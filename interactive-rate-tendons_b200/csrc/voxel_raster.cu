@@ -133,7 +133,14 @@ __device__ bool segment_aabox_intersect(const D3 &A, const D3 &B, const D3 &C, c
 // "voxel index times metric cell size" initial error (:371-373) and the overshoot past B (:423-424).
 __device__ void add_line(const GridDev &g, const WarpHash &h, const D3 &a, const D3 &b) {
   const D3 ll = {g.lo[0], g.lo[1], g.lo[2]}, ur = {g.hi[0], g.hi[1], g.hi[2]};
-  if (!segment_aabox_intersect(a, b, ll, ur)) return;
+  // A segment whose endpoints both lie inside the grid box (by a safety margin of a ten-thousandth
+  // of a cell) intersects it: the reference's separating-axis test cannot report otherwise, so it
+  // is only evaluated for segments that touch or leave the box.
+  const double mx = 1e-4 * g.d[0], my = 1e-4 * g.d[1], mz = 1e-4 * g.d[2];
+  const bool inside = a.x > ll.x + mx && a.x < ur.x - mx && b.x > ll.x + mx && b.x < ur.x - mx &&
+                      a.y > ll.y + my && a.y < ur.y - my && b.y > ll.y + my && b.y < ur.y - my &&
+                      a.z > ll.z + mz && a.z < ur.z - mz && b.z > ll.z + mz && b.z < ur.z - mz;
+  if (!inside && !segment_aabox_intersect(a, b, ll, ur)) return;
   const D3 A = {(a.x - ll.x) * g.inv_d[0], (a.y - ll.y) * g.inv_d[1], (a.z - ll.z) * g.inv_d[2]};
   const D3 B = {(b.x - ll.x) * g.inv_d[0], (b.y - ll.y) * g.inv_d[1], (b.z - ll.z) * g.inv_d[2]};
   const int Axi = (int)A.x - (A.x < 0), Ayi = (int)A.y - (A.y < 0), Azi = (int)A.z - (A.z < 0);
@@ -814,11 +821,12 @@ int irt_voxelize_edges(irt_ctx *ctx, const irt_robot *rb, const irt_space *space
   IRT_CUDA(ctx, cudaMemGetInfo(&free_b, &total_b));
   free_b += ctx->arena_bytes;  // the arena is ours to reuse
   const size_t per_sample = (size_t)cap * 24 + (size_t)S * 8 + 72;
-  size_t budget = (size_t)6 << 30;
+  size_t budget = (size_t)16 << 30;
   if (budget > free_b * 2 / 5) budget = free_b * 2 / 5;
   int64_t cap_samples = (int64_t)(budget / per_sample);
   if (cap_samples > 0x3fffffff) cap_samples = 0x3fffffff;
-  int64_t chunk = cap_samples / 48;
+  // typical roadmap edges need 4-15 FK samples; a chunk whose pool overflows is split and redone
+  int64_t chunk = cap_samples / 12;
   if (chunk < 256) { chunk = 256; if (cap_samples < chunk * 8) cap_samples = chunk * 8; }
   if (chunk > n) {
     chunk = n;
@@ -861,8 +869,15 @@ int irt_voxelize_edges(irt_ctx *ctx, const irt_robot *rb, const irt_space *space
 
   uint64_t grand_total = 0;
   const int T = 256;
-  for (int64_t off = 0; off < n; off += chunk) {
-    const int32_t E = (int32_t)((n - off < chunk) ? (n - off) : chunk);
+  // work list of edge ranges in index order; a range whose sample pool overflows is split in two
+  std::vector<std::pair<int64_t, int64_t>> work;
+  for (int64_t off = n - ((n - 1) % chunk + 1); off >= 0; off -= chunk)
+    work.emplace_back(off, std::min<int64_t>(chunk, n - off));
+  while (!work.empty()) {
+    const int64_t off = work.back().first;
+    const int32_t E = (int32_t)work.back().second;
+    work.pop_back();
+    bool pool_overflow = false;
     IRT_CUDA(ctx, cudaMemcpyAsync(d_a, a + off * S, (size_t)E * S * 8, cudaMemcpyHostToDevice, st));
     IRT_CUDA(ctx, cudaMemcpyAsync(d_b, b + off * S, (size_t)E * S * 8, cudaMemcpyHostToDevice, st));
     IRT_CUDA(ctx, cudaMemcpyAsync(d_thr, h_thr.data() + off, (size_t)E * 8, cudaMemcpyHostToDevice, st));
@@ -903,7 +918,9 @@ int irt_voxelize_edges(irt_ctx *ctx, const irt_robot *rb, const irt_space *space
       int32_t h_cnt[4];
       IRT_CUDA(ctx, cudaMemcpyAsync(h_cnt, d_counters, 16, cudaMemcpyDeviceToHost, st));
       IRT_CUDA(ctx, cudaStreamSynchronize(st));
-      const int32_t ncur = std::min(*(cur == d_q0 ? &h_cnt[2] : &h_cnt[3]), (int32_t)cap_samples);
+      const int32_t ncur_raw = *(cur == d_q0 ? &h_cnt[2] : &h_cnt[3]);
+      if (ncur_raw > (int32_t)cap_samples) pool_overflow = true;
+      const int32_t ncur = std::min(ncur_raw, (int32_t)cap_samples);
       if (ncur == 0) break;
       const int32_t s_lo = std::min(h_cnt[0], (int32_t)cap_samples);
       IRT_CUDA(ctx, cudaMemsetAsync(d_counters + 1, 0, 4, st));  // n_pend
@@ -917,6 +934,7 @@ int irt_voxelize_edges(irt_ctx *ctx, const irt_robot *rb, const irt_space *space
       if (h_cnt[0] > (int32_t)cap_samples) {  // keep the counter in range
         int32_t capv = (int32_t)cap_samples;
         IRT_CUDA(ctx, cudaMemcpyAsync(d_counters, &capv, 4, cudaMemcpyHostToDevice, st));
+        pool_overflow = true;
       }
       rc = run_fk(s_lo, s_hi);
       if (rc) return rc;
@@ -929,6 +947,13 @@ int irt_voxelize_edges(irt_ctx *ctx, const irt_robot *rb, const irt_space *space
       std::swap(cur, nxt);
       std::swap(n_cur, n_nxt);
       tr.point("bisection round", s_hi - s_lo);
+    }
+    if (pool_overflow && E > 256) {  // redo this range as two halves (nothing was appended yet)
+      const int64_t h1 = E / 2;
+      work.emplace_back(off + h1, E - h1);
+      work.emplace_back(off, h1);
+      tr.point("pool overflow -> split");
+      continue;
     }
     edge_finish_kernel<<<(E + T - 1) / T, T, 0, st>>>(P, E, d_tlimit, d_flags_out);
     IRT_LAUNCHED(ctx);
