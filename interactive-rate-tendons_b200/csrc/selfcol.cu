@@ -93,7 +93,9 @@ self_collision_kernel(const double *__restrict__ p, const int32_t *__restrict__ 
     const double *src = p + shape * (int64_t)cap_pts * 3;
     for (int i = lane; i < N * 3; i += 32) px[i] = src[i];
     __syncwarp();
-    // accumulated L2 distances, summed in the reference's order (collision.cpp:22-29)
+    // segment lengths (the reference's per-point distance, collision.cpp:22-29); acc[] is only
+    // turned into the running sum (same sequential order as the reference) if it is ever needed
+    double maxlen = 0.0;
     for (int i = lane; i < N; i += 32) {
       double len = 0.0;
       if (i > 0) {
@@ -102,12 +104,15 @@ self_collision_kernel(const double *__restrict__ p, const int32_t *__restrict__ 
         len = sqrt((dx * dx + dy * dy) + dz * dz);
       }
       acc[i] = len;
+      maxlen = fmax(maxlen, len);
     }
-    __syncwarp();
-    if (lane == 0) {
-      double dsum = 0.0;
-      for (int i = 0; i < N; i++) { dsum += acc[i]; acc[i] = dsum; }
-    }
+    for (int o = 16; o > 0; o >>= 1) maxlen = fmax(maxlen, __shfl_xor_sync(0xffffffffu, maxlen, o));
+    // Index pre-filter, exact: acc[b] - acc[a+1] is a sum of (b - a - 1) segment lengths, so it is
+    // below 3r whenever (b - a - 1) * maxlen is (with a 1e-9 safety factor for the rounding of the
+    // running sum): such pairs are skipped by the reference's own rule (collision.cpp:37-39).
+    // min_gap = smallest b - a - 1 that can survive the rule.
+    const double safe = dist_to_consider * (1.0 - 1e-9);
+    const int min_gap = (maxlen > 0.0) ? (int)fmin(1e6, floor(safe / maxlen)) : 1000000;
     __syncwarp();
     // chunk bounding spheres over capsules [c*8, c*8+8) i.e. points [c*8, min(c*8+8, N-1)]
     const int ncap = N - 1;
@@ -125,6 +130,7 @@ self_collision_kernel(const double *__restrict__ p, const int32_t *__restrict__ 
     }
     __syncwarp();
     bool hit = false;
+    bool have_acc = false;
     const int npairs = nchunk * nchunk;
     for (int base_pair = 0; base_pair < npairs && !hit; base_pair += 32) {
       const int pair = base_pair + lane;
@@ -132,7 +138,9 @@ self_collision_kernel(const double *__restrict__ p, const int32_t *__restrict__ 
       int ca = 0, cb = 0;
       if (pair < npairs) {
         ca = pair / nchunk; cb = pair - ca * nchunk;
-        if (cb >= ca) {
+        // largest index gap b - a - 1 inside this chunk pair
+        const int max_gap = (cb + 1) * SC_CHUNK - 1 - ca * SC_CHUNK - 1;
+        if (cb >= ca && max_gap >= min_gap) {
           const double dx = ch[4 * ca] - ch[4 * cb], dy = ch[4 * ca + 1] - ch[4 * cb + 1],
                        dz = ch[4 * ca + 2] - ch[4 * cb + 2];
           const double reach = (ch[4 * ca + 3] + ch[4 * cb + 3] + rr) * (1.0 + 1e-9) + 1e-12;
@@ -140,6 +148,14 @@ self_collision_kernel(const double *__restrict__ p, const int32_t *__restrict__ 
         }
       }
       unsigned m = __ballot_sync(0xffffffffu, near);
+      if (m && !have_acc) {  // rare: some distant chunks come close -> build the exact running sum
+        if (lane == 0) {
+          double dsum = 0.0;
+          for (int i = 0; i < N; i++) { dsum += acc[i]; acc[i] = dsum; }
+        }
+        have_acc = true;
+        __syncwarp();
+      }
       while (m && !hit) {
         const int src_lane = __ffs(m) - 1;
         m &= m - 1;

@@ -51,7 +51,8 @@ struct Trace {
 constexpr int RS_WARPS = 4;
 constexpr int RS_HASH = 1024;        // hash entries per warp (power of two)
 constexpr uint32_t RS_EMPTY = 0xffffffffu;
-constexpr int RS_WARP_BYTES = RS_HASH * 18 + 16;
+constexpr int RS_MAXS = 128;          // samples of one set handled by the flat segment walk
+constexpr int RS_WARP_BYTES = RS_HASH * 18 + 16 + RS_MAXS * 8;
 constexpr int RS_SMEM = RS_WARPS * RS_WARP_BYTES;
 constexpr uint32_t INVALID_MASK = IRT_FLAG_NONCONVERGED | IRT_FLAG_LENGTH_LIMIT |
                                   IRT_FLAG_SELF_COLLISION | IRT_FLAG_BAD_STATE;
@@ -102,11 +103,24 @@ __device__ __forceinline__ void hash_insert(const WarpHash &h, uint32_t key, uns
   *h.overflow = 1u;
 }
 
-// VoxelOctree::set_cell(ix,iy,iz,true) -- collision/VoxelOctree.cpp:262-272,1501-1503
-__device__ __forceinline__ void set_cell(const WarpHash &h, int ix, int iy, int iz) {
-  const uint32_t key = morton_key((uint32_t)ix >> 2, (uint32_t)iy >> 2, (uint32_t)iz >> 2);
-  const unsigned long long mask = 1ull << ((ix & 3) * 16 + (iy & 3) * 4 + (iz & 3));
-  hash_insert(h, key, mask);
+// VoxelOctree::set_cell(ix,iy,iz,true) -- collision/VoxelOctree.cpp:262-272,1501-1503.
+// Consecutive cells of a segment mostly fall into the same 4x4x4 block: bits are collected in
+// registers and flushed to the shared hash (one Morton key + one atomicOr) when the block changes.
+struct BlockAcc {
+  int bx = -1, by = 0, bz = 0;
+  unsigned long long mask = 0ull;
+};
+__device__ __forceinline__ void flush_block(const WarpHash &h, BlockAcc &acc) {
+  if (acc.mask) hash_insert(h, morton_key((uint32_t)acc.bx, (uint32_t)acc.by, (uint32_t)acc.bz), acc.mask);
+  acc.mask = 0ull;
+}
+__device__ __forceinline__ void set_cell(const WarpHash &h, BlockAcc &acc, int ix, int iy, int iz) {
+  const int bx = ix >> 2, by = iy >> 2, bz = iz >> 2;
+  if (bx != acc.bx || by != acc.by || bz != acc.bz) {
+    flush_block(h, acc);
+    acc.bx = bx; acc.by = by; acc.bz = bz;
+  }
+  acc.mask |= 1ull << ((ix & 3) * 16 + (iy & 3) * 4 + (iz & 3));
 }
 
 // collision/collision_primitives.h:62-85, literal operation order
@@ -148,9 +162,10 @@ __device__ void add_line(const GridDev &g, const WarpHash &h, const D3 &a, const
   const int N = g.Ng;
 #define IDX_IN(v) (0 <= (v) && (v) < N)
 #define VOX_IN(x, y, z) (IDX_IN(x) && IDX_IN(y) && IDX_IN(z))
+  BlockAcc acc;
   bool entered = VOX_IN(Axi, Ayi, Azi);
-  if (entered) set_cell(h, Axi, Ayi, Azi);
-  if (VOX_IN(Bxi, Byi, Bzi)) set_cell(h, Bxi, Byi, Bzi);
+  if (VOX_IN(Bxi, Byi, Bzi)) set_cell(h, acc, Bxi, Byi, Bzi);
+  if (entered) set_cell(h, acc, Axi, Ayi, Azi);
   D3 U = {B.x - A.x, B.y - A.y, B.z - A.z};
   {
     const double z = (U.x * U.x + U.y * U.y) + U.z * U.z;  // Eigen normalized()
@@ -187,8 +202,9 @@ __device__ void add_line(const GridDev &g, const WarpHash &h, const D3 &a, const
       tz += tz_delta;
     }
     if (!entered && VOX_IN(xi, yi, zi)) entered = true;
-    if (entered) set_cell(h, xi, yi, zi);
+    if (entered) set_cell(h, acc, xi, yi, zi);
   }
+  flush_block(h, acc);
 #undef IDX_IN
 #undef VOX_IN
 }
@@ -219,6 +235,8 @@ swept_voxel_raster_kernel(const GridDev g, const double *__restrict__ pts,
   h.list = reinterpret_cast<uint16_t *>(wbase + RS_HASH * 16);
   h.count = reinterpret_cast<uint32_t *>(wbase + RS_HASH * 18);
   h.overflow = h.count + 1;
+  int32_t *ls = reinterpret_cast<int32_t *>(wbase + RS_HASH * 18 + 16);  // sample ids
+  int32_t *lc = ls + RS_MAXS;                                            // first flat segment index
   for (int i = lane; i < RS_HASH; i += 32) { h.keys[i] = RS_EMPTY; h.bits[i] = 0ull; }
   if (lane == 0) { *h.count = 0u; *h.overflow = 0u; }
   __syncwarp();
@@ -227,7 +245,8 @@ swept_voxel_raster_kernel(const GridDev g, const double *__restrict__ pts,
        set += (int64_t)gridDim.x * RS_WARPS) {
     const double lim = tlimit ? tlimit[set] : 0.0;
     double tl = 0.0;
-    int ns = 0;
+    int ns = 0, nsm = 0, total = 0;
+    // pass 1: list the included samples with their cumulative segment counts (flat work list)
     for (int smp = set_head[set]; smp >= 0; smp = sample_next ? sample_next[smp] : -1) {
       ns++;
       if (tlimit) {
@@ -236,12 +255,26 @@ swept_voxel_raster_kernel(const GridDev g, const double *__restrict__ pts,
         if (tl < t) tl = t;        // :419-422 last valid t
       }
       const int P = npts[smp];
-      const double *sp = pts + (int64_t)smp * cap_pts * 3;
-      for (int i = 1 + lane; i < P; i += 32) {  // add_piecewise_line: segments (i-1, i)
-        const D3 a = rotate_pt(g, sp + 3 * (i - 1));
-        const D3 b = rotate_pt(g, sp + 3 * i);
-        add_line(g, h, a, b);
+      if (P < 2) continue;         // add_piecewise_line of fewer than 2 points adds nothing
+      if (nsm < RS_MAXS) {
+        if (lane == 0) { ls[nsm] = smp; lc[nsm] = total; }
+        nsm++;
+        total += P - 1;
+      } else {  // very long sample lists: the remainder goes sample by sample
+        const double *sp = pts + (int64_t)smp * cap_pts * 3;
+        for (int i = 1 + lane; i < P; i += 32)
+          add_line(g, h, rotate_pt(g, sp + 3 * (i - 1)), rotate_pt(g, sp + 3 * i));
       }
+    }
+    __syncwarp();
+    // pass 2: lanes take consecutive segments of the concatenated polylines
+    for (int f = lane; f < total; f += 32) {
+      int k = 0;
+      for (int step = RS_MAXS >> 1; step > 0; step >>= 1)
+        if (k + step < nsm && lc[k + step] <= f) k += step;
+      const int i = f - lc[k] + 1;  // segment (i-1, i) of sample ls[k]
+      const double *sp = pts + (int64_t)ls[k] * cap_pts * 3;
+      add_line(g, h, rotate_pt(g, sp + 3 * (i - 1)), rotate_pt(g, sp + 3 * i));
     }
     __syncwarp();
     const int cnt = (int)min(*h.count, (uint32_t)RS_HASH);
