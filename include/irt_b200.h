@@ -236,6 +236,42 @@ int irt_check_sets_popcount(irt_ctx *ctx, const irt_setstore *store, const irt_e
  * sum(12*nb + 8) + 8*Nb^3 + ceil(n/8) */
 int64_t irt_check_sets_algorithmic_bytes(const irt_setstore *store, int64_t begin, int64_t end);
 
+/* ---- .rmp roadmap files (SURVEY 8f "next" #1) ----------------------------------------------
+ * The reference's binary roadmap format: LazyRmpParser / RmpStreamer
+ * (motion-planning/VoxelCachedLazyPRM.cpp:862-1114, serialize_inner :636-657):
+ *   u32 nV, u32 nE, bool has_voxels, [u8 Nb, f64 lims[6]],
+ *   per vertex: u32 index, vector<f64> state (u32 count + data), optional<Vector3d> tip,
+ *               [bool has, u32 nblocks, nblocks x {u8 bx, u8 by, u8 bz, u64 bits}]
+ *   per edge:   u32 source, u32 target, f64 weight, [bool has, u32 nblocks, blocks...]
+ * irt_rmp_read parses such a file into host arrays whose voxel part is already the CSR
+ * (offsets / Morton keys / bits) that irt_setstore_import takes; irt_rmp_write is the inverse
+ * (blocks are written in key order == the reference's visit_leaves order).  Host-side IO only. */
+typedef struct irt_rmp {
+  uint32_t n_verts, n_edges;
+  int32_t has_voxels; /* reference voxel header present */
+  int32_t Nb;         /* blocks per axis (Ng / 4) */
+  double lims[6];
+  int32_t state_size; /* all vertex states must have this many reals */
+  int32_t _pad;
+  uint32_t *v_index;  /* [nV] */
+  double *v_state;    /* [nV][state_size] */
+  uint8_t *v_has_tip; /* [nV] */
+  double *v_tip;      /* [nV][3] */
+  uint8_t *v_has_vox; /* [nV] */
+  uint64_t *v_off;    /* [nV + 1] */
+  uint32_t *v_keys;   /* [v_off[nV]] Morton keys */
+  uint64_t *v_bits;
+  uint32_t *e_src, *e_dst; /* [nE] */
+  double *e_weight;        /* [nE] */
+  uint8_t *e_has_vox;      /* [nE] */
+  uint64_t *e_off;         /* [nE + 1] */
+  uint32_t *e_keys;
+  uint64_t *e_bits;
+} irt_rmp;
+int irt_rmp_read(const char *path, irt_rmp **out);
+int irt_rmp_write(const char *path, const irt_rmp *r);
+void irt_rmp_free(irt_rmp *r);
+
 #ifdef __cplusplus
 }
 #endif

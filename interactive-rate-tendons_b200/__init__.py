@@ -70,6 +70,17 @@ class Space(C.Structure):
                 ("min_retraction_change", C.c_double)]
 
 
+class Rmp(C.Structure):
+    """irt_rmp: a roadmap file parsed into host arrays (voxels as CSR with Morton keys)"""
+    _fields_ = [("n_verts", C.c_uint32), ("n_edges", C.c_uint32), ("has_voxels", C.c_int32),
+                ("Nb", C.c_int32), ("lims", C.c_double * 6), ("state_size", C.c_int32), ("_pad", C.c_int32),
+                ("v_index", C.c_void_p), ("v_state", C.c_void_p), ("v_has_tip", C.c_void_p),
+                ("v_tip", C.c_void_p), ("v_has_vox", C.c_void_p), ("v_off", C.c_void_p),
+                ("v_keys", C.c_void_p), ("v_bits", C.c_void_p), ("e_src", C.c_void_p),
+                ("e_dst", C.c_void_p), ("e_weight", C.c_void_p), ("e_has_vox", C.c_void_p),
+                ("e_off", C.c_void_p), ("e_keys", C.c_void_p), ("e_bits", C.c_void_p)]
+
+
 class FkOutputs(C.Structure):
     _fields_ = [("p", C.c_void_p), ("R", C.c_void_p), ("t", C.c_void_p), ("npts", C.c_void_p),
                 ("L", C.c_void_p), ("L_i", C.c_void_p), ("tip", C.c_void_p), ("uv", C.c_void_p),
@@ -90,6 +101,7 @@ ABI_SYMBOLS = [
     "irt_voxelize_vertices", "irt_voxelize_shapes", "irt_voxelize_edges", "irt_valid_segment_count",
     "irt_check_sets", "irt_check_sets_dev", "irt_check_sets_popcount",
     "irt_check_sets_algorithmic_bytes",
+    "irt_rmp_read", "irt_rmp_write", "irt_rmp_free",
 ]
 
 _lib = None
@@ -146,6 +158,9 @@ def lib():
         "irt_check_sets_dev": (i32, [vp, vp, vp, i64, i64, vp, vp]),
         "irt_check_sets_popcount": (i32, [vp, vp, vp, i64, i64, vp]),
         "irt_check_sets_algorithmic_bytes": (i64, [vp, i64, i64]),
+        "irt_rmp_read": (i32, [C.c_char_p, C.POINTER(C.POINTER(Rmp))]),
+        "irt_rmp_write": (i32, [C.c_char_p, C.POINTER(Rmp)]),
+        "irt_rmp_free": (None, [C.POINTER(Rmp)]),
     }
     for name, (res, args) in sig.items():
         f = getattr(L, name)
@@ -456,6 +471,69 @@ class SetStore:
     def algorithmic_bytes(self, begin=0, end=None):
         end = self.num_sets if end is None else end
         return int(self.ctx.L.irt_check_sets_algorithmic_bytes(self.h, begin, end))
+
+
+def _arr(ptr, n, dtype):
+    if n == 0:
+        return np.zeros(0, dtype=dtype)
+    buf = (C.c_char * (n * np.dtype(dtype).itemsize)).from_address(ptr)
+    return np.frombuffer(buf, dtype=dtype).copy()
+
+
+def read_rmp(path):
+    """Parse a reference `.rmp` roadmap (VoxelCachedLazyPRM.cpp:862-1114) into numpy arrays; the
+    vertex / edge voxel caches come back as CSR triples ready for SetStore.import_csr."""
+    L = lib()
+    p = C.POINTER(Rmp)()
+    rc = L.irt_rmp_read(os.fsencode(path), C.byref(p))
+    if rc != IRT_OK:
+        raise IrtError(rc, "cannot parse %s" % path)
+    r = p.contents
+    nv, ne, S = r.n_verts, r.n_edges, r.state_size
+    voff = _arr(r.v_off, nv + 1, np.uint64)
+    eoff = _arr(r.e_off, ne + 1, np.uint64)
+    out = dict(
+        n_verts=nv, n_edges=ne, has_voxels=bool(r.has_voxels), Ng=r.Nb * 4, lims=list(r.lims),
+        v_index=_arr(r.v_index, nv, np.uint32), v_state=_arr(r.v_state, nv * S, np.float64).reshape(nv, S),
+        v_has_tip=_arr(r.v_has_tip, nv, np.uint8).astype(bool), v_tip=_arr(r.v_tip, nv * 3, np.float64).reshape(nv, 3),
+        v_has_vox=_arr(r.v_has_vox, nv, np.uint8).astype(bool), v_off=voff,
+        v_keys=_arr(r.v_keys, int(voff[-1]), np.uint32), v_bits=_arr(r.v_bits, int(voff[-1]), np.uint64),
+        e_src=_arr(r.e_src, ne, np.uint32), e_dst=_arr(r.e_dst, ne, np.uint32),
+        e_weight=_arr(r.e_weight, ne, np.float64), e_has_vox=_arr(r.e_has_vox, ne, np.uint8).astype(bool),
+        e_off=eoff, e_keys=_arr(r.e_keys, int(eoff[-1]), np.uint32), e_bits=_arr(r.e_bits, int(eoff[-1]), np.uint64))
+    L.irt_rmp_free(p)
+    return out
+
+
+def write_rmp(path, d):
+    """Inverse of read_rmp: `d` has the same keys (numpy arrays)."""
+    L = lib()
+    keep = []
+
+    def ptr(a, dt):
+        a = np.ascontiguousarray(a, dtype=dt)
+        if a.size == 0:
+            a = np.zeros(1, dtype=dt)
+        keep.append(a)
+        return a.ctypes.data
+
+    r = Rmp()
+    r.n_verts, r.n_edges = int(d["n_verts"]), int(d["n_edges"])
+    r.has_voxels = int(bool(d["has_voxels"]))
+    r.Nb = int(d["Ng"]) // 4
+    for i, v in enumerate(d["lims"]):
+        r.lims[i] = float(v)
+    r.state_size = int(np.asarray(d["v_state"]).shape[1]) if r.n_verts else 0
+    r.v_index = ptr(d["v_index"], np.uint32); r.v_state = ptr(d["v_state"], np.float64)
+    r.v_has_tip = ptr(d["v_has_tip"], np.uint8); r.v_tip = ptr(d["v_tip"], np.float64)
+    r.v_has_vox = ptr(d["v_has_vox"], np.uint8); r.v_off = ptr(d["v_off"], np.uint64)
+    r.v_keys = ptr(d["v_keys"], np.uint32); r.v_bits = ptr(d["v_bits"], np.uint64)
+    r.e_src = ptr(d["e_src"], np.uint32); r.e_dst = ptr(d["e_dst"], np.uint32)
+    r.e_weight = ptr(d["e_weight"], np.float64); r.e_has_vox = ptr(d["e_has_vox"], np.uint8)
+    r.e_off = ptr(d["e_off"], np.uint64); r.e_keys = ptr(d["e_keys"], np.uint32); r.e_bits = ptr(d["e_bits"], np.uint64)
+    rc = L.irt_rmp_write(os.fsencode(path), C.byref(r))
+    if rc != IRT_OK:
+        raise IrtError(rc, "cannot write %s" % path)
 
 
 def unpack_verdicts(words, n):

@@ -1,0 +1,127 @@
+"""`.rmp` roadmap files: the native reader/writer against a byte-level restatement of
+the reference's RmpStreamer layout written here with struct.pack
+(motion-planning/VoxelCachedLazyPRM.cpp:636-657, 862-1114)."""
+import struct
+
+import numpy as np
+import pytest
+
+
+def _pack_blocks(wl, keys, bits, Nb):
+    bx, by, bz = wl.morton_decode(np.asarray(keys, dtype=np.uint32), Nb)
+    out = struct.pack("<I", len(keys))
+    for x, y, z, b in zip(bx.tolist(), by.tolist(), bz.tolist(), np.asarray(bits).tolist()):
+        out += struct.pack("<BBBQ", x, y, z, b)
+    return out
+
+
+def _reference_style_bytes(wl, d):
+    """what RmpStreamer writes: u32 nV, u32 nE, bool has_voxels, [u8 Nb, 6 f64], items..."""
+    Nb = d["Ng"] // 4
+    out = struct.pack("<II?", d["n_verts"], d["n_edges"], d["has_voxels"])
+    if d["has_voxels"]:
+        out += struct.pack("<B6d", Nb, *d["lims"])
+    for i in range(d["n_verts"]):
+        st = d["v_state"][i]
+        out += struct.pack("<II", int(d["v_index"][i]), len(st)) + struct.pack("<%dd" % len(st), *st)
+        out += struct.pack("<?", bool(d["v_has_tip"][i]))
+        if d["v_has_tip"][i]:
+            out += struct.pack("<3d", *d["v_tip"][i])
+        if d["has_voxels"]:
+            out += struct.pack("<?", bool(d["v_has_vox"][i]))
+            if d["v_has_vox"][i]:
+                lo, hi = int(d["v_off"][i]), int(d["v_off"][i + 1])
+                out += _pack_blocks(wl, d["v_keys"][lo:hi], d["v_bits"][lo:hi], Nb)
+    for i in range(d["n_edges"]):
+        out += struct.pack("<IId", int(d["e_src"][i]), int(d["e_dst"][i]), float(d["e_weight"][i]))
+        if d["has_voxels"]:
+            out += struct.pack("<?", bool(d["e_has_vox"][i]))
+            if d["e_has_vox"][i]:
+                lo, hi = int(d["e_off"][i]), int(d["e_off"][i + 1])
+                out += _pack_blocks(wl, d["e_keys"][lo:hi], d["e_bits"][lo:hi], Nb)
+    return out
+
+
+def _roadmap(orc, wl, n=24):
+    spec = wl.robot_b(0.003)
+    g = wl.workspace_grid(spec)
+    rb = orc.robot(spec)
+    grid = orc.grid(g["Ng"], g["lim"])
+    st = wl.sample_states(spec, n, stream=401)
+    vs, vflags = orc.voxelize_vertices_batch(rb, grid, st)
+    pairs = wl.knn_edges(spec, st, k=2)
+    es, einfo = orc.voxelize_edges_batch(rb, grid, orc.space(), st[pairs[:, 0]], st[pairs[:, 1]])
+    voff, vkeys, vbits = vs.export()
+    eoff, ekeys, ebits = es.export()
+    ref = orc.fk_batch(rb, st, 68, want_p=False)
+    d = dict(n_verts=n, n_edges=len(pairs), has_voxels=True, Ng=g["Ng"], lims=g["lim"],
+             v_index=np.arange(n, dtype=np.uint32), v_state=st, v_has_tip=np.arange(n) % 5 != 0, v_tip=ref["tip"],
+             v_has_vox=(np.diff(voff.astype(np.int64)) > 0), v_off=voff, v_keys=vkeys, v_bits=vbits,
+             e_src=pairs[:, 0].astype(np.uint32), e_dst=pairs[:, 1].astype(np.uint32),
+             e_weight=np.linalg.norm(st[pairs[:, 0]] - st[pairs[:, 1]], axis=1),
+             e_has_vox=(np.diff(eoff.astype(np.int64)) > 0), e_off=eoff, e_keys=ekeys, e_bits=ebits)
+    return spec, g, d
+
+
+def test_rmp_roundtrip_and_reference_layout(tmp_path, orc, wl):
+    import irt_b200
+    spec, g, d = _roadmap(orc, wl)
+    ref_bytes = _reference_style_bytes(wl, d)
+    ref_file = tmp_path / "ref.rmp"
+    ref_file.write_bytes(ref_bytes)
+    r = irt_b200.read_rmp(str(ref_file))
+    assert r["n_verts"] == d["n_verts"] and r["n_edges"] == d["n_edges"] and r["Ng"] == 128
+    assert np.allclose(r["lims"], d["lims"], atol=0)
+    for k in ("v_index", "v_state", "v_has_tip", "v_has_vox", "v_off", "v_keys", "v_bits",
+              "e_src", "e_dst", "e_weight", "e_has_vox", "e_off", "e_keys", "e_bits"):
+        assert np.array_equal(r[k], np.asarray(d[k])), k
+    assert np.array_equal(r["v_tip"][d["v_has_tip"]], d["v_tip"][d["v_has_tip"]])
+    out_file = tmp_path / "out.rmp"
+    irt_b200.write_rmp(str(out_file), r)
+    assert out_file.read_bytes() == ref_bytes          # byte-identical to the reference layout
+    # no-voxel roadmap
+    d2 = dict(d, has_voxels=False)
+    f2 = tmp_path / "novox.rmp"
+    f2.write_bytes(_reference_style_bytes(wl, d2))
+    r2 = irt_b200.read_rmp(str(f2))
+    assert not r2["has_voxels"] and r2["v_keys"].size == 0 and np.array_equal(r2["v_state"], d["v_state"])
+    # truncated file is rejected
+    bad = tmp_path / "bad.rmp"
+    bad.write_bytes(ref_bytes[:len(ref_bytes) // 2])
+    with pytest.raises(irt_b200.IrtError):
+        irt_b200.read_rmp(str(bad))
+
+
+@pytest.mark.gpu
+def test_rmp_loads_into_device_store(tmp_path, orc, wl):
+    """a reference-style .rmp goes file -> CSR -> device store -> verdicts, and a GPU-built roadmap
+    is written back byte-identically"""
+    import irt_b200 as irt
+    spec, g, d = _roadmap(orc, wl, n=64)
+    f = tmp_path / "ref.rmp"
+    f.write_bytes(_reference_style_bytes(wl, d))
+    r = irt.read_rmp(str(f))
+    ctx = irt.Context(0)
+    grid = irt.make_grid(r["Ng"], r["lims"])
+    es = irt.SetStore(ctx, grid)
+    es.import_csr(r["e_off"], r["e_keys"], r["e_bits"])
+    env_blocks = wl.dense_to_morton_blocks(wl.lung_like_env_dense(spec, g))
+    env = irt.Env(ctx, grid)
+    env.update(env_blocks)
+    got = es.check(env)
+    x = d["e_bits"] & env_blocks[d["e_keys"]]
+    want = np.add.reduceat((x != 0).astype(np.int64), d["e_off"][:-1].astype(np.int64)) > 0
+    want[np.diff(d["e_off"].astype(np.int64)) == 0] = False
+    assert np.array_equal(got, want)
+    # GPU-built caches written in the reference's format are byte-identical to the oracle-built file
+    rb = irt.Robot(ctx, spec)
+    vs = irt.SetStore(ctx, grid)
+    vs.voxelize_vertices(rb, r["v_state"])
+    es2 = irt.SetStore(ctx, grid)
+    es2.voxelize_edges(rb, irt.make_space(), r["v_state"][r["e_src"]], r["v_state"][r["e_dst"]])
+    voff, vkeys, vbits = vs.export_csr()
+    eoff, ekeys, ebits = es2.export_csr()
+    out = dict(r, v_off=voff, v_keys=vkeys, v_bits=vbits, e_off=eoff, e_keys=ekeys, e_bits=ebits)
+    g_file = tmp_path / "gpu.rmp"
+    irt.write_rmp(str(g_file), out)
+    assert g_file.read_bytes() == f.read_bytes()
