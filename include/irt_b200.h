@@ -212,6 +212,14 @@ int irt_voxelize_shapes(irt_ctx *ctx, const double *p, const int32_t *npts, int 
 int irt_voxelize_edges(irt_ctx *ctx, const irt_robot *rb, const irt_space *space,
                        const double *a, const double *b, int state_size, int64_t n,
                        irt_setstore *store, uint32_t *flags, double *t_last, int32_t *nsamples);
+/* Same, for edges given as index pairs into one list of roadmap vertices (the planner's own
+ * representation: boost::source(e) / boost::target(e), VoxelCachedLazyPRM.cpp:2888-2891).  The FK of
+ * every vertex is computed once and shared by all incident edges.  pairs: int64[n_edges][2].
+ * IRT_ERR_OUT_OF_RANGE if an index is outside [0, n_vertices). */
+int irt_voxelize_edges_indexed(irt_ctx *ctx, const irt_robot *rb, const irt_space *space,
+                               const double *vertex_states, int state_size, int64_t n_vertices,
+                               const int64_t *pairs, int64_t n_edges, irt_setstore *store,
+                               uint32_t *flags, double *t_last, int32_t *nsamples);
 /* OMPL StateSpace::validSegmentCount for the compound space of Problem.cpp:101-163 (host) */
 uint32_t irt_valid_segment_count(const irt_robot_desc *desc, const irt_space *space,
                                  const double *a, const double *b);

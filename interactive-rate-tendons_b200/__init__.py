@@ -98,7 +98,8 @@ ABI_SYMBOLS = [
     "irt_setstore_create", "irt_setstore_destroy", "irt_setstore_num_sets",
     "irt_setstore_num_blocks", "irt_setstore_import", "irt_setstore_export",
     "irt_setstore_device_ptrs", "irt_morton_key", "irt_morton_decode",
-    "irt_voxelize_vertices", "irt_voxelize_shapes", "irt_voxelize_edges", "irt_valid_segment_count",
+    "irt_voxelize_vertices", "irt_voxelize_shapes", "irt_voxelize_edges", "irt_voxelize_edges_indexed",
+    "irt_valid_segment_count",
     "irt_check_sets", "irt_check_sets_dev", "irt_check_sets_popcount",
     "irt_check_sets_algorithmic_bytes",
     "irt_rmp_read", "irt_rmp_write", "irt_rmp_free",
@@ -153,6 +154,7 @@ def lib():
         "irt_voxelize_vertices": (i32, [vp, vp, vp, i32, i64, vp, vp, vp]),
         "irt_voxelize_shapes": (i32, [vp, vp, vp, i32, i64, vp]),
         "irt_voxelize_edges": (i32, [vp, vp, C.POINTER(Space), vp, vp, i32, i64, vp, vp, vp, vp]),
+        "irt_voxelize_edges_indexed": (i32, [vp, vp, C.POINTER(Space), vp, i32, i64, vp, i64, vp, vp, vp, vp]),
         "irt_valid_segment_count": (u32, [C.POINTER(RobotDesc), C.POINTER(Space), vp, vp]),
         "irt_check_sets": (i32, [vp, vp, vp, i64, i64, vp]),
         "irt_check_sets_dev": (i32, [vp, vp, vp, i64, i64, vp, vp]),
@@ -446,6 +448,21 @@ class SetStore:
         nsamples = np.zeros(n, dtype=np.int32)
         self.ctx.check(self.ctx.L.irt_voxelize_edges(self.ctx.h, robot.h, C.byref(space), _ptr(a), _ptr(b),
                                                      S, n, self.h, _ptr(flags), _ptr(t_last), _ptr(nsamples)))
+        return dict(flags=flags, t_last=t_last, nsamples=nsamples)
+
+    def voxelize_edges_indexed(self, robot, space, vertex_states, pairs):
+        """precomputeEdgeVoxelCache with edges given as (source, target) vertex indices; every
+        vertex's FK is computed once and shared by its incident edges."""
+        vs = _np(vertex_states, np.float64)
+        pr = _np(pairs, np.int64).reshape(-1, 2)
+        nv, S = vs.shape
+        n = pr.shape[0]
+        flags = np.zeros(n, dtype=np.uint32)
+        t_last = np.zeros(n)
+        nsamples = np.zeros(n, dtype=np.int32)
+        self.ctx.check(self.ctx.L.irt_voxelize_edges_indexed(
+            self.ctx.h, robot.h, C.byref(space), _ptr(vs), S, nv, _ptr(pr), n, self.h,
+            _ptr(flags), _ptr(t_last), _ptr(nsamples)))
         return dict(flags=flags, t_last=t_last, nsamples=nsamples)
 
     def check(self, env, begin=0, end=None):

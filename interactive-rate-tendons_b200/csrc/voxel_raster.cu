@@ -448,6 +448,70 @@ __global__ void edge_init_kernel(EdgePool P, int32_t E) {
   P.eflags[e] = 0u;
 }
 
+// indexed form: the endpoints of edge e are roadmap vertices whose FK already exists in a vertex
+// pool; one warp per endpoint sample copies state, shape, point count and validity flags.
+__global__ void edge_init_indexed_kernel(EdgePool P, int32_t E, const int64_t *__restrict__ pairs,
+                                         const double *__restrict__ vstates, const double *__restrict__ vp,
+                                         const int32_t *__restrict__ vnpts, const uint32_t *__restrict__ vflags,
+                                         double *__restrict__ a_out, double *__restrict__ b_out) {
+  const int lane = threadIdx.x & 31;
+  const int64_t w = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (w >= 2 * (int64_t)E) return;
+  const int32_t e = (int32_t)(w >> 1), side = (int32_t)(w & 1);
+  const int64_t v = pairs[2 * (int64_t)e + side];
+  const int32_t smp = 2 * e + side;
+  const int np = vnpts[v];
+  const double *src = vp + v * (int64_t)P.cap_pts * 3;
+  double *dst = P.s_p + (int64_t)smp * P.cap_pts * 3;
+  for (int i = lane; i < np * 3; i += 32) dst[i] = src[i];
+  double *eo = (side ? b_out : a_out) + (int64_t)e * P.S;
+  for (int k = lane; k < P.S; k += 32) {
+    const double x = vstates[v * P.S + k];
+    P.s_state[(int64_t)smp * P.S + k] = x;
+    eo[k] = x;
+  }
+  if (lane == 0) {
+    P.s_edge[smp] = e;
+    P.s_t[smp] = side ? 1.0 : 0.0;
+    P.s_npts[smp] = np;
+    P.s_flags[smp] = vflags[v];
+    P.s_next[smp] = side ? (smp - 1) : -1;
+    if (side) {
+      P.head[e] = smp;
+      P.first_invalid[e] = (unsigned long long)__double_as_longlong(10.0);
+      P.eflags[e] = 0u;
+    }
+  }
+}
+
+// rel_threshold = 1 / validSegmentCount(a, b) (VoxelBackboneMotionValidator.cpp:55-56), the same
+// arithmetic as irt_valid_segment_count (this file is compiled without FMA contraction)
+__global__ void edge_threshold_kernel(EdgePool P, int32_t E, const double *__restrict__ a,
+                                      const double *__restrict__ b, double len_t, double len_r,
+                                      double len_s, double *__restrict__ thr) {
+  const int32_t e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= E) return;
+  const double pi = 3.14159265358979323846;
+  const double *ea = a + (int64_t)e * P.S, *eb = b + (int64_t)e * P.S;
+  double d2 = 0;
+  for (int i = 0; i < P.N; i++) d2 += (ea[i] - eb[i]) * (ea[i] - eb[i]);
+  unsigned sc = (unsigned)ceil(sqrt(d2) / len_t);
+  int idx = P.N;
+  if (P.enable_rotation) {
+    double d = fabs(ea[idx] - eb[idx]);
+    d = (d > pi) ? 2.0 * pi - d : d;
+    const unsigned c = (unsigned)ceil(d / len_r);
+    if (c > sc) sc = c;
+    idx++;
+  }
+  if (P.enable_retraction) {
+    const double d = sqrt((ea[idx] - eb[idx]) * (ea[idx] - eb[idx]));
+    const unsigned c = (unsigned)ceil(d / len_s);
+    if (c > sc) sc = c;
+  }
+  thr[e] = 1.0 / double(sc);
+}
+
 // after FK: invalid samples lower first_invalid_t of their edge (VoxelEnvironment.cpp:266-268)
 __global__ void edge_mark_kernel(EdgePool P, int32_t lo, int32_t hi) {
   const int32_t i = lo + blockIdx.x * blockDim.x + threadIdx.x;
@@ -829,11 +893,21 @@ int irt_voxelize_shapes(irt_ctx *ctx, const double *p, const int32_t *npts, int 
   return setstore_finalize(ctx, store, n, (int64_t)running, st);
 }
 
-int irt_voxelize_edges(irt_ctx *ctx, const irt_robot *rb, const irt_space *space, const double *a,
-                       const double *b, int state_size, int64_t n, irt_setstore *store,
-                       uint32_t *flags, double *t_last, int32_t *nsamples) {
-  if (!ctx || !rb || !space || !store || n < 0 || (n > 0 && (!a || !b)))
-    return IRT_ERR_INVALID_ARGUMENT;
+}  // extern "C"
+
+// a, b: per-edge endpoint states (host) -- or, indexed form: vstates[nv][S] + pairs[n][2]
+static int voxelize_edges_core(irt_ctx *ctx, const irt_robot *rb, const irt_space *space, const double *a,
+                               const double *b, const double *vstates, int64_t nv, const int64_t *pairs,
+                               int state_size, int64_t n, irt_setstore *store, uint32_t *flags,
+                               double *t_last, int32_t *nsamples) {
+  const bool indexed = pairs != nullptr;
+  if (!ctx || !rb || !space || !store || n < 0) return IRT_ERR_INVALID_ARGUMENT;
+  if (!indexed && n > 0 && (!a || !b)) return IRT_ERR_INVALID_ARGUMENT;
+  if (indexed && (nv < 0 || (nv > 0 && !vstates))) return IRT_ERR_INVALID_ARGUMENT;
+  if (indexed)
+    for (int64_t i = 0; i < 2 * n; i++)
+      if (pairs[i] < 0 || pairs[i] >= nv)
+        return irt_fail(ctx, IRT_ERR_OUT_OF_RANGE, "edge endpoint %lld outside [0,%lld)", (long long)pairs[i], (long long)nv);
   if (state_size != rb->state_size)
     return irt_fail(ctx, IRT_ERR_INVALID_ARGUMENT, "State is not the right size (%d != %d)",
                     state_size, rb->state_size);
@@ -866,10 +940,17 @@ int irt_voxelize_edges(irt_ctx *ctx, const irt_robot *rb, const irt_space *space
     cap_samples = std::min<int64_t>(cap_samples, std::max<int64_t>(chunk * 64, 4096));
   }
 
-  // host: rel_threshold = 1 / validSegmentCount  (VoxelBackboneMotionValidator.cpp:55-56)
-  std::vector<double> h_thr((size_t)n);
-  for (int64_t i = 0; i < n; i++)
-    h_thr[i] = 1.0 / double(irt_valid_segment_count(&rb->desc, space, a + i * S, b + i * S));
+  // longest valid segment lengths of the three subspaces (Problem.cpp:118-144), as in
+  // irt_valid_segment_count; the per-edge count itself is evaluated on the device
+  double len_t, len_r, len_s;
+  {
+    double ext2 = 0;
+    for (int i = 0; i < rb->desc.n_tendons; i++) ext2 += rb->desc.max_tension[i] * rb->desc.max_tension[i];
+    const double tendon_extent = std::sqrt(ext2);
+    len_t = tendon_extent * (space->min_tension_change / tendon_extent);
+    len_r = M_PI * (space->min_rotation_change / (2 * M_PI));
+    len_s = rb->desc.L * std::fmin(0.01, space->min_retraction_change / rb->desc.L);
+  }
 
   EdgePool P;
   std::memset(&P, 0, sizeof(P));
@@ -879,7 +960,16 @@ int irt_voxelize_edges(irt_ctx *ctx, const irt_robot *rb, const irt_space *space
   Interval *d_q0 = nullptr, *d_q1 = nullptr;
   Pending *d_pend = nullptr;
   RasterScratch rs;
+  // indexed form: FK of every roadmap vertex once; edges gather their endpoint shapes from it
+  double *d_vstates = nullptr, *d_vp = nullptr;
+  int32_t *d_vnpts = nullptr;
+  uint32_t *d_vflags = nullptr;
+  int64_t *d_pairs = nullptr;
   rc = arena_layout(ctx, [&](Arena &A) {
+    if (indexed &&
+        !(A.alloc(&d_vstates, (size_t)nv * S) && A.alloc(&d_vp, (size_t)nv * cap * 3) &&
+          A.alloc(&d_vnpts, (size_t)nv) && A.alloc(&d_vflags, (size_t)nv) && A.alloc(&d_pairs, (size_t)chunk * 2)))
+      return false;
     return A.alloc(&d_a, (size_t)chunk * S) && A.alloc(&d_b, (size_t)chunk * S) &&
            A.alloc(&d_thr, (size_t)chunk) && A.alloc(&d_tlimit, (size_t)chunk) &&
            A.alloc(&d_tlast, (size_t)chunk) && A.alloc(&d_nsamp_set, (size_t)chunk) &&
@@ -902,6 +992,20 @@ int irt_voxelize_edges(irt_ctx *ctx, const irt_robot *rb, const irt_space *space
 
   uint64_t grand_total = 0;
   const int T = 256;
+  if (indexed && nv > 0) {
+    IRT_CUDA(ctx, cudaMemcpyAsync(d_vstates, vstates, (size_t)nv * S * 8, cudaMemcpyHostToDevice, st));
+    for (int64_t v0 = 0; v0 < nv; v0 += 1048576) {
+      const int64_t m = std::min<int64_t>(1048576, nv - v0);
+      irt_fk_outputs o;
+      std::memset(&o, 0, sizeof(o));
+      o.p = d_vp + v0 * cap * 3; o.npts = d_vnpts + v0; o.flags = d_vflags + v0;
+      rc = fk_launch(ctx, rb, d_vstates + v0 * S, m, cap, o, nullptr, st);
+      if (rc) return rc;
+      rc = self_collision_launch(ctx, rb, o.p, o.npts, m, cap, o.flags, st);
+      if (rc) return rc;
+    }
+    tr.point("vertex fk", nv);
+  }
   // work list of edge ranges in index order; a range whose sample pool overflows is split in two
   std::vector<std::pair<int64_t, int64_t>> work;
   for (int64_t off = n - ((n - 1) % chunk + 1); off >= 0; off -= chunk)
@@ -911,11 +1015,19 @@ int irt_voxelize_edges(irt_ctx *ctx, const irt_robot *rb, const irt_space *space
     const int32_t E = (int32_t)work.back().second;
     work.pop_back();
     bool pool_overflow = false;
-    IRT_CUDA(ctx, cudaMemcpyAsync(d_a, a + off * S, (size_t)E * S * 8, cudaMemcpyHostToDevice, st));
-    IRT_CUDA(ctx, cudaMemcpyAsync(d_b, b + off * S, (size_t)E * S * 8, cudaMemcpyHostToDevice, st));
-    IRT_CUDA(ctx, cudaMemcpyAsync(d_thr, h_thr.data() + off, (size_t)E * 8, cudaMemcpyHostToDevice, st));
     IRT_CUDA(ctx, cudaMemsetAsync(d_counters, 0, 32, st));
-    edge_init_kernel<<<(E + T - 1) / T, T, 0, st>>>(P, E);
+    if (indexed) {
+      IRT_CUDA(ctx, cudaMemcpyAsync(d_pairs, pairs + 2 * off, (size_t)E * 16, cudaMemcpyHostToDevice, st));
+      const int64_t threads = (int64_t)E * 2 * 32;
+      edge_init_indexed_kernel<<<(unsigned)((threads + T - 1) / T), T, 0, st>>>(
+          P, E, d_pairs, d_vstates, d_vp, d_vnpts, d_vflags, d_a, d_b);
+    } else {
+      IRT_CUDA(ctx, cudaMemcpyAsync(d_a, a + off * S, (size_t)E * S * 8, cudaMemcpyHostToDevice, st));
+      IRT_CUDA(ctx, cudaMemcpyAsync(d_b, b + off * S, (size_t)E * S * 8, cudaMemcpyHostToDevice, st));
+      edge_init_kernel<<<(E + T - 1) / T, T, 0, st>>>(P, E);
+    }
+    IRT_LAUNCHED(ctx);
+    edge_threshold_kernel<<<(E + T - 1) / T, T, 0, st>>>(P, E, d_a, d_b, len_t, len_r, len_s, d_thr);
     IRT_LAUNCHED(ctx);
     int32_t n_samples = 2 * E;
     IRT_CUDA(ctx, cudaMemcpyAsync(d_counters, &n_samples, 4, cudaMemcpyHostToDevice, st));
@@ -936,8 +1048,13 @@ int irt_voxelize_edges(irt_ctx *ctx, const irt_robot *rb, const irt_space *space
       return IRT_OK;
     };
     tr.point("h2d + init");
-    rc = run_fk(0, n_samples);
-    if (rc) return rc;
+    if (indexed) {  // endpoint shapes came from the vertex pool: only mark the invalid ones
+      edge_mark_kernel<<<(n_samples + T - 1) / T, T, 0, st>>>(P, 0, n_samples);
+      IRT_LAUNCHED(ctx);
+    } else {
+      rc = run_fk(0, n_samples);
+      if (rc) return rc;
+    }
     tr.point("round 0 fk", n_samples);
     Interval *cur = d_q0, *nxt = d_q1;
     int32_t *n_cur = d_counters + 2, *n_nxt = d_counters + 3;
@@ -1006,6 +1123,25 @@ int irt_voxelize_edges(irt_ctx *ctx, const irt_robot *rb, const irt_space *space
   rc = setstore_finalize(ctx, store, n, (int64_t)grand_total, st);
   tr.point("finalize");
   return rc;
+}
+
+extern "C" {
+
+int irt_voxelize_edges(irt_ctx *ctx, const irt_robot *rb, const irt_space *space, const double *a,
+                       const double *b, int state_size, int64_t n, irt_setstore *store,
+                       uint32_t *flags, double *t_last, int32_t *nsamples) {
+  return voxelize_edges_core(ctx, rb, space, a, b, nullptr, 0, nullptr, state_size, n, store, flags, t_last,
+                             nsamples);
+}
+
+int irt_voxelize_edges_indexed(irt_ctx *ctx, const irt_robot *rb, const irt_space *space,
+                               const double *vertex_states, int state_size, int64_t n_vertices,
+                               const int64_t *pairs, int64_t n_edges, irt_setstore *store,
+                               uint32_t *flags, double *t_last, int32_t *nsamples) {
+  if (n_edges > 0 && !pairs) return IRT_ERR_INVALID_ARGUMENT;
+  static const int64_t dummy[2] = {0, 0};
+  return voxelize_edges_core(ctx, rb, space, nullptr, nullptr, vertex_states, n_vertices,
+                             pairs ? pairs : dummy, state_size, n_edges, store, flags, t_last, nsamples);
 }
 
 }  // extern "C"

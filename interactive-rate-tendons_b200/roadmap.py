@@ -114,7 +114,7 @@ class VoxelCachedLazyPRM:
     def precomputeEdgeVoxelCache(self):
         lo, hi = self.shard(len(self.edges))
         e = self.edges[lo:hi]
-        info = self.edge_store.voxelize_edges(self.robot, self.space, self.states[e[:, 0]], self.states[e[:, 1]])
+        info = self.edge_store.voxelize_edges_indexed(self.robot, self.space, self.states, e)
         self.edge_flags = info["flags"]
         self.edge_info = info
         self._have_ecache = True

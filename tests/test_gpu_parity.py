@@ -460,3 +460,28 @@ def test_full_size_check_properties(irt, ctx, wl):
     assert not store.check(env).any()
     env.update(np.full(Nb ** 3, 2 ** 64 - 1, dtype=np.uint64))
     assert store.check(env).all()
+
+
+def test_edge_indexed_form_matches_per_edge_form(irt, ctx, orc, wl):
+    """edges given as (source, target) vertex indices share the endpoints' FK; results must be
+    identical to the per-edge (a, b) form and to the oracle"""
+    spec = wl.robot_b(0.003)
+    g = wl.workspace_grid(spec)
+    states = wl.sample_states(spec, 500, stream=54)
+    pairs = wl.knn_edges(spec, states, k=4)[:900]
+    rb = irt.Robot(ctx, spec)
+    grid = irt.make_grid(g["Ng"], g["lim"])
+    s1, s2 = irt.SetStore(ctx, grid), irt.SetStore(ctx, grid)
+    i1 = s1.voxelize_edges(rb, irt.make_space(), states[pairs[:, 0]], states[pairs[:, 1]])
+    i2 = s2.voxelize_edges_indexed(rb, irt.make_space(), states, pairs)
+    for k in ("flags", "t_last", "nsamples"):
+        assert np.array_equal(i1[k], i2[k]), k
+    assert _csr_flips(s1.export_csr(), s2.export_csr()) == 0
+    ostore, oinfo = orc.voxelize_edges_batch(orc.robot(spec), orc.grid(g["Ng"], g["lim"]), orc.space(),
+                                             states[pairs[:, 0]], states[pairs[:, 1]])
+    assert _csr_flips(s2.export_csr(), ostore.export()) == 0
+    with pytest.raises(irt.IrtError) as ei:
+        s2.voxelize_edges_indexed(rb, irt.make_space(), states, np.array([[0, 500]]))
+    assert ei.value.status == irt.IRT_ERR_OUT_OF_RANGE
+    s2.voxelize_edges_indexed(rb, irt.make_space(), states, np.zeros((0, 2), dtype=np.int64))
+    assert s2.num_sets == 0

@@ -11,13 +11,16 @@ grid = irt_b200.make_grid(g["Ng"], g["lim"])
 nv = int(sys.argv[1]) if len(sys.argv) > 1 else 100000
 st = wl.sample_states(spec, nv, stream=200)
 pairs = knn_edges_gpu(torch, st, spec, 10, torch.device("cuda"))
-a, b = st[pairs[:, 0]].copy(), st[pairs[:, 1]].copy()
 store = irt_b200.SetStore(ctx, grid)
 for rep in range(2):
     t0 = time.perf_counter()
-    info = store.voxelize_edges(rb, irt_b200.make_space(), a, b)
+    info = store.voxelize_edges_indexed(rb, irt_b200.make_space(), st, pairs)
     dt = time.perf_counter() - t0
-    print("edges %d: %.3f s, %.2f Medges/s, samples/edge %.2f, blocks/edge %.1f" % (len(a), dt, len(a) / dt / 1e6, info["nsamples"].mean(), store.num_blocks / len(a)), flush=True)
+    print("indexed edges %d: %.3f s, %.2f Medges/s, samples/edge %.2f, blocks/edge %.1f" % (len(pairs), dt, len(pairs) / dt / 1e6, info["nsamples"].mean(), store.num_blocks / len(pairs)), flush=True)
+if "--pairwise" in sys.argv:
+    a, b = st[pairs[:, 0]].copy(), st[pairs[:, 1]].copy()
+    t0 = time.perf_counter(); store.voxelize_edges(rb, irt_b200.make_space(), a, b); dt = time.perf_counter() - t0
+    print("pairwise edges %d: %.3f s" % (len(pairs), dt))
 vs = irt_b200.SetStore(ctx, grid)
 t0 = time.perf_counter(); vs.voxelize_vertices(rb, st); dt = time.perf_counter() - t0
 print("vertices %d: %.3f s" % (nv, dt))
