@@ -66,6 +66,7 @@ typedef enum irt_status {
 #define IRT_FLAG_PARTIAL 16u       /* edge: PartialVoxelization::is_fully_valid == false */
 #define IRT_FLAG_BAD_STATE 32u     /* retraction < 0 or NaN: outside the reference's state space */
 #define IRT_FLAG_CAPACITY 64u      /* per-item scratch capacity exceeded (result incomplete) */
+#define IRT_FLAG_ENV_COLLISION 128u /* until-invalid mode: the sample's own voxels hit the environment */
 
 typedef struct irt_ctx irt_ctx;
 typedef struct irt_robot irt_robot;
@@ -212,6 +213,15 @@ int irt_voxelize_shapes(irt_ctx *ctx, const double *p, const int32_t *npts, int 
 int irt_voxelize_edges(irt_ctx *ctx, const irt_robot *rb, const irt_space *space,
                        const double *a, const double *b, int state_size, int64_t n,
                        irt_setstore *store, uint32_t *flags, double *t_last, int32_t *nsamples);
+/* AbstractVoxelMotionValidator::voxelize_until_invalid (AbstractVoxelMotionValidator.h:109-127 ->
+ * VoxelBackboneMotionValidator::voxelize_until_invalid_impl, .cpp:83-91): like irt_voxelize_edges,
+ * but a sample is also invalid when its backbone voxels collide with `env`
+ * (is_valid_shape && !_vc->collides(shape)); the stored set is the swept volume up to the last
+ * valid t, which is what checkMotion(s1, s2, last_valid) reports. */
+int irt_voxelize_edges_until_invalid(irt_ctx *ctx, const irt_robot *rb, const irt_space *space,
+                                     const double *a, const double *b, int state_size, int64_t n,
+                                     const irt_env *env, irt_setstore *store, uint32_t *flags,
+                                     double *t_last, int32_t *nsamples);
 /* Same, for edges given as index pairs into one list of roadmap vertices (the planner's own
  * representation: boost::source(e) / boost::target(e), VoxelCachedLazyPRM.cpp:2888-2891).  The FK of
  * every vertex is computed once and shared by all incident edges.  pairs: int64[n_edges][2].

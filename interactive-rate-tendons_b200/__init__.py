@@ -32,6 +32,7 @@ FLAG_OUT_OF_DOMAIN = 8
 FLAG_PARTIAL = 16
 FLAG_BAD_STATE = 32
 FLAG_CAPACITY = 64
+FLAG_ENV_COLLISION = 128
 INVALID_MASK = FLAG_NONCONVERGED | FLAG_LENGTH_LIMIT | FLAG_SELF_COLLISION | FLAG_BAD_STATE
 
 IRT_OK, IRT_ERR_NO_DEVICE, IRT_ERR_INVALID_ARGUMENT, IRT_ERR_OUT_OF_RANGE = 0, 1, 2, 3
@@ -98,7 +99,7 @@ ABI_SYMBOLS = [
     "irt_setstore_create", "irt_setstore_destroy", "irt_setstore_num_sets",
     "irt_setstore_num_blocks", "irt_setstore_import", "irt_setstore_export",
     "irt_setstore_device_ptrs", "irt_morton_key", "irt_morton_decode",
-    "irt_voxelize_vertices", "irt_voxelize_shapes", "irt_voxelize_edges", "irt_voxelize_edges_indexed",
+    "irt_voxelize_vertices", "irt_voxelize_shapes", "irt_voxelize_edges", "irt_voxelize_edges_until_invalid", "irt_voxelize_edges_indexed",
     "irt_valid_segment_count",
     "irt_check_sets", "irt_check_sets_dev", "irt_check_sets_popcount",
     "irt_check_sets_algorithmic_bytes",
@@ -154,6 +155,7 @@ def lib():
         "irt_voxelize_vertices": (i32, [vp, vp, vp, i32, i64, vp, vp, vp]),
         "irt_voxelize_shapes": (i32, [vp, vp, vp, i32, i64, vp]),
         "irt_voxelize_edges": (i32, [vp, vp, C.POINTER(Space), vp, vp, i32, i64, vp, vp, vp, vp]),
+        "irt_voxelize_edges_until_invalid": (i32, [vp, vp, C.POINTER(Space), vp, vp, i32, i64, vp, vp, vp, vp, vp]),
         "irt_voxelize_edges_indexed": (i32, [vp, vp, C.POINTER(Space), vp, i32, i64, vp, i64, vp, vp, vp, vp]),
         "irt_valid_segment_count": (u32, [C.POINTER(RobotDesc), C.POINTER(Space), vp, vp]),
         "irt_check_sets": (i32, [vp, vp, vp, i64, i64, vp]),
@@ -448,6 +450,19 @@ class SetStore:
         nsamples = np.zeros(n, dtype=np.int32)
         self.ctx.check(self.ctx.L.irt_voxelize_edges(self.ctx.h, robot.h, C.byref(space), _ptr(a), _ptr(b),
                                                      S, n, self.h, _ptr(flags), _ptr(t_last), _ptr(nsamples)))
+        return dict(flags=flags, t_last=t_last, nsamples=nsamples)
+
+    def voxelize_edges_until_invalid(self, robot, space, a, b, env):
+        """voxelize_until_invalid: swept volume up to the first configuration that is invalid or
+        whose backbone hits `env`.  Returns dict(flags, t_last, nsamples)."""
+        a, b = _np(a, np.float64), _np(b, np.float64)
+        n, S = a.shape
+        flags = np.zeros(n, dtype=np.uint32)
+        t_last = np.zeros(n)
+        nsamples = np.zeros(n, dtype=np.int32)
+        self.ctx.check(self.ctx.L.irt_voxelize_edges_until_invalid(
+            self.ctx.h, robot.h, C.byref(space), _ptr(a), _ptr(b), S, n, env.h, self.h,
+            _ptr(flags), _ptr(t_last), _ptr(nsamples)))
         return dict(flags=flags, t_last=t_last, nsamples=nsamples)
 
     def voxelize_edges_indexed(self, robot, space, vertex_states, pairs):

@@ -55,7 +55,7 @@ constexpr int RS_MAXS = 128;          // samples of one set handled by the flat 
 constexpr int RS_WARP_BYTES = RS_HASH * 18 + 16 + RS_MAXS * 8;
 constexpr int RS_SMEM = RS_WARPS * RS_WARP_BYTES;
 constexpr uint32_t INVALID_MASK = IRT_FLAG_NONCONVERGED | IRT_FLAG_LENGTH_LIMIT |
-                                  IRT_FLAG_SELF_COLLISION | IRT_FLAG_BAD_STATE;
+                                  IRT_FLAG_SELF_COLLISION | IRT_FLAG_BAD_STATE | IRT_FLAG_ENV_COLLISION;
 
 struct D3 {
   double x, y, z;
@@ -123,6 +123,28 @@ __device__ __forceinline__ void set_cell(const WarpHash &h, BlockAcc &acc, int i
   acc.mask |= 1ull << ((ix & 3) * 16 + (iy & 3) * 4 + (iz & 3));
 }
 
+// cell sinks of the voxel traversal: HashSink builds a voxel set, EnvSink only asks whether any
+// traversed cell is occupied in the environment (AbstractVoxelValidityChecker::collides of a shape)
+struct HashSink {
+  const WarpHash &h;
+  BlockAcc acc;
+  __device__ __forceinline__ explicit HashSink(const WarpHash &hh) : h(hh) {}
+  __device__ __forceinline__ void cell(int ix, int iy, int iz) { set_cell(h, acc, ix, iy, iz); }
+  __device__ __forceinline__ void finish() { flush_block(h, acc); }
+};
+struct EnvSink {
+  const uint64_t *env;
+  const uint32_t *occ;
+  bool hit = false;
+  __device__ __forceinline__ EnvSink(const uint64_t *e, const uint32_t *o) : env(e), occ(o) {}
+  __device__ __forceinline__ void cell(int ix, int iy, int iz) {
+    const uint32_t key = morton_key((uint32_t)ix >> 2, (uint32_t)iy >> 2, (uint32_t)iz >> 2);
+    if ((occ[key >> 5] >> (key & 31)) & 1u)
+      if ((env[key] >> ((ix & 3) * 16 + (iy & 3) * 4 + (iz & 3))) & 1ull) hit = true;
+  }
+  __device__ __forceinline__ void finish() {}
+};
+
 // collision/collision_primitives.h:62-85, literal operation order
 __device__ bool segment_aabox_intersect(const D3 &A, const D3 &B, const D3 &C, const D3 &D) {
   const D3 AB = {B.x - A.x, B.y - A.y, B.z - A.z};
@@ -145,7 +167,8 @@ __device__ bool segment_aabox_intersect(const D3 &A, const D3 &B, const D3 &C, c
 
 // VoxelOctree::add_line -- collision/VoxelOctree.cpp:325-426, reproduced literally including the
 // "voxel index times metric cell size" initial error (:371-373) and the overshoot past B (:423-424).
-__device__ void add_line(const GridDev &g, const WarpHash &h, const D3 &a, const D3 &b) {
+template <typename Sink>
+__device__ void add_line(const GridDev &g, Sink &sink, const D3 &a, const D3 &b) {
   const D3 ll = {g.lo[0], g.lo[1], g.lo[2]}, ur = {g.hi[0], g.hi[1], g.hi[2]};
   // A segment whose endpoints both lie inside the grid box (by a safety margin of a ten-thousandth
   // of a cell) intersects it: the reference's separating-axis test cannot report otherwise, so it
@@ -162,10 +185,9 @@ __device__ void add_line(const GridDev &g, const WarpHash &h, const D3 &a, const
   const int N = g.Ng;
 #define IDX_IN(v) (0 <= (v) && (v) < N)
 #define VOX_IN(x, y, z) (IDX_IN(x) && IDX_IN(y) && IDX_IN(z))
-  BlockAcc acc;
   bool entered = VOX_IN(Axi, Ayi, Azi);
-  if (VOX_IN(Bxi, Byi, Bzi)) set_cell(h, acc, Bxi, Byi, Bzi);
-  if (entered) set_cell(h, acc, Axi, Ayi, Azi);
+  if (VOX_IN(Bxi, Byi, Bzi)) sink.cell(Bxi, Byi, Bzi);
+  if (entered) sink.cell(Axi, Ayi, Azi);
   D3 U = {B.x - A.x, B.y - A.y, B.z - A.z};
   {
     const double z = (U.x * U.x + U.y * U.y) + U.z * U.z;  // Eigen normalized()
@@ -202,9 +224,9 @@ __device__ void add_line(const GridDev &g, const WarpHash &h, const D3 &a, const
       tz += tz_delta;
     }
     if (!entered && VOX_IN(xi, yi, zi)) entered = true;
-    if (entered) set_cell(h, acc, xi, yi, zi);
+    if (entered) sink.cell(xi, yi, zi);
   }
-  flush_block(h, acc);
+  sink.finish();
 #undef IDX_IN
 #undef VOX_IN
 }
@@ -262,8 +284,10 @@ swept_voxel_raster_kernel(const GridDev g, const double *__restrict__ pts,
         total += P - 1;
       } else {  // very long sample lists: the remainder goes sample by sample
         const double *sp = pts + (int64_t)smp * cap_pts * 3;
-        for (int i = 1 + lane; i < P; i += 32)
-          add_line(g, h, rotate_pt(g, sp + 3 * (i - 1)), rotate_pt(g, sp + 3 * i));
+        for (int i = 1 + lane; i < P; i += 32) {
+          HashSink sink(h);
+          add_line(g, sink, rotate_pt(g, sp + 3 * (i - 1)), rotate_pt(g, sp + 3 * i));
+        }
       }
     }
     __syncwarp();
@@ -274,7 +298,8 @@ swept_voxel_raster_kernel(const GridDev g, const double *__restrict__ pts,
         if (k + step < nsm && lc[k + step] <= f) k += step;
       const int i = f - lc[k] + 1;  // segment (i-1, i) of sample ls[k]
       const double *sp = pts + (int64_t)ls[k] * cap_pts * 3;
-      add_line(g, h, rotate_pt(g, sp + 3 * (i - 1)), rotate_pt(g, sp + 3 * i));
+      HashSink sink(h);
+      add_line(g, sink, rotate_pt(g, sp + 3 * (i - 1)), rotate_pt(g, sp + 3 * i));
     }
     __syncwarp();
     const int cnt = (int)min(*h.count, (uint32_t)RS_HASH);
@@ -306,6 +331,24 @@ swept_voxel_raster_kernel(const GridDev g, const double *__restrict__ pts,
     if (lane == 0) { *h.count = 0u; *h.overflow = 0u; }
     __syncwarp();
   }
+}
+
+// voxelize_until_invalid: a sample is also invalid when its own backbone voxels hit the
+// environment (_vc->collides(shape), VoxelBackboneMotionValidator.cpp:83-91).  One warp per
+// sample; no set is built, the traversal just probes the environment grid.
+__global__ void sample_env_collision_kernel(const GridDev g, const double *__restrict__ pts,
+                                            const int32_t *__restrict__ npts, int cap_pts, int64_t n,
+                                            const uint64_t *__restrict__ env, const uint32_t *__restrict__ occ,
+                                            uint32_t *__restrict__ flags) {
+  const int lane = threadIdx.x & 31;
+  const int64_t smp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (smp >= n) return;
+  if (flags[smp] & INVALID_MASK) return;  // is_valid_shape short-circuits the collision check
+  const int P = npts[smp];
+  const double *sp = pts + smp * (int64_t)cap_pts * 3;
+  EnvSink sink(env, occ);
+  for (int i = 1 + lane; i < P; i += 32) add_line(g, sink, rotate_pt(g, sp + 3 * (i - 1)), rotate_pt(g, sp + 3 * i));
+  if (__any_sync(0xffffffffu, sink.hit) && lane == 0) flags[smp] |= IRT_FLAG_ENV_COLLISION;
 }
 
 // pack the slots into the CSR: one warp per set, coalesced copies
@@ -898,9 +941,12 @@ int irt_voxelize_shapes(irt_ctx *ctx, const double *p, const int32_t *npts, int 
 // a, b: per-edge endpoint states (host) -- or, indexed form: vstates[nv][S] + pairs[n][2]
 static int voxelize_edges_core(irt_ctx *ctx, const irt_robot *rb, const irt_space *space, const double *a,
                                const double *b, const double *vstates, int64_t nv, const int64_t *pairs,
-                               int state_size, int64_t n, irt_setstore *store, uint32_t *flags,
-                               double *t_last, int32_t *nsamples) {
+                               int state_size, int64_t n, const irt_env *env, irt_setstore *store,
+                               uint32_t *flags, double *t_last, int32_t *nsamples) {
   const bool indexed = pairs != nullptr;
+  if (env && store && env->grid.Ng != store->grid.Ng)
+    return irt_fail(ctx, IRT_ERR_INVALID_ARGUMENT, "voxel dimension mismatch (%d != %d)", env->grid.Ng,
+                    store->grid.Ng);
   if (!ctx || !rb || !space || !store || n < 0) return IRT_ERR_INVALID_ARGUMENT;
   if (!indexed && n > 0 && (!a || !b)) return IRT_ERR_INVALID_ARGUMENT;
   if (indexed && (nv < 0 || (nv > 0 && !vstates))) return IRT_ERR_INVALID_ARGUMENT;
@@ -1003,6 +1049,11 @@ static int voxelize_edges_core(irt_ctx *ctx, const irt_robot *rb, const irt_spac
       if (rc) return rc;
       rc = self_collision_launch(ctx, rb, o.p, o.npts, m, cap, o.flags, st);
       if (rc) return rc;
+      if (env) {
+        sample_env_collision_kernel<<<(unsigned)((m * 32 + T - 1) / T), T, 0, st>>>(
+            g, o.p, o.npts, cap, m, env->d_blocks, env->d_occ, o.flags);
+        IRT_LAUNCHED(ctx);
+      }
     }
     tr.point("vertex fk", nv);
   }
@@ -1043,6 +1094,11 @@ static int voxelize_edges_core(irt_ctx *ctx, const irt_robot *rb, const irt_spac
       if (r) return r;
       r = self_collision_launch(ctx, rb, o.p, o.npts, hi - lo, cap, o.flags, st);
       if (r) return r;
+      if (env) {
+        sample_env_collision_kernel<<<(unsigned)(((int64_t)(hi - lo) * 32 + T - 1) / T), T, 0, st>>>(
+            g, o.p, o.npts, cap, hi - lo, env->d_blocks, env->d_occ, o.flags);
+        IRT_LAUNCHED(ctx);
+      }
       edge_mark_kernel<<<(hi - lo + T - 1) / T, T, 0, st>>>(P, lo, hi);
       IRT_LAUNCHED(ctx);
       return IRT_OK;
@@ -1130,8 +1186,17 @@ extern "C" {
 int irt_voxelize_edges(irt_ctx *ctx, const irt_robot *rb, const irt_space *space, const double *a,
                        const double *b, int state_size, int64_t n, irt_setstore *store,
                        uint32_t *flags, double *t_last, int32_t *nsamples) {
-  return voxelize_edges_core(ctx, rb, space, a, b, nullptr, 0, nullptr, state_size, n, store, flags, t_last,
-                             nsamples);
+  return voxelize_edges_core(ctx, rb, space, a, b, nullptr, 0, nullptr, state_size, n, nullptr, store, flags,
+                             t_last, nsamples);
+}
+
+int irt_voxelize_edges_until_invalid(irt_ctx *ctx, const irt_robot *rb, const irt_space *space,
+                                     const double *a, const double *b, int state_size, int64_t n,
+                                     const irt_env *env, irt_setstore *store, uint32_t *flags,
+                                     double *t_last, int32_t *nsamples) {
+  if (!env) return IRT_ERR_INVALID_ARGUMENT;
+  return voxelize_edges_core(ctx, rb, space, a, b, nullptr, 0, nullptr, state_size, n, env, store, flags,
+                             t_last, nsamples);
 }
 
 int irt_voxelize_edges_indexed(irt_ctx *ctx, const irt_robot *rb, const irt_space *space,
@@ -1141,7 +1206,7 @@ int irt_voxelize_edges_indexed(irt_ctx *ctx, const irt_robot *rb, const irt_spac
   if (n_edges > 0 && !pairs) return IRT_ERR_INVALID_ARGUMENT;
   static const int64_t dummy[2] = {0, 0};
   return voxelize_edges_core(ctx, rb, space, nullptr, nullptr, vertex_states, n_vertices,
-                             pairs ? pairs : dummy, state_size, n_edges, store, flags, t_last, nsamples);
+                             pairs ? pairs : dummy, state_size, n_edges, nullptr, store, flags, t_last, nsamples);
 }
 
 }  // extern "C"

@@ -522,6 +522,33 @@ public:
     pv.voxels = collision::VoxelOctree::from_store(ctx, st, 0, voxels_);
     return pv;
   }
+  /// voxelize_until_invalid (AbstractVoxelMotionValidator.h:109-127): also stops at the first
+  /// configuration whose backbone voxels hit the obstacle voxels of this validator
+  PartialVoxelization voxelize_until_invalid(const std::vector<double> &a, const std::vector<double> &b) const {
+    const size_t S = robot_.state_size();
+    if (a.size() != S || b.size() != S) throw std::invalid_argument("start and end are different sizes");
+    irt_ctx *ctx = robot_.ctx();
+    irt_grid g = voxels_.grid(venv_.inv_rotation);
+    irt_setstore *st = nullptr;
+    irt::check(ctx, irt_setstore_create(ctx, &g, &st));
+    std::shared_ptr<irt_setstore> guard(st, [](irt_setstore *x) { irt_setstore_destroy(x); });
+    irt_env *env = nullptr;
+    irt::check(ctx, irt_env_create(ctx, &g, &env));
+    std::shared_ptr<irt_env> eg(env, [](irt_env *x) { irt_env_destroy(x); });
+    voxels_.upload_env(ctx, env);
+    uint32_t flags = 0;
+    double t_last = 0.0;
+    irt::check(ctx, irt_voxelize_edges_until_invalid(ctx, robot_.handle(), &space_, a.data(), b.data(), (int)S, 1,
+                                                     env, st, &flags, &t_last, nullptr));
+    if (flags & IRT_FLAG_OUT_OF_DOMAIN) throw std::domain_error("point is out of the voxel dimensions");
+    PartialVoxelization pv;
+    pv.is_fully_valid = !(flags & IRT_FLAG_PARTIAL);
+    pv.t = t_last;
+    pv.last_valid = interpolate(a, b, t_last);
+    pv.last_backbone = robot_.shape(pv.last_valid).p;
+    pv.voxels = collision::VoxelOctree::from_store(ctx, st, 0, voxels_);
+    return pv;
+  }
   bool collides(const collision::VoxelOctree &swept) const { return voxels_.collides(swept); }
   size_t num_voxelize_errors() const { return num_voxelize_errors_; }
   uint32_t valid_segment_count(const std::vector<double> &a, const std::vector<double> &b) const {

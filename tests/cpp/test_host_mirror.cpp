@@ -155,6 +155,15 @@ int main() {
     CHECK(validator.collides(pv.voxels) == (orc_octree_collides(oenv, ov) == 1));
     CHECK(validator.valid_segment_count(a, b) == orc_valid_segment_count(&orb, &osp, a.data(), b.data()));
     orc_octree_free(ov);
+    // voxelize_until_invalid against the obstacle
+    auto pu = validator.voxelize_until_invalid(a, b);
+    orc_octree *ou = orc_octree_new(&og);
+    orc_edge_out iu;
+    orc_voxelize_edge(&orb, &og, &osp, a.data(), b.data(), oenv, ou, &iu);
+    CHECK(pu.is_fully_valid == (iu.is_fully_valid != 0));
+    CHECK(pu.t == iu.t);
+    CHECK((int64_t)pu.voxels.ncells() == orc_octree_ncells(ou));
+    orc_octree_free(ou);
   }
 
   // ---- VoxelCachedLazyPRM batch entry points --------------------------------------------------

@@ -485,3 +485,36 @@ def test_edge_indexed_form_matches_per_edge_form(irt, ctx, orc, wl):
     assert ei.value.status == irt.IRT_ERR_OUT_OF_RANGE
     s2.voxelize_edges_indexed(rb, irt.make_space(), states, np.zeros((0, 2), dtype=np.int64))
     assert s2.num_sets == 0
+
+
+def test_edge_until_invalid_matches_oracle(irt, ctx, orc, wl):
+    """voxelize_until_invalid: bisection stops at the first sample whose backbone hits the
+    environment; PARTIAL flag, last valid t and the voxels of the valid prefix are bit-exact"""
+    spec = wl.robot_b(0.003)
+    g = wl.workspace_grid(spec)
+    Nb = g["Ng"] // 4
+    a, b = _edges(wl, spec, 150, 3, 55, 220)
+    env_blocks = wl.dense_to_morton_blocks(wl.lung_like_env_dense(spec, g))
+    grid = irt.make_grid(g["Ng"], g["lim"])
+    ogrid = orc.grid(g["Ng"], g["lim"])
+    oenv = _oracle_env(orc, wl, ogrid, env_blocks, Nb)
+    env = irt.Env(ctx, grid)
+    env.update(env_blocks)
+    rb = irt.Robot(ctx, spec)
+    store = irt.SetStore(ctx, grid)
+    info = store.voxelize_edges_until_invalid(rb, irt.make_space(), a, b, env)
+    got_off, got_keys, got_bits = store.export_csr()
+    orb = orc.robot(spec)
+    n_partial = 0
+    for i in range(len(a)):
+        tree, oi = orc.voxelize_edge(orb, ogrid, orc.space(), a[i], b[i], env=oenv)
+        assert bool(info["flags"][i] & irt.FLAG_PARTIAL) == (not oi["is_fully_valid"]), i
+        assert info["t_last"][i] == oi["t"], i
+        bxyz, bits = tree.export()
+        keys = [orc.morton_key(int(x), int(y), int(z), Nb) for x, y, z in bxyz]
+        lo, hi = int(got_off[i]), int(got_off[i + 1])
+        assert list(got_keys[lo:hi]) == keys and np.array_equal(got_bits[lo:hi], bits), i
+        n_partial += not oi["is_fully_valid"]
+    assert 20 < n_partial < len(a) - 20, "fixture must mix blocked and free motions (%d)" % n_partial
+    # the valid prefix never touches the environment
+    assert not store.check(env).any()
