@@ -518,3 +518,31 @@ def test_edge_until_invalid_matches_oracle(irt, ctx, orc, wl):
     assert 20 < n_partial < len(a) - 20, "fixture must mix blocked and free motions (%d)" % n_partial
     # the valid prefix never touches the environment
     assert not store.check(env).any()
+
+
+@pytest.mark.parametrize("Ng,dL,lim", [(64, 0.005, [-0.21, 0.21, -0.21, 0.21, -0.21, 0.21]),
+                                       (256, 0.0015, [-0.21, 0.21, -0.21, 0.21, -0.21, 0.21]),
+                                       (128, 0.003, [-0.25, 0.22, -0.21, 0.30, -0.05, 0.40])])
+def test_voxelisation_other_grids(irt, ctx, orc, wl, Ng, dL, lim):
+    """coarser / finer grids and non-cubic cells (dx != dy != dz), vertices and edges"""
+    spec = wl.robot_b(dL)
+    states = wl.sample_states(spec, 400, stream=56)
+    # include degenerate shapes: fully retracted (one point) and the single-point grid {s}
+    states[0, -1] = spec["L"]
+    states[1, -1] = spec["L"] - 0.2 * dL
+    rb = irt.Robot(ctx, spec)
+    grid = irt.make_grid(Ng, lim)
+    ogrid = orc.grid(Ng, lim)
+    vs = irt.SetStore(ctx, grid)
+    flags, _ = vs.voxelize_vertices(rb, states)
+    ostore, oflags = orc.voxelize_vertices_batch(orc.robot(spec), ogrid, states)
+    assert np.array_equal(flags, oflags)
+    assert _csr_flips(vs.export_csr(), ostore.export()) == 0
+    off = vs.export_csr()[0]
+    assert off[1] == off[0] and off[2] == off[1]  # one-point shapes voxelise to the empty set
+    pairs = wl.knn_edges(spec, states, k=3)[:300]
+    es = irt.SetStore(ctx, grid)
+    info = es.voxelize_edges_indexed(rb, irt.make_space(), states, pairs)
+    oes, oinfo = orc.voxelize_edges_batch(orc.robot(spec), ogrid, orc.space(), states[pairs[:, 0]], states[pairs[:, 1]])
+    assert np.array_equal(info["flags"], oinfo["flags"]) and np.array_equal(info["t_last"], oinfo["t_last"])
+    assert _csr_flips(es.export_csr(), oes.export()) == 0
