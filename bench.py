@@ -6,8 +6,8 @@
 
 A "step" is one pass of batched forward kinematics over config C2 of BASELINE.json
 (6-tendon helical robot with retraction, 1M configurations per GPU) with inputs resident in
-HBM.  The same run also measures the roadmap voxel check (K3) over a roadmap built with the
-real pipeline, the end-to-end FK rate through the host-pointer C ABI, and the CPU baseline
+HBM.  The same run also measures the roadmap voxel check (K3) over a config-C4-sized roadmap
+(1M valid vertices, exact k=10 nearest-neighbour edges, ~6M edges) built with the real pipeline, the end-to-end FK rate through the host-pointer C ABI, and the CPU baseline
 (the oracle restatement of the reference, timed on this box's host cores).
 Prints ONE JSON line on rank 0.
 """
@@ -177,7 +177,7 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--roadmap-vertices", type=int, default=100_000,
+    ap.add_argument("--roadmap-vertices", type=int, default=1_000_000,
                     help="vertices of the roadmap used for the K3 sweep (k=10 nearest-neighbour edges)")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--skip-roadmap", action="store_true")

@@ -306,9 +306,7 @@ class Robot:
                       t=((n, cap), np.float64), npts=((n,), np.int32), L=((n,), np.float64),
                       L_i=((n, N), np.float64), tip=((n, 3), np.float64), uv=((n, 12), np.float64),
                       flags=((n,), np.uint32), iters=((n,), np.int32), nsteps=((n,), np.int32))
-        want = set(want)
-        if "flags" in want:
-            want |= {"p", "npts"}
+        want = set(want)  # (flags alone is fine: the library keeps the points on the device)
         out = {k: np.zeros(*shapes[k]) for k in want}
         o = FkOutputs()
         for k, a in out.items():
