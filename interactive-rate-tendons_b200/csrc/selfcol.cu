@@ -73,9 +73,70 @@ __device__ bool capsules_collide(const P3 &a0, const P3 &a1, const P3 &b0, const
   return dot3(diff, diff) <= (rr * rr);
 }
 
+// Stage 1 -- conservative FP32 pair filter, one warp per shape.  Every capsule pair (a, b) that can
+// survive the reference's 3r arc-length rule (exact index bound from the longest segment:
+// acc[b] - acc[a+1] <= (b - a - 1) * maxlen) is tested with
+//     |mid_a - mid_b| <= 2r + len_a/2 + len_b/2        (a lower bound of the capsule distance)
+// in single precision with outward margins.  A shape with no such pair cannot self-collide; the
+// others (rare: the backbone has to curl back on itself) go to stage 2.  Rows a and R-1-a are
+// given to the same lane so that lanes carry equal work.
+constexpr int SC_FILTER_WARPS = 8;
+
+__global__ void __launch_bounds__(SC_FILTER_WARPS * 32)
+self_collision_filter_kernel(const double *__restrict__ p, const int32_t *__restrict__ npts, int64_t n,
+                             int cap_pts, double r, int32_t *__restrict__ cand, int32_t *__restrict__ n_cand) {
+  extern __shared__ float fsm[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float4 *seg = reinterpret_cast<float4 *>(fsm) + (size_t)warp * cap_pts;  // (mid.x, mid.y, mid.z, half length)
+  const float rr = (float)(2.0 * r) * 1.00001f + 1e-6f;
+
+  for (int64_t shape = (int64_t)blockIdx.x * SC_FILTER_WARPS + warp; shape < n;
+       shape += (int64_t)gridDim.x * SC_FILTER_WARPS) {
+    const int N = npts[shape];
+    __syncwarp();
+    if (N <= 3) continue;  // collision.cpp:14 and the loop bounds a < N-3
+    const double *src = p + shape * (int64_t)cap_pts * 3;
+    const int ncap = N - 1;
+    float maxhl = 0.0f;
+    for (int i = lane; i < ncap; i += 32) {
+      const double ax = src[3 * i], ay = src[3 * i + 1], az = src[3 * i + 2];
+      const double bx = src[3 * i + 3], by = src[3 * i + 4], bz = src[3 * i + 5];
+      const float dx = (float)(bx - ax), dy = (float)(by - ay), dz = (float)(bz - az);
+      const float hl = 0.5f * sqrtf(dx * dx + dy * dy + dz * dz) * 1.00001f + 1e-9f;
+      seg[i] = make_float4((float)(0.5 * (ax + bx)), (float)(0.5 * (ay + by)), (float)(0.5 * (az + bz)), hl);
+      maxhl = fmaxf(maxhl, hl);
+    }
+    for (int o = 16; o > 0; o >>= 1) maxhl = fmaxf(maxhl, __shfl_xor_sync(0xffffffffu, maxhl, o));
+    __syncwarp();
+    // smallest index gap b - a - 1 that can reach 3r of arc length (maxhl over-estimates len/2)
+    const float safe = (float)(3.0 * r) * 0.9999f;
+    const int min_gap = (maxhl > 0.0f) ? (int)fminf(1e6f, floorf(safe / (2.0f * maxhl))) : 1000000;
+    const int first = 1 + (min_gap < 1 ? 1 : min_gap);  // b >= a + first (and the reference's b >= a + 2)
+    const int R = ncap - first;                         // rows a = 0 .. R-1 have at least one b
+    bool found = false;
+    for (int k = lane; k < (R + 1) / 2; k += 32) {
+      for (int half = 0; half < 2; half++) {
+        const int a = half ? (R - 1 - k) : k;
+        if (half && a == k) break;
+        if (a >= N - 3) continue;
+        const float4 sa = seg[a];
+        for (int b = a + first; b < ncap; b++) {
+          const float4 sb = seg[b];
+          const float dx = sa.x - sb.x, dy = sa.y - sb.y, dz = sa.z - sb.z;
+          const float reach = rr + sa.w + sb.w;
+          if (dx * dx + dy * dy + dz * dz <= reach * reach) found = true;
+        }
+      }
+    }
+    if (__any_sync(0xffffffffu, found) && lane == 0) cand[atomicAdd(n_cand, 1)] = (int32_t)shape;
+  }
+}
+
+// Stage 2 -- exact test, one warp per candidate shape (all shapes when cand == nullptr).
 __global__ void __launch_bounds__(SC_WARPS * 32)
 self_collision_kernel(const double *__restrict__ p, const int32_t *__restrict__ npts, int64_t n,
-                      int cap_pts, double r, uint32_t *__restrict__ flags) {
+                      int cap_pts, double r, uint32_t *__restrict__ flags,
+                      const int32_t *__restrict__ cand, const int32_t *__restrict__ n_cand) {
   extern __shared__ double sm[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   // per warp: xyz[cap*3], acc[cap], chunk centre xyz + radius [4 * nchunk_max]
@@ -85,8 +146,9 @@ self_collision_kernel(const double *__restrict__ p, const int32_t *__restrict__ 
   const double dist_to_consider = 3.0 * r;
   const double rr = r + r;
 
-  for (int64_t shape = (int64_t)blockIdx.x * SC_WARPS + warp; shape < n;
-       shape += (int64_t)gridDim.x * SC_WARPS) {
+  const int64_t n_work = cand ? (int64_t)*n_cand : n;
+  for (int64_t w = (int64_t)blockIdx.x * SC_WARPS + warp; w < n_work; w += (int64_t)gridDim.x * SC_WARPS) {
+    const int64_t shape = cand ? (int64_t)cand[w] : w;
     const int N = npts[shape];
     __syncwarp();
     if (N <= 2) continue;  // collision.cpp:14
@@ -188,16 +250,38 @@ int self_collision_launch(irt_ctx *ctx, const irt_robot *rb, const double *d_p,
                           const int32_t *d_npts, int64_t n, int cap_pts, uint32_t *d_flags,
                           cudaStream_t st) {
   if (n <= 0) return IRT_OK;
+  if (n > 0x7fffffffLL) return irt_fail(ctx, IRT_ERR_INVALID_ARGUMENT, "batch too large");
+  if (cap_pts > IRT_CAP_PTS_MAX) return irt_fail(ctx, IRT_ERR_CAPACITY, "cap_pts=%d too large", cap_pts);
   const int nchunk_max = (cap_pts + SC_CHUNK - 1) / SC_CHUNK;
   size_t smem = (size_t)SC_WARPS * ((size_t)cap_pts * 4 + (size_t)nchunk_max * 4) * sizeof(double);
   if (smem > 200 * 1024) return irt_fail(ctx, IRT_ERR_CAPACITY, "cap_pts=%d too large", cap_pts);
   IRT_CUDA(ctx, cudaFuncSetAttribute(self_collision_kernel,
                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  // candidate list lives behind the bucket permutation area of the context scratch
+  const size_t perm_bytes = (size_t)n * 8 + 4096 + 256;
+  char *scr = (char *)ctx_scratch(ctx, perm_bytes + (size_t)n * 4 + 256);
+  if (!scr) return irt_fail(ctx, IRT_ERR_CUDA, "scratch alloc failed");
+  int32_t *d_ncand = (int32_t *)(scr + perm_bytes);
+  int32_t *d_cand = d_ncand + 64;
+  IRT_CUDA(ctx, cudaMemsetAsync(d_ncand, 0, 4, st));
+  {
+    int64_t fb = (n + SC_FILTER_WARPS - 1) / SC_FILTER_WARPS;
+    const int64_t fmax_blocks = (int64_t)ctx->sm_count * 16;
+    if (fb > fmax_blocks) fb = fmax_blocks;
+    const size_t fsmem = (size_t)SC_FILTER_WARPS * cap_pts * sizeof(float4);
+    if (fsmem > 48 * 1024)
+      IRT_CUDA(ctx, cudaFuncSetAttribute(self_collision_filter_kernel,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem));
+    self_collision_filter_kernel<<<(unsigned)fb, SC_FILTER_WARPS * 32, fsmem, st>>>(d_p, d_npts, n, cap_pts,
+                                                                                  rb->dev.r, d_cand, d_ncand);
+  }
+  IRT_LAUNCHED(ctx);
+  // stage 2 runs over however many candidates stage 1 found (count stays on the device)
   int64_t blocks = (n + SC_WARPS - 1) / SC_WARPS;
-  const int64_t max_blocks = (int64_t)ctx->sm_count * 16;
+  const int64_t max_blocks = (int64_t)ctx->sm_count * 4;
   if (blocks > max_blocks) blocks = max_blocks;
-  self_collision_kernel<<<(unsigned)blocks, SC_WARPS * 32, smem, st>>>(d_p, d_npts, n, cap_pts,
-                                                                      rb->dev.r, d_flags);
+  self_collision_kernel<<<(unsigned)blocks, SC_WARPS * 32, smem, st>>>(d_p, d_npts, n, cap_pts, rb->dev.r,
+                                                                      d_flags, d_cand, d_ncand);
   IRT_LAUNCHED(ctx);
   IRT_CUDA(ctx, cudaGetLastError());
   return IRT_OK;
