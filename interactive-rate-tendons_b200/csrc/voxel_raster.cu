@@ -49,11 +49,14 @@ struct Trace {
 };
 
 constexpr int RS_WARPS = 4;
-constexpr int RS_HASH = 1024;        // hash entries per warp (power of two)
+constexpr int RS_HLOG_SMALL = 8;     // main pass: 256 hash entries per warp (a set rarely exceeds ~150 blocks)
+constexpr int RS_HLOG_BIG = 12;      // fallback pass for the sets that overflow it: 4096 entries, 1 warp per CTA
+constexpr int RS_SLOT = 1 << RS_HLOG_SMALL;   // slot capacity of the main pass
+constexpr int RS_BIGSLOT = 1 << RS_HLOG_BIG;  // slot capacity of the fallback pass
+constexpr int RS_MAX_OVF = 2048;     // fallback slots per raster launch
 constexpr uint32_t RS_EMPTY = 0xffffffffu;
 constexpr int RS_MAXS = 128;          // samples of one set handled by the flat segment walk
-constexpr int RS_WARP_BYTES = RS_HASH * 18 + 16 + RS_MAXS * 8;
-constexpr int RS_SMEM = RS_WARPS * RS_WARP_BYTES;
+constexpr int rs_warp_bytes(int hlog) { return (1 << hlog) * 18 + 16 + RS_MAXS * 8; }
 constexpr uint32_t INVALID_MASK = IRT_FLAG_NONCONVERGED | IRT_FLAG_LENGTH_LIMIT |
                                   IRT_FLAG_SELF_COLLISION | IRT_FLAG_BAD_STATE | IRT_FLAG_ENV_COLLISION;
 
@@ -82,23 +85,30 @@ __device__ __forceinline__ D3 rotate_pt(const GridDev &g, const double *p) {
 }
 
 struct WarpHash {
-  uint32_t *keys;   // [RS_HASH]
-  unsigned long long *bits;  // [RS_HASH]
-  uint16_t *list;   // [RS_HASH] slots in insertion order (dense list of the occupied entries)
+  uint32_t *keys;   // [H]
+  unsigned long long *bits;  // [H]
+  uint16_t *list;   // [H] slots in insertion order (dense list of the occupied entries)
   uint32_t *count;  // number of occupied entries
   uint32_t *overflow;
+  int hlog;         // H = 1 << hlog
 };
 
 __device__ __forceinline__ void hash_insert(const WarpHash &h, uint32_t key, unsigned long long mask) {
-  uint32_t slot = (key * 2654435761u) >> (32 - 10);  // RS_HASH == 1 << 10
-  for (int probe = 0; probe < RS_HASH; probe++) {
+  const uint32_t H = 1u << h.hlog;
+  if (*h.overflow) return;  // this set will be redone with the big table
+  uint32_t slot = (key * 2654435761u) >> (32 - h.hlog);
+  for (uint32_t probe = 0; probe < H; probe++) {
     const uint32_t old = atomicCAS(&h.keys[slot], RS_EMPTY, key);
-    if (old == RS_EMPTY) h.list[atomicAdd(h.count, 1u)] = (uint16_t)slot;
+    if (old == RS_EMPTY) {
+      const uint32_t idx = atomicAdd(h.count, 1u);
+      h.list[idx] = (uint16_t)slot;
+      if (idx >= (H >> 2) * 3) *h.overflow = 1u;  // keep the load factor below 3/4
+    }
     if (old == RS_EMPTY || old == key) {
       atomicOr(&h.bits[slot], mask);
       return;
     }
-    slot = (slot + 1) & (RS_HASH - 1);
+    slot = (slot + 1) & (H - 1);
   }
   *h.overflow = 1u;
 }
@@ -233,38 +243,47 @@ __device__ void add_line(const GridDev &g, Sink &sink, const D3 &a, const D3 &b)
 
 // One warp per set.  A set is a linked list of FK samples (set_head / sample_next); a sample is
 // included iff t < tlimit[set] (edges) -- vertices have a single sample and no limit.
-// Output: the set's occupied leaf blocks, key-sorted, in its slot of capacity RS_HASH
-// (slot_keys / slot_bits), counts[set], optional t_last / nsamples.  A gather kernel then packs
-// the slots into the CSR at the scanned offsets.  Per-set cost is proportional to the number of
-// occupied blocks: occupied hash slots are kept in an append list, so neither the compaction nor
-// the clean-up ever scans the whole table.
-__global__ void __launch_bounds__(RS_WARPS * 32)
+// Output: the set's occupied leaf blocks, key-sorted, in its slot (slot_keys / slot_bits),
+// counts[set], optional t_last / nsamples.  A gather kernel then packs the slots into the CSR at
+// the scanned offsets.  Per-set cost is proportional to the number of occupied blocks: occupied
+// hash slots are kept in an append list, so neither the sort nor the clean-up scans the table.
+// HLOG = RS_HLOG_SMALL: main pass over all sets; a set that outgrows the small table is appended
+// to ovf_list and left for the HLOG = RS_HLOG_BIG pass, which works through that list (count on
+// the device) with one warp per CTA and writes into the big slots.
+template <int HLOG, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32)
 swept_voxel_raster_kernel(const GridDev g, const double *__restrict__ pts,
                           const int32_t *__restrict__ npts, int cap_pts,
                           const int32_t *__restrict__ set_head, const int32_t *__restrict__ sample_next,
                           const double *__restrict__ sample_t, const double *__restrict__ tlimit,
                           int64_t nsets, uint32_t *__restrict__ counts, double *__restrict__ t_last,
                           int32_t *__restrict__ nsamples, uint32_t *__restrict__ slot_keys,
-                          uint64_t *__restrict__ slot_bits, uint32_t *__restrict__ set_flags) {
+                          uint64_t *__restrict__ slot_bits, uint32_t *__restrict__ set_flags,
+                          int32_t *__restrict__ ovf_list, int32_t *__restrict__ ovf_count,
+                          int32_t *__restrict__ ovf_slot) {
+  constexpr int H = 1 << HLOG;
+  constexpr bool BIG = (HLOG == RS_HLOG_BIG);
   extern __shared__ unsigned long long rs_smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  // per warp: bits u64[H] | keys u32[H] | dense keys u32[H] | list u16[H] | count, overflow
-  unsigned char *wbase = reinterpret_cast<unsigned char *>(rs_smem) + (size_t)warp * RS_WARP_BYTES;
+  // per warp: bits u64[H] | keys u32[H] | dense keys u32[H] | list u16[H] | count, overflow | sample list
+  unsigned char *wbase = reinterpret_cast<unsigned char *>(rs_smem) + (size_t)warp * rs_warp_bytes(HLOG);
   WarpHash h;
+  h.hlog = HLOG;
   h.bits = reinterpret_cast<unsigned long long *>(wbase);
-  h.keys = reinterpret_cast<uint32_t *>(wbase + RS_HASH * 8);
-  uint32_t *dk = reinterpret_cast<uint32_t *>(wbase + RS_HASH * 12);
-  h.list = reinterpret_cast<uint16_t *>(wbase + RS_HASH * 16);
-  h.count = reinterpret_cast<uint32_t *>(wbase + RS_HASH * 18);
+  h.keys = reinterpret_cast<uint32_t *>(wbase + H * 8);
+  uint32_t *dk = reinterpret_cast<uint32_t *>(wbase + H * 12);
+  h.list = reinterpret_cast<uint16_t *>(wbase + H * 16);
+  h.count = reinterpret_cast<uint32_t *>(wbase + H * 18);
   h.overflow = h.count + 1;
-  int32_t *ls = reinterpret_cast<int32_t *>(wbase + RS_HASH * 18 + 16);  // sample ids
-  int32_t *lc = ls + RS_MAXS;                                            // first flat segment index
-  for (int i = lane; i < RS_HASH; i += 32) { h.keys[i] = RS_EMPTY; h.bits[i] = 0ull; }
+  int32_t *ls = reinterpret_cast<int32_t *>(wbase + H * 18 + 16);  // sample ids
+  int32_t *lc = ls + RS_MAXS;                                      // first flat segment index
+  for (int i = lane; i < H; i += 32) { h.keys[i] = RS_EMPTY; h.bits[i] = 0ull; }
   if (lane == 0) { *h.count = 0u; *h.overflow = 0u; }
   __syncwarp();
 
-  for (int64_t set = (int64_t)blockIdx.x * RS_WARPS + warp; set < nsets;
-       set += (int64_t)gridDim.x * RS_WARPS) {
+  const int64_t n_work = BIG ? (int64_t)min(*ovf_count, RS_MAX_OVF) : nsets;
+  for (int64_t w = (int64_t)blockIdx.x * WARPS + warp; w < n_work; w += (int64_t)gridDim.x * WARPS) {
+    const int64_t set = BIG ? (int64_t)ovf_list[w] : w;
     const double lim = tlimit ? tlimit[set] : 0.0;
     double tl = 0.0;
     int ns = 0, nsm = 0, total = 0;
@@ -302,27 +321,44 @@ swept_voxel_raster_kernel(const GridDev g, const double *__restrict__ pts,
       add_line(g, sink, rotate_pt(g, sp + 3 * (i - 1)), rotate_pt(g, sp + 3 * i));
     }
     __syncwarp();
-    const int cnt = (int)min(*h.count, (uint32_t)RS_HASH);
-    for (int i = lane; i < cnt; i += 32) dk[i] = h.keys[h.list[i]];
-    __syncwarp();
-    // rank sort by key == the reference's visit_leaves order
-    uint32_t *sk = slot_keys + set * RS_HASH;
-    uint64_t *sb = slot_bits + set * RS_HASH;
-    for (int i = lane; i < cnt; i += 32) {
-      const uint32_t k = dk[i];
-      int rank = 0;
-      for (int j = 0; j < cnt; j++) rank += (dk[j] < k);
-      sk[rank] = k;
-      sb[rank] = h.bits[h.list[i]];
+    const bool over = *h.overflow != 0u;
+    const int used = (int)min(*h.count, (uint32_t)H);
+    int cnt = used;
+    int64_t slot_id = set;
+    if (!BIG && over) {
+      // defer to the big-table pass (or give up with a flag when its slots are exhausted)
+      cnt = 0;
+      if (lane == 0) {
+        const int32_t idx = atomicAdd(ovf_count, 1);
+        if (idx < RS_MAX_OVF) ovf_list[idx] = (int32_t)set;
+        else if (set_flags) set_flags[set] |= IRT_FLAG_CAPACITY;
+      }
+    } else {
+      if (BIG) {
+        slot_id = w;
+        if (over && lane == 0 && set_flags) set_flags[set] |= IRT_FLAG_CAPACITY;
+      }
+      for (int i = lane; i < cnt; i += 32) dk[i] = h.keys[h.list[i]];
+      __syncwarp();
+      // rank sort by key == the reference's visit_leaves order
+      uint32_t *sk = slot_keys + slot_id * H;
+      uint64_t *sb = slot_bits + slot_id * H;
+      for (int i = lane; i < cnt; i += 32) {
+        const uint32_t k = dk[i];
+        int rank = 0;
+        for (int j = 0; j < cnt; j++) rank += (dk[j] < k);
+        sk[rank] = k;
+        sb[rank] = h.bits[h.list[i]];
+      }
     }
     if (lane == 0) {
       counts[set] = (uint32_t)cnt;
+      if (BIG) ovf_slot[set] = (int32_t)w + 1;
       if (t_last) t_last[set] = tl;
       if (nsamples) nsamples[set] = ns;
-      if (*h.overflow && set_flags) set_flags[set] |= IRT_FLAG_CAPACITY;
     }
     __syncwarp();
-    for (int i = lane; i < cnt; i += 32) {  // clean only what was used
+    for (int i = lane; i < used; i += 32) {  // clean only what was used
       const int sl = h.list[i];
       h.keys[sl] = RS_EMPTY;
       h.bits[sl] = 0ull;
@@ -353,6 +389,8 @@ __global__ void sample_env_collision_kernel(const GridDev g, const double *__res
 
 // pack the slots into the CSR: one warp per set, coalesced copies
 __global__ void raster_gather_kernel(const uint32_t *__restrict__ slot_keys, const uint64_t *__restrict__ slot_bits,
+                                     const uint32_t *__restrict__ big_keys, const uint64_t *__restrict__ big_bits,
+                                     const int32_t *__restrict__ ovf_slot,
                                      const uint32_t *__restrict__ counts, const uint64_t *__restrict__ offsets,
                                      int64_t nsets, uint32_t *__restrict__ out_keys, uint64_t *__restrict__ out_bits) {
   const int lane = threadIdx.x & 31;
@@ -360,9 +398,12 @@ __global__ void raster_gather_kernel(const uint32_t *__restrict__ slot_keys, con
   if (set >= nsets) return;
   const uint32_t n = counts[set];
   const uint64_t base = offsets[set];
+  const int32_t ov = ovf_slot[set];
+  const uint32_t *sk = ov ? big_keys + (int64_t)(ov - 1) * RS_BIGSLOT : slot_keys + set * RS_SLOT;
+  const uint64_t *sb = ov ? big_bits + (int64_t)(ov - 1) * RS_BIGSLOT : slot_bits + set * RS_SLOT;
   for (uint32_t i = lane; i < n; i += 32) {
-    out_keys[base + i] = slot_keys[set * RS_HASH + i];
-    out_bits[base + i] = slot_bits[set * RS_HASH + i];
+    out_keys[base + i] = sk[i];
+    out_bits[base + i] = sb[i];
   }
 }
 
@@ -734,18 +775,21 @@ int arena_layout(irt_ctx *ctx, const F &layout) {
   return IRT_OK;
 }
 
-constexpr int64_t RS_CHUNK_SETS = 65536;  // sets rasterised per launch (slot scratch = 12 KiB per set)
+constexpr int64_t RS_CHUNK_SETS = 262144;  // sets rasterised per launch (slot scratch = 3 KiB per set)
 
 struct RasterScratch {
-  uint32_t *slot_keys = nullptr;
-  uint64_t *slot_bits = nullptr;
+  uint32_t *slot_keys = nullptr, *big_keys = nullptr;
+  uint64_t *slot_bits = nullptr, *big_bits = nullptr;
   uint32_t *counts = nullptr;
   uint64_t *scan_tmp = nullptr;
+  int32_t *ovf_list = nullptr, *ovf_count = nullptr, *ovf_slot = nullptr;
   template <typename A>
   bool layout(A &a, int64_t chunk) {
     const int64_t ntiles = (chunk + SCAN_TILE - 1) / SCAN_TILE;
-    return a.alloc(&slot_keys, (size_t)chunk * RS_HASH) && a.alloc(&slot_bits, (size_t)chunk * RS_HASH) &&
-           a.alloc(&counts, (size_t)chunk) && a.alloc(&scan_tmp, (size_t)ntiles + 2);
+    return a.alloc(&slot_keys, (size_t)chunk * RS_SLOT) && a.alloc(&slot_bits, (size_t)chunk * RS_SLOT) &&
+           a.alloc(&big_keys, (size_t)RS_MAX_OVF * RS_BIGSLOT) && a.alloc(&big_bits, (size_t)RS_MAX_OVF * RS_BIGSLOT) &&
+           a.alloc(&counts, (size_t)chunk) && a.alloc(&scan_tmp, (size_t)ntiles + 2) &&
+           a.alloc(&ovf_list, (size_t)RS_MAX_OVF) && a.alloc(&ovf_count, 64) && a.alloc(&ovf_slot, (size_t)chunk);
   }
 };
 
@@ -756,18 +800,28 @@ int raster_append(irt_ctx *ctx, const GridDev &g, const double *d_pts, const int
                   const double *d_tlimit, int64_t nsets, double *d_tlast, int32_t *d_nsamples,
                   uint32_t *d_setflags, RasterScratch &rs, irt_setstore *store, int64_t set_base,
                   uint64_t leaf_base, uint64_t *leaf_total_out, cudaStream_t st) {
-  IRT_CUDA(ctx, cudaFuncSetAttribute(swept_voxel_raster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     RS_SMEM));
+  auto k_small = swept_voxel_raster_kernel<RS_HLOG_SMALL, RS_WARPS>;
+  auto k_big = swept_voxel_raster_kernel<RS_HLOG_BIG, 1>;
+  const int smem_small = RS_WARPS * rs_warp_bytes(RS_HLOG_SMALL), smem_big = rs_warp_bytes(RS_HLOG_BIG);
+  IRT_CUDA(ctx, cudaFuncSetAttribute(k_big, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_big));
   uint64_t running = leaf_base;
   for (int64_t c0 = 0; c0 < nsets; c0 += RS_CHUNK_SETS) {
     const int64_t m = (nsets - c0 < RS_CHUNK_SETS) ? (nsets - c0) : RS_CHUNK_SETS;
     int64_t blocks = (m + RS_WARPS - 1) / RS_WARPS;
-    const int64_t max_blocks = (int64_t)ctx->sm_count * 8;
+    const int64_t max_blocks = (int64_t)ctx->sm_count * 16;
     if (blocks > max_blocks) blocks = max_blocks;
-    swept_voxel_raster_kernel<<<(unsigned)blocks, RS_WARPS * 32, RS_SMEM, st>>>(
+    IRT_CUDA(ctx, cudaMemsetAsync(rs.ovf_count, 0, 4, st));
+    IRT_CUDA(ctx, cudaMemsetAsync(rs.ovf_slot, 0, (size_t)m * 4, st));
+    k_small<<<(unsigned)blocks, RS_WARPS * 32, smem_small, st>>>(
         g, d_pts, d_npts, cap_pts, d_heads + c0, d_next, d_st, d_tlimit ? d_tlimit + c0 : nullptr, m, rs.counts,
         d_tlast ? d_tlast + c0 : nullptr, d_nsamples ? d_nsamples + c0 : nullptr, rs.slot_keys, rs.slot_bits,
-        d_setflags ? d_setflags + c0 : nullptr);
+        d_setflags ? d_setflags + c0 : nullptr, rs.ovf_list, rs.ovf_count, rs.ovf_slot);
+    IRT_LAUNCHED(ctx);
+    // sets that outgrew the small table (normally none): big-table pass over the device-side list
+    k_big<<<(unsigned)ctx->sm_count, 32, smem_big, st>>>(
+        g, d_pts, d_npts, cap_pts, d_heads + c0, d_next, d_st, d_tlimit ? d_tlimit + c0 : nullptr, m, rs.counts,
+        d_tlast ? d_tlast + c0 : nullptr, d_nsamples ? d_nsamples + c0 : nullptr, rs.big_keys, rs.big_bits,
+        d_setflags ? d_setflags + c0 : nullptr, rs.ovf_list, rs.ovf_count, rs.ovf_slot);
     IRT_LAUNCHED(ctx);
     IRT_CUDA(ctx, cudaGetLastError());
     uint64_t total = 0;
@@ -777,7 +831,8 @@ int raster_append(irt_ctx *ctx, const GridDev &g, const double *d_pts, const int
     if (rc) return rc;
     const int T = 256;
     raster_gather_kernel<<<(unsigned)((m * 32 + T - 1) / T), T, 0, st>>>(
-        rs.slot_keys, rs.slot_bits, rs.counts, store->d_offsets + set_base + c0, m, store->d_keys, store->d_bits);
+        rs.slot_keys, rs.slot_bits, rs.big_keys, rs.big_bits, rs.ovf_slot, rs.counts,
+        store->d_offsets + set_base + c0, m, store->d_keys, store->d_bits);
     IRT_LAUNCHED(ctx);
     IRT_CUDA(ctx, cudaGetLastError());
     running += total;

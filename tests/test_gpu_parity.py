@@ -546,3 +546,22 @@ def test_voxelisation_other_grids(irt, ctx, orc, wl, Ng, dL, lim):
     oes, oinfo = orc.voxelize_edges_batch(orc.robot(spec), ogrid, orc.space(), states[pairs[:, 0]], states[pairs[:, 1]])
     assert np.array_equal(info["flags"], oinfo["flags"]) and np.array_equal(info["t_last"], oinfo["t_last"])
     assert _csr_flips(es.export_csr(), oes.export()) == 0
+
+
+def test_edge_large_swept_volumes_use_big_table(irt, ctx, orc, wl):
+    """long edges at a fine grid: hundreds of leaf blocks per set, more than the rasteriser's
+    small per-warp hash holds -> the big-table fallback pass must give the same bit-exact sets"""
+    spec = wl.robot_a(0.0015)
+    g = wl.workspace_grid(spec, Ng=256)
+    st = wl.sample_states(spec, 60, stream=57) * 0.6   # moderate tensions: mostly valid shapes
+    a, b = st[:30], st[30:]
+    rb = irt.Robot(ctx, spec)
+    grid = irt.make_grid(g["Ng"], g["lim"])
+    store = irt.SetStore(ctx, grid)
+    info = store.voxelize_edges(rb, irt.make_space(), a, b)
+    ostore, oinfo = orc.voxelize_edges_batch(orc.robot(spec), orc.grid(g["Ng"], g["lim"]), orc.space(), a, b)
+    assert np.array_equal(info["flags"], oinfo["flags"])
+    assert not (info["flags"] & irt.FLAG_CAPACITY).any()
+    off = ostore.export()[0].astype(np.int64)
+    assert np.diff(off).max() > 192, "fixture must exceed the small hash (max %d blocks)" % np.diff(off).max()
+    assert _csr_flips(store.export_csr(), ostore.export()) == 0
