@@ -385,7 +385,11 @@ def main():
                         "edge_voxel_cache": t_evox,
                         "edges_per_s_K1K2": (hi - lo) / t_evox if t_evox > 0 else None},
             "roofline": {"bound": "hbm", "kernel": "voxel_and_popc_kernel", "achieved": ach3, "peak": hbm_peak,
-                         "unit": "GB/s", "frac": ach3 / hbm_peak, "traffic": prof.get("k3_dram_bytes_per_launch"),
+                         "unit": "GB/s", "frac": ach3 / hbm_peak,
+                         "traffic": (prof.get("k3_dram_bytes_per_launch") or
+                                     (int(prof["k3_dram_bytes_over_algorithmic"] * alg_bytes)
+                                      if prof.get("k3_dram_bytes_over_algorithmic") else None)),
+                         "traffic_source": prof.get("k3_source"),
                          "peak_source": hbm_src, "algorithmic_bytes": alg_bytes,
                          "note": "duration includes the verdict memset and (N>1) the NCCL all_gather"},
         }

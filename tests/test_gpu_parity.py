@@ -565,3 +565,17 @@ def test_edge_large_swept_volumes_use_big_table(irt, ctx, orc, wl):
     off = ostore.export()[0].astype(np.int64)
     assert np.diff(off).max() > 192, "fixture must exceed the small hash (max %d blocks)" % np.diff(off).max()
     assert _csr_flips(store.export_csr(), ostore.export()) == 0
+
+
+def test_config_c1_full(irt, ctx, orc, wl):
+    """BASELINE.json configs[0] in full: default 4-tendon straight-routed robot, FK of 10k random
+    tension configurations + vertex voxelisation at 128^3, against the CPU path"""
+    spec = wl.robot_a(0.003)
+    states = wl.sample_states(spec, 10_000, stream=1)
+    rb, out, ref = _fk_compare(irt, ctx, orc, spec, states, want_all=True)
+    g = wl.workspace_grid(spec)
+    store = irt.SetStore(ctx, irt.make_grid(g["Ng"], g["lim"]))
+    flags, _ = store.voxelize_vertices(rb, states)
+    ostore, oflags = orc.voxelize_vertices_batch(orc.robot(spec), orc.grid(g["Ng"], g["lim"]), states)
+    assert np.array_equal(flags, oflags)
+    assert _csr_flips(store.export_csr(), ostore.export()) == 0

@@ -18,6 +18,25 @@ if which == "fk":
     for _ in range(3):
         rb.shape_batch_dev(st, n, outs)
         ctx.synchronize()
+elif which == "k3real":
+    # K3 over a roadmap store built by the real pipeline (bench.py's edge_check at 300k vertices)
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    from bench import knn_edges_gpu
+    spec = wl.robot_b(0.003)
+    rb = irt_b200.Robot(ctx, spec)
+    g = wl.workspace_grid(spec)
+    grid = irt_b200.make_grid(g["Ng"], g["lim"])
+    st = wl.sample_states(spec, 300000, stream=200)
+    pairs = knn_edges_gpu(torch, st, spec, 10, torch.device("cuda"))
+    store = irt_b200.SetStore(ctx, grid)
+    store.voxelize_edges_indexed(rb, irt_b200.make_space(), st, pairs)
+    env = irt_b200.Env(ctx, grid)
+    env.update(wl.dense_to_morton_blocks(wl.lung_like_env_dense(spec, g)))
+    words = torch.zeros((len(pairs) + 31) // 32, dtype=torch.int32, device="cuda")
+    for _ in range(3):
+        store.check_dev(env, words); ctx.synchronize()
+    print("k3real sets", store.num_sets, "leaves", store.num_blocks, "alg bytes", store.algorithmic_bytes(),
+          "collide frac", irt_b200.unpack_verdicts(words.cpu().numpy().view(np.uint32), len(pairs)).mean())
 else:
     rng = np.random.default_rng(8)
     Ng, Nb = 128, 32
