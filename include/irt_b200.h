@@ -14,6 +14,10 @@
  *     "_dev" entry points take DEVICE pointers (cudaMalloc'ed or torch tensors' data_ptr())
  *     and a cudaStream_t passed as void* (NULL = the context's own stream); they are
  *     asynchronous with respect to the host.
+ *   - threading: a context owns one stream and grow-only device scratch; calls on the SAME context
+ *     must be serialised by the caller (the reference calls its validators from many OpenMP
+ *     threads, one item each -- here one call carries the whole batch).  Different contexts,
+ *     robots, stores and environments can be used from different host threads concurrently.
  *   - there is NO CPU fallback: without a CUDA device irt_ctx_create fails with
  *     IRT_ERR_NO_DEVICE and nothing else can be called.
  *   - per-item problems (non-convergence, limits, ...) are NOT errors: they are reported in a

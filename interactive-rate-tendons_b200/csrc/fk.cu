@@ -718,9 +718,14 @@ int fk_launch(irt_ctx *ctx, const irt_robot *rb, const double *d_states, int64_t
     case 4: return launch_nt<4>(ctx, rb, d_states, n, cap_pts, o, d_perm, st);
     case 5: return launch_nt<5>(ctx, rb, d_states, n, cap_pts, o, d_perm, st);
     case 6: return launch_nt<6>(ctx, rb, d_states, n, cap_pts, o, d_perm, st);
+    case 7: return launch_nt<7>(ctx, rb, d_states, n, cap_pts, o, d_perm, st);
     case 8: return launch_nt<8>(ctx, rb, d_states, n, cap_pts, o, d_perm, st);
+    case 9: return launch_nt<9>(ctx, rb, d_states, n, cap_pts, o, d_perm, st);
+    case 10: return launch_nt<10>(ctx, rb, d_states, n, cap_pts, o, d_perm, st);
+    case 11: return launch_nt<11>(ctx, rb, d_states, n, cap_pts, o, d_perm, st);
+    case 12: return launch_nt<12>(ctx, rb, d_states, n, cap_pts, o, d_perm, st);
     default:
-      return irt_fail(ctx, IRT_ERR_UNSUPPORTED,
-                      "no fk kernel instantiated for %d tendons (have 1-6, 8)", d.n_tendons);
+      return irt_fail(ctx, IRT_ERR_UNSUPPORTED, "no fk kernel for %d tendons (1..%d supported)",
+                      d.n_tendons, IRT_MAX_TENDONS);
   }
 }

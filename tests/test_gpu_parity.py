@@ -72,9 +72,9 @@ def test_fk_full_tendon_result(irt, ctx, orc, wl):
 
 
 def test_fk_other_tendon_counts(irt, ctx, orc, wl):
-    """1, 2, 3, 5 and 8 tendons, mixed straight / helical / quadratic routing"""
+    """1, 2, 3, 5, 7, 8 and 12 tendons, mixed straight / helical / quadratic routing"""
     base = wl.robot_b(0.005)
-    for n_t in (1, 2, 3, 5, 8):
+    for n_t in (1, 2, 3, 5, 7, 8, 12):
         spec = dict(base)
         spec["C"] = [[0.4 * k, (-1) ** k * 9.0, 20.0 * (k % 2)] for k in range(n_t)]
         spec["D"] = [[0.008 + 0.0005 * k, 0.01 * (k % 3)] for k in range(n_t)]
