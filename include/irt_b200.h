@@ -174,6 +174,22 @@ int irt_env_update_dev(irt_ctx *ctx, irt_env *env, const uint64_t *d_blocks, voi
 int irt_env_update_sparse(irt_ctx *ctx, irt_env *env, const uint8_t *bxyz,
                           const uint64_t *bits, int64_t nblocks);
 int64_t irt_env_nblocks(irt_ctx *ctx, const irt_env *env); /* VoxelOctree::nblocks */
+/* environment preparation on the device, in place (the steps apps apply to the obstacle tree
+ * before planning).  Synchronous; bit-exact with the reference's trees.
+ *   irt_env_dilate          VoxelOctree::dilate_6neighbor(num) (collision/VoxelOctree.cpp:757-787)
+ *                           or, use_diagonal != 0, dilate_27neighbor(num) (:789-825, including
+ *                           its neighbour list as written: (x+1,y+1,z+1) twice, no (x-1,y+1,z+1))
+ *   irt_env_dilate_sphere   VoxelOctree::dilate_sphere(r) (:949-951) =
+ *                           dilate_6neighbor(round(r / min(dx,dy,dz)))
+ *   irt_env_remove_interior VoxelOctree::remove_interior_6neighbor (:533-600) or, keep_diagonal
+ *                           != 0, remove_interior_27neighbor (:602-689, the default of
+ *                           VoxelOctree::remove_interior, VoxelOctree.h:165); cells outside the
+ *                           grid count as occupied
+ *   irt_env_download        dense host copy blocks[Nb^3] indexed by Morton key */
+int irt_env_dilate(irt_ctx *ctx, irt_env *env, int num, int use_diagonal);
+int irt_env_dilate_sphere(irt_ctx *ctx, irt_env *env, double r);
+int irt_env_remove_interior(irt_ctx *ctx, irt_env *env, int keep_diagonal);
+int irt_env_download(irt_ctx *ctx, const irt_env *env, uint64_t *blocks);
 
 /* ---- set store: replaces vertexVoxelsProperty_/edgeVoxelsProperty_
  * (std::shared_ptr<VoxelOctree> per vertex/edge, VoxelCachedLazyPRM.h:141,165-179) ------- */

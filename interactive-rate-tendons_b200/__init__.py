@@ -96,6 +96,7 @@ ABI_SYMBOLS = [
     "irt_fk_batch", "irt_fk_batch_dev", "irt_home_lengths_batch",
     "irt_env_create", "irt_env_destroy", "irt_env_update", "irt_env_update_dev",
     "irt_env_update_sparse", "irt_env_nblocks",
+    "irt_env_dilate", "irt_env_dilate_sphere", "irt_env_remove_interior", "irt_env_download",
     "irt_setstore_create", "irt_setstore_destroy", "irt_setstore_num_sets",
     "irt_setstore_num_blocks", "irt_setstore_import", "irt_setstore_export",
     "irt_setstore_device_ptrs", "irt_morton_key", "irt_morton_decode",
@@ -143,6 +144,10 @@ def lib():
         "irt_env_update_dev": (i32, [vp, vp, vp, vp]),
         "irt_env_update_sparse": (i32, [vp, vp, vp, vp, i64]),
         "irt_env_nblocks": (i64, [vp, vp]),
+        "irt_env_dilate": (i32, [vp, vp, i32, i32]),
+        "irt_env_dilate_sphere": (i32, [vp, vp, C.c_double]),
+        "irt_env_remove_interior": (i32, [vp, vp, i32]),
+        "irt_env_download": (i32, [vp, vp, vp]),
         "irt_setstore_create": (i32, [vp, C.POINTER(Grid), C.POINTER(vp)]),
         "irt_setstore_destroy": (None, [vp]),
         "irt_setstore_num_sets": (i64, [vp]),
@@ -378,6 +383,24 @@ class Env:
 
     def nblocks(self):
         return int(self.ctx.L.irt_env_nblocks(self.ctx.h, self.h))
+
+    def dilate(self, num=1, use_diagonal=False):
+        """VoxelOctree::dilate_6neighbor / dilate_27neighbor, in place on the device."""
+        self.ctx.check(self.ctx.L.irt_env_dilate(self.ctx.h, self.h, int(num), int(bool(use_diagonal))))
+
+    def dilate_sphere(self, r):
+        """VoxelOctree::dilate_sphere(r)."""
+        self.ctx.check(self.ctx.L.irt_env_dilate_sphere(self.ctx.h, self.h, float(r)))
+
+    def remove_interior(self, keep_diagonal=True):
+        """VoxelOctree::remove_interior(keep_diagonal)."""
+        self.ctx.check(self.ctx.L.irt_env_remove_interior(self.ctx.h, self.h, int(bool(keep_diagonal))))
+
+    def download(self):
+        """Dense host copy: uint64[Nb^3] indexed by Morton key."""
+        out = np.zeros(self.Nb ** 3, np.uint64)
+        self.ctx.check(self.ctx.L.irt_env_download(self.ctx.h, self.h, _ptr(out)))
+        return out
 
 
 class SetStore:

@@ -112,6 +112,7 @@ int setstore_grow_blocks(irt_ctx *ctx, irt_setstore *s, int64_t need_blocks, int
 #define IRT_LAUNCHED(ctx) ((ctx)->launches.fetch_add(1, std::memory_order_relaxed))
 
 // internal cross-file entry points
+int env_rebuild_occ(irt_ctx *ctx, irt_env *env, cudaStream_t st);
 int setstore_reserve(irt_ctx *ctx, irt_setstore *s, int64_t n_sets, int64_t n_blocks);
 int setstore_finalize(irt_ctx *ctx, irt_setstore *s, int64_t n_sets, int64_t n_blocks,
                       cudaStream_t st);

@@ -271,7 +271,8 @@ void irt_env_destroy(irt_env *env) {
   delete env;
 }
 
-static int env_rebuild_occ(irt_ctx *ctx, irt_env *env, cudaStream_t st) {
+}  // extern "C"
+int env_rebuild_occ(irt_ctx *ctx, irt_env *env, cudaStream_t st) {
   const int64_t nwords = (env->n_blocks_total + 31) / 32;
   const int T = 256;
   env_build_occ_kernel<<<(unsigned)((nwords + T - 1) / T), T, 0, st>>>(env->d_blocks,
@@ -280,6 +281,7 @@ static int env_rebuild_occ(irt_ctx *ctx, irt_env *env, cudaStream_t st) {
   IRT_CUDA(ctx, cudaGetLastError());
   return IRT_OK;
 }
+extern "C" {
 
 int irt_env_update_dev(irt_ctx *ctx, irt_env *env, const uint64_t *d_blocks, void *stream) {
   if (!ctx || !env || !d_blocks) return IRT_ERR_INVALID_ARGUMENT;

@@ -382,7 +382,32 @@ public:
     return word & 1u;
   }
 
+  /// environment preparation (collision/VoxelOctree.cpp:533-952; VoxelOctree.h:155-201), on the GPU:
+  /// upload, morph in place on the device grid, read the dense grid back
+  void dilate_6neighbor(int num = 1) { on_device([&](irt_ctx *c, irt_env *e) { return irt_env_dilate(c, e, num, 0); }); }
+  void dilate_27neighbor(int num = 1) { on_device([&](irt_ctx *c, irt_env *e) { return irt_env_dilate(c, e, num, 1); }); }
+  void dilate(int num = 1, bool use_diagonal = false) { use_diagonal ? dilate_27neighbor(num) : dilate_6neighbor(num); }
+  void dilate_sphere(double r) { on_device([&](irt_ctx *c, irt_env *e) { return irt_env_dilate_sphere(c, e, r); }); }
+  void remove_interior_6neighbor() { on_device([&](irt_ctx *c, irt_env *e) { return irt_env_remove_interior(c, e, 0); }); }
+  void remove_interior_27neighbor() { on_device([&](irt_ctx *c, irt_env *e) { return irt_env_remove_interior(c, e, 1); }); }
+  void remove_interior(bool keep_diagonal = true) { keep_diagonal ? remove_interior_27neighbor() : remove_interior_6neighbor(); }
+
   // ---- helpers used by the validators ------------------------------------------------------
+  template <class F> void on_device(F &&op) {
+    auto ctx = irt::Context::global();
+    irt_grid g = grid();
+    irt_env *env = nullptr;
+    irt::check(ctx->get(), irt_env_create(ctx->get(), &g, &env));
+    std::shared_ptr<irt_env> eg(env, [](irt_env *x) { irt_env_destroy(x); });
+    upload_env(ctx->get(), env);
+    irt::check(ctx->get(), op(ctx->get(), env));
+    const size_t Nb = N_ / 4;
+    std::vector<uint64_t> dense(Nb * Nb * Nb);
+    irt::check(ctx->get(), irt_env_download(ctx->get(), env, dense.data()));
+    blocks_.clear();
+    for (size_t k = 0; k < dense.size(); k++)
+      if (dense[k]) blocks_[(uint32_t)k] = dense[k];
+  }
   void upload_env(irt_ctx *ctx, irt_env *env) const {
     std::vector<uint8_t> xyz(3 * blocks_.size() + 3);
     std::vector<uint64_t> bits(blocks_.size() + 1);

@@ -123,6 +123,10 @@ class Oracle:
         L.orc_octree_export.argtypes = [C.c_void_p, C.c_int64, C.POINTER(C.c_uint8), C.POINTER(C.c_uint64)]
         L.orc_octree_add_sphere.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.c_double]
         L.orc_octree_add_capsule.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_double), C.c_double]
+        L.orc_octree_dilate_6neighbor.argtypes = [C.c_void_p, C.c_int]
+        L.orc_octree_dilate_27neighbor.argtypes = [C.c_void_p, C.c_int]
+        L.orc_octree_dilate_sphere.argtypes = [C.c_void_p, C.c_double]
+        L.orc_octree_remove_interior.argtypes = [C.c_void_p, C.c_int]
         L.orc_find_cell.restype = C.c_int
         L.orc_valid_segment_count.restype = C.c_uint32
         L.orc_voxelize_shape.argtypes = [C.POINTER(OrcGrid), C.POINTER(C.c_double), C.c_int, C.c_void_p]
@@ -401,6 +405,15 @@ class Octree:
 
     def add_voxels(self, other):
         self.orc.lib.orc_octree_add_voxels(self.h, other.h)
+
+    def dilate(self, num=1, use_diagonal=False):
+        (self.orc.lib.orc_octree_dilate_27neighbor if use_diagonal else self.orc.lib.orc_octree_dilate_6neighbor)(self.h, num)
+
+    def dilate_sphere(self, r):
+        self.orc.lib.orc_octree_dilate_sphere(self.h, r)
+
+    def remove_interior(self, keep_diagonal=True):
+        self.orc.lib.orc_octree_remove_interior(self.h, int(keep_diagonal))
 
     def collides(self, other):
         return int(self.orc.lib.orc_octree_collides(self.h, other.h))

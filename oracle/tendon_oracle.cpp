@@ -1050,6 +1050,129 @@ void orc_octree_add_capsule(orc_octree *t, const double *pa, const double *pb, d
   });
 }
 
+// ---- environment preparation ----
+// dilate_one_impl / dilate_6neighbor / dilate_27neighbor / dilate_sphere --
+// collision/VoxelOctree.cpp:693-952, restated literally: depth-limited DFS inside the 3x3x3 block
+// neighbourhood (12^3 cells), at most four dilation steps per pass over a snapshot of the tree.
+}  // extern "C"
+namespace {
+typedef void (*NeighborFn)(int x, int y, int z, int out[27][3], int *count);
+void neighbors6(int x, int y, int z, int out[27][3], int *count) {
+  const int d[6][3] = {{-1, 0, 0}, {1, 0, 0}, {0, -1, 0}, {0, 1, 0}, {0, 0, -1}, {0, 0, 1}};
+  for (int i = 0; i < 6; i++) { out[i][0] = x + d[i][0]; out[i][1] = y + d[i][1]; out[i][2] = z + d[i][2]; }
+  *count = 6;
+}
+void neighbors27(int x, int y, int z, int out[27][3], int *count) {
+  // the reference's list (VoxelOctree.cpp:790-818) names (x+1,y+1,z+1) twice and never
+  // (x-1,y+1,z+1): reproduced as written
+  const int d[27][3] = {
+      {0, 0, 0},  {-1, 0, 0},  {1, 0, 0},  {0, -1, 0},  {-1, -1, 0},  {1, -1, 0},  {0, 1, 0},  {-1, 1, 0},  {1, 1, 0},
+      {0, 0, -1}, {-1, 0, -1}, {1, 0, -1}, {0, -1, -1}, {-1, -1, -1}, {1, -1, -1}, {0, 1, -1}, {-1, 1, -1}, {1, 1, -1},
+      {0, 0, 1},  {-1, 0, 1},  {1, 0, 1},  {0, -1, 1},  {-1, -1, 1},  {1, -1, 1},  {0, 1, 1},  {1, 1, 1},   {1, 1, 1}};
+  for (int i = 0; i < 27; i++) { out[i][0] = x + d[i][0]; out[i][1] = y + d[i][1]; out[i][2] = z + d[i][2]; }
+  *count = 27;
+}
+struct DepthSet {
+  uint8_t depths[12][12][12];
+  uint64_t voxels[3][3][3];
+  bool in(int x, int y, int z, int d) const { return d == 0 || d <= depths[x][y][z]; }
+  bool add(int x, int y, int z, int d) {
+    if (!in(x, y, z, d)) {
+      depths[x][y][z] = (uint8_t)d;
+      voxels[x / 4][y / 4][z / 4] |= bitmask(x % 4, y % 4, z % 4);
+      return true;
+    }
+    return false;
+  }
+};
+void dfs_visit(DepthSet &vs, NeighborFn nb, int x, int y, int z, int d) {
+  if (!vs.add(x, y, z, d)) return;
+  int out[27][3], cnt = 0;
+  nb(x, y, z, out, &cnt);
+  for (int i = 0; i < cnt; i++) dfs_visit(vs, nb, out[i][0], out[i][1], out[i][2], d - 1);
+}
+void dilate_one_impl(orc_octree *t, NeighborFn nb, int num) {
+  if (num <= 0) return;
+  const int Nb = t->Ng / 4;
+  for (; num > 0; num -= 4) {
+    OrcNode *copy = node_copy(t->root);
+    node_visit_leaves(copy, Nb, 0, 0, 0, [&](int bx, int by, int bz, uint64_t old_b) {
+      const int n = std::min(num, 4);
+      DepthSet vs;
+      std::memset(&vs, 0, sizeof(vs));
+      for (int x = 0; x < 4; ++x)
+        for (int y = 0; y < 4; ++y)
+          for (int z = 0; z < 4; ++z)
+            if (old_b & bitmask(x, y, z)) dfs_visit(vs, nb, x + 4, y + 4, z + 4, n + 1);
+      for (int nx = 0; nx < 3; ++nx) {
+        const int bxi = bx + nx - 1;
+        if (bxi < 0 || bxi >= Nb) continue;
+        for (int ny = 0; ny < 3; ++ny) {
+          const int byi = by + ny - 1;
+          if (byi < 0 || byi >= Nb) continue;
+          for (int nz = 0; nz < 3; ++nz) {
+            const int bzi = bz + nz - 1;
+            if (bzi < 0 || bzi >= Nb) continue;
+            if (vs.voxels[nx][ny][nz]) node_union_block(t->root, Nb, bxi, byi, bzi, vs.voxels[nx][ny][nz]);
+          }
+        }
+      }
+    });
+    node_free(copy);
+  }
+}
+// remove_interior_6neighbor / _27neighbor -- collision/VoxelOctree.cpp:533-689
+void remove_interior(orc_octree *t, bool diagonal) {
+  const int Nb = t->Ng / 4;
+  OrcNode *copy = node_copy(t->root);
+  const uint64_t full = ~uint64_t(0);
+  node_visit_leaves(copy, Nb, 0, 0, 0, [&](int bx, int by, int bz, uint64_t old_b) {
+    uint64_t nbh[3][3][3];
+    for (int i = 0; i < 3; ++i)
+      for (int j = 0; j < 3; ++j)
+        for (int k = 0; k < 3; ++k) {
+          const int x = bx - 1 + i, y = by - 1 + j, z = bz - 1 + k;
+          if (x < 0 || Nb - 1 < x || y < 0 || Nb - 1 < y || z < 0 || Nb - 1 < z) nbh[i][j][k] = full;
+          else if (i == 1 && j == 1 && k == 1) nbh[i][j][k] = old_b;
+          else nbh[i][j][k] = node_block(copy, Nb, x, y, z);
+        }
+    auto neighbor = [&](int ix, int iy, int iz) -> bool {
+      int nx = 1, ny = 1, nz = 1;
+      if (ix == -1) { ix = 3; nx = 0; } else if (ix == 4) { ix = 0; nx = 2; }
+      if (iy == -1) { iy = 3; ny = 0; } else if (iy == 4) { iy = 0; ny = 2; }
+      if (iz == -1) { iz = 3; nz = 0; } else if (iz == 4) { iz = 0; nz = 2; }
+      return (nbh[nx][ny][nz] & bitmask(ix, iy, iz)) != 0;
+    };
+    uint64_t new_b = old_b;
+    for (int ix = 0; ix < 4; ix++)
+      for (int iy = 0; iy < 4; iy++)
+        for (int iz = 0; iz < 4; iz++) {
+          bool interior = true;
+          if (diagonal) {
+            for (int i = -1; i <= 1 && interior; ++i)
+              for (int j = -1; j <= 1 && interior; ++j)
+                for (int k = -1; k <= 1 && interior; ++k)
+                  if (!neighbor(ix + i, iy + j, iz + k)) interior = false;
+          } else {
+            interior = neighbor(ix, iy, iz) && neighbor(ix - 1, iy, iz) && neighbor(ix + 1, iy, iz) &&
+                       neighbor(ix, iy - 1, iz) && neighbor(ix, iy + 1, iz) && neighbor(ix, iy, iz - 1) &&
+                       neighbor(ix, iy, iz + 1);
+          }
+          if (interior) new_b &= ~bitmask(ix, iy, iz);
+        }
+    node_set_block(t->root, Nb, bx, by, bz, new_b);
+  });
+  node_free(copy);
+}
+}  // namespace
+extern "C" {
+void orc_octree_dilate_6neighbor(orc_octree *t, int num) { dilate_one_impl(t, neighbors6, num); }
+void orc_octree_dilate_27neighbor(orc_octree *t, int num) { dilate_one_impl(t, neighbors27, num); }
+void orc_octree_dilate_sphere(orc_octree *t, double r) {  // VoxelOctree.cpp:949-951 ("attempt #3")
+  dilate_one_impl(t, neighbors6, int(std::round(r / std::min(t->dx, std::min(t->dy, t->dz)))));
+}
+void orc_octree_remove_interior(orc_octree *t, int keep_diagonal) { remove_interior(t, keep_diagonal != 0); }
+
 // ---- OMPL-side restatement ----
 // Problem.cpp:101-163: tension RealVector (weight 1), rotation SO2, retraction RealVector.
 // OMPL 1.5 (documented behaviour): StateSpace::validSegmentCount =

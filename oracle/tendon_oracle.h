@@ -129,6 +129,12 @@ int64_t orc_octree_export(const orc_octree *t, int64_t cap, uint8_t *bxyz, uint6
 /* find_cell (VoxelOctree.cpp:309-317): returns 0, or 1 for domain_error */
 int orc_find_cell(const orc_grid *g, const double *p, int64_t *cell);
 void orc_octree_add_sphere(orc_octree *t, const double *c, double r);
+/* environment preparation: collision/VoxelOctree.cpp:533-689 (remove_interior: keep_diagonal != 0
+ * is the 27-neighbour variant) and :693-952 (dilate) */
+void orc_octree_dilate_6neighbor(orc_octree *t, int num);
+void orc_octree_dilate_27neighbor(orc_octree *t, int num);
+void orc_octree_dilate_sphere(orc_octree *t, double r);
+void orc_octree_remove_interior(orc_octree *t, int keep_diagonal);
 void orc_octree_add_capsule(orc_octree *t, const double *a, const double *b, double r);
 
 /* OMPL-side restatement (Problem.cpp:101-163, VoxelBackboneMotionValidator.cpp:55-66) */

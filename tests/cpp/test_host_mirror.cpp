@@ -108,6 +108,28 @@ int main() {
     for (int64_t i = 0; i < nb; i++) env_vox.set_block(xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2], bits[i]);
     CHECK((int64_t)env_vox.nblocks() == nb && (int64_t)env_vox.ncells() == orc_octree_ncells(oenv));
   }
+  {  // environment preparation on the device vs the oracle's tree (VoxelOctree.cpp:533-952)
+    auto same = [&](const collision::VoxelOctree &v, const orc_octree *o) {
+      std::vector<uint8_t> xyz(3 * 65536);
+      std::vector<uint64_t> bits(65536);
+      int64_t nb = orc_octree_export(o, 65536, xyz.data(), bits.data());
+      if ((int64_t)v.nblocks() != nb) return false;
+      for (int64_t i = 0; i < nb; i++)
+        if (v.block(xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2]) != bits[i]) return false;
+      return true;
+    };
+    collision::VoxelOctree v = env_vox;
+    orc_octree *o = orc_octree_copy(oenv);
+    v.dilate_sphere(0.015); orc_octree_dilate_sphere(o, 0.015);
+    CHECK(same(v, o) && v.ncells() > env_vox.ncells());
+    v.remove_interior(); orc_octree_remove_interior(o, 1);
+    CHECK(same(v, o));
+    v.dilate(2, true); orc_octree_dilate_27neighbor(o, 2);
+    CHECK(same(v, o));
+    v.remove_interior(false); orc_octree_remove_interior(o, 0);
+    CHECK(same(v, o));
+    orc_octree_free(o);
+  }
   try { collision::VoxelOctree bad(100); CHECK(false); } catch (const std::invalid_argument &) {}
   try { collision::VoxelOctree(64).collides(env_vox); CHECK(false); } catch (const std::invalid_argument &) {}
 

@@ -579,3 +579,78 @@ def test_config_c1_full(irt, ctx, orc, wl):
     ostore, oflags = orc.voxelize_vertices_batch(orc.robot(spec), orc.grid(g["Ng"], g["lim"]), states)
     assert np.array_equal(flags, oflags)
     assert _csr_flips(store.export_csr(), ostore.export()) == 0
+
+
+# ---------------------------------------------------------------------------------------------
+# environment preparation on the device (irt_env_dilate / dilate_sphere / remove_interior)
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.gpu
+def test_env_preparation_bit_exact(irt, ctx, orc, wl):
+    spec = wl.robot_b(0.003)
+    g = wl.workspace_grid(spec)
+    Nb = g["Ng"] // 4
+    grid = irt.make_grid(g["Ng"], g["lim"])
+    ogrid = orc.grid(g["Ng"], g["lim"])
+    env_blocks = wl.dense_to_morton_blocks(wl.lung_like_env_dense(spec, g))
+    # scatter single cells on faces, edges and corners of the grid and of leaf blocks
+    rng = np.random.default_rng(5)
+    for bx, by, bz in [(0, 0, 0), (Nb - 1, Nb - 1, Nb - 1), (0, Nb - 1, 3), (Nb - 1, 0, 0), (7, 0, Nb - 1)]:
+        env_blocks[wl.morton_key(np.array([bx]), np.array([by]), np.array([bz]), Nb)[0]] |= np.uint64(
+            (1 << 0) | (1 << 63) | (1 << int(rng.integers(0, 64))))
+    oenv0 = _oracle_env(orc, wl, ogrid, env_blocks, Nb)
+    env = irt.Env(ctx, grid)
+    cases = [("dilate", (1, False)), ("dilate", (2, False)), ("dilate", (5, False)), ("dilate", (0, False)),
+             ("dilate", (1, True)), ("dilate", (3, True)), ("dilate_sphere", (2.6 * oenv0_d(g),)),
+             ("remove_interior", (False,)), ("remove_interior", (True,))]
+    for name, args in cases:
+        env.update(env_blocks)
+        getattr(env, name)(*args)
+        o = oenv0.copy()
+        getattr(o, name)(*args)
+        got, want = env.download(), o.dense_morton()
+        flips = int(np.count_nonzero(got != want))
+        assert flips == 0, (name, args, flips)
+        assert env.nblocks() == o.nblocks()
+    # the pipeline apps run on an obstacle tree before planning, chained on the device
+    env.update(env_blocks)
+    env.dilate_sphere(spec["r"])
+    env.remove_interior()
+    o = oenv0.copy(); o.dilate_sphere(spec["r"]); o.remove_interior(True)
+    assert np.array_equal(env.download(), o.dense_morton())
+    # the prepared environment drives K3 like an uploaded one (occupancy bitmap was rebuilt)
+    states = wl.sample_states(spec, 2000, stream=91)
+    store = irt.SetStore(ctx, grid)
+    store.voxelize_vertices(irt.Robot(ctx, spec), states)
+    env2 = irt.Env(ctx, grid)
+    env2.update(o.dense_morton())
+    assert np.array_equal(store.check(env), store.check(env2))
+
+
+def oenv0_d(g):
+    lim, Ng = g["lim"], g["Ng"]
+    return min(lim[1] - lim[0], lim[3] - lim[2], lim[5] - lim[4]) / Ng
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("Ng", [4, 16, 64])
+def test_env_preparation_small_grids(irt, ctx, orc, wl, Ng):
+    lim = [0, 1, -1, 1, 0, 0.5]
+    Nb = Ng // 4
+    grid, ogrid = irt.make_grid(Ng, lim), orc.grid(Ng, lim)
+    rng = np.random.default_rng(Ng)
+    blocks = np.zeros(Nb ** 3, np.uint64)
+    pick = rng.integers(0, Nb ** 3, max(1, Nb ** 3 // 6))
+    blocks[pick] = rng.integers(1, 2 ** 63, len(pick), dtype=np.uint64) & rng.integers(1, 2 ** 63, len(pick), dtype=np.uint64)
+    oenv0 = _oracle_env(orc, wl, ogrid, blocks, Nb)
+    env = irt.Env(ctx, grid)
+    for name, args in [("dilate", (1, False)), ("dilate", (4, False)), ("dilate", (2, True)),
+                       ("remove_interior", (False,)), ("remove_interior", (True,))]:
+        env.update(blocks)
+        getattr(env, name)(*args)
+        o = oenv0.copy()
+        getattr(o, name)(*args)
+        assert np.array_equal(env.download(), o.dense_morton()), (name, args)
+    # all-full grid: everything is interior, outside counts as occupied
+    env.update(np.full(Nb ** 3, np.uint64(2 ** 64 - 1)))
+    env.remove_interior()
+    assert env.nblocks() == 0 and not env.download().any()

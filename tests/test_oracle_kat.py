@@ -461,3 +461,134 @@ def test_batch_drivers_match_single_calls(orc, wl):
     v = orc.check_sets_batch(store, env, nthreads=2)
     for i in range(16):
         assert v[i] == store.get(i).collides(env)
+
+
+# ---- environment preparation (collision/VoxelOctree.cpp:533-952) vs dense numpy morphology ----
+_OFF6 = [(-1, 0, 0), (1, 0, 0), (0, -1, 0), (0, 1, 0), (0, 0, -1), (0, 0, 1)]
+# the reference's 27-neighbour list as written: (+1,+1,+1) twice, (-1,+1,+1) never
+_OFF27_REF = [(i, j, k) for i in (-1, 0, 1) for j in (-1, 0, 1) for k in (-1, 0, 1)
+              if (i, j, k) not in ((0, 0, 0), (-1, 1, 1))]
+
+
+def _dense_of(tree, Ng):
+    d = np.zeros((Ng, Ng, Ng), dtype=bool)
+    for c in tree.cells():
+        d[c] = True
+    return d
+
+
+def _tree_from_dense(orc, g, dense):
+    t = orc.octree(g)
+    Ng = dense.shape[0]
+    w = (1 << (np.arange(4)[:, None, None] * 16 + np.arange(4)[None, :, None] * 4
+               + np.arange(4)[None, None, :]).astype(np.uint64))
+    for bx in range(Ng // 4):
+        for by in range(Ng // 4):
+            for bz in range(Ng // 4):
+                blk = dense[4 * bx:4 * bx + 4, 4 * by:4 * by + 4, 4 * bz:4 * bz + 4]
+                if blk.any():
+                    t.set_block(bx, by, bz, int(np.sum(w[blk], dtype=np.uint64)))
+    return t
+
+
+def _shifted(dense, off, fill):
+    """out[c] = dense[c + off], `fill` outside the grid."""
+    Ng = dense.shape[0]
+    p = np.pad(dense, 1, constant_values=fill)
+    i, j, k = off
+    return p[1 + i:1 + i + Ng, 1 + j:1 + j + Ng, 1 + k:1 + k + Ng]
+
+
+def _np_dilate(dense, offs, num):
+    for _ in range(num):
+        new = dense.copy()
+        for d in offs:  # cell c is reached from c - d
+            new |= _shifted(dense, (-d[0], -d[1], -d[2]), False)
+        dense = new
+    return dense
+
+
+def _np_remove_interior(dense, diagonal):
+    offs = [(i, j, k) for i in (-1, 0, 1) for j in (-1, 0, 1) for k in (-1, 0, 1)] if diagonal \
+        else _OFF6 + [(0, 0, 0)]
+    interior = np.ones_like(dense)
+    for d in offs:
+        interior &= _shifted(dense, d, True)
+    return dense & ~interior
+
+
+def _random_env_dense(rng, Ng, nblob):
+    d = np.zeros((Ng, Ng, Ng), dtype=bool)
+    ax = np.arange(Ng)
+    X, Y, Z = np.meshgrid(ax, ax, ax, indexing="ij")
+    for _ in range(nblob):
+        c = rng.integers(-1, Ng + 1, 3)  # blobs may poke through the grid faces
+        r = rng.uniform(0.5, Ng / 5)
+        d |= (X - c[0]) ** 2 + (Y - c[1]) ** 2 + (Z - c[2]) ** 2 <= r * r
+    d[rng.integers(0, Ng, 12), rng.integers(0, Ng, 12), rng.integers(0, Ng, 12)] = True
+    return d
+
+
+def test_dilate_single_cell_hand_count(orc):
+    g = _grid(orc, 32, (0, 1, 0, 1, 0, 1))
+    t = orc.octree(g)
+    t.set_block(3, 3, 3, 1 << (1 * 16 + 2 * 4 + 1))  # one interior cell
+    a = t.copy(); a.dilate(1)
+    assert a.ncells() == 7  # the cell + its six face neighbours
+    a = t.copy(); a.dilate(3)
+    assert a.ncells() == 63  # L1 ball of radius 3: 1 + sum_{k<=3} (4k^2 + 2)
+    a = t.copy(); a.dilate(6)
+    assert a.ncells() == 377  # radius 6 crosses the four-steps-per-pass boundary of the reference
+    a = t.copy(); a.dilate(1, True)
+    assert a.ncells() == 26  # 27 minus the never-named (x-1,y+1,z+1)
+    c = (13, 14, 13)
+    assert (c[0] - 1, c[1] + 1, c[2] + 1) not in a.cells() and (c[0] + 1, c[1] + 1, c[2] + 1) in a.cells()
+    a = t.copy(); a.dilate(0)
+    assert a.ncells() == 1
+    # corner cell: clipped at the grid faces
+    t = orc.octree(g)
+    t.set_block(0, 0, 0, 1)
+    a = t.copy(); a.dilate(2)
+    assert a.ncells() == 10  # |{x+y+z<=2, x,y,z>=0}|
+
+
+@pytest.mark.parametrize("Ng", [16, 32])
+def test_dilate_and_remove_interior_vs_dense_numpy(orc, Ng):
+    g = _grid(orc, Ng, (0, 1, 0, 2, 0, 0.5))
+    rng = np.random.default_rng(77 + Ng)
+    for trial in range(4):
+        dense = _random_env_dense(rng, Ng, 3 + trial)
+        t = _tree_from_dense(orc, g, dense)
+        assert np.array_equal(_dense_of(t, Ng), dense)
+        for num in (1, 2, 4, 5, 9):
+            a = t.copy(); a.dilate(num)
+            assert np.array_equal(_dense_of(a, Ng), _np_dilate(dense, _OFF6, num)), (trial, num)
+        for num in (1, 3, 5):
+            a = t.copy(); a.dilate(num, True)
+            assert np.array_equal(_dense_of(a, Ng), _np_dilate(dense, _OFF27_REF, num)), (trial, num)
+        for diag in (False, True):
+            a = t.copy(); a.remove_interior(diag)
+            assert np.array_equal(_dense_of(a, Ng), _np_remove_interior(dense, diag)), (trial, diag)
+    # dilate_sphere(r) = dilate_6neighbor(round(r / min(dx,dy,dz))): dz = 0.5/Ng is the smallest
+    a, b = t.copy(), t.copy()
+    a.dilate_sphere(2.4 * 0.5 / Ng); b.dilate(2)
+    assert a.cells() == b.cells()
+    a, b = t.copy(), t.copy()
+    a.dilate_sphere(2.6 * 0.5 / Ng); b.dilate(3)
+    assert a.cells() == b.cells()
+
+
+def test_remove_interior_full_grid_and_shell(orc):
+    g = _grid(orc, 16, (0, 1, 0, 1, 0, 1))
+    t = orc.octree(g)
+    for bx in range(4):
+        for by in range(4):
+            for bz in range(4):
+                t.set_block(bx, by, bz, (1 << 64) - 1)
+    a = t.copy(); a.remove_interior(True)
+    assert a.ncells() == 0 and a.nblocks() == 0  # outside counts as occupied: everything is interior
+    t.set_block(0, 0, 0, ((1 << 64) - 1) & ~1)  # open one corner cell
+    a = t.copy(); a.remove_interior(False)
+    assert a.cells() == {(1, 0, 0), (0, 1, 0), (0, 0, 1)}
+    a = t.copy(); a.remove_interior(True)
+    assert a.cells() == {(i, j, k) for i in (0, 1) for j in (0, 1) for k in (0, 1)} - {(0, 0, 0)}
