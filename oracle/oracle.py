@@ -257,6 +257,10 @@ class Oracle:
         self.lib.orc_closest_st_segment(_dp(a), _dp(b), _dp(c), _dp(d), C.byref(s), C.byref(t))
         return s.value, t.value
 
+    def segment_aabox_intersect(self, A, B, Cc, D):
+        a, b, c, d = (np.ascontiguousarray(v, dtype=np.float64) for v in (A, B, Cc, D))
+        return bool(self.lib.orc_segment_aabox_intersect(_dp(a), _dp(b), _dp(c), _dp(d)))
+
     def validity_flags(self, rb, state, shape):
         state = np.ascontiguousarray(state, dtype=np.float64)
         p = np.ascontiguousarray(shape["p"], dtype=np.float64)

@@ -1,0 +1,229 @@
+"""ctypes binding of oracle/_ref/ — pieces of the REFERENCE ITSELF, compiled here.
+
+TEST INFRASTRUCTURE ONLY (same rule as oracle/oracle.py).
+
+* libtreenode_ref.so: the reference's collision/detail/TreeNode.h(.hxx) (std-only header), i.e. the
+  real octree storage, set algebra, collides() and visit_leaves() order.
+* libfk_ref.so: the reference's tendon/get_r_info.cpp, tendon/tendon_deriv.cpp,
+  tendon/solve_initial_bending.cpp and collision/collision_primitives.cpp, unmodified, compiled against
+  the Eigen stand-in in oracle/ref_shim/eigen_standin (Eigen is not installed; see that header for what
+  this does and does not pin).
+
+Both are built by `make -C oracle ref` only where /root/reference exists; they travel to the GPU box
+as prebuilt files.  Nothing here is needed at run time by the product.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+REF_DIR = os.path.join(_HERE, "_ref")
+REF_SRC = "/root/reference/cpp/src"
+
+
+def build():
+    """(Re)build oracle/_ref when the reference sources are present; no-op otherwise."""
+    if os.path.isdir(REF_SRC):
+        subprocess.check_call(["make", "-C", _HERE, "-s", "ref"], env=dict(os.environ, CXX="g++"))
+
+
+def available():
+    return all(os.path.exists(os.path.join(REF_DIR, n))
+               for n in ("libtreenode_ref.so", "libfk_ref.so"))
+
+
+def _dp(a):
+    return a.ctypes.data_as(C.POINTER(C.c_double))
+
+
+class RefTree:
+    """collision::detail::TreeNode<Ng> of the reference behind a handle."""
+    _lib = None
+
+    @classmethod
+    def lib(cls):
+        if cls._lib is None:
+            L = C.CDLL(os.path.join(REF_DIR, "libtreenode_ref.so"))
+            u64, vp = C.c_uint64, C.c_void_p
+            L.tnref_new.restype = vp
+            L.tnref_new.argtypes = [u64]
+            L.tnref_free.argtypes = [vp]
+            L.tnref_clone.restype = vp
+            L.tnref_clone.argtypes = [vp]
+            L.tnref_nblocks.restype = u64
+            L.tnref_nblocks.argtypes = [vp]
+            L.tnref_is_empty.argtypes = [vp]
+            L.tnref_block.restype = u64
+            L.tnref_block.argtypes = [vp, u64, u64, u64]
+            L.tnref_set_block.argtypes = [vp, u64, u64, u64, u64]
+            for n in ("tnref_union_block", "tnref_intersect_block"):
+                getattr(L, n).restype = u64
+                getattr(L, n).argtypes = [vp, u64, u64, u64, u64]
+            for n in ("tnref_union_tree", "tnref_intersect_tree", "tnref_remove_tree",
+                      "tnref_collides", "tnref_equals"):
+                getattr(L, n).restype = C.c_int
+                getattr(L, n).argtypes = [vp, vp]
+            L.tnref_leaves.restype = u64
+            L.tnref_leaves.argtypes = [vp, C.POINTER(u64), u64]
+            L.tnref_check_csr.restype = C.c_int
+            L.tnref_check_csr.argtypes = [vp, u64, C.POINTER(u64), C.POINTER(C.c_uint8),
+                                          C.POINTER(C.c_uint8), C.POINTER(C.c_uint8),
+                                          C.POINTER(u64), C.POINTER(C.c_uint8)]
+            cls._lib = L
+        return cls._lib
+
+    def __init__(self, Ng, _h=None):
+        self.Ng = int(Ng)
+        self.h = _h if _h is not None else self.lib().tnref_new(self.Ng)
+        if not self.h:
+            raise ValueError("unsupported Ng %r" % (Ng,))
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            self.lib().tnref_free(self.h)
+            self.h = None
+
+    def copy(self):
+        return RefTree(self.Ng, self.lib().tnref_clone(self.h))
+
+    def nblocks(self):
+        return int(self.lib().tnref_nblocks(self.h))
+
+    def is_empty(self):
+        return bool(self.lib().tnref_is_empty(self.h))
+
+    def block(self, bx, by, bz):
+        return int(self.lib().tnref_block(self.h, bx, by, bz))
+
+    def set_block(self, bx, by, bz, v):
+        self.lib().tnref_set_block(self.h, bx, by, bz, int(v))
+
+    def union_block(self, bx, by, bz, v):
+        """VoxelOctree::union_block (collision/VoxelOctree.cpp:224-233): the wrapper the callers use
+        forwards to TreeNode::union_block only for a non-zero value."""
+        if not v:
+            return self.block(bx, by, bz)
+        return int(self.lib().tnref_union_block(self.h, bx, by, bz, int(v)))
+
+    def node_union_block(self, bx, by, bz, v):
+        """raw TreeNode::union_block (creates an empty leaf for v == 0)"""
+        return int(self.lib().tnref_union_block(self.h, bx, by, bz, int(v)))
+
+    def intersect_block(self, bx, by, bz, v):
+        return int(self.lib().tnref_intersect_block(self.h, bx, by, bz, int(v)))
+
+    def union_tree(self, o):
+        assert self.lib().tnref_union_tree(self.h, o.h) == 0
+
+    def intersect_tree(self, o):
+        assert self.lib().tnref_intersect_tree(self.h, o.h) == 0
+
+    def remove_tree(self, o):
+        assert self.lib().tnref_remove_tree(self.h, o.h) == 0
+
+    def collides(self, o):
+        r = self.lib().tnref_collides(self.h, o.h)
+        assert r >= 0
+        return bool(r)
+
+    def equals(self, o):
+        return bool(self.lib().tnref_equals(self.h, o.h))
+
+    def leaves(self):
+        """(bx, by, bz, bits) arrays in the reference's visit_leaves order."""
+        n = self.nblocks()
+        buf = np.zeros((max(n, 1), 4), dtype=np.uint64)
+        m = int(self.lib().tnref_leaves(self.h, buf.ctypes.data_as(C.POINTER(C.c_uint64)), n))
+        assert m == n
+        buf = buf[:n]
+        return (buf[:, 0].astype(np.uint8), buf[:, 1].astype(np.uint8), buf[:, 2].astype(np.uint8),
+                buf[:, 3].copy())
+
+    def check_csr(self, off, bx, by, bz, bits):
+        """Verdicts of env.collides(set_i) for sets given as CSR block lists."""
+        off = np.ascontiguousarray(off, dtype=np.uint64)
+        bx, by, bz = (np.ascontiguousarray(a, dtype=np.uint8) for a in (bx, by, bz))
+        bits = np.ascontiguousarray(bits, dtype=np.uint64)
+        n = len(off) - 1
+        out = np.zeros(n, dtype=np.uint8)
+        u8p, u64p = C.POINTER(C.c_uint8), C.POINTER(C.c_uint64)
+        rc = self.lib().tnref_check_csr(self.h, n, off.ctypes.data_as(u64p), bx.ctypes.data_as(u8p),
+                                        by.ctypes.data_as(u8p), bz.ctypes.data_as(u8p),
+                                        bits.ctypes.data_as(u64p), out.ctypes.data_as(u8p))
+        assert rc == 0
+        return out.astype(bool)
+
+
+class RefFK:
+    """The reference's FK arithmetic (see module docstring) for one robot spec
+    (same dict as oracle.Oracle.robot)."""
+    _lib = None
+
+    @classmethod
+    def lib(cls):
+        if cls._lib is None:
+            L = C.CDLL(os.path.join(REF_DIR, "libfk_ref.so"))
+            L.fkref_initial_bending.restype = C.c_int
+            L.fkref_shape.restype = C.c_int
+            L.fkref_segment_aabox_intersect.restype = C.c_int
+            L.fkref_closest_t_segment.restype = C.c_double
+            cls._lib = L
+        return cls._lib
+
+    def __init__(self, spec):
+        self.spec = spec
+        self.N = len(spec["C"])
+        self.Nc = len(spec["C"][0])
+        self.Nd = len(spec["D"][0])
+        self.C = np.ascontiguousarray(spec["C"], dtype=np.float64).reshape(self.N, self.Nc)
+        self.D = np.ascontiguousarray(spec["D"], dtype=np.float64).reshape(self.N, self.Nd)
+        self.mat = [C.c_double(float(spec[k])) for k in ("ro", "ri", "E", "nu")]
+
+    def _hdr(self):
+        return [C.c_int(self.N), C.c_int(self.Nc), C.c_int(self.Nd), _dp(self.C), _dp(self.D)]
+
+    def r_info(self, t):
+        r, rd, rdd = (np.zeros((self.N, 3)) for _ in range(3))
+        self.lib().fkref_r_info(*self._hdr(), C.c_double(t), _dp(r), _dp(rd), _dp(rdd))
+        return r, rd, rdd
+
+    def deriv(self, tau, x, t, unopt=False):
+        tau = np.ascontiguousarray(tau, dtype=np.float64)
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        assert len(tau) == self.N and len(x) == 19 + self.N
+        out = np.zeros_like(x)
+        self.lib().fkref_deriv(*self._hdr(), _dp(tau), *self.mat, _dp(x), C.c_double(t), _dp(out),
+                               C.c_int(int(unopt)))
+        return out
+
+    def initial_bending(self, tau, s_start):
+        tau = np.ascontiguousarray(tau, dtype=np.float64)
+        v0, u0 = np.zeros(3), np.zeros(3)
+        it = self.lib().fkref_initial_bending(*self._hdr(), _dp(tau), *self.mat,
+                                              C.c_double(float(self.spec["residual_threshold"])),
+                                              C.c_double(s_start), _dp(v0), _dp(u0))
+        return v0, u0, int(it)
+
+    def shape_states(self, tau, times):
+        """RK4 walk over `times` (driver is NOT the reference's, see fk_ref.cpp) with the reference's
+        derivative and initial condition.  Returns states [nt][19+N] and the step count."""
+        tau = np.ascontiguousarray(tau, dtype=np.float64)
+        times = np.ascontiguousarray(times, dtype=np.float64)
+        st = np.zeros((len(times), 19 + self.N))
+        n = self.lib().fkref_shape(*self._hdr(), _dp(tau), *self.mat,
+                                   C.c_double(float(self.spec["residual_threshold"])),
+                                   C.c_double(float(self.spec["dL"])), _dp(times), C.c_int(len(times)),
+                                   _dp(st))
+        return st, int(n)
+
+    def closest_st_segment(self, A, B, Cc, D):
+        a, b, c, d = (np.ascontiguousarray(v, dtype=np.float64) for v in (A, B, Cc, D))
+        s, t = C.c_double(), C.c_double()
+        self.lib().fkref_closest_st_segment(_dp(a), _dp(b), _dp(c), _dp(d), C.byref(s), C.byref(t))
+        return s.value, t.value
+
+    def segment_aabox_intersect(self, A, B, Cc, D):
+        a, b, c, d = (np.ascontiguousarray(v, dtype=np.float64) for v in (A, B, Cc, D))
+        return bool(self.lib().fkref_segment_aabox_intersect(_dp(a), _dp(b), _dp(c), _dp(d)))

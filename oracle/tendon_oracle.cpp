@@ -882,6 +882,11 @@ void orc_closest_st_segment(const double *A, const double *B, const double *C, c
   *t = st.second;
 }
 
+int orc_segment_aabox_intersect(const double *A, const double *B, const double *C, const double *D) {
+  return segment_aabox_intersect(mk(A[0], A[1], A[2]), mk(B[0], B[1], B[2]), mk(C[0], C[1], C[2]),
+                                 mk(D[0], D[1], D[2])) ? 1 : 0;
+}
+
 uint32_t orc_validity_flags(const orc_robot *rb, const double *state, const orc_fk_out *fk,
                             const double *p) {
   std::vector<V3> pts(fk->npts);

@@ -101,6 +101,8 @@ void orc_closest_st_segment(const double *A, const double *B, const double *C, c
                             double *s, double *t);
 /* validity flag word for one computed shape (AbstractValidityChecker.cpp:99-114),
  * every test evaluated independently */
+/* collision/collision_primitives.h:62-85 */
+int orc_segment_aabox_intersect(const double *A, const double *B, const double *C, const double *D);
 uint32_t orc_validity_flags(const orc_robot *rb, const double *state, const orc_fk_out *fk,
                             const double *p);
 

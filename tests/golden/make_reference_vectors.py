@@ -1,0 +1,94 @@
+"""Generate tests/golden/reference_vectors.npz from the REFERENCE's own code (oracle/_ref).
+
+Run in the container that has /root/reference:  python tests/golden/make_reference_vectors.py
+The vectors are outputs of the reference's unmodified source files compiled here
+(oracle/ref.py explains which, and the Eigen stand-in caveat); they let the pins in
+tests/test_oracle_vs_reference.py run where /root/reference and oracle/_ref are absent.
+"""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+
+from oracle import ref  # noqa: E402
+import irt_b200.workloads as wl  # noqa: E402
+
+SEED = 20220801
+
+
+def robots():
+    return {"a005": wl.robot_a(0.005), "b003": wl.robot_b(0.003), "b005rot": wl.robot_b(0.005, rotation=True)}
+
+
+def random_ode_state(rng, N):
+    x = np.zeros(19 + N)
+    x[:3] = rng.normal(size=3) * 0.1
+    q, _ = np.linalg.qr(rng.normal(size=(3, 3)))
+    x[3:12] = q.T.reshape(-1)
+    x[12:15] = np.array([0, 0, 1.0]) + rng.normal(size=3) * 0.05
+    x[15:18] = rng.normal(size=3) * 5
+    x[18] = rng.uniform(0, 0.2)
+    x[19:] = rng.uniform(0, 0.2, N)
+    return x
+
+
+def main():
+    ref.build()
+    assert ref.available()
+    out = {}
+    rng = np.random.default_rng(SEED)
+    for name, spec in robots().items():
+        rf = ref.RefFK(spec)
+        N = rf.N
+        n = 64
+        ts = rng.uniform(0, spec["L"], n)
+        taus = rng.uniform(0, 20, (n, N))
+        xs = np.stack([random_ode_state(rng, N) for _ in range(n)])
+        out[name + "_t"] = ts
+        out[name + "_tau"] = taus
+        out[name + "_x"] = xs
+        out[name + "_rinfo"] = np.stack([np.stack(rf.r_info(t)) for t in ts])           # [n][3][N][3]
+        out[name + "_dxdt"] = np.stack([rf.deriv(taus[i], xs[i], ts[i]) for i in range(n)])
+        s0 = rng.uniform(0, 0.9 * spec["L"], n) if spec.get("enable_retraction") else np.zeros(n)
+        ib = [rf.initial_bending(taus[i], s0[i]) for i in range(n)]
+        out[name + "_s0"] = s0
+        out[name + "_v0"] = np.stack([b[0] for b in ib])
+        out[name + "_u0"] = np.stack([b[1] for b in ib])
+        out[name + "_iters"] = np.array([b[2] for b in ib], dtype=np.int32)
+    # capsule-pair primitive: random, degenerate and parallel cases
+    rf = ref.RefFK(wl.robot_a())
+    segs = rng.normal(size=(256, 4, 3))
+    segs[:16, 1] = segs[:16, 0]                       # A == B
+    segs[16:32, 3] = segs[16:32, 2]                   # C == D
+    segs[32:64, 3] = segs[32:64, 2] + (segs[32:64, 1] - segs[32:64, 0]) * rng.uniform(-2, 2, (32, 1))  # parallel
+    segs[64:80, 2] = segs[64:80, 0] + 0.3 * (segs[64:80, 1] - segs[64:80, 0])   # collinear, overlapping
+    segs[64:80, 3] = segs[64:80, 0] + 1.7 * (segs[64:80, 1] - segs[64:80, 0])
+    out["segs"] = segs
+    out["segs_st"] = np.array([rf.closest_st_segment(*s) for s in segs])
+    boxes = rng.uniform(-1, 1, (256, 4, 3))
+    out["boxes"] = boxes
+    out["boxes_hit"] = np.array([rf.segment_aabox_intersect(*b) for b in boxes], dtype=np.uint8)
+    # octree: a random edit script replayed on the reference's TreeNode<32>; leaves in visit order
+    Ng = 32
+    t = ref.RefTree(Ng)
+    script = []
+    for _ in range(400):
+        op = int(rng.integers(0, 2))   # set_block / union_block (the two the hot path uses)
+        bx, by, bz = (int(v) for v in rng.integers(0, Ng // 4, 3))
+        val = int(rng.integers(0, 2 ** 63)) if rng.random() > 0.15 else 0
+        script.append((op, bx, by, bz, val))
+        (t.set_block, t.union_block)[op](bx, by, bz, val)
+    out["tree_script"] = np.array(script, dtype=np.uint64)
+    bx, by, bz, bits = t.leaves()
+    out["tree_leaves_xyz"] = np.stack([bx, by, bz], axis=1)
+    out["tree_leaves_bits"] = bits
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "reference_vectors.npz")
+    np.savez_compressed(path, **out)
+    print("wrote", path, os.path.getsize(path), "bytes")
+
+
+if __name__ == "__main__":
+    main()

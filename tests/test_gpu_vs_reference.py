@@ -1,0 +1,116 @@
+"""GPU parity against the REFERENCE'S OWN CODE (oracle/_ref, prebuilt where /root/reference exists
+and shipped with the repo snapshot; see oracle/ref.py for exactly what it is).
+
+* K3 verdicts vs the reference's real octree: every GPU-built set is rebuilt as a
+  collision::detail::TreeNode<128> and tested with TreeNode::collides (TreeNode.hxx:165-174, :268) --
+  the loop of VoxelCachedLazyPRM.cpp:1584-1591.  Bit-exact, 0 flips.
+* K1 backbone points vs an RK4 walk whose derivative and initial condition are the reference's
+  unmodified tendon_deriv.cpp / solve_initial_bending.cpp / get_r_info.cpp: 1e-9 L.
+"""
+import numpy as np
+import pytest
+
+from oracle import ref
+
+pytestmark = [pytest.mark.gpu,
+              pytest.mark.skipif(not ref.available(), reason="oracle/_ref was not shipped")]
+
+FK_REL_TOL = 1e-9
+
+
+@pytest.fixture(scope="module")
+def irt():
+    import irt_b200
+    return irt_b200
+
+
+@pytest.fixture(scope="module")
+def ctx(irt):
+    return irt.Context(0)
+
+
+def _ref_env(wl, Ng, env_blocks):
+    Nb = Ng // 4
+    keys = np.nonzero(env_blocks)[0].astype(np.uint32)
+    ex, ey, ez = wl.morton_decode(keys, Nb)
+    renv = ref.RefTree(Ng)
+    for x, y, z, k in zip(ex.tolist(), ey.tolist(), ez.tolist(), keys.tolist()):
+        renv.set_block(x, y, z, int(env_blocks[k]))
+    return renv
+
+
+def test_k3_verdicts_vs_reference_treenode(irt, ctx, wl):
+    spec = wl.robot_b(0.003)
+    g = wl.workspace_grid(spec)
+    Nb = g["Ng"] // 4
+    grid = irt.make_grid(g["Ng"], g["lim"])
+    rb = irt.Robot(ctx, spec)
+    states = wl.sample_states(spec, 20000, stream=71)
+    store = irt.SetStore(ctx, grid)
+    store.voxelize_vertices(rb, states)
+    env_blocks = wl.dense_to_morton_blocks(wl.lung_like_env_dense(spec, g))
+    env = irt.Env(ctx, grid)
+    env.update(env_blocks)
+    got = store.check(env)
+    off, keys, bits = store.export_csr()
+    bx, by, bz = wl.morton_decode(keys, Nb)
+    want = _ref_env(wl, g["Ng"], env_blocks).check_csr(off, bx, by, bz, bits)
+    flips = int(np.count_nonzero(got != want))
+    assert flips == 0, "%d verdict flips vs TreeNode::collides" % flips
+    assert 0.02 < want.mean() < 0.98
+
+
+def test_k3_edge_verdicts_vs_reference_treenode(irt, ctx, wl):
+    """swept-volume sets of roadmap edges (K2 output) against the reference octree, incl. a tick
+    of the replanning loop (changed environment)"""
+    spec = wl.robot_b(0.003)
+    g = wl.workspace_grid(spec)
+    Nb = g["Ng"] // 4
+    grid = irt.make_grid(g["Ng"], g["lim"])
+    rb = irt.Robot(ctx, spec)
+    a = wl.sample_states(spec, 1500, stream=72)
+    b = a + 0.05 * (wl.sample_states(spec, 1500, stream=73) - a)
+    store = irt.SetStore(ctx, grid)
+    store.voxelize_edges(rb, irt.make_space(), a, b)
+    off, keys, bits = store.export_csr()
+    bx, by, bz = wl.morton_decode(keys, Nb)
+    env_blocks = wl.dense_to_morton_blocks(wl.lung_like_env_dense(spec, g))
+    env = irt.Env(ctx, grid)
+    for tick in range(3):
+        if tick:
+            rng = np.random.default_rng(tick)
+            env_blocks = wl.toggle_blob(env_blocks, g, rng.uniform(-0.1, 0.1, 3), 0.012)
+        env.update(env_blocks)
+        got = store.check(env)
+        want = _ref_env(wl, g["Ng"], env_blocks).check_csr(off, bx, by, bz, bits)
+        assert np.array_equal(got, want)
+
+
+@pytest.mark.parametrize("robot,dL,rot", [("a", 0.005, False), ("b", 0.003, False), ("b", 0.005, True)])
+def test_k1_points_vs_reference_derivative(irt, ctx, wl, robot, dL, rot):
+    spec = wl.robot_a(dL) if robot == "a" else wl.robot_b(dL, rotation=rot)
+    rb = irt.Robot(ctx, spec)
+    rf = ref.RefFK(spec)
+    N = rf.N
+    states = wl.sample_states(spec, 200, stream=74)
+    out = rb.shape_batch(states, want=("p", "t", "npts", "L", "L_i", "uv", "iters", "nsteps", "flags"))
+    worst = 0.0
+    for i, s in enumerate(states):
+        n = int(out["npts"][i])
+        if n < 2:
+            continue
+        st, nsteps = rf.shape_states(s[:N], out["t"][i, :n])
+        assert nsteps == out["nsteps"][i]
+        p = st[:, :3]
+        if rot:
+            c, sn = np.cos(s[N]), np.sin(s[N])
+            p = p @ np.array([[c, -sn, 0], [sn, c, 0], [0, 0, 1]]).T
+        worst = max(worst, np.abs(p - out["p"][i, :n]).max() / spec["L"])
+        assert abs(st[-1, 18] - out["L"][i]) < FK_REL_TOL * spec["L"]
+        assert np.abs(st[-1, 19:] - out["L_i"][i]).max() < FK_REL_TOL * spec["L"]
+        s0 = s[-1] if spec.get("enable_retraction") else 0.0
+        v0, u0, it = rf.initial_bending(s[:N], s0)
+        assert it == out["iters"][i]
+        assert np.allclose(out["uv"][i][0:3], u0, rtol=1e-9, atol=1e-10)
+        assert np.allclose(out["uv"][i][6:9], v0, rtol=1e-9, atol=1e-10)
+    assert worst < FK_REL_TOL, worst

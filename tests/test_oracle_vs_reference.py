@@ -1,0 +1,205 @@
+"""Pins of the CPU oracle against the REFERENCE'S OWN CODE (no GPU needed).
+
+Two layers:
+* golden: tests/golden/reference_vectors.npz holds outputs of the reference's unmodified sources
+  compiled in the build container (tests/golden/make_reference_vectors.py, oracle/ref.py);
+  these tests run anywhere.
+* live: when oracle/_ref/ is present (it is built wherever /root/reference exists and travels with
+  the repo snapshot), the oracle is compared with the reference pieces directly on more inputs.
+
+What "reference" means here, precisely: collision/detail/TreeNode.h is the real thing (std-only);
+tendon_deriv / solve_initial_bending / get_r_info2 / closest_st_segment / segment_aabox_intersect are
+the reference's unmodified .cpp files compiled against a stand-in for Eigen's fixed-size algebra
+(oracle/ref_shim/eigen_standin/Eigen/Core), so they pin the reference's formulas, operand order and
+control flow, not Eigen's rounding.  The RK4 stepping (Boost.odeint), t_range, add_line and the
+swept-volume driver remain restated-only.
+"""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import ref
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "reference_vectors.npz")
+live = pytest.mark.skipif(not ref.available(), reason="oracle/_ref not built (no /root/reference here)")
+
+
+@pytest.fixture(scope="module")
+def gold():
+    return np.load(GOLD)
+
+
+@pytest.fixture(scope="module")
+def robots(wl):
+    return {"a005": wl.robot_a(0.005), "b003": wl.robot_b(0.003),
+            "b005rot": wl.robot_b(0.005, rotation=True)}
+
+
+# ------------------------------------------------------------------ golden (reference outputs)
+@pytest.mark.parametrize("name", ["a005", "b003", "b005rot"])
+def test_golden_routing_bit_exact(orc, gold, robots, name):
+    rb = orc.robot(robots[name])
+    for t, want in zip(gold[name + "_t"], gold[name + "_rinfo"]):
+        got = np.stack(orc.routing(rb, float(t)))
+        assert np.array_equal(got, want)          # get_r_info.cpp:105-144, bit for bit
+
+
+@pytest.mark.parametrize("name", ["a005", "b003", "b005rot"])
+def test_golden_tendon_deriv(orc, gold, robots, name):
+    rb = orc.robot(robots[name])
+    worst = 0.0
+    for t, tau, x, want in zip(gold[name + "_t"], gold[name + "_tau"], gold[name + "_x"],
+                               gold[name + "_dxdt"]):
+        got = orc.deriv(rb, tau, x, float(t))
+        worst = max(worst, np.abs(got - want).max() / max(1.0, np.abs(want).max()))
+    assert worst <= 1e-13, worst                 # tendon_deriv.cpp:95-178 (observed: 0)
+
+
+@pytest.mark.parametrize("name", ["a005", "b003", "b005rot"])
+def test_golden_initial_bending(orc, gold, robots, name):
+    spec = robots[name]
+    rb = orc.robot(spec)
+    N = len(spec["C"])
+    for tau, s0, v0, u0, it in zip(gold[name + "_tau"], gold[name + "_s0"], gold[name + "_v0"],
+                                   gold[name + "_u0"], gold[name + "_iters"]):
+        state = list(tau) + ([0.0] if spec.get("enable_rotation") else []) + \
+            ([float(s0)] if spec.get("enable_retraction") else [])
+        assert len(state) == orc.state_size(rb) and len(tau) == N
+        s = orc.shape(rb, state)
+        assert s["iters"] == int(it)             # solve_initial_bending.cpp:15-73: same trip count
+        assert np.allclose(s["v_i"], v0, rtol=0, atol=1e-15)
+        assert np.allclose(s["u_i"], u0, rtol=1e-14, atol=1e-13)
+
+
+def test_golden_closest_st_segment(orc, gold):
+    for seg, want in zip(gold["segs"], gold["segs_st"]):
+        got = orc.closest_st_segment(*seg)
+        assert got == (want[0], want[1])         # collision_primitives.cpp:10-102, all branches
+
+
+def test_golden_segment_aabox(orc, gold):
+    hits = np.array([orc.segment_aabox_intersect(*b) for b in gold["boxes"]], dtype=np.uint8)
+    assert np.array_equal(hits, gold["boxes_hit"]) and 0 < hits.sum() < len(hits)
+
+
+def test_golden_octree_edit_script(orc, gold):
+    """set_block / union_block replayed on the oracle's octree give the reference TreeNode's leaves
+    in the reference's visit_leaves order (TreeNode.hxx:75-190)."""
+    g = orc.grid(32, [0, 1, 0, 1, 0, 1])
+    t = orc.octree(g)
+    for op, bx, by, bz, val in gold["tree_script"].tolist():
+        (t.set_block, t.union_block)[op](bx, by, bz, val)
+    bxyz, bits = t.export()
+    assert np.array_equal(bxyz, gold["tree_leaves_xyz"])
+    assert np.array_equal(bits, gold["tree_leaves_bits"])
+    assert t.nblocks() == len(bits)
+
+
+def test_golden_file_matches_generator(gold):
+    keys = set(gold.files)
+    assert {"segs", "segs_st", "boxes", "tree_script", "a005_dxdt", "b003_rinfo"} <= keys
+
+
+# ------------------------------------------------------------------ live (oracle/_ref present)
+@live
+@pytest.mark.parametrize("name", ["a005", "b003", "b005rot"])
+def test_live_shape_against_reference_deriv(orc, wl, robots, name):
+    """Whole shapes: RK4 over the oracle's own t grid with the reference's tendon_deriv and
+    solve_initial_bending inside, vs the oracle's shape().  Positions within 1e-13 L."""
+    spec = robots[name]
+    rb = orc.robot(spec)
+    rf = ref.RefFK(spec)
+    N = rf.N
+    states = wl.sample_states(spec, 40, stream=11)
+    worst = 0.0
+    for s in states:
+        sh = orc.shape(rb, s)
+        if len(sh["t"]) < 2:
+            continue
+        st, nsteps = rf.shape_states(s[:N], sh["t"])
+        assert nsteps == sh["nsteps"]
+        rot = s[N] if spec.get("enable_rotation") else 0.0
+        p = st[:, :3]
+        if rot:                                   # TendonResult::rotate_z (TendonResult.cpp:13-18)
+            c, sn = np.cos(rot), np.sin(rot)
+            p = p @ np.array([[c, -sn, 0], [sn, c, 0], [0, 0, 1]]).T
+        worst = max(worst, np.abs(p - sh["p"]).max() / spec["L"])
+        assert abs(st[-1, 18] - sh["L"]) <= 1e-13
+        assert np.allclose(st[-1, 19:], sh["L_i"], rtol=0, atol=1e-13)
+    assert worst <= 1e-13, worst
+
+
+@live
+def test_live_unopt_solver_agrees(wl, robots):
+    """KAT (vii): the reference's block-elimination solve vs its dense 6x6 solve (stand-in: LU)."""
+    rng = np.random.default_rng(5)
+    from tests.golden.make_reference_vectors import random_ode_state
+    for spec in robots.values():
+        rf = ref.RefFK(spec)
+        for _ in range(20):
+            x = random_ode_state(rng, rf.N)
+            tau = rng.uniform(0, 20, rf.N)
+            t = rng.uniform(0, spec["L"])
+            a, b = rf.deriv(tau, x, t), rf.deriv(tau, x, t, unopt=True)
+            assert np.abs(a - b).max() <= 1e-10 * max(1.0, np.abs(a).max())
+
+
+@live
+@pytest.mark.parametrize("Ng", [4, 8, 64, 128, 512])
+def test_live_octree_algebra(orc, Ng):
+    """Random trees: block(), nblocks(), leaf order, collides() and add_voxels == union_tree."""
+    rng = np.random.default_rng(Ng)
+    g = orc.grid(Ng, [0, 1, 0, 1, 0, 1])
+    Nb = Ng // 4
+    for trial in range(6):
+        ta, tb = orc.octree(g), orc.octree(g)
+        ra, rb_ = ref.RefTree(Ng), ref.RefTree(Ng)
+        n = int(rng.integers(0, 40))
+        for (to, tr) in ((ta, ra), (tb, rb_)):
+            for _ in range(n):
+                bx, by, bz = (int(v) for v in rng.integers(0, Nb, 3))
+                # sparse bit patterns so that collides() has both outcomes
+                val = int(rng.integers(0, 2 ** 63)) & int(rng.integers(0, 2 ** 63)) & int(rng.integers(0, 2 ** 63))
+                if rng.random() < 0.5:
+                    to.union_block(bx, by, bz, val), tr.union_block(bx, by, bz, val)
+                else:
+                    to.set_block(bx, by, bz, val), tr.set_block(bx, by, bz, val)
+        assert bool(ta.collides(tb)) == ra.collides(rb_)
+        assert bool(tb.collides(ta)) == rb_.collides(ra)
+        for to, tr in ((ta, ra), (tb, rb_)):
+            bxyz, bits = to.export()
+            x, y, z, rbits = tr.leaves()
+            assert np.array_equal(bxyz, np.stack([x, y, z], axis=1).reshape(-1, 3))
+            assert np.array_equal(bits, rbits)
+            assert to.nblocks() == tr.nblocks()
+        ta.add_voxels(tb)
+        ra.union_tree(rb_)
+        bxyz, bits = ta.export()
+        x, y, z, rbits = ra.leaves()
+        assert np.array_equal(bits, rbits) and np.array_equal(bxyz[:, 0], x)
+
+
+@live
+def test_live_verdicts_of_a_voxelised_roadmap(orc, wl):
+    """The loop of VoxelCachedLazyPRM.cpp:1584-1591 with the reference's TreeNode::collides on sets the
+    oracle voxelised, vs the oracle's check_sets_batch."""
+    spec = wl.robot_b(dL=0.003)
+    rb = orc.robot(spec)
+    g = wl.workspace_grid(spec)
+    og = orc.grid(g["Ng"], g["lim"], g["inv_rot"])
+    states = wl.sample_states(spec, 300, stream=21)
+    store, _ = orc.voxelize_vertices_batch(rb, og, states)
+    env_blocks = wl.dense_to_morton_blocks(wl.lung_like_env_dense(spec, g))
+    Nb = g["Ng"] // 4
+    keys = np.nonzero(env_blocks)[0].astype(np.uint32)
+    ex, ey, ez = wl.morton_decode(keys, Nb)
+    oenv, renv = orc.octree(og), ref.RefTree(g["Ng"])
+    for x, y, z, k in zip(ex.tolist(), ey.tolist(), ez.tolist(), keys.tolist()):
+        oenv.set_block(x, y, z, int(env_blocks[k]))
+        renv.set_block(x, y, z, int(env_blocks[k]))
+    off, skeys, bits = store.export()
+    bx, by, bz = wl.morton_decode(skeys, Nb)
+    want = renv.check_csr(off, bx, by, bz, bits)
+    got = orc.check_sets_batch(store, oenv).astype(bool)
+    assert np.array_equal(got, want) and 0 < want.sum() < len(want)
