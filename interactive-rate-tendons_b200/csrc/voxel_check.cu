@@ -12,12 +12,11 @@
 //                the role of the octree's "null child" early-out.
 //   set store    CSR, structure-of-arrays: keys uint32[nb], bits uint64[nb], offsets uint64[n+1];
 //                12 bytes per occupied leaf block = the algorithmic traffic of SURVEY 8(d).
-// K3: one warp per tile of 32 consecutive sets = one uint32 verdict word.  The tile's leaves
-// are one contiguous CSR range; lanes stream it with 128-bit loads (uint4 of keys + 2 x
-// ulonglong2 of bits per lane and iteration, two iterations in flight), test
-// `bits & env[key]` behind the occupancy bitmap, and a leaf that hits is attributed to its set
-// by a warp broadcast against the 32 set offsets the lanes hold in registers.  The word is
-// produced by one __ballot_sync: no atomics, no memset, no per-set divergence.
+// K3: one CTA per tile of 256 consecutive sets = 8 uint32 verdict words.  The tile's leaves are
+// one contiguous CSR range that the CTA streams with 128-bit loads; a leaf whose `bits & env[key]`
+// (behind the occupancy bitmap) is non-zero sets one bit in a shared-memory hit bitmap, and each
+// thread then tests the bits of the one set it owns; the word is one __ballot_sync per warp: no
+// global atomics, no memset, no search, no per-set divergence (details at the kernel).
 #include <cstring>
 #include <vector>
 
@@ -61,119 +60,133 @@ __global__ void count_nonzero_kernel(const uint64_t *__restrict__ blocks, int64_
 }
 
 // K3 `voxel_and_popc`
+//
+// One CTA per tile of K3_THREADS consecutive sets (= 8 verdict words).  The tile's leaves are one
+// contiguous CSR range that all 256 threads stream as 16-byte aligned quads (uint4 of keys +
+// 2 x ulonglong2 of bits per thread and step, two steps in flight, ld.global.cs).  A leaf whose
+// `bits & env[key]` is non-zero sets ONE BIT at its tile-relative position in a shared-memory hit
+// bitmap (atomicOr, only on a hit); after the stream thread t -- which owns set s0+t and holds its
+// leaf range [lo,hi) -- tests the bits of its range (1-2 words for a typical 20-60 leaf set), and a
+// __ballot_sync per warp is the verdict word.  No shuffles, no search and no per-set divergence in the
+// streaming loop; tiles with more leaves than the bitmap holds are streamed in chunks.  The bitmap is
+// double-buffered by tile parity so a chunk costs two __syncthreads.
+constexpr int K3_CHUNK_LEAVES = 32768;                      // hit-bitmap capacity per buffer (4 KiB)
+constexpr int K3_BM_WORDS = K3_CHUNK_LEAVES / 32 + 2;       // +1 straddle word, +1 pad
+
 template <bool OCC_SMEM, bool STATS>
 __global__ void __launch_bounds__(K3_THREADS)
 voxel_and_popc_kernel(const uint32_t *__restrict__ keys, const uint64_t *__restrict__ bits,
                       const uint64_t *__restrict__ offsets, const uint64_t *__restrict__ env,
-                      const uint32_t *__restrict__ occ, int occ_words, int64_t set_begin,
-                      int64_t set_end, uint32_t *__restrict__ verdict,
+                      const uint32_t *__restrict__ occ, int occ_words, uint32_t key_mask,
+                      int64_t set_begin, int64_t set_end, uint32_t *__restrict__ verdict,
                       unsigned long long *__restrict__ stats) {
-  extern __shared__ uint32_t s_occ[];
+  extern __shared__ uint32_t s_mem[];
+  uint32_t *s_hit = s_mem;                     // [2][K3_BM_WORDS]
+  uint32_t *s_occ = s_mem + 2 * K3_BM_WORDS;   // [occ_words] when OCC_SMEM
   if (OCC_SMEM) {
-    for (int i = threadIdx.x; i < occ_words; i += blockDim.x) s_occ[i] = occ[i];
-    __syncthreads();
+    for (int i = threadIdx.x; i < occ_words; i += K3_THREADS) s_occ[i] = occ[i];
   }
   const uint32_t *occp = OCC_SMEM ? s_occ : occ;
-  const int lane = threadIdx.x & 31;
-  const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
-  const int64_t ntiles = (set_end - set_begin + 31) >> 5;
-  unsigned long long vox = 0, hits = 0;
+  const int tid = threadIdx.x;
+  const int64_t n_sets = set_end - set_begin;
+  const int64_t ntiles = (n_sets + K3_THREADS - 1) / K3_THREADS;
+  const int64_t nwords_out = (n_sets + 31) >> 5;
+  unsigned long long vox = 0, nhit = 0;
+  int parity = 0;
 
-  for (int64_t tile = warp; tile < ntiles; tile += nwarps) {
-    const int64_t s0 = set_begin + (tile << 5);
-    const int64_t sl = s0 + lane;
-    // lane l owns set s0+l: leaves [lo, hi), kept as 32-bit positions relative to the tile
-    uint64_t lo = 0, hi = 0;
+  for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const int64_t s0 = set_begin + tile * K3_THREADS;
+    const int64_t sl = s0 + tid;
+    const uint64_t t_lo = offsets[s0];
+    const uint64_t t_hi = offsets[min(s0 + (int64_t)K3_THREADS, set_end)];
+    uint64_t lo = t_hi, hi = t_hi;
     if (sl < set_end) { lo = offsets[sl]; hi = offsets[sl + 1]; }
-    const uint64_t t_lo = __shfl_sync(0xffffffffu, lo, 0);
-    const int last = (int)min((int64_t)31, set_end - 1 - s0);
-    const uint64_t t_hi = __shfl_sync(0xffffffffu, hi, last);
-    const uint32_t tile_n = (uint32_t)(t_hi - t_lo);
-    const uint32_t rlo = (sl < set_end) ? (uint32_t)(lo - t_lo) : tile_n;  // ascending over lanes
-    uint32_t own = 0;  // bit l set: set s0+l collides (as discovered by this lane)
+    bool own = false;
 
-    // position of the first leaf of this lane's quad relative to the tile start (may be < 0)
-    const int64_t q_begin = (int64_t)(t_lo >> 2), q_end = (int64_t)((t_hi + 3) >> 2);
-    const int32_t head = (int32_t)((q_begin << 2) - (int64_t)t_lo);  // in (-4, 0]
+    for (uint64_t c_lo = t_lo; c_lo < t_hi; c_lo += K3_CHUNK_LEAVES) {   // block-uniform
+      const uint64_t c_hi = min(c_lo + (uint64_t)K3_CHUNK_LEAVES, t_hi);
+      const uint32_t c_n = (uint32_t)(c_hi - c_lo);
+      uint32_t *hitw = s_hit + parity * K3_BM_WORDS;
+      parity ^= 1;
+      for (uint32_t i = tid; i < (c_n + 31) / 32 + 1; i += K3_THREADS) hitw[i] = 0;
+      __syncthreads();   // also orders the s_occ fill before its first use
 
-    auto process = [&](int32_t r0, const uint4 &kk, const ulonglong2 &b01, const ulonglong2 &b23) {
-      const uint32_t k[4] = {kk.x, kk.y, kk.z, kk.w};
-      const uint64_t b[4] = {b01.x, b01.y, b23.x, b23.y};
-      uint32_t hitmask = 0;
+      const int64_t q_begin = (int64_t)(c_lo >> 2), q_end = (int64_t)((c_hi + 3) >> 2);
+      const int32_t head = (int32_t)((q_begin << 2) - (int64_t)c_lo);  // in (-4, 0]
+
+      auto process = [&](int32_t r0, const uint4 &kk, const ulonglong2 &b01, const ulonglong2 &b23) {
+        const uint32_t k[4] = {kk.x & key_mask, kk.y & key_mask, kk.z & key_mask, kk.w & key_mask};
+        const uint64_t b[4] = {b01.x, b01.y, b23.x, b23.y};
+        uint32_t hitmask = 0;
 #pragma unroll
-      for (int e = 0; e < 4; e++) {
-        const uint32_t r = (uint32_t)(r0 + e);                    // negative wraps to huge: out of range
-        if (r >= tile_n || b[e] == 0ull) continue;
-        if (!((occp[k[e] >> 5] >> (k[e] & 31)) & 1u)) continue;  // empty environment leaf
-        const uint64_t x = b[e] & env[k[e]];
-        if (x == 0ull) continue;
-        hitmask |= 1u << e;
-        if (STATS) { vox += (unsigned long long)__popcll(x); hits++; }
-      }
-      // attribute hits to sets: every lane binary-searches (5 shuffles) the 32 set starts held
-      // across the warp for the owner of its first in-range leaf; the other three leaves of the
-      // quad have the same owner unless a set boundary falls inside the quad (rare: then those
-      // leaves are searched individually, warp-uniformly).
-      if (__any_sync(0xffffffffu, hitmask != 0)) {
-        const uint32_t rf = (r0 < 0) ? 0u : (uint32_t)r0;  // first leaf of the quad inside the tile
-        int o = 0;
-#pragma unroll
-        for (int step = 16; step > 0; step >>= 1) {
-          const uint32_t v = __shfl_sync(0xffffffffu, rlo, (o + step) & 31);
-          if (v <= rf) o += step;  // o + step <= 31 always holds here
-        }
-        const uint32_t nxt = __shfl_sync(0xffffffffu, rlo, (o + 1) & 31);
-        const uint32_t next_start = (o == 31) ? tile_n : nxt;  // start of the next set's leaves
-        const bool straddles = hitmask != 0 && (uint32_t)(r0 + 3) >= next_start;
-        if (hitmask != 0 && !straddles) own |= 1u << o;
-        if (__any_sync(0xffffffffu, straddles)) {
-#pragma unroll
-          for (int e = 0; e < 4; e++) {
-            const uint32_t r = (uint32_t)(r0 + e);
-            int oe = 0;
-#pragma unroll
-            for (int step = 16; step > 0; step >>= 1) {
-              const uint32_t v = __shfl_sync(0xffffffffu, rlo, (oe + step) & 31);
-              if (v <= r) oe += step;
+        for (int e = 0; e < 4; e++) {
+          if ((occp[k[e] >> 5] >> (k[e] & 31)) & 1u) {   // occupied environment leaf
+            const uint64_t x = b[e] & env[k[e]];
+            if (x != 0ull) {
+              hitmask |= 1u << e;
+              if (STATS) {
+                if ((uint32_t)(r0 + e) < c_n) { vox += (unsigned long long)__popcll(x); nhit++; }
+              }
             }
-            if (straddles && ((hitmask >> e) & 1u)) own |= 1u << oe;
           }
         }
-      }
-    };
+        if (hitmask) {
+          // clip leaves of the neighbouring chunks / tiles (only the first and last quad can have any)
+          if (r0 < 0) { hitmask >>= -r0; r0 = 0; }
+          if ((uint32_t)r0 + 4u > c_n) hitmask &= (c_n > (uint32_t)r0) ? (0xFu >> ((uint32_t)r0 + 4u - c_n)) : 0u;
+          const uint64_t m = (uint64_t)hitmask << (r0 & 31);
+          if ((uint32_t)m) atomicOr(&hitw[r0 >> 5], (uint32_t)m);
+          if ((uint32_t)(m >> 32)) atomicOr(&hitw[(r0 >> 5) + 1], (uint32_t)(m >> 32));
+        }
+      };
 
-    // flat walk over the tile's leaves in 16-byte aligned quads, two iterations in flight
-    for (int64_t qbase = q_begin; qbase < q_end; qbase += 64) {  // warp-uniform trip count
-      const int64_t qa = qbase + lane, qb = qa + 32;
-      uint4 ka = make_uint4(0, 0, 0, 0), kb = ka;
-      ulonglong2 a01 = make_ulonglong2(0, 0), a23 = a01, b01 = a01, b23 = a01;
-      const bool va = qa < q_end, vb = qb < q_end;
-      if (va) {
-        ka = __ldcs(reinterpret_cast<const uint4 *>(keys) + qa);
-        a01 = __ldcs(reinterpret_cast<const ulonglong2 *>(bits) + 2 * qa);
-        a23 = __ldcs(reinterpret_cast<const ulonglong2 *>(bits) + 2 * qa + 1);
+      // flat walk over the chunk's leaves, two quads per thread in flight
+      for (int64_t qbase = q_begin; qbase < q_end; qbase += 2 * K3_THREADS) {
+        const int64_t qa = qbase + tid, qb = qa + K3_THREADS;
+        const bool va = qa < q_end, vb = qb < q_end;
+        uint4 ka, kb;
+        ulonglong2 a01, a23, b01, b23;
+        if (va) {
+          ka = __ldcs(reinterpret_cast<const uint4 *>(keys) + qa);
+          a01 = __ldcs(reinterpret_cast<const ulonglong2 *>(bits) + 2 * qa);
+          a23 = __ldcs(reinterpret_cast<const ulonglong2 *>(bits) + 2 * qa + 1);
+        }
+        if (vb) {
+          kb = __ldcs(reinterpret_cast<const uint4 *>(keys) + qb);
+          b01 = __ldcs(reinterpret_cast<const ulonglong2 *>(bits) + 2 * qb);
+          b23 = __ldcs(reinterpret_cast<const ulonglong2 *>(bits) + 2 * qb + 1);
+        }
+        const int32_t ra = head + (int32_t)((qa - q_begin) << 2);
+        if (va) process(ra, ka, a01, a23);
+        if (vb) process(ra + 4 * K3_THREADS, kb, b01, b23);
       }
-      if (vb) {
-        kb = __ldcs(reinterpret_cast<const uint4 *>(keys) + qb);
-        b01 = __ldcs(reinterpret_cast<const ulonglong2 *>(bits) + 2 * qb);
-        b23 = __ldcs(reinterpret_cast<const ulonglong2 *>(bits) + 2 * qb + 1);
+      __syncthreads();
+
+      // does any hit bit fall into this thread's set range, clipped to the chunk?
+      const uint64_t a64 = max(lo, c_lo), b64 = min(hi, c_hi);
+      if (a64 < b64 && !own) {
+        const uint32_t a = (uint32_t)(a64 - c_lo), b = (uint32_t)(b64 - c_lo);   // [a, b), b > a
+        const uint32_t w0 = a >> 5, w1 = (b - 1) >> 5;
+        for (uint32_t w = w0; w <= w1; w++) {
+          uint32_t m = hitw[w];
+          if (w == w0) m &= 0xffffffffu << (a & 31);
+          if (w == w1) m &= 0xffffffffu >> (31 - ((b - 1) & 31));
+          if (m) { own = true; break; }
+        }
       }
-      const int32_t ra = head + (int32_t)((qa - q_begin) << 2);
-      process(ra, ka, a01, a23);
-      if (qbase + 32 < q_end) process(ra + 128, kb, b01, b23);
     }
-    const unsigned word = __reduce_or_sync(0xffffffffu, own);
-    if (lane == 0) verdict[tile] = word;
+    const unsigned word = __ballot_sync(0xffffffffu, own);
+    const int64_t wi = tile * (K3_THREADS / 32) + (tid >> 5);
+    if ((tid & 31) == 0 && wi < nwords_out) verdict[wi] = word;
   }
   if (STATS) {
     for (int o = 16; o > 0; o >>= 1) {
       vox += __shfl_down_sync(0xffffffffu, vox, o);
-      hits += __shfl_down_sync(0xffffffffu, hits, o);
+      nhit += __shfl_down_sync(0xffffffffu, nhit, o);
     }
-    if (lane == 0 && (vox | hits)) {
+    if ((tid & 31) == 0 && (vox | nhit)) {
       atomicAdd(&stats[0], vox);
-      atomicAdd(&stats[1], hits);
+      atomicAdd(&stats[1], nhit);
     }
   }
 }
@@ -446,19 +459,21 @@ static int check_sets_impl(irt_ctx *ctx, const irt_setstore *store, const irt_en
   }
   const int occ_words = (int)((env->n_blocks_total + 31) / 32);
   const bool occ_smem = (size_t)occ_words * 4 <= 64 * 1024;
-  const int64_t ntiles = (n + 31) / 32;
-  int64_t blocks = (ntiles * 32 + K3_THREADS - 1) / K3_THREADS;
-  const int64_t max_blocks = (int64_t)ctx->sm_count * 8;  // 8 resident CTAs of 256 threads per SM
+  int64_t blocks = (n + K3_THREADS - 1) / K3_THREADS;     // one CTA per tile of 256 sets ...
+  const int64_t max_blocks = (int64_t)ctx->sm_count * 8;  // ... persistent over 8 CTAs per SM
   if (blocks > max_blocks) blocks = max_blocks;
-  const size_t smem = occ_smem ? (size_t)occ_words * 4 : 0;
+  const size_t smem = (size_t)2 * K3_BM_WORDS * 4 + (occ_smem ? (size_t)occ_words * 4 : 0);
+  // keys are < Nb^3 (a power of two); the mask only keeps the (clipped) leaves that a quad reads
+  // beyond the end of the store inside the tables
+  const uint32_t key_mask = (uint32_t)(env->n_blocks_total - 1);
 #define K3_LAUNCH(OS, ST)                                                                          \
   do {                                                                                             \
     auto kfn = voxel_and_popc_kernel<OS, ST>;                                                      \
     if (smem > 48 * 1024)                                                                          \
       IRT_CUDA(ctx, cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
     kfn<<<(unsigned)blocks, K3_THREADS, smem, st>>>(store->d_keys, store->d_bits, store->d_offsets, \
-                                                    env->d_blocks, env->d_occ, occ_words, begin,   \
-                                                    end, d_verdict, d_stats);                      \
+                                                    env->d_blocks, env->d_occ, occ_words, key_mask, \
+                                                    begin, end, d_verdict, d_stats);               \
   } while (0)
   if (occ_smem) {
     if (d_stats) K3_LAUNCH(true, true); else K3_LAUNCH(true, false);
