@@ -73,20 +73,41 @@ __global__ void count_nonzero_kernel(const uint64_t *__restrict__ blocks, int64_
 constexpr int K3_CHUNK_LEAVES = 32768;                      // hit-bitmap capacity per buffer (4 KiB)
 constexpr int K3_BM_WORDS = K3_CHUNK_LEAVES / 32 + 2;       // +1 straddle word, +1 pad
 
+// predicated 8-byte read-only load: the four environment look-ups of a quad are issued back to back
+// (no branch per look-up), so their latencies overlap; lanes whose leaf is in an empty environment
+// block issue nothing
+__device__ __forceinline__ uint64_t ld_env_if(const uint64_t *p, uint32_t pred) {
+  uint64_t v;
+  asm("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %1, 0;\n\tmov.u64 %0, 0;\n\t@p ld.global.nc.u64 %0, [%2];\n\t}"
+      : "=l"(v) : "r"(pred), "l"(p));
+  return v;
+}
+
+// streaming 16-byte loads (evict-first); volatile keeps the issue order of the software pipeline
+__device__ __forceinline__ uint4 ld_stream(const uint4 *p) {
+  uint4 v;
+  asm volatile("ld.global.cs.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ ulonglong2 ld_stream(const ulonglong2 *p) {
+  ulonglong2 v;
+  asm volatile("ld.global.cs.v2.u64 {%0,%1}, [%2];" : "=l"(v.x), "=l"(v.y) : "l"(p));
+  return v;
+}
+
 template <bool OCC_SMEM, bool STATS>
 __global__ void __launch_bounds__(K3_THREADS)
 voxel_and_popc_kernel(const uint32_t *__restrict__ keys, const uint64_t *__restrict__ bits,
                       const uint64_t *__restrict__ offsets, const uint64_t *__restrict__ env,
-                      const uint32_t *__restrict__ occ, int occ_words, uint32_t key_mask,
+                      const uint32_t *__restrict__ occ, int occ_words,
                       int64_t set_begin, int64_t set_end, uint32_t *__restrict__ verdict,
                       unsigned long long *__restrict__ stats) {
+  // [0, 2*K3_BM_WORDS): two hit bitmaps; [2*K3_BM_WORDS, +occ_words): occupancy bitmap (OCC_SMEM)
   extern __shared__ uint32_t s_mem[];
-  uint32_t *s_hit = s_mem;                     // [2][K3_BM_WORDS]
-  uint32_t *s_occ = s_mem + 2 * K3_BM_WORDS;   // [occ_words] when OCC_SMEM
+  constexpr int OCC_OFF = 2 * K3_BM_WORDS;
   if (OCC_SMEM) {
-    for (int i = threadIdx.x; i < occ_words; i += K3_THREADS) s_occ[i] = occ[i];
+    for (int i = threadIdx.x; i < occ_words; i += K3_THREADS) s_mem[OCC_OFF + i] = occ[i];
   }
-  const uint32_t *occp = OCC_SMEM ? s_occ : occ;
   const int tid = threadIdx.x;
   const int64_t n_sets = set_end - set_begin;
   const int64_t ntiles = (n_sets + K3_THREADS - 1) / K3_THREADS;
@@ -106,28 +127,34 @@ voxel_and_popc_kernel(const uint32_t *__restrict__ keys, const uint64_t *__restr
     for (uint64_t c_lo = t_lo; c_lo < t_hi; c_lo += K3_CHUNK_LEAVES) {   // block-uniform
       const uint64_t c_hi = min(c_lo + (uint64_t)K3_CHUNK_LEAVES, t_hi);
       const uint32_t c_n = (uint32_t)(c_hi - c_lo);
-      uint32_t *hitw = s_hit + parity * K3_BM_WORDS;
+      const int hit_off = parity * K3_BM_WORDS;
       parity ^= 1;
-      for (uint32_t i = tid; i < (c_n + 31) / 32 + 1; i += K3_THREADS) hitw[i] = 0;
-      __syncthreads();   // also orders the s_occ fill before its first use
+      for (uint32_t i = tid; i < (c_n + 31) / 32 + 1; i += K3_THREADS) s_mem[hit_off + i] = 0;
+      __syncthreads();   // also orders the occupancy fill before its first use
 
-      const int64_t q_begin = (int64_t)(c_lo >> 2), q_end = (int64_t)((c_hi + 3) >> 2);
-      const int32_t head = (int32_t)((q_begin << 2) - (int64_t)c_lo);  // in (-4, 0]
+      const int64_t q_begin = (int64_t)(c_lo >> 2);
+      const int nq = (int)((int64_t)((c_hi + 3) >> 2) - q_begin);          // <= 8193 quads
+      const int32_t head = (int32_t)((q_begin << 2) - (int64_t)c_lo);      // in (-4, 0]
 
       auto process = [&](int32_t r0, const uint4 &kk, const ulonglong2 &b01, const ulonglong2 &b23) {
-        const uint32_t k[4] = {kk.x & key_mask, kk.y & key_mask, kk.z & key_mask, kk.w & key_mask};
+        const uint32_t k[4] = {kk.x, kk.y, kk.z, kk.w};
         const uint64_t b[4] = {b01.x, b01.y, b23.x, b23.y};
+        uint32_t o[4];
+        uint64_t ev[4];
+#pragma unroll
+        for (int e = 0; e < 4; e++) {   // occupied environment leaf?
+          const uint32_t w = OCC_SMEM ? s_mem[OCC_OFF + (k[e] >> 5)] : __ldg(occ + (k[e] >> 5));
+          o[e] = (w >> (k[e] & 31)) & 1u;
+        }
+#pragma unroll
+        for (int e = 0; e < 4; e++) ev[e] = ld_env_if(env + k[e], o[e]);
         uint32_t hitmask = 0;
 #pragma unroll
         for (int e = 0; e < 4; e++) {
-          if ((occp[k[e] >> 5] >> (k[e] & 31)) & 1u) {   // occupied environment leaf
-            const uint64_t x = b[e] & env[k[e]];
-            if (x != 0ull) {
-              hitmask |= 1u << e;
-              if (STATS) {
-                if ((uint32_t)(r0 + e) < c_n) { vox += (unsigned long long)__popcll(x); nhit++; }
-              }
-            }
+          const uint64_t x = b[e] & ev[e];
+          if (x != 0ull) hitmask |= 1u << e;
+          if (STATS) {
+            if (x != 0ull && (uint32_t)(r0 + e) < c_n) { vox += (unsigned long long)__popcll(x); nhit++; }
           }
         }
         if (hitmask) {
@@ -135,30 +162,36 @@ voxel_and_popc_kernel(const uint32_t *__restrict__ keys, const uint64_t *__restr
           if (r0 < 0) { hitmask >>= -r0; r0 = 0; }
           if ((uint32_t)r0 + 4u > c_n) hitmask &= (c_n > (uint32_t)r0) ? (0xFu >> ((uint32_t)r0 + 4u - c_n)) : 0u;
           const uint64_t m = (uint64_t)hitmask << (r0 & 31);
-          if ((uint32_t)m) atomicOr(&hitw[r0 >> 5], (uint32_t)m);
-          if ((uint32_t)(m >> 32)) atomicOr(&hitw[(r0 >> 5) + 1], (uint32_t)(m >> 32));
+          if ((uint32_t)m) atomicOr(&s_mem[hit_off + (r0 >> 5)], (uint32_t)m);
+          if ((uint32_t)(m >> 32)) atomicOr(&s_mem[hit_off + (r0 >> 5) + 1], (uint32_t)(m >> 32));
         }
       };
 
-      // flat walk over the chunk's leaves, two quads per thread in flight
-      for (int64_t qbase = q_begin; qbase < q_end; qbase += 2 * K3_THREADS) {
-        const int64_t qa = qbase + tid, qb = qa + K3_THREADS;
-        const bool va = qa < q_end, vb = qb < q_end;
-        uint4 ka, kb;
-        ulonglong2 a01, a23, b01, b23;
-        if (va) {
-          ka = __ldcs(reinterpret_cast<const uint4 *>(keys) + qa);
-          a01 = __ldcs(reinterpret_cast<const ulonglong2 *>(bits) + 2 * qa);
-          a23 = __ldcs(reinterpret_cast<const ulonglong2 *>(bits) + 2 * qa + 1);
-        }
+      // flat walk over the chunk's leaves: software-pipelined ping-pong, the loads of a thread's next
+      // quad are issued before its current quad is processed (two quads per thread in flight)
+      const uint4 *kp = reinterpret_cast<const uint4 *>(keys) + q_begin + tid;
+      const ulonglong2 *bp = reinterpret_cast<const ulonglong2 *>(bits) + 2 * (q_begin + tid);
+      int32_t ra = head + 4 * tid;
+      uint4 ka = make_uint4(0, 0, 0, 0), kb = ka;
+      ulonglong2 a01 = make_ulonglong2(0, 0), a23 = a01, b01 = a01, b23 = a01;
+      if (tid < nq) { ka = ld_stream(kp); a01 = ld_stream(bp); a23 = ld_stream(bp + 1); }
+      for (int i = tid; i < nq; i += 2 * K3_THREADS) {
+        const bool vb = i + K3_THREADS < nq, vc = i + 2 * K3_THREADS < nq;
         if (vb) {
-          kb = __ldcs(reinterpret_cast<const uint4 *>(keys) + qb);
-          b01 = __ldcs(reinterpret_cast<const ulonglong2 *>(bits) + 2 * qb);
-          b23 = __ldcs(reinterpret_cast<const ulonglong2 *>(bits) + 2 * qb + 1);
+          kb = ld_stream(kp + K3_THREADS);
+          b01 = ld_stream(bp + 2 * K3_THREADS);
+          b23 = ld_stream(bp + 2 * K3_THREADS + 1);
         }
-        const int32_t ra = head + (int32_t)((qa - q_begin) << 2);
-        if (va) process(ra, ka, a01, a23);
+        process(ra, ka, a01, a23);
+        if (vc) {
+          ka = ld_stream(kp + 2 * K3_THREADS);
+          a01 = ld_stream(bp + 4 * K3_THREADS);
+          a23 = ld_stream(bp + 4 * K3_THREADS + 1);
+        }
         if (vb) process(ra + 4 * K3_THREADS, kb, b01, b23);
+        kp += 2 * K3_THREADS;
+        bp += 4 * K3_THREADS;
+        ra += 8 * K3_THREADS;
       }
       __syncthreads();
 
@@ -168,7 +201,7 @@ voxel_and_popc_kernel(const uint32_t *__restrict__ keys, const uint64_t *__restr
         const uint32_t a = (uint32_t)(a64 - c_lo), b = (uint32_t)(b64 - c_lo);   // [a, b), b > a
         const uint32_t w0 = a >> 5, w1 = (b - 1) >> 5;
         for (uint32_t w = w0; w <= w1; w++) {
-          uint32_t m = hitw[w];
+          uint32_t m = s_mem[hit_off + w];
           if (w == w0) m &= 0xffffffffu << (a & 31);
           if (w == w1) m &= 0xffffffffu >> (31 - ((b - 1) & 31));
           if (m) { own = true; break; }
@@ -242,7 +275,8 @@ int setstore_grow_blocks(irt_ctx *ctx, irt_setstore *s, int64_t need_blocks, int
 
 int setstore_finalize(irt_ctx *ctx, irt_setstore *s, int64_t n_sets, int64_t n_blocks,
                       cudaStream_t st) {
-  (void)ctx; (void)st;
+  // K3 reads whole 16-byte quads: the (clipped) leaves past the end of the store must hold valid keys
+  if (s->d_keys) IRT_CUDA(ctx, cudaMemsetAsync(s->d_keys + n_blocks, 0, 4 * sizeof(uint32_t), st));
   s->n_sets = n_sets;
   s->n_blocks = n_blocks;
   return IRT_OK;
@@ -463,17 +497,14 @@ static int check_sets_impl(irt_ctx *ctx, const irt_setstore *store, const irt_en
   const int64_t max_blocks = (int64_t)ctx->sm_count * 8;  // ... persistent over 8 CTAs per SM
   if (blocks > max_blocks) blocks = max_blocks;
   const size_t smem = (size_t)2 * K3_BM_WORDS * 4 + (occ_smem ? (size_t)occ_words * 4 : 0);
-  // keys are < Nb^3 (a power of two); the mask only keeps the (clipped) leaves that a quad reads
-  // beyond the end of the store inside the tables
-  const uint32_t key_mask = (uint32_t)(env->n_blocks_total - 1);
 #define K3_LAUNCH(OS, ST)                                                                          \
   do {                                                                                             \
     auto kfn = voxel_and_popc_kernel<OS, ST>;                                                      \
     if (smem > 48 * 1024)                                                                          \
       IRT_CUDA(ctx, cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
     kfn<<<(unsigned)blocks, K3_THREADS, smem, st>>>(store->d_keys, store->d_bits, store->d_offsets, \
-                                                    env->d_blocks, env->d_occ, occ_words, key_mask, \
-                                                    begin, end, d_verdict, d_stats);               \
+                                                    env->d_blocks, env->d_occ, occ_words, begin,   \
+                                                    end, d_verdict, d_stats);                      \
   } while (0)
   if (occ_smem) {
     if (d_stats) K3_LAUNCH(true, true); else K3_LAUNCH(true, false);
