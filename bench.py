@@ -111,6 +111,55 @@ def cpu_fk_rate(spec, n_tendons, seconds, threads=None, stream=900):
     return done / el, nt, done, el
 
 
+def cpu_edge_check_rate(prm, wl, g, env_blocks, gpu_verdicts, seconds, sample=200000):
+    """edges/s of the reference's TreeNode::collides over the first `sample` cached edge sets (kind
+    "reference"), or of the oracle port when oracle/_ref was not shipped (kind "port")."""
+    from oracle import ref as oref
+    Ng, Nb = g["Ng"], g["Ng"] // 4
+    off, keys, bits = prm.edge_store.export_csr()
+    m = int(min(sample, len(off) - 1))
+    off = off[:m + 1].copy()
+    keys, bits = keys[:int(off[-1])], bits[:int(off[-1])]
+    nt = os.cpu_count() or 1
+    ekeys = np.nonzero(env_blocks)[0].astype(np.uint32)
+    ex, ey, ez = wl.morton_decode(ekeys, Nb)
+    if oref.available():
+        bx, by, bz = wl.morton_decode(keys, Nb)
+        env = oref.RefTree(Ng)
+        for x, y, z, k in zip(ex.tolist(), ey.tolist(), ez.tolist(), ekeys.tolist()):
+            env.set_block(x, y, z, int(env_blocks[k]))
+        sets = oref.RefSets(Ng, off, bx, by, bz, bits)          # untimed: the planner keeps them cached
+        run = lambda: sets.check(env, nt)
+        kind, what = "reference", "collision/detail/TreeNode.h (TreeNode::collides) compiled as is, OpenMP loop"
+    else:
+        from oracle.oracle import Oracle
+        orc = Oracle("fast")
+        og = orc.grid(Ng, g["lim"], g["inv_rot"])
+        store = orc.setstore(og, m)
+        for i in range(m):
+            t = store.get(i)
+            for j in range(int(off[i]), int(off[i + 1])):
+                x, y, z = (int(v[0]) for v in wl.morton_decode(keys[j:j + 1], Nb))
+                t.set_block(x, y, z, int(bits[j]))
+        env = orc.octree(og)
+        for x, y, z, k in zip(ex.tolist(), ey.tolist(), ez.tolist(), ekeys.tolist()):
+            env.set_block(x, y, z, int(env_blocks[k]))
+        run = lambda: orc.check_sets_batch(store, env, nthreads=nt).astype(bool)
+        kind, what = "port", "oracle restatement of TreeNode::collides, OpenMP loop"
+    v = run()                                                   # warm-up + parity with the GPU verdicts
+    equal = bool(np.array_equal(v, np.asarray(gpu_verdicts[:m]).astype(bool)))
+    reps, t0 = 0, time.perf_counter()
+    while True:
+        run()
+        reps += 1
+        el = time.perf_counter() - t0
+        if el >= seconds or reps >= 5000:
+            break
+    return {"value": m * reps / el, "unit": "edges/s", "cores": nt, "kind": kind,
+            "sample": "first %d cached edge sets of this roadmap, %d sweeps in %.1f s; %s" % (m, reps, el, what),
+            "verdicts_equal_gpu": equal}
+
+
 def knn_edges_gpu(torch, states_np, spec, k, device):
     """undirected k-nearest-neighbour edges under the compound-space metric of Problem.cpp:118-141
     (exact, brute force on the GPU with torch: benchmark INPUT generation, not the hot path)."""
@@ -352,13 +401,20 @@ def main():
                 prm.edge_store.check_dev(prm.env, d_words, 0, hi - lo, stream=sptr)
             return gather_verdict_words(d_words, dist if world > 1 else None)
 
+        # L2 rule: the sweep's input (the set store of this rank) is >> the 126 MB L2 at the default
+        # roadmap size, so consecutive sweeps cannot hit in L2 and no flush write is needed (a flush would
+        # leave ~100 MB of dirty lines whose write-back competes with the sweep's reads); smaller stores
+        # (--roadmap-vertices below ~100k) are flushed.
+        k3_flush = (prm.edge_store.algorithmic_bytes() if hi > lo else 0) < 4 * 126e6
         for _ in range(args.warmup):
-            flush.zero_()
+            if k3_flush:
+                flush.zero_()
             k3_step()
         barrier()
         ev3 = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
         for a, b in ev3:
-            flush.zero_()
+            if k3_flush:
+                flush.zero_()
             a.record(stream)
             k3_step()
             b.record(stream)
@@ -391,7 +447,9 @@ def main():
                                       if prof.get("k3_dram_bytes_over_algorithmic") else None)),
                          "traffic_source": prof.get("k3_source"),
                          "peak_source": hbm_src, "algorithmic_bytes": alg_bytes,
-                         "note": "duration includes the verdict memset and (N>1) the NCCL all_gather"},
+                         "l2": ("512 MB flush write between timed sweeps" if k3_flush else
+                                "no flush: the store streamed per sweep (%.0f MB) is >> L2 (126 MB)" % (alg_bytes / 1e6)),
+                         "note": "duration = the whole sweep step (K3 launch; N>1: + the NCCL all_gather)"},
         }
         # ---- C5: interactive replanning tick = env change + upload + vertex sweep + edge sweep + gather
         nvt = len(prm.states)
@@ -436,6 +494,13 @@ def main():
         edge_check["valid_edge_fraction"] = float(verd.mean())
         lo_w = irt_b200.unpack_verdicts(d_words.cpu().numpy().view(np.uint32), hi - lo) if hi > lo else np.zeros(0)
         edge_check["collision_fraction"] = float(lo_w.mean()) if hi > lo else None
+
+        # ---- CPU baseline of the edge check (rank 0 at N=1 only): the reference's own octree code
+        # (oracle/_ref/libtreenode_ref.so = collision/detail/TreeNode.h compiled as is) running the OpenMP
+        # loop of VoxelCachedLazyPRM.cpp:1584-1591 over a bounded sample of the same cached edge sets
+        if rank == 0 and world == 1 and args.cpu_seconds > 0 and hi > lo:
+            edge_check["cpu_baseline"] = cpu_edge_check_rate(prm, wl, g, env_blocks, lo_w,
+                                                             min(args.cpu_seconds, 10.0))
 
     # ---------------- CPU baseline (rank 0 at N=1 only) ------------------------------------------
     cpu = None

@@ -72,6 +72,7 @@ __global__ void count_nonzero_kernel(const uint64_t *__restrict__ blocks, int64_
 // double-buffered by tile parity so a chunk costs two __syncthreads.
 constexpr int K3_CHUNK_LEAVES = 32768;                      // hit-bitmap capacity per buffer (4 KiB)
 constexpr int K3_BM_WORDS = K3_CHUNK_LEAVES / 32 + 2;       // +1 straddle word, +1 pad
+constexpr int K3_SMEM_FIXED_WORDS = 3 * K3_BM_WORDS + (3 * K3_BM_WORDS & 1) + 2 * 2 * (K3_THREADS + 2);
 
 // predicated 8-byte read-only load: the four environment look-ups of a quad are issued back to back
 // (no branch per look-up), so their latencies overlap; lanes whose leaf is in an empty environment
@@ -82,6 +83,11 @@ __device__ __forceinline__ uint64_t ld_env_if(const uint64_t *p, uint32_t pred) 
       : "=l"(v) : "r"(pred), "l"(p));
   return v;
 }
+
+__device__ __forceinline__ void cp_async8(void *smem_dst, const void *gsrc) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
 // streaming 16-byte loads (evict-first); volatile keeps the issue order of the software pipeline
 __device__ __forceinline__ uint4 ld_stream(const uint4 *p) {
@@ -96,41 +102,62 @@ __device__ __forceinline__ ulonglong2 ld_stream(const ulonglong2 *p) {
 }
 
 template <bool OCC_SMEM, bool STATS>
-__global__ void __launch_bounds__(K3_THREADS)
+__global__ void __launch_bounds__(K3_THREADS, 4)
 voxel_and_popc_kernel(const uint32_t *__restrict__ keys, const uint64_t *__restrict__ bits,
                       const uint64_t *__restrict__ offsets, const uint64_t *__restrict__ env,
                       const uint32_t *__restrict__ occ, int occ_words,
                       int64_t set_begin, int64_t set_end, uint32_t *__restrict__ verdict,
                       unsigned long long *__restrict__ stats) {
-  // [0, 2*K3_BM_WORDS): two hit bitmaps; [2*K3_BM_WORDS, +occ_words): occupancy bitmap (OCC_SMEM)
-  extern __shared__ uint32_t s_mem[];
-  constexpr int OCC_OFF = 2 * K3_BM_WORDS;
-  if (OCC_SMEM) {
-    for (int i = threadIdx.x; i < occ_words; i += K3_THREADS) s_mem[OCC_OFF + i] = occ[i];
-  }
+  // [0, 3*K3_BM_WORDS): three hit bitmaps (rotating, so a chunk costs ONE __syncthreads: the buffer
+  // cleared during chunk k was last read two barriers ago); then two tiles of set offsets
+  // (cp.async prefetch of the next tile's CSR offsets while this tile streams); then the
+  // occupancy bitmap (OCC_SMEM)
+  extern __shared__ __align__(16) uint32_t s_mem[];
+  constexpr int OFF_OFF = 3 * K3_BM_WORDS + (3 * K3_BM_WORDS & 1);          // 8-byte aligned
+  constexpr int OCC_OFF = OFF_OFF + 2 * 2 * (K3_THREADS + 2);
+  uint64_t *s_off = reinterpret_cast<uint64_t *>(s_mem + OFF_OFF);          // [2][K3_THREADS + 2]
   const int tid = threadIdx.x;
   const int64_t n_sets = set_end - set_begin;
   const int64_t ntiles = (n_sets + K3_THREADS - 1) / K3_THREADS;
   const int64_t nwords_out = (n_sets + 31) >> 5;
   unsigned long long vox = 0, nhit = 0;
-  int parity = 0;
+
+  // asynchronous copy of the offsets of tile t into s_off[buf]: entry i = offsets[s0 + min(i, n_valid)]
+  auto prefetch_offsets = [&](int64_t t, int buf) {
+    const int64_t s0 = set_begin + t * K3_THREADS;
+    const int64_t n_valid = min((int64_t)K3_THREADS, set_end - s0);
+    uint64_t *dst = s_off + buf * (K3_THREADS + 2);
+    cp_async8(dst + tid, offsets + s0 + min((int64_t)tid, n_valid));
+    if (tid == 0) cp_async8(dst + K3_THREADS, offsets + s0 + n_valid);
+  };
+
+  if ((int64_t)blockIdx.x < ntiles) prefetch_offsets(blockIdx.x, 0);
+  if (OCC_SMEM) {
+    for (int i = tid; i < occ_words; i += K3_THREADS) s_mem[OCC_OFF + i] = occ[i];
+  }
+  for (int i = tid; i < K3_BM_WORDS; i += K3_THREADS) s_mem[i] = 0;
+  cp_async_wait_all();
+  __syncthreads();
+  int hb = 0, mb = 0;   // current hit bitmap / offsets buffer
 
   for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-    const int64_t s0 = set_begin + tile * K3_THREADS;
-    const int64_t sl = s0 + tid;
-    const uint64_t t_lo = offsets[s0];
-    const uint64_t t_hi = offsets[min(s0 + (int64_t)K3_THREADS, set_end)];
-    uint64_t lo = t_hi, hi = t_hi;
-    if (sl < set_end) { lo = offsets[sl]; hi = offsets[sl + 1]; }
+    const uint64_t *my_off = s_off + mb * (K3_THREADS + 2);
+    const uint64_t t_lo = my_off[0], t_hi = my_off[K3_THREADS];
+    const uint64_t lo = my_off[tid], hi = my_off[tid + 1];
+    if (tile + gridDim.x < ntiles) prefetch_offsets(tile + gridDim.x, mb ^ 1);
+    mb ^= 1;
     bool own = false;
+    if (t_lo == t_hi) {   // a tile of empty sets: no chunk below, but the prefetch still needs its barrier
+      cp_async_wait_all();
+      __syncthreads();
+    }
 
     for (uint64_t c_lo = t_lo; c_lo < t_hi; c_lo += K3_CHUNK_LEAVES) {   // block-uniform
       const uint64_t c_hi = min(c_lo + (uint64_t)K3_CHUNK_LEAVES, t_hi);
       const uint32_t c_n = (uint32_t)(c_hi - c_lo);
-      const int hit_off = parity * K3_BM_WORDS;
-      parity ^= 1;
-      for (uint32_t i = tid; i < (c_n + 31) / 32 + 1; i += K3_THREADS) s_mem[hit_off + i] = 0;
-      __syncthreads();   // also orders the occupancy fill before its first use
+      const int hit_off = hb * K3_BM_WORDS;
+      hb = (hb == 2) ? 0 : hb + 1;
+      const int next_hit_off = hb * K3_BM_WORDS;
 
       const int64_t q_begin = (int64_t)(c_lo >> 2);
       const int nq = (int)((int64_t)((c_hi + 3) >> 2) - q_begin);          // <= 8193 quads
@@ -193,6 +220,8 @@ voxel_and_popc_kernel(const uint32_t *__restrict__ keys, const uint64_t *__restr
         bp += 4 * K3_THREADS;
         ra += 8 * K3_THREADS;
       }
+      for (int i = tid; i < K3_BM_WORDS; i += K3_THREADS) s_mem[next_hit_off + i] = 0;
+      cp_async_wait_all();
       __syncthreads();
 
       // does any hit bit fall into this thread's set range, clipped to the chunk?
@@ -496,7 +525,7 @@ static int check_sets_impl(irt_ctx *ctx, const irt_setstore *store, const irt_en
   int64_t blocks = (n + K3_THREADS - 1) / K3_THREADS;     // one CTA per tile of 256 sets ...
   const int64_t max_blocks = (int64_t)ctx->sm_count * 8;  // ... persistent over 8 CTAs per SM
   if (blocks > max_blocks) blocks = max_blocks;
-  const size_t smem = (size_t)2 * K3_BM_WORDS * 4 + (occ_smem ? (size_t)occ_words * 4 : 0);
+  const size_t smem = (size_t)K3_SMEM_FIXED_WORDS * 4 + (occ_smem ? (size_t)occ_words * 4 : 0);
 #define K3_LAUNCH(OS, ST)                                                                          \
   do {                                                                                             \
     auto kfn = voxel_and_popc_kernel<OS, ST>;                                                      \

@@ -71,6 +71,12 @@ class RefTree:
             L.tnref_check_csr.argtypes = [vp, u64, C.POINTER(u64), C.POINTER(C.c_uint8),
                                           C.POINTER(C.c_uint8), C.POINTER(C.c_uint8),
                                           C.POINTER(u64), C.POINTER(C.c_uint8)]
+            L.tnref_sets_build.restype = vp
+            L.tnref_sets_build.argtypes = [u64, u64, C.POINTER(u64), C.POINTER(C.c_uint8),
+                                           C.POINTER(C.c_uint8), C.POINTER(C.c_uint8), C.POINTER(u64)]
+            L.tnref_sets_free.argtypes = [vp]
+            L.tnref_sets_check.restype = C.c_int
+            L.tnref_sets_check.argtypes = [vp, vp, C.POINTER(C.c_uint8), C.c_int]
             cls._lib = L
         return cls._lib
 
@@ -153,6 +159,34 @@ class RefTree:
                                         by.ctypes.data_as(u8p), bz.ctypes.data_as(u8p),
                                         bits.ctypes.data_as(u64p), out.ctypes.data_as(u8p))
         assert rc == 0
+        return out.astype(bool)
+
+
+class RefSets:
+    """Cached voxel sets kept as reference TreeNodes (the form the reference's planner stores them in);
+    check(env) is the OpenMP loop of VoxelCachedLazyPRM.cpp:1584-1591."""
+
+    def __init__(self, Ng, off, bx, by, bz, bits):
+        off = np.ascontiguousarray(off, dtype=np.uint64)
+        bx, by, bz = (np.ascontiguousarray(a, dtype=np.uint8) for a in (bx, by, bz))
+        bits = np.ascontiguousarray(bits, dtype=np.uint64)
+        self.n = len(off) - 1
+        u8p, u64p = C.POINTER(C.c_uint8), C.POINTER(C.c_uint64)
+        self.h = RefTree.lib().tnref_sets_build(int(Ng), self.n, off.ctypes.data_as(u64p),
+                                                bx.ctypes.data_as(u8p), by.ctypes.data_as(u8p),
+                                                bz.ctypes.data_as(u8p), bits.ctypes.data_as(u64p))
+        if not self.h:
+            raise ValueError("unsupported Ng %r" % (Ng,))
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            RefTree.lib().tnref_sets_free(self.h)
+            self.h = None
+
+    def check(self, env, nthreads=1):
+        out = np.zeros(self.n, dtype=np.uint8)
+        RefTree.lib().tnref_sets_check(env.h, self.h, out.ctypes.data_as(C.POINTER(C.c_uint8)),
+                                       int(nthreads))
         return out.astype(bool)
 
 

@@ -148,4 +148,38 @@ int tnref_check_csr(const void *env, uint64_t n, const uint64_t *off, const uint
   return 0;
 }
 
+// Timing form of the same loop: the sets are built once (untimed by the caller) and kept as trees,
+// as the reference keeps them in its vertex/edge properties (VoxelCachedLazyPRM.h:141,165-179);
+// tnref_sets_check then is the `#pragma omp parallel for` of VoxelCachedLazyPRM.cpp:1584-1591 with
+// nothing but TreeNode::collides inside.
+struct SetArray { std::vector<AnyTree *> sets; };
+
+void *tnref_sets_build(uint64_t Ng, uint64_t n, const uint64_t *off, const uint8_t *bx,
+                       const uint8_t *by, const uint8_t *bz, const uint64_t *bits) {
+  SetArray *a = new SetArray();
+  a->sets.resize(n, nullptr);
+  for (uint64_t i = 0; i < n; i++) {
+    AnyTree *s = make(Ng);
+    if (!s) { delete a; return nullptr; }
+    for (uint64_t k = off[i]; k < off[i + 1]; k++) s->set_block(bx[k], by[k], bz[k], bits[k]);
+    a->sets[i] = s;
+  }
+  return a;
+}
+void tnref_sets_free(void *h) {
+  SetArray *a = static_cast<SetArray *>(h);
+  if (!a) return;
+  for (AnyTree *s : a->sets) delete s;
+  delete a;
+}
+int tnref_sets_check(const void *env, const void *h, uint8_t *verdict, int nthreads) {
+  const AnyTree *e = static_cast<const AnyTree *>(env);
+  const SetArray *a = static_cast<const SetArray *>(h);
+  const int64_t n = (int64_t)a->sets.size();
+  (void)nthreads;
+#pragma omp parallel for schedule(static) num_threads(nthreads)
+  for (int64_t i = 0; i < n; i++) verdict[i] = (uint8_t)e->collides(*a->sets[i]);
+  return 0;
+}
+
 }  // extern "C"
