@@ -3,7 +3,8 @@
 TEST INFRASTRUCTURE ONLY.  May be imported by tests/, __graft_entry__.smoke() and
 bench.py's cpu_baseline / --impl reference legs; never by the product package.
 See oracle/tendon_oracle.h for what is restated and the parity status
-("parity unpinned by the reference": the reference ships no tests or fixtures).
+(partly pinned by the reference's own code in oracle/_ref, see oracle/ref.py; "parity unpinned by
+the reference" for the parts that are restated only).
 """
 import ctypes as C
 import os

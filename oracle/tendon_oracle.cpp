@@ -5,7 +5,8 @@
  * following the cited reference lines operation by operation (own 3-vector and
  * 3x3 helpers in place of Eigen, own RK4 in place of Boost.odeint, own
  * interpolation / segment count in place of OMPL).  See tendon_oracle.h for the
- * parity status ("parity unpinned by the reference": no reference tests exist).
+ * parity status (partly pinned by pieces of the reference compiled into oracle/_ref;
+ * "parity unpinned by the reference" for the rest).
  *
  * Citations are relative to /root/reference/cpp/src/.
  */

@@ -8,14 +8,23 @@
  * it.  The product path (interactive-rate-tendons_b200/) never links, imports or
  * calls anything in this directory.
  *
- * PARITY STATUS: "parity unpinned by the reference" -- the reference ships no
- * tests, fixtures or golden vectors and cannot be compiled in this image (needs
- * Eigen3, Boost.odeint, OMPL, FCL, ITK ...).  The oracle is pinned instead by
+ * PARITY STATUS.  The reference ships no tests, fixtures or golden vectors and
+ * cannot be compiled as a whole in this image (needs Eigen3, Boost.odeint, OMPL,
+ * FCL, ITK ...).  The pieces of it that DO compile here pin this oracle
+ * (oracle/_ref, oracle/ref.py, tests/test_oracle_vs_reference.py):
+ *   - collision/detail/TreeNode.h as is: octree storage, set algebra, collides,
+ *     visit_leaves order;
+ *   - tendon_deriv.cpp, solve_initial_bending.cpp, get_r_info.cpp and
+ *     collision_primitives.{h,cpp}, unmodified, against a stand-in for the Eigen
+ *     subset they use (pins formulas / operand order / control flow, not Eigen's
+ *     rounding): routing bit-exact, derivative identical, same fixed-point
+ *     iteration counts.
+ * "Parity unpinned by the reference" still holds for what is restated only: the
+ * RK4 stepping of Boost.odeint and t_range, calc_point_forces, home lengths,
+ * collides_self, VoxelOctree::add_line / find_cell, the swept-volume driver and
+ * OMPL 1.5 validSegmentCount / interpolate.  Those are pinned by
  *   (1) analytic known-answer tests (tests/test_oracle_kat.py) and
  *   (2) an independent numpy + mpmath restatement (oracle/fk_second_opinion.py).
- * Third-party arithmetic restated from documented behaviour (unverified against
- * source): Eigen 3 fixed-size products / inverse / normalized, Boost.odeint
- * runge_kutta4 + integrate_times, OMPL 1.5 validSegmentCount / interpolate.
  *
  * All file:line citations are relative to /root/reference/cpp/src/.
  */
