@@ -68,7 +68,7 @@ typedef enum irt_status {
 #define IRT_FLAG_SELF_COLLISION 4u /* collides_self (collision/collision.cpp:6-46) */
 #define IRT_FLAG_OUT_OF_DOMAIN 8u  /* find_cell would throw std::domain_error */
 #define IRT_FLAG_PARTIAL 16u       /* edge: PartialVoxelization::is_fully_valid == false */
-#define IRT_FLAG_BAD_STATE 32u     /* retraction < 0 or NaN: outside the reference's state space */
+#define IRT_FLAG_BAD_STATE 32u     /* retraction NaN, or so far below 0 that the grid exceeds max_points: outside the reference's state space */
 #define IRT_FLAG_CAPACITY 64u      /* per-item scratch capacity exceeded (result incomplete) */
 #define IRT_FLAG_ENV_COLLISION 128u /* until-invalid mode: the sample's own voxels hit the environment */
 
@@ -159,6 +159,25 @@ int irt_fk_batch(irt_ctx *ctx, const irt_robot *rb, const double *states, int st
                  int64_t n, int cap_pts, const irt_fk_outputs *out);
 int irt_fk_batch_dev(irt_ctx *ctx, const irt_robot *rb, const double *d_states, int state_size,
                      int64_t n, int cap_pts, const irt_fk_outputs *d_out, void *stream);
+/* Batched finite-difference tip Jacobians: what the reference's IK and tip
+ * controllers compute with one FK per perturbed parameter.  J is [n][3][S] (row i of seed k at
+ * J[(k*3+i)*S + j], levmar's jac[i*m+j] layout), tips is [n][3] (may be NULL): the value the
+ * differences are taken from.  One K1 launch over n*(S+1) or n*(2S+1) states.
+ *   IRT_JAC_FORWARD_FIXED   tip_control::Jacobian (tip-control/tip_control.cpp:243-265):
+ *                           (fk(state + delta e_j).back() - tip) / delta
+ *   IRT_JAC_LEVMAR_FORWARD  levmar-2.6 dlevmar_fdif_forw_jac_approx (3rdparty/levmar-2.6/misc_core.c:137-172)
+ *   IRT_JAC_LEVMAR_CENTRAL  dlevmar_fdif_cent_jac_approx (misc_core.c:175-211), the form
+ *                           tip_control::inverse_kinematics_impl asks for (tip_control.cpp:85)
+ * The two levmar modes differentiate the reference's wrapper fk_wrap (tip_control.cpp:92-122):
+ * a retraction beyond L evaluates to (0, 0, L - s).  d = max(|1e-4 p_j|, delta). */
+#define IRT_JAC_FORWARD_FIXED 0
+#define IRT_JAC_LEVMAR_FORWARD 1
+#define IRT_JAC_LEVMAR_CENTRAL 2
+int irt_fk_tip_jacobian_batch(irt_ctx *ctx, const irt_robot *rb, const double *states, int state_size,
+                              int64_t n, int mode, double delta, double *tips, double *J);
+int irt_fk_tip_jacobian_batch_dev(irt_ctx *ctx, const irt_robot *rb, const double *d_states,
+                                  int state_size, int64_t n, int mode, double delta, double *d_tips,
+                                  double *d_J, void *stream);
 /* TendonRobot::home_shape(state).L_i (tendon/TendonRobot.cpp:249-314), host arrays */
 int irt_home_lengths_batch(irt_ctx *ctx, const irt_robot *rb, const double *states,
                            int state_size, int64_t n, double *L_i);

@@ -31,6 +31,7 @@ FLAG_SELF_COLLISION = 4
 FLAG_OUT_OF_DOMAIN = 8
 FLAG_PARTIAL = 16
 FLAG_BAD_STATE = 32
+JAC_FORWARD_FIXED, JAC_LEVMAR_FORWARD, JAC_LEVMAR_CENTRAL = 0, 1, 2
 FLAG_CAPACITY = 64
 FLAG_ENV_COLLISION = 128
 INVALID_MASK = FLAG_NONCONVERGED | FLAG_LENGTH_LIMIT | FLAG_SELF_COLLISION | FLAG_BAD_STATE
@@ -94,6 +95,7 @@ ABI_SYMBOLS = [
     "irt_ctx_device", "irt_ctx_synchronize", "irt_ctx_launch_count", "irt_measure_fp64_peak",
     "irt_robot_create", "irt_robot_destroy", "irt_robot_state_size", "irt_robot_max_points",
     "irt_fk_batch", "irt_fk_batch_dev", "irt_home_lengths_batch",
+    "irt_fk_tip_jacobian_batch", "irt_fk_tip_jacobian_batch_dev",
     "irt_env_create", "irt_env_destroy", "irt_env_update", "irt_env_update_dev",
     "irt_env_update_sparse", "irt_env_nblocks",
     "irt_env_dilate", "irt_env_dilate_sphere", "irt_env_remove_interior", "irt_env_download",
@@ -138,6 +140,8 @@ def lib():
         "irt_fk_batch": (i32, [vp, vp, vp, i32, i64, i32, C.POINTER(FkOutputs)]),
         "irt_fk_batch_dev": (i32, [vp, vp, vp, i32, i64, i32, C.POINTER(FkOutputs), vp]),
         "irt_home_lengths_batch": (i32, [vp, vp, vp, i32, i64, vp]),
+        "irt_fk_tip_jacobian_batch": (i32, [vp, vp, vp, i32, i64, i32, C.c_double, vp, vp]),
+        "irt_fk_tip_jacobian_batch_dev": (i32, [vp, vp, vp, i32, i64, i32, C.c_double, vp, vp, vp]),
         "irt_env_create": (i32, [vp, C.POINTER(Grid), C.POINTER(vp)]),
         "irt_env_destroy": (None, [vp]),
         "irt_env_update": (i32, [vp, vp, vp]),
@@ -331,6 +335,20 @@ class Robot:
         self.ctx.check(self.ctx.L.irt_fk_batch_dev(
             self.ctx.h, self.h, _ptr(d_states), self.state_size, int(n), cap, C.byref(o),
             C.c_void_p(stream) if stream else None))
+
+    def tip_jacobian_batch(self, states, mode=JAC_LEVMAR_CENTRAL, delta=1e-4):
+        """Finite-difference tip Jacobians of every row of `states` in one FK batch: returns
+        (tips [n][3], J [n][3][S]).  mode: JAC_FORWARD_FIXED = tip_control::Jacobian
+        (tip-control/tip_control.cpp:243-265); JAC_LEVMAR_FORWARD / JAC_LEVMAR_CENTRAL = the rule of
+        levmar-2.6 behind tip_control::inverse_kinematics (misc_core.c:137-211)."""
+        states = _np(states, np.float64)
+        if states.ndim != 2:
+            raise IrtError(IRT_ERR_INVALID_ARGUMENT, "states must be [n][S]")
+        n, S = states.shape
+        tips, J = np.zeros((n, 3)), np.zeros((n, 3, S))
+        self.ctx.check(self.ctx.L.irt_fk_tip_jacobian_batch(
+            self.ctx.h, self.h, _ptr(states), S, n, int(mode), float(delta), _ptr(tips), _ptr(J)))
+        return tips, J
 
     def home_lengths(self, states):
         states = _np(states, np.float64)

@@ -383,7 +383,12 @@ fk_rk4_fp64_kernel(const RobotDev rb, const double *__restrict__ states, int sta
 
   uint32_t flags = 0;
   bool active = in_range;
-  if (RETRACT && !(s_start >= 0.0)) {  // s < 0 or NaN: outside the reference's state space
+  // The reference integrates from any s_start (TendonRobot.cpp:345-359 only truncates at L).  A base
+  // slightly before 0 is what the finite-difference Jacobians of its IK produce (state - d), so
+  // s < 0 is supported as long as the grid still fits max_points (K <= Kfull below; the first gap is
+  // always in [dL/2, 3dL/2), so the two head steps suffice); NaN or anything further out is outside the
+  // reference's state space (OMPL bounds [0, L]) and is flagged.
+  if (RETRACT && !(s_start >= -rb.dL)) {
     flags |= IRT_FLAG_BAD_STATE;
     active = false;
   }
@@ -395,7 +400,11 @@ fk_rk4_fp64_kernel(const RobotDev rb, const double *__restrict__ states, int sta
     if (RETRACT) {
       const double lim = rb.L - (rb.dL / 2);
       for (double pacc = s_start; pacc <= lim; pacc += rb.dL) K++;
-      if (K > rb.Kfull) K = rb.Kfull;
+      if (K > rb.Kfull) {   // only possible for s < 0: one grid point more than the outputs hold
+        flags |= IRT_FLAG_BAD_STATE;
+        active = false;
+        K = 0;
+      }
     } else {
       K = rb.Kfull;
     }
@@ -617,11 +626,11 @@ __global__ void fk_count_nodes_kernel(const RobotDev rb, const double *__restric
     // bucket key = number of RK4 steps the configuration will take (K - 1 regular + 1 or 2 head)
     double s = states[i * state_size + state_size - 1];
     int T = 0;
-    if (s >= 0.0 && s < rb.L) {
+    if (s >= -rb.dL && s < rb.L) {
       int K = 0;
       const double lim = rb.L - (rb.dL / 2);
       for (double p = s; p <= lim; p += rb.dL) K++;
-      if (K > rb.Kfull) K = rb.Kfull;
+      if (K > rb.Kfull) K = 0;   // flagged IRT_FLAG_BAD_STATE by the FK kernel
       if (K >= 1) {
         const double t1 = rb.node_t[K - 1];
         const double h0 = fmin(rb.dL, t1 - s);

@@ -275,6 +275,42 @@ private:
 
 }  // namespace tendon
 
+/// Batched forms of the finite-difference Jacobians behind the reference's IK and tip controllers
+/// (SURVEY 8(f) row 3).  J of seed k is returned row-major 3 x S (J[i * S + j] = d tip_i / d state_j).
+namespace tip_control {
+
+/// tip_control::Jacobian (tip-control/tip_control.cpp:243-265) for many states at once:
+/// forward difference with the fixed step `dist` from ps = forward_kinematics(state).back()
+inline std::vector<std::vector<double>> Jacobian_batch(const tendon::TendonRobot &robot, double dist,
+                                                       const std::vector<std::vector<double>> &states,
+                                                       std::vector<collision::Point> *tips = nullptr,
+                                                       int mode = IRT_JAC_FORWARD_FIXED) {
+  const size_t S = robot.state_size(), n = states.size();
+  for (auto &st : states)
+    if (st.size() != S) throw std::invalid_argument("State is not the right size");
+  std::vector<double> flat(n * S), tip(n * 3), J(n * 3 * S);
+  for (size_t i = 0; i < n; i++) std::copy(states[i].begin(), states[i].end(), flat.begin() + i * S);
+  irt::check(robot.ctx(), irt_fk_tip_jacobian_batch(robot.ctx(), robot.handle(), flat.data(), (int)S,
+                                                    (int64_t)n, mode, dist, tip.data(), J.data()));
+  std::vector<std::vector<double>> out(n);
+  for (size_t i = 0; i < n; i++) out[i].assign(J.begin() + i * 3 * S, J.begin() + (i + 1) * 3 * S);
+  if (tips) {
+    tips->resize(n);
+    for (size_t i = 0; i < n; i++) (*tips)[i] = {tip[3 * i], tip[3 * i + 1], tip[3 * i + 2]};
+  }
+  return out;
+}
+
+/// the Jacobian levmar's dlevmar_bc_dif builds inside tip_control::inverse_kinematics
+/// (central differences, d = max(|1e-4 p_j|, delta); tip_control.cpp:85, levmar-2.6 misc_core.c:175-211)
+inline std::vector<std::vector<double>> levmar_jacobian_batch(const tendon::TendonRobot &robot, double delta,
+                                                              const std::vector<std::vector<double>> &states,
+                                                              std::vector<collision::Point> *tips = nullptr) {
+  return Jacobian_batch(robot, delta, states, tips, IRT_JAC_LEVMAR_CENTRAL);
+}
+
+}  // namespace tip_control
+
 namespace collision {
 
 /// Value-type mirror of collision::VoxelOctree: the sparse set of occupied 4x4x4 leaf blocks.

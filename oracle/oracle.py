@@ -243,6 +243,13 @@ class Oracle:
                     u_f=np.array(out.u_f[:]), v_i=np.array(out.v_i[:]), v_f=np.array(out.v_f[:]),
                     converged=bool(out.converged), iters=out.iters, nsteps=out.nsteps, _raw=out)
 
+    def tip_jacobian(self, rb, state, mode, delta):
+        state = np.ascontiguousarray(state, dtype=np.float64)
+        m = self.state_size(rb)
+        tip, J = np.zeros(3), np.zeros((3, m))
+        self.lib.orc_tip_jacobian(C.byref(rb), _dp(state), C.c_int(mode), C.c_double(delta), _dp(tip), _dp(J))
+        return tip, J
+
     def home_lengths(self, rb, s):
         out = np.zeros(rb.n_tendons)
         self.lib.orc_home_lengths(C.byref(rb), C.c_double(s), _dp(out))

@@ -261,3 +261,77 @@ class RefFK:
     def segment_aabox_intersect(self, A, B, Cc, D):
         a, b, c, d = (np.ascontiguousarray(v, dtype=np.float64) for v in (A, B, Cc, D))
         return bool(self.lib().fkref_segment_aabox_intersect(_dp(a), _dp(b), _dp(c), _dp(d)))
+
+
+class RefLevmar:
+    """levmar-2.6 as vendored by the reference (3rdparty/levmar-2.6, compiled WITHOUT LAPACK, see
+    oracle/Makefile): the optimiser behind tip_control::inverse_kinematics (tip_control.cpp:34-153).
+    Callbacks are Python callables f(p: ndarray[m]) -> ndarray[n] (and J(p) -> ndarray[n][m])."""
+    _lib = None
+    FUNC = C.CFUNCTYPE(None, C.POINTER(C.c_double), C.POINTER(C.c_double), C.c_int, C.c_int, C.c_void_p)
+    INFO_SZ = 10
+
+    @classmethod
+    def available(cls):
+        return os.path.exists(os.path.join(REF_DIR, "liblevmar_ref.so"))
+
+    @classmethod
+    def lib(cls):
+        if cls._lib is None:
+            L = C.CDLL(os.path.join(REF_DIR, "liblevmar_ref.so"))
+            dp = C.POINTER(C.c_double)
+            L.dlevmar_fdif_forw_jac_approx.restype = None
+            L.dlevmar_fdif_forw_jac_approx.argtypes = [cls.FUNC, dp, dp, dp, C.c_double, dp, C.c_int, C.c_int, C.c_void_p]
+            L.dlevmar_fdif_cent_jac_approx.restype = None
+            L.dlevmar_fdif_cent_jac_approx.argtypes = [cls.FUNC, dp, dp, dp, C.c_double, dp, C.c_int, C.c_int, C.c_void_p]
+            L.dlevmar_bc_dif.restype = C.c_int
+            L.dlevmar_bc_dif.argtypes = [cls.FUNC, dp, dp, C.c_int, C.c_int, dp, dp, dp, C.c_int, dp, dp, dp, dp, C.c_void_p]
+            L.dlevmar_bc_der.restype = C.c_int
+            L.dlevmar_bc_der.argtypes = [cls.FUNC, cls.FUNC, dp, dp, C.c_int, C.c_int, dp, dp, dp, C.c_int, dp, dp, dp, dp, C.c_void_p]
+            cls._lib = L
+        return cls._lib
+
+    @classmethod
+    def _wrap(cls, f, rows=None):
+        def cb(p, out, m, n, _):
+            v = np.asarray(f(np.array([p[i] for i in range(m)])), dtype=np.float64).reshape(-1)
+            for i in range(len(v)):
+                out[i] = v[i]
+        return cls.FUNC(cb)
+
+    @classmethod
+    def fdif_jac(cls, f, p, n, delta, central):
+        """levmar's own finite-difference Jacobian (misc_core.c:137-211), jac[i*m+j] layout -> [n][m]"""
+        p = np.array(p, dtype=np.float64)
+        m = len(p)
+        J, w1, w2 = np.zeros((n, m)), np.zeros(n), np.zeros(n)
+        cb = cls._wrap(f)
+        if central:
+            cls.lib().dlevmar_fdif_cent_jac_approx(cb, _dp(p), _dp(w1), _dp(w2), delta, _dp(J), m, n, None)
+        else:
+            hx = np.asarray(f(p.copy()), dtype=np.float64).copy()
+            cls.lib().dlevmar_fdif_forw_jac_approx(cb, _dp(p), _dp(hx), _dp(w1), delta, _dp(J), m, n, None)
+        return J
+
+    @classmethod
+    def bc_dif(cls, f, p0, x, lb, ub, itmax, opts5):
+        """dlevmar_bc_dif as called at tip_control.cpp:124-137.  Returns (p, info[10], rc)."""
+        p = np.array(p0, dtype=np.float64)
+        x = np.array(x, dtype=np.float64)
+        lb, ub = np.array(lb, dtype=np.float64), np.array(ub, dtype=np.float64)
+        opts, info = np.array(opts5, dtype=np.float64), np.zeros(cls.INFO_SZ)
+        rc = cls.lib().dlevmar_bc_dif(cls._wrap(f), _dp(p), _dp(x), len(p), len(x), _dp(lb), _dp(ub), None,
+                                      itmax, _dp(opts), _dp(info), None, None, None)
+        return p, info, rc
+
+    @classmethod
+    def bc_der(cls, f, jacf, p0, x, lb, ub, itmax, opts4):
+        """dlevmar_bc_der: the same driver with a caller-supplied Jacobian (dlevmar_bc_dif is this
+        function with levmar's own finite-difference wrappers, lmbc_core.c)."""
+        p = np.array(p0, dtype=np.float64)
+        x = np.array(x, dtype=np.float64)
+        lb, ub = np.array(lb, dtype=np.float64), np.array(ub, dtype=np.float64)
+        opts, info = np.array(opts4, dtype=np.float64), np.zeros(cls.INFO_SZ)
+        rc = cls.lib().dlevmar_bc_der(cls._wrap(f), cls._wrap(jacf), _dp(p), _dp(x), len(p), len(x), _dp(lb),
+                                      _dp(ub), None, itmax, _dp(opts), _dp(info), None, None, None)
+        return p, info, rc

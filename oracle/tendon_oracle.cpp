@@ -865,6 +865,72 @@ int orc_shape(const orc_robot *rb, const double *state, int cap_pts, double *t, 
   return n;
 }
 
+// ---- finite-difference tip Jacobians, sequential like the reference --------
+namespace {
+// robot.forward_kinematics(state).back()
+void fk_tip(const orc_robot &rb, const double *state, double *tip) {
+  Shape s;
+  robot_shape(rb, state, s);
+  for (int k = 0; k < 3; k++) tip[k] = s.p.back()[k];
+}
+// fk_wrap of tip-control/tip_control.cpp:92-122 (what levmar differentiates)
+void fk_wrap(const orc_robot &rb, const double *p, int m, double *x) {
+  if (rb.enable_retraction && p[m - 1] > rb.L) {
+    x[0] = 0.0; x[1] = 0.0; x[2] = rb.L - p[m - 1];
+    return;
+  }
+  fk_tip(rb, p, x);
+}
+}  // namespace
+
+void orc_tip_jacobian(const orc_robot *rb, const double *state, int mode, double delta, double *tip,
+                      double *J) {
+  const int m = orc_state_size(rb), n = 3;
+  std::vector<double> p(state, state + m);
+  double hx[3], hxx[3], hxm[3], hxp[3];
+  if (mode == 0) {
+    // tip_control::Jacobian, tip-control/tip_control.cpp:243-265 (ps = fk(state).back())
+    fk_tip(*rb, p.data(), hx);
+    for (int i = 0; i < m; i++) {
+      std::vector<double> tau2 = p;
+      tau2[i] = p[i] + delta;
+      fk_tip(*rb, tau2.data(), hxx);
+      for (int j = 0; j < 3; j++) J[j * m + i] = (hxx[j] - hx[j]) / delta;
+    }
+  } else if (mode == 1) {
+    // dlevmar_fdif_forw_jac_approx, 3rdparty/levmar-2.6/misc_core.c:137-172
+    fk_wrap(*rb, p.data(), m, hx);
+    for (int j = 0; j < m; ++j) {
+      double d = 1E-04 * p[j];
+      d = std::fabs(d);
+      if (d < delta) d = delta;
+      double tmp = p[j];
+      p[j] += d;
+      fk_wrap(*rb, p.data(), m, hxx);
+      p[j] = tmp;
+      d = 1.0 / d;
+      for (int i = 0; i < n; ++i) J[i * m + j] = (hxx[i] - hx[i]) * d;
+    }
+  } else {
+    // dlevmar_fdif_cent_jac_approx, misc_core.c:175-211
+    fk_wrap(*rb, p.data(), m, hx);
+    for (int j = 0; j < m; ++j) {
+      double d = 1E-04 * p[j];
+      d = std::fabs(d);
+      if (d < delta) d = delta;
+      double tmp = p[j];
+      p[j] -= d;
+      fk_wrap(*rb, p.data(), m, hxm);
+      p[j] = tmp + d;
+      fk_wrap(*rb, p.data(), m, hxp);
+      p[j] = tmp;
+      d = 0.5 / d;
+      for (int i = 0; i < n; ++i) J[i * m + j] = (hxp[i] - hxm[i]) * d;
+    }
+  }
+  if (tip) for (int k = 0; k < 3; k++) tip[k] = hx[k];
+}
+
 void orc_home_lengths(const orc_robot *rb, double s_start, double *L_i) {
   home_lengths(*rb, s_start, L_i);
 }

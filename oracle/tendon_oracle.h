@@ -104,6 +104,11 @@ void orc_tendon_deriv_alt(const orc_robot *rb, const double *tau, const double *
  * returns npts, or -1 if cap_pts too small, -2 on bad sizes. */
 int orc_shape(const orc_robot *rb, const double *state, int cap_pts, double *t, double *p,
               double *R, orc_fk_out *out);
+/* finite-difference tip Jacobian J[3][m] (levmar's jac[i*m+j] layout): mode 0 tip_control::Jacobian
+ * (tip-control/tip_control.cpp:243-265), 1/2 levmar-2.6 forward/central rule (misc_core.c:137-211)
+ * applied to fk_wrap (tip_control.cpp:92-122) */
+void orc_tip_jacobian(const orc_robot *rb, const double *state, int mode, double delta, double *tip,
+                      double *J);
 void orc_home_lengths(const orc_robot *rb, double s_start, double *L_i);
 int orc_collides_self(const double *p, int npts, double r);
 void orc_closest_st_segment(const double *A, const double *B, const double *C, const double *D,

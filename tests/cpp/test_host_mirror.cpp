@@ -230,6 +230,25 @@ int main() {
   prm.precomputeVertexValidity();
   for (size_t i = 0; i < verts.size(); i++) CHECK(prm.vertexValidity()[i] == ((prm.vertexFlags()[i] & 39u) == 0 ? 1u : 0u));
 
+  // ---- tip_control::Jacobian / levmar's central-difference Jacobian for a batch of IK seeds -----
+  {
+    std::vector<std::vector<double>> seeds(states.begin(), states.begin() + 24);
+    seeds[0][7] = 0.0;                      // base at 0: the central difference evaluates s = -d
+    seeds[1][7] = robot.specs.L - 1e-5;     // s + d > L: fk_wrap's (0, 0, L - s) branch
+    for (int mode = 0; mode < 3; mode++) {
+      const double delta = mode == 0 ? 1e-3 : 1e-4;
+      std::vector<collision::Point> tips;
+      auto Js = tip_control::Jacobian_batch(robot, delta, seeds, &tips, mode);
+      for (size_t i = 0; i < seeds.size(); i++) {
+        double tip[3], J[3 * 8];
+        orc_tip_jacobian(&orb, seeds[i].data(), mode, delta, tip, J);
+        for (int c = 0; c < 3; c++) CHECK(std::fabs(tips[i][c] - tip[c]) < 1e-9 * robot.specs.L);
+        // the difference of two tips that agree to 1e-9 L, divided by the step
+        for (int c = 0; c < 24; c++) CHECK(std::fabs(Js[i][c] - J[c]) < 2e-9 * robot.specs.L / delta);
+      }
+    }
+  }
+
   orc_octree_free(oenv);
   std::printf(failures ? "FAILED (%d)\n" : "host mirror ok\n", failures);
   return failures ? 1 : 0;

@@ -101,8 +101,13 @@ def test_fk_edge_cases(irt, ctx, orc, wl):
     _fk_compare(irt, ctx, orc, spec, states, want_all=True)
     out = rb.shape_batch(states, want=("p", "npts", "flags"))
     assert out["npts"][0] == 1 and out["npts"][1] == 1 and out["npts"][2] == 1
-    # negative retraction / NaN: outside the reference's state space -> BAD_STATE, no points
-    bad = rb.shape_batch(np.array([tau + [-0.01], tau + [float("nan")]]), want=("p", "npts", "flags"))
+    # a base slightly before 0 (what the reference's finite-difference Jacobians evaluate): same grid
+    # size, longer first gap -- integrated like the reference does
+    neg = np.array([tau + [s] for s in (-1e-7, -1e-4, -0.0005, -0.0014, -0.002, -0.00249)])
+    _fk_compare(irt, ctx, orc, spec, neg, want_all=True)
+    # NaN, or so far before 0 that the grid would not fit max_points: BAD_STATE, no points
+    bad = rb.shape_batch(np.array([tau + [-0.0026], tau + [-0.01], tau + [-1e30], tau + [float("nan")]]),
+                         want=("p", "npts", "flags"))
     assert np.all(bad["flags"] & irt.FLAG_BAD_STATE) and np.all(bad["npts"] == 0)
     # zero tension
     z = rb.shape_batch(np.array([[0.0] * 6 + [0.05]]), want=("p", "npts", "t"))
@@ -654,3 +659,42 @@ def test_env_preparation_small_grids(irt, ctx, orc, wl, Ng):
     env.update(np.full(Nb ** 3, np.uint64(2 ** 64 - 1)))
     env.remove_interior()
     assert env.nblocks() == 0 and not env.download().any()
+
+
+@pytest.mark.parametrize("mode,delta", [(0, 1e-3), (0, 1e-4), (1, 1e-4), (2, 1e-4), (2, 1e-6)])
+def test_tip_jacobian_batch(irt, ctx, orc, wl, mode, delta):
+    """finite-difference tip Jacobians of a batch of IK seeds in one FK launch vs
+    the sequential rules of tip_control::Jacobian (tip_control.cpp:243-265) and levmar-2.6
+    (misc_core.c:137-211 on fk_wrap, tip_control.cpp:92-122)."""
+    spec = wl.robot_b(0.005, rotation=True)
+    rb = irt.Robot(ctx, spec)
+    orb = orc.robot(spec)
+    L = spec["L"]
+    states = wl.sample_states(spec, 300, stream=91)
+    states[0, -1] = 0.0            # s - d < 0: the base before the origin is integrated like the reference
+    states[1, -1] = L - 0.3 * delta  # s + d > L: fk_wrap returns (0, 0, L - s)
+    states[2, -1] = L              # degenerate one-point shape
+    states[3, :6] = 0.0            # tau = 0: tau - d < 0
+    tips, J = rb.tip_jacobian_batch(states, mode=mode, delta=delta)
+    assert J.shape == (300, 3, rb.state_size)
+    worst_t = worst_J = 0.0
+    for i, s in enumerate(states):
+        t_ref, J_ref = orc.tip_jacobian(orb, s, mode, delta)
+        worst_t = max(worst_t, np.abs(tips[i] - t_ref).max() / L)
+        worst_J = max(worst_J, np.abs(J[i] - J_ref).max())
+    assert worst_t < FK_REL_TOL
+    # a Jacobian entry is the difference of two tips (each within FK_REL_TOL * L) over the step
+    assert worst_J < 2 * FK_REL_TOL * L / min(delta, 1e-4), worst_J
+    # the batched Jacobian predicts the tip displacement of a small step (sanity, all modes)
+    if mode == 2 and delta == 1e-4:
+        dq = np.zeros_like(states[10]); dq[:6] = 1e-3
+        t1 = rb.shape_batch((states[10] + dq)[None], want=("tip",))["tip"][0]
+        assert np.abs(tips[10] + J[10] @ dq - t1).max() < 1e-6
+    # error convention
+    with pytest.raises(irt.IrtError):
+        rb.tip_jacobian_batch(states[:, :-1])
+    with pytest.raises(irt.IrtError):
+        rb.tip_jacobian_batch(states, mode=7)
+    with pytest.raises(irt.IrtError):
+        rb.tip_jacobian_batch(states, delta=0.0)
+    assert rb.tip_jacobian_batch(states[:0])[1].shape == (0, 3, rb.state_size)

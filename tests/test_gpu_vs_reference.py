@@ -114,3 +114,39 @@ def test_k1_points_vs_reference_derivative(irt, ctx, wl, robot, dL, rot):
         assert np.allclose(out["uv"][i][0:3], u0, rtol=1e-9, atol=1e-10)
         assert np.allclose(out["uv"][i][6:9], v0, rtol=1e-9, atol=1e-10)
     assert worst < FK_REL_TOL, worst
+
+
+@pytest.mark.skipif(not ref.RefLevmar.available(), reason="oracle/_ref/liblevmar_ref.so was not shipped")
+def test_ik_levmar_driven_by_gpu_jacobians(irt, ctx, orc, wl):
+    """The IK of the reference end to end ("IK"): its own optimiser, levmar-2.6's
+    box-constrained LM, once as the reference runs it -- dlevmar_bc_dif differentiating a CPU FK
+    sequentially (tip_control.cpp:124-137) -- and once as dlevmar_bc_der with the GPU supplying tips and
+    whole central-difference Jacobians per call (one K1 launch instead of 2S+1 sequential FKs).
+    dlevmar_bc_dif IS dlevmar_bc_der with finite-difference wrappers, so the iterates agree."""
+    spec = wl.robot_b(0.005)
+    rb = irt.Robot(ctx, spec)
+    orb = orc.robot(spec)
+    L = spec["L"]
+    delta = 1e-6
+
+    def f_cpu(p):
+        if p[-1] > L:
+            return np.array([0.0, 0.0, L - p[-1]])
+        return orc.shape(orb, p)["p"][-1]
+
+    def f_gpu(p):
+        return rb.tip_jacobian_batch(p[None], mode=irt.JAC_LEVMAR_CENTRAL, delta=delta)[0][0]
+
+    def j_gpu(p):
+        return rb.tip_jacobian_batch(p[None], mode=irt.JAC_LEVMAR_CENTRAL, delta=delta)[1][0]
+
+    lb, ub = np.zeros(7), np.array([20.0] * 6 + [L])
+    st = wl.sample_states(spec, 5, stream=34)
+    for s in st:
+        goal_state = np.clip(s + np.array([0.8, -0.5, 0.3, 0.6, -0.4, 0.2, 0.004]), lb, ub)
+        des = f_cpu(goal_state)
+        p_ref, info_ref, _ = ref.RefLevmar.bc_dif(f_cpu, s, des, lb, ub, 100, [0.1, 1e-9, 1e-8, 1e-8, -delta])
+        p_gpu, info_gpu, _ = ref.RefLevmar.bc_der(f_gpu, j_gpu, s, des, lb, ub, 100, [0.1, 1e-9, 1e-8, 1e-8])
+        assert info_gpu[5] == info_ref[5] and info_gpu[6] == info_ref[6]      # iterations, stop reason
+        assert np.abs(p_gpu - p_ref).max() < 1e-6 * 20.0
+        assert np.linalg.norm(f_cpu(p_gpu) - des) < 2e-4

@@ -203,3 +203,55 @@ def test_live_verdicts_of_a_voxelised_roadmap(orc, wl):
     want = renv.check_csr(off, bx, by, bz, bits)
     got = orc.check_sets_batch(store, oenv).astype(bool)
     assert np.array_equal(got, want) and 0 < want.sum() < len(want)
+
+
+# ------------------------------------------------------------------ levmar (vendored by the reference)
+levmar = pytest.mark.skipif(not (ref.available() and ref.RefLevmar.available()),
+                            reason="oracle/_ref/liblevmar_ref.so not built")
+
+
+def _fk_wrap(orc, rb, L):
+    """fk_wrap of tip-control/tip_control.cpp:92-122 on the oracle's FK"""
+    def f(p):
+        if rb.enable_retraction and p[-1] > L:
+            return np.array([0.0, 0.0, L - p[-1]])
+        return orc.shape(rb, p)["p"][-1]
+    return f
+
+
+@levmar
+@pytest.mark.parametrize("name", ["a005", "b003", "b005rot"])
+def test_live_levmar_finite_difference_rule(orc, wl, robots, name):
+    """orc_tip_jacobian modes 1/2 == levmar-2.6's own dlevmar_fdif_{forw,cent}_jac_approx
+    (misc_core.c:137-211) driving the same FK: bit for bit."""
+    spec = robots[name]
+    rb = orc.robot(spec)
+    f = _fk_wrap(orc, rb, spec["L"])
+    states = wl.sample_states(spec, 6, stream=33)
+    if spec.get("enable_retraction"):
+        states[0, -1] = 0.0
+        states[1, -1] = spec["L"] - 1e-5
+    for s in states:
+        for central in (False, True):
+            for delta in (1e-6, 1e-4):
+                want = ref.RefLevmar.fdif_jac(f, s, 3, delta, central)
+                _, got = orc.tip_jacobian(rb, s, 2 if central else 1, delta)
+                assert np.array_equal(got, want)
+
+
+@levmar
+def test_live_ik_with_reference_levmar(orc, wl):
+    """tip_control::inverse_kinematics (tip_control.cpp:34-153) = dlevmar_bc_dif over fk_wrap with the
+    defaults of Controller.h:55-65: reaches the tip of a nearby configuration."""
+    spec = wl.robot_b(0.005)
+    rb = orc.robot(spec)
+    L = spec["L"]
+    f = _fk_wrap(orc, rb, L)
+    st = wl.sample_states(spec, 4, stream=34)
+    lb, ub = np.zeros(7), np.array([20.0] * 6 + [L])       # Bounds::from_robot, tip_control.cpp:160-176
+    for s in st:
+        goal_state = np.clip(s + np.array([0.8, -0.5, 0.3, 0.6, -0.4, 0.2, 0.004]), lb, ub)
+        des = f(goal_state)
+        p, info, rc = ref.RefLevmar.bc_dif(f, s, des, lb, ub, 100, [0.1, 1e-9, 1e-8, 1e-8, -1e-6])
+        assert rc >= 0 and np.all(p >= lb) and np.all(p <= ub)
+        assert np.linalg.norm(f(p) - des) < 2e-4 and info[1] < info[0]
