@@ -698,3 +698,73 @@ def test_tip_jacobian_batch(irt, ctx, orc, wl, mode, delta):
     with pytest.raises(irt.IrtError):
         rb.tip_jacobian_batch(states, delta=0.0)
     assert rb.tip_jacobian_batch(states[:0])[1].shape == (0, 3, rb.state_size)
+
+
+def test_full_size_roadmap_generation_properties(irt, ctx, orc, wl):
+    """Config C3 at full size: 100k vertices / ~1M k-NN edges, 128^3 grid.  Size-independent properties
+    of the swept-volume build (determinism, shard invariance, endpoint containment, verdict
+    monotonicity) plus the oracle on a random sample of its edges."""
+    import torch
+    from bench import knn_edges_gpu
+    spec = wl.robot_b(0.003)
+    g = wl.workspace_grid(spec)
+    Nb = g["Ng"] // 4
+    grid = irt.make_grid(g["Ng"], g["lim"])
+    rb = irt.Robot(ctx, spec)
+    nv = 100_000
+    st = wl.sample_states(spec, nv, stream=200)
+    pairs = knn_edges_gpu(torch, st, spec, 17, torch.device("cuda"))   # ~1M undirected edges after dedupe
+    assert 900_000 <= len(pairs) <= 1_250_000
+    sp = irt.make_space()
+    full = irt.SetStore(ctx, grid)
+    info = full.voxelize_edges_indexed(rb, sp, st, pairs)
+    off, keys, bits = full.export_csr()
+    ne = len(pairs)
+    assert len(off) == ne + 1 and np.all(np.diff(off.astype(np.int64)) >= 0)
+    # keys sorted strictly inside every set (visit_leaves order), no empty leaves
+    inner = np.ones(len(keys), dtype=bool)
+    inner[off[:-1][off[:-1] < len(keys)].astype(np.int64)] = False
+    assert np.all(np.diff(keys.astype(np.int64))[inner[1:]] > 0) and np.all(bits != 0)
+    # determinism: a second build is identical
+    again = irt.SetStore(ctx, grid)
+    info2 = again.voxelize_edges_indexed(rb, sp, st, pairs)
+    o2, k2, b2 = again.export_csr()
+    assert np.array_equal(off, o2) and np.array_equal(keys, k2) and np.array_equal(bits, b2)
+    assert all(np.array_equal(info[k], info2[k]) for k in ("flags", "t_last", "nsamples"))
+    # shard invariance: the edge list split at an arbitrary point gives the same sets (what N ranks hold)
+    cut = 333_337
+    lo_s, hi_s = irt.SetStore(ctx, grid), irt.SetStore(ctx, grid)
+    lo_s.voxelize_edges_indexed(rb, sp, st, pairs[:cut])
+    hi_s.voxelize_edges_indexed(rb, sp, st, pairs[cut:])
+    ol, kl, bl = lo_s.export_csr()
+    oh, kh, bh = hi_s.export_csr()
+    assert np.array_equal(np.concatenate([kl, kh]), keys) and np.array_equal(np.concatenate([bl, bh]), bits)
+    assert np.array_equal(np.concatenate([ol, oh[1:] + ol[-1]]), off)
+    # endpoint containment: a fully valid edge's swept volume contains both endpoint vertex sets
+    vs = irt.SetStore(ctx, grid)
+    vflags, _ = vs.voxelize_vertices(rb, st)
+    vo, vk, vb = vs.export_csr()
+    rng = np.random.default_rng(3)
+    full_valid = np.nonzero(info["flags"] == 0)[0]
+    for e in rng.choice(full_valid, size=2000, replace=False):
+        es = dict(zip(keys[int(off[e]):int(off[e + 1])].tolist(), bits[int(off[e]):int(off[e + 1])].tolist()))
+        for v in pairs[e]:
+            for k, b in zip(vk[int(vo[v]):int(vo[v + 1])].tolist(), vb[int(vo[v]):int(vo[v + 1])].tolist()):
+                assert es.get(k, 0) & b == b
+    # verdict monotonicity: an edge whose endpoint vertex collides collides itself
+    env = irt.Env(ctx, grid)
+    env.update(wl.dense_to_morton_blocks(wl.lung_like_env_dense(spec, g)))
+    ev, vv = full.check(env), vs.check(env)
+    ok = info["flags"] == 0
+    assert np.all(ev[ok] | ~(vv[pairs[ok, 0]] | vv[pairs[ok, 1]]))
+    assert 0.05 < ev.mean() < 0.95
+    # the oracle on a random sample of these edges: bit-exact sets, flags and sample counts
+    sample = np.sort(rng.choice(ne, size=400, replace=False))
+    ostore, oinfo = orc.voxelize_edges_batch(orc.robot(spec), orc.grid(g["Ng"], g["lim"]), orc.space(),
+                                             st[pairs[sample, 0]], st[pairs[sample, 1]])
+    oo, ok_, ob = ostore.export()
+    for j, e in enumerate(sample):
+        assert np.array_equal(keys[int(off[e]):int(off[e + 1])], ok_[int(oo[j]):int(oo[j + 1])])
+        assert np.array_equal(bits[int(off[e]):int(off[e + 1])], ob[int(oo[j]):int(oo[j + 1])])
+    assert np.array_equal(info["flags"][sample], oinfo["flags"])
+    assert np.array_equal(info["t_last"][sample], oinfo["t_last"])
