@@ -362,22 +362,41 @@ def main():
         setattr(o, kname, t.data_ptr())
     import ctypes as C
 
-    def e2e_step():
+    h_rowoff = torch.zeros(n + 1, dtype=torch.int64).pin_memory()
+
+    def e2e_step():      # packed rows: TendonResult's per-shape vectors laid end to end (the public call)
+        ctx.check(ctx.L.irt_fk_batch_packed(ctx.h, rb.h, C.c_void_p(h_states.data_ptr()), rb.state_size, n,
+                                            C.byref(o), n * cap, C.c_void_p(h_rowoff.data_ptr())))
+
+    def e2e_dense_step():  # dense [n][max_points] rows, zero padded
         ctx.check(ctx.L.irt_fk_batch(ctx.h, rb.h, C.c_void_p(h_states.data_ptr()), rb.state_size, n, cap, C.byref(o)))
 
-    e2e_step()
-    barrier()
-    e2e_steps = max(2, min(args.steps, 5))
-    t0 = time.perf_counter()
-    for _ in range(e2e_steps):
-        e2e_step()
-    barrier()
-    e2e_s = max_over_ranks((time.perf_counter() - t0) / e2e_steps)
+    def time_e2e(fn):
+        fn()
+        barrier()
+        k = max(2, min(args.steps, 5))
+        t0 = time.perf_counter()
+        for _ in range(k):
+            fn()
+        barrier()
+        return max_over_ranks((time.perf_counter() - t0) / k)
+
+    e2e_dense_s = time_e2e(e2e_dense_step)
+    dense_npts = h_out["npts"].clone()
+    dense_rows = h_out["p"].reshape(n * cap, 3)[(torch.arange(cap)[None, :] < dense_npts[:, None]).reshape(-1)].clone()
+    e2e_s = time_e2e(e2e_step)
+    rows = int(h_rowoff[-1])
     h2d = n * rb.state_size * 8
-    d2h = n * (cap * 24 + 4 + 8 + rb.n_tendons * 8)
+    d2h = rows * 24 + n * (4 + 8 + rb.n_tendons * 8) + (n + 1) * 8
     e2e = {"value": world * n / e2e_s, "unit": "shapes/s", "h2d_bytes_per_step": h2d,
            "d2h_bytes_per_step": d2h, "ms_per_step": e2e_s * 1e3,
-           "api": "irt_fk_batch (host pointers, pinned), outputs p/npts/L/L_i"}
+           "api": "irt_fk_batch_packed (host pointers, pinned): p packed per shape + row_offsets, npts, L, L_i",
+           "rows_per_step": rows,
+           "dense": {"value": world * n / e2e_dense_s, "ms_per_step": e2e_dense_s * 1e3,
+                     "d2h_bytes_per_step": n * (cap * 24 + 4 + 8 + rb.n_tendons * 8),
+                     "api": "irt_fk_batch: p as [n][max_points][3], zero padded"},
+           "packed_equals_dense": bool(torch.equal(h_out["p"].reshape(n * cap, 3)[:rows], dense_rows)
+                                       and torch.equal(h_out["npts"], dense_npts))}
     # parity spot check of the timed outputs against each other (device path == host path)
     same = bool(torch.equal(h_out["npts"], outs["npts"].cpu()))
 

@@ -159,6 +159,14 @@ int irt_fk_batch(irt_ctx *ctx, const irt_robot *rb, const double *states, int st
                  int64_t n, int cap_pts, const irt_fk_outputs *out);
 int irt_fk_batch_dev(irt_ctx *ctx, const irt_robot *rb, const double *d_states, int state_size,
                      int64_t n, int cap_pts, const irt_fk_outputs *d_out, void *stream);
+/* Packed form of irt_fk_batch (host pointers): out->p / R / t hold only the rows that exist, shape i
+ * in rows [row_offsets[i], row_offsets[i+1]) -- the reference's per-shape std::vector<Point> /
+ * vector<Matrix3d> / vector<double> (tendon/TendonResult.h:17-28) laid end to end; all other members
+ * of `out` are per shape as in irt_fk_batch.  row_offsets has n+1 entries; cap_rows is the capacity
+ * of the caller's p/R/t buffers in rows (n * irt_robot_max_points always suffices), IRT_ERR_CAPACITY
+ * if it is too small.  With retraction this moves ~3/4 of the bytes of the dense form over PCIe. */
+int irt_fk_batch_packed(irt_ctx *ctx, const irt_robot *rb, const double *states, int state_size,
+                        int64_t n, const irt_fk_outputs *out, int64_t cap_rows, int64_t *row_offsets);
 /* Batched finite-difference tip Jacobians: what the reference's IK and tip
  * controllers compute with one FK per perturbed parameter.  J is [n][3][S] (row i of seed k at
  * J[(k*3+i)*S + j], levmar's jac[i*m+j] layout), tips is [n][3] (may be NULL): the value the

@@ -94,7 +94,7 @@ ABI_SYMBOLS = [
     "irt_abi_version", "irt_status_string", "irt_ctx_create", "irt_ctx_destroy", "irt_last_error",
     "irt_ctx_device", "irt_ctx_synchronize", "irt_ctx_launch_count", "irt_measure_fp64_peak",
     "irt_robot_create", "irt_robot_destroy", "irt_robot_state_size", "irt_robot_max_points",
-    "irt_fk_batch", "irt_fk_batch_dev", "irt_home_lengths_batch",
+    "irt_fk_batch", "irt_fk_batch_dev", "irt_fk_batch_packed", "irt_home_lengths_batch",
     "irt_fk_tip_jacobian_batch", "irt_fk_tip_jacobian_batch_dev",
     "irt_env_create", "irt_env_destroy", "irt_env_update", "irt_env_update_dev",
     "irt_env_update_sparse", "irt_env_nblocks",
@@ -139,6 +139,7 @@ def lib():
         "irt_robot_max_points": (i32, [vp]),
         "irt_fk_batch": (i32, [vp, vp, vp, i32, i64, i32, C.POINTER(FkOutputs)]),
         "irt_fk_batch_dev": (i32, [vp, vp, vp, i32, i64, i32, C.POINTER(FkOutputs), vp]),
+        "irt_fk_batch_packed": (i32, [vp, vp, vp, i32, i64, C.POINTER(FkOutputs), i64, vp]),
         "irt_home_lengths_batch": (i32, [vp, vp, vp, i32, i64, vp]),
         "irt_fk_tip_jacobian_batch": (i32, [vp, vp, vp, i32, i64, i32, C.c_double, vp, vp]),
         "irt_fk_tip_jacobian_batch_dev": (i32, [vp, vp, vp, i32, i64, i32, C.c_double, vp, vp, vp]),
@@ -324,6 +325,38 @@ class Robot:
         if "R" in out:  # column-major 3x3 -> [n][cap][row][col]
             out["R"] = out["R"].reshape(n, cap, 3, 3).transpose(0, 1, 3, 2)
         return out
+
+    def shape_batch_packed(self, states, want=("p", "npts", "L", "L_i", "tip", "flags"), out=None,
+                           cap_rows=None):
+        """Like shape_batch, but p / R / t are packed: shape i owns rows
+        [row_offsets[i], row_offsets[i+1]) (the reference's per-shape vectors laid end to end).
+        `out` may carry preallocated (e.g. pinned) arrays; returns the dict with "row_offsets" and
+        "rows" (total) added."""
+        states = _np(states, np.float64)
+        if states.ndim != 2:
+            raise IrtError(IRT_ERR_INVALID_ARGUMENT, "states must be [n][S]")
+        n, S = states.shape
+        N = self.n_tendons
+        cap_rows = int(cap_rows if cap_rows is not None else n * self.max_points)
+        shapes = dict(p=((cap_rows, 3), np.float64), R=((cap_rows, 9), np.float64),
+                      t=((cap_rows,), np.float64), npts=((n,), np.int32), L=((n,), np.float64),
+                      L_i=((n, N), np.float64), tip=((n, 3), np.float64), uv=((n, 12), np.float64),
+                      flags=((n,), np.uint32), iters=((n,), np.int32), nsteps=((n,), np.int32))
+        res = dict(out) if out is not None else {}
+        for k in want:
+            if k not in res:
+                res[k] = np.empty(*shapes[k])
+        if "row_offsets" not in res:
+            res["row_offsets"] = np.zeros(n + 1, dtype=np.int64)
+        o = FkOutputs()
+        for k in shapes:
+            if k in res:
+                setattr(o, k, _ptr(res[k]).value if hasattr(res[k], "data_ptr") else res[k].ctypes.data)
+        self.ctx.check(self.ctx.L.irt_fk_batch_packed(self.ctx.h, self.h, _ptr(states), S, n, C.byref(o),
+                                                      cap_rows, _ptr(res["row_offsets"])))
+        res["rows"] = int(np.asarray(res["row_offsets"])[-1]) if not hasattr(res["row_offsets"], "data_ptr") \
+            else int(res["row_offsets"][-1])
+        return res
 
     def shape_batch_dev(self, d_states, n, outputs, cap_pts=None, stream=None):
         """Device-resident form: d_states and every value of `outputs` are torch CUDA tensors

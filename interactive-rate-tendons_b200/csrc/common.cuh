@@ -33,6 +33,10 @@ struct irt_ctx {
   void *io = nullptr;
   size_t io_bytes = 0;
   cudaEvent_t ev_computed[2] = {nullptr, nullptr}, ev_copied[2] = {nullptr, nullptr};
+  // packed FK outputs: per-stage "row offsets are on the host" events and a small pinned host buffer
+  cudaEvent_t ev_offsets[2] = {nullptr, nullptr};
+  void *pinned = nullptr;
+  size_t pinned_bytes = 0;
 };
 
 // device-resident robot constants (passed to kernels by value)
@@ -98,6 +102,7 @@ int grid_check(irt_ctx *ctx, const irt_grid *g);
 void *ctx_scratch(irt_ctx *ctx, size_t bytes);  // nullptr on failure
 void *ctx_arena(irt_ctx *ctx, size_t bytes);    // nullptr on failure
 void *ctx_io(irt_ctx *ctx, size_t bytes);       // nullptr on failure
+void *ctx_pinned(irt_ctx *ctx, size_t bytes);   // page-locked HOST memory, nullptr on failure
 int setstore_grow_blocks(irt_ctx *ctx, irt_setstore *s, int64_t need_blocks, int64_t keep_blocks,
                          cudaStream_t st);
 
@@ -116,8 +121,12 @@ int env_rebuild_occ(irt_ctx *ctx, irt_env *env, cudaStream_t st);
 int setstore_reserve(irt_ctx *ctx, irt_setstore *s, int64_t n_sets, int64_t n_blocks);
 int setstore_finalize(irt_ctx *ctx, irt_setstore *s, int64_t n_sets, int64_t n_blocks,
                       cudaStream_t st);
+// d_row_off == nullptr: dense outputs p/R/t[n][cap_pts]; else packed rows, configuration i at row d_row_off[i]
 int fk_launch(irt_ctx *ctx, const irt_robot *rb, const double *d_states, int64_t n, int cap_pts,
-              const irt_fk_outputs &o, const int32_t *d_perm, cudaStream_t st);
+              const irt_fk_outputs &o, const int32_t *d_perm, cudaStream_t st,
+              const int64_t *d_row_off = nullptr);
+int fk_row_counts(irt_ctx *ctx, const irt_robot *rb, const double *d_states, int64_t n,
+                  int64_t *d_counts, cudaStream_t st);
 int self_collision_launch(irt_ctx *ctx, const irt_robot *rb, const double *d_p,
                           const int32_t *d_npts, int64_t n, int cap_pts, uint32_t *d_flags,
-                          cudaStream_t st);
+                          cudaStream_t st, const int64_t *d_row_off = nullptr);

@@ -46,11 +46,22 @@ void *ctx_arena(irt_ctx *ctx, size_t bytes) {
 void *ctx_io(irt_ctx *ctx, size_t bytes) {
   if (bytes <= ctx->io_bytes) return ctx->io;
   if (ctx->io) cudaFree(ctx->io);
+  if (ctx->pinned) cudaFreeHost(ctx->pinned);
   ctx->io = nullptr;
   ctx->io_bytes = 0;
   if (cudaMalloc(&ctx->io, bytes) != cudaSuccess) return nullptr;
   ctx->io_bytes = bytes;
   return ctx->io;
+}
+
+void *ctx_pinned(irt_ctx *ctx, size_t bytes) {
+  if (bytes <= ctx->pinned_bytes) return ctx->pinned;
+  if (ctx->pinned) cudaFreeHost(ctx->pinned);
+  ctx->pinned = nullptr;
+  ctx->pinned_bytes = 0;
+  if (cudaMallocHost(&ctx->pinned, bytes) != cudaSuccess) return nullptr;
+  ctx->pinned_bytes = bytes;
+  return ctx->pinned;
 }
 
 extern "C" {
@@ -90,6 +101,7 @@ int irt_ctx_create(int device, irt_ctx **out) {
   }
   for (int b = 0; b < 2; b++) {
     cudaEventCreateWithFlags(&ctx->ev_computed[b], cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&ctx->ev_offsets[b], cudaEventDisableTiming);
     cudaEventCreateWithFlags(&ctx->ev_copied[b], cudaEventDisableTiming);
   }
   *out = ctx;
@@ -102,8 +114,10 @@ void irt_ctx_destroy(irt_ctx *ctx) {
   if (ctx->scratch) cudaFree(ctx->scratch);
   if (ctx->arena) cudaFree(ctx->arena);
   if (ctx->io) cudaFree(ctx->io);
+  if (ctx->pinned) cudaFreeHost(ctx->pinned);
   for (int b = 0; b < 2; b++) {
     if (ctx->ev_computed[b]) cudaEventDestroy(ctx->ev_computed[b]);
+    if (ctx->ev_offsets[b]) cudaEventDestroy(ctx->ev_offsets[b]);
     if (ctx->ev_copied[b]) cudaEventDestroy(ctx->ev_copied[b]);
   }
   if (ctx->stream) cudaStreamDestroy(ctx->stream);

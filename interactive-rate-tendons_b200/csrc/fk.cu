@@ -318,9 +318,9 @@ struct RotZ {
 };
 
 template <int NT>
-__device__ __forceinline__ void emit_node(const irt_fk_outputs &o, int64_t cfg, int cap_pts, int k,
+__device__ __forceinline__ void emit_node(const irt_fk_outputs &o, int64_t row_base, int k,
                                           double t, const FkState<NT> &x, const RotZ &rz) {
-  const int64_t row = cfg * cap_pts + k;
+  const int64_t row = row_base + k;
   const double p0 = x.P(0), p1 = x.P(1), p2 = x.P(2);
   double px = p0, py = p1;
   if (rz.on) {
@@ -352,7 +352,8 @@ __device__ __forceinline__ void emit_node(const irt_fk_outputs &o, int64_t cfg, 
 template <int NT, bool RETRACT>
 __global__ void __launch_bounds__(FK_THREADS, FK_MIN_BLOCKS)
 fk_rk4_fp64_kernel(const RobotDev rb, const double *__restrict__ states, int state_size, int64_t n,
-                   int cap_pts, const irt_fk_outputs o, const int32_t *__restrict__ perm) {
+                   int cap_pts, const irt_fk_outputs o, const int32_t *__restrict__ perm,
+                   const int64_t *__restrict__ row_off) {
   extern __shared__ double smem[];
   double *tab = smem;                                // [n_table][NT][6]
   double *head = smem + (size_t)rb.n_table * NT * 6; // [4][NT][6]
@@ -367,6 +368,8 @@ fk_rk4_fp64_kernel(const RobotDev rb, const double *__restrict__ states, int sta
   const bool in_range = gi < n;
   const int64_t cfg = in_range ? (perm ? (int64_t)perm[gi] : gi) : 0;
   const double *st = states + cfg * state_size;
+  // first output row of this configuration: dense [n][cap_pts] layout, or packed rows (row_off[cfg])
+  const int64_t row_base = row_off ? (in_range ? row_off[cfg] : 0) : cfg * cap_pts;
 
   double tau[NT];
 #pragma unroll
@@ -505,7 +508,7 @@ fk_rk4_fp64_kernel(const RobotDev rb, const double *__restrict__ states, int sta
   // repeated while t_next - t > eps).  Then the regular steps node q -> node q-1.  All steps run
   // through ONE rk4_step call site in a loop that is end-aligned across the warp, so that every
   // lane is at the same regular step q in the same iteration (table reads are broadcasts).
-  if (run) emit_node<NT>(o, cfg, cap_pts, 0, s_start, x, rz);
+  if (run) emit_node<NT>(o, row_base, 0, s_start, x, rz);
   int nhead = 0;
   double hh0 = 0.0, hh1 = 0.0;
   const double *hd0 = head, *hd1 = head + NT * 6, *hd2 = head + 2 * NT * 6, *hd3 = head + 3 * NT * 6;
@@ -569,7 +572,7 @@ fk_rk4_fp64_kernel(const RobotDev rb, const double *__restrict__ states, int sta
         emit_idx = -1;
       }
       rk4_step<NT>(x, tau, Kse, Kbt, h, p0, p1, p2);
-      if (emit_idx >= 0) emit_node<NT>(o, cfg, cap_pts, emit_idx, rb.node_t[K - emit_idx], x, rz);
+      if (emit_idx >= 0) emit_node<NT>(o, row_base, emit_idx, rb.node_t[K - emit_idx], x, rz);
     }
   }
 
@@ -577,7 +580,7 @@ fk_rk4_fp64_kernel(const RobotDev rb, const double *__restrict__ states, int sta
   int npts = 0;
   if (degenerate) {
     npts = 1;
-    emit_node<NT>(o, cfg, cap_pts, 0, s_start, x, rz);  // p = 0, R = I, v = e3, u = 0
+    emit_node<NT>(o, row_base, 0, s_start, x, rz);  // p = 0, R = I, v = e3, u = 0
   } else if (run) {
     npts = K + 1;
   }
@@ -645,6 +648,26 @@ __global__ void fk_count_nodes_kernel(const RobotDev rb, const double *__restric
     if (sh[k]) atomicAdd(&hist[k], sh[k]);
 }
 
+__global__ void fk_row_count_kernel(const RobotDev rb, const double *__restrict__ states, int state_size,
+                                    int64_t n, int64_t *__restrict__ counts) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  int npts = rb.Kfull + 1;
+  if (rb.enable_retraction) {
+    double s = states[i * state_size + state_size - 1];
+    if (!(s >= -rb.dL)) {
+      npts = 0;
+    } else {
+      if (s > rb.L) s = rb.L;
+      int K = 0;
+      const double lim = rb.L - (rb.dL / 2);
+      for (double p = s; p <= lim; p += rb.dL) K++;
+      npts = (K > rb.Kfull) ? 0 : ((s == rb.L) ? 1 : K + 1);
+    }
+  }
+  counts[i] = npts;
+}
+
 __global__ void fk_bucket_scan_kernel(int32_t *hist, int nb) {
   // exclusive scan in DESCENDING key order; hist[k] becomes the first slot of bucket k
   if (threadIdx.x == 0 && blockIdx.x == 0) {
@@ -668,7 +691,7 @@ __global__ void fk_bucket_scatter_kernel(const int32_t *__restrict__ keys, int64
 
 template <int NT>
 int launch_nt(irt_ctx *ctx, const irt_robot *rb, const double *d_states, int64_t n, int cap_pts,
-              const irt_fk_outputs &o, const int32_t *d_perm, cudaStream_t st) {
+              const irt_fk_outputs &o, const int32_t *d_perm, const int64_t *d_row_off, cudaStream_t st) {
   const RobotDev &d = rb->dev;
   size_t smem = ((size_t)d.n_table + 4) * NT * 6 * sizeof(double);
 #if FK_SMEM_ACC >= 1
@@ -678,11 +701,11 @@ int launch_nt(irt_ctx *ctx, const irt_robot *rb, const double *d_states, int64_t
   if (d.enable_retraction) {
     auto k = fk_rk4_fp64_kernel<NT, true>;
     IRT_CUDA(ctx, cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k<<<(unsigned)blocks, FK_THREADS, smem, st>>>(d, d_states, rb->state_size, n, cap_pts, o, d_perm);
+    k<<<(unsigned)blocks, FK_THREADS, smem, st>>>(d, d_states, rb->state_size, n, cap_pts, o, d_perm, d_row_off);
   } else {
     auto k = fk_rk4_fp64_kernel<NT, false>;
     IRT_CUDA(ctx, cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k<<<(unsigned)blocks, FK_THREADS, smem, st>>>(d, d_states, rb->state_size, n, cap_pts, o, d_perm);
+    k<<<(unsigned)blocks, FK_THREADS, smem, st>>>(d, d_states, rb->state_size, n, cap_pts, o, d_perm, d_row_off);
   }
   IRT_LAUNCHED(ctx);
   IRT_CUDA(ctx, cudaGetLastError());
@@ -691,9 +714,22 @@ int launch_nt(irt_ctx *ctx, const irt_robot *rb, const double *d_states, int64_t
 
 }  // namespace
 
+// Rows (backbone points) every configuration will emit, for the packed output layout: the same node
+// count rule as the FK kernel (util::range's accumulation; 1 for the degenerate s == L shape; 0 for a
+// state outside the reference's state space).
+int fk_row_counts(irt_ctx *ctx, const irt_robot *rb, const double *d_states, int64_t n,
+                  int64_t *d_counts, cudaStream_t st) {
+  if (n <= 0) return IRT_OK;
+  const int T = 256;
+  fk_row_count_kernel<<<(unsigned)((n + T - 1) / T), T, 0, st>>>(rb->dev, d_states, rb->state_size, n, d_counts);
+  IRT_LAUNCHED(ctx);
+  IRT_CUDA(ctx, cudaGetLastError());
+  return IRT_OK;
+}
+
 // d_perm == nullptr: when retraction is enabled a bucket permutation is built in ctx scratch.
 int fk_launch(irt_ctx *ctx, const irt_robot *rb, const double *d_states, int64_t n, int cap_pts,
-              const irt_fk_outputs &o, const int32_t *d_perm, cudaStream_t st) {
+              const irt_fk_outputs &o, const int32_t *d_perm, cudaStream_t st, const int64_t *d_row_off) {
   if (n <= 0) return IRT_OK;
   if (n > 0x7fffffffLL) return irt_fail(ctx, IRT_ERR_INVALID_ARGUMENT, "batch too large");
   const RobotDev &d = rb->dev;
@@ -721,18 +757,18 @@ int fk_launch(irt_ctx *ctx, const irt_robot *rb, const double *d_states, int64_t
     d_perm = perm;
   }
   switch (d.n_tendons) {
-    case 1: return launch_nt<1>(ctx, rb, d_states, n, cap_pts, o, d_perm, st);
-    case 2: return launch_nt<2>(ctx, rb, d_states, n, cap_pts, o, d_perm, st);
-    case 3: return launch_nt<3>(ctx, rb, d_states, n, cap_pts, o, d_perm, st);
-    case 4: return launch_nt<4>(ctx, rb, d_states, n, cap_pts, o, d_perm, st);
-    case 5: return launch_nt<5>(ctx, rb, d_states, n, cap_pts, o, d_perm, st);
-    case 6: return launch_nt<6>(ctx, rb, d_states, n, cap_pts, o, d_perm, st);
-    case 7: return launch_nt<7>(ctx, rb, d_states, n, cap_pts, o, d_perm, st);
-    case 8: return launch_nt<8>(ctx, rb, d_states, n, cap_pts, o, d_perm, st);
-    case 9: return launch_nt<9>(ctx, rb, d_states, n, cap_pts, o, d_perm, st);
-    case 10: return launch_nt<10>(ctx, rb, d_states, n, cap_pts, o, d_perm, st);
-    case 11: return launch_nt<11>(ctx, rb, d_states, n, cap_pts, o, d_perm, st);
-    case 12: return launch_nt<12>(ctx, rb, d_states, n, cap_pts, o, d_perm, st);
+    case 1: return launch_nt<1>(ctx, rb, d_states, n, cap_pts, o, d_perm, d_row_off, st);
+    case 2: return launch_nt<2>(ctx, rb, d_states, n, cap_pts, o, d_perm, d_row_off, st);
+    case 3: return launch_nt<3>(ctx, rb, d_states, n, cap_pts, o, d_perm, d_row_off, st);
+    case 4: return launch_nt<4>(ctx, rb, d_states, n, cap_pts, o, d_perm, d_row_off, st);
+    case 5: return launch_nt<5>(ctx, rb, d_states, n, cap_pts, o, d_perm, d_row_off, st);
+    case 6: return launch_nt<6>(ctx, rb, d_states, n, cap_pts, o, d_perm, d_row_off, st);
+    case 7: return launch_nt<7>(ctx, rb, d_states, n, cap_pts, o, d_perm, d_row_off, st);
+    case 8: return launch_nt<8>(ctx, rb, d_states, n, cap_pts, o, d_perm, d_row_off, st);
+    case 9: return launch_nt<9>(ctx, rb, d_states, n, cap_pts, o, d_perm, d_row_off, st);
+    case 10: return launch_nt<10>(ctx, rb, d_states, n, cap_pts, o, d_perm, d_row_off, st);
+    case 11: return launch_nt<11>(ctx, rb, d_states, n, cap_pts, o, d_perm, d_row_off, st);
+    case 12: return launch_nt<12>(ctx, rb, d_states, n, cap_pts, o, d_perm, d_row_off, st);
     default:
       return irt_fail(ctx, IRT_ERR_UNSUPPORTED, "no fk kernel for %d tendons (1..%d supported)",
                       d.n_tendons, IRT_MAX_TENDONS);

@@ -84,7 +84,8 @@ constexpr int SC_FILTER_WARPS = 8;
 
 __global__ void __launch_bounds__(SC_FILTER_WARPS * 32)
 self_collision_filter_kernel(const double *__restrict__ p, const int32_t *__restrict__ npts, int64_t n,
-                             int cap_pts, double r, int32_t *__restrict__ cand, int32_t *__restrict__ n_cand) {
+                             int cap_pts, double r, int32_t *__restrict__ cand, int32_t *__restrict__ n_cand,
+                             const int64_t *__restrict__ row_off) {
   extern __shared__ float fsm[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   float4 *seg = reinterpret_cast<float4 *>(fsm) + (size_t)warp * cap_pts;  // (mid.x, mid.y, mid.z, half length)
@@ -95,7 +96,7 @@ self_collision_filter_kernel(const double *__restrict__ p, const int32_t *__rest
     const int N = npts[shape];
     __syncwarp();
     if (N <= 3) continue;  // collision.cpp:14 and the loop bounds a < N-3
-    const double *src = p + shape * (int64_t)cap_pts * 3;
+    const double *src = p + (row_off ? row_off[shape] : shape * (int64_t)cap_pts) * 3;   // packed or dense rows
     const int ncap = N - 1;
     float maxhl = 0.0f;
     for (int i = lane; i < ncap; i += 32) {
@@ -136,7 +137,8 @@ self_collision_filter_kernel(const double *__restrict__ p, const int32_t *__rest
 __global__ void __launch_bounds__(SC_WARPS * 32)
 self_collision_kernel(const double *__restrict__ p, const int32_t *__restrict__ npts, int64_t n,
                       int cap_pts, double r, uint32_t *__restrict__ flags,
-                      const int32_t *__restrict__ cand, const int32_t *__restrict__ n_cand) {
+                      const int32_t *__restrict__ cand, const int32_t *__restrict__ n_cand,
+                      const int64_t *__restrict__ row_off) {
   extern __shared__ double sm[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   // per warp: xyz[cap*3], acc[cap], chunk centre xyz + radius [4 * nchunk_max]
@@ -152,7 +154,7 @@ self_collision_kernel(const double *__restrict__ p, const int32_t *__restrict__ 
     const int N = npts[shape];
     __syncwarp();
     if (N <= 2) continue;  // collision.cpp:14
-    const double *src = p + shape * (int64_t)cap_pts * 3;
+    const double *src = p + (row_off ? row_off[shape] : shape * (int64_t)cap_pts) * 3;   // packed or dense rows
     for (int i = lane; i < N * 3; i += 32) px[i] = src[i];
     __syncwarp();
     // segment lengths (the reference's per-point distance, collision.cpp:22-29); acc[] is only
@@ -248,7 +250,7 @@ self_collision_kernel(const double *__restrict__ p, const int32_t *__restrict__ 
 
 int self_collision_launch(irt_ctx *ctx, const irt_robot *rb, const double *d_p,
                           const int32_t *d_npts, int64_t n, int cap_pts, uint32_t *d_flags,
-                          cudaStream_t st) {
+                          cudaStream_t st, const int64_t *d_row_off) {
   if (n <= 0) return IRT_OK;
   if (n > 0x7fffffffLL) return irt_fail(ctx, IRT_ERR_INVALID_ARGUMENT, "batch too large");
   if (cap_pts > IRT_CAP_PTS_MAX) return irt_fail(ctx, IRT_ERR_CAPACITY, "cap_pts=%d too large", cap_pts);
@@ -273,7 +275,7 @@ int self_collision_launch(irt_ctx *ctx, const irt_robot *rb, const double *d_p,
       IRT_CUDA(ctx, cudaFuncSetAttribute(self_collision_filter_kernel,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem));
     self_collision_filter_kernel<<<(unsigned)fb, SC_FILTER_WARPS * 32, fsmem, st>>>(d_p, d_npts, n, cap_pts,
-                                                                                  rb->dev.r, d_cand, d_ncand);
+                                                                                  rb->dev.r, d_cand, d_ncand, d_row_off);
   }
   IRT_LAUNCHED(ctx);
   // stage 2 runs over however many candidates stage 1 found (count stays on the device)
@@ -281,7 +283,7 @@ int self_collision_launch(irt_ctx *ctx, const irt_robot *rb, const double *d_p,
   const int64_t max_blocks = (int64_t)ctx->sm_count * 4;
   if (blocks > max_blocks) blocks = max_blocks;
   self_collision_kernel<<<(unsigned)blocks, SC_WARPS * 32, smem, st>>>(d_p, d_npts, n, cap_pts, rb->dev.r,
-                                                                      d_flags, d_cand, d_ncand);
+                                                                      d_flags, d_cand, d_ncand, d_row_off);
   IRT_LAUNCHED(ctx);
   IRT_CUDA(ctx, cudaGetLastError());
   return IRT_OK;

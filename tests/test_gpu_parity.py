@@ -768,3 +768,38 @@ def test_full_size_roadmap_generation_properties(irt, ctx, orc, wl):
         assert np.array_equal(bits[int(off[e]):int(off[e + 1])], ob[int(oo[j]):int(oo[j + 1])])
     assert np.array_equal(info["flags"][sample], oinfo["flags"])
     assert np.array_equal(info["t_last"][sample], oinfo["t_last"])
+
+
+@pytest.mark.parametrize("robot,rot,n", [("b", True, 250_000), ("a", False, 5000), ("b", False, 1)])
+def test_fk_packed_outputs_equal_dense(irt, ctx, wl, robot, rot, n):
+    """irt_fk_batch_packed: shape i's rows [row_offsets[i], row_offsets[i+1]) are exactly the first
+    npts[i] rows of the dense form (bit for bit, across chunk boundaries of the pipeline), every per-shape
+    output identical, self-collision flags computed from the packed rows."""
+    spec = wl.robot_a(0.005) if robot == "a" else wl.robot_b(0.005, rotation=rot)
+    rb = irt.Robot(ctx, spec)
+    st = wl.sample_states(spec, n, stream=77)
+    if spec.get("enable_retraction") and n >= 8:
+        L = spec["L"]
+        st[0, -1], st[1, -1], st[2, -1], st[3, -1], st[4, -1] = L, L + 0.01, 0.1995, -0.001, -0.01
+    want = ("p", "R", "t", "npts", "L", "L_i", "tip", "uv", "flags", "iters", "nsteps")
+    if n > 100_000:
+        want = ("p", "t", "npts", "L_i", "tip", "flags")
+    d = rb.shape_batch(st, want=want)
+    k = rb.shape_batch_packed(st, want=want)
+    ro = k["row_offsets"]
+    assert ro[0] == 0 and np.array_equal(np.diff(ro), d["npts"]) and k["rows"] == int(d["npts"].sum())
+    for name in ("npts", "L", "L_i", "tip", "uv", "flags", "iters", "nsteps"):
+        if name in want:
+            assert np.array_equal(d[name], k[name]), name
+    cap = rb.max_points
+    mask = np.arange(cap)[None, :] < d["npts"][:, None]
+    assert np.array_equal(d["p"][mask], k["p"][:k["rows"]])
+    assert np.array_equal(d["t"][mask], k["t"][:k["rows"]])
+    if "R" in want:   # dense R is returned as [n][cap][row][col]; packed stays column-major 9-vectors
+        assert np.array_equal(d["R"].transpose(0, 1, 3, 2).reshape(n, cap, 9)[mask], k["R"][:k["rows"]])
+    # capacity error: one row too few
+    if k["rows"] > 0:
+        with pytest.raises(irt.IrtError) as ei:
+            rb.shape_batch_packed(st, want=("p", "npts"), cap_rows=k["rows"] - 1)
+        assert ei.value.status == irt.IRT_ERR_CAPACITY
+    assert rb.shape_batch_packed(st[:0], want=("p", "npts"))["rows"] == 0
