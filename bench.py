@@ -7,7 +7,7 @@
 A "step" is one pass of batched forward kinematics over config C2 of BASELINE.json
 (6-tendon helical robot with retraction, 1M configurations per GPU) with inputs resident in
 HBM.  The same run also measures the roadmap voxel check (K3) over a config-C4-sized roadmap
-(1M valid vertices, exact k=10 nearest-neighbour edges, ~6M edges) built with the real pipeline, the end-to-end FK rate through the host-pointer C ABI, and the CPU baseline
+(1M valid vertices, exact k=17 nearest-neighbour edges, ~10M undirected edges) built with the real pipeline, the end-to-end FK rate through the host-pointer C ABI, and the CPU baseline
 (the oracle restatement of the reference, timed on this box's host cores).
 Prints ONE JSON line on rank 0.
 """
@@ -227,7 +227,10 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--roadmap-vertices", type=int, default=1_000_000,
-                    help="vertices of the roadmap used for the K3 sweep (k=10 nearest-neighbour edges)")
+                    help="vertices of the roadmap used for the K3 sweep (exact --roadmap-k nearest-neighbour edges)")
+    ap.add_argument("--roadmap-k", type=int, default=17,
+                    help="k of the exact k-NN that generates the roadmap topology; 17 gives ~10.4 undirected "
+                         "edges per vertex after dedupe = config C4's ~10M edges at 1M vertices")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--skip-roadmap", action="store_true")
     args = ap.parse_args()
@@ -411,7 +414,7 @@ def main():
         nv = args.roadmap_vertices
         t_build0 = time.perf_counter()
         prm.createRoadmap(nv, lambda cnt, rnd: wl.sample_states(spec3, cnt, stream=200 + rnd),
-                          lambda st: knn_edges_gpu(torch, st, spec3, 10, dev))
+                          lambda st: knn_edges_gpu(torch, st, spec3, args.roadmap_k, dev))
         t_sample = time.perf_counter() - t_build0
         t1 = time.perf_counter()
         prm.precomputeVertexVoxelCache()
