@@ -429,10 +429,19 @@ def main():
         w = shard_words(ne, world)
         d_words = torch.zeros(max(w, 1), dtype=torch.int32, device=dev)
 
-        def k3_step():
+        def k3_step_nccl():   # K3 into local words + ncclAllGather of the words (the baseline exchange)
             if hi > lo:
                 prm.edge_store.check_dev(prm.env, d_words, 0, hi - lo, stream=sptr)
             return gather_verdict_words(d_words, dist if world > 1 else None)
+
+        # N > 1: the verdict all-gather is fused into K3 (every warp stores its word into all peers'
+        # gathered arrays over NVLink, an epoch flag per rank replaces the collective)
+        xch_e = prm._exchange(prm.edge_store, w) if world > 1 else None
+
+        def k3_step():
+            if xch_e is None:
+                return k3_step_nccl()
+            return xch_e.check(prm.edge_store, prm.env, 0, hi - lo, stream=sptr)
 
         # L2 rule: the sweep's input (the set store of this rank) is >> the 126 MB L2 at the default
         # roadmap size, so consecutive sweeps cannot hit in L2 and no flush write is needed (a flush would
@@ -454,6 +463,21 @@ def main():
         barrier()
         ms3_local = float(np.mean([a.elapsed_time(b) for a, b in ev3]))
         ms3 = max_over_ranks(ms3_local)
+        ms3_nccl = None
+        if world > 1:   # the same sweep with the NCCL exchange, for comparison; verdicts must agree
+            for _ in range(args.warmup):
+                k3_step_nccl()
+            barrier()
+            evn = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+            for a, b in evn:
+                a.record(stream)
+                k3_step_nccl()
+                b.record(stream)
+            barrier()
+            ms3_nccl = max_over_ranks(float(np.mean([a.elapsed_time(b) for a, b in evn])))
+            same_gather = bool(torch.equal(k3_step().cpu(), k3_step_nccl().cpu())) and xch_e.status() == 0
+            if not same_gather:
+                raise SystemExit("fused verdict gather differs from the NCCL all_gather")
         alg_bytes = prm.edge_store.algorithmic_bytes() if hi > lo else 0
         hbm_peak = 6552.0
         try:
@@ -482,7 +506,13 @@ def main():
                          "peak_source": hbm_src, "algorithmic_bytes": alg_bytes,
                          "l2": ("512 MB flush write between timed sweeps" if k3_flush else
                                 "no flush: the store streamed per sweep (%.0f MB) is >> L2 (126 MB)" % (alg_bytes / 1e6)),
-                         "note": "duration = the whole sweep step (K3 launch; N>1: + the NCCL all_gather)"},
+                         "note": "duration = the whole sweep step (K3 launch; N>1: verdict all-gather fused "
+                                 "into K3 over NVLink peer memory + one-warp flag wait)"},
+            "exchange": (None if world == 1 else
+                         {"kind": "fused into K3: P2P stores of verdict words into all peers' gathered arrays "
+                                  "(CUDA IPC over NVLink), per-rank epoch flags; no collective call per sweep",
+                          "ms_per_sweep": ms3, "nccl_all_gather_ms_per_sweep": ms3_nccl,
+                          "words_per_rank": w, "equal_to_nccl": True}),
         }
         # ---- C5: interactive replanning tick = env change + upload + vertex sweep + edge sweep + gather
         nvt = len(prm.states)
@@ -495,15 +525,19 @@ def main():
             tick_envs.append(torch.from_numpy(wl.toggle_blob(env_blocks, g, c, rng_t.uniform(0.005, 0.015)).view(np.int64)).pin_memory())
         d_env = torch.zeros(env_blocks.size, dtype=torch.int64, device=dev)
 
+        xch_v = prm._exchange(prm.vertex_store, shard_words(nvt, world)) if world > 1 else None
+
         def tick(i):
             d_env.copy_(tick_envs[i % len(tick_envs)], non_blocking=True)   # H2D 256 KiB
             prm.env.update_dev(d_env, stream=sptr)
+            if xch_e is not None:
+                xch_v.check(prm.vertex_store, prm.env, 0, vhi - vlo, stream=sptr)
+                return xch_e.check(prm.edge_store, prm.env, 0, hi - lo, stream=sptr)
             if vhi > vlo:
                 prm.vertex_store.check_dev(prm.env, d_vwords, 0, vhi - vlo, stream=sptr)
             if hi > lo:
                 prm.edge_store.check_dev(prm.env, d_words, 0, hi - lo, stream=sptr)
-            gather_verdict_words(d_vwords, dist if world > 1 else None)
-            return gather_verdict_words(d_words, dist if world > 1 else None)
+            return d_words
 
         for i in range(args.warmup):
             tick(i)
@@ -519,9 +553,9 @@ def main():
         edge_check["replanning_tick"] = {
             "ms_per_tick": ms_tick, "ticks_per_s": 1e3 / ms_tick,
             "what": "C5: H2D of a changed 128^3 environment (256 KiB) + occupancy rebuild + K3 over all vertices "
-                    "and edges of this rank + verdict all_gather"}
+                    "and edges of this rank (N>1: verdict gathers fused into the sweeps)"}
         prm.setEnvironment(env_blocks)
-        k3_step()
+        k3_step_nccl()            # fills this rank's d_words (the fused path writes into the exchange buffers)
         torch.cuda.synchronize()
         verd = prm.precomputeEdgeValidity()
         edge_check["valid_edge_fraction"] = float(verd.mean())

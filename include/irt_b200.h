@@ -297,6 +297,23 @@ int irt_check_sets_dev(irt_ctx *ctx, const irt_setstore *store, const irt_env *e
  * size-independent checksum and for reporting. */
 int irt_check_sets_popcount(irt_ctx *ctx, const irt_setstore *store, const irt_env *env,
                             int64_t begin, int64_t end, uint64_t *stats);
+/* ---- multi-GPU: verdict all-gather fused into K3 over peer memory (NVLink / NVSwitch) -----------
+ * One process per GPU.  Every rank creates an exchange buffer, publishes its handle (host-side
+ * all-gather of irt_xchg_handle_size() bytes, e.g. with torch.distributed / MPI) and connects.  A
+ * sweep then stores every verdict word straight into all peers' copies of the gathered array and
+ * raises a per-rank epoch flag; a one-warp kernel on the same stream waits for all flags.  Replaces
+ * K3 + ncclAllGather of the verdict words (VoxelCachedLazyPRM.cpp:1584-1591 sharded over GPUs).
+ * slot_words = words every rank contributes (the same on all ranks, >= ceil(shard sets / 32)). */
+typedef struct irt_xchg irt_xchg;
+int irt_xchg_create(irt_ctx *ctx, int rank, int world, int64_t slot_words, irt_xchg **out);
+void irt_xchg_destroy(irt_xchg *x);
+int irt_xchg_handle_size(void);
+int irt_xchg_export(irt_xchg *x, void *handle);
+int irt_xchg_connect(irt_xchg *x, const void *handles /* [world][handle_size], rank order */);
+int irt_check_sets_allgather_dev(irt_ctx *ctx, const irt_setstore *store, const irt_env *env,
+                                 int64_t begin, int64_t end, irt_xchg *x, void *stream,
+                                 const uint32_t **d_gathered /* [world][slot_words] device words */);
+int irt_xchg_status(irt_xchg *x); /* 0, or 1 + rank of a peer whose flag never arrived */
 /* algorithmic bytes one irt_check_sets call over [begin,end) moves:
  * sum(12*nb + 8) + 8*Nb^3 + ceil(n/8) */
 int64_t irt_check_sets_algorithmic_bytes(const irt_setstore *store, int64_t begin, int64_t end);

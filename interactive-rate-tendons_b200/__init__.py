@@ -106,6 +106,8 @@ ABI_SYMBOLS = [
     "irt_valid_segment_count",
     "irt_check_sets", "irt_check_sets_dev", "irt_check_sets_popcount",
     "irt_check_sets_algorithmic_bytes",
+    "irt_xchg_create", "irt_xchg_destroy", "irt_xchg_handle_size", "irt_xchg_export", "irt_xchg_connect",
+    "irt_check_sets_allgather_dev", "irt_xchg_status",
     "irt_rmp_read", "irt_rmp_write", "irt_rmp_free",
 ]
 
@@ -172,6 +174,13 @@ def lib():
         "irt_check_sets_dev": (i32, [vp, vp, vp, i64, i64, vp, vp]),
         "irt_check_sets_popcount": (i32, [vp, vp, vp, i64, i64, vp]),
         "irt_check_sets_algorithmic_bytes": (i64, [vp, i64, i64]),
+        "irt_xchg_create": (i32, [vp, i32, i32, i64, C.POINTER(vp)]),
+        "irt_xchg_destroy": (None, [vp]),
+        "irt_xchg_handle_size": (i32, []),
+        "irt_xchg_export": (i32, [vp, vp]),
+        "irt_xchg_connect": (i32, [vp, vp]),
+        "irt_check_sets_allgather_dev": (i32, [vp, vp, vp, i64, i64, vp, vp, C.POINTER(vp)]),
+        "irt_xchg_status": (i32, [vp]),
         "irt_rmp_read": (i32, [C.c_char_p, C.POINTER(C.POINTER(Rmp))]),
         "irt_rmp_write": (i32, [C.c_char_p, C.POINTER(Rmp)]),
         "irt_rmp_free": (None, [C.POINTER(Rmp)]),
@@ -575,6 +584,63 @@ class SetStore:
     def algorithmic_bytes(self, begin=0, end=None):
         end = self.num_sets if end is None else end
         return int(self.ctx.L.irt_check_sets_algorithmic_bytes(self.h, begin, end))
+
+
+class _DeviceWords:
+    """zero-copy view of device words for torch.as_tensor(..., device="cuda")"""
+
+    def __init__(self, ptr, n):
+        self.__cuda_array_interface__ = {"shape": (int(n),), "typestr": "<i4", "data": (int(ptr), False),
+                                         "version": 2}
+
+
+class VerdictExchange:
+    """Verdict all-gather fused into K3 over peer memory (include/irt_b200.h, irt_xchg_*).
+    `dist` is an initialised torch.distributed (NCCL) used once, to publish the IPC handles."""
+
+    def __init__(self, ctx, rank, world, slot_words, dist=None):
+        self.ctx, self.rank, self.world, self.slot_words = ctx, rank, world, int(slot_words)
+        h = C.c_void_p()
+        ctx.check(ctx.L.irt_xchg_create(ctx.h, rank, world, self.slot_words, C.byref(h)))
+        self.h = h
+        if world > 1:
+            import torch
+            hs = ctx.L.irt_xchg_handle_size()
+            mine = np.zeros(hs, dtype=np.uint8)
+            ctx.check(ctx.L.irt_xchg_export(self.h, _ptr(mine)))
+            dev = torch.device("cuda", ctx.device)
+            t = torch.from_numpy(mine).to(dev)
+            allh = torch.empty(world * hs, dtype=torch.uint8, device=dev)
+            dist.all_gather_into_tensor(allh, t)
+            handles = np.ascontiguousarray(allh.cpu().numpy())
+            ctx.check(ctx.L.irt_xchg_connect(self.h, _ptr(handles)))
+            dist.barrier()   # every rank has mapped every buffer before the first sweep
+
+    def close(self):
+        if getattr(self, "h", None) and getattr(self.ctx, "h", None):
+            self.ctx.L.irt_xchg_destroy(self.h)
+        self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def check(self, store, env, begin=0, end=None, stream=None):
+        """K3 + fused all-gather (asynchronous on `stream`).  Returns a zero-copy torch int32 view
+        [world * slot_words] of this sweep's gathered verdict words (valid until the sweep after next)."""
+        import torch
+        end = store.num_sets if end is None else end
+        out = C.c_void_p()
+        self.ctx.check(self.ctx.L.irt_check_sets_allgather_dev(
+            self.ctx.h, store.h, env.h, int(begin), int(end), self.h,
+            C.c_void_p(stream) if stream else None, C.byref(out)))
+        return torch.as_tensor(_DeviceWords(out.value, self.world * self.slot_words),
+                               device=torch.device("cuda", self.ctx.device))
+
+    def status(self):
+        return int(self.ctx.L.irt_xchg_status(self.h))
 
 
 def _arr(ptr, n, dtype):

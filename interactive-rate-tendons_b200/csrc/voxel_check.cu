@@ -72,6 +72,7 @@ __global__ void count_nonzero_kernel(const uint64_t *__restrict__ blocks, int64_
 // double-buffered by tile parity so a chunk costs two __syncthreads.
 constexpr int K3_CHUNK_LEAVES = 32768;                      // hit-bitmap capacity per buffer (4 KiB)
 constexpr int K3_BM_WORDS = K3_CHUNK_LEAVES / 32 + 2;       // +1 straddle word, +1 pad
+constexpr int K3_GATHER_TILES = 256;                         // staged verdict words per CTA: 8 KiB
 constexpr int K3_SMEM_FIXED_WORDS = 3 * K3_BM_WORDS + (3 * K3_BM_WORDS & 1) + 2 * 2 * (K3_THREADS + 2);
 
 // predicated 8-byte read-only load: the four environment look-ups of a quad are issued back to back
@@ -101,13 +102,50 @@ __device__ __forceinline__ ulonglong2 ld_stream(const ulonglong2 *p) {
   return v;
 }
 
-template <bool OCC_SMEM, bool STATS>
+// Verdict exchange fused into K3 (multi-GPU): every rank holds the gathered verdict array of ALL ranks
+// in a buffer its peers can write (CUDA IPC over NVLink).  A warp stores its verdict word straight into
+// every peer's copy; the last CTA to finish raises this rank's epoch flag on every peer.  No NCCL call,
+// no extra kernel between the sweep and its consumers except a one-warp flag wait.
+constexpr int IRT_MAX_PEERS = 16;
+struct XchgDev {
+  uint32_t *peer[IRT_MAX_PEERS];  // base of every rank's buffer as mapped in THIS process (own: local)
+  int world, rank, parity;
+  int64_t slot_words;             // words every rank contributes
+  uint32_t epoch;
+  unsigned int *done;             // local CTA counter
+  // buffer layout (uint32): words[2][world][slot_words], flags[2][world]
+  __device__ __forceinline__ uint32_t *words(int r) const {
+    return peer[r] + ((int64_t)parity * world + rank) * slot_words;
+  }
+  __device__ __forceinline__ uint32_t *flag(int r) const {
+    return peer[r] + (int64_t)2 * world * slot_words + parity * world + rank;
+  }
+};
+
+// last-CTA epilogue of a gathering kernel: data stores of all CTAs happen-before the flag stores
+__device__ __forceinline__ void xchg_signal(const XchgDev &x) {
+  // the CTA barrier orders every thread's peer stores before thread 0's system-scope fence (fences are
+  // cumulative), so ONE fence per CTA publishes them all: 256 per-thread MEMBAR.SYS cost ~10 us per sweep
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence_system();
+    const unsigned prev = atomicAdd(x.done, 1u);
+    if (prev == gridDim.x - 1) {
+      *x.done = 0;
+      __threadfence_system();
+      for (int r = 0; r < x.world; r++)
+        asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(x.flag(r)), "r"(x.epoch) : "memory");
+    }
+  }
+}
+
+template <bool OCC_SMEM, bool STATS, bool GATHER = false>
 __global__ void __launch_bounds__(K3_THREADS, 4)
 voxel_and_popc_kernel(const uint32_t *__restrict__ keys, const uint64_t *__restrict__ bits,
                       const uint64_t *__restrict__ offsets, const uint64_t *__restrict__ env,
                       const uint32_t *__restrict__ occ, int occ_words,
                       int64_t set_begin, int64_t set_end, uint32_t *__restrict__ verdict,
-                      unsigned long long *__restrict__ stats) {
+                      unsigned long long *__restrict__ stats, const XchgDev xd) {
   // [0, 3*K3_BM_WORDS): three hit bitmaps (rotating, so a chunk costs ONE __syncthreads: the buffer
   // cleared during chunk k was last read two barriers ago); then two tiles of set offsets
   // (cp.async prefetch of the next tile's CSR offsets while this tile streams); then the
@@ -139,6 +177,21 @@ voxel_and_popc_kernel(const uint32_t *__restrict__ keys, const uint64_t *__restr
   cp_async_wait_all();
   __syncthreads();
   int hb = 0, mb = 0;   // current hit bitmap / offsets buffer
+  // GATHER: verdict words of the tiles this CTA has finished, [K3_GATHER_TILES][8]
+  uint32_t *s_gw = s_mem + OCC_OFF + (OCC_SMEM ? occ_words : 0);
+  int kt = 0, kt_base = 0;
+  auto flush_gathered = [&](int first_tile, int ntl) {   // block-uniform arguments
+    __syncthreads();
+    for (int idx = tid; idx < ntl * (K3_THREADS / 32); idx += K3_THREADS) {
+      const int64_t t = (int64_t)blockIdx.x + (int64_t)(first_tile + idx / (K3_THREADS / 32)) * gridDim.x;
+      const int64_t wi = t * (K3_THREADS / 32) + idx % (K3_THREADS / 32);
+      if (wi < nwords_out) {
+        const uint32_t v = s_gw[idx];
+        for (int r = 0; r < xd.world; r++) xd.words(r)[wi] = v;   // P2P stores over NVLink
+      }
+    }
+    __syncthreads();
+  };
 
   for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
     const uint64_t *my_off = s_off + mb * (K3_THREADS + 2);
@@ -239,7 +292,22 @@ voxel_and_popc_kernel(const uint32_t *__restrict__ keys, const uint64_t *__restr
     }
     const unsigned word = __ballot_sync(0xffffffffu, own);
     const int64_t wi = tile * (K3_THREADS / 32) + (tid >> 5);
-    if ((tid & 31) == 0 && wi < nwords_out) verdict[wi] = word;
+    if (GATHER) {
+      // stage this CTA's words in shared memory; they go to the peers as 32-byte runs (one tile = 8
+      // consecutive words) instead of one 4-byte NVLink write per warp
+      if ((tid & 31) == 0) s_gw[kt * (K3_THREADS / 32) + (tid >> 5)] = word;
+      if (++kt == K3_GATHER_TILES) { flush_gathered(kt_base, kt); kt_base += kt; kt = 0; }
+    } else if ((tid & 31) == 0 && wi < nwords_out) {
+      verdict[wi] = word;
+    }
+  }
+  if (GATHER) {
+    flush_gathered(kt_base, kt);
+    // padding words of this rank's slot (sets beyond the shard) read as "no collision" everywhere
+    for (int64_t wi = nwords_out + (int64_t)blockIdx.x * K3_THREADS + tid; wi < xd.slot_words;
+         wi += (int64_t)gridDim.x * K3_THREADS)
+      for (int r = 0; r < xd.world; r++) xd.words(r)[wi] = 0u;
+    xchg_signal(xd);
   }
   if (STATS) {
     for (int o = 16; o > 0; o >>= 1) {
@@ -251,6 +319,30 @@ voxel_and_popc_kernel(const uint32_t *__restrict__ keys, const uint64_t *__restr
       atomicAdd(&stats[1], nhit);
     }
   }
+}
+
+// a rank whose shard is empty still has to clear its slot and raise its flag
+__global__ void xchg_empty_shard_kernel(const XchgDev xd) {
+  for (int64_t wi = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; wi < xd.slot_words;
+       wi += (int64_t)gridDim.x * blockDim.x)
+    for (int r = 0; r < xd.world; r++) xd.words(r)[wi] = 0u;
+  xchg_signal(xd);
+}
+
+// one warp: lane r waits until rank r's flag of this parity shows `epoch`.  Bounded: a peer that never
+// arrives sets *err instead of hanging the GPU.
+__global__ void xchg_wait_kernel(const uint32_t *__restrict__ flags, int world, uint32_t epoch,
+                                 unsigned int *__restrict__ err) {
+  const int r = threadIdx.x;
+  if (r >= world) return;
+  const uint32_t *f = flags + r;
+  for (long it = 0; it < (1L << 24); it++) {
+    uint32_t v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(f) : "memory");
+    if (v == epoch) return;
+    __nanosleep(64);
+  }
+  atomicExch(err, 1u + (unsigned)r);
 }
 
 int ensure_store_capacity(irt_ctx *ctx, irt_setstore *s, int64_t n_sets, int64_t n_blocks) {
@@ -506,8 +598,8 @@ int irt_setstore_device_ptrs(const irt_setstore *s, const uint64_t **d_offsets,
 // ---- K3 ----------------------------------------------------------------------------------
 static int check_sets_impl(irt_ctx *ctx, const irt_setstore *store, const irt_env *env,
                            int64_t begin, int64_t end, uint32_t *d_verdict,
-                           unsigned long long *d_stats, cudaStream_t st) {
-  if (!ctx || !store || !env || !d_verdict) return IRT_ERR_INVALID_ARGUMENT;
+                           unsigned long long *d_stats, cudaStream_t st, const XchgDev *xd = nullptr) {
+  if (!ctx || !store || !env || (!d_verdict && !xd)) return IRT_ERR_INVALID_ARGUMENT;
   if (store->grid.Ng != env->grid.Ng)  // check_dims -- collision/VoxelOctree.cpp:46-53
     return irt_fail(ctx, IRT_ERR_INVALID_ARGUMENT, "voxel dimension mismatch (%d != %d)",
                     store->grid.Ng, env->grid.Ng);
@@ -515,6 +607,12 @@ static int check_sets_impl(irt_ctx *ctx, const irt_setstore *store, const irt_en
     return irt_fail(ctx, IRT_ERR_OUT_OF_RANGE, "set range [%lld,%lld) outside [0,%lld)",
                     (long long)begin, (long long)end, (long long)store->n_sets);
   const int64_t n = end - begin;
+  if (xd && (n == 0 || store->n_blocks == 0)) {   // nothing to test: clear the slot, raise the flag
+    xchg_empty_shard_kernel<<<8, 256, 0, st>>>(*xd);
+    IRT_LAUNCHED(ctx);
+    IRT_CUDA(ctx, cudaGetLastError());
+    return IRT_OK;
+  }
   if (n == 0) return IRT_OK;
   if (store->n_blocks == 0) {
     IRT_CUDA(ctx, cudaMemsetAsync(d_verdict, 0, (size_t)((n + 31) / 32) * 4, st));
@@ -533,17 +631,146 @@ static int check_sets_impl(irt_ctx *ctx, const irt_setstore *store, const irt_en
       IRT_CUDA(ctx, cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
     kfn<<<(unsigned)blocks, K3_THREADS, smem, st>>>(store->d_keys, store->d_bits, store->d_offsets, \
                                                     env->d_blocks, env->d_occ, occ_words, begin,   \
-                                                    end, d_verdict, d_stats);                      \
+                                                    end, d_verdict, d_stats, XchgDev());           \
   } while (0)
-  if (occ_smem) {
+#define K3_LAUNCH_GATHER(OS)                                                                       \
+  do {                                                                                             \
+    auto kfn = voxel_and_popc_kernel<OS, false, true>;                                             \
+    const size_t gsmem = smem + (size_t)K3_GATHER_TILES * (K3_THREADS / 32) * 4;                   \
+    if (gsmem > 48 * 1024)                                                                         \
+      IRT_CUDA(ctx, cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gsmem)); \
+    kfn<<<(unsigned)blocks, K3_THREADS, gsmem, st>>>(store->d_keys, store->d_bits, store->d_offsets, \
+                                                    env->d_blocks, env->d_occ, occ_words, begin,   \
+                                                    end, nullptr, nullptr, *xd);                   \
+  } while (0)
+  if (xd) {
+    // one resident wave: every CTA ends with a system-scope fence that holds its SM slot for the
+    // round trip of its peer stores; a second wave would pay that latency twice
+    if (blocks > (int64_t)ctx->sm_count * 4) blocks = (int64_t)ctx->sm_count * 4;
+    if ((n + 31) / 32 > xd->slot_words)
+      return irt_fail(ctx, IRT_ERR_CAPACITY, "shard of %lld sets exceeds the exchange slot (%lld words)",
+                      (long long)n, (long long)xd->slot_words);
+    if (occ_smem) K3_LAUNCH_GATHER(true); else K3_LAUNCH_GATHER(false);
+  } else if (occ_smem) {
     if (d_stats) K3_LAUNCH(true, true); else K3_LAUNCH(true, false);
   } else {
     if (d_stats) K3_LAUNCH(false, true); else K3_LAUNCH(false, false);
   }
+#undef K3_LAUNCH_GATHER
 #undef K3_LAUNCH
   IRT_LAUNCHED(ctx);
   IRT_CUDA(ctx, cudaGetLastError());
   return IRT_OK;
+}
+
+// ---- verdict exchange over peer memory (multi-GPU) ----------------------------------------------
+struct irt_xchg {
+  irt_ctx *ctx = nullptr;
+  int rank = 0, world = 1;
+  int64_t slot_words = 0;
+  uint32_t *local = nullptr;          // words[2][world][slot_words], flags[2][world]
+  uint32_t *peer[IRT_MAX_PEERS] = {};  // peers' buffers mapped here (peer[rank] == local)
+  bool opened[IRT_MAX_PEERS] = {};
+  unsigned int *d_done = nullptr;     // [0] CTA counter, [1] error word
+  uint32_t epoch = 0;
+  bool connected = false;
+};
+
+int irt_xchg_create(irt_ctx *ctx, int rank, int world, int64_t slot_words, irt_xchg **out) {
+  if (!ctx || !out || world < 1 || world > IRT_MAX_PEERS || rank < 0 || rank >= world || slot_words < 1)
+    return IRT_ERR_INVALID_ARGUMENT;
+  *out = nullptr;
+  IRT_CUDA(ctx, cudaSetDevice(ctx->device));
+  irt_xchg *x = new irt_xchg();
+  x->ctx = ctx; x->rank = rank; x->world = world; x->slot_words = slot_words;
+  const size_t bytes = ((size_t)2 * world * slot_words + (size_t)2 * world) * 4;
+  if (cudaMalloc(&x->local, bytes) != cudaSuccess || cudaMalloc(&x->d_done, 64) != cudaSuccess) {
+    irt_xchg_destroy(x);
+    return irt_fail(ctx, IRT_ERR_CUDA, "exchange buffer allocation failed");
+  }
+  cudaMemset(x->local, 0, bytes);
+  cudaMemset(x->d_done, 0, 64);
+  x->peer[rank] = x->local;
+  x->connected = (world == 1);
+  *out = x;
+  return IRT_OK;
+}
+
+void irt_xchg_destroy(irt_xchg *x) {
+  if (!x) return;
+  cudaSetDevice(x->ctx->device);
+  cudaDeviceSynchronize();
+  for (int r = 0; r < x->world; r++)
+    if (x->opened[r]) cudaIpcCloseMemHandle(x->peer[r]);
+  if (x->local) cudaFree(x->local);
+  if (x->d_done) cudaFree(x->d_done);
+  delete x;
+}
+
+int irt_xchg_handle_size(void) { return (int)sizeof(cudaIpcMemHandle_t); }
+
+// the handle every rank publishes (host-side all-gather of irt_xchg_handle_size() bytes per rank)
+int irt_xchg_export(irt_xchg *x, void *handle) {
+  if (!x || !handle) return IRT_ERR_INVALID_ARGUMENT;
+  IRT_CUDA(x->ctx, cudaSetDevice(x->ctx->device));
+  cudaIpcMemHandle_t h;
+  IRT_CUDA(x->ctx, cudaIpcGetMemHandle(&h, x->local));
+  std::memcpy(handle, &h, sizeof(h));
+  return IRT_OK;
+}
+
+// handles: [world][irt_xchg_handle_size()] in rank order.  Collective in the sense that every rank must
+// have created its buffer before any rank connects.
+int irt_xchg_connect(irt_xchg *x, const void *handles) {
+  if (!x || !handles) return IRT_ERR_INVALID_ARGUMENT;
+  IRT_CUDA(x->ctx, cudaSetDevice(x->ctx->device));
+  for (int r = 0; r < x->world; r++) {
+    if (r == x->rank || x->opened[r]) continue;
+    cudaIpcMemHandle_t h;
+    std::memcpy(&h, (const char *)handles + (size_t)r * sizeof(h), sizeof(h));
+    void *p = nullptr;
+    IRT_CUDA(x->ctx, cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+    x->peer[r] = (uint32_t *)p;
+    x->opened[r] = true;
+  }
+  x->connected = true;
+  return IRT_OK;
+}
+
+// K3 over sets [begin, end) of this rank's store with the verdict all-gather fused in: on return of
+// the stream work, *d_gathered (device, [world][slot_words] words, rank-major) holds every rank's
+// verdict words of this sweep.  Consumers must read it in stream order before the sweep after next
+// (two buffers alternate).  Every rank must call this the same number of times.
+int irt_check_sets_allgather_dev(irt_ctx *ctx, const irt_setstore *store, const irt_env *env,
+                                 int64_t begin, int64_t end, irt_xchg *x, void *stream,
+                                 const uint32_t **d_gathered) {
+  if (!ctx || !x || !store || !env) return IRT_ERR_INVALID_ARGUMENT;
+  if (!x->connected) return irt_fail(ctx, IRT_ERR_INVALID_ARGUMENT, "exchange not connected");
+  IRT_CUDA(ctx, cudaSetDevice(ctx->device));
+  cudaStream_t st = stream ? (cudaStream_t)stream : ctx->stream;
+  x->epoch++;
+  XchgDev xd;
+  std::memset(&xd, 0, sizeof(xd));
+  for (int r = 0; r < x->world; r++) xd.peer[r] = x->peer[r];
+  xd.world = x->world; xd.rank = x->rank; xd.parity = (int)(x->epoch & 1u);
+  xd.slot_words = x->slot_words; xd.epoch = x->epoch; xd.done = x->d_done;
+  int rc = check_sets_impl(ctx, store, env, begin, end, nullptr, nullptr, st, &xd);
+  if (rc) return rc;
+  const uint32_t *flags = x->local + (size_t)2 * x->world * x->slot_words + (size_t)xd.parity * x->world;
+  xchg_wait_kernel<<<1, 32, 0, st>>>(flags, x->world, x->epoch, x->d_done + 1);
+  IRT_LAUNCHED(ctx);
+  IRT_CUDA(ctx, cudaGetLastError());
+  if (d_gathered) *d_gathered = x->local + (size_t)xd.parity * x->world * x->slot_words;
+  return IRT_OK;
+}
+
+// 0 when every wait so far saw all peers arrive; 1 + rank of a peer that timed out otherwise
+int irt_xchg_status(irt_xchg *x) {
+  if (!x) return -1;
+  unsigned int e = 0;
+  cudaSetDevice(x->ctx->device);
+  cudaMemcpy(&e, x->d_done + 1, 4, cudaMemcpyDeviceToHost);
+  return (int)e;
 }
 
 int irt_check_sets_dev(irt_ctx *ctx, const irt_setstore *store, const irt_env *env,

@@ -14,8 +14,11 @@ stay on the host and are not re-implemented here; the roadmap is (states, edge i
 Multi-GPU (one process per GPU): vertices and edges are sharded by contiguous index range
 (boundaries aligned to 64 so verdict words never straddle shards), every rank voxelises and
 checks only its shard, the environment grid is replicated, and ONLY the collision-verdict
-bitmask is exchanged -- one all_gather of uint32 words (NCCL over NVLink on GPUs; gloo in the
-CPU tests of the host logic).
+bitmask is exchanged.  On GPUs the exchange is fused into K3: every warp stores its verdict word
+straight into all peers' copies of the gathered array over NVLink (CUDA IPC peer memory) and a
+per-rank epoch flag replaces the collective (VerdictExchange / irt_check_sets_allgather_dev);
+torch.distributed (NCCL) only publishes the IPC handles once.  The plain all_gather of uint32 words
+(NCCL, or gloo in the CPU tests of the host logic) remains as the fallback path (fused_gather=False).
 """
 import numpy as np
 
@@ -73,6 +76,16 @@ class VoxelCachedLazyPRM:
         self.vertex_validity = np.zeros(0, dtype=np.uint8)
         self.edge_validity = np.zeros(0, dtype=np.uint8)
         self._have_vcache = self._have_ecache = False
+        self.fused_gather = True     # multi-GPU sweeps: fuse the verdict all-gather into K3 (peer memory)
+        self._xchg = {}
+
+    def _exchange(self, store, slot_words):
+        """one exchange buffer per (store, slot size); creating it is collective (IPC handle all-gather)"""
+        from . import VerdictExchange
+        key = (id(store), int(slot_words))
+        if key not in self._xchg:
+            self._xchg[key] = VerdictExchange(self.ctx, self.rank, self.world, max(int(slot_words), 1), self.dist)
+        return self._xchg[key]
 
     # ---- roadmap content ----------------------------------------------------------------
     def set_roadmap(self, states, edges):
@@ -139,6 +152,19 @@ class VoxelCachedLazyPRM:
         w = shard_words(n_total, self.world)
         use_cuda = torch.cuda.is_available()
         dev = torch.device("cuda", self.ctx.device) if use_cuda else torch.device("cpu")
+        fused = (use_cuda and self.world > 1 and self.dist is not None and self.dist.is_initialized()
+                 and self.dist.get_backend() == "nccl" and self.fused_gather)
+        if fused:
+            # K3 stores its verdict words straight into every peer's gathered array (NVLink P2P)
+            x = self._exchange(store, w)
+            stream = torch.cuda.current_stream(dev).cuda_stream
+            allw = x.check(store, self.env, 0, hi - lo, stream=stream or None)
+            if not stream:
+                self.ctx.synchronize()
+            collides = assemble_verdicts(allw.cpu().numpy().view(np.uint32), n_total, self.world)
+            if x.status():
+                raise RuntimeError("verdict exchange: peer %d never arrived" % (x.status() - 1))
+            return collides
         words = torch.zeros(max(w, 1), dtype=torch.int32, device=dev)
         if hi > lo:
             stream = torch.cuda.current_stream(dev).cuda_stream if use_cuda else None
