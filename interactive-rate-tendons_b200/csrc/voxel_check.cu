@@ -17,6 +17,7 @@
 // (behind the occupancy bitmap) is non-zero sets one bit in a shared-memory hit bitmap, and each
 // thread then tests the bits of the one set it owns; the word is one __ballot_sync per warp: no
 // global atomics, no memset, no search, no per-set divergence (details at the kernel).
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -110,6 +111,7 @@ constexpr int IRT_MAX_PEERS = 16;
 struct XchgDev {
   uint32_t *peer[IRT_MAX_PEERS];  // base of every rank's buffer as mapped in THIS process (own: local)
   int world, rank, parity;
+  int flush_tiles;                // staged tiles per P2P flush (<= K3_GATHER_TILES)
   int64_t slot_words;             // words every rank contributes
   uint32_t epoch;
   unsigned int *done;             // local CTA counter
@@ -296,7 +298,7 @@ voxel_and_popc_kernel(const uint32_t *__restrict__ keys, const uint64_t *__restr
       // stage this CTA's words in shared memory; they go to the peers as 32-byte runs (one tile = 8
       // consecutive words) instead of one 4-byte NVLink write per warp
       if ((tid & 31) == 0) s_gw[kt * (K3_THREADS / 32) + (tid >> 5)] = word;
-      if (++kt == K3_GATHER_TILES) { flush_gathered(kt_base, kt); kt_base += kt; kt = 0; }
+      if (++kt == xd.flush_tiles) { flush_gathered(kt_base, kt); kt_base += kt; kt = 0; }
     } else if ((tid & 31) == 0 && wi < nwords_out) {
       verdict[wi] = word;
     }
@@ -646,7 +648,11 @@ static int check_sets_impl(irt_ctx *ctx, const irt_setstore *store, const irt_en
   if (xd) {
     // one resident wave: every CTA ends with a system-scope fence that holds its SM slot for the
     // round trip of its peer stores; a second wave would pay that latency twice
-    if (blocks > (int64_t)ctx->sm_count * 4) blocks = (int64_t)ctx->sm_count * 4;
+    {
+      const char *wv = getenv("IRT_K3_GATHER_WAVES");   // tuning knob (default 1)
+      const int64_t waves = (wv && atoi(wv) > 0) ? atoi(wv) : 1;
+      if (blocks > (int64_t)ctx->sm_count * 4 * waves) blocks = (int64_t)ctx->sm_count * 4 * waves;
+    }
     if ((n + 31) / 32 > xd->slot_words)
       return irt_fail(ctx, IRT_ERR_CAPACITY, "shard of %lld sets exceeds the exchange slot (%lld words)",
                       (long long)n, (long long)xd->slot_words);
@@ -754,6 +760,13 @@ int irt_check_sets_allgather_dev(irt_ctx *ctx, const irt_setstore *store, const 
   for (int r = 0; r < x->world; r++) xd.peer[r] = x->peer[r];
   xd.world = x->world; xd.rank = x->rank; xd.parity = (int)(x->epoch & 1u);
   xd.slot_words = x->slot_words; xd.epoch = x->epoch; xd.done = x->d_done;
+  {
+    // peer stores trickle out while the sweep runs (every flush_tiles tiles), so the fence at the end of
+    // a CTA only waits for its last few; tuning knob IRT_K3_GATHER_FLUSH
+    const char *fl = getenv("IRT_K3_GATHER_FLUSH");
+    int f = (fl && atoi(fl) > 0) ? atoi(fl) : 4;
+    xd.flush_tiles = f > K3_GATHER_TILES ? K3_GATHER_TILES : f;
+  }
   int rc = check_sets_impl(ctx, store, env, begin, end, nullptr, nullptr, st, &xd);
   if (rc) return rc;
   const uint32_t *flags = x->local + (size_t)2 * x->world * x->slot_words + (size_t)xd.parity * x->world;
