@@ -1,14 +1,13 @@
-"""Latency / throughput of the batched finite-difference tip Jacobian next to the
-sequential CPU rule it replaces (oracle port of levmar's central differences, one thread)."""
+"""Latency / throughput of the batched finite-difference tip Jacobian.  (The CPU
+figure quoted beside it in INTEGRATION.md -- 0.72 ms for the 15 sequential FKs of one Jacobian on one
+host thread -- was taken once with the oracle port; tools/ does not load oracle/.)"""
 import sys, os, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
 import irt_b200, irt_b200.workloads as wl
-from oracle.oracle import Oracle
 ctx = irt_b200.Context(0)
 spec = wl.robot_b(0.005)
 rb = irt_b200.Robot(ctx, spec)
-orc = Oracle("fast"); orb = orc.robot(spec)
 st = wl.sample_states(spec, 100000, stream=5)
 for n in (1, 10, 100, 1000, 10000, 100000):
     s = st[:n]
@@ -19,8 +18,3 @@ for n in (1, 10, 100, 1000, 10000, 100000):
         rb.tip_jacobian_batch(s, mode=2, delta=1e-6)
     dt = (time.perf_counter() - t0) / reps
     print("GPU n=%6d seeds: %.3f ms per batch (host buffers), %.0f Jacobians/s, %.2f M FK/s" % (n, dt * 1e3, n / dt, n * 15 / dt / 1e6), flush=True)
-t0 = time.perf_counter(); k = 0
-while time.perf_counter() - t0 < 3.0:
-    orc.tip_jacobian(orb, st[k % 1000], 2, 1e-6); k += 1
-dt = (time.perf_counter() - t0) / k
-print("CPU oracle port, 1 thread: %.3f ms per Jacobian (15 sequential FKs), %.0f Jacobians/s" % (dt * 1e3, 1 / dt))
