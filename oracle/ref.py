@@ -335,3 +335,138 @@ class RefLevmar:
         rc = cls.lib().dlevmar_bc_der(cls._wrap(f), cls._wrap(jacf), _dp(p), _dp(x), len(p), len(x), _dp(lb),
                                       _dp(ub), None, itmax, _dp(opts), _dp(info), None, None, None)
         return p, info, rc
+
+
+class RefVoxelOctree:
+    """collision::VoxelOctree of the reference: its own class declaration and member definitions
+    (constructor, limits, cells, find_cell, add_line, add_piecewise_line, add_voxels, dilate_*,
+    remove_interior_*, collides, visit_leaves), cut out of VoxelOctree.{h,cpp} at build time and compiled
+    unmodified over the real TreeNode.h; Point arithmetic through the Eigen stand-in
+    (oracle/ref_shim/voxeloctree_ref.cpp)."""
+    _lib = None
+
+    @classmethod
+    def available(cls):
+        return os.path.exists(os.path.join(REF_DIR, "libvoxeloctree_ref.so"))
+
+    @classmethod
+    def lib(cls):
+        if cls._lib is None:
+            L = C.CDLL(os.path.join(REF_DIR, "libvoxeloctree_ref.so"))
+            u64, vp, dp = C.c_uint64, C.c_void_p, C.POINTER(C.c_double)
+            L.voref_new.restype = vp
+            L.voref_new.argtypes = [u64, dp]
+            L.voref_free.argtypes = [vp]
+            L.voref_copy.restype = vp
+            L.voref_copy.argtypes = [vp]
+            for n in ("voref_nblocks", "voref_ncells"):
+                getattr(L, n).restype = u64
+                getattr(L, n).argtypes = [vp]
+            L.voref_block.restype = u64
+            L.voref_block.argtypes = [vp, u64, u64, u64]
+            L.voref_set_block.argtypes = [vp, u64, u64, u64, u64]
+            L.voref_union_block.restype = u64
+            L.voref_union_block.argtypes = [vp, u64, u64, u64, u64]
+            L.voref_set_cell.argtypes = [vp, u64, u64, u64]
+            L.voref_add_line.argtypes = [vp, dp, dp]
+            L.voref_add_piecewise_line.argtypes = [vp, dp, C.c_int]
+            L.voref_add_voxels.argtypes = [vp, vp]
+            L.voref_find_cell.restype = C.c_int
+            L.voref_find_cell.argtypes = [vp, dp, C.POINTER(C.c_int64)]
+            L.voref_nearest_cell.argtypes = [vp, dp, C.POINTER(C.c_int64)]
+            L.voref_collides.restype = C.c_int
+            L.voref_collides.argtypes = [vp, vp]
+            L.voref_dilate.argtypes = [vp, C.c_int, C.c_int]
+            L.voref_dilate_sphere.argtypes = [vp, C.c_double]
+            L.voref_remove_interior.argtypes = [vp, C.c_int]
+            L.voref_bitmask.restype = u64
+            L.voref_bitmask.argtypes = [C.c_int, C.c_int, C.c_int]
+            L.voref_leaves.restype = u64
+            L.voref_leaves.argtypes = [vp, C.POINTER(u64), u64]
+            cls._lib = L
+        return cls._lib
+
+    def __init__(self, Ng, lim, _h=None):
+        self.Ng, self.lim = int(Ng), [float(v) for v in lim]
+        if _h is None:
+            l = np.array(self.lim, dtype=np.float64)
+            _h = self.lib().voref_new(self.Ng, _dp(l))
+        if not _h:
+            raise ValueError("unsupported voxel dimension %r" % (Ng,))
+        self.h = _h
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            self.lib().voref_free(self.h)
+            self.h = None
+
+    def copy(self):
+        return RefVoxelOctree(self.Ng, self.lim, self.lib().voref_copy(self.h))
+
+    def nblocks(self):
+        return int(self.lib().voref_nblocks(self.h))
+
+    def ncells(self):
+        return int(self.lib().voref_ncells(self.h))
+
+    def block(self, bx, by, bz):
+        return int(self.lib().voref_block(self.h, bx, by, bz))
+
+    def set_block(self, bx, by, bz, v):
+        self.lib().voref_set_block(self.h, bx, by, bz, int(v))
+
+    def union_block(self, bx, by, bz, v):
+        return int(self.lib().voref_union_block(self.h, bx, by, bz, int(v)))
+
+    def set_cell(self, ix, iy, iz):
+        return bool(self.lib().voref_set_cell(self.h, ix, iy, iz))
+
+    def add_line(self, a, b):
+        a, b = (np.ascontiguousarray(v, dtype=np.float64) for v in (a, b))
+        self.lib().voref_add_line(self.h, _dp(a), _dp(b))
+
+    def add_piecewise_line(self, pts):
+        pts = np.ascontiguousarray(pts, dtype=np.float64)
+        self.lib().voref_add_piecewise_line(self.h, _dp(pts), len(pts))
+
+    def add_voxels(self, other):
+        self.lib().voref_add_voxels(self.h, other.h)
+
+    def find_cell(self, p):
+        p = np.ascontiguousarray(p, dtype=np.float64)
+        cell = np.zeros(3, dtype=np.int64)
+        err = self.lib().voref_find_cell(self.h, _dp(p), cell.ctypes.data_as(C.POINTER(C.c_int64)))
+        return None if err else tuple(int(c) for c in cell)
+
+    def nearest_cell(self, p):
+        p = np.ascontiguousarray(p, dtype=np.float64)
+        cell = np.zeros(3, dtype=np.int64)
+        self.lib().voref_nearest_cell(self.h, _dp(p), cell.ctypes.data_as(C.POINTER(C.c_int64)))
+        return tuple(int(c) for c in cell)
+
+    def collides(self, other):
+        r = self.lib().voref_collides(self.h, other.h)
+        if r < 0:
+            raise ValueError("voxel dimension mismatch")
+        return bool(r)
+
+    def dilate(self, num=1, use_diagonal=False):
+        self.lib().voref_dilate(self.h, int(num), int(use_diagonal))
+
+    def dilate_sphere(self, r):
+        self.lib().voref_dilate_sphere(self.h, float(r))
+
+    def remove_interior(self, keep_diagonal=True):
+        self.lib().voref_remove_interior(self.h, int(keep_diagonal))
+
+    @classmethod
+    def bitmask(cls, x, y, z):
+        return int(cls.lib().voref_bitmask(x, y, z))
+
+    def export(self):
+        """(bxyz uint8[n,3], bits uint64[n]) in visit_leaves order (same form as oracle Octree.export)"""
+        n = self.nblocks()
+        buf = np.zeros((max(n, 1), 4), dtype=np.uint64)
+        m = int(self.lib().voref_leaves(self.h, buf.ctypes.data_as(C.POINTER(C.c_uint64)), n))
+        assert m == n
+        return buf[:n, :3].astype(np.uint8), buf[:n, 3].copy()

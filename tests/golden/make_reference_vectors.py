@@ -37,7 +37,7 @@ def random_ode_state(rng, N):
 
 def main():
     ref.build()
-    assert ref.available()
+    assert ref.available() and ref.RefVoxelOctree.available()
     out = {}
     rng = np.random.default_rng(SEED)
     for name, spec in robots().items():
@@ -85,6 +85,63 @@ def main():
     bx, by, bz, bits = t.leaves()
     out["tree_leaves_xyz"] = np.stack([bx, by, bz], axis=1)
     out["tree_leaves_bits"] = bits
+    # VoxelOctree::add_line / find_cell / dilate / remove_interior (the reference's own text, see
+    # oracle/ref_shim/voxeloctree_ref.cpp): segments of every kind -> leaves in visit_leaves order
+    lim = [-0.21, 0.21] * 3
+    dxv = 0.42 / 128
+    segs2 = []
+    for i in range(600):
+        kind = i % 6
+        a = rng.uniform(-0.25, 0.25, 3)
+        if kind == 0:
+            b = a + rng.normal(size=3) * 0.004                 # short, like a backbone segment
+        elif kind == 1:
+            b = rng.uniform(-0.3, 0.3, 3)                      # long, may cross or miss the grid
+        elif kind == 2:
+            b = a.copy(); b[rng.integers(0, 3)] += rng.uniform(-0.05, 0.05)   # axis aligned
+        elif kind == 3:
+            b = a.copy()                                       # zero length
+        elif kind == 4:
+            a = np.round(a / dxv) * dxv; b = a + rng.integers(-3, 4, 3) * dxv   # on cell boundaries
+        else:
+            a = rng.uniform(-0.2, 0.2, 3); b = a + rng.uniform(-1, 1, 3) * np.array([1e-12, 0.02, 1e-11])
+        segs2.append((a, b))
+    segs2 = np.array(segs2)
+    out["vo_lim"] = np.array(lim)
+    out["vo_segs"] = segs2
+    leaf_off, leaf_xyz, leaf_bits = [0], [], []
+    for k in range(0, len(segs2), 3):                          # three segments per tree
+        t = ref.RefVoxelOctree(128, lim)
+        for a, b in segs2[k:k + 3]:
+            t.add_line(a, b)
+        xyz, bits = t.export()
+        leaf_xyz.append(xyz); leaf_bits.append(bits); leaf_off.append(leaf_off[-1] + len(bits))
+    out["vo_leaf_off"] = np.array(leaf_off)
+    out["vo_leaf_xyz"] = np.concatenate(leaf_xyz)
+    out["vo_leaf_bits"] = np.concatenate(leaf_bits)
+    t = ref.RefVoxelOctree(128, lim)
+    pts = rng.uniform(-0.22, 0.22, (500, 3))
+    pts[:8] = np.array([[-0.21, 0, 0], [0.21, 0, 0], [0, -0.21, 0.21], [0.2099999, 0, 0], [0, 0, 0],
+                        [dxv, 2 * dxv, -3 * dxv], [-0.2100001, 0, 0], [0, 0.2100001, 0]])
+    out["vo_pts"] = pts
+    out["vo_find_cell"] = np.array([(-1, -1, -1) if t.find_cell(p) is None else t.find_cell(p) for p in pts])
+    out["vo_nearest_cell"] = np.array([t.nearest_cell(p) for p in pts])
+    # environment preparation on a small random obstacle set (32^3 grid)
+    seed_cells = rng.integers(2, 30, (60, 3))
+    out["vo_env_cells"] = seed_cells
+    prep = {}
+    for name, args in (("dilate6x1", ("dilate", 1, False)), ("dilate6x3", ("dilate", 3, False)),
+                       ("dilate27x2", ("dilate", 2, True)), ("sphere", ("dilate_sphere", 0.07)),
+                       ("interior27", ("remove_interior", True)), ("interior6", ("remove_interior", False))):
+        t = ref.RefVoxelOctree(32, [0, 1] * 3)
+        for c in seed_cells:
+            t.set_cell(*[int(v) for v in c])
+        if name.startswith("interior"):
+            t.dilate(3, True)                                  # something with an interior to remove
+        getattr(t, args[0])(*args[1:])
+        xyz, bits = t.export()
+        out["vo_prep_%s_xyz" % name] = xyz
+        out["vo_prep_%s_bits" % name] = bits
     path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "reference_vectors.npz")
     np.savez_compressed(path, **out)
     print("wrote", path, os.path.getsize(path), "bytes")

@@ -150,3 +150,61 @@ def test_ik_levmar_driven_by_gpu_jacobians(irt, ctx, orc, wl):
         assert info_gpu[5] == info_ref[5] and info_gpu[6] == info_ref[6]      # iterations, stop reason
         assert np.abs(p_gpu - p_ref).max() < 1e-6 * 20.0
         assert np.linalg.norm(f_cpu(p_gpu) - des) < 2e-4
+
+
+vo_ref = pytest.mark.skipif(not ref.RefVoxelOctree.available(),
+                            reason="oracle/_ref/libvoxeloctree_ref.so was not shipped")
+
+
+@vo_ref
+@pytest.mark.parametrize("robot", ["a", "b"])
+def test_k2_vertex_sets_vs_reference_add_line(irt, ctx, wl, robot):
+    """K2 vertex voxel sets vs VoxelOctree::add_piecewise_line -- the reference's own add_line text
+    (VoxelOctree.cpp:325-432) -- applied to the points K1 produced: bit-exact CSR, visit_leaves order."""
+    spec = wl.robot_a(0.003) if robot == "a" else wl.robot_b(0.003)
+    g = wl.workspace_grid(spec)
+    Nb = g["Ng"] // 4
+    rb = irt.Robot(ctx, spec)
+    states = wl.sample_states(spec, 1500, stream=81)
+    fk = rb.shape_batch(states, want=("p", "npts", "flags"))
+    store = irt.SetStore(ctx, irt.make_grid(g["Ng"], g["lim"]))
+    flags, _ = store.voxelize_vertices(rb, states)
+    off, keys, bits = store.export_csr()
+    flips = 0
+    for i in range(len(states)):
+        t = ref.RefVoxelOctree(g["Ng"], g["lim"])
+        t.add_piecewise_line(fk["p"][i, :fk["npts"][i]])   # invalid shapes are voxelised too (cache)
+        xyz, rbits = t.export()
+        rkeys = wl.morton_key(xyz[:, 0].astype(np.int64), xyz[:, 1].astype(np.int64), xyz[:, 2].astype(np.int64), Nb) \
+            if len(xyz) else np.zeros(0, dtype=np.uint32)
+        gk, gb = keys[int(off[i]):int(off[i + 1])], bits[int(off[i]):int(off[i + 1])]
+        if not (np.array_equal(gk, np.asarray(rkeys, dtype=np.uint32)) and np.array_equal(gb, rbits)):
+            flips += 1
+    assert flips == 0, "%d vertex sets differ from the reference's add_piecewise_line" % flips
+
+
+@vo_ref
+def test_env_preparation_vs_reference(irt, ctx, wl):
+    """irt_env_dilate / dilate_sphere / remove_interior vs the reference's own tree walks
+    (VoxelOctree.cpp:533-952) on the C4/C5 environment"""
+    spec = wl.robot_b(0.003)
+    g = wl.workspace_grid(spec)
+    Nb = g["Ng"] // 4
+    grid = irt.make_grid(g["Ng"], g["lim"])
+    blocks = wl.dense_to_morton_blocks(wl.lung_like_env_dense(spec, g))
+    keys = np.nonzero(blocks)[0].astype(np.uint32)
+    ex, ey, ez = wl.morton_decode(keys, Nb)
+    for op in (("dilate", 1, False), ("dilate", 2, True), ("dilate_sphere", 0.01),
+               ("remove_interior", True), ("remove_interior", False)):
+        env = irt.Env(ctx, grid)
+        env.update(blocks)
+        tr = ref.RefVoxelOctree(g["Ng"], g["lim"])
+        for x, y, z, k in zip(ex.tolist(), ey.tolist(), ez.tolist(), keys.tolist()):
+            tr.set_block(x, y, z, int(blocks[k]))
+        getattr(env, op[0])(*op[1:])
+        getattr(tr, op[0])(*op[1:])
+        got = env.download()
+        xyz, rbits = tr.export()
+        want = np.zeros_like(got)
+        want[wl.morton_key(xyz[:, 0].astype(np.int64), xyz[:, 1].astype(np.int64), xyz[:, 2].astype(np.int64), Nb)] = rbits
+        assert np.array_equal(got, want), op

@@ -255,3 +255,94 @@ def test_live_ik_with_reference_levmar(orc, wl):
         p, info, rc = ref.RefLevmar.bc_dif(f, s, des, lb, ub, 100, [0.1, 1e-9, 1e-8, 1e-8, -1e-6])
         assert rc >= 0 and np.all(p >= lb) and np.all(p <= ub)
         assert np.linalg.norm(f(p) - des) < 2e-4 and info[1] < info[0]
+
+
+# ------------------------------------------------------------------ VoxelOctree core (reference's own text)
+vox = pytest.mark.skipif(not (ref.available() and ref.RefVoxelOctree.available()),
+                         reason="oracle/_ref/libvoxeloctree_ref.so not built")
+
+
+def _same_tree(a, b):
+    ea, eb = a.export(), b.export()
+    return np.array_equal(ea[0], eb[0]) and np.array_equal(ea[1], eb[1])
+
+
+def test_golden_add_line(orc, gold):
+    """VoxelOctree::add_line (VoxelOctree.cpp:325-426, both quirks included): segments of every kind,
+    leaves bit-exact and in visit_leaves order."""
+    lim = gold["vo_lim"].tolist()
+    g = orc.grid(128, lim)
+    segs, off = gold["vo_segs"], gold["vo_leaf_off"]
+    for k in range(0, len(segs), 3):
+        t = orc.octree(g)
+        for a, b in segs[k:k + 3]:
+            t.add_line(a, b)
+        xyz, bits = t.export()
+        lo, hi = off[k // 3], off[k // 3 + 1]
+        assert np.array_equal(xyz, gold["vo_leaf_xyz"][lo:hi]) and np.array_equal(bits, gold["vo_leaf_bits"][lo:hi]), k
+    assert off[-1] > 300    # the fixture is not trivially empty
+
+
+def test_golden_find_cell(orc, gold):
+    g = orc.grid(128, gold["vo_lim"].tolist())
+    for p, want in zip(gold["vo_pts"], gold["vo_find_cell"]):
+        got = orc.find_cell(g, p)                      # VoxelOctree.cpp:309-317, domain_check :1511-1521
+        assert (got is None and want[0] < 0) or tuple(want) == got
+    assert (gold["vo_find_cell"][:, 0] < 0).sum() >= 2   # the out-of-domain probes are in the fixture
+
+
+@pytest.mark.parametrize("name,op", [("dilate6x1", ("dilate", 1, False)), ("dilate6x3", ("dilate", 3, False)),
+                                     ("dilate27x2", ("dilate", 2, True)), ("sphere", ("dilate_sphere", 0.07)),
+                                     ("interior27", ("remove_interior", True)),
+                                     ("interior6", ("remove_interior", False))])
+def test_golden_environment_preparation(orc, gold, name, op):
+    """dilate_6/27neighbor, dilate_sphere, remove_interior_6/27neighbor (VoxelOctree.cpp:533-952)"""
+    g = orc.grid(32, [0, 1] * 3)
+    t = orc.octree(g)
+    for x, y, z in gold["vo_env_cells"].tolist():
+        t.union_block(x // 4, y // 4, z // 4, 1 << ((x % 4) * 16 + (y % 4) * 4 + (z % 4)))
+    if name.startswith("interior"):
+        t.dilate(3, True)
+    getattr(t, op[0])(*op[1:])
+    xyz, bits = t.export()
+    assert np.array_equal(xyz, gold["vo_prep_%s_xyz" % name])
+    assert np.array_equal(bits, gold["vo_prep_%s_bits" % name])
+
+
+@vox
+def test_live_backbone_voxelisation(orc, wl, robots):
+    """VoxelBackboneValidityChecker::voxelize_impl (VoxelBackboneValidityChecker.h:49-57) =
+    add_piecewise_line of the shape: oracle vs the reference's own add_line on real backbones."""
+    for name in ("a005", "b003"):
+        spec = robots[name]
+        rb = orc.robot(spec)
+        g = wl.workspace_grid(spec)
+        og = orc.grid(g["Ng"], g["lim"])
+        for s in wl.sample_states(spec, 150, stream=44):
+            p = orc.shape(rb, s)["p"]
+            t = ref.RefVoxelOctree(g["Ng"], g["lim"])
+            t.add_piecewise_line(p)
+            assert _same_tree(orc.voxelize_shape(og, p), t)
+    assert ref.RefVoxelOctree.bitmask(1, 2, 3) == 1 << (16 + 8 + 3)
+
+
+@vox
+def test_live_lung_environment_preparation(orc, wl):
+    """the C4/C5 environment through every preparation step, oracle vs reference"""
+    spec = wl.robot_b(0.003)
+    g = wl.workspace_grid(spec)
+    blocks = wl.dense_to_morton_blocks(wl.lung_like_env_dense(spec, g))
+    Nb = g["Ng"] // 4
+    keys = np.nonzero(blocks)[0].astype(np.uint32)
+    ex, ey, ez = wl.morton_decode(keys, Nb)
+    og = orc.grid(g["Ng"], g["lim"])
+    for op in (("dilate", 1, False), ("dilate", 2, True), ("dilate_sphere", 0.01),
+               ("remove_interior", True), ("remove_interior", False)):
+        to, tr = orc.octree(og), ref.RefVoxelOctree(g["Ng"], g["lim"])
+        for x, y, z, k in zip(ex.tolist(), ey.tolist(), ez.tolist(), keys.tolist()):
+            to.set_block(x, y, z, int(blocks[k]))
+            tr.set_block(x, y, z, int(blocks[k]))
+        getattr(to, op[0])(*op[1:])
+        getattr(tr, op[0])(*op[1:])
+        assert _same_tree(to, tr), op
+        assert tr.collides(tr) and to.nblocks() == tr.nblocks() and to.ncells() == tr.ncells()
