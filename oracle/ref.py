@@ -470,3 +470,97 @@ class RefVoxelOctree:
         m = int(self.lib().voref_leaves(self.h, buf.ctypes.data_as(C.POINTER(C.c_uint64)), n))
         assert m == n
         return buf[:n, :3].astype(np.uint8), buf[:n, 3].copy()
+
+
+class RefSelfCollision:
+    """collision::collides_self(CapsuleSequence) of the reference (collision/collision.cpp:6-46) with the
+    structs and inline capsule tests it needs, compiled from the reference's own text
+    (oracle/ref_shim/selfcol_ref.cpp)."""
+    _lib = None
+
+    @classmethod
+    def available(cls):
+        return os.path.exists(os.path.join(REF_DIR, "libselfcol_ref.so"))
+
+    @classmethod
+    def lib(cls):
+        if cls._lib is None:
+            L = C.CDLL(os.path.join(REF_DIR, "libselfcol_ref.so"))
+            dp = C.POINTER(C.c_double)
+            L.scref_collides_self.restype = C.c_int
+            L.scref_collides_self.argtypes = [dp, C.c_int, C.c_double]
+            L.scref_capsules_collide.restype = C.c_int
+            L.scref_capsules_collide.argtypes = [dp, dp, C.c_double, dp, dp, C.c_double]
+            cls._lib = L
+        return cls._lib
+
+    @classmethod
+    def collides_self(cls, p, r):
+        p = np.ascontiguousarray(p, dtype=np.float64)
+        return bool(cls.lib().scref_collides_self(_dp(p), len(p), float(r)))
+
+
+class RefSweptVolume:
+    """VoxelEnvironment::voxelize_valid_backbone_motion of the reference (VoxelEnvironment.cpp:207-444)
+    compiled from its own text (oracle/ref_shim/sweptvol_ref.cpp).  FK, validity and interpolation are
+    callbacks, as in the reference: fk(state) -> points [n][3]; valid(state, points) -> bool;
+    interp(a, b, t) -> state."""
+    _lib = None
+    INTERP = C.CFUNCTYPE(None, C.POINTER(C.c_double), C.POINTER(C.c_double), C.c_int, C.c_double,
+                         C.POINTER(C.c_double))
+    FK = C.CFUNCTYPE(C.c_int, C.POINTER(C.c_double), C.c_int, C.POINTER(C.c_double), C.c_int)
+    VALID = C.CFUNCTYPE(C.c_int, C.POINTER(C.c_double), C.c_int, C.POINTER(C.c_double), C.c_int)
+
+    @classmethod
+    def available(cls):
+        return os.path.exists(os.path.join(REF_DIR, "libsweptvol_ref.so"))
+
+    @classmethod
+    def lib(cls):
+        if cls._lib is None:
+            L = C.CDLL(os.path.join(REF_DIR, "libsweptvol_ref.so"))
+            dp, u64p = C.POINTER(C.c_double), C.POINTER(C.c_uint64)
+            L.veref_voxelize_valid_backbone_motion.restype = C.c_int
+            L.veref_voxelize_valid_backbone_motion.argtypes = [
+                C.c_uint64, dp, dp, dp, dp, C.c_int, C.c_double, C.c_int, cls.INTERP, cls.FK, cls.VALID,
+                C.POINTER(C.c_int), dp, dp, C.POINTER(C.c_int), u64p, u64p]
+            cls._lib = L
+        return cls._lib
+
+    @classmethod
+    def voxelize(cls, Ng, lim, inv_rot, a, b, rel_threshold, cap_pts, fk, valid, interp):
+        a = np.ascontiguousarray(a, dtype=np.float64)
+        b = np.ascontiguousarray(b, dtype=np.float64)
+        S = len(a)
+        lim = np.ascontiguousarray(lim, dtype=np.float64)
+        R = np.ascontiguousarray(np.eye(3) if inv_rot is None else inv_rot, dtype=np.float64).reshape(3, 3)
+
+        def interp_cb(pa, pb, s, t, out):
+            v = interp(np.array([pa[i] for i in range(s)]), np.array([pb[i] for i in range(s)]), t)
+            for i in range(s):
+                out[i] = v[i]
+
+        def fk_cb(ps, s, pout, cap):
+            p = np.asarray(fk(np.array([ps[i] for i in range(s)])), dtype=np.float64).reshape(-1, 3)
+            assert len(p) <= cap
+            for i, row in enumerate(p):
+                pout[3 * i], pout[3 * i + 1], pout[3 * i + 2] = row
+            return len(p)
+
+        def valid_cb(ps, s, pp, n):
+            pts = np.array([pp[i] for i in range(3 * n)]).reshape(n, 3)
+            return int(bool(valid(np.array([ps[i] for i in range(s)]), pts)))
+
+        ok, nfk, t_last = C.c_int(), C.c_int(), C.c_double()
+        last = np.zeros(S)
+        cap_leaves = 1 << 16
+        leaves = np.zeros((cap_leaves, 4), dtype=np.uint64)
+        nl = C.c_uint64(cap_leaves)
+        rc = cls.lib().veref_voxelize_valid_backbone_motion(
+            int(Ng), _dp(lim), _dp(R), _dp(a), _dp(b), S, float(rel_threshold), int(cap_pts),
+            cls.INTERP(interp_cb), cls.FK(fk_cb), cls.VALID(valid_cb), C.byref(ok), C.byref(t_last), _dp(last),
+            C.byref(nfk), leaves.ctypes.data_as(C.POINTER(C.c_uint64)), C.byref(nl))
+        n = int(nl.value)
+        assert n <= cap_leaves
+        return dict(rc=rc, is_fully_valid=bool(ok.value), t=t_last.value, last_valid=last, nsamples=nfk.value,
+                    bxyz=leaves[:n, :3].astype(np.uint8), bits=leaves[:n, 3].copy())

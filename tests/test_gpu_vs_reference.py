@@ -209,3 +209,23 @@ def test_env_preparation_vs_reference(irt, ctx, wl):
         want = np.zeros_like(got)
         want[wl.morton_key(xyz[:, 0].astype(np.int64), xyz[:, 1].astype(np.int64), xyz[:, 2].astype(np.int64), Nb)] = rbits
         assert np.array_equal(got, want), op
+
+
+@pytest.mark.skipif(not ref.RefSelfCollision.available(), reason="oracle/_ref/libselfcol_ref.so was not shipped")
+def test_self_collision_flags_vs_reference(irt, ctx, wl):
+    """IRT_FLAG_SELF_COLLISION of the validity epilogue (FP32 pair filter + exact kernel) vs the
+    reference's own collides_self text (collision.cpp:6-46) on the points K1 produced."""
+    n = hit = 0
+    for base in (wl.robot_a(0.005), wl.robot_b(0.003)):
+        for E in (0.5e6, 2.1e6):
+            spec = dict(base)
+            spec["E"] = E
+            rb = irt.Robot(ctx, spec)
+            st = wl.sample_states(spec, 600, stream=14)
+            out = rb.shape_batch(st, want=("p", "npts", "flags"))
+            for i in range(len(st)):
+                want = ref.RefSelfCollision.collides_self(out["p"][i, :out["npts"][i]], spec["r"])
+                assert bool(out["flags"][i] & irt.FLAG_SELF_COLLISION) == want, (E, i)
+                n += 1
+                hit += want
+    assert 0.1 * n < hit < 0.9 * n

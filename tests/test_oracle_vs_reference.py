@@ -346,3 +346,88 @@ def test_live_lung_environment_preparation(orc, wl):
         getattr(tr, op[0])(*op[1:])
         assert _same_tree(to, tr), op
         assert tr.collides(tr) and to.nblocks() == tr.nblocks() and to.ncells() == tr.ncells()
+
+
+# ------------------------------------------------------------------ collides_self (reference's own text)
+@pytest.mark.skipif(not ref.RefSelfCollision.available(), reason="oracle/_ref/libselfcol_ref.so not built")
+def test_live_collides_self(orc, wl):
+    """collision::collides_self (collision.cpp:6-46) on real backbones, soft enough to curl back onto
+    themselves: oracle vs the reference's own text, both outcomes well represented."""
+    n = hit = 0
+    for base in (wl.robot_a(0.005), wl.robot_b(0.003)):
+        for E in (0.5e6, 2.1e6):
+            spec = dict(base)
+            spec["E"] = E
+            rb = orc.robot(spec)
+            for s in wl.sample_states(spec, 250, stream=13):
+                p = orc.shape(rb, s)["p"]
+                want = ref.RefSelfCollision.collides_self(p, spec["r"])
+                assert orc.collides_self(p, spec["r"]) == want
+                n += 1
+                hit += want
+    # degenerate inputs: fewer than three points never collide (collision.cpp:14)
+    for k in (0, 1, 2):
+        assert not ref.RefSelfCollision.collides_self(np.zeros((k, 3)), 0.015)
+        assert not orc.collides_self(np.zeros((k, 3)), 0.015)
+    assert 0.1 * n < hit < 0.9 * n
+
+
+# ------------------------------------------------------------------ swept-volume driver (reference's own text)
+@pytest.mark.skipif(not ref.RefSweptVolume.available(), reason="oracle/_ref/libsweptvol_ref.so not built")
+@pytest.mark.parametrize("variant", ["b003", "b003rot_rotgrid", "a003_soft"])
+def test_live_swept_volume_driver(orc, wl, variant):
+    """VoxelEnvironment::voxelize_valid_backbone_motion (VoxelEnvironment.cpp:207-444): the oracle's
+    voxelize_edge vs the reference's own text driven by the same FK / validity / interpolation callbacks.
+    Leaves, is_fully_valid, t, last_valid and the number of FK calls (LIFO order) must be identical, on
+    fully valid AND partially valid edges."""
+    inv_rot = None
+    if variant == "b003":
+        spec = wl.robot_b(0.003)
+    elif variant == "b003rot_rotgrid":
+        spec = wl.robot_b(0.003, rotation=True)
+        c, s = np.cos(0.3), np.sin(0.3)
+        inv_rot = np.array([[c, 0, s], [0, 1, 0], [-s, 0, c]]) @ np.array([[1, 0, 0], [0, c, -s], [0, s, c]])
+    else:
+        spec = wl.robot_a(0.003)
+        spec["E"] = 1.0e6                                   # soft: edges run into invalid shapes
+    rb = orc.robot(spec)
+    g = wl.workspace_grid(spec)
+    og = orc.grid(g["Ng"], g["lim"], inv_rot)
+    sp = orc.space()
+    st = wl.sample_states(spec, 1200, stream=17)
+    frac = 0.5 if variant == "a003_soft" else 0.08
+    n = partial = 0
+    for i in range(0, 1200, 2):
+        if n >= 30:
+            break
+        a = st[i]
+        b = a + frac * (st[i + 1] - a)
+        if orc.validity_flags(rb, a, orc.shape(rb, a)) != 0:
+            continue                                        # the planner only starts edges at valid vertices
+        tree, info = orc.voxelize_edge(rb, og, sp, a, b)
+        if info["out_of_domain"]:
+            continue
+        cache = {}
+
+        def fk(s_):
+            sh = orc.shape(rb, s_)
+            cache[s_.tobytes()] = sh
+            return sh["p"]
+
+        def valid(s_, p_):
+            return orc.validity_flags(rb, s_, cache[s_.tobytes()]) == 0
+
+        r = ref.RefSweptVolume.voxelize(g["Ng"], g["lim"], inv_rot, a, b,
+                                        1.0 / orc.valid_segment_count(rb, sp, a, b), 128, fk, valid,
+                                        lambda x, y, t: orc.interpolate(rb, x, y, t))
+        assert r["rc"] == 0
+        bxyz, bits = tree.export()
+        assert np.array_equal(bxyz, r["bxyz"]) and np.array_equal(bits, r["bits"]), i
+        assert r["is_fully_valid"] == info["is_fully_valid"] and r["t"] == info["t"], i
+        assert r["nsamples"] == info["nsamples"], i
+        assert np.array_equal(r["last_valid"], info["last_valid"]), i
+        n += 1
+        partial += not info["is_fully_valid"]
+    assert n >= 10
+    if variant == "a003_soft":
+        assert partial >= 3, "fixture must contain partially valid edges"
