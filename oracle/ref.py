@@ -9,7 +9,13 @@ TEST INFRASTRUCTURE ONLY (same rule as oracle/oracle.py).
   the Eigen stand-in in oracle/ref_shim/eigen_standin (Eigen is not installed; see that header for what
   this does and does not pin).
 
-Both are built by `make -C oracle ref` only where /root/reference exists; they travel to the GPU box
+* libvoxeloctree_ref.so, libselfcol_ref.so, libsweptvol_ref.so: the hot-path core of
+  collision/VoxelOctree.{h,cpp} (add_line, find_cell, dilate_*, remove_interior_* ...), collides_self
+  (collision/collision.cpp) and VoxelEnvironment::voxelize_valid_backbone_motion, cut out of the
+  reference's files by function-name anchors at build time and compiled unmodified.
+* liblevmar_ref.so: the levmar-2.6 the reference vendors (without LAPACK).
+
+All are built by `make -C oracle ref` only where /root/reference exists; they travel to the GPU box
 as prebuilt files.  Nothing here is needed at run time by the product.
 """
 import ctypes as C

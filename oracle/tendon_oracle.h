@@ -18,11 +18,16 @@
  *     collision_primitives.{h,cpp}, unmodified, against a stand-in for the Eigen
  *     subset they use (pins formulas / operand order / control flow, not Eigen's
  *     rounding): routing bit-exact, derivative identical, same fixed-point
- *     iteration counts.
+ *     iteration counts;
+ *   - the hot-path core of VoxelOctree.{h,cpp} (add_line, find_cell, cells,
+ *     dilate_*, remove_interior_*), collides_self (collision.cpp) and
+ *     VoxelEnvironment::voxelize_valid_backbone_motion, cut out of the reference's
+ *     files by function anchors at build time and compiled unmodified: voxel
+ *     sets, verdicts, swept volumes, FK call counts identical;
+ *   - the reference's vendored levmar-2.6: finite-difference Jacobian rule.
  * "Parity unpinned by the reference" still holds for what is restated only: the
- * RK4 stepping of Boost.odeint and t_range, calc_point_forces, home lengths,
- * collides_self, VoxelOctree::add_line / find_cell, the swept-volume driver and
- * OMPL 1.5 validSegmentCount / interpolate.  Those are pinned by
+ * RK4 stepping of Boost.odeint and t_range, calc_point_forces, home lengths /
+ * length limits and OMPL 1.5 validSegmentCount / interpolate.  Those are pinned by
  *   (1) analytic known-answer tests (tests/test_oracle_kat.py) and
  *   (2) an independent numpy + mpmath restatement (oracle/fk_second_opinion.py).
  *
