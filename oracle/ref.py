@@ -570,3 +570,63 @@ class RefSweptVolume:
         assert n <= cap_leaves
         return dict(rc=rc, is_fully_valid=bool(ok.value), t=t_last.value, last_valid=last, nsamples=nfk.value,
                     bxyz=leaves[:n, :3].astype(np.uint8), bits=leaves[:n, 3].copy())
+
+
+class RefTendonRobot:
+    """tendon::TendonRobot of the reference: TendonRobot.h as is, tension_shape / home_shape /
+    calc_point_forces / is_valid cut out of TendonRobot.cpp at build time, over the unmodified derivative /
+    initial-condition / routing sources, against the Eigen and Boost.odeint stand-ins
+    (oracle/ref_shim/tendonrobot_ref.cpp)."""
+    _lib = None
+
+    @classmethod
+    def available(cls):
+        return os.path.exists(os.path.join(REF_DIR, "libtendonrobot_ref.so"))
+
+    @classmethod
+    def lib(cls):
+        if cls._lib is None:
+            L = C.CDLL(os.path.join(REF_DIR, "libtendonrobot_ref.so"))
+            L.trref_shape.restype = C.c_int
+            L.trref_flags.restype = C.c_uint
+            cls._lib = L
+        return cls._lib
+
+    def __init__(self, spec):
+        self.spec = spec
+        self.N = len(spec["C"])
+        self.Nc, self.Nd = len(spec["C"][0]), len(spec["D"][0])
+        self.C = np.ascontiguousarray(spec["C"], dtype=np.float64).reshape(self.N, self.Nc)
+        self.D = np.ascontiguousarray(spec["D"], dtype=np.float64).reshape(self.N, self.Nd)
+        self.hdr = np.array([spec["r"], spec["L"], spec["dL"], spec["ro"], spec["ri"], spec["E"], spec["nu"],
+                             spec["residual_threshold"], float(bool(spec.get("enable_rotation"))),
+                             float(bool(spec.get("enable_retraction")))], dtype=np.float64)
+        self.lim = np.ascontiguousarray(np.stack([spec["max_tension"], spec["min_length"], spec["max_length"]],
+                                                 axis=1), dtype=np.float64)
+
+    def _args(self):
+        return [_dp(self.hdr), C.c_int(self.N), C.c_int(self.Nc), C.c_int(self.Nd), _dp(self.C), _dp(self.D),
+                _dp(self.lim)]
+
+    def shape(self, state, cap=1024):
+        state = np.ascontiguousarray(state, dtype=np.float64)
+        t, p, R = np.zeros(cap), np.zeros((cap, 3)), np.zeros((cap, 9))
+        L_i, misc = np.zeros(self.N), np.zeros(14)
+        n = self.lib().trref_shape(*self._args(), _dp(state), C.c_int(cap), _dp(t), _dp(p), _dp(R), _dp(L_i),
+                                   _dp(misc))
+        assert n >= 0
+        return dict(t=t[:n].copy(), p=p[:n].copy(), R=R[:n].reshape(n, 3, 3).transpose(0, 2, 1).copy(),
+                    L=misc[0], L_i=L_i, u_i=misc[1:4].copy(), u_f=misc[4:7].copy(), v_i=misc[7:10].copy(),
+                    v_f=misc[10:13].copy(), converged=bool(misc[13]))
+
+    def home_lengths(self, state):
+        state = np.ascontiguousarray(state, dtype=np.float64)
+        out = np.zeros(self.N)
+        self.lib().trref_home_lengths(*self._args(), _dp(state), _dp(out))
+        return out
+
+    def flags(self, state):
+        """bit 0 !converged, bit 1 length limits violated, bit 2 self-collision (the ingredients of
+        AbstractValidityChecker::is_valid_shape, evaluated separately)"""
+        state = np.ascontiguousarray(state, dtype=np.float64)
+        return int(self.lib().trref_flags(*self._args(), _dp(state)))

@@ -37,7 +37,7 @@ def random_ode_state(rng, N):
 
 def main():
     ref.build()
-    assert ref.available() and ref.RefVoxelOctree.available()
+    assert ref.available() and ref.RefVoxelOctree.available() and ref.RefTendonRobot.available()
     out = {}
     rng = np.random.default_rng(SEED)
     for name, spec in robots().items():
@@ -142,6 +142,25 @@ def main():
         xyz, bits = t.export()
         out["vo_prep_%s_xyz" % name] = xyz
         out["vo_prep_%s_bits" % name] = bits
+    # TendonRobot::shape of the reference (its own tension_shape text, Eigen + odeint stand-ins): whole shapes
+    for name, spec in {"a005": wl.robot_a(0.005), "b003": wl.robot_b(0.003),
+                       "b005rot": wl.robot_b(0.005, rotation=True),
+                       "a003soft": dict(wl.robot_a(0.003), E=0.7e6)}.items():
+        rr = ref.RefTendonRobot(spec)
+        st = wl.sample_states(spec, 24, stream=29)
+        if spec.get("enable_retraction"):
+            L = spec["L"]
+            st[0, -1], st[1, -1], st[2, -1], st[3, -1], st[4, -1] = L, L + 0.01, 0.1995, 0.0, -0.001
+        shapes = [rr.shape(s_) for s_ in st]
+        out["tr_%s_states" % name] = st
+        out["tr_%s_off" % name] = np.concatenate([[0], np.cumsum([len(sh["t"]) for sh in shapes])])
+        out["tr_%s_t" % name] = np.concatenate([sh["t"] for sh in shapes])
+        out["tr_%s_p" % name] = np.concatenate([sh["p"] for sh in shapes])
+        out["tr_%s_L" % name] = np.array([sh["L"] for sh in shapes])
+        out["tr_%s_Li" % name] = np.stack([sh["L_i"] for sh in shapes])
+        out["tr_%s_conv" % name] = np.array([sh["converged"] for sh in shapes])
+        out["tr_%s_flags" % name] = np.array([rr.flags(s_) for s_ in st], dtype=np.uint32)
+        out["tr_%s_home" % name] = np.stack([rr.home_lengths(s_) for s_ in st])
     path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "reference_vectors.npz")
     np.savez_compressed(path, **out)
     print("wrote", path, os.path.getsize(path), "bytes")

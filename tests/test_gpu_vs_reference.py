@@ -229,3 +229,39 @@ def test_self_collision_flags_vs_reference(irt, ctx, wl):
                 n += 1
                 hit += want
     assert 0.1 * n < hit < 0.9 * n
+
+
+@pytest.mark.skipif(not ref.RefTendonRobot.available(), reason="oracle/_ref/libtendonrobot_ref.so was not shipped")
+@pytest.mark.parametrize("name", ["a005", "b003", "b005rot", "a003soft", "b005tight"])
+def test_k1_vs_reference_tendon_robot_shape(irt, ctx, wl, name):
+    """K1 + validity epilogue vs the reference's own TendonRobot::shape text (tension_shape, home_shape,
+    calc_point_forces, collides_self; Eigen and Boost.odeint stand-ins): node counts and grids exact, points /
+    lengths within 1e-9 L, NONCONVERGED / LENGTH_LIMIT / SELF_COLLISION flags identical."""
+    spec = {"a005": wl.robot_a(0.005), "b003": wl.robot_b(0.003), "b005rot": wl.robot_b(0.005, rotation=True),
+            "a003soft": dict(wl.robot_a(0.003), E=0.7e6),
+            "b005tight": dict(wl.robot_b(0.005), residual_threshold=1e-13)}[name]
+    rb, rr = irt.Robot(ctx, spec), ref.RefTendonRobot(spec)
+    L = spec["L"]
+    st = wl.sample_states(spec, 400, stream=23)
+    if spec.get("enable_retraction"):
+        st[0, -1], st[1, -1], st[2, -1], st[3, -1], st[4, -1] = L, L + 0.01, 0.1995, 0.0, -0.001
+    out = rb.shape_batch(st, want=("p", "R", "t", "npts", "L", "L_i", "uv", "flags"))
+    home = rb.home_lengths(st)
+    seen = 0
+    for i, s in enumerate(st):
+        b = rr.shape(s)
+        n = len(b["t"])
+        assert out["npts"][i] == n
+        assert np.allclose(out["t"][i, :n], b["t"], rtol=0, atol=1e-15)
+        assert np.abs(out["p"][i, :n] - b["p"]).max(initial=0.0) < FK_REL_TOL * L
+        assert np.abs(out["R"][i, :n] - b["R"]).max(initial=0.0) < 1e-9
+        assert abs(out["L"][i] - b["L"]) < FK_REL_TOL * L
+        assert np.abs(out["L_i"][i] - b["L_i"]).max() < FK_REL_TOL * L
+        fr = rr.flags(s)
+        assert (int(out["flags"][i]) & 7) == fr, (i, int(out["flags"][i]), fr)
+        seen |= fr
+        assert np.abs(home[i] - rr.home_lengths(s)).max() < 1e-15
+    if name == "b005tight":
+        assert seen & 1
+    if name == "a003soft":
+        assert seen & 2 and seen & 4

@@ -431,3 +431,64 @@ def test_live_swept_volume_driver(orc, wl, variant):
     assert n >= 10
     if variant == "a003_soft":
         assert partial >= 3, "fixture must contain partially valid edges"
+
+
+# ------------------------------------------------------------------ TendonRobot::shape (reference's own text)
+@pytest.mark.skipif(not ref.RefTendonRobot.available(), reason="oracle/_ref/libtendonrobot_ref.so not built")
+@pytest.mark.parametrize("name", ["a005", "b003", "b005rot", "a003soft", "b005tight"])
+def test_live_tendon_robot_shape(orc, wl, name):
+    """TendonRobot::shape -> tension_shape (TendonRobot.cpp:325-500: t_range, initial condition, RK4 over the
+    grid, observer, result assembly, calc_point_forces convergence flag), home_shape lengths (:249-314),
+    rotate_z, and the three ingredients of is_valid_shape -- the oracle vs the reference's own text
+    (Eigen and Boost.odeint stand-ins).  Grids, points, frames, lengths and flags are compared exactly,
+    except rotate_z (Eigen's AngleAxis computes the zz entry as (1 - c) + c)."""
+    spec = {"a005": wl.robot_a(0.005), "b003": wl.robot_b(0.003), "b005rot": wl.robot_b(0.005, rotation=True),
+            "a003soft": dict(wl.robot_a(0.003), E=0.7e6),
+            "b005tight": dict(wl.robot_b(0.005), residual_threshold=1e-13)}[name]
+    rb, rr = orc.robot(spec), ref.RefTendonRobot(spec)
+    st = wl.sample_states(spec, 200, stream=23)
+    if spec.get("enable_retraction"):
+        L = spec["L"]
+        st[0, -1], st[1, -1], st[2, -1], st[3, -1], st[4, -1] = L, L + 0.01, 0.1995, 0.0, -0.001
+    tol = 2e-16 if spec.get("enable_rotation") else 0.0
+    seen = 0
+    for s in st:
+        a, b = orc.shape(rb, s), rr.shape(s)
+        assert np.array_equal(a["t"], b["t"])
+        for k in ("p", "R"):
+            assert np.abs(a[k] - b[k]).max(initial=0.0) <= tol * max(1.0, spec["L"]), k
+        assert a["L"] == b["L"] and np.array_equal(a["L_i"], b["L_i"])
+        for k in ("u_i", "u_f", "v_i", "v_f"):
+            assert np.array_equal(a[k], b[k]), k
+        assert a["converged"] == b["converged"]
+        fr = rr.flags(s)
+        assert (orc.validity_flags(rb, s, a) & 7) == fr
+        seen |= fr
+        sret = s[-1] if spec.get("enable_retraction") else 0.0
+        assert np.array_equal(orc.home_lengths(rb, sret), rr.home_lengths(s))
+    if name == "b005tight":
+        assert seen & 1, "fixture must contain non-converged shapes"
+    if name == "a003soft":
+        assert seen & 2 and seen & 4, "fixture must contain length-limit and self-collision cases"
+
+
+@pytest.mark.parametrize("name", ["a005", "b003", "b005rot", "a003soft"])
+def test_golden_tendon_robot_shape(orc, wl, gold, name):
+    """whole shapes of the reference's TendonRobot::shape (see test_live_tendon_robot_shape), from the
+    committed vectors: runs where oracle/_ref is absent"""
+    spec = {"a005": wl.robot_a(0.005), "b003": wl.robot_b(0.003), "b005rot": wl.robot_b(0.005, rotation=True),
+            "a003soft": dict(wl.robot_a(0.003), E=0.7e6)}[name]
+    rb = orc.robot(spec)
+    k = "tr_%s_" % name
+    off = gold[k + "off"]
+    tol = 2e-16 if spec.get("enable_rotation") else 0.0
+    for i, s in enumerate(gold[k + "states"]):
+        a = orc.shape(rb, s)
+        lo, hi = off[i], off[i + 1]
+        assert np.array_equal(a["t"], gold[k + "t"][lo:hi])
+        assert np.abs(a["p"] - gold[k + "p"][lo:hi]).max(initial=0.0) <= tol
+        assert a["L"] == gold[k + "L"][i] and np.array_equal(a["L_i"], gold[k + "Li"][i])
+        assert a["converged"] == bool(gold[k + "conv"][i])
+        assert (orc.validity_flags(rb, s, a) & 7) == int(gold[k + "flags"][i])
+        sret = s[-1] if spec.get("enable_retraction") else 0.0
+        assert np.array_equal(orc.home_lengths(rb, sret), gold[k + "home"][i])
