@@ -24,10 +24,15 @@
  *     VoxelEnvironment::voxelize_valid_backbone_motion, cut out of the reference's
  *     files by function anchors at build time and compiled unmodified: voxel
  *     sets, verdicts, swept volumes, FK call counts identical;
+ *   - TendonRobot.h as is plus tension_shape / home_shape / calc_point_forces /
+ *     is_valid cut out of TendonRobot.cpp, with a second stand-in for the two
+ *     Boost.odeint facilities they use: grids, points, frames, lengths and all
+ *     validity flags identical;
  *   - the reference's vendored levmar-2.6: finite-difference Jacobian rule.
- * "Parity unpinned by the reference" still holds for what is restated only: the
- * RK4 stepping of Boost.odeint and t_range, calc_point_forces, home lengths /
- * length limits and OMPL 1.5 validSegmentCount / interpolate.  Those are pinned by
+ * "Parity unpinned by the reference" still holds for third-party arithmetic that
+ * is not under /root/reference: Eigen's rounding, Boost.odeint's stepping rule
+ * (restated here and in the stand-in) and OMPL 1.5 validSegmentCount /
+ * interpolate.  Those are pinned by
  *   (1) analytic known-answer tests (tests/test_oracle_kat.py) and
  *   (2) an independent numpy + mpmath restatement (oracle/fk_second_opinion.py).
  *
