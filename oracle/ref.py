@@ -14,6 +14,8 @@ TEST INFRASTRUCTURE ONLY (same rule as oracle/oracle.py).
   (collision/collision.cpp) and VoxelEnvironment::voxelize_valid_backbone_motion, cut out of the
   reference's files by function-name anchors at build time and compiled unmodified.
 * liblevmar_ref.so: the levmar-2.6 the reference vendors (without LAPACK).
+* libtendonrobot_ref.so: TendonRobot::shape / home_shape / is_valid (tension_shape cut out by anchors).
+* librmp_ref.so: the .rmp writer and reader (RmpStreamer, LazyRmpParser) of VoxelCachedLazyPRM.cpp.
 
 All are built by `make -C oracle ref` only where /root/reference exists; they travel to the GPU box
 as prebuilt files.  Nothing here is needed at run time by the product.
@@ -630,3 +632,92 @@ class RefTendonRobot:
         AbstractValidityChecker::is_valid_shape, evaluated separately)"""
         state = np.ascontiguousarray(state, dtype=np.float64)
         return int(self.lib().trref_flags(*self._args(), _dp(state)))
+
+
+class RefRmp:
+    """The reference's .rmp writer (RmpStreamer) and reader (LazyRmpParser), VoxelCachedLazyPRM.cpp:635-1114,
+    compiled from their own text (oracle/ref_shim/rmp_ref.cpp).  Roadmaps are exchanged in the dict form of
+    irt_b200.read_rmp / write_rmp, with block coordinates instead of Morton keys
+    (v_bxyz / e_bxyz uint8[nb][3])."""
+    _lib = None
+
+    @classmethod
+    def available(cls):
+        return os.path.exists(os.path.join(REF_DIR, "librmp_ref.so"))
+
+    @classmethod
+    def lib(cls):
+        if cls._lib is None:
+            L = C.CDLL(os.path.join(REF_DIR, "librmp_ref.so"))
+            vp, u32, u64, dp = C.c_void_p, C.c_uint32, C.c_uint64, C.POINTER(C.c_double)
+            u8p, u64p = C.POINTER(C.c_uint8), C.POINTER(C.c_uint64)
+            L.rmpref_writer_open.restype = vp
+            L.rmpref_writer_open.argtypes = [C.c_char_p, u32, u32]
+            L.rmpref_write_reference.argtypes = [vp, u64, dp]
+            L.rmpref_write_vertex.argtypes = [vp, u32, dp, C.c_int, C.c_int, dp, C.c_int, u64, dp, u64, u8p, u64p]
+            L.rmpref_write_edge.argtypes = [vp, u32, u32, C.c_double, C.c_int, u64, dp, u64, u8p, u64p]
+            L.rmpref_writer_close.argtypes = [vp]
+            L.rmpref_reader_open.restype = vp
+            L.rmpref_reader_open.argtypes = [C.c_char_p]
+            L.rmpref_reader_close.argtypes = [vp]
+            L.rmpref_next.argtypes = [vp, C.POINTER(u32), dp, dp, C.c_int, u64p, u64]
+            cls._lib = L
+        return cls._lib
+
+    @classmethod
+    def write(cls, path, d):
+        L = cls.lib()
+        u8p, u64p = C.POINTER(C.c_uint8), C.POINTER(C.c_uint64)
+        h = L.rmpref_writer_open(os.fsencode(path), int(d["n_verts"]), int(d["n_edges"]))
+        assert h
+        lim = np.ascontiguousarray(d["lims"], dtype=np.float64)
+        Ng = int(d["Ng"])
+        if d["has_voxels"]:
+            assert L.rmpref_write_reference(h, Ng, _dp(lim)) == 0
+        # without reference voxels RmpStreamer::try_write_voxels throws on any voxel object
+        # (VoxelCachedLazyPRM.cpp:1082-1086); such a roadmap is written with null voxel pointers
+        hv = bool(d["has_voxels"])
+
+        def blocks(off, bxyz, bits, i):
+            lo, hi = int(off[i]), int(off[i + 1])
+            xb = np.ascontiguousarray(bxyz[lo:hi], dtype=np.uint8).reshape(-1, 3)
+            bb = np.ascontiguousarray(bits[lo:hi], dtype=np.uint64)
+            return hi - lo, xb, bb
+
+        for i in range(int(d["n_verts"])):
+            st = np.ascontiguousarray(d["v_state"][i], dtype=np.float64)
+            tip = np.ascontiguousarray(d["v_tip"][i], dtype=np.float64)
+            nb, xb, bb = blocks(d["v_off"], d["v_bxyz"], d["v_bits"], i)
+            assert L.rmpref_write_vertex(h, int(d["v_index"][i]), _dp(st), len(st), int(bool(d["v_has_tip"][i])),
+                                         _dp(tip), int(hv and bool(d["v_has_vox"][i])), Ng, _dp(lim), nb,
+                                         xb.ctypes.data_as(u8p), bb.ctypes.data_as(u64p)) == 0
+        for i in range(int(d["n_edges"])):
+            nb, xb, bb = blocks(d["e_off"], d["e_bxyz"], d["e_bits"], i)
+            assert L.rmpref_write_edge(h, int(d["e_src"][i]), int(d["e_dst"][i]), float(d["e_weight"][i]),
+                                       int(hv and bool(d["e_has_vox"][i])), Ng, _dp(lim), nb,
+                                       xb.ctypes.data_as(u8p), bb.ctypes.data_as(u64p)) == 0
+        L.rmpref_writer_close(h)
+
+    @classmethod
+    def read(cls, path, cap_state=64, cap_leaves=1 << 16):
+        """list of ("vertex", index, state, tip or None, leaves or None) / ("edge", src, dst, weight, leaves)"""
+        L = cls.lib()
+        h = L.rmpref_reader_open(os.fsencode(path))
+        assert h
+        out = []
+        hdr = (C.c_uint32 * 6)()
+        vals, state = np.zeros(4), np.zeros(cap_state)
+        leaves = np.zeros((cap_leaves, 4), dtype=np.uint64)
+        while True:
+            t = L.rmpref_next(h, hdr, _dp(vals), _dp(state), cap_state, leaves.ctypes.data_as(C.POINTER(C.c_uint64)),
+                              cap_leaves)
+            assert t >= 0, "reference parser failed"
+            if t == 3:
+                break
+            lv = leaves[:hdr[5]].copy() if hdr[4] else None
+            if t == 1:
+                out.append(("vertex", int(hdr[0]), state[:hdr[2]].copy(), vals[1:4].copy() if hdr[3] else None, lv))
+            else:
+                out.append(("edge", int(hdr[0]), int(hdr[1]), float(vals[0]), lv))
+        L.rmpref_reader_close(h)
+        return out

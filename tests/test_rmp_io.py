@@ -125,3 +125,62 @@ def test_rmp_loads_into_device_store(tmp_path, orc, wl):
     g_file = tmp_path / "gpu.rmp"
     irt.write_rmp(str(g_file), out)
     assert g_file.read_bytes() == f.read_bytes()
+
+
+def test_rmp_against_reference_reader_and_writer(tmp_path, orc, wl):
+    """The native .rmp writer / reader against the REFERENCE'S OWN RmpStreamer / LazyRmpParser
+    (VoxelCachedLazyPRM.cpp:635-1114, compiled from their own text into oracle/_ref/librmp_ref.so):
+    same roadmap -> byte-identical files; each side parses the other's file."""
+    from oracle import ref
+    if not ref.RefRmp.available():
+        pytest.skip("oracle/_ref/librmp_ref.so not built (no /root/reference here)")
+    import irt_b200
+    for has_voxels in (True, False):
+        spec, g, d = _roadmap(orc, wl)
+        d = dict(d, has_voxels=has_voxels)
+        Nb = d["Ng"] // 4
+        dd = dict(d)
+        for pre in ("v", "e"):
+            bx, by, bz = wl.morton_decode(np.asarray(d[pre + "_keys"], dtype=np.uint32), Nb)
+            dd[pre + "_bxyz"] = np.stack([bx, by, bz], axis=1).astype(np.uint8)
+        ref_file, own_file = tmp_path / ("ref%d.rmp" % has_voxels), tmp_path / ("own%d.rmp" % has_voxels)
+        ref.RefRmp.write(str(ref_file), dd)
+        irt_b200.write_rmp(str(own_file), d)
+        assert own_file.read_bytes() == ref_file.read_bytes()
+        assert ref_file.read_bytes() == _reference_style_bytes(wl, d)     # and the struct.pack restatement
+        # the reference's parser on the native file
+        items = ref.RefRmp.read(str(own_file))
+        assert len(items) == d["n_verts"] + d["n_edges"]
+        # the reference's binary_read(std::optional<T>&) (VoxelCachedLazyPRM.cpp:715-724) leaves the optional
+        # untouched when the file says "absent", and LazyRmpParser::next() (:899-903) reuses one _current_vertex:
+        # a vertex written without a tip comes back with the LAST tip read before it.  The native reader
+        # reports what the file holds (v_has_tip); the expectation here follows the reference's carry-over.
+        last_tip = None
+        for i in range(d["n_verts"]):
+            kind, idx, st, tip, lv = items[i]
+            assert kind == "vertex" and idx == d["v_index"][i] and np.array_equal(st, d["v_state"][i])
+            if d["v_has_tip"][i]:
+                last_tip = np.asarray(d["v_tip"][i], dtype=np.float64)
+            assert (tip is not None) == (last_tip is not None)
+            if tip is not None:
+                assert np.array_equal(tip, last_tip)
+            lo, hi = int(d["v_off"][i]), int(d["v_off"][i + 1])
+            if has_voxels and d["v_has_vox"][i]:
+                assert np.array_equal(lv[:, :3].astype(np.uint8), dd["v_bxyz"][lo:hi])
+                assert np.array_equal(lv[:, 3], d["v_bits"][lo:hi])
+            else:
+                assert lv is None
+        for i in range(d["n_edges"]):
+            kind, src, dst, w, lv = items[d["n_verts"] + i]
+            assert kind == "edge" and (src, dst, w) == (d["e_src"][i], d["e_dst"][i], d["e_weight"][i])
+            lo, hi = int(d["e_off"][i]), int(d["e_off"][i + 1])
+            if has_voxels and d["e_has_vox"][i]:
+                assert np.array_equal(lv[:, 3], d["e_bits"][lo:hi])
+            else:
+                assert lv is None
+        # the native reader on the reference's file
+        r = irt_b200.read_rmp(str(ref_file))
+        assert r["n_verts"] == d["n_verts"] and bool(r["has_voxels"]) == has_voxels
+        assert np.array_equal(r["v_state"], d["v_state"]) and np.array_equal(r["e_weight"], d["e_weight"])
+        if has_voxels:
+            assert np.array_equal(r["v_keys"], d["v_keys"]) and np.array_equal(r["e_bits"], d["e_bits"])
