@@ -20,6 +20,7 @@
 // There is no CPU fallback: without a CUDA device the Context constructor throws.
 #pragma once
 
+#include <algorithm>
 #include <array>
 #include <cmath>
 #include <cstdint>
@@ -27,6 +28,8 @@
 #include <functional>
 #include <map>
 #include <memory>
+#include <random>
+#include <set>
 #include <stdexcept>
 #include <string>
 #include <tuple>
@@ -212,6 +215,31 @@ struct TendonRobot {  // tendon/TendonRobot.h:52-355
     return shape(st);
   }
   std::vector<collision::Point> forward_kinematics(const std::vector<double> &state) const { return shape(state).p; }
+
+  /// random_state (tendon/TendonRobot.cpp:219-247): tensions U[0, max_tension], rotation U[-pi, pi],
+  /// retraction U[0, L], in state order.  The generator overload is what a seeded caller uses; the
+  /// argument-free form keeps the reference's thread-local std::mt19937 seeded from std::random_device.
+  template <class Generator>
+  std::vector<double> random_state(Generator &generator) const {
+    std::vector<double> state;
+    for (auto &tendon : tendons) {
+      std::uniform_real_distribution<double> dist(0.0, tendon.max_tension);
+      state.push_back(dist(generator));
+    }
+    if (enable_rotation) {
+      std::uniform_real_distribution<double> dist(-M_PI, M_PI);
+      state.push_back(dist(generator));
+    }
+    if (enable_retraction) {
+      std::uniform_real_distribution<double> dist(0.0, specs.L);
+      state.push_back(dist(generator));
+    }
+    return state;
+  }
+  std::vector<double> random_state() const {
+    static thread_local std::mt19937 generator{std::random_device{}()};
+    return random_state(generator);
+  }
 
   /// home_shape (tendon/TendonRobot.cpp:249-314): straight backbone, closed-form tendon lengths
   TendonResult home_shape(double s_start = 0) const {
@@ -665,6 +693,152 @@ public:
     vflags_.clear(); eflags_.clear();
     clearValidity();
   }
+  // ---- createRoadmap (VoxelCachedLazyPRM.h:468-495, .cpp:1380-1561) -------------------------------------
+  enum CreateRoadmapOption : unsigned {
+    LazyRoadmap = 0x0,       // nothing is checked, just sampled configs and connecting edges
+    VoxelizeVertices = 0x1,  // voxelize vertices, rejecting invalid shapes
+    ValidateVertices = 0x2,  // ... and rejecting vertices that hit the environment
+    VoxelizeEdges = 0x4,     // voxelize edges, removing those that are not fully valid
+    ValidateEdges = 0x8,     // ... and removing edges that hit the environment
+  };
+  using Sampler = std::function<std::vector<double>()>;
+  /// sampler_->sampleUniform: by default TendonRobot::random_state over a seeded std::mt19937
+  /// (the reference's `sample_like_sphere` RetractionSampler is a setSampler() away)
+  void setSampler(Sampler s) { sampler_ = std::move(s); }
+  void setSeed(uint32_t seed) { gen_.seed(seed); }
+  /// KBoundedStrategy(k, range) over nn_ (.cpp:1329-1345): the k nearest milestones of v -- v itself is
+  /// one of them, it is in nn_ by then -- no further away than range.  magic::DEFAULT_NEAREST_NEIGHBORS_LAZY
+  /// = 5 (.cpp:125); range defaults to SelfConfig::configurePlannerRange's 20 % of the maximum extent.
+  void setMaxNearestNeighbors(size_t k) { k_ = k; }
+  void setRange(double d) { range_ = d; }
+  double getRange() const { return range_ > 0.0 ? range_ : 0.2 * maximumExtent(); }
+  /// replaces the default exact (brute-force) neighbour search: v -> candidate neighbours, nearest first
+  void setConnectionStrategy(std::function<std::vector<size_t>(size_t)> f) { connection_ = std::move(f); }
+
+  /// weights and extents of the compound space of Problem::create_space_information (Problem.cpp:101-163)
+  double tensionExtent() const {
+    double e2 = 0.0;
+    for (auto &t : robot_.tendons) e2 += t.max_tension * t.max_tension;
+    return std::sqrt(e2);
+  }
+  double maximumExtent() const {  // CompoundStateSpace: sum of weight_i * extent_i
+    const double ext = tensionExtent();
+    double e = ext;
+    if (robot_.enable_rotation) e += (ext / (4.0 * M_PI)) * M_PI;
+    if (robot_.enable_retraction) e += (2.0 * ext / robot_.specs.L) * robot_.specs.L;
+    return e;
+  }
+  /// distanceFunction / motionCost: CompoundStateSpace::distance = sum of weight_i * d_i
+  double distance(const std::vector<double> &a, const std::vector<double> &b) const {
+    const size_t N = robot_.tendons.size();
+    const double ext = tensionExtent();
+    double d2 = 0.0;
+    for (size_t i = 0; i < N; i++) d2 += (a[i] - b[i]) * (a[i] - b[i]);
+    double d = std::sqrt(d2);
+    size_t k = N;
+    if (robot_.enable_rotation) {
+      double dr = std::fabs(a[k] - b[k]);  // SO2StateSpace::distance
+      if (dr > M_PI) dr = 2.0 * M_PI - dr;
+      d += (ext / (4.0 * M_PI)) * dr;
+      k++;
+    }
+    if (robot_.enable_retraction) d += (2.0 * ext / robot_.specs.L) * std::fabs(a[k] - b[k]);
+    return d;
+  }
+
+  /// Brings the roadmap up to N vertices.  Same order of work as the reference: rejection-sample the new
+  /// vertices (here: whole candidate batches through ONE FK / voxelise / check call each round instead of
+  /// an OpenMP loop of single shapes), add them all, connect every new vertex to its neighbours
+  /// sequentially, then voxelise (and validate) the new edges as one batch and remove the invalid ones.
+  /// Options only pertain to what is added.  Duplicate states (addMilestone's was_added == false) cannot
+  /// be told apart from a rejected sample here and are not looked for.
+  void createRoadmap(size_t N, unsigned opt = LazyRoadmap) {
+    const size_t Nv = states_.size();
+    if (N <= Nv) return;  // "Graph is already at or bigger than N, skipping roadmap creation"
+    const bool validate_verts = opt & ValidateVertices, validate_edges = opt & ValidateEdges;
+    const bool voxelize_verts = validate_verts || (opt & VoxelizeVertices);
+    const bool voxelize_edges = validate_edges || (opt & VoxelizeEdges);
+    const size_t S = robot_.state_size();
+    const bool had_vcache = vflags_.size() == Nv && Nv > 0, had_ecache = eflags_.size() == edges_.size() && !edges_.empty();
+    const uint32_t bad_shape = IRT_FLAG_NONCONVERGED | IRT_FLAG_LENGTH_LIMIT | IRT_FLAG_SELF_COLLISION |
+                               IRT_FLAG_BAD_STATE | IRT_FLAG_OUT_OF_DOMAIN;
+
+    // ---- rejection sampling, a batch per round (.cpp:1415-1455) ----
+    std::vector<std::vector<double>> added;
+    irt_setstore *scratch = nullptr;
+    irt_grid g = env_voxels_.grid(venv_.inv_rotation);
+    irt::check(ctx_, irt_setstore_create(ctx_, &g, &scratch));
+    std::shared_ptr<irt_setstore> guard(scratch, [](irt_setstore *x) { irt_setstore_destroy(x); });
+    for (int round = 0; added.size() < N - Nv; round++) {
+      if (round >= 1000) throw std::runtime_error("createRoadmap: rejection sampling does not terminate");
+      const size_t need = N - Nv - added.size(), m = need + need / 4 + 16;
+      std::vector<std::vector<double>> cand(m);
+      for (auto &c : cand) {
+        c = sampler_ ? sampler_() : robot_.random_state(gen_);
+        if (c.size() != S) throw std::invalid_argument("State is not the right size");
+      }
+      std::vector<char> keep(m, 1);
+      if (voxelize_verts) {
+        std::vector<double> flat(m * S), tips(3 * m);
+        std::vector<uint32_t> fl(m), words((m + 31) / 32 + 1, 0);
+        for (size_t i = 0; i < m; i++) std::copy(cand[i].begin(), cand[i].end(), flat.begin() + i * S);
+        irt::check(ctx_, irt_voxelize_vertices(ctx_, robot_.handle(), flat.data(), (int)S, (int64_t)m, scratch,
+                                               fl.data(), tips.data()));
+        if (validate_verts) irt::check(ctx_, irt_check_sets(ctx_, scratch, env_, 0, (int64_t)m, words.data()));
+        for (size_t i = 0; i < m; i++)
+          keep[i] = !(fl[i] & bad_shape) && !((words[i >> 5] >> (i & 31)) & 1u);
+      }
+      for (size_t i = 0; i < m && added.size() < N - Nv; i++)
+        if (keep[i]) added.push_back(std::move(cand[i]));
+    }
+    states_.insert(states_.end(), added.begin(), added.end());
+    vertex_validity_.resize(N, VALIDITY_UNKNOWN);
+    if (voxelize_verts || had_vcache) {
+      precomputeVertexVoxelCache();  // one batch over all vertices: the old sets are recomputed, not changed
+      if (validate_verts) std::fill(vertex_validity_.begin() + Nv, vertex_validity_.end(), VALIDITY_TRUE);
+    }
+
+    // ---- empty edges, sequentially, new vertices in index order (.cpp:1486-1500) ----
+    std::set<std::pair<size_t, size_t>> have;
+    for (auto &e : edges_) have.insert(std::minmax(e.first, e.second));
+    std::vector<std::pair<size_t, size_t>> new_edges;
+    for (size_t v = Nv; v < N; v++)
+      for (size_t n : (connection_ ? connection_(v) : nearestKBounded(v)))
+        if (n != v && have.insert(std::minmax(v, n)).second) new_edges.emplace_back(v, n);  // connectVertices
+
+    // ---- voxelise / validate the new edges and remove the invalid ones (.cpp:1505-1551) ----
+    if (voxelize_edges && !new_edges.empty()) {
+      const size_t m = new_edges.size();
+      std::vector<double> a(m * S), b(m * S);
+      for (size_t i = 0; i < m; i++) {
+        std::copy(states_[new_edges[i].first].begin(), states_[new_edges[i].first].end(), a.begin() + i * S);
+        std::copy(states_[new_edges[i].second].begin(), states_[new_edges[i].second].end(), b.begin() + i * S);
+      }
+      std::vector<uint32_t> fl(m), words((m + 31) / 32 + 1, 0);
+      irt::check(ctx_, irt_voxelize_edges(ctx_, robot_.handle(), &space_, a.data(), b.data(), (int)S, (int64_t)m,
+                                          scratch, fl.data(), nullptr, nullptr));
+      if (validate_edges) irt::check(ctx_, irt_check_sets(ctx_, scratch, env_, 0, (int64_t)m, words.data()));
+      std::vector<std::pair<size_t, size_t>> kept;
+      for (size_t i = 0; i < m; i++)
+        if (!(fl[i] & IRT_FLAG_PARTIAL) && !((words[i >> 5] >> (i & 31)) & 1u)) kept.push_back(new_edges[i]);
+      new_edges.swap(kept);
+    }
+    const size_t Ne = edges_.size();
+    edges_.insert(edges_.end(), new_edges.begin(), new_edges.end());
+    edge_validity_.resize(edges_.size(), VALIDITY_UNKNOWN);
+    if (voxelize_edges || had_ecache) {
+      precomputeEdgeVoxelCache();
+      if (validate_edges) std::fill(edge_validity_.begin() + Ne, edge_validity_.end(), VALIDITY_TRUE);
+    } else {
+      eflags_.clear();
+    }
+    if (!(voxelize_verts || had_vcache)) vflags_.clear();
+  }
+  const std::vector<std::vector<double>> &states() const { return states_; }
+  const std::vector<std::pair<size_t, size_t>> &edges() const { return edges_; }
+  /// tip position of every vertex with a voxel cache (tipPositionProperty_), xyz per vertex
+  const std::vector<double> &tipPositions() const { return tips_; }
+
   void precomputeVertexVoxelCache() {  // .cpp:1687-1734
     const size_t S = robot_.state_size(), n = states_.size();
     std::vector<double> flat(n * S);
@@ -713,6 +887,17 @@ public:
   const std::vector<uint32_t> &edgeFlags() const { return eflags_; }
 
 private:
+  /// exact k nearest of v among all milestones (v included, like nn_->nearestK), cut at the range
+  std::vector<size_t> nearestKBounded(size_t v) const {
+    std::vector<std::pair<double, size_t>> d(states_.size());
+    for (size_t i = 0; i < states_.size(); i++) d[i] = {distance(states_[v], states_[i]), i};
+    const size_t k = std::min(k_, d.size());
+    std::partial_sort(d.begin(), d.begin() + k, d.end());
+    std::vector<size_t> out;
+    const double bound = getRange();
+    for (size_t i = 0; i < k && d[i].first <= bound; i++) out.push_back(d[i].second);
+    return out;
+  }
   void sweep(irt_setstore *st, const std::vector<uint32_t> &flags, uint32_t mask, std::vector<unsigned> &validity) {
     const int64_t n = irt_setstore_num_sets(st);
     std::vector<uint32_t> words((n + 31) / 32 + 1, 0);
@@ -735,6 +920,11 @@ private:
   std::vector<uint32_t> vflags_, eflags_;
   std::vector<double> tips_;
   std::vector<unsigned> vertex_validity_, edge_validity_;
+  Sampler sampler_;
+  std::function<std::vector<size_t>(size_t)> connection_;
+  std::mt19937 gen_{20220801u};
+  size_t k_ = 5;
+  double range_ = 0.0;
 };
 
 }  // namespace motion_planning

@@ -26,6 +26,8 @@ from . import (INVALID_MASK, FLAG_PARTIAL, Env, SetStore, make_space, shard_rang
 
 VALIDITY_UNKNOWN = 0  # VoxelCachedLazyPRM.h:598-601
 VALIDITY_TRUE = 1
+# CreateRoadmapOption, VoxelCachedLazyPRM.h:468-479
+LazyRoadmap, VoxelizeVertices, ValidateVertices, VoxelizeEdges, ValidateEdges = 0x0, 0x1, 0x2, 0x4, 0x8
 
 
 def shard_words(n, world, align=64):
@@ -76,6 +78,9 @@ class VoxelCachedLazyPRM:
         self.vertex_validity = np.zeros(0, dtype=np.uint8)
         self.edge_validity = np.zeros(0, dtype=np.uint8)
         self._have_vcache = self._have_ecache = False
+        self.seed = 20220801         # of the default sampler (the reference seeds from std::random_device)
+        self.max_nearest_neighbors = 5   # magic::DEFAULT_NEAREST_NEIGHBORS_LAZY (VoxelCachedLazyPRM.cpp:125)
+        self.range = None            # maxDistance_; None = configurePlannerRange's 20 % of the maximum extent
         self.fused_gather = True     # multi-GPU sweeps: fuse the verdict all-gather into K3 (peer memory)
         self._xchg = {}
 
@@ -94,24 +99,140 @@ class VoxelCachedLazyPRM:
         self._have_vcache = self._have_ecache = False
         self.clearValidity()
 
-    def createRoadmap(self, n_vertices, sampler, connect, max_rounds=64):
-        """Rejection-sample `n_vertices` valid configurations (VoxelCachedLazyPRM.cpp:1415-1455:
-        a sample is kept iff is_valid_shape) and connect them with `connect(states) -> edges`
-        (the reference's connectionStrategy_, host side).  `sampler(count, round) -> states`."""
-        kept = []
-        total = 0
+    def distance(self, a, b):
+        """distanceFunction / motionCost of the compound space of Problem::create_space_information
+        (Problem.cpp:101-163): |d tau| + (ext / 4 pi) * SO2 distance + (2 ext / L) * |d retraction|,
+        ext = |max_tension|.  a: [S] or [m][S], b: [n][S] -> [n] or [m][n]."""
+        d = self.robot.spec
+        N = len(d["C"])
+        ext = float(np.linalg.norm(np.asarray(d["max_tension"], dtype=np.float64)[:N]))
+        a = np.asarray(a, dtype=np.float64)[..., None, :]
+        b = np.asarray(b, dtype=np.float64)
+        out = np.sqrt(((a[..., :N] - b[..., :N]) ** 2).sum(-1))
+        k = N
+        if d.get("enable_rotation"):
+            dr = np.abs(a[..., k] - b[..., k])
+            out = out + (ext / (4 * np.pi)) * np.where(dr > np.pi, 2 * np.pi - dr, dr)
+            k += 1
+        if d.get("enable_retraction"):
+            out = out + (2 * ext / d["L"]) * np.abs(a[..., k] - b[..., k])
+        return out
+
+    def maximum_extent(self):
+        """CompoundStateSpace::getMaximumExtent = sum of weight_i * extent_i"""
+        d = self.robot.spec
+        ext = float(np.linalg.norm(np.asarray(d["max_tension"], dtype=np.float64)[:len(d["C"])]))
+        return ext * (1.0 + (0.25 if d.get("enable_rotation") else 0.0) + (2.0 if d.get("enable_retraction") else 0.0))
+
+    def k_bounded_neighbors(self, v, k=None, bound=None):
+        """KBoundedStrategy(k, range) over nn_ (VoxelCachedLazyPRM.cpp:1329-1345): the k nearest milestones of
+        v -- v itself is one of them, it is in nn_ by then -- no further away than the range.  Exact."""
+        k = self.max_nearest_neighbors if k is None else k
+        bound = (self.range or 0.2 * self.maximum_extent()) if bound is None else bound
+        d = self.distance(self.states[v], self.states)
+        order = np.lexsort((np.arange(len(d)), d))[:k]
+        return order[d[order] <= bound]
+
+    def random_states(self, count, rnd=0):
+        """TendonRobot::random_state (tendon/TendonRobot.cpp:219-247) for a batch, seeded: tensions
+        U[0, max_tension], rotation U[-pi, pi], retraction U[0, L], in state order"""
+        d = self.robot.spec
+        g = np.random.Generator(np.random.Philox(key=[self.seed, rnd]))
+        N = len(d["C"])
+        cols = [g.uniform(0.0, d["max_tension"][j], count) for j in range(N)]
+        if d.get("enable_rotation"):
+            cols.append(g.uniform(-np.pi, np.pi, count))
+        if d.get("enable_retraction"):
+            cols.append(g.uniform(0.0, d["L"], count))
+        return np.ascontiguousarray(np.stack(cols, axis=1))
+
+    def createRoadmap(self, n_vertices, sampler=None, connect=None, max_rounds=64, opt=VoxelizeVertices):
+        """Brings the roadmap up to `n_vertices` (VoxelCachedLazyPRM.cpp:1380-1561), in the reference's order:
+        rejection-sample the new vertices, add them all, connect every new vertex, then voxelise / validate
+        the new edges as one batch and remove the invalid ones.  `opt` is the reference's
+        CreateRoadmapOption bit set (VoxelCachedLazyPRM.h:468-479) and only pertains to what is added:
+          LazyRoadmap       nothing is checked
+          VoxelizeVertices  a sample is kept iff is_valid_shape                    (.cpp:1415-1443)
+          ValidateVertices  ... and its voxels miss the environment
+          VoxelizeEdges     new edges that are not fully valid are removed         (.cpp:1505-1551)
+          ValidateEdges     ... and new edges whose swept volume hits the environment
+        sampler(count, round) -> states (default: random_states = TendonRobot::random_state);
+        connect(states) -> int64[n_edges][2] for the whole vertex list (default: k_bounded_neighbors of every
+        new vertex, new vertices in index order, no duplicates -- connectionStrategy_ + getEdge, .cpp:1486-1500).
+        Candidates are judged as whole batches (one FK / voxelise / check call per round), on every rank
+        alike; the edge work is sharded like every other sweep."""
+        validate_verts, validate_edges = bool(opt & ValidateVertices), bool(opt & ValidateEdges)
+        voxelize_verts = validate_verts or bool(opt & VoxelizeVertices)
+        voxelize_edges = validate_edges or bool(opt & VoxelizeEdges)
+        nv0, ne0 = len(self.states), len(self.edges)
+        if n_vertices <= nv0:
+            return self      # "Graph is already at or bigger than N, skipping roadmap creation"
+        sampler = sampler or self.random_states
+        kept, total = [], 0
+        scratch = SetStore(self.ctx, self.grid) if validate_verts else None
         for rnd in range(max_rounds):
-            need = n_vertices - total
+            need = n_vertices - nv0 - total
             if need <= 0:
                 break
-            cand = sampler(int(need * 1.25) + 64, rnd)
-            out = self.robot.shape_batch(cand, want=("flags",))
-            ok = (out["flags"] & INVALID_MASK) == 0
+            cand = np.ascontiguousarray(sampler(int(need * 1.25) + 64, rnd), dtype=np.float64)
+            ok = np.ones(len(cand), dtype=bool)
+            if validate_verts:
+                flags, _ = scratch.voxelize_vertices(self.robot, cand)
+                ok = ((flags & INVALID_MASK) == 0) & ~scratch.check(self.env)
+            elif voxelize_verts:
+                ok = (self.robot.shape_batch(cand, want=("flags",))["flags"] & INVALID_MASK) == 0
             good = cand[ok][:need]
             kept.append(good)
             total += len(good)
-        states = np.concatenate(kept, axis=0)[:n_vertices]
-        self.set_roadmap(states, connect(states))
+        if total < n_vertices - nv0:
+            raise RuntimeError("createRoadmap: rejection sampling kept %d of %d vertices in %d rounds"
+                               % (total, n_vertices - nv0, max_rounds))
+        old_vv, old_ev = self.vertex_validity, self.edge_validity
+        had_vcache, had_ecache = self._have_vcache, self._have_ecache
+        states = np.concatenate([self.states.reshape(-1, self.robot.state_size)] + kept, axis=0)[:n_vertices]
+        self.states = np.ascontiguousarray(states)
+        # ---- empty edges ----
+        if connect is not None:
+            new_edges = np.ascontiguousarray(connect(self.states), dtype=np.int64).reshape(-1, 2)
+            if ne0:     # keep what was there, add what is new (getEdge: an edge can exist already)
+                have = set(map(tuple, np.sort(self.edges, axis=1).tolist()))
+                new_edges = np.array([e for e in new_edges.tolist() if tuple(sorted(e)) not in have],
+                                     dtype=np.int64).reshape(-1, 2)
+        else:
+            have = set(map(tuple, np.sort(self.edges, axis=1).tolist()))
+            out = []
+            for v in range(nv0, n_vertices):
+                for n in self.k_bounded_neighbors(v).tolist():
+                    key = (min(v, n), max(v, n))
+                    if n != v and key not in have:      # connectVertices: a == b makes no edge
+                        have.add(key)
+                        out.append((v, n))
+            new_edges = np.array(out, dtype=np.int64).reshape(-1, 2)
+        self.edges = np.concatenate([self.edges, new_edges], axis=0)
+        self._have_vcache = self._have_ecache = False
+        # ---- voxelise / validate the new edges, remove the invalid ones ----
+        if voxelize_edges and len(new_edges):
+            self.precomputeEdgeVoxelCache()
+            n = len(self.edges)
+            bad = self._gather_flags(self.edge_flags, n, FLAG_PARTIAL)
+            if validate_edges:
+                bad |= self._sweep(self.edge_store, n, self.edge_flags)
+            bad[:ne0] = False
+            self.edges = np.ascontiguousarray(self.edges[~bad])
+            self._have_ecache = False
+        # ---- caches and validity words of the grown roadmap ----
+        if voxelize_verts or had_vcache:
+            self.precomputeVertexVoxelCache()
+        if voxelize_edges or had_ecache:
+            self.precomputeEdgeVoxelCache()
+        self.vertex_validity = np.zeros(len(self.states), dtype=np.uint8)
+        self.vertex_validity[:nv0] = old_vv[:nv0]
+        self.edge_validity = np.zeros(len(self.edges), dtype=np.uint8)
+        self.edge_validity[:ne0] = old_ev[:ne0]
+        if validate_verts:
+            self.vertex_validity[nv0:] = VALIDITY_TRUE
+        if validate_edges:
+            self.edge_validity[ne0:] = VALIDITY_TRUE
         return self
 
     def shard(self, n):

@@ -5,7 +5,9 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <algorithm>
 #include <random>
+#include <set>
 #include <vector>
 
 #include "../../interactive-rate-tendons_b200/host/irt_host.hpp"
@@ -27,6 +29,8 @@ static orc_robot to_orc(const tendon::TendonRobot &rb) {
   std::memcpy(&o, &d, sizeof(o));
   return o;
 }
+
+#include "create_roadmap_checks.hpp"
 
 int main() {
   // Robot B: 6 helical tendons, retraction + rotation
@@ -229,6 +233,9 @@ int main() {
   prm.setEnvironment(env_vox.empty_copy());
   prm.precomputeVertexValidity();
   for (size_t i = 0; i < verts.size(); i++) CHECK(prm.vertexValidity()[i] == ((prm.vertexFlags()[i] & 39u) == 0 ? 1u : 0u));
+
+  // ---- createRoadmap(N, opt) (VoxelCachedLazyPRM.cpp:1380-1561) and TendonRobot::random_state ---------
+  check_create_roadmap(robot, venv, env_vox, orb, og, oenv, osp);
 
   // ---- tip_control::Jacobian / levmar's central-difference Jacobian for a batch of IK seeds -----
   {

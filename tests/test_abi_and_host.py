@@ -168,3 +168,35 @@ def test_two_rank_gloo_verdict_gather(tmp_path):
                          capture_output=True, text=True, env=env, timeout=300)
     assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
     assert out.stdout.count("ok") == 2
+
+
+def test_cpp_host_mirror_compiles_and_links(tmp_path, irt, orc):
+    """the whole C++ host mirror test links against the C-ABI library here; it must then refuse to run
+    without a device (no CPU fallback) -- the run itself is tests/test_gpu_host_cpp.py"""
+    exe = str(tmp_path / "test_host_mirror")
+    pkg = os.path.dirname(irt.LIB_PATH)
+    subprocess.check_call(["g++", "-std=c++17", "-O0", "-Wall", "-Wextra", "-Werror",
+                           os.path.join(ROOT, "tests", "cpp", "test_host_mirror.cpp"), "-o", exe,
+                           "-L" + pkg, "-lirt_b200", "-L" + os.path.join(ROOT, "oracle"), "-loracle",
+                           "-Wl,-rpath," + pkg, "-Wl,-rpath," + os.path.join(ROOT, "oracle"), "-fopenmp"])
+    import torch
+    if not torch.cuda.is_available():
+        out = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+        assert out.returncode != 0 and "no CUDA device" in out.stderr
+
+
+def test_cpp_create_roadmap_host_logic(tmp_path, orc):
+    """VoxelCachedLazyPRM::createRoadmap(N, opt) and TendonRobot::random_state of the C++ mirror: the host
+    logic above the boundary (rejection rounds, KBounded connection, removal of invalid edges, validity
+    bookkeeping, growing) against the oracle, with the C-ABI calls answered by a test-only stand-in over the
+    oracle (tests/cpp/abi_standin_over_oracle.cpp).  The same checks run on the real library on the GPU box."""
+    exe = str(tmp_path / "test_create_roadmap_host")
+    cpp = os.path.join(ROOT, "tests", "cpp")
+    subprocess.check_call(["g++", "-std=c++17", "-O1", "-Wall", "-Wextra", "-Werror",
+                           os.path.join(cpp, "test_create_roadmap_host.cpp"),
+                           os.path.join(cpp, "abi_standin_over_oracle.cpp"), "-o", exe,
+                           "-L" + os.path.join(ROOT, "oracle"), "-loracle",
+                           "-Wl,-rpath," + os.path.join(ROOT, "oracle"), "-fopenmp"])
+    out = subprocess.run([exe], capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-2000:]
+    assert "createRoadmap host logic ok" in out.stdout

@@ -803,3 +803,59 @@ def test_fk_packed_outputs_equal_dense(irt, ctx, wl, robot, rot, n):
             rb.shape_batch_packed(st, want=("p", "npts"), cap_rows=k["rows"] - 1)
         assert ei.value.status == irt.IRT_ERR_CAPACITY
     assert rb.shape_batch_packed(st[:0], want=("p", "npts"))["rows"] == 0
+
+
+def test_create_roadmap_options(irt, ctx, orc, wl):
+    """createRoadmap(N, opt) of the batch mirror (VoxelCachedLazyPRM.cpp:1380-1561): with every option on, each
+    kept vertex is a valid shape that misses the environment, and the kept edges are exactly those candidate
+    edges (k nearest incl. the vertex itself, range-bounded, new vertices in index order) that the oracle finds
+    fully valid and collision free; growing the roadmap only touches what is added."""
+    from irt_b200 import roadmap as R
+    spec = wl.robot_b(0.003, rotation=True)
+    g = wl.workspace_grid(spec)
+    Nb = g["Ng"] // 4
+    grid = irt.make_grid(g["Ng"], g["lim"])
+    rb = irt.Robot(ctx, spec)
+    prm = R.VoxelCachedLazyPRM(ctx, rb, grid)
+    env_blocks = wl.dense_to_morton_blocks(wl.lung_like_env_dense(spec, g))
+    prm.setEnvironment(env_blocks)
+    prm.createRoadmap(150, opt=R.VoxelizeVertices | R.ValidateVertices | R.VoxelizeEdges | R.ValidateEdges)
+    assert prm.states.shape == (150, 8)
+    orb, ogrid, osp = orc.robot(spec), orc.grid(g["Ng"], g["lim"]), orc.space()
+    oenv = _oracle_env(orc, wl, ogrid, env_blocks, Nb)
+    ostore, oflags = orc.voxelize_vertices_batch(orb, ogrid, prm.states)
+    assert np.all(oflags == 0) and not orc.check_sets_batch(ostore, oenv).any()
+    assert np.all(prm.vertex_validity == R.VALIDITY_TRUE) and np.all(prm.vertex_flags == 0)
+    assert _csr_flips(prm.vertex_store.export_csr(), ostore.export()) == 0
+    # replay the connection loop and ask the oracle about every candidate
+    have, cand = set(), []
+    for v in range(150):
+        d = prm.distance(prm.states[v], prm.states)
+        order = np.lexsort((np.arange(150), d))[:5]
+        assert order[0] == v
+        for n in order[d[order] <= 0.2 * prm.maximum_extent()].tolist():
+            key = (min(v, n), max(v, n))
+            if n != v and key not in have:
+                have.add(key)
+                cand.append((v, n))
+    cand = np.array(cand, dtype=np.int64)
+    oes, oinfo = orc.voxelize_edges_batch(orb, ogrid, osp, prm.states[cand[:, 0]], prm.states[cand[:, 1]])
+    ok = ((oinfo["flags"] & irt.FLAG_PARTIAL) == 0) & ~orc.check_sets_batch(oes, oenv).astype(bool)
+    assert ok.sum() > 0
+    assert np.array_equal(prm.edges, cand[ok])
+    assert np.all(prm.edge_validity == R.VALIDITY_TRUE) and np.all(prm.edge_flags == 0)
+    assert prm.edge_store.num_sets == len(prm.edges)
+    # growing: N <= size is a no-op; lazy growth keeps what was there and validates nothing new
+    states0, edges0 = prm.states.copy(), prm.edges.copy()
+    prm.createRoadmap(100)
+    assert len(prm.states) == 150 and np.array_equal(prm.edges, edges0)
+    prm.createRoadmap(200, opt=R.LazyRoadmap)
+    assert len(prm.states) == 200 and np.array_equal(prm.states[:150], states0)
+    assert np.array_equal(prm.edges[:len(edges0)], edges0) and len(prm.edges) > len(edges0)
+    assert np.all(prm.vertex_validity[:150] == R.VALIDITY_TRUE) and not prm.vertex_validity[150:].any()
+    assert np.all(prm.edge_validity[:len(edges0)] == R.VALIDITY_TRUE) and not prm.edge_validity[len(edges0):].any()
+    assert prm.vertex_store.num_sets == 200 and prm.edge_store.num_sets == len(prm.edges)   # caches follow
+    # the default sampler is TendonRobot::random_state: inside the state bounds
+    s = prm.random_states(1000, 3)
+    assert s[:, :6].min() >= 0 and s[:, :6].max() <= 20 and np.abs(s[:, 6]).max() <= np.pi
+    assert s[:, 7].min() >= 0 and s[:, 7].max() <= spec["L"]

@@ -1,0 +1,142 @@
+"""Host logic of the Python batch mirror's createRoadmap(N, opt) (interactive-rate-tendons_b200/roadmap.py;
+reference: VoxelCachedLazyPRM.cpp:1380-1561) WITHOUT a GPU: the three device objects it talks to (Robot,
+SetStore, Env) are replaced, in this test only, by stand-ins answered by the CPU oracle, so that the rejection
+rounds, the KBounded connection loop, the removal of invalid edges, the validity bookkeeping and the growing
+of a roadmap are checked here.  The same scenario runs on the real library in
+tests/test_gpu_parity.py::test_create_roadmap_options."""
+import numpy as np
+import pytest
+
+
+class _Robot:
+    def __init__(self, orc, spec, wl):
+        self.orc, self.spec, self.orb = orc, spec, orc.robot(spec)
+        self.state_size = wl.state_size(spec)
+
+    def shape_batch(self, states, want=("flags",)):
+        return dict(flags=self.orc.fk_batch(self.orb, states, 128, want_p=False)["flags"])
+
+
+class _Env:
+    def __init__(self, oenv):
+        self.oenv = oenv
+
+
+class _Store:
+    def __init__(self, orc, ogrid):
+        self.orc, self.ogrid, self.store, self.calls = orc, ogrid, None, 0
+
+    @property
+    def num_sets(self):
+        return self.store.size() if self.store is not None else 0
+
+    def voxelize_vertices(self, robot, states):
+        self.calls += 1
+        self.store, flags = self.orc.voxelize_vertices_batch(robot.orb, self.ogrid, states)
+        return flags, None
+
+    def voxelize_edges_indexed(self, robot, space, vertex_states, pairs):
+        self.calls += 1
+        self.store, info = self.orc.voxelize_edges_batch(robot.orb, self.ogrid, self.orc.space(),
+                                                         vertex_states[pairs[:, 0]], vertex_states[pairs[:, 1]])
+        return info
+
+    def check(self, env, begin=0, end=None):
+        return self.orc.check_sets_batch(self.store, env.oenv, begin, end).astype(bool)
+
+
+def _prm(R, orc, wl, spec, g, oenv, monkeypatch):
+    ogrid = orc.grid(g["Ng"], g["lim"])
+    monkeypatch.setattr(R, "SetStore", lambda ctx, grid: _Store(orc, ogrid))
+    monkeypatch.setattr(R, "Env", lambda ctx, grid: _Env(oenv))
+
+    class PRM(R.VoxelCachedLazyPRM):
+        def _sweep(self, store, n_total, flags):     # world == 1: the K3 sweep of this rank, no exchange
+            return store.check(self.env)
+
+    return PRM(None, _Robot(orc, spec, wl), None)
+
+
+def test_create_roadmap_options_host_logic(orc, wl, monkeypatch):
+    from irt_b200 import roadmap as R
+    spec = wl.robot_b(0.003, rotation=True)
+    g = wl.workspace_grid(spec)
+    ogrid, osp = orc.grid(g["Ng"], g["lim"]), orc.space()
+    oenv = orc.octree(ogrid)
+    oenv.add_sphere([0.05, 0.02, 0.12], 0.03)
+    prm = _prm(R, orc, wl, spec, g, oenv, monkeypatch)
+    n = 100
+    prm.createRoadmap(n, opt=R.VoxelizeVertices | R.ValidateVertices | R.VoxelizeEdges | R.ValidateEdges)
+    assert prm.states.shape == (n, 8)
+    ostore, oflags = orc.voxelize_vertices_batch(prm.robot.orb, ogrid, prm.states)
+    assert np.all(oflags == 0) and not orc.check_sets_batch(ostore, oenv).any()
+    assert np.all(prm.vertex_validity == R.VALIDITY_TRUE) and np.all(prm.vertex_flags == 0)
+    # the rejection really rejected: the first candidates of round 0, in order, minus the bad ones
+    cand = prm.random_states(int(n * 1.25) + 64, 0)
+    cs, cf = orc.voxelize_vertices_batch(prm.robot.orb, ogrid, cand)
+    good = (cf == 0) & ~orc.check_sets_batch(cs, oenv).astype(bool)
+    assert not good.all()
+    k = min(n, int(good.sum()))
+    assert np.array_equal(prm.states[:k], cand[good][:k])
+    # edges: replay of the connection loop, every candidate judged by the oracle
+    have, pairs = set(), []
+    for v in range(n):
+        d = prm.distance(prm.states[v], prm.states)
+        order = np.lexsort((np.arange(n), d))[:5]
+        assert order[0] == v and np.array_equal(order[d[order] <= prm.maximum_extent() * 0.2], prm.k_bounded_neighbors(v))
+        for m in prm.k_bounded_neighbors(v).tolist():
+            key = (min(v, m), max(v, m))
+            if m != v and key not in have:
+                have.add(key)
+                pairs.append((v, m))
+    pairs = np.array(pairs, dtype=np.int64)
+    oes, oinfo = orc.voxelize_edges_batch(prm.robot.orb, ogrid, osp, prm.states[pairs[:, 0]], prm.states[pairs[:, 1]])
+    ok = ((oinfo["flags"] & 16) == 0) & ~orc.check_sets_batch(oes, oenv).astype(bool)
+    assert 0 < ok.sum() < len(pairs), "fixture must both keep and remove edges"
+    assert np.array_equal(prm.edges, pairs[ok])
+    assert np.all(prm.edge_validity == R.VALIDITY_TRUE) and np.all(prm.edge_flags == 0)
+    assert prm.edge_store.num_sets == len(prm.edges) and prm.vertex_store.num_sets == n
+    # growing
+    states0, edges0 = prm.states.copy(), prm.edges.copy()
+    prm.createRoadmap(n - 10)
+    assert len(prm.states) == n and np.array_equal(prm.edges, edges0)
+    prm.createRoadmap(n + 40, opt=R.LazyRoadmap)
+    assert len(prm.states) == n + 40 and np.array_equal(prm.states[:n], states0)
+    assert np.array_equal(prm.edges[:len(edges0)], edges0) and len(prm.edges) > len(edges0)
+    assert np.all(prm.vertex_validity[:n] == R.VALIDITY_TRUE) and not prm.vertex_validity[n:].any()
+    assert np.all(prm.edge_validity[:len(edges0)] == R.VALIDITY_TRUE) and not prm.edge_validity[len(edges0):].any()
+    assert prm.vertex_store.num_sets == n + 40 and prm.edge_store.num_sets == len(prm.edges)
+    # every new edge has a new vertex as its source and none is a duplicate
+    new = prm.edges[len(edges0):]
+    assert np.all(new[:, 0] >= n) and len(set(map(tuple, np.sort(prm.edges, axis=1).tolist()))) == len(prm.edges)
+
+
+def test_create_roadmap_lazy_and_custom_callbacks(orc, wl, monkeypatch):
+    """LazyRoadmap touches no device object; VoxelizeVertices alone rejects on is_valid_shape only; a caller's
+    sampler / connect (the form bench.py uses) are honoured."""
+    from irt_b200 import roadmap as R
+    spec = wl.robot_a(0.003)
+    spec["E"] = 1.4e6          # soft backbone: a good share of random states violates the length limits
+    g = wl.workspace_grid(spec)
+    oenv = orc.octree(orc.grid(g["Ng"], g["lim"]))
+    prm = _prm(R, orc, wl, spec, g, oenv, monkeypatch)
+    prm.createRoadmap(30, opt=R.LazyRoadmap)
+    assert len(prm.states) == 30 and prm.vertex_store.calls == 0 and prm.edge_store.calls == 0
+    assert not prm.vertex_validity.any() and not prm.edge_validity.any()
+    assert np.array_equal(prm.states, prm.random_states(int(30 * 1.25) + 64, 0)[:30])
+
+    prm2 = _prm(R, orc, wl, spec, g, oenv, monkeypatch)
+    seen = []
+
+    def sampler(count, rnd):
+        seen.append((count, rnd))
+        return wl.sample_states(spec, count, stream=300 + rnd)
+
+    prm2.createRoadmap(60, sampler, lambda st: wl.knn_edges(spec, st, k=3))
+    flags = orc.fk_batch(prm2.robot.orb, prm2.states, 128, want_p=False)["flags"]
+    assert len(prm2.states) == 60 and np.all(flags == 0) and seen[0] == (60 + 15 + 64, 0)
+    cand = wl.sample_states(spec, seen[0][0], stream=300)
+    assert (orc.fk_batch(prm2.robot.orb, cand, 128, want_p=False)["flags"] != 0).any(), "fixture must reject some"
+    assert np.array_equal(prm2.edges, wl.knn_edges(spec, prm2.states, k=3))
+    assert prm2.vertex_store.num_sets == 60 and prm2.edge_store.calls == 0     # vertex cache only
+    assert not prm2.vertex_validity.any()                                       # voxelised, not validated
