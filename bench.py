@@ -111,6 +111,32 @@ def cpu_fk_rate(spec, n_tendons, seconds, threads=None, stream=900):
     return done / el, nt, done, el
 
 
+def cpu_fk_rate_reference_text(spec, threads, seconds):
+    """For information, beside the port: TendonRobot::shape compiled from the reference's OWN text
+    (oracle/_ref/libtendonrobot_ref_release.so: TendonRobot.h as is, tension_shape cut out by anchors, the
+    reference's Release flags) in the OpenMP loop of apps/estimate_length_discretization.cpp:62-71.  It links
+    against this repo's stand-ins for Eigen and Boost.odeint (neither is installed), which allocate where the
+    real libraries do not, so it is several times SLOWER than the reference would be with real Eigen -- and
+    than the port; the line's value therefore stays the port, the stronger baseline."""
+    from oracle import ref as oref
+    import irt_b200.workloads as wl
+    if not oref.RefTendonRobot.release_available():
+        return None
+    r = oref.RefTendonRobot(spec)
+    batch, done, k, t0 = 250 * threads, 0, 0, time.perf_counter()
+    while True:
+        r.shape_batch(wl.sample_states(spec, batch, stream=1500 + k), threads, release=True)
+        done += batch
+        k += 1
+        el = time.perf_counter() - t0
+        if el >= seconds:
+            break
+    return {"value": done / el, "unit": "shapes/s", "cores": threads, "kind": "reference",
+            "sample": "%d configs in %.1f s" % (done, el),
+            "note": "the reference's TendonRobot::shape text over Eigen / Boost.odeint STAND-INS (slower than "
+                    "real Eigen); not the line's value"}
+
+
 def cpu_edge_check_rate(prm, wl, g, env_blocks, gpu_verdicts, seconds, sample=200000):
     """edges/s of the reference's TreeNode::collides over the first `sample` cached edge sets (kind
     "reference"), or of the oracle port when oracle/_ref was not shipped (kind "port")."""
@@ -191,8 +217,10 @@ def knn_edges_gpu(torch, states_np, spec, k, device):
 
 def run_reference(args, rank, world):
     """--impl reference: the reference's own CPU implementation of the path.  The reference cannot
-    be compiled in this image (Eigen3/Boost.odeint/OMPL/FCL/ITK absent), so this arm times the
-    oracle port (line-for-line restatement) with all host threads, on bounded samples."""
+    be compiled as it is in this image (Eigen3/Boost.odeint/OMPL/FCL/ITK absent), so this arm times the
+    oracle port (operation-by-operation restatement, pinned bit-exactly by the reference's own text in
+    oracle/_ref) with all host threads, on bounded samples; the reference's own TendonRobot::shape text over
+    the Eigen / odeint stand-ins is timed beside it (`reference_own_text`), see cpu_fk_rate_reference_text."""
     if rank != 0:
         return
     import irt_b200.workloads as wl
@@ -205,6 +233,7 @@ def run_reference(args, rank, world):
             rates.append((r, done, el))
     value = float(np.mean([r for r, _, _ in rates]))
     done = int(np.mean([d for _, d, _ in rates]))
+    own_text = cpu_fk_rate_reference_text(spec, nt, 4.0)
     line = {
         "impl": "reference", "metric": "fk_shapes_per_s", "value": value, "unit": "shapes/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
@@ -217,6 +246,8 @@ def run_reference(args, rank, world):
                          "sample": "%d configs per step (~%.0f s), OpenMP over configs" % (done, per_step)},
         "e2e": {"value": value, "unit": "shapes/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
+    if own_text:
+        line["reference_own_text"] = own_text
     print(json.dumps(line), flush=True)
 
 

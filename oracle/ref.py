@@ -621,6 +621,30 @@ class RefTendonRobot:
                     L=misc[0], L_i=L_i, u_i=misc[1:4].copy(), u_f=misc[4:7].copy(), v_i=misc[7:10].copy(),
                     v_f=misc[10:13].copy(), converged=bool(misc[13]))
 
+    _release = None
+
+    @classmethod
+    def release_available(cls):
+        return os.path.exists(os.path.join(REF_DIR, "libtendonrobot_ref_release.so"))
+
+    def shape_batch(self, states, nthreads=1, release=True):
+        """TendonRobot::shape over a batch in the OpenMP loop of apps/estimate_length_discretization.cpp:62-71.
+        release=True: the build with the reference's own Release flags (-Ofast ..., CMakeLists.txt:66), the
+        TIMING baseline of bench.py; never a parity checker.  Returns (tips[n][3], npts[n])."""
+        cls = type(self)
+        if release:
+            if cls._release is None:
+                cls._release = C.CDLL(os.path.join(REF_DIR, "libtendonrobot_ref_release.so"))
+            L = cls._release
+        else:
+            L = self.lib()
+        states = np.ascontiguousarray(states, dtype=np.float64)
+        n = states.shape[0]
+        tips, npts = np.zeros((n, 3)), np.zeros(n, dtype=np.int32)
+        L.trref_shape_batch(*self._args(), _dp(states), C.c_longlong(n), C.c_int(int(nthreads)), _dp(tips),
+                            npts.ctypes.data_as(C.POINTER(C.c_int)))
+        return tips, npts
+
     def home_lengths(self, state):
         state = np.ascontiguousarray(state, dtype=np.float64)
         out = np.zeros(self.N)

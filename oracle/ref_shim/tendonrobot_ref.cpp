@@ -107,6 +107,28 @@ int trref_shape(const double *hdr, int N, int Nc, int Nd, const double *C, const
   return n;
 }
 
+// TendonRobot::shape over a batch, the OpenMP loop of apps/estimate_length_discretization.cpp:62-71 (one
+// robot, `#pragma omp parallel for` over configurations, every TendonResult kept until the loop ends like
+// the app keeps them).  Timing baseline of bench.py (--impl reference / cpu_baseline); tips[n][3] and
+// npts[n] are written so the work cannot be optimised away and so the caller can spot-check the results.
+void trref_shape_batch(const double *hdr, int N, int Nc, int Nd, const double *C, const double *D,
+                       const double *lim, const double *states, long long n, int nthreads, double *tips,
+                       int *npts) {
+  const tendon::TendonRobot rb = make_robot(hdr, N, Nc, Nd, C, D, lim);
+  const size_t S = rb.state_size();
+  std::vector<tendon::TendonResult> results((size_t)n);
+#pragma omp parallel for num_threads(nthreads) schedule(static)
+  for (long long i = 0; i < n; i++) {
+    std::vector<double> st(states + i * S, states + (i + 1) * S);
+    results[(size_t)i] = rb.shape(st);
+  }
+  for (long long i = 0; i < n; i++) {
+    const auto &res = results[(size_t)i];
+    npts[i] = (int)res.p.size();
+    for (int k = 0; k < 3; k++) tips[3 * i + k] = res.p.empty() ? 0.0 : res.p.back()[k];
+  }
+}
+
 // home_shape(state).L_i
 void trref_home_lengths(const double *hdr, int N, int Nc, int Nd, const double *C, const double *D,
                         const double *lim, const double *state, double *L_i) {

@@ -492,3 +492,20 @@ def test_golden_tendon_robot_shape(orc, wl, gold, name):
         assert (orc.validity_flags(rb, s, a) & 7) == int(gold[k + "flags"][i])
         sret = s[-1] if spec.get("enable_retraction") else 0.0
         assert np.array_equal(orc.home_lengths(rb, sret), gold[k + "home"][i])
+
+
+@pytest.mark.skipif(not (ref.RefTendonRobot.available() and ref.RefTendonRobot.release_available()),
+                    reason="oracle/_ref/libtendonrobot_ref*.so not built")
+def test_reference_batch_loop_is_a_sound_timing_baseline(orc, wl):
+    """bench.py's `reference_own_text` figure times trref_shape_batch (the reference's TendonRobot::shape in the
+    OpenMP loop of apps/estimate_length_discretization.cpp:62-71).  Its results must be the reference's: node
+    counts equal, tips identical between the -O2 build and the oracle, and within 1e-12 L for the -Ofast build
+    (which may reassociate)."""
+    spec = wl.robot_b(0.005)
+    st = wl.sample_states(spec, 300, stream=77)
+    rr = ref.RefTendonRobot(spec)
+    want = orc.fk_batch(orc.robot(spec), st, 64)
+    tips, npts = rr.shape_batch(st, nthreads=2, release=False)
+    assert np.array_equal(npts, want["npts"]) and np.array_equal(tips, want["tip"])
+    tips_r, npts_r = rr.shape_batch(st, nthreads=2, release=True)
+    assert np.array_equal(npts_r, want["npts"]) and np.abs(tips_r - want["tip"]).max() < 1e-12 * spec["L"]
