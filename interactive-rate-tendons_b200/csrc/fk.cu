@@ -349,8 +349,16 @@ __device__ __forceinline__ void emit_node(const irt_fk_outputs &o, int64_t row_b
   }
 }
 
+// FK_MAXNREG (experiments, tools/time_fk_variants.py): an explicit register cap instead of the minimum-blocks
+// hint, which only ever yields 255 or 168 registers here.  Measured: 200 registers x 10 warps/SM and 224 x 9
+// are 7-16 % slower than 255 x 8 (profiles/README.md) -- the spills cost more than the warps bring.
+#ifdef FK_MAXNREG
+#define FK_KERNEL_BOUNDS __maxnreg__(FK_MAXNREG)
+#else
+#define FK_KERNEL_BOUNDS __launch_bounds__(FK_THREADS, FK_MIN_BLOCKS)
+#endif
 template <int NT, bool RETRACT>
-__global__ void __launch_bounds__(FK_THREADS, FK_MIN_BLOCKS)
+__global__ void FK_KERNEL_BOUNDS
 fk_rk4_fp64_kernel(const RobotDev rb, const double *__restrict__ states, int state_size, int64_t n,
                    int cap_pts, const irt_fk_outputs o, const int32_t *__restrict__ perm,
                    const int64_t *__restrict__ row_off) {
