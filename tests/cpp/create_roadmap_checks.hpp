@@ -1,6 +1,6 @@
 // createRoadmap(N, opt) and TendonRobot::random_state of the C++ host mirror, checked against the CPU oracle.
-// Shared by tests/cpp/test_host_mirror.cpp (GPU box: the real libirt_b200.so) and
-// tests/cpp/test_create_roadmap_host.cpp (no GPU: the host logic over tests/cpp/abi_standin_over_oracle.cpp).
+// Part of tests/cpp/test_host_mirror.cpp, which runs against the real libirt_b200.so on the GPU box and, for the
+// host logic, against tests/cpp/abi_standin_over_oracle.cpp where there is no GPU.
 // Needs CHECK(), the mirror header and oracle/tendon_oracle.h from the including file.
 #pragma once
 

@@ -185,18 +185,21 @@ def test_cpp_host_mirror_compiles_and_links(tmp_path, irt, orc):
         assert out.returncode != 0 and "no CUDA device" in out.stderr
 
 
-def test_cpp_create_roadmap_host_logic(tmp_path, orc):
-    """VoxelCachedLazyPRM::createRoadmap(N, opt) and TendonRobot::random_state of the C++ mirror: the host
-    logic above the boundary (rejection rounds, KBounded connection, removal of invalid edges, validity
-    bookkeeping, growing) against the oracle, with the C-ABI calls answered by a test-only stand-in over the
-    oracle (tests/cpp/abi_standin_over_oracle.cpp).  The same checks run on the real library on the GPU box."""
-    exe = str(tmp_path / "test_create_roadmap_host")
+def test_cpp_host_mirror_host_logic(tmp_path, orc):
+    """The C++ host mirror's logic above the boundary, WITHOUT a GPU: the same test source that runs against
+    libirt_b200.so on the GPU box (tests/cpp/test_host_mirror.cpp) is linked against a test-only stand-in of
+    the C ABI answered by the oracle (tests/cpp/abi_standin_over_oracle.cpp).  Covers the layout conversions
+    (column-major R, Morton keys, CSR <-> block maps), status -> exception translation, home_shape, the
+    validators' PartialVoxelization assembly, the batch entry points of VoxelCachedLazyPRM incl.
+    createRoadmap(N, opt) (rejection rounds, KBounded connection, removal of invalid edges, growing) and the
+    batched Jacobians."""
+    exe = str(tmp_path / "test_host_mirror_cpu")
     cpp = os.path.join(ROOT, "tests", "cpp")
     subprocess.check_call(["g++", "-std=c++17", "-O1", "-Wall", "-Wextra", "-Werror",
-                           os.path.join(cpp, "test_create_roadmap_host.cpp"),
+                           os.path.join(cpp, "test_host_mirror.cpp"),
                            os.path.join(cpp, "abi_standin_over_oracle.cpp"), "-o", exe,
                            "-L" + os.path.join(ROOT, "oracle"), "-loracle",
                            "-Wl,-rpath," + os.path.join(ROOT, "oracle"), "-fopenmp"])
-    out = subprocess.run([exe], capture_output=True, text=True, timeout=600)
+    out = subprocess.run([exe], capture_output=True, text=True, timeout=900)
     assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-2000:]
-    assert "createRoadmap host logic ok" in out.stdout
+    assert "host mirror ok" in out.stdout and "createRoadmap: 120 vertices" in out.stdout
