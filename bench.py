@@ -383,7 +383,7 @@ def main():
                 "traffic": prof.get("fk_dram_bytes_per_launch"),
                 "peak_source": "live DFMA-chain probe on this GPU (MEASURED_PEAKS.json has no FP64 entry)",
                 "flop_per_shape": fshape, "mean_rk4_steps": mean_steps, "mean_fixed_point_iters": mean_iters,
-                "note": "duration = whole step (3 bucket-sort launches + the RK4 kernel)"}
+                "note": "duration = whole step (2 bucket-sort launches + the RK4 kernel)"}
 
     # ---------------- e2e: host-pointer C ABI, pinned buffers, H2D + D2H inside ----------------
     h_states = torch.from_numpy(states).pin_memory()

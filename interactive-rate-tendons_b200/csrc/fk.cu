@@ -676,25 +676,49 @@ __global__ void fk_row_count_kernel(const RobotDev rb, const double *__restrict_
   counts[i] = npts;
 }
 
-__global__ void fk_bucket_scan_kernel(int32_t *hist, int nb) {
-  // exclusive scan in DESCENDING key order; hist[k] becomes the first slot of bucket k
-  if (threadIdx.x == 0 && blockIdx.x == 0) {
-    int32_t acc = 0;
-    for (int k = nb - 1; k >= 0; k--) {
-      int32_t c = hist[k];
-      hist[k] = acc;
-      acc += c;
+// Scatter into buckets in DESCENDING key order.  hist[k] = number of configurations with key k (final: the
+// count kernel ran before on the same stream); cursor[k] = slots of bucket k handed out so far (zeroed).
+// Every block ranks its configurations per bucket in shared memory and reserves ONE contiguous run per
+// (block, bucket) with a single global atomic, so the ~n same-address atomics of a naive scatter become
+// ~n/256 * (occupied buckets); the bucket starts (an exclusive scan of <= a few hundred counts) are recomputed
+// per block by warp 0 instead of by a kernel of their own.  Which slot inside its bucket a configuration gets
+// is arbitrary; results are written at the original index, so they do not depend on it.
+__global__ void fk_bucket_scatter_kernel(const int32_t *__restrict__ keys, int64_t n,
+                                         const int32_t *__restrict__ hist, int32_t *__restrict__ cursor,
+                                         int nb, int32_t *__restrict__ perm) {
+  extern __shared__ int32_t sh[];
+  int32_t *cnt = sh, *base = sh + nb;   // per-bucket: configurations of this block, then first slot of its run
+  for (int k = threadIdx.x; k < nb; k += blockDim.x) cnt[k] = 0;
+  __syncthreads();
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  int key = 0, local = 0;
+  if (i < n) {
+    key = keys[i];
+    local = atomicAdd(&cnt[key], 1);
+  }
+  if (threadIdx.x < 32) {   // bucket starts: exclusive scan of hist from the highest key down
+    const int lane = threadIdx.x;
+    int32_t carry = 0;
+    for (int top = nb - 1; top >= 0; top -= 32) {
+      const int k = top - lane;
+      const int32_t c = (k >= 0) ? hist[k] : 0;
+      int32_t incl = c;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        const int32_t t = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= d) incl += t;
+      }
+      if (k >= 0) base[k] = carry + incl - c;
+      carry += __shfl_sync(0xffffffffu, incl, 31);
     }
   }
-}
-
-__global__ void fk_bucket_scatter_kernel(const int32_t *__restrict__ keys, int64_t n,
-                                         int32_t *__restrict__ cursor, int32_t *__restrict__ perm) {
-  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) {
-    int32_t pos = atomicAdd(&cursor[keys[i]], 1);
-    perm[pos] = (int32_t)i;
+  __syncthreads();
+  for (int k = threadIdx.x; k < nb; k += blockDim.x) {
+    const int32_t c = cnt[k];
+    if (c) base[k] += atomicAdd(&cursor[k], c);
   }
+  __syncthreads();
+  if (i < n) perm[base[key] + local] = (int32_t)i;
 }
 
 template <int NT>
@@ -746,20 +770,19 @@ int fk_launch(irt_ctx *ctx, const irt_robot *rb, const double *d_states, int64_t
     return irt_fail(ctx, IRT_ERR_CAPACITY, "routing table (%zu B) exceeds shared memory", smem);
   if (d.enable_retraction && !d_perm) {
     const int nb = d.Kfull + 2;
-    size_t bytes = (size_t)n * 4 * 2 + (size_t)nb * 4 + 256;
+    size_t bytes = (size_t)n * 4 * 2 + (size_t)nb * 4 * 2 + 256;
     char *scr = (char *)ctx_scratch(ctx, bytes);
     if (!scr) return irt_fail(ctx, IRT_ERR_CUDA, "scratch alloc of %zu bytes failed", bytes);
     int32_t *keys = (int32_t *)scr;
     int32_t *perm = keys + n;
-    int32_t *hist = perm + n;
-    IRT_CUDA(ctx, cudaMemsetAsync(hist, 0, (size_t)nb * 4, st));
+    int32_t *hist = perm + n;      // [nb] counts, then [nb] cursors
+    int32_t *cursor = hist + nb;
+    IRT_CUDA(ctx, cudaMemsetAsync(hist, 0, (size_t)nb * 4 * 2, st));
     const int T = 256;
     const unsigned B = (unsigned)((n + T - 1) / T);
     fk_count_nodes_kernel<<<B, T, nb * sizeof(int32_t), st>>>(d, d_states, rb->state_size, n, keys, hist);
     IRT_LAUNCHED(ctx);
-    fk_bucket_scan_kernel<<<1, 32, 0, st>>>(hist, nb);
-    IRT_LAUNCHED(ctx);
-    fk_bucket_scatter_kernel<<<B, T, 0, st>>>(keys, n, hist, perm);
+    fk_bucket_scatter_kernel<<<B, T, 2 * nb * sizeof(int32_t), st>>>(keys, n, hist, cursor, nb, perm);
     IRT_LAUNCHED(ctx);
     IRT_CUDA(ctx, cudaGetLastError());
     d_perm = perm;

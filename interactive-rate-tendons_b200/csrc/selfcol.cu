@@ -260,7 +260,7 @@ int self_collision_launch(irt_ctx *ctx, const irt_robot *rb, const double *d_p,
   IRT_CUDA(ctx, cudaFuncSetAttribute(self_collision_kernel,
                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   // candidate list lives behind the bucket permutation area of the context scratch
-  const size_t perm_bytes = (size_t)n * 8 + 4096 + 256;
+  const size_t perm_bytes = (size_t)n * 8 + 8192 + 256;  // fk_launch: keys + perm + 2 x (Kfull + 2) counters
   char *scr = (char *)ctx_scratch(ctx, perm_bytes + (size_t)n * 4 + 256);
   if (!scr) return irt_fail(ctx, IRT_ERR_CUDA, "scratch alloc failed");
   int32_t *d_ncand = (int32_t *)(scr + perm_bytes);
