@@ -81,7 +81,7 @@ class ClockSampler(threading.Thread):
                 "reasons": sorted(self.reasons)}
 
 
-def cpu_fk_rate(spec, n_tendons, seconds, threads=None, stream=900):
+def cpu_fk_rate(spec, n_tendons, seconds, threads=None, stream=900, batch=20000):
     """oracle (restatement of the reference CPU path, -O3 -march=native -fopenmp) timed on a
     bounded sample of the SAME workload; loop shape = apps/estimate_length_discretization.cpp:62-71"""
     from oracle.oracle import Oracle, build
@@ -96,7 +96,6 @@ def cpu_fk_rate(spec, n_tendons, seconds, threads=None, stream=900):
     except Exception:
         avail = os.cpu_count() or 1
     nt = threads or max(avail, orc.max_threads())
-    batch = 20000
     done, t0 = 0, time.perf_counter()
     cap = len(orc.t_range(0.0, spec["L"], spec["dL"]))
     k = 0
@@ -174,6 +173,11 @@ def cpu_edge_check_rate(prm, wl, g, env_blocks, gpu_verdicts, seconds, sample=20
         kind, what = "port", "oracle restatement of TreeNode::collides, OpenMP loop"
     v = run()                                                   # warm-up + parity with the GPU verdicts
     equal = bool(np.array_equal(v, np.asarray(gpu_verdicts[:m]).astype(bool)))
+    k2 = None
+    try:    # K2 parity on a sample: the first edges' swept volumes against the oracle's LIFO restatement
+        k2 = k2_flips_vs_oracle(prm, wl, g, off, keys, bits, min(1000, m), nt)
+    except Exception as e:   # reporting only: never lose the bench line over it
+        k2 = {"error": repr(e)[:200]}
     reps, t0 = 0, time.perf_counter()
     while True:
         run()
@@ -183,7 +187,31 @@ def cpu_edge_check_rate(prm, wl, g, env_blocks, gpu_verdicts, seconds, sample=20
             break
     return {"value": m * reps / el, "unit": "edges/s", "cores": nt, "kind": kind,
             "sample": "first %d cached edge sets of this roadmap, %d sweeps in %.1f s; %s" % (m, reps, el, what),
-            "verdicts_equal_gpu": equal}
+            "verdicts_equal_gpu": equal, "k2_vs_oracle": k2}
+
+
+def k2_flips_vs_oracle(prm, wl, g, off, keys, bits, m, nt):
+    """SURVEY 8(d) 'flips vs oracle' for K2: the cached swept volumes of the first m edges of the roadmap
+    (device CSR, already on the host) against the oracle's voxelize_edge on the same endpoint states;
+    differing voxels, differing flag words and differing verdict-relevant sets are COUNTED."""
+    from oracle.oracle import Oracle
+    orc = Oracle("canonical")
+    e = prm.edges[:m]
+    ostore, oinfo = orc.voxelize_edges_batch(orc.robot(prm.robot.spec), orc.grid(g["Ng"], g["lim"], g["inv_rot"]),
+                                             orc.space(), prm.states[e[:, 0]], prm.states[e[:, 1]], nthreads=nt)
+    wo, wk, wb = ostore.export()
+    go, gk, gb = off[:m + 1], keys[:int(off[m])], bits[:int(off[m])]
+    flips = sets = 0
+    if not (np.array_equal(go, wo) and np.array_equal(gk, wk) and np.array_equal(gb, wb)):
+        for i in range(m):
+            a = dict(zip(gk[int(go[i]):int(go[i + 1])].tolist(), gb[int(go[i]):int(go[i + 1])].tolist()))
+            b = dict(zip(wk[int(wo[i]):int(wo[i + 1])].tolist(), wb[int(wo[i]):int(wo[i + 1])].tolist()))
+            f = sum(bin(a.get(k, 0) ^ b.get(k, 0)).count("1") for k in set(a) | set(b))
+            flips += f
+            sets += f > 0
+    return {"edges": int(m), "voxel_flips": int(flips), "sets_with_flips": int(sets),
+            "flag_mismatches": int(np.count_nonzero(np.asarray(prm.edge_flags[:m]) != oinfo["flags"])),
+            "oracle_voxels": int(sum(bin(int(x)).count("1") for x in wb.tolist()))}
 
 
 def knn_edges_gpu(torch, states_np, spec, k, device):
@@ -592,6 +620,16 @@ def main():
         edge_check["valid_edge_fraction"] = float(verd.mean())
         lo_w = irt_b200.unpack_verdicts(d_words.cpu().numpy().view(np.uint32), hi - lo) if hi > lo else np.zeros(0)
         edge_check["collision_fraction"] = float(lo_w.mean()) if hi > lo else None
+        try:    # K2 unit-of-work figures of SURVEY 8(d); reporting only
+            if hi > lo:
+                edge_check["fk_samples_per_edge_p99"] = float(np.percentile(einfo["nsamples"], 99))
+                full = irt_b200.Env(ctx, grid)      # every voxel set: popcount(set & env) = voxels of the set
+                full.update(np.full(env_blocks.size, 0xFFFFFFFFFFFFFFFF, dtype=np.uint64))
+                vox, _ = prm.edge_store.popcount(full)
+                edge_check["voxels_per_edge"] = vox / (hi - lo)
+                del full
+        except Exception as e:
+            edge_check["k2_figures_error"] = repr(e)[:200]
 
         # ---- CPU baseline of the edge check (rank 0 at N=1 only): the reference's own octree code
         # (oracle/_ref/libtreenode_ref.so = collision/detail/TreeNode.h compiled as is) running the OpenMP
@@ -606,6 +644,11 @@ def main():
         rate, nt, done, el = cpu_fk_rate(spec, rb.n_tendons, args.cpu_seconds)
         cpu = {"value": rate, "unit": "shapes/s", "cores": nt, "kind": "port",
                "sample": "%d configs of the same workload in %.1f s (oracle -O3 -march=native -fopenmp)" % (done, el)}
+        try:
+            r1, _, d1, e1 = cpu_fk_rate(spec, rb.n_tendons, min(2.0, args.cpu_seconds), threads=1, batch=2000)
+            cpu["single_thread"] = {"value": r1, "sample": "%d configs in %.1f s" % (d1, e1)}
+        except Exception as e:
+            cpu["single_thread"] = {"error": repr(e)[:200]}
 
     if rank == 0:
         line = {
