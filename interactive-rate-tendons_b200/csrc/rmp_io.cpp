@@ -12,15 +12,21 @@
 
 namespace {
 
+// Counts in the file are untrusted: every read is checked against the bytes that are left, so a truncated
+// or corrupt file ends in IRT_ERR_INVALID_ARGUMENT, never in an out-of-memory allocation or a crash.
 struct Reader {
   std::FILE *f;
+  uint64_t left = 0;  // bytes of the file not consumed yet
   bool ok = true;
   template <typename T>
   bool get(T *dst, size_t count = 1) {
     if (!ok) return false;
-    if (count && std::fread(dst, sizeof(T), count, f) != count) ok = false;
-    return ok;
+    if (!fits(count, sizeof(T))) return ok = false;
+    if (count && std::fread(dst, sizeof(T), count, f) != count) return ok = false;
+    left -= (uint64_t)count * sizeof(T);
+    return true;
   }
+  bool fits(uint64_t count, uint64_t size) const { return count <= left / (size ? size : 1); }
 };
 
 template <typename T>
@@ -33,13 +39,14 @@ T *dup(const std::vector<T> &v) {
 bool read_blocks(Reader &in, int Nb, std::vector<uint32_t> &keys, std::vector<uint64_t> &bits) {
   uint32_t nblocks = 0;
   if (!in.get(&nblocks)) return false;
+  if (!in.fits(nblocks, 11)) return in.ok = false;
   std::vector<unsigned char> buf((size_t)nblocks * 11);
   if (!in.get(buf.data(), buf.size())) return false;
   for (uint32_t i = 0; i < nblocks; i++) {
     const unsigned char *r = &buf[(size_t)i * 11];
     uint64_t v;
     std::memcpy(&v, r + 3, 8);
-    if (r[0] >= Nb || r[1] >= Nb || r[2] >= Nb) return false;
+    if (r[0] >= Nb || r[1] >= Nb || r[2] >= Nb) return in.ok = false;
     keys.push_back(irt_morton_key(r[0], r[1], r[2], Nb));
     bits.push_back(v);
   }
@@ -73,13 +80,18 @@ void irt_rmp_free(irt_rmp *r) {
   std::free(r);
 }
 
-int irt_rmp_read(const char *path, irt_rmp **out) {
-  if (!path || !out) return IRT_ERR_INVALID_ARGUMENT;
-  *out = nullptr;
-  std::FILE *f = std::fopen(path, "rb");
-  if (!f) return IRT_ERR_INVALID_ARGUMENT;
+static int rmp_read_impl(std::FILE *f, irt_rmp **out) {
   Reader in{f};
+  if (std::fseek(f, 0, SEEK_END) != 0) return IRT_ERR_INVALID_ARGUMENT;
+  const long size = std::ftell(f);
+  if (size < 0 || std::fseek(f, 0, SEEK_SET) != 0) return IRT_ERR_INVALID_ARGUMENT;
+  in.left = (uint64_t)size;
   irt_rmp *r = (irt_rmp *)std::calloc(1, sizeof(irt_rmp));
+  if (!r) return IRT_ERR_CAPACITY;
+  struct Guard {  // frees the partial result if a container throws on the way
+    irt_rmp *r;
+    ~Guard() { if (r) irt_rmp_free(r); }
+  } guard{r};
   uint8_t has_vox = 0;
   in.get(&r->n_verts); in.get(&r->n_edges); in.get(&has_vox);
   r->has_voxels = has_vox ? 1 : 0;
@@ -87,6 +99,8 @@ int irt_rmp_read(const char *path, irt_rmp **out) {
     uint8_t nb = 0;
     in.get(&nb); in.get(r->lims, 6);
     r->Nb = nb;
+    // VoxelOctree(Ng): Ng = 4 Nb must be a power of two in [4, 512] (collision/VoxelOctree.cpp:83-116)
+    if (nb < 1 || nb > 128 || (nb & (nb - 1)) != 0) in.ok = false;
   }
   std::vector<uint32_t> vidx, vkeys, esrc, edst, ekeys;
   std::vector<double> vstate, vtip, ew;
@@ -99,7 +113,7 @@ int irt_rmp_read(const char *path, irt_rmp **out) {
     ok = in.get(&idx) && in.get(&cnt);
     if (!ok) break;
     if (r->state_size < 0) r->state_size = (int32_t)cnt;
-    if ((int32_t)cnt != r->state_size) { ok = false; break; }
+    if ((int32_t)cnt != r->state_size || !in.fits(cnt, sizeof(double))) { ok = false; break; }
     std::vector<double> st(cnt);
     uint8_t has_tip = 0;
     double tip[3] = {0, 0, 0};
@@ -129,23 +143,54 @@ int irt_rmp_read(const char *path, irt_rmp **out) {
     esrc.push_back(s); edst.push_back(t); ew.push_back(w); ehasvox.push_back(hv);
     eoff.push_back(ekeys.size());
   }
-  std::fclose(f);
   if (r->state_size < 0) r->state_size = 0;
   r->v_index = dup(vidx); r->v_state = dup(vstate); r->v_has_tip = dup(vhastip); r->v_tip = dup(vtip);
   r->v_has_vox = dup(vhasvox); r->v_off = dup(voff); r->v_keys = dup(vkeys); r->v_bits = dup(vbits);
   r->e_src = dup(esrc); r->e_dst = dup(edst); r->e_weight = dup(ew); r->e_has_vox = dup(ehasvox);
   r->e_off = dup(eoff); r->e_keys = dup(ekeys); r->e_bits = dup(ebits);
-  if (!ok) {
-    irt_rmp_free(r);
-    return IRT_ERR_INVALID_ARGUMENT;  // truncated or malformed file
-  }
+  if (!ok || !in.ok) return IRT_ERR_INVALID_ARGUMENT;  // truncated or malformed file (guard frees r)
+  if (!r->v_index || !r->v_state || !r->v_has_tip || !r->v_tip || !r->v_has_vox || !r->v_off || !r->v_keys ||
+      !r->v_bits || !r->e_src || !r->e_dst || !r->e_weight || !r->e_has_vox || !r->e_off || !r->e_keys ||
+      !r->e_bits)
+    return IRT_ERR_CAPACITY;
+  guard.r = nullptr;
   *out = r;
   return IRT_OK;
+}
+
+int irt_rmp_read(const char *path, irt_rmp **out) {
+  if (!path || !out) return IRT_ERR_INVALID_ARGUMENT;
+  *out = nullptr;
+  std::FILE *f = std::fopen(path, "rb");
+  if (!f) return IRT_ERR_INVALID_ARGUMENT;
+  int rc;
+  try {
+    rc = rmp_read_impl(f, out);
+  } catch (...) {  // std::bad_alloc of a container: the C ABI never throws
+    rc = IRT_ERR_CAPACITY;
+  }
+  std::fclose(f);
+  return rc;
 }
 
 int irt_rmp_write(const char *path, const irt_rmp *r) {
   if (!path || !r) return IRT_ERR_INVALID_ARGUMENT;
   if (r->has_voxels && (r->Nb < 1 || r->Nb > 128)) return IRT_ERR_INVALID_ARGUMENT;  // u8 Nb, Ng <= 512
+  if (r->state_size < 0) return IRT_ERR_INVALID_ARGUMENT;
+  if (r->n_verts && (!r->v_index || (r->state_size && !r->v_state))) return IRT_ERR_INVALID_ARGUMENT;
+  if (r->n_edges && (!r->e_src || !r->e_dst || !r->e_weight)) return IRT_ERR_INVALID_ARGUMENT;
+  for (uint32_t i = 0; i < r->n_verts; i++) {
+    if (r->v_has_tip && r->v_has_tip[i] && !r->v_tip) return IRT_ERR_INVALID_ARGUMENT;
+    if (r->has_voxels && r->v_has_vox && r->v_has_vox[i] &&
+        (!r->v_off || !r->v_keys || !r->v_bits || r->v_off[i + 1] < r->v_off[i] ||
+         r->v_off[i + 1] - r->v_off[i] > 0xffffffffull))
+      return IRT_ERR_INVALID_ARGUMENT;
+  }
+  for (uint32_t i = 0; i < r->n_edges; i++)
+    if (r->has_voxels && r->e_has_vox && r->e_has_vox[i] &&
+        (!r->e_off || !r->e_keys || !r->e_bits || r->e_off[i + 1] < r->e_off[i] ||
+         r->e_off[i + 1] - r->e_off[i] > 0xffffffffull))
+      return IRT_ERR_INVALID_ARGUMENT;
   std::FILE *f = std::fopen(path, "wb");
   if (!f) return IRT_ERR_INVALID_ARGUMENT;
   bool ok = std::fwrite(&r->n_verts, 4, 1, f) == 1 && std::fwrite(&r->n_edges, 4, 1, f) == 1;

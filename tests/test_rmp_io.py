@@ -184,3 +184,67 @@ def test_rmp_against_reference_reader_and_writer(tmp_path, orc, wl):
         assert np.array_equal(r["v_state"], d["v_state"]) and np.array_equal(r["e_weight"], d["e_weight"])
         if has_voxels:
             assert np.array_equal(r["v_keys"], d["v_keys"]) and np.array_equal(r["e_bits"], d["e_bits"])
+
+
+def test_rmp_reader_rejects_truncated_and_corrupt_files(tmp_path, orc, wl):
+    """Counts inside a .rmp file are untrusted input: a file cut anywhere, or with a count far beyond the bytes
+    that follow, must come back as an error status -- no crash, no attempt to allocate what the count claims."""
+    import irt_b200
+    spec, g, d = _roadmap(orc, wl, n=6)
+    good = tmp_path / "good.rmp"
+    irt_b200.write_rmp(str(good), d)
+    blob = good.read_bytes()
+    assert irt_b200.read_rmp(str(good))["n_verts"] == 6
+    bad = tmp_path / "bad.rmp"
+    # every proper prefix (every byte in the header and the first records, then a stride through the rest)
+    cuts = list(range(0, 400)) + list(range(400, len(blob), 37)) + [len(blob) - 1]
+    for cut in cuts:
+        bad.write_bytes(blob[:cut])
+        with pytest.raises(irt_b200.IrtError):
+            irt_b200.read_rmp(str(bad))
+    # trailing garbage is not read (the reader stops after n_verts + n_edges records, like LazyRmpParser)
+    bad.write_bytes(blob + b"\x00" * 7)
+    assert irt_b200.read_rmp(str(bad))["n_edges"] == d["n_edges"]
+
+    def patched(offset, fmt, value):
+        b = bytearray(blob)
+        struct.pack_into(fmt, b, offset, value)
+        bad.write_bytes(bytes(b))
+        with pytest.raises(irt_b200.IrtError) as e:
+            irt_b200.read_rmp(str(bad))
+        return e.value.status
+
+    hdr = 4 + 4 + 1 + 1 + 48            # nV, nE, has_voxels, Nb, 6 limits
+    assert patched(0, "<I", 0xFFFFFFFF) == irt_b200.IRT_ERR_INVALID_ARGUMENT      # 4e9 vertices, 6 in the file
+    assert patched(4, "<I", 0xFFFFFFF0) == irt_b200.IRT_ERR_INVALID_ARGUMENT      # 4e9 edges
+    assert patched(9, "<B", 0) == irt_b200.IRT_ERR_INVALID_ARGUMENT               # Nb = 0
+    assert patched(9, "<B", 48) == irt_b200.IRT_ERR_INVALID_ARGUMENT              # Ng = 192: not a power of two
+    assert patched(hdr + 4, "<I", 0x7FFFFFFF) == irt_b200.IRT_ERR_INVALID_ARGUMENT  # state size of vertex 0: 2^31 doubles
+    # the first vertex with voxels: patch its block count to 4e9 and a block coordinate beyond Nb
+    S = d["v_state"].shape[1]
+    off = hdr
+    i = 0
+    while not d["v_has_vox"][i]:
+        off += 8 + 8 * S + 1 + (24 if d["v_has_tip"][i] else 0) + 1
+        i += 1
+    off += 8 + 8 * S + 1 + (24 if d["v_has_tip"][i] else 0) + 1
+    assert patched(off, "<I", 0xFFFFFFFF) == irt_b200.IRT_ERR_INVALID_ARGUMENT
+    assert patched(off + 4, "<B", 200) == irt_b200.IRT_ERR_INVALID_ARGUMENT       # bx = 200 >= Nb = 32
+
+
+def test_rmp_writer_rejects_inconsistent_descriptors(tmp_path, orc, wl):
+    import ctypes as C
+    import irt_b200
+    spec, g, d = _roadmap(orc, wl, n=4)
+    out = str(tmp_path / "x.rmp")
+    with pytest.raises(irt_b200.IrtError):
+        irt_b200.write_rmp(out, dict(d, Ng=4 * 200))                              # Nb does not fit the u8 of the format
+    L = irt_b200.lib()
+    r = irt_b200.Rmp()
+    r.n_verts, r.state_size = 3, -1
+    assert L.irt_rmp_write(out.encode(), C.byref(r)) == irt_b200.IRT_ERR_INVALID_ARGUMENT
+    r.state_size = 7                                                               # vertices declared, no arrays
+    assert L.irt_rmp_write(out.encode(), C.byref(r)) == irt_b200.IRT_ERR_INVALID_ARGUMENT
+    assert L.irt_rmp_read(out.encode(), None) == irt_b200.IRT_ERR_INVALID_ARGUMENT
+    p = C.POINTER(irt_b200.Rmp)()
+    assert L.irt_rmp_read(str(tmp_path / "missing.rmp").encode(), C.byref(p)) == irt_b200.IRT_ERR_INVALID_ARGUMENT
