@@ -81,13 +81,13 @@ class ClockSampler(threading.Thread):
                 "reasons": sorted(self.reasons)}
 
 
-def cpu_fk_rate(spec, n_tendons, seconds, threads=None, stream=900, batch=20000):
+def cpu_fk_rate(spec, n_tendons, seconds, threads=None, stream=900, batch=20000, variant="fast"):
     """oracle (restatement of the reference CPU path, -O3 -march=native -fopenmp) timed on a
     bounded sample of the SAME workload; loop shape = apps/estimate_length_discretization.cpp:62-71"""
     from oracle.oracle import Oracle, build
     import irt_b200.workloads as wl
     build()
-    orc = Oracle("fast")
+    orc = Oracle(variant)
     rb = orc.robot(spec)
     # all host threads this process may use (torchrun exports OMP_NUM_THREADS=1; the explicit
     # num_threads clause of the oracle's OpenMP loops overrides it)
@@ -649,6 +649,12 @@ def main():
             cpu["single_thread"] = {"value": r1, "sample": "%d configs in %.1f s" % (d1, e1)}
         except Exception as e:
             cpu["single_thread"] = {"error": repr(e)[:200]}
+        try:    # the port under the reference's own Release flags (CMakeLists.txt:66), all threads
+            r2, _, d2, e2 = cpu_fk_rate(spec, rb.n_tendons, min(3.0, args.cpu_seconds), variant="refflags")
+            cpu["reference_release_flags"] = {"value": r2, "flags": "-Ofast -DNDEBUG -mfpmath=sse -mtune=native",
+                                              "sample": "%d configs in %.1f s" % (d2, e2)}
+        except Exception as e:
+            cpu["reference_release_flags"] = {"error": repr(e)[:200]}
 
     if rank == 0:
         line = {

@@ -65,12 +65,12 @@ class OrcEdgeOut(C.Structure):
 def build(force=False):
     """Compile oracle/liboracle.so and liboracle_fast.so (gcc only, no GPU needed)."""
     need = force or not all(os.path.exists(os.path.join(_HERE, n))
-                            for n in ("liboracle.so", "liboracle_fast.so"))
+                            for n in ("liboracle.so", "liboracle_fast.so", "liboracle_refflags.so"))
     src_m = max(os.path.getmtime(os.path.join(_HERE, n))
                 for n in ("tendon_oracle.cpp", "tendon_oracle.h"))
     if not need:
         need = any(os.path.getmtime(os.path.join(_HERE, n)) < src_m
-                   for n in ("liboracle.so", "liboracle_fast.so"))
+                   for n in ("liboracle.so", "liboracle_fast.so", "liboracle_refflags.so"))
     if need:
         subprocess.check_call(["make", "-C", _HERE, "-s"], env=dict(os.environ, CXX="g++"))
 
@@ -87,7 +87,8 @@ class Oracle:
     """One loaded oracle library ("canonical" or "fast")."""
 
     def __init__(self, variant="canonical"):
-        name = {"canonical": "liboracle.so", "fast": "liboracle_fast.so"}[variant]
+        name = {"canonical": "liboracle.so", "fast": "liboracle_fast.so",
+                "refflags": "liboracle_refflags.so"}[variant]
         path = os.path.join(_HERE, name)
         if not os.path.exists(path):
             build()
