@@ -407,6 +407,10 @@ class Octree:
         pts = np.ascontiguousarray(pts, dtype=np.float64)
         self.orc.lib.orc_octree_add_piecewise_line(self.h, _dp(pts), len(pts))
 
+    def add_point(self, p):
+        p = np.ascontiguousarray(p, dtype=np.float64)
+        self.orc.lib.orc_octree_add_point(self.h, _dp(p))
+
     def add_sphere(self, c, r):
         c = np.ascontiguousarray(c, dtype=np.float64)
         self.orc.lib.orc_octree_add_sphere(self.h, _dp(c), r)

@@ -379,6 +379,10 @@ class RefVoxelOctree:
             L.voref_add_line.argtypes = [vp, dp, dp]
             L.voref_add_piecewise_line.argtypes = [vp, dp, C.c_int]
             L.voref_add_voxels.argtypes = [vp, vp]
+            if hasattr(L, "voref_add_sphere"):
+                L.voref_add_point.argtypes = [vp, dp]
+                L.voref_add_sphere.argtypes = [vp, dp, C.c_double]
+                L.voref_add_capsule.argtypes = [vp, dp, dp, C.c_double]
             L.voref_find_cell.restype = C.c_int
             L.voref_find_cell.argtypes = [vp, dp, C.POINTER(C.c_int64)]
             L.voref_nearest_cell.argtypes = [vp, dp, C.POINTER(C.c_int64)]
@@ -439,6 +443,25 @@ class RefVoxelOctree:
 
     def add_voxels(self, other):
         self.lib().voref_add_voxels(self.h, other.h)
+
+    @classmethod
+    def has_primitives(cls):
+        return cls.available() and hasattr(cls.lib(), "voref_add_sphere")
+
+    def add_point(self, p):
+        """VoxelOctree::add(Point) -> add_point (VoxelOctree.cpp:319-323)"""
+        p = np.ascontiguousarray(p, dtype=np.float64)
+        self.lib().voref_add_point(self.h, _dp(p))
+
+    def add_sphere(self, c, r):
+        """VoxelOctree::add_sphere (VoxelOctree.cpp:434-469)"""
+        c = np.ascontiguousarray(c, dtype=np.float64)
+        self.lib().voref_add_sphere(self.h, _dp(c), float(r))
+
+    def add_capsule(self, a, b, r):
+        """VoxelOctree::add_capsule (VoxelOctree.cpp:471-515)"""
+        a, b = (np.ascontiguousarray(v, dtype=np.float64) for v in (a, b))
+        self.lib().voref_add_capsule(self.h, _dp(a), _dp(b), float(r))
 
     def find_cell(self, p):
         p = np.ascontiguousarray(p, dtype=np.float64)

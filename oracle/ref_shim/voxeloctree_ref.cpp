@@ -9,6 +9,8 @@
 //   vo_A.inc      VoxelOctree.cpp from `#define my_assert` up to (not including) add_sphere:
 //                 constructor, limits, block / cell accessors, nearest_cell / find_cell, add_point,
 //                 **add_line**, add_piecewise_line                                (cpp:36-432)
+//   vo_P.inc      add_sphere, add_capsule (cpp:434-515) with struct Sphere / Capsule and the inline collides()
+//                 overloads of collision.hxx:55-108 (this library only; the sweptvol / rmp extractions drop them)
 //   vo_B.inc      add_voxels ... visit_modify_voxels: remove_interior_6/27neighbor, dilate_6/27neighbor,
 //                 dilate_sphere, collides, remove/intersect, the visitors         (cpp:517-1074)
 //   vo_C.inc      bitmask, is_in_domain, domain_check                            (cpp:1499-1521)
@@ -41,10 +43,20 @@
 #include <vector>
 
 namespace collision {
+#ifdef VOREF_WITH_PRIMITIVES
+// struct Sphere / Capsule (truncated at their first cpptoml / fcl member) and the inline collides() overloads
+// for Point / Sphere / Capsule (collision.hxx:55-108), as in selfcol_ref.cpp
+#include "sc_sphere.inc"
+#include "sc_capsule.inc"
+#include "sc_collides.inc"
+#endif
 #include "vo_class.inc"
 }  // namespace collision
 
 #include "vo_A.inc"  // opens namespace collision { and leaves it open, like the file it comes from
+#ifdef VOREF_WITH_PRIMITIVES
+#include "vo_P.inc"  // add_sphere, add_capsule (cpp:434-515): Environment::voxelize's primitives
+#endif
 #include "vo_B.inc"
 #include "vo_C.inc"
 }  // namespace collision (opened inside vo_A.inc)
@@ -120,6 +132,15 @@ void voref_dilate_sphere(void *h, double r) { static_cast<VoxelOctree *>(h)->dil
 void voref_remove_interior(void *h, int keep_diagonal) {
   static_cast<VoxelOctree *>(h)->remove_interior(keep_diagonal != 0);
 }
+#ifdef VOREF_WITH_PRIMITIVES
+void voref_add_point(void *h, const double *p) { static_cast<VoxelOctree *>(h)->add(Point(p)); }
+void voref_add_sphere(void *h, const double *c, double r) {
+  static_cast<VoxelOctree *>(h)->add(collision::Sphere{Point(c), r});
+}
+void voref_add_capsule(void *h, const double *a, const double *b, double r) {
+  static_cast<VoxelOctree *>(h)->add(collision::Capsule{Point(a), Point(b), r});
+}
+#endif
 uint64_t voref_bitmask(int x, int y, int z) { return VoxelOctree::bitmask(x, y, z); }
 // visit_leaves order; writes min(n, cap) records {bx,by,bz,bits} and returns n
 uint64_t voref_leaves(const void *h, uint64_t *out, uint64_t cap) {

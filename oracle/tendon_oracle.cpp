@@ -1095,6 +1095,8 @@ static void add_region(orc_octree *t, const V3 &ll, const V3 &tr, const Pred &in
       }
 }
 extern "C" {
+// VoxelOctree::add(Point) -> add_point (VoxelOctree.cpp:319-323): the cell of a point inside the (inclusive) limits
+void orc_octree_add_point(orc_octree *t, const double *p) { add_point(t, mk(p[0], p[1], p[2])); }
 void orc_octree_add_sphere(orc_octree *t, const double *c, double r) {
   V3 ctr = mk(c[0], c[1], c[2]);
   add_point(t, ctr);

@@ -154,6 +154,7 @@ int orc_octree_collides(const orc_octree *a, const orc_octree *b);
 int64_t orc_octree_export(const orc_octree *t, int64_t cap, uint8_t *bxyz, uint64_t *bits);
 /* find_cell (VoxelOctree.cpp:309-317): returns 0, or 1 for domain_error */
 int orc_find_cell(const orc_grid *g, const double *p, int64_t *cell);
+void orc_octree_add_point(orc_octree *t, const double *p);
 void orc_octree_add_sphere(orc_octree *t, const double *c, double r);
 /* environment preparation: collision/VoxelOctree.cpp:533-689 (remove_interior: keep_diagonal != 0
  * is the 27-neighbour variant) and :693-952 (dilate) */

@@ -348,6 +348,48 @@ def test_live_lung_environment_preparation(orc, wl):
         assert tr.collides(tr) and to.nblocks() == tr.nblocks() and to.ncells() == tr.ncells()
 
 
+@vox
+@pytest.mark.skipif(not ref.RefVoxelOctree.has_primitives(), reason="libvoxeloctree_ref.so built without primitives")
+@pytest.mark.parametrize("Ng,lim", [(16, [0, 1, 0, 1, 0, 1]), (64, [-0.3, 0.2, -0.1, 0.4, 0.0, 0.25]),
+                                     (128, [-0.21, 0.21, -0.21, 0.21, -0.21, 0.21])])
+def test_live_environment_primitives(orc, wl, Ng, lim):
+    """Environment::voxelize's primitives (motion-planning/Environment.cpp:62-74): VoxelOctree::add(Point),
+    add_sphere, add_capsule (VoxelOctree.cpp:319-323, 434-515) with collides(Sphere, Point) /
+    collides(Capsule, Point) (collision.hxx:62-84): oracle vs the reference's own text, bit-exact -- objects
+    inside, straddling a face, outside the grid, degenerate capsules, radii below a cell and above the grid."""
+    rng = np.random.default_rng(1234 + Ng)
+    lo, hi = np.array(lim[0::2]), np.array(lim[1::2])
+    ext = hi - lo
+    og = orc.grid(Ng, lim)
+    to, tr = orc.octree(og), ref.RefVoxelOctree(Ng, lim)
+    n_obj = 0
+    for k in range(60):
+        c = lo + ext * rng.uniform(-0.3, 1.3, 3)
+        r = float(ext.min() * rng.choice([0.001, 0.01, 0.05, 0.15, 0.4, 2.0]))
+        kind = k % 3
+        if kind == 0:
+            to.add_point(c); tr.add_point(c)
+        elif kind == 1:
+            to.add_sphere(c, r); tr.add_sphere(c, r)
+        else:
+            b = c if k % 9 == 2 else c + ext * rng.uniform(-0.5, 0.5, 3)      # a == b: closest_t's eps branch
+            to.add_capsule(c, b, min(r, 0.2 * ext.min())); tr.add_capsule(c, b, min(r, 0.2 * ext.min()))
+        n_obj += 1
+        if k % 10 == 9:
+            assert _same_tree(to, tr), (Ng, k)
+    # points exactly on the limits (inclusive on both ends, clamped into the last cell) and cell corners
+    for p in (lo, hi, (lo + hi) / 2, lo + ext / Ng * 3, hi + 1e-12, lo - 1e-12):
+        to.add_point(p); tr.add_point(p)
+    assert _same_tree(to, tr) and to.ncells() == tr.ncells() and to.ncells() > 0
+    # the lung-like capsule tree the benchmark environment is made of
+    if Ng == 128:
+        spec = wl.robot_b(0.003)
+        to, tr = orc.octree(og), ref.RefVoxelOctree(Ng, lim)
+        for a, b, rad in wl.lung_like_capsules(spec):
+            to.add_capsule(a, b, rad); tr.add_capsule(a, b, rad)
+        assert _same_tree(to, tr) and tr.ncells() > 1000
+
+
 # ------------------------------------------------------------------ collides_self (reference's own text)
 @pytest.mark.skipif(not ref.RefSelfCollision.available(), reason="oracle/_ref/libselfcol_ref.so not built")
 def test_live_collides_self(orc, wl):
