@@ -213,6 +213,18 @@ int64_t irt_env_nblocks(irt_ctx *ctx, const irt_env *env); /* VoxelOctree::nbloc
  *                           VoxelOctree::remove_interior, VoxelOctree.h:165); cells outside the
  *                           grid count as occupied
  *   irt_env_download        dense host copy blocks[Nb^3] indexed by Morton key */
+/* Environment::voxelize(reference) (motion-planning/Environment.cpp:62-74): voxels->add(p) / add(s) / add(c) for
+ * the environment's points [n][3], spheres [n][4] = (c, r) and capsules [n][7] = (a, b, r), OR-ed into the
+ * grid (clear_first != 0: into an empty one, like the reference's empty_copy()).  A voxel is set when its
+ * CENTRE is inside the object (VoxelOctree::add_sphere / add_capsule, collision/VoxelOctree.cpp:434-515;
+ * collides(Sphere, Point) / collides(Capsule, Point), collision/collision.hxx:62-84), plus the cells of the
+ * points, sphere centres and capsule end points themselves (add_point, :319-323).  Bit-exact with the
+ * reference's trees.  Environment::voxelize(reference, dilate) (:76-101) is the same call with `dilate` added
+ * to every radius and the points turned into spheres of that radius (host side, see the mirrors).
+ * Meshes are not supported (the reference throws std::logic_error for them as well). */
+int irt_env_add_primitives(irt_ctx *ctx, irt_env *env, const double *points, int64_t n_points,
+                           const double *spheres, int64_t n_spheres, const double *capsules,
+                           int64_t n_capsules, int clear_first);
 int irt_env_dilate(irt_ctx *ctx, irt_env *env, int num, int use_diagonal);
 int irt_env_dilate_sphere(irt_ctx *ctx, irt_env *env, double r);
 int irt_env_remove_interior(irt_ctx *ctx, irt_env *env, int keep_diagonal);

@@ -98,6 +98,7 @@ ABI_SYMBOLS = [
     "irt_fk_tip_jacobian_batch", "irt_fk_tip_jacobian_batch_dev",
     "irt_env_create", "irt_env_destroy", "irt_env_update", "irt_env_update_dev",
     "irt_env_update_sparse", "irt_env_nblocks",
+    "irt_env_add_primitives",
     "irt_env_dilate", "irt_env_dilate_sphere", "irt_env_remove_interior", "irt_env_download",
     "irt_setstore_create", "irt_setstore_destroy", "irt_setstore_num_sets",
     "irt_setstore_num_blocks", "irt_setstore_import", "irt_setstore_export",
@@ -151,6 +152,7 @@ def lib():
         "irt_env_update_dev": (i32, [vp, vp, vp, vp]),
         "irt_env_update_sparse": (i32, [vp, vp, vp, vp, i64]),
         "irt_env_nblocks": (i64, [vp, vp]),
+        "irt_env_add_primitives": (i32, [vp, vp, vp, i64, vp, i64, vp, i64, i32]),
         "irt_env_dilate": (i32, [vp, vp, i32, i32]),
         "irt_env_dilate_sphere": (i32, [vp, vp, C.c_double]),
         "irt_env_remove_interior": (i32, [vp, vp, i32]),
@@ -443,6 +445,28 @@ class Env:
 
     def nblocks(self):
         return int(self.ctx.L.irt_env_nblocks(self.ctx.h, self.h))
+
+    def add_primitives(self, points=None, spheres=None, capsules=None, clear=False, dilate=0.0):
+        """Environment::voxelize (motion-planning/Environment.cpp:62-101) on the device: points [n][3], spheres
+        [n][4] = (c, r), capsules [n][7] = (a, b, r) OR-ed into the grid (clear=True: into an empty one).
+        dilate > 0 is the reference's second overload: every radius grows by `dilate` and the points become
+        spheres of that radius; dilate == 0 there voxelises NOTHING (its `dummy` environment stays empty,
+        Environment.cpp:86-99) -- use dilate=0.0 here for the plain overload."""
+        def arr(a, w):
+            a = np.zeros((0, w)) if a is None else np.ascontiguousarray(a, dtype=np.float64).reshape(-1, w)
+            return a
+        pts, sph, cap = arr(points, 3), arr(spheres, 4), arr(capsules, 7)
+        if dilate < 0.0:
+            raise IrtError(IRT_ERR_INVALID_ARGUMENT, "Negative dilation value given")   # Environment.cpp:83-85
+        if dilate > 0.0:
+            sph = np.concatenate([np.concatenate([pts, np.full((len(pts), 1), dilate)], axis=1),
+                                  sph + np.array([0, 0, 0, dilate])], axis=0)
+            cap = cap + np.array([0, 0, 0, 0, 0, 0, dilate])
+            pts = np.zeros((0, 3))
+        sph, cap, pts = (np.ascontiguousarray(x) for x in (sph, cap, pts))
+        self.ctx.check(self.ctx.L.irt_env_add_primitives(
+            self.ctx.h, self.h, _ptr(pts) if len(pts) else None, len(pts), _ptr(sph) if len(sph) else None, len(sph),
+            _ptr(cap) if len(cap) else None, len(cap), int(bool(clear))))
 
     def dilate(self, num=1, use_diagonal=False):
         """VoxelOctree::dilate_6neighbor / dilate_27neighbor, in place on the device."""

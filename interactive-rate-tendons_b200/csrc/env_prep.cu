@@ -1,4 +1,5 @@
-// env_prep.cu -- environment preparation on the device.
+// env_prep.cu -- environment preparation on the device: morphology (below) and the voxelisation
+// of Environment's points / spheres / capsules (Environment::voxelize, at the end of this file).
 //
 // Replaces VoxelOctree::dilate_6neighbor / dilate_27neighbor / dilate_sphere
 // (collision/VoxelOctree.cpp:693-952) and remove_interior_6neighbor / _27neighbor (:533-689) on the
@@ -15,7 +16,10 @@
 // One thread per 4x4x4 leaf block: it loads the 3x3x3 block neighbourhood once and derives every
 // shifted copy with per-axis shift/mask pairs, so a step is ~27 loads + ~400 integer ops per
 // block and the whole 128^3 grid is one 2M-thread launch.
+#include <vector>
+
 #include "common.cuh"
+#include "env_prims.h"
 
 namespace {
 
@@ -146,9 +150,95 @@ int env_morph(irt_ctx *ctx, irt_env *env, bool erode, uint32_t offsets, int num)
   return IRT_OK;
 }
 
+// ---- Environment::voxelize's primitives (motion-planning/Environment.cpp:62-74) -------------------------
+// One thread per 4x4x4 leaf block ORs the bits of every object into its own block (no atomics); the objects
+// are staged through shared memory in chunks.  The per-block arithmetic is env_prims.h (checked against the
+// oracle on the host).  add_point() of the centres / end points / plain points is a second, tiny kernel.
+constexpr int EP_CHUNK = 64;
+
+__global__ void __launch_bounds__(128)
+env_add_primitives_kernel(uint64_t *__restrict__ blocks, const GridDev gd, const double *__restrict__ prims,
+                          int64_t n_prims) {
+  __shared__ double sh[EP_CHUNK * EP_PRIM_DOUBLES];
+  const uint32_t key = blockIdx.x * blockDim.x + threadIdx.x;
+  const bool live = key < (uint32_t)gd.Nb * gd.Nb * gd.Nb;
+  const int bx = (int)compact3(key >> 2), by = (int)compact3(key >> 1), bz = (int)compact3(key);
+  uint64_t acc = 0ull;
+  for (int64_t base = 0; base < n_prims; base += EP_CHUNK) {
+    const int m = (int)((n_prims - base < EP_CHUNK) ? (n_prims - base) : EP_CHUNK);
+    __syncthreads();
+    for (int i = threadIdx.x; i < m * EP_PRIM_DOUBLES; i += blockDim.x) sh[i] = prims[base * EP_PRIM_DOUBLES + i];
+    __syncthreads();
+    if (live)
+      for (int i = 0; i < m; i++) acc |= ep_block_bits(gd.lo, gd.d, bx, by, bz, sh + i * EP_PRIM_DOUBLES);
+  }
+  if (live && acc) blocks[key] |= acc;
+}
+
+__global__ void env_add_points_kernel(uint64_t *__restrict__ blocks, const GridDev gd,
+                                      const double *__restrict__ pts, int64_t n) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const double p[3] = {pts[3 * i], pts[3 * i + 1], pts[3 * i + 2]};
+  int c[3];
+  if (!ep_point_cell(gd.lo, gd.hi, gd.d, gd.Ng, p, c)) return;
+  const uint32_t key = (spread3((uint32_t)(c[0] >> 2)) << 2) | (spread3((uint32_t)(c[1] >> 2)) << 1) |
+                       spread3((uint32_t)(c[2] >> 2));
+  atomicOr((unsigned long long *)&blocks[key], 1ull << ((c[0] & 3) * 16 + (c[1] & 3) * 4 + (c[2] & 3)));
+}
+
 }  // namespace
 
 extern "C" {
+
+int irt_env_add_primitives(irt_ctx *ctx, irt_env *env, const double *points, int64_t n_points,
+                           const double *spheres, int64_t n_spheres, const double *capsules,
+                           int64_t n_capsules, int clear_first) {
+  if (!ctx || !env || n_points < 0 || n_spheres < 0 || n_capsules < 0 || (n_points && !points) ||
+      (n_spheres && !spheres) || (n_capsules && !capsules))
+    return IRT_ERR_INVALID_ARGUMENT;
+  IRT_CUDA(ctx, cudaSetDevice(ctx->device));
+  cudaStream_t st = ctx->stream;
+  if (clear_first) IRT_CUDA(ctx, cudaMemsetAsync(env->d_blocks, 0, (size_t)env->n_blocks_total * 8, st));
+  // host staging: objects as 8 doubles each; add_point() inputs = plain points, sphere centres, capsule ends
+  const int64_t n_prims = n_spheres + n_capsules, n_pts = n_points + n_spheres + 2 * n_capsules;
+  if (n_prims + n_pts > 0) {
+    std::vector<double> h((size_t)n_prims * EP_PRIM_DOUBLES + (size_t)n_pts * 3);
+    double *hp = h.data(), *hq = h.data() + (size_t)n_prims * EP_PRIM_DOUBLES;
+    for (int64_t i = 0; i < n_points; i++, hq += 3) { hq[0] = points[3 * i]; hq[1] = points[3 * i + 1]; hq[2] = points[3 * i + 2]; }
+    for (int64_t i = 0; i < n_spheres; i++, hp += EP_PRIM_DOUBLES, hq += 3) {
+      const double *s = spheres + 4 * i;
+      hp[0] = s[0]; hp[1] = s[1]; hp[2] = s[2]; hp[3] = hp[4] = hp[5] = 0.0; hp[6] = s[3]; hp[7] = 0.0;
+      hq[0] = s[0]; hq[1] = s[1]; hq[2] = s[2];
+    }
+    for (int64_t i = 0; i < n_capsules; i++, hp += EP_PRIM_DOUBLES, hq += 6) {
+      const double *c = capsules + 7 * i;
+      for (int k = 0; k < 6; k++) hp[k] = hq[k] = c[k];
+      hp[6] = c[6]; hp[7] = 1.0;
+    }
+    double *d = (double *)ctx_scratch(ctx, h.size() * sizeof(double));
+    if (!d) return irt_fail(ctx, IRT_ERR_CUDA, "scratch alloc failed");
+    IRT_CUDA(ctx, cudaMemcpyAsync(d, h.data(), h.size() * sizeof(double), cudaMemcpyHostToDevice, st));
+    IRT_CUDA(ctx, cudaStreamSynchronize(st));  // h is pageable and goes out of scope
+    if (n_prims > 0) {
+      const int T = 128;
+      env_add_primitives_kernel<<<(unsigned)((env->n_blocks_total + T - 1) / T), T, 0, st>>>(env->d_blocks, env->gd,
+                                                                                            d, n_prims);
+      IRT_LAUNCHED(ctx);
+    }
+    if (n_pts > 0) {
+      const int T = 256;
+      env_add_points_kernel<<<(unsigned)((n_pts + T - 1) / T), T, 0, st>>>(
+          env->d_blocks, env->gd, d + (size_t)n_prims * EP_PRIM_DOUBLES, n_pts);
+      IRT_LAUNCHED(ctx);
+    }
+    IRT_CUDA(ctx, cudaGetLastError());
+  }
+  int rc = env_rebuild_occ(ctx, env, st);
+  if (rc) return rc;
+  IRT_CUDA(ctx, cudaStreamSynchronize(st));
+  return IRT_OK;
+}
 
 int irt_env_dilate(irt_ctx *ctx, irt_env *env, int num, int use_diagonal) {
   if (!ctx || !env) return IRT_ERR_INVALID_ARGUMENT;

@@ -341,6 +341,15 @@ inline std::vector<std::vector<double>> levmar_jacobian_batch(const tendon::Tend
 
 namespace collision {
 
+struct Sphere {  // collision/Sphere.h
+  Point c;
+  double r;
+};
+struct Capsule {  // collision/Capsule.h
+  Point a, b;
+  double r;
+};
+
 /// Value-type mirror of collision::VoxelOctree: the sparse set of occupied 4x4x4 leaf blocks.
 /// Storage is a key-ordered map (Morton key == the reference's visit_leaves order); the heavy
 /// operations (voxelising shapes, collides) go through the C ABI.
@@ -448,6 +457,29 @@ public:
 
   /// environment preparation (collision/VoxelOctree.cpp:533-952; VoxelOctree.h:155-201), on the GPU:
   /// upload, morph in place on the device grid, read the dense grid back
+  /// add(Point) / add_sphere / add_capsule (collision/VoxelOctree.cpp:319-323, 434-515; VoxelOctree.h:240-242): a
+  /// voxel is set when its centre is inside the object; on the GPU, like every other bulk operation here
+  void add_point(const Point &p) { add_primitives({p}, {}, {}); }
+  void add(const Point &p) { add_point(p); }
+  void add_sphere(const Sphere &s) { add_primitives({}, {s}, {}); }
+  void add(const Sphere &s) { add_sphere(s); }
+  void add_capsule(const Capsule &c) { add_primitives({}, {}, {c}); }
+  void add(const Capsule &c) { add_capsule(c); }
+  /// all objects of an Environment in ONE device call (Environment::voxelize, Environment.cpp:62-74)
+  void add_primitives(const std::vector<Point> &points, const std::vector<Sphere> &spheres,
+                      const std::vector<Capsule> &capsules) {
+    std::vector<double> p, s, c;
+    for (auto &q : points) p.insert(p.end(), q.begin(), q.end());
+    for (auto &q : spheres) { s.insert(s.end(), q.c.begin(), q.c.end()); s.push_back(q.r); }
+    for (auto &q : capsules) {
+      c.insert(c.end(), q.a.begin(), q.a.end()); c.insert(c.end(), q.b.begin(), q.b.end()); c.push_back(q.r);
+    }
+    on_device([&](irt_ctx *cx, irt_env *e) {
+      return irt_env_add_primitives(cx, e, p.data(), (int64_t)points.size(), s.data(), (int64_t)spheres.size(),
+                                    c.data(), (int64_t)capsules.size(), 0);
+    });
+  }
+
   void dilate_6neighbor(int num = 1) { on_device([&](irt_ctx *c, irt_env *e) { return irt_env_dilate(c, e, num, 0); }); }
   void dilate_27neighbor(int num = 1) { on_device([&](irt_ctx *c, irt_env *e) { return irt_env_dilate(c, e, num, 1); }); }
   void dilate(int num = 1, bool use_diagonal = false) { use_diagonal ? dilate_27neighbor(num) : dilate_6neighbor(num); }
@@ -522,6 +554,35 @@ private:
 }  // namespace collision
 
 namespace motion_planning {
+
+/// the voxelisable part of motion_planning::Environment (motion-planning/Environment.h): points, spheres,
+/// capsules and voxelize() (Environment.cpp:62-101).  Meshes are not supported there either (std::logic_error).
+struct Environment {
+  std::vector<collision::Point> points;
+  std::vector<collision::Sphere> spheres;
+  std::vector<collision::Capsule> capsules;
+  void push_back(const collision::Point &p) { points.push_back(p); }
+  void push_back(const collision::Sphere &s) { spheres.push_back(s); }
+  void push_back(const collision::Capsule &c) { capsules.push_back(c); }
+
+  std::shared_ptr<collision::VoxelOctree> voxelize(const collision::VoxelOctree &reference) const {
+    auto voxels = std::make_shared<collision::VoxelOctree>(reference.empty_copy());
+    voxels->add_primitives(points, spheres, capsules);
+    return voxels;
+  }
+  /// every radius grown by `dilate`, points become spheres.  As in the reference, dilate == 0 voxelises an
+  /// EMPTY environment (its `dummy` is only filled when dilate > 0, Environment.cpp:86-99).
+  std::shared_ptr<collision::VoxelOctree> voxelize(const collision::VoxelOctree &reference, double dilate) const {
+    if (dilate < 0.0) throw std::invalid_argument("Negative dilation value given");
+    Environment dummy;
+    if (dilate > 0.0) {
+      for (auto &p : points) dummy.spheres.push_back(collision::Sphere{p, dilate});
+      for (auto &s : spheres) dummy.spheres.push_back(collision::Sphere{s.c, s.r + dilate});
+      for (auto &c : capsules) dummy.capsules.push_back(collision::Capsule{c.a, c.b, c.r + dilate});
+    }
+    return dummy.voxelize(reference);
+  }
+};
 
 /// the part of VoxelEnvironment the hot path uses: inv_rotation + PartialVoxelization
 struct VoxelEnvironment {

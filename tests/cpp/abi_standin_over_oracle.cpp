@@ -215,6 +215,15 @@ int irt_setstore_export(irt_ctx *, const irt_setstore *s, uint64_t *offsets, uin
   return IRT_OK;
 }
 
+int irt_env_add_primitives(irt_ctx *, irt_env *env, const double *points, int64_t n_points, const double *spheres,
+                           int64_t n_spheres, const double *capsules, int64_t n_capsules, int clear_first) {
+  if (clear_first) orc_octree_clear(env->t);
+  for (int64_t i = 0; i < n_points; i++) orc_octree_add_point(env->t, points + 3 * i);
+  for (int64_t i = 0; i < n_spheres; i++) orc_octree_add_sphere(env->t, spheres + 4 * i, spheres[4 * i + 3]);
+  for (int64_t i = 0; i < n_capsules; i++)
+    orc_octree_add_capsule(env->t, capsules + 7 * i, capsules + 7 * i + 3, capsules[7 * i + 6]);
+  return IRT_OK;
+}
 int irt_env_dilate(irt_ctx *, irt_env *env, int num, int use_diagonal) {
   if (use_diagonal) orc_octree_dilate_27neighbor(env->t, num); else orc_octree_dilate_6neighbor(env->t, num);
   return IRT_OK;

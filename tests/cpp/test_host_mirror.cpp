@@ -134,6 +134,44 @@ int main() {
     CHECK(same(v, o));
     orc_octree_free(o);
   }
+  {  // Environment::voxelize (Environment.cpp:62-101) and VoxelOctree::add(Point / Sphere / Capsule)
+    motion_planning::Environment e;
+    e.push_back(collision::Point{0.01, -0.02, 0.03});
+    e.push_back(collision::Point{0.5, 0.5, 0.5});                                   // outside the grid: ignored
+    e.push_back(collision::Sphere{{0.05, 0.02, 0.12}, 0.03});
+    e.push_back(collision::Sphere{{-0.2, 0.0, 0.0}, 0.04});                         // straddles a face
+    e.push_back(collision::Capsule{{0.0, 0.0, 0.0}, {0.03, -0.05, 0.15}, 0.012});
+    e.push_back(collision::Capsule{{0.1, 0.1, 0.1}, {0.1, 0.1, 0.1}, 0.02});        // degenerate: a sphere
+    auto same_tree = [&](const collision::VoxelOctree &v, const orc_octree *o) {
+      bool ok = (int64_t)v.nblocks() == orc_octree_nblocks(o) && (int64_t)v.ncells() == orc_octree_ncells(o);
+      v.visit_leaves([&](size_t bx, size_t by, size_t bz, uint64_t b) { ok = ok && orc_octree_block(o, bx, by, bz) == b; });
+      return ok;
+    };
+    for (double dilate : {-1.0, 0.0, 0.006}) {   // -1: the plain overload
+      orc_octree *o = orc_octree_new(&og);
+      if (dilate < 0.0) {
+        for (auto &p : e.points) orc_octree_add_point(o, p.data());
+        for (auto &s : e.spheres) orc_octree_add_sphere(o, s.c.data(), s.r);
+        for (auto &c : e.capsules) orc_octree_add_capsule(o, c.a.data(), c.b.data(), c.r);
+      } else if (dilate > 0.0) {
+        for (auto &p : e.points) orc_octree_add_sphere(o, p.data(), dilate);
+        for (auto &s : e.spheres) orc_octree_add_sphere(o, s.c.data(), s.r + dilate);
+        for (auto &c : e.capsules) orc_octree_add_capsule(o, c.a.data(), c.b.data(), c.r + dilate);
+      }  // dilate == 0: the reference voxelises an empty dummy environment
+      auto v = dilate < 0.0 ? e.voxelize(env_vox) : e.voxelize(env_vox, dilate);
+      CHECK(same_tree(*v, o));
+      if (dilate == 0.0) CHECK(v->is_empty());
+      if (dilate < 0.0) {   // one object at a time gives the same tree as the batch
+        collision::VoxelOctree w = env_vox.empty_copy();
+        for (auto &p : e.points) w.add(p);
+        for (auto &s : e.spheres) w.add(s);
+        for (auto &c : e.capsules) w.add(c);
+        CHECK(same_tree(w, o) && w.ncells() > 500);
+      }
+      orc_octree_free(o);
+    }
+    try { e.voxelize(env_vox, -0.5); CHECK(false); } catch (const std::invalid_argument &) {}
+  }
   try { collision::VoxelOctree bad(100); CHECK(false); } catch (const std::invalid_argument &) {}
   try { collision::VoxelOctree(64).collides(env_vox); CHECK(false); } catch (const std::invalid_argument &) {}
 

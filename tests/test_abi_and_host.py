@@ -203,3 +203,17 @@ def test_cpp_host_mirror_host_logic(tmp_path, orc):
     out = subprocess.run([exe], capture_output=True, text=True, timeout=900)
     assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-2000:]
     assert "host mirror ok" in out.stdout and "createRoadmap: 120 vertices" in out.stdout
+
+
+def test_env_primitive_arithmetic_on_host(tmp_path, orc):
+    """The per-leaf-block arithmetic the device kernel env_add_primitives_kernel runs (csrc/env_prims.h: voxel
+    centres inside spheres / capsules, add_point cells) compiled for the host with -ffp-contract=off and
+    compared with the oracle's add_point / add_sphere / add_capsule on four grids: 0 flips."""
+    exe = str(tmp_path / "test_env_prims_host")
+    subprocess.check_call(["g++", "-std=c++17", "-O2", "-ffp-contract=off", "-Wall", "-Wextra", "-Werror",
+                           os.path.join(ROOT, "tests", "cpp", "test_env_prims_host.cpp"), "-o", exe,
+                           "-L" + os.path.join(ROOT, "oracle"), "-loracle",
+                           "-Wl,-rpath," + os.path.join(ROOT, "oracle"), "-fopenmp"])
+    out = subprocess.run([exe], capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
+    assert "env primitives ok" in out.stdout and out.stdout.count(" 0 flips") == 4

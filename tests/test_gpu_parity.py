@@ -859,3 +859,65 @@ def test_create_roadmap_options(irt, ctx, orc, wl):
     s = prm.random_states(1000, 3)
     assert s[:, :6].min() >= 0 and s[:, :6].max() <= 20 and np.abs(s[:, 6]).max() <= np.pi
     assert s[:, 7].min() >= 0 and s[:, 7].max() <= spec["L"]
+
+
+@pytest.mark.parametrize("Ng,lim", [(16, [0, 1, 0, 1, 0, 1]), (64, [-0.3, 0.2, -0.1, 0.4, 0.0, 0.25]),
+                                     (128, [-0.21, 0.21, -0.21, 0.21, -0.21, 0.21])])
+def test_env_add_primitives_bit_exact(irt, ctx, orc, wl, Ng, lim):
+    """Environment::voxelize on the device (irt_env_add_primitives) against the oracle's add_point / add_sphere /
+    add_capsule (pinned by the reference's own text): objects inside, straddling a face, outside the grid,
+    degenerate capsules, radii below a cell and beyond the grid; 0 flips."""
+    rng = np.random.default_rng(4321 + Ng)
+    lo, hi = np.array(lim[0::2]), np.array(lim[1::2])
+    ext = hi - lo
+    grid, og = irt.make_grid(Ng, lim), orc.grid(Ng, lim)
+    want = orc.octree(og)
+    pts, sph, cap = [], [], []
+    for k in range(90):
+        c = lo + ext * rng.uniform(-0.3, 1.3, 3)
+        r = float(ext.min() * rng.choice([0.001, 0.01, 0.05, 0.12, 0.02, 0.2]))
+        if k % 3 == 0:
+            want.add_point(c); pts.append(c)
+        elif k % 3 == 1:
+            want.add_sphere(c, r); sph.append(np.append(c, r))
+        else:
+            b = c if k % 9 == 2 else c + ext * rng.uniform(-0.5, 0.5, 3)
+            want.add_capsule(c, b, r); cap.append(np.concatenate([c, b, [r]]))
+    for p in (lo, hi, lo + ext / Ng * 3, hi + np.array([1e-12, 0, 0])):
+        want.add_point(p); pts.append(p)
+    env = irt.Env(ctx, grid)
+    env.update(np.full((Ng // 4) ** 3, 0xFFFF, dtype=np.uint64))         # stale content: clear=True must drop it
+    env.add_primitives(pts, sph, cap, clear=True)
+    got, ref = env.download(), want.dense_morton()
+    flips = int(sum(bin(int(x)).count("1") for x in (got ^ ref)[got != ref]))
+    assert flips == 0, "%d voxel flips" % flips
+    assert 0 < np.count_nonzero(ref) and env.nblocks() == np.count_nonzero(ref)
+    # OR-ing more objects into the existing grid (clear=False), one kind at a time
+    big = np.append(lo + ext / 2, 3.0 * ext.max())
+    want.add_sphere(big[:3], big[3])
+    env.add_primitives(spheres=[big])
+    assert np.array_equal(env.download(), want.dense_morton()) and np.all(env.download() == ~np.uint64(0))
+    # nothing to add is a no-op; empty arrays are accepted
+    env.add_primitives(clear=True)
+    assert env.nblocks() == 0
+
+
+def test_env_voxelize_lung_capsules_and_dilate(irt, ctx, orc, wl):
+    """the benchmark environment's capsule tree through Environment::voxelize(reference[, dilate]) on the device,
+    followed by the preparation steps the apps apply (dilate by the robot radius, shell only)"""
+    spec = wl.robot_b(0.003)
+    g = wl.workspace_grid(spec)
+    grid, og = irt.make_grid(g["Ng"], g["lim"]), orc.grid(g["Ng"], g["lim"])
+    caps = np.array([np.concatenate([a, b, [r]]) for a, b, r in wl.lung_like_capsules(spec)])
+    for dilate in (0.0, 0.004):
+        want = orc.octree(og)
+        for c in caps:
+            want.add_capsule(c[:3], c[3:6], c[6] + dilate)
+        env = irt.Env(ctx, grid)
+        env.add_primitives(capsules=caps, clear=True, dilate=dilate)
+        assert np.array_equal(env.download(), want.dense_morton()) and env.nblocks() > 100
+        env.dilate_sphere(spec["r"]); want.dilate_sphere(spec["r"])
+        env.remove_interior(); want.remove_interior()
+        assert np.array_equal(env.download(), want.dense_morton())
+    with pytest.raises(irt.IrtError):
+        irt.Env(ctx, grid).add_primitives(capsules=caps, dilate=-1.0)
