@@ -162,6 +162,27 @@ def main():
         out["tr_%s_flags" % name] = np.array([rr.flags(s_) for s_ in st], dtype=np.uint32)
         out["tr_%s_home" % name] = np.stack([rr.home_lengths(s_) for s_ in st])
     path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "reference_vectors.npz")
+    # Environment::voxelize's primitives: VoxelOctree::add(Point) / add_sphere / add_capsule of the reference
+    # (VoxelOctree.cpp:319-323, 434-515) on a non-cubic-celled 64^3 grid; kind 0 point, 1 sphere, 2 capsule
+    prng = np.random.default_rng(20220801 + 77)
+    plim = [-0.3, 0.2, -0.1, 0.4, 0.0, 0.25]
+    plo, pext = np.array(plim[0::2]), np.array(plim[1::2]) - np.array(plim[0::2])
+    objs = np.zeros((45, 8))
+    t = ref.RefVoxelOctree(64, plim)
+    for k in range(len(objs)):
+        a = plo + pext * prng.uniform(-0.3, 1.3, 3)
+        b = a if k % 9 == 2 else a + pext * prng.uniform(-0.5, 0.5, 3)
+        r = float(pext.min() * prng.choice([0.001, 0.01, 0.05, 0.12, 0.02, 0.2]))
+        objs[k] = np.concatenate([a, b, [r, k % 3]])
+        if k % 3 == 0:
+            t.add_point(a)
+        elif k % 3 == 1:
+            t.add_sphere(a, r)
+        else:
+            t.add_capsule(a, b, r)
+    out["vo_prim_lim"] = np.array(plim)
+    out["vo_prim_objs"] = objs
+    out["vo_prim_xyz"], out["vo_prim_bits"] = t.export()
     np.savez_compressed(path, **out)
     print("wrote", path, os.path.getsize(path), "bytes")
 

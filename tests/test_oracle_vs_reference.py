@@ -348,6 +348,22 @@ def test_live_lung_environment_preparation(orc, wl):
         assert tr.collides(tr) and to.nblocks() == tr.nblocks() and to.ncells() == tr.ncells()
 
 
+def test_golden_environment_primitives(orc, gold):
+    """add(Point) / add_sphere / add_capsule of the reference (VoxelOctree.cpp:319-323, 434-515), committed as
+    golden leaves: the oracle reproduces them where /root/reference and oracle/_ref are absent"""
+    t = orc.octree(orc.grid(64, gold["vo_prim_lim"].tolist()))
+    for o in gold["vo_prim_objs"]:
+        if o[7] == 0:
+            t.add_point(o[:3])
+        elif o[7] == 1:
+            t.add_sphere(o[:3], float(o[6]))
+        else:
+            t.add_capsule(o[:3], o[3:6], float(o[6]))
+    xyz, bits = t.export()
+    assert np.array_equal(xyz, gold["vo_prim_xyz"]) and np.array_equal(bits, gold["vo_prim_bits"])
+    assert len(bits) > 100
+
+
 @vox
 @pytest.mark.skipif(not ref.RefVoxelOctree.has_primitives(), reason="libvoxeloctree_ref.so built without primitives")
 @pytest.mark.parametrize("Ng,lim", [(16, [0, 1, 0, 1, 0, 1]), (64, [-0.3, 0.2, -0.1, 0.4, 0.0, 0.25]),
