@@ -211,6 +211,35 @@ def test_env_preparation_vs_reference(irt, ctx, wl):
         assert np.array_equal(got, want), op
 
 
+@vo_ref
+@pytest.mark.skipif(not ref.RefVoxelOctree.has_primitives(), reason="libvoxeloctree_ref.so built without primitives")
+def test_env_voxelize_vs_reference(irt, ctx, wl):
+    """irt_env_add_primitives (Environment::voxelize, Environment.cpp:62-74) vs the reference's own
+    add(Point) / add_sphere / add_capsule text (VoxelOctree.cpp:319-323, 434-515): the benchmark's capsule tree
+    plus points and spheres inside, across and outside the grid; 0 flips"""
+    spec = wl.robot_b(0.003)
+    g = wl.workspace_grid(spec)
+    Nb = g["Ng"] // 4
+    rng = np.random.default_rng(99)
+    caps = [np.concatenate([a, b, [r]]) for a, b, r in wl.lung_like_capsules(spec)]
+    pts = rng.uniform(-0.25, 0.25, (40, 3))
+    sph = np.concatenate([rng.uniform(-0.25, 0.25, (30, 3)), rng.choice([0.0005, 0.004, 0.02, 0.06], (30, 1))], axis=1)
+    tr = ref.RefVoxelOctree(g["Ng"], g["lim"])
+    for p in pts:
+        tr.add_point(p)
+    for s_ in sph:
+        tr.add_sphere(s_[:3], float(s_[3]))
+    for c in caps:
+        tr.add_capsule(c[:3], c[3:6], float(c[6]))
+    env = irt.Env(ctx, irt.make_grid(g["Ng"], g["lim"]))
+    env.add_primitives(pts, sph, np.array(caps), clear=True)
+    got = env.download()
+    xyz, rbits = tr.export()
+    want = np.zeros_like(got)
+    want[wl.morton_key(xyz[:, 0].astype(np.int64), xyz[:, 1].astype(np.int64), xyz[:, 2].astype(np.int64), Nb)] = rbits
+    assert np.array_equal(got, want) and np.count_nonzero(want) > 500
+
+
 @pytest.mark.skipif(not ref.RefSelfCollision.available(), reason="oracle/_ref/libselfcol_ref.so was not shipped")
 def test_self_collision_flags_vs_reference(irt, ctx, wl):
     """IRT_FLAG_SELF_COLLISION of the validity epilogue (FP32 pair filter + exact kernel) vs the
