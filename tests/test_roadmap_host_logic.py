@@ -44,6 +44,21 @@ class _Store:
     def check(self, env, begin=0, end=None):
         return self.orc.check_sets_batch(self.store, env.oenv, begin, end).astype(bool)
 
+    def check_dev(self, env, d_words, begin=0, end=None, stream=None):
+        """the device-pointer form the real _sweep calls: verdict bits packed into int32 words (torch, CPU here)"""
+        import torch
+        v = self.check(env, begin, end)
+        bits = np.zeros(d_words.numel() * 32, dtype=np.uint8)
+        bits[:len(v)] = v
+        d_words.copy_(torch.from_numpy(np.packbits(bits, bitorder="little").view(np.int32).copy()))
+
+
+class _Ctx:
+    device = 0
+
+    def synchronize(self):
+        pass
+
 
 def _prm(R, orc, wl, spec, g, oenv, monkeypatch):
     ogrid = orc.grid(g["Ng"], g["lim"])
@@ -140,3 +155,63 @@ def test_create_roadmap_lazy_and_custom_callbacks(orc, wl, monkeypatch):
     assert np.array_equal(prm2.edges, wl.knn_edges(spec, prm2.states, k=3))
     assert prm2.vertex_store.num_sets == 60 and prm2.edge_store.calls == 0     # vertex cache only
     assert not prm2.vertex_validity.any()                                       # voxelised, not validated
+
+
+_GLOO_WORKER = r'''
+import os, sys
+sys.path.insert(0, %(root)r)
+sys.path.insert(0, os.path.join(%(root)r, "tests"))
+import numpy as np, torch.distributed as dist
+import irt_b200.workloads as wl
+from irt_b200 import roadmap as R
+from oracle.oracle import Oracle
+import test_roadmap_host_logic as T
+rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+dist.init_process_group("gloo", rank=rank, world_size=world)
+orc = Oracle("canonical")
+spec = wl.robot_b(0.003, rotation=True)
+g = wl.workspace_grid(spec)
+ogrid = orc.grid(g["Ng"], g["lim"])
+oenv = orc.octree(ogrid)
+oenv.add_sphere([0.05, 0.02, 0.12], 0.03)
+R.SetStore = lambda ctx, grid: T._Store(orc, ogrid)
+R.Env = lambda ctx, grid: T._Env(oenv)
+prm = R.VoxelCachedLazyPRM(T._Ctx(), T._Robot(orc, spec, wl), None, rank=rank, world=world, dist=dist)
+prm.createRoadmap(70, opt=R.VoxelizeVertices | R.ValidateVertices | R.VoxelizeEdges | R.ValidateEdges)
+lo, hi = prm.shard(len(prm.edges))
+assert prm.edge_store.num_sets == hi - lo and len(prm.edge_flags) == hi - lo      # every rank keeps its shard only
+vv, ev = prm.precomputeVertexValidity(), prm.precomputeEdgeValidity()             # the real sharded sweeps + gathers
+np.savez(%(out)r + "_%%d.npz" %% rank, states=prm.states, edges=prm.edges, vv=vv, ev=ev)
+dist.barrier()
+dist.destroy_process_group()
+print("ok", rank)
+'''
+
+
+def test_create_roadmap_two_ranks_gloo(tmp_path, orc, wl, monkeypatch):
+    """N > 1 host path of createRoadmap(N, opt): every rank voxelises and checks only its shard of the new
+    edges, the PARTIAL flags and verdict words are all-gathered (the real _sweep / _gather_flags over gloo), and
+    both ranks end with the same roadmap as a single process."""
+    import os
+    import subprocess
+    import sys
+    from irt_b200 import roadmap as R
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    script = tmp_path / "worker.py"
+    script.write_text(_GLOO_WORKER % {"root": root, "out": str(tmp_path / "rank")})
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                          "--master-addr", "127.0.0.1", "--master-port", "29613", str(script)],
+                         capture_output=True, text=True, env=dict(os.environ, MASTER_ADDR="127.0.0.1"), timeout=600)
+    assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-3000:]
+    r0, r1 = np.load(str(tmp_path / "rank_0.npz")), np.load(str(tmp_path / "rank_1.npz"))
+    for k in ("states", "edges", "vv", "ev"):
+        assert np.array_equal(r0[k], r1[k]), k
+    # the single-process roadmap
+    spec = wl.robot_b(0.003, rotation=True)
+    g = wl.workspace_grid(spec)
+    oenv = orc.octree(orc.grid(g["Ng"], g["lim"]))
+    oenv.add_sphere([0.05, 0.02, 0.12], 0.03)
+    prm = _prm(R, orc, wl, spec, g, oenv, monkeypatch)
+    prm.createRoadmap(70, opt=R.VoxelizeVertices | R.ValidateVertices | R.VoxelizeEdges | R.ValidateEdges)
+    assert np.array_equal(prm.states, r0["states"]) and np.array_equal(prm.edges, r0["edges"])
+    assert np.all(r0["vv"] == R.VALIDITY_TRUE) and np.all(r0["ev"] == R.VALIDITY_TRUE) and len(r0["ev"]) > 50
