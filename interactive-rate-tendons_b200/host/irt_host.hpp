@@ -414,6 +414,134 @@ public:
   }
   bool operator==(const VoxelOctree &o) const { return N_ == o.N_ && lim_ == o.lim_ && blocks_ == o.blocks_; }
 
+  // ---- the rest of the reference's value-type surface (collision/VoxelOctree.h:91-290), host side ----
+  using ConstOccupiedVoxelVisitor = std::function<void(size_t, size_t, size_t)>;
+  using ConstVoxelVisitor = std::function<void(size_t, size_t, size_t, bool)>;
+  static size_t largest_supported_size() { return 512; }
+  static size_t to_supported_size(size_t Ndim) {  // VoxelOctree.cpp:82-96
+    for (size_t n = 4; n <= 512; n *= 2)
+      if (Ndim <= n) return n;
+    throw std::invalid_argument("too large for supported voxel octree: " + std::to_string(Ndim));
+  }
+  static uint64_t bitmask(size_t x, size_t y, size_t z) { return uint64_t(1) << (x * 16 + y * 4 + z); }
+  size_t N() const { return N_ * N_ * N_; }
+  size_t Nby() const { return N_ / 4; }
+  size_t Nbz() const { return N_ / 4; }
+  void set_xlim(const std::pair<double, double> &l) { set_xlim(l.first, l.second); }
+  void set_ylim(const std::pair<double, double> &l) { set_ylim(l.first, l.second); }
+  void set_zlim(const std::pair<double, double> &l) { set_zlim(l.first, l.second); }
+  Point lower_left() const { return {lim_[0], lim_[2], lim_[4]}; }
+  Point upper_right() const { return {lim_[1], lim_[3], lim_[5]}; }
+  double dbx() const { return dx() * 4; }
+  double dby() const { return dy() * 4; }
+  double dbz() const { return dz() * 4; }
+  bool is_in_domain(double x, double y, double z) const {  // inclusive on both ends, VoxelOctree.cpp:1505-1509
+    return lim_[0] <= x && x <= lim_[1] && lim_[2] <= y && y <= lim_[3] && lim_[4] <= z && z <= lim_[5];
+  }
+  Point voxel_center(size_t ix, size_t iy, size_t iz) const {
+    return {lim_[0] + (ix + 0.5) * dx(), lim_[2] + (iy + 0.5) * dy(), lim_[4] + (iz + 0.5) * dz()};
+  }
+  Point block_center(size_t bx, size_t by, size_t bz) const {
+    return {lim_[0] + (bx + 0.5) * dbx(), lim_[2] + (by + 0.5) * dby(), lim_[4] + (bz + 0.5) * dbz()};
+  }
+  /// returns the block's value before the operation, like the reference (VoxelOctree.cpp:235-249)
+  uint64_t intersect_block(size_t bx, size_t by, size_t bz, uint64_t v) {
+    const uint64_t old = block(bx, by, bz);
+    set_block(bx, by, bz, old & v);
+    return old;
+  }
+  uint64_t subtract_block(size_t bx, size_t by, size_t bz, uint64_t v) { return intersect_block(bx, by, bz, ~v); }
+  /// VoxelOctree.cpp:256-267 as written: the return value is `oldval & mask` when setting and
+  /// `oldval & ~mask` when clearing (not "did the cell change", whatever its comment says)
+  bool set_cell(size_t ix, size_t iy, size_t iz, bool value = true) {
+    const uint64_t mask = bitmask(ix % 4, iy % 4, iz % 4);
+    if (value) return union_block(ix / 4, iy / 4, iz / 4, mask) & mask;
+    return intersect_block(ix / 4, iy / 4, iz / 4, ~mask) & ~mask;
+  }
+  std::tuple<size_t, size_t, size_t> nearest_cell(double x, double y, double z) const {  // bounds truncating, :295-307
+    const int ix = (int)((x - lim_[0]) / dx()), iy = (int)((y - lim_[2]) / dy()), iz = (int)((z - lim_[4]) / dz());
+    return {std::min(N_ - 1, size_t(std::max(0, ix))), std::min(N_ - 1, size_t(std::max(0, iy))),
+            std::min(N_ - 1, size_t(std::max(0, iz)))};
+  }
+  std::tuple<size_t, size_t, size_t> find_cell(double x, double y, double z) const {  // bounds checking, :309-317
+    domain_check(x, y, z);
+    return {size_t((x - lim_[0]) / dx()), size_t((y - lim_[2]) / dy()), size_t((z - lim_[4]) / dz())};
+  }
+  std::tuple<size_t, size_t, size_t> nearest_block_idx(double x, double y, double z) const {  // :271-282
+    const int ix = (int)((x - lim_[0]) / dx()), iy = (int)((y - lim_[2]) / dy()), iz = (int)((z - lim_[4]) / dz());
+    return {std::min(N_ / 4 - 1, size_t(std::max(0, ix / 4))), std::min(N_ / 4 - 1, size_t(std::max(0, iy / 4))),
+            std::min(N_ / 4 - 1, size_t(std::max(0, iz / 4)))};
+  }
+  std::tuple<size_t, size_t, size_t> find_block_idx(double x, double y, double z) const {  // :284-293
+    auto [ix, iy, iz] = find_cell(x, y, z);
+    return {ix / 4, iy / 4, iz / 4};
+  }
+  uint64_t find_block(double x, double y, double z) const {
+    auto [bx, by, bz] = find_block_idx(x, y, z);
+    return block(bx, by, bz);
+  }
+  std::tuple<size_t, size_t, size_t> nearest_cell(const Point &p) const { return nearest_cell(p[0], p[1], p[2]); }
+  std::tuple<size_t, size_t, size_t> find_cell(const Point &p) const { return find_cell(p[0], p[1], p[2]); }
+  std::tuple<size_t, size_t, size_t> nearest_block_idx(const Point &p) const { return nearest_block_idx(p[0], p[1], p[2]); }
+  std::tuple<size_t, size_t, size_t> find_block_idx(const Point &p) const { return find_block_idx(p[0], p[1], p[2]); }
+  uint64_t find_block(const Point &p) const { return find_block(p[0], p[1], p[2]); }
+  bool collides(const Point &p) const {  // :967-971
+    if (!is_in_domain(p[0], p[1], p[2])) return false;
+    auto [ix, iy, iz] = nearest_cell(p);
+    return cell(ix, iy, iz);
+  }
+  void add(const VoxelOctree &o) { add_voxels(o); }
+  void remove_point(double x, double y, double z) {  // :980-984
+    if (!is_in_domain(x, y, z)) return;
+    auto [ix, iy, iz] = nearest_cell(x, y, z);
+    set_cell(ix, iy, iz, false);
+  }
+  void remove_point(const Point &p) { remove_point(p[0], p[1], p[2]); }
+  void remove_voxels(const VoxelOctree &o) {  // :986-990
+    check_dims(o);
+    for (auto &kv : o.blocks_) {
+      auto it = blocks_.find(kv.first);
+      if (it != blocks_.end() && !(it->second &= ~kv.second)) blocks_.erase(it);
+    }
+  }
+  void remove(const Point &p) { remove_point(p); }
+  void remove(const VoxelOctree &o) { remove_voxels(o); }
+  void intersect_voxels(const VoxelOctree &o) {  // :992-996
+    check_dims(o);
+    for (auto it = blocks_.begin(); it != blocks_.end();) {
+      auto jt = o.blocks_.find(it->first);
+      const uint64_t v = jt == o.blocks_.end() ? 0 : (it->second & jt->second);
+      if (v) { it->second = v; ++it; } else { it = blocks_.erase(it); }
+    }
+  }
+  void intersect(const VoxelOctree &o) { intersect_voxels(o); }
+  /// TreeNode::visit_blocks (detail/TreeNode.hxx:193-208, :270): octant recursion; an absent child is
+  /// reported ONCE, at its origin block, with value 0
+  void visit_blocks(const ConstBlockVisitor &f) const {
+    if (N_ == 4) { f(0, 0, 0, block(0, 0, 0)); return; }
+    visit_blocks_impl(f, 0u, N_ / 4);
+  }
+  void visit_occupied_voxels(const ConstOccupiedVoxelVisitor &f) const {  // :1013-1033
+    visit_leaves([&](size_t bx, size_t by, size_t bz, uint64_t b) {
+      for (size_t x = 0; x < 4; x++)
+        for (size_t y = 0; y < 4; y++)
+          for (size_t z = 0; z < 4; z++)
+            if (b & bitmask(x, y, z)) f(4 * bx + x, 4 * by + y, 4 * bz + z);
+    });
+  }
+  void visit_voxels(const ConstVoxelVisitor &f) const {  // :1035-1052
+    visit_blocks([&](size_t bx, size_t by, size_t bz, uint64_t b) {
+      for (size_t x = 0; x < 4; x++)
+        for (size_t y = 0; y < 4; y++)
+          for (size_t z = 0; z < 4; z++) f(4 * bx + x, 4 * by + y, 4 * bz + z, (b & bitmask(x, y, z)) != 0);
+    });
+  }
+  void add_line(const Point &a, const Point &b) { add_piecewise_line({a, b}); }  // one segment of :428-432
+  void erode_6neighbor() { throw std::runtime_error("erode_6neighbor() unimplemented"); }   // as in the reference,
+  void erode_27neighbor() { throw std::runtime_error("erode_27neighbor() unimplemented"); } // :954-965
+  void erode(bool use_diagonal = false) { use_diagonal ? erode_27neighbor() : erode_6neighbor(); }
+  void erode_sphere(double) { throw std::runtime_error("erode_sphere() unimplemented"); }
+
   irt_grid grid(const std::array<double, 9> &inv_rot = {1, 0, 0, 0, 1, 0, 0, 0, 1}) const {
     irt_grid g;
     std::memset(&g, 0, sizeof(g));
@@ -540,6 +668,23 @@ public:
 private:
   static void lim_check(double a, double b) {
     if (a >= b) throw std::length_error("limits must be positive in size");  // VoxelOctree.cpp:152-177
+  }
+  void domain_check(double x, double y, double z) const {  // VoxelOctree.cpp:1511-1521
+    if (!is_in_domain(x, y, z)) throw std::domain_error("point is out of the voxel dimensions");
+  }
+  /// node covering nb^3 blocks whose Morton keys start at key_lo (keys are in the reference's child order)
+  void visit_blocks_impl(const ConstBlockVisitor &f, uint32_t key_lo, size_t nb) const {
+    const size_t c = nb / 2, cc = c * c * c;
+    for (uint32_t i = 0; i < 8; i++) {
+      const uint32_t lo = key_lo + i * (uint32_t)cc;
+      auto it = blocks_.lower_bound(lo);
+      const bool present = it != blocks_.end() && it->first < lo + cc;
+      int bx, by, bz;
+      irt_morton_decode(lo, (int)(N_ / 4), &bx, &by, &bz);
+      if (!present) f((size_t)bx, (size_t)by, (size_t)bz, 0);
+      else if (c == 1) f((size_t)bx, (size_t)by, (size_t)bz, it->second);
+      else visit_blocks_impl(f, lo, c);
+    }
   }
   void check_dims(const VoxelOctree &o) const {
     if (N_ != o.N_)

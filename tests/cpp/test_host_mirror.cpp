@@ -6,6 +6,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <algorithm>
+#include <array>
 #include <random>
 #include <set>
 #include <vector>
@@ -171,6 +172,99 @@ int main() {
       orc_octree_free(o);
     }
     try { e.voxelize(env_vox, -0.5); CHECK(false); } catch (const std::invalid_argument &) {}
+  }
+  {  // the rest of VoxelOctree's value-type surface (collision/VoxelOctree.h:91-290)
+    using VO = collision::VoxelOctree;
+    CHECK(VO::to_supported_size(5) == 8 && VO::to_supported_size(512) == 512 && VO::largest_supported_size() == 512);
+    try { VO::to_supported_size(513); CHECK(false); } catch (const std::invalid_argument &) {}
+    CHECK(env_vox.N() == 128u * 128 * 128 && env_vox.Nby() == 32 && env_vox.dbx() == 4 * env_vox.dx());
+    CHECK(env_vox.lower_left()[0] == -0.21 && env_vox.upper_right()[2] == 0.21);
+    // find_cell / nearest_cell / find_block_idx against the oracle, incl. the limits and the domain error
+    std::uniform_real_distribution<double> W(-0.23, 0.23);
+    for (int i = 0; i < 400; i++) {
+      double p[3] = {W(gen), W(gen), W(gen)};
+      if (i == 0) { p[0] = -0.21; p[1] = 0.21; p[2] = 0.0; }
+      int64_t cell[3];
+      const int err = orc_find_cell(&og, p, cell);
+      CHECK((err != 0) == !env_vox.is_in_domain(p[0], p[1], p[2]));
+      try {
+        auto [ix, iy, iz] = env_vox.find_cell(collision::Point{p[0], p[1], p[2]});
+        CHECK(err == 0 && (int64_t)ix == cell[0] && (int64_t)iy == cell[1] && (int64_t)iz == cell[2]);
+        auto [bx, by, bz] = env_vox.find_block_idx(p[0], p[1], p[2]);
+        CHECK(bx == ix / 4 && by == iy / 4 && bz == iz / 4 && env_vox.find_block(p[0], p[1], p[2]) == env_vox.block(bx, by, bz));
+      } catch (const std::domain_error &) { CHECK(err != 0); }
+      auto [nx, ny, nz] = env_vox.nearest_cell(p[0], p[1], p[2]);
+      CHECK(nx < 128 && ny < 128 && nz < 128);
+      if (err == 0) CHECK((int64_t)std::min<size_t>(127, (size_t)cell[0]) == (int64_t)nx);
+      CHECK(env_vox.collides(collision::Point{p[0], p[1], p[2]}) == (err == 0 && env_vox.cell(nx, ny, nz)));
+    }
+    {  // voxel centres are where add_sphere tests them; a point at a centre lands in that cell
+      auto c = env_vox.voxel_center(17, 5, 100);
+      auto [ix, iy, iz] = env_vox.find_cell(c);
+      CHECK(ix == 17 && iy == 5 && iz == 100);
+      auto bc = env_vox.block_center(3, 4, 5);
+      auto [bx, by, bz] = env_vox.find_block_idx(bc[0], bc[1], bc[2]);
+      CHECK(bx == 3 && by == 4 && bz == 5);
+    }
+    // add_line == the oracle's add_line; set algebra against the same operations done block by block
+    VO a = env_vox.empty_copy(), b = env_vox.empty_copy();
+#ifdef IRT_TEST_OVER_STANDIN
+    {  // add_line(a, b) = one segment of add_piecewise_line, long segments that also leave the grid.  Host-logic
+       // build only: on the GPU box add_piecewise_line is exercised with real backbones above.
+      VO l = env_vox.empty_copy();
+      orc_octree *ol = orc_octree_new(&og);
+      for (int i = 0; i < 20; i++) {
+        collision::Point p{W(gen), W(gen), W(gen)}, q{W(gen), W(gen), W(gen)};
+        l.add_line(p, q);
+        orc_octree_add_line(ol, p.data(), q.data());
+      }
+      CHECK((int64_t)l.nblocks() == orc_octree_nblocks(ol) && (int64_t)l.ncells() == orc_octree_ncells(ol));
+      l.visit_leaves([&](size_t bx, size_t by, size_t bz, uint64_t v) { CHECK(orc_octree_block(ol, bx, by, bz) == v); });
+      orc_octree_free(ol);
+    }
+#endif
+    for (int i = 0; i < 600; i++) {   // two overlapping random sets, built on the host
+      const size_t x = gen() % 12, y = gen() % 12, z = gen() % 12;
+      a.union_block(x, y, z, gen() & gen());
+      b.union_block((x + i % 2) % 12, y, z, gen() & gen());
+    }
+    VO inter = a, diff = a, uni = a;
+    inter.intersect(b); diff.remove(b); uni.add(b);
+    size_t n_i = 0, n_d = 0, n_u = 0;
+    uni.visit_leaves([&](size_t bx, size_t by, size_t bz, uint64_t v) {
+      const uint64_t x = a.block(bx, by, bz), y = b.block(bx, by, bz);
+      CHECK(v == (x | y) && inter.block(bx, by, bz) == (x & y) && diff.block(bx, by, bz) == (x & ~y));
+      n_u += 1; n_i += (x & y) != 0; n_d += (x & ~y) != 0;
+    });
+    CHECK(inter.nblocks() == n_i && diff.nblocks() == n_d && uni.nblocks() == n_u && n_i > 0 && n_d > 0);
+    CHECK(inter.collides(b) && !diff.collides(b) && !(a == b) && a == a);
+    // set_cell's return value as the reference computes it; intersect / subtract_block return the old value
+    VO s8(8);
+    CHECK(!s8.set_cell(5, 0, 6) && s8.set_cell(5, 0, 6) && s8.cell(5, 0, 6) && s8.block(1, 0, 1) == VO::bitmask(1, 0, 2));
+    CHECK(!s8.set_cell(5, 0, 6, false) && s8.is_empty());          // no OTHER bit was set in that block
+    s8.set_block(1, 1, 0, 0xff);
+    CHECK(s8.intersect_block(1, 1, 0, 0x0f) == 0xff && s8.subtract_block(1, 1, 0, 0x03) == 0x0f && s8.block(1, 1, 0) == 0x0c);
+    s8.remove_point(0.6, 0.6, 0.1);                                   // cell (4,4,0) = bit 0 of block (1,1,0): not set
+    CHECK(s8.block(1, 1, 0) == 0x0c);
+    // visit_blocks: octant order, one call per absent child (TreeNode.hxx:193-208)
+    std::vector<std::array<uint64_t, 4>> seen;
+    s8.visit_blocks([&](size_t x, size_t y, size_t z, uint64_t v) { seen.push_back({x, y, z, v}); });
+    CHECK(seen.size() == 8 && seen[6] == (std::array<uint64_t, 4>{1, 1, 0, 0x0c}) && seen[1] == (std::array<uint64_t, 4>{0, 0, 1, 0}));
+    VO s16(16);
+    s16.set_cell(9, 2, 13);   // block (2,0,3): octant (1,0,1) of the root, child (0,0,1) inside it
+    seen.clear();
+    s16.visit_blocks([&](size_t x, size_t y, size_t z, uint64_t v) { seen.push_back({x, y, z, v}); });
+    CHECK(seen.size() == 7 + 8);                                       // 7 absent octants + the 8 blocks of the present one
+    CHECK(seen[5] == (std::array<uint64_t, 4>{2, 0, 2, 0}) && seen[6] == (std::array<uint64_t, 4>{2, 0, 3, VO::bitmask(1, 2, 1)}));
+    size_t nvox = 0, nocc = 0;
+    s16.visit_voxels([&](size_t, size_t, size_t, bool o) { nvox++; nocc += o; });
+    CHECK(nvox == 15 * 64 && nocc == 1);
+    s16.visit_occupied_voxels([&](size_t x, size_t y, size_t z) { CHECK(x == 9 && y == 2 && z == 13); });
+    VO s4(4);
+    seen.clear();
+    s4.visit_blocks([&](size_t x, size_t y, size_t z, uint64_t v) { seen.push_back({x, y, z, v}); });
+    CHECK(seen.size() == 1 && seen[0][3] == 0);
+    try { s4.erode_sphere(0.1); CHECK(false); } catch (const std::runtime_error &) {}
   }
   try { collision::VoxelOctree bad(100); CHECK(false); } catch (const std::invalid_argument &) {}
   try { collision::VoxelOctree(64).collides(env_vox); CHECK(false); } catch (const std::invalid_argument &) {}

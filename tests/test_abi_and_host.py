@@ -195,7 +195,7 @@ def test_cpp_host_mirror_host_logic(tmp_path, orc):
     batched Jacobians."""
     exe = str(tmp_path / "test_host_mirror_cpu")
     cpp = os.path.join(ROOT, "tests", "cpp")
-    subprocess.check_call(["g++", "-std=c++17", "-O1", "-Wall", "-Wextra", "-Werror",
+    subprocess.check_call(["g++", "-std=c++17", "-O1", "-Wall", "-Wextra", "-Werror", "-DIRT_TEST_OVER_STANDIN",
                            os.path.join(cpp, "test_host_mirror.cpp"),
                            os.path.join(cpp, "abi_standin_over_oracle.cpp"), "-o", exe,
                            "-L" + os.path.join(ROOT, "oracle"), "-loracle",
