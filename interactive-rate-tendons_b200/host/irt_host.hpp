@@ -1065,6 +1065,12 @@ public:
                                         estore_, eflags_.data(), nullptr, nullptr));
   }
   void precomputeVoxelCache() { precomputeVertexVoxelCache(); precomputeEdgeVoxelCache(); }
+  /// clear*VoxelCache (.cpp:1814-1829): drop the cached sets; validity words stay, like the reference's
+  void clearVertexVoxelCache() { clear_store(vstore_); vflags_.clear(); tips_.clear(); }
+  void clearEdgeVoxelCache() { clear_store(estore_); eflags_.clear(); }
+  void clearVoxelCache() { clearVertexVoxelCache(); clearEdgeVoxelCache(); }
+  size_t vertexVoxelCacheSize() const { return (size_t)irt_setstore_num_sets(vstore_); }
+  size_t edgeVoxelCacheSize() const { return (size_t)irt_setstore_num_sets(estore_); }
   void precomputeVertexValidity() {  // .cpp:1563-1598 with warm caches
     if (vflags_.size() != states_.size()) precomputeVertexVoxelCache();
     sweep(vstore_, vflags_, IRT_FLAG_NONCONVERGED | IRT_FLAG_LENGTH_LIMIT | IRT_FLAG_SELF_COLLISION | IRT_FLAG_BAD_STATE,
@@ -1093,6 +1099,12 @@ public:
   const std::vector<uint32_t> &edgeFlags() const { return eflags_; }
 
 private:
+  void clear_store(irt_setstore *st) {
+    const uint64_t off = 0;
+    const uint32_t key = 0;
+    const uint64_t bits = 0;
+    irt::check(ctx_, irt_setstore_import(ctx_, st, 0, &off, &key, &bits));
+  }
   /// exact k nearest of v among all milestones (v included, like nn_->nearestK), cut at the range
   std::vector<size_t> nearestKBounded(size_t v) const {
     std::vector<std::pair<double, size_t>> d(states_.size());

@@ -6,7 +6,7 @@ Mirrors the batch entry points of the reference planner (motion-planning/VoxelCa
   createRoadmap(N, ...)            VoxelCachedLazyPRM.cpp:1380-1561 (sampling + voxel caches)
   precomputeVertexVoxelCache()     :1687-1734     precomputeEdgeVoxelCache()   :1736-1782
   precomputeVertexValidity()       :1563-1598     precomputeEdgeValidity()     :1600-1647
-  clearValidity()                  :1656-1663
+  clearValidity()                  :1656-1663     clear{Vertex,Edge}VoxelCache() :1814-1829
 
 The graph search, nearest-neighbour structures, IK and file formats of the reference planner
 stay on the host and are not re-implemented here; the roadmap is (states, edge index pairs).
@@ -257,6 +257,24 @@ class VoxelCachedLazyPRM:
     def precomputeVoxelCache(self):
         self.precomputeVertexVoxelCache()
         self.precomputeEdgeVoxelCache()
+
+    def clearVertexVoxelCache(self):
+        """clearVertexVoxelCache (VoxelCachedLazyPRM.cpp:1814-1818): the cached sets go, validity words stay"""
+        self.vertex_store = SetStore(self.ctx, self.grid)
+        self.vertex_flags = self.tips = None
+        self._have_vcache = False
+        self._xchg = {k: v for k, v in self._xchg.items() if k[0] == id(self.edge_store)}
+
+    def clearEdgeVoxelCache(self):
+        """clearEdgeVoxelCache (VoxelCachedLazyPRM.cpp:1820-1824)"""
+        self.edge_store = SetStore(self.ctx, self.grid)
+        self.edge_flags = None
+        self._have_ecache = False
+        self._xchg = {k: v for k, v in self._xchg.items() if k[0] == id(self.vertex_store)}
+
+    def clearVoxelCache(self):
+        self.clearVertexVoxelCache()
+        self.clearEdgeVoxelCache()
 
     # ---- environment ------------------------------------------------------------------------
     def setEnvironment(self, blocks):

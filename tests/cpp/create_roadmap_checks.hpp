@@ -71,6 +71,14 @@ static void check_create_roadmap(const tendon::TendonRobot &robot, const motion_
   for (size_t i = 0; i < 150; i++) CHECK(rm.vertexValidity()[i] == (i < 120 ? PRM::VALIDITY_TRUE : PRM::VALIDITY_UNKNOWN));
   for (size_t i = 0; i < rm.edges().size(); i++)
     CHECK(rm.edgeValidity()[i] == (i < edges0.size() ? PRM::VALIDITY_TRUE : PRM::VALIDITY_UNKNOWN));
+  // clear*VoxelCache (.cpp:1814-1829): the sets go, the validity words stay; the next sweep rebuilds the caches
+  rm.clearVoxelCache();
+  CHECK(rm.vertexVoxelCacheSize() == 0 && rm.edgeVoxelCacheSize() == 0 && rm.vertexFlags().empty());
+  CHECK(rm.vertexValidity()[0] == PRM::VALIDITY_TRUE && rm.edgeValidity()[0] == PRM::VALIDITY_TRUE);
+  rm.precomputeValidity();
+  CHECK(rm.vertexVoxelCacheSize() == 150 && rm.edgeVoxelCacheSize() == rm.edges().size());
+  for (size_t i = 0; i < 120; i++) CHECK(rm.vertexValidity()[i] == PRM::VALIDITY_TRUE);
+  for (size_t i = 0; i < edges0.size(); i++) CHECK(rm.edgeValidity()[i] == PRM::VALIDITY_TRUE);
   // a lazy roadmap from scratch touches no kernel-side state: no caches, nothing validated
   PRM lazy(robot, venv, env_vox);
   lazy.createRoadmap(40);

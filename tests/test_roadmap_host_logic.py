@@ -121,6 +121,14 @@ def test_create_roadmap_options_host_logic(orc, wl, monkeypatch):
     assert np.all(prm.vertex_validity[:n] == R.VALIDITY_TRUE) and not prm.vertex_validity[n:].any()
     assert np.all(prm.edge_validity[:len(edges0)] == R.VALIDITY_TRUE) and not prm.edge_validity[len(edges0):].any()
     assert prm.vertex_store.num_sets == n + 40 and prm.edge_store.num_sets == len(prm.edges)
+    # clear*VoxelCache: the sets go, the validity words stay; the next sweep rebuilds the caches it needs
+    vv0, ev0 = prm.vertex_validity.copy(), prm.edge_validity.copy()
+    prm.clearVoxelCache()
+    assert prm.vertex_store.num_sets == 0 and prm.edge_store.num_sets == 0 and prm.vertex_flags is None
+    assert np.array_equal(prm.vertex_validity, vv0) and np.array_equal(prm.edge_validity, ev0)
+    prm.precomputeValidity()
+    assert prm.vertex_store.num_sets == n + 40 and prm.edge_store.num_sets == len(prm.edges)
+    assert np.all(prm.vertex_validity[:n] == R.VALIDITY_TRUE) and np.all(prm.edge_validity[:len(edges0)] == R.VALIDITY_TRUE)
     # every new edge has a new vertex as its source and none is a duplicate
     new = prm.edges[len(edges0):]
     assert np.all(new[:, 0] >= n) and len(set(map(tuple, np.sort(prm.edges, axis=1).tolist()))) == len(prm.edges)
