@@ -521,11 +521,7 @@ fk_rk4_fp64_kernel(const RobotDev rb, const double *__restrict__ states, int sta
   double hh0 = 0.0, hh1 = 0.0;
   const double *hd0 = head, *hd1 = head + NT * 6, *hd2 = head + 2 * NT * 6, *hd3 = head + 3 * NT * 6;
   double rt_h1[NT * 6], rt_h2[NT * 6], rt_h3[NT * 6];
-#ifdef EXP_NO_HEAD
-  if (false) {
-#else
   if (integ) {
-#endif
     if (RETRACT) {
       const double eps = 2.220446049250313e-16;
       const double t1 = rb.node_t[K - 1];
@@ -554,11 +550,7 @@ fk_rk4_fp64_kernel(const RobotDev rb, const double *__restrict__ states, int sta
 #pragma unroll 1
     for (int j = 0; j < Tmax; j++) {
       const int q = Tmax - j;  // regular step q: node q -> node q-1 (1 <= q <= K-1)
-#ifdef EXP_NO_HEAD
-      if (!integ || q > K - 1) continue;
-#else
       if (!integ || q > K - 1 + nhead) continue;
-#endif
       const double *p0, *p1, *p2;
       double h;
       int emit_idx;
