@@ -261,7 +261,10 @@ def run_reference(args, rank, world):
             rates.append((r, done, el))
     value = float(np.mean([r for r, _, _ in rates]))
     done = int(np.mean([d for _, d, _ in rates]))
-    own_text = cpu_fk_rate_reference_text(spec, nt, 4.0)
+    try:
+        own_text = cpu_fk_rate_reference_text(spec, nt, 4.0)
+    except Exception as e:      # informational figure: never lose the reference line over it
+        own_text = {"error": repr(e)[:200]}
     line = {
         "impl": "reference", "metric": "fk_shapes_per_s", "value": value, "unit": "shapes/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
