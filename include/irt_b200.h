@@ -172,7 +172,8 @@ int irt_fk_batch_packed(irt_ctx *ctx, const irt_robot *rb, const double *states,
  * J[(k*3+i)*S + j], levmar's jac[i*m+j] layout), tips is [n][3] (may be NULL): the value the
  * differences are taken from.  One K1 launch over n*(S+1) or n*(2S+1) states.
  *   IRT_JAC_FORWARD_FIXED   tip_control::Jacobian (tip-control/tip_control.cpp:243-265):
- *                           (fk(state + delta e_j).back() - tip) / delta
+ *                           (fk(state + delta e_j).back() - tip) / delta; the reference's `dist` is a C float
+ *                           promoted to double, so pass delta = (double)(float)dist for the same step
  *   IRT_JAC_LEVMAR_FORWARD  levmar-2.6 dlevmar_fdif_forw_jac_approx (3rdparty/levmar-2.6/misc_core.c:137-172)
  *   IRT_JAC_LEVMAR_CENTRAL  dlevmar_fdif_cent_jac_approx (misc_core.c:175-211), the form
  *                           tip_control::inverse_kinematics_impl asks for (tip_control.cpp:85)

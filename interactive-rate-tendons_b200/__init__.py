@@ -384,7 +384,9 @@ class Robot:
         """Finite-difference tip Jacobians of every row of `states` in one FK batch: returns
         (tips [n][3], J [n][3][S]).  mode: JAC_FORWARD_FIXED = tip_control::Jacobian
         (tip-control/tip_control.cpp:243-265); JAC_LEVMAR_FORWARD / JAC_LEVMAR_CENTRAL = the rule of
-        levmar-2.6 behind tip_control::inverse_kinematics (misc_core.c:137-211)."""
+        levmar-2.6 behind tip_control::inverse_kinematics (misc_core.c:137-211).
+        tip_control::Jacobian takes its step as a C `float`: pass delta=float(np.float32(dist)) to take exactly
+        the step the reference takes (oracle == the reference's own text bit for bit with that step)."""
         states = _np(states, np.float64)
         if states.ndim != 2:
             raise IrtError(IRT_ERR_INVALID_ARGUMENT, "states must be [n][S]")

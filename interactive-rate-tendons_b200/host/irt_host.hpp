@@ -329,6 +329,25 @@ inline std::vector<std::vector<double>> Jacobian_batch(const tendon::TendonRobot
   return out;
 }
 
+/// tip_control::Jacobian with the reference's own signature (tip_control.cpp:243-265): forward differences
+/// from the CALLER'S ps with a step that is a C `float` (tau[i] + dist and the division promote it to
+/// double, so the step really taken is double(float(dist))).  One FK batch of S perturbed states; J is
+/// returned row-major 3 x S (the reference returns an Eigen::MatrixXd with J(j, i) at the same place).
+/// For the batched form above pass double(float(dist)) to take the same step.
+inline std::vector<double> Jacobian(const tendon::TendonRobot &robot, const collision::Point &ps, float dist,
+                                    const std::vector<double> &tau) {
+  const size_t S = tau.size();
+  std::vector<std::vector<double>> pert(S, tau);
+  for (size_t i = 0; i < S; i++) pert[i][i] = tau[i] + dist;
+  auto shapes = robot.shape_batch(pert);
+  std::vector<double> J(3 * S);
+  for (size_t i = 0; i < S; i++) {
+    const collision::Point pos = shapes[i].p.back();
+    for (size_t j = 0; j < 3; j++) J[j * S + i] = (pos[j] - ps[j]) / dist;
+  }
+  return J;
+}
+
 /// the Jacobian levmar's dlevmar_bc_dif builds inside tip_control::inverse_kinematics
 /// (central differences, d = max(|1e-4 p_j|, delta); tip_control.cpp:85, levmar-2.6 misc_core.c:175-211)
 inline std::vector<std::vector<double>> levmar_jacobian_batch(const tendon::TendonRobot &robot, double delta,

@@ -668,6 +668,15 @@ class RefTendonRobot:
                             npts.ctypes.data_as(C.POINTER(C.c_int)))
         return tips, npts
 
+    def tip_jacobian(self, state, ps, dist):
+        """tip_control::Jacobian(robot, ps, dist, state) (tip-control/tip_control.cpp:243-265), its own text;
+        `dist` is a C float there.  Returns J as [3][S]."""
+        state = np.ascontiguousarray(state, dtype=np.float64)
+        ps = np.ascontiguousarray(ps, dtype=np.float64)
+        J = np.zeros((3, len(state)))
+        self.lib().trref_tip_jacobian(*self._args(), _dp(state), _dp(ps), C.c_float(dist), _dp(J))
+        return J
+
     def home_lengths(self, state):
         state = np.ascontiguousarray(state, dtype=np.float64)
         out = np.zeros(self.N)

@@ -13,6 +13,7 @@
 //   tr_B.inc   TendonRobot::is_valid, TendonRobot::collides_self               (:955-974)
 //   tr_rot.inc TendonResult::rotate_z                                          (TendonResult.cpp:13-18)
 //   tr_deg.inc poly_degree, TendonSpecs::r_degree / theta_degree               (TendonSpecs.cpp:8-30)
+//   tr_jac.inc tip_control::Jacobian                                          (tip-control/tip_control.cpp:243-265)
 //   sc_*.inc   Sphere / Capsule / CapsuleSequence, the inline collides overloads, collides_self
 //              (as for libselfcol_ref.so)
 // against TWO stand-ins: Eigen (eigen_standin/) and Boost.odeint (odeint_standin/): read their headers for
@@ -54,6 +55,13 @@ namespace collision {
 #include "tr_rot.inc"
 #include "tr_deg.inc"
 }  // namespace tendon
+
+// tip_control::Jacobian (tip-control/tip_control.cpp:243-265), cut out by anchors (tr_jac.inc): the
+// forward-difference tip Jacobian of the resolved-rate controllers -- note its `float dist`
+namespace tip_control {
+namespace E = Eigen;
+#include "tr_jac.inc"
+}  // namespace tip_control
 
 namespace {
 
@@ -127,6 +135,17 @@ void trref_shape_batch(const double *hdr, int N, int Nc, int Nd, const double *C
     npts[i] = (int)res.p.size();
     for (int k = 0; k < 3; k++) tips[3 * i + k] = res.p.empty() ? 0.0 : res.p.back()[k];
   }
+}
+
+// tip_control::Jacobian(robot, ps, dist, tau): J is written row-major 3 x S (J[j * S + i] = J(j, i))
+void trref_tip_jacobian(const double *hdr, int N, int Nc, int Nd, const double *C, const double *D,
+                        const double *lim, const double *state, const double *ps, float dist, double *J) {
+  tendon::TendonRobot rb = make_robot(hdr, N, Nc, Nd, C, D, lim);
+  const size_t S = rb.state_size();
+  std::vector<double> st(state, state + S);
+  Eigen::MatrixXd Jm = tip_control::Jacobian(rb, Eigen::Vector3d(ps[0], ps[1], ps[2]), dist, st);
+  for (size_t j = 0; j < 3; j++)
+    for (size_t i = 0; i < S; i++) J[j * S + i] = Jm(j, i);
 }
 
 // home_shape(state).L_i

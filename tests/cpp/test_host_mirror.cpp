@@ -388,6 +388,19 @@ int main() {
     }
   }
 
+  {  // tip_control::Jacobian with the reference's signature: caller's ps, float step (tip_control.cpp:243-265)
+    for (int i = 0; i < 6; i++) {
+      const float dist = i % 2 ? 1e-3f : 1e-4f;
+      double tip[3], J[3 * 8];
+      orc_tip_jacobian(&orb, states[i].data(), 0, (double)dist, tip, J);
+      auto Jm = tip_control::Jacobian(robot, collision::Point{tip[0], tip[1], tip[2]}, dist, states[i]);
+      for (int c = 0; c < 24; c++) CHECK(std::fabs(Jm[c] - J[c]) < 2e-9 * robot.specs.L / dist);
+      // a shifted ps shifts every column by -shift / dist
+      auto Js = tip_control::Jacobian(robot, collision::Point{tip[0] + 1e-3, tip[1], tip[2]}, dist, states[i]);
+      for (int c = 0; c < 8; c++) CHECK(std::fabs((Js[c] - Jm[c]) + 1e-3 / dist) < 1e-6 / dist);
+    }
+  }
+
   orc_octree_free(oenv);
   std::printf(failures ? "FAILED (%d)\n" : "host mirror ok\n", failures);
   return failures ? 1 : 0;

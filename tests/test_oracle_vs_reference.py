@@ -567,3 +567,24 @@ def test_reference_batch_loop_is_a_sound_timing_baseline(orc, wl):
     assert np.array_equal(npts, want["npts"]) and np.array_equal(tips, want["tip"])
     tips_r, npts_r = rr.shape_batch(st, nthreads=2, release=True)
     assert np.array_equal(npts_r, want["npts"]) and np.abs(tips_r - want["tip"]).max() < 1e-12 * spec["L"]
+
+
+@pytest.mark.skipif(not ref.RefTendonRobot.available(), reason="oracle/_ref/libtendonrobot_ref.so not built")
+@pytest.mark.parametrize("name", ["a005", "b003rot"])
+def test_live_tip_control_jacobian(orc, wl, name):
+    """tip_control::Jacobian (tip-control/tip_control.cpp:243-265), the reference's own text: forward
+    differences from the caller's ps with a step that is a C `float` there.  The oracle's mode 0
+    (IRT_JAC_FORWARD_FIXED) with delta = double(float(dist)) is bit-exact; with the unrounded double step it
+    differs at the 1e-8 level, which is why the mirrors round the step the way the reference's signature does."""
+    spec = {"a005": wl.robot_a(0.005), "b003rot": wl.robot_b(0.003, rotation=True)}[name]
+    rb, rr = orc.robot(spec), ref.RefTendonRobot(spec)
+    worst_unrounded = 0.0
+    for st in wl.sample_states(spec, 12, stream=91):
+        for dist in (1e-3, 1e-4, 0.01):
+            d32 = float(np.float32(dist))
+            tip, J = orc.tip_jacobian(rb, st, 0, d32)
+            Jr = rr.tip_jacobian(st, tip, dist)
+            assert np.array_equal(J, Jr), (name, dist)
+            _, Ju = orc.tip_jacobian(rb, st, 0, dist)
+            worst_unrounded = max(worst_unrounded, float(np.abs(Ju - Jr).max() / max(1e-300, np.abs(Jr).max())))
+    assert 0 < worst_unrounded < 1e-5
