@@ -16,6 +16,8 @@ TEST INFRASTRUCTURE ONLY (same rule as oracle/oracle.py).
 * liblevmar_ref.so: the levmar-2.6 the reference vendors (without LAPACK).
 * libtendonrobot_ref.so: TendonRobot::shape / home_shape / is_valid (tension_shape cut out by anchors).
 * librmp_ref.so: the .rmp writer and reader (RmpStreamer, LazyRmpParser) of VoxelCachedLazyPRM.cpp.
+* libik_ref.so: tip_control::inverse_kinematics (inverse_kinematics_impl, Bounds) over the vendored levmar;
+  libtendonrobot_ref.so also carries tip_control::Jacobian.
 
 All are built by `make -C oracle ref` only where /root/reference exists; they travel to the GPU box
 as prebuilt files.  Nothing here is needed at run time by the product.
@@ -676,6 +678,30 @@ class RefTendonRobot:
         J = np.zeros((3, len(state)))
         self.lib().trref_tip_jacobian(*self._args(), _dp(state), _dp(ps), C.c_float(dist), _dp(J))
         return J
+
+    _ik = None
+
+    @classmethod
+    def ik_available(cls):
+        return os.path.exists(os.path.join(REF_DIR, "libik_ref.so"))
+
+    def inverse_kinematics(self, initial_state, des, max_iters=100, mu_init=1e-3, stop_JT_err_inf=1e-9,
+                           stop_Dp=1e-4, stop_err=1e-4, fd_delta=1e-6):
+        """tip_control::inverse_kinematics over the robot's own forward_kinematics (tip_control.cpp:29-153,
+        160-184, 347-368 without the printing), its own text, driving the reference's vendored levmar.
+        Returns dict(state, tip, error, iters, num_fk_calls, info[10])."""
+        cls = type(self)
+        if cls._ik is None:
+            cls._ik = C.CDLL(os.path.join(REF_DIR, "libik_ref.so"))
+            cls._ik.trref_inverse_kinematics.restype = C.c_int
+        s0 = np.ascontiguousarray(initial_state, dtype=np.float64)
+        des = np.ascontiguousarray(des, dtype=np.float64)
+        opts = np.array([max_iters, mu_init, stop_JT_err_inf, stop_Dp, stop_err, fd_delta], dtype=np.float64)
+        state, tip, misc, info = np.zeros(len(s0)), np.zeros(3), np.zeros(3), np.zeros(10)
+        rc = cls._ik.trref_inverse_kinematics(*self._args(), _dp(s0), _dp(des), _dp(opts), _dp(state), _dp(tip),
+                                              _dp(misc), _dp(info))
+        assert rc == 0, "the reference's inverse_kinematics threw"
+        return dict(state=state, tip=tip, error=misc[0], iters=int(misc[1]), num_fk_calls=int(misc[2]), info=info)
 
     def home_lengths(self, state):
         state = np.ascontiguousarray(state, dtype=np.float64)

@@ -588,3 +588,44 @@ def test_live_tip_control_jacobian(orc, wl, name):
             _, Ju = orc.tip_jacobian(rb, st, 0, dist)
             worst_unrounded = max(worst_unrounded, float(np.abs(Ju - Jr).max() / max(1e-300, np.abs(Jr).max())))
     assert 0 < worst_unrounded < 1e-5
+
+
+@levmar
+@pytest.mark.skipif(not ref.RefTendonRobot.ik_available(), reason="oracle/_ref/libik_ref.so not built")
+@pytest.mark.parametrize("name", ["b005", "b005rot"])
+def test_live_inverse_kinematics_own_text(orc, wl, name):
+    """tip_control::inverse_kinematics compiled from the reference's OWN text (inverse_kinematics_impl with its
+    levmar options, fk_wrap and its (0, 0, L - s) branch, Bounds::from_robot, canonical_angle; the robot's own
+    forward_kinematics underneath) against the driver as the tests restate it (dlevmar_bc_dif over the ORACLE's
+    FK with the same options and bounds): same iteration / FK-call counts; solution and levmar info bit for bit
+    without rotation, to 1e-6 with it."""
+    spec = wl.robot_b(0.005, rotation=(name == "b005rot"))
+    rb, rr = orc.robot(spec), ref.RefTendonRobot(spec)
+    L, N, S = spec["L"], 6, wl.state_size(spec)
+    f = _fk_wrap(orc, rb, L)
+    lb, ub = np.zeros(S), np.zeros(S)
+    ub[:N] = 20.0
+    if spec.get("enable_rotation"):
+        lb[N], ub[N] = np.finfo(np.float64).min, np.finfo(np.float64).max      # Bounds::from_robot
+    ub[-1] = L
+    step = np.zeros(S)
+    step[:N] = [0.8, -0.5, 0.3, 0.6, -0.4, 0.2]
+    step[-1] = 0.004
+    if spec.get("enable_rotation"):
+        step[N] = 0.3
+    for s0 in wl.sample_states(spec, 4, stream=35):
+        des = f(np.clip(s0 + step, np.maximum(lb, -10), np.minimum(ub, 10)))
+        p, info, rc = ref.RefLevmar.bc_dif(f, s0, des, lb, ub, 100, [0.1, 1e-9, 1e-8, 1e-8, -1e-6])
+        got = rr.inverse_kinematics(s0, des, 100, 0.1, 1e-9, 1e-4, 1e-4, 1e-6)
+        assert rc >= 0 and got["iters"] == int(info[5]) and got["num_fk_calls"] == int(info[7])
+        want_state = p.copy()
+        if not spec.get("enable_rotation"):
+            assert np.array_equal(got["info"], info) and np.array_equal(got["state"], want_state)
+            assert np.array_equal(got["tip"], orc.shape(rb, p)["p"][-1]) and got["error"] == np.sqrt(info[1])
+        else:
+            # rotate_z is the one place where the own text and the oracle differ (by <= 2e-16: Eigen's AngleAxis
+            # forms the zz entry as (1 - c) + c); a hundred LM iterations carry that to ~1e-8
+            want_state[N] = (want_state[N] + np.pi) % (2 * np.pi) - np.pi          # util::canonical_angle
+            assert np.allclose(got["info"], info, rtol=1e-6, atol=0) and np.allclose(got["state"], want_state, rtol=1e-6, atol=1e-9)
+            assert np.allclose(got["tip"], orc.shape(rb, p)["p"][-1], rtol=0, atol=1e-9 * L)
+        assert info[1] < info[0] and got["iters"] > 1      # it did iterate and the tip error went down
