@@ -10,6 +10,15 @@ HBM.  The same run also measures the roadmap voxel check (K3) over a config-C4-s
 (1M valid vertices, exact k=17 nearest-neighbour edges, ~10M undirected edges) built with the real pipeline, the end-to-end FK rate through the host-pointer C ABI, and the CPU baseline
 (the oracle restatement of the reference, timed on this box's host cores).
 Prints ONE JSON line on rank 0.
+
+Keys beyond the base contract: `roofline` (K1: algorithmic FLOP / event-timed step against a live DFMA-chain
+peak), `cpu_baseline` (FK: the port on all host threads, + single thread, + under the reference's Release
+flags), `edge_check` (K3 sweep with its own HBM `roofline`, the K1+K2 build times and K2's unit-of-work figures
+-- FK samples / edge mean and p99, blocks and voxels / edge --, the C5 replanning tick, its own `cpu_baseline` =
+the reference's TreeNode::collides from oracle/_ref with `verdicts_equal_gpu`, and `k2_vs_oracle` = voxel flips
+and flag mismatches of the first 1000 cached edge sets against the oracle, counted).  `--impl reference` adds
+`reference_own_text` (the reference's TendonRobot::shape text over the Eigen / odeint stand-ins, for
+information).  Every reporting-only addition is guarded: it can fail without costing the line.
 """
 import argparse
 import json
