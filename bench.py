@@ -38,6 +38,16 @@ DL = 0.005
 WORKLOAD = "C2: 6-tendon helical robot, retraction (RetractionSampler), dL=0.005, 1M configs/GPU"
 
 
+def workload_config(spec_cap=41, state_size=7):
+    """the `config` object of BOTH arms (the driver compares them): the workload, not how an arm samples it"""
+    return {"workload": WORKLOAD, "n_configs_per_gpu": N_CONFIGS, "state_size": state_size,
+            "max_points": spec_cap, "seed": 20220801,
+            "step": "FK of every configuration + the validity epilogue is_valid_shape (converged, length limits, "
+                    "collides_self), AbstractValidityChecker.cpp:80-114",
+            "outputs": "p, npts, L, L_i, flags",
+            "l2": "read-only L2 flush (summing read of 512 MB) between timed steps; outputs (984 MB) exceed L2"}
+
+
 def flops_per_shape(n_tendons, mean_steps, mean_iters):
     """F_shape = n_steps * (4 * (346 + 162 N) + 13 (19 + N)) + iters * (30 + 46 N)"""
     N = n_tendons
@@ -92,7 +102,9 @@ class ClockSampler(threading.Thread):
 
 def cpu_fk_rate(spec, n_tendons, seconds, threads=None, stream=900, batch=20000, variant="fast"):
     """oracle (restatement of the reference CPU path, -O3 -march=native -fopenmp) timed on a
-    bounded sample of the SAME workload; loop shape = apps/estimate_length_discretization.cpp:62-71"""
+    bounded sample of the SAME workload; loop shape = apps/estimate_length_discretization.cpp:62-71.
+    The work per configuration is the GPU step's: TendonRobot::shape + is_valid_shape (the oracle's fk_batch
+    always evaluates the validity flags incl. collides_self).  Inputs are generated BEFORE the clock starts."""
     from oracle.oracle import Oracle, build
     import irt_b200.workloads as wl
     build()
@@ -105,12 +117,12 @@ def cpu_fk_rate(spec, n_tendons, seconds, threads=None, stream=900, batch=20000,
     except Exception:
         avail = os.cpu_count() or 1
     nt = threads or max(avail, orc.max_threads())
-    done, t0 = 0, time.perf_counter()
     cap = len(orc.t_range(0.0, spec["L"], spec["dL"]))
-    k = 0
+    pool = [wl.sample_states(spec, batch, stream=stream + k) for k in range(8)]   # untimed
+    orc.fk_batch(rb, pool[0][:max(256, nt * 8)], cap, nthreads=nt)                 # warm-up (thread pool, pages)
+    done, k, t0 = 0, 0, time.perf_counter()
     while True:
-        st = wl.sample_states(spec, batch, stream=stream + k)
-        orc.fk_batch(rb, st, cap, nthreads=nt)
+        orc.fk_batch(rb, pool[k % len(pool)], cap, nthreads=nt)
         done += batch
         k += 1
         el = time.perf_counter() - t0
@@ -280,10 +292,11 @@ def run_reference(args, rank, world):
         "ms_per_step": 1e3 * float(np.mean([e for _, _, e in rates])),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic",
-        "config": {"workload": WORKLOAD, "n_configs_per_step": done,
-                   "note": "bounded sample of the same workload per step"},
+        "config": workload_config(),
         "cpu_baseline": {"value": value, "unit": "shapes/s", "cores": nt, "kind": "port",
-                         "sample": "%d configs per step (~%.0f s), OpenMP over configs" % (done, per_step)},
+                         "sample": "%d configs of the workload per step (~%.0f s of %d threads; ms_per_step is that "
+                                   "sample's time, not a 1M-config step), OpenMP over configs; work per config = "
+                                   "TendonRobot::shape + is_valid_shape" % (done, per_step, nt)},
         "e2e": {"value": value, "unit": "shapes/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     if own_text:
@@ -379,63 +392,89 @@ def main():
                 npts=torch.zeros(n, dtype=torch.int32, device=dev),
                 L=torch.zeros(n, dtype=torch.float64, device=dev),
                 L_i=torch.zeros(n, rb.n_tendons, dtype=torch.float64, device=dev),
+                flags=torch.zeros(n, dtype=torch.int32, device=dev),
                 iters=torch.zeros(n, dtype=torch.int32, device=dev),
                 nsteps=torch.zeros(n, dtype=torch.int32, device=dev))
+    outs_fk_only = {k: v for k, v in outs.items() if k != "flags"}
     flush = torch.empty(512 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
+    flush.zero_()
+    flush_i64 = flush.view(torch.int64)
 
-    def fk_step():
+    def l2_flush():
+        """read-only flush: a summing read of 512 MB leaves the L2 full of CLEAN lines of an unrelated buffer (a
+        flush WRITE would leave ~100 MB of dirty lines whose write-back competes with the next kernel's
+        traffic).  The same rule for every timed loop, every N and both exchange variants."""
+        return flush_i64.sum()
+
+    def fk_step():         # the headline step: FK + validity epilogue (what the CPU arm computes per config)
         rb.shape_batch_dev(d_states, n, outs, stream=sptr)
 
-    for _ in range(args.warmup):
-        flush.zero_()
-        fk_step()
-    barrier()
+    def fk_only_step():    # FK without the epilogue (no flags requested: the self-collision kernels do not run)
+        rb.shape_batch_dev(d_states, n, outs_fk_only, stream=sptr)
+
+    def time_steps(step):
+        for _ in range(args.warmup):
+            l2_flush()
+            step()
+        barrier()
+        l0 = ctx.launch_count()
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+        t0 = time.perf_counter()
+        for a, b in ev:
+            l2_flush()           # between timed iterations, outside the event pair
+            a.record(stream)
+            step()
+            b.record(stream)
+        barrier()
+        wall = time.perf_counter() - t0
+        return float(np.mean([a.elapsed_time(b) for a, b in ev])), ctx.launch_count() - l0, wall
+
+    ms_fkonly_local, _, _ = time_steps(fk_only_step)
     sampler = ClockSampler(local_rank)
     sampler.start()
-    launches0 = ctx.launch_count()
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    t_wall0 = time.perf_counter()
-    for a, b in ev:
-        flush.zero_()            # L2 flush between timed iterations (outside the event pair)
-        a.record(stream)
-        fk_step()
-        b.record(stream)
-    barrier()
-    t_wall = time.perf_counter() - t_wall0
-    launches = ctx.launch_count() - launches0
+    ms_local, launches, t_wall = time_steps(fk_step)
     sampler.stop_flag = True
     sampler.join()
-    ms_local = float(np.mean([a.elapsed_time(b) for a, b in ev]))
     ms = max_over_ranks(ms_local)
+    ms_fkonly = max_over_ranks(ms_fkonly_local)
     value = world * n / (ms * 1e-3)
     mean_steps = float(outs["nsteps"].double().mean().item())
     mean_iters = float(outs["iters"].double().mean().item())
+    valid_fraction = float((outs["flags"] == 0).double().mean().item())
     fshape = flops_per_shape(rb.n_tendons, mean_steps, mean_iters)
     achieved = n * fshape / (ms_local * 1e-3) / 1e12
+    achieved_fkonly = n * fshape / (ms_fkonly_local * 1e-3) / 1e12
     prof = {}
     try:
         with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
             prof = json.load(f)
     except Exception:
         pass
+    peak_tf = fp64_peak / 1e12
     roofline = {"bound": "fp64", "kernel": "fk_rk4_fp64_kernel<6,true>", "achieved": achieved,
-                "peak": fp64_peak / 1e12, "unit": "TFLOP/s", "frac": achieved / (fp64_peak / 1e12),
+                "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf,
                 "traffic": prof.get("fk_dram_bytes_per_launch"),
-                "peak_source": "live DFMA-chain probe on this GPU (MEASURED_PEAKS.json has no FP64 entry)",
+                "peak_source": "live DFMA-chain probe on this GPU (MEASURED_PEAKS.json has no FP64 entry; "
+                               "profiles/ holds the probe's ncu line)",
                 "flop_per_shape": fshape, "mean_rk4_steps": mean_steps, "mean_fixed_point_iters": mean_iters,
-                "note": "duration = whole step (2 bucket-sort launches + the RK4 kernel)"}
+                "note": "duration = the whole step: 2 bucket-sort launches + the RK4 kernel + the 2 self-collision "
+                        "launches of the validity epilogue; the algorithmic FLOP (SURVEY 8d) count the FK only, so "
+                        "the epilogue is pure overhead in this fraction",
+                "fk_only": {"ms_per_step": ms_fkonly, "value": world * n / (ms_fkonly * 1e-3),
+                            "achieved": achieved_fkonly, "frac": achieved_fkonly / peak_tf,
+                            "note": "same step without flags (FK kernels only), for comparison with round 1"}}
 
     # ---------------- e2e: host-pointer C ABI, pinned buffers, H2D + D2H inside ----------------
+    import ctypes as C
     h_states = torch.from_numpy(states).pin_memory()
     h_out = dict(p=torch.zeros(n, cap, 3, dtype=torch.float64).pin_memory(),
                  npts=torch.zeros(n, dtype=torch.int32).pin_memory(),
                  L=torch.zeros(n, dtype=torch.float64).pin_memory(),
-                 L_i=torch.zeros(n, rb.n_tendons, dtype=torch.float64).pin_memory())
+                 L_i=torch.zeros(n, rb.n_tendons, dtype=torch.float64).pin_memory(),
+                 flags=torch.zeros(n, dtype=torch.int32).pin_memory())
     o = irt_b200.FkOutputs()
     for kname, t in h_out.items():
         setattr(o, kname, t.data_ptr())
-    import ctypes as C
-
     h_rowoff = torch.zeros(n + 1, dtype=torch.int64).pin_memory()
 
     def e2e_step():      # packed rows: TendonResult's per-shape vectors laid end to end (the public call)
@@ -444,6 +483,13 @@ def main():
 
     def e2e_dense_step():  # dense [n][max_points] rows, zero padded
         ctx.check(ctx.L.irt_fk_batch(ctx.h, rb.h, C.c_void_p(h_states.data_ptr()), rb.state_size, n, cap, C.byref(o)))
+
+    h_tip = torch.zeros(n, 3, dtype=torch.float64).pin_memory()
+    o_small = irt_b200.FkOutputs()
+    o_small.tip, o_small.L_i, o_small.flags = h_tip.data_ptr(), h_out["L_i"].data_ptr(), h_out["flags"].data_ptr()
+
+    def e2e_small_step():  # what samplers / IK consume: tip, L_i, validity flags (the shapes stay on the device)
+        ctx.check(ctx.L.irt_fk_batch(ctx.h, rb.h, C.c_void_p(h_states.data_ptr()), rb.state_size, n, cap, C.byref(o_small)))
 
     def time_e2e(fn):
         fn()
@@ -460,19 +506,58 @@ def main():
     dense_rows = h_out["p"].reshape(n * cap, 3)[(torch.arange(cap)[None, :] < dense_npts[:, None]).reshape(-1)].clone()
     e2e_s = time_e2e(e2e_step)
     rows = int(h_rowoff[-1])
+    packed_ok = bool(torch.equal(h_out["p"].reshape(n * cap, 3)[:rows], dense_rows) and torch.equal(h_out["npts"], dense_npts))
+    e2e_small_s = time_e2e(e2e_small_step)
     h2d = n * rb.state_size * 8
-    d2h = rows * 24 + n * (4 + 8 + rb.n_tendons * 8) + (n + 1) * 8
+    d2h = rows * 24 + n * (4 + 8 + rb.n_tendons * 8 + 4) + (n + 1) * 8
+    d2h_small = n * (24 + rb.n_tendons * 8 + 4)
+
+    # memcpy-only control: the same bytes between the same pinned buffers and the device, no kernels -- the PCIe /
+    # host-memory roofline of the e2e call on THIS box at THIS rank count (all ranks copy at once)
+    d_rows = outs["p"].reshape(-1)[:rows * 3]
+    h_rows = h_out["p"].reshape(-1)[:rows * 3]
+    d_small = torch.zeros(d2h_small // 8 + 1, dtype=torch.float64, device=dev)
+    h_small = torch.zeros(d2h_small // 8 + 1, dtype=torch.float64).pin_memory()
+    d_misc = torch.zeros((d2h - rows * 24) // 8 + 1, dtype=torch.float64, device=dev)
+    h_misc = torch.zeros((d2h - rows * 24) // 8 + 1, dtype=torch.float64).pin_memory()
+    cstream = torch.cuda.Stream(device=dev)
+
+    def copy_only():     # H2D and D2H on two streams, like the pipelined call
+        d_states.copy_(h_states, non_blocking=True)
+        with torch.cuda.stream(cstream):
+            h_rows.copy_(d_rows, non_blocking=True)
+            h_misc.copy_(d_misc, non_blocking=True)
+        torch.cuda.synchronize()
+
+    def copy_only_small():
+        d_states.copy_(h_states, non_blocking=True)
+        with torch.cuda.stream(cstream):
+            h_small.copy_(d_small, non_blocking=True)
+        torch.cuda.synchronize()
+
+    copy_s = time_e2e(copy_only)
+    copy_small_s = time_e2e(copy_only_small)
     e2e = {"value": world * n / e2e_s, "unit": "shapes/s", "h2d_bytes_per_step": h2d,
            "d2h_bytes_per_step": d2h, "ms_per_step": e2e_s * 1e3,
-           "api": "irt_fk_batch_packed (host pointers, pinned): p packed per shape + row_offsets, npts, L, L_i",
+           "api": "irt_fk_batch_packed (host pointers, pinned): p packed per shape + row_offsets, npts, L, L_i, flags",
            "rows_per_step": rows,
+           "roofline": {"bound": "pcie", "unit": "GB/s", "achieved": (h2d + d2h) / e2e_s / 1e9,
+                        "peak": (h2d + d2h) / copy_s / 1e9, "frac": copy_s / e2e_s,
+                        "peak_source": "memcpy-only control in this run: the same bytes between the same pinned "
+                                       "buffers and the device (H2D and D2H on two streams), all %d ranks copying at "
+                                       "once, %.2f ms" % (world, copy_s * 1e3)},
            "dense": {"value": world * n / e2e_dense_s, "ms_per_step": e2e_dense_s * 1e3,
-                     "d2h_bytes_per_step": n * (cap * 24 + 4 + 8 + rb.n_tendons * 8),
+                     "d2h_bytes_per_step": n * (cap * 24 + 4 + 8 + rb.n_tendons * 8 + 4),
                      "api": "irt_fk_batch: p as [n][max_points][3], zero padded"},
-           "packed_equals_dense": bool(torch.equal(h_out["p"].reshape(n * cap, 3)[:rows], dense_rows)
-                                       and torch.equal(h_out["npts"], dense_npts))}
+           "small": {"value": world * n / e2e_small_s, "ms_per_step": e2e_small_s * 1e3,
+                     "d2h_bytes_per_step": d2h_small, "h2d_bytes_per_step": h2d,
+                     "api": "irt_fk_batch with tip, L_i, flags only (what samplers and IK consume; shapes stay on "
+                            "the device)",
+                     "memcpy_only_ms": copy_small_s * 1e3, "device_step_ms": ms},
+           "packed_equals_dense": packed_ok}
     # parity spot check of the timed outputs against each other (device path == host path)
-    same = bool(torch.equal(h_out["npts"], outs["npts"].cpu()))
+    same = bool(torch.equal(h_out["npts"], outs["npts"].cpu()) and torch.equal(h_out["flags"], outs["flags"].cpu()))
+    del d_small, h_small, d_misc, h_misc
 
     # ---------------- K3: roadmap voxel check ---------------------------------------------------
     edge_check = None
@@ -490,9 +575,18 @@ def main():
         t1 = time.perf_counter()
         prm.precomputeVertexVoxelCache()
         t_vvox = time.perf_counter() - t1
+        # K2: the swept-volume cache of every edge.  Built twice: the first call also pays one-time costs (the
+        # context's sample-pool arena and the set store are cudaMalloc'ed, kernels are loaded); the second is
+        # the steady state a planner sees whenever it (re)builds a cache -- like the warm-up steps of the FK loop.
         t1 = time.perf_counter()
         einfo = prm.precomputeEdgeVoxelCache()
+        t_evox_first = time.perf_counter() - t1
+        barrier()
+        t1 = time.perf_counter()
+        einfo = prm.precomputeEdgeVoxelCache()
+        torch.cuda.synchronize()
         t_evox = time.perf_counter() - t1
+        t_evox = max_over_ranks(t_evox)
         env_blocks = wl.dense_to_morton_blocks(wl.lung_like_env_dense(spec3, g))
         prm.setEnvironment(env_blocks)
         ne = len(prm.edges)
@@ -505,7 +599,7 @@ def main():
                 prm.edge_store.check_dev(prm.env, d_words, 0, hi - lo, stream=sptr)
             return gather_verdict_words(d_words, dist if world > 1 else None)
 
-        # N > 1: the verdict all-gather is fused into K3 (every warp stores its word into all peers'
+        # N > 1: the verdict all-gather is fused into K3 (every CTA stores its words into all peers'
         # gathered arrays over NVLink, an epoch flag per rank replaces the collective)
         xch_e = prm._exchange(prm.edge_store, w) if world > 1 else None
 
@@ -514,41 +608,32 @@ def main():
                 return k3_step_nccl()
             return xch_e.check(prm.edge_store, prm.env, 0, hi - lo, stream=sptr)
 
-        # L2 rule: the sweep's input (the set store of this rank) is >> the 126 MB L2 at the default
-        # roadmap size, so consecutive sweeps cannot hit in L2 and no flush write is needed (a flush would
-        # leave ~100 MB of dirty lines whose write-back competes with the sweep's reads); smaller stores
-        # (--roadmap-vertices below ~100k) are flushed.
-        k3_flush = (prm.edge_store.algorithmic_bytes() if hi > lo else 0) < 4 * 126e6
-        for _ in range(args.warmup):
-            if k3_flush:
-                flush.zero_()
-            k3_step()
-        barrier()
-        ev3 = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-        for a, b in ev3:
-            if k3_flush:
-                flush.zero_()
-            a.record(stream)
-            k3_step()
-            b.record(stream)
-        barrier()
-        ms3_local = float(np.mean([a.elapsed_time(b) for a, b in ev3]))
-        ms3 = max_over_ranks(ms3_local)
-        ms3_nccl = None
-        if world > 1:   # the same sweep with the NCCL exchange, for comparison; verdicts must agree
+        def time_sweeps(step):
+            """ONE L2 rule for every N and both exchange variants: the read-only flush before every sweep"""
             for _ in range(args.warmup):
-                k3_step_nccl()
+                l2_flush()
+                step()
             barrier()
-            evn = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-            for a, b in evn:
+            evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+            for a, b in evs:
+                l2_flush()
                 a.record(stream)
-                k3_step_nccl()
+                step()
                 b.record(stream)
             barrier()
-            ms3_nccl = max_over_ranks(float(np.mean([a.elapsed_time(b) for a, b in evn])))
-            same_gather = bool(torch.equal(k3_step().cpu(), k3_step_nccl().cpu())) and xch_e.status() == 0
-            if not same_gather:
-                raise SystemExit("fused verdict gather differs from the NCCL all_gather")
+            return float(np.mean([a.elapsed_time(b) for a, b in evs]))
+
+        ms3_local = time_sweeps(k3_step)
+        ms3 = max_over_ranks(ms3_local)
+        ms3_nccl = None
+        mism_nccl = None
+        if world > 1:   # the same sweep with the NCCL exchange, for comparison; verdicts must agree
+            ms3_nccl = max_over_ranks(time_sweeps(k3_step_nccl))
+            wf, wn = k3_step().cpu().numpy().view(np.uint32), k3_step_nccl().cpu().numpy().view(np.uint32)
+            mism_nccl = int(sum(bin(int(x)).count("1") for x in (wf ^ wn).tolist()))
+            mism_nccl = int(sum_over_ranks(mism_nccl))
+            if xch_e.status() != 0:
+                raise SystemExit("fused verdict gather: a peer never arrived")
         alg_bytes = prm.edge_store.algorithmic_bytes() if hi > lo else 0
         hbm_peak = 6552.0
         try:
@@ -559,6 +644,30 @@ def main():
             hbm_peak, hbm_src = 6650.0, "fallback 6.65 TB/s (of fallback)"
         ach3 = alg_bytes / (ms3_local * 1e-3) / 1e9
         nblk = prm.edge_store.num_blocks
+        # K2 figures: FK-equivalent work of the build against the FP64 peak
+        k2 = None
+        try:
+            if hi > lo:
+                ns_edge = np.asarray(einfo["nsamples"], dtype=np.int64)
+                n_mid = int((ns_edge - 2).clip(min=0).sum())
+                vst = torch.from_numpy(prm.states[:min(len(prm.states), 200000)]).to(dev)
+                vo = dict(nsteps=torch.zeros(len(vst), dtype=torch.int32, device=dev),
+                          iters=torch.zeros(len(vst), dtype=torch.int32, device=dev))
+                rb3.shape_batch_dev(vst, len(vst), vo, stream=sptr)
+                torch.cuda.synchronize()
+                f3 = flops_per_shape(rb3.n_tendons, float(vo["nsteps"].double().mean()), float(vo["iters"].double().mean()))
+                fk_samples = n_mid + len(prm.states)
+                k2_tf = fk_samples * f3 / t_evox / 1e12
+                k2 = {"edges": hi - lo, "seconds": t_evox, "seconds_first_call": t_evox_first,
+                      "edges_per_s": (hi - lo) / t_evox, "fk_samples": fk_samples, "mid_samples": n_mid,
+                      "vertex_samples": len(prm.states), "flop_per_sample": f3, "fk_equivalent_tflops": k2_tf,
+                      "frac_of_fp64_peak": k2_tf / peak_tf,
+                      "note": "FK-equivalent roofline of the whole K2 build (vertex FK shared by the incident edges + "
+                              "bisection samples, validity epilogue, subdivision tests, rasterisation, CSR packing): "
+                              "algorithmic FK FLOP of every sample / wall time of the second build / FP64 peak"}
+                del vst, vo
+        except Exception as e:
+            k2 = {"error": repr(e)[:200]}
         edge_check = {
             "metric": "roadmap_voxel_edge_checks_per_s", "value": ne / (ms3 * 1e-3), "unit": "edges/s",
             "ms_per_sweep": ms3, "scaling": "strong", "n_vertices": len(prm.states), "n_edges": ne,
@@ -566,8 +675,11 @@ def main():
             "fk_samples_per_edge": float(np.mean(einfo["nsamples"])) if hi > lo else None,
             "collision_fraction": None,
             "build_s": {"sample_valid_vertices_and_knn": t_sample, "vertex_voxel_cache": t_vvox,
-                        "edge_voxel_cache": t_evox,
-                        "edges_per_s_K1K2": (hi - lo) / t_evox if t_evox > 0 else None},
+                        "edge_voxel_cache": t_evox, "edge_voxel_cache_first_call": t_evox_first,
+                        "edges_per_s_K1K2": (hi - lo) / t_evox if t_evox > 0 else None,
+                        "note": "edge_voxel_cache = second build of the same cache (max over ranks); the first call "
+                                "also pays the one-time cudaMalloc of the sample-pool arena and the set store"},
+            "k2": k2,
             "roofline": {"bound": "hbm", "kernel": "voxel_and_popc_kernel", "achieved": ach3, "peak": hbm_peak,
                          "unit": "GB/s", "frac": ach3 / hbm_peak,
                          "traffic": (prof.get("k3_dram_bytes_per_launch") or
@@ -575,15 +687,15 @@ def main():
                                       if prof.get("k3_dram_bytes_over_algorithmic") else None)),
                          "traffic_source": prof.get("k3_source"),
                          "peak_source": hbm_src, "algorithmic_bytes": alg_bytes,
-                         "l2": ("512 MB flush write between timed sweeps" if k3_flush else
-                                "no flush: the store streamed per sweep (%.0f MB) is >> L2 (126 MB)" % (alg_bytes / 1e6)),
+                         "l2": "read-only flush (summing read of 512 MB) before every sweep, at every N and for both "
+                               "exchange variants; the store streamed per sweep is %.0f MB" % (alg_bytes / 1e6),
                          "note": "duration = the whole sweep step (K3 launch; N>1: verdict all-gather fused "
-                                 "into K3 over NVLink peer memory + one-warp flag wait)"},
+                                 "into K3 over NVLink peer memory, flag wait folded into the kernel's last CTA)"},
             "exchange": (None if world == 1 else
                          {"kind": "fused into K3: P2P stores of verdict words into all peers' gathered arrays "
                                   "(CUDA IPC over NVLink), per-rank epoch flags; no collective call per sweep",
                           "ms_per_sweep": ms3, "nccl_all_gather_ms_per_sweep": ms3_nccl,
-                          "words_per_rank": w, "equal_to_nccl": True}),
+                          "words_per_rank": w, "mismatches_vs_nccl": mism_nccl}),
         }
         # ---- C5: interactive replanning tick = env change + upload + vertex sweep + edge sweep + gather
         nvt = len(prm.states)
@@ -632,6 +744,37 @@ def main():
         edge_check["valid_edge_fraction"] = float(verd.mean())
         lo_w = irt_b200.unpack_verdicts(d_words.cpu().numpy().view(np.uint32), hi - lo) if hi > lo else np.zeros(0)
         edge_check["collision_fraction"] = float(lo_w.mean()) if hi > lo else None
+        if world > 1:   # the gathered table against every rank's own K3 verdicts: collisions counted both ways
+            coll_g = prm._sweep(prm.edge_store, ne, prm.edge_flags)
+            edge_check["exchange"]["collisions_in_gathered_table"] = int(coll_g.sum())
+            edge_check["exchange"]["collisions_local_sum"] = int(sum_over_ranks(int(lo_w.sum())))
+            edge_check["exchange"]["mismatches_vs_unsharded"] = int(
+                np.count_nonzero(coll_g[lo:hi] != lo_w.astype(bool))) if hi > lo else 0
+            edge_check["exchange"]["mismatches_vs_unsharded"] = int(sum_over_ranks(edge_check["exchange"]["mismatches_vs_unsharded"]))
+        try:    # C5 end to end: the tick's verdict words on the HOST and a path validated by look-ups
+            rng_p = np.random.default_rng(wl.SEED + 9)
+            t0 = time.perf_counter()
+            prm.setEnvironment(tick_envs[1].numpy().view(np.uint64))
+            prm.precomputeValidity()             # both sweeps + gathers + D2H of the words + validity tables
+            t_words = time.perf_counter() - t0
+            vv = np.nonzero(prm.vertex_validity)[0]
+            paths = []
+            t0 = time.perf_counter()
+            for _ in range(3):
+                a_, b_ = (int(x) for x in rng_p.choice(vv, 2, replace=False))
+                pth, its = prm.solveWithRoadmap(a_, b_, max_iterations=200)
+                paths.append({"found": pth is not None, "vertices": None if pth is None else len(pth), "searches": its})
+            t_paths = time.perf_counter() - t0
+            edge_check["replanning_tick_with_path"] = {
+                "ms_words_on_host": t_words * 1e3, "ms_per_path_query": t_paths * 1e3 / 3, "queries": paths,
+                "lookups": dict(prm.lookups),
+                "what": "setEnvironment (H2D) + precomputeValidity (vertex and edge sweeps, gathers, D2H of the verdict "
+                        "words, validity tables) timed on the host clock; then solveWithRoadmap = A* (host, Python "
+                        "mirror) + constructSolution's computeVertexValidity / computeEdgeValidity as table look-ups + "
+                        "remove-and-retry (VoxelCachedLazyPRM.cpp:2689-2771)"}
+            prm.setEnvironment(env_blocks)
+        except Exception as e:
+            edge_check["replanning_tick_with_path"] = {"error": repr(e)[:300]}
         try:    # K2 unit-of-work figures of SURVEY 8(d); reporting only
             if hi > lo:
                 edge_check["fk_samples_per_edge_p99"] = float(np.percentile(einfo["nsamples"], 99))
@@ -642,6 +785,22 @@ def main():
                 del full
         except Exception as e:
             edge_check["k2_figures_error"] = repr(e)[:200]
+        try:    # a LOW-collision environment (wide airways: ~5 % of the leaf blocks occupied, few sets hit)
+            env_lo = wl.dense_to_morton_blocks(wl.lung_like_env_dense(spec3, g, radius_scale=8.5))
+            prm.setEnvironment(env_lo)
+            ms_lo = max_over_ranks(time_sweeps(k3_step))
+            k3_step_nccl()
+            torch.cuda.synchronize()
+            lw = irt_b200.unpack_verdicts(d_words.cpu().numpy().view(np.uint32), hi - lo) if hi > lo else np.zeros(1)
+            edge_check["low_collision_env"] = {
+                "occupied_block_fraction": float(np.count_nonzero(env_lo)) / env_lo.size,
+                "collision_fraction": float(lw.mean()), "ms_per_sweep": ms_lo,
+                "value": ne / (ms_lo * 1e-3), "roofline_frac": (alg_bytes / (ms_lo * 1e-3) / 1e9) / hbm_peak if world == 1 else None}
+            prm.setEnvironment(env_blocks)
+            k3_step_nccl()
+            torch.cuda.synchronize()
+        except Exception as e:
+            edge_check["low_collision_env"] = {"error": repr(e)[:200]}
 
         # ---- CPU baseline of the edge check (rank 0 at N=1 only): the reference's own octree code
         # (oracle/_ref/libtreenode_ref.so = collision/detail/TreeNode.h compiled as is) running the OpenMP
@@ -673,13 +832,11 @@ def main():
             "metric": "fk_shapes_per_s", "value": value, "unit": "shapes/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "n_configs_per_gpu": n, "state_size": rb.state_size,
-                       "max_points": cap, "seed": wl.SEED,
-                       "l2": "512 MB flush write between timed steps; outputs (%.0f MB) exceed L2" % (n * cap * 24 / 1e6),
-                       "outputs": "p, npts, L, L_i (+iters, nsteps)"},
+            "config": workload_config(cap, rb.state_size),
             "clocks": sampler.result(), "e2e": e2e, "gpu_launches": int(launches),
             "roofline": roofline, "cpu_baseline": cpu, "edge_check": edge_check,
             "wall_s_timed_region": t_wall, "host_vs_device_path_equal": same,
+            "valid_shape_fraction": valid_fraction,
         }
         print(json.dumps(line), flush=True)
     if world > 1:

@@ -37,6 +37,8 @@ struct irt_ctx {
   cudaEvent_t ev_offsets[2] = {nullptr, nullptr};
   void *pinned = nullptr;
   size_t pinned_bytes = 0;
+  bool debug_sync = false;   // IRT_B200_DEBUG_SYNC=1
+  bool fk_smem = false;      // IRT_FK_SMEM=1: K1 variant with the integration state in shared memory (if built)
 };
 
 // device-resident robot constants (passed to kernels by value)
@@ -52,6 +54,12 @@ struct RobotDev {
   int n_table;        // 2*Kfull - 1 entries: idx(node i) = 2i, idx(mid of step i -> i-1) = 2i - 1
   int n_head;         // no-retraction robots: tabulated first-gap stages (<= 4 entries)
   double head_h[2];   // no-retraction robots: first-gap step sizes (h[1] = 0 if one step)
+  double tau_bin_scale;  // FK bucket key: tension bin = (int)(sum(tau) * tau_bin_scale)
+  int simple_routing;    // every tendon is straight or helical with constant rho (n_c <= 2, n_d == 1)
+  int c1_uniform;        // ... and all tendons wind at the same rate |C1| (or not at all)
+  double c1_abs;         // that rate
+  double c1_sign[IRT_MAX_TENDONS];                        // C1_j = c1_sign_j * c1_abs (0 for a straight tendon)
+  double sin_c0[IRT_MAX_TENDONS], cos_c0[IRT_MAX_TENDONS];  // sin / cos of C0_j (host libm)
   const double *table;  // device: [n_table][N][6] = rx, ry, rdx, rdy, rddx, rddy
   const double *head;   // device: [4][N][6]
   const double *node_t; // device: [Kfull] canonical node times L - i*dL
@@ -114,19 +122,29 @@ int setstore_grow_blocks(irt_ctx *ctx, irt_setstore *s, int64_t need_blocks, int
                       cudaGetErrorString(_e), __FILE__, __LINE__);                      \
   } while (0)
 
-#define IRT_LAUNCHED(ctx) ((ctx)->launches.fetch_add(1, std::memory_order_relaxed))
+// counts a kernel launch; with IRT_B200_DEBUG_SYNC=1 in the environment (read at context creation) it also
+// synchronises the device and reports the first kernel that failed with its source line
+void irt_launched(irt_ctx *ctx, const char *file, int line);
+#define IRT_LAUNCHED(ctx) irt_launched((ctx), __FILE__, __LINE__)
 
 // internal cross-file entry points
 int env_rebuild_occ(irt_ctx *ctx, irt_env *env, cudaStream_t st);
 int setstore_reserve(irt_ctx *ctx, irt_setstore *s, int64_t n_sets, int64_t n_blocks);
 int setstore_finalize(irt_ctx *ctx, irt_setstore *s, int64_t n_sets, int64_t n_blocks,
                       cudaStream_t st);
-// d_row_off == nullptr: dense outputs p/R/t[n][cap_pts]; else packed rows, configuration i at row d_row_off[i]
+// d_row_off == nullptr: dense outputs p/R/t[n][cap_pts]; else packed rows, configuration i at row d_row_off[i].
+// d_range != nullptr: the batch is rows [lo, hi) of d_states and of the outputs, {lo, hi} read from device memory
+// when the kernels run (n = upper bound of hi - lo); work = fk_work_bytes(rb, n) bytes of device scratch private
+// to this launch (nullptr: the context's scratch buffer, one launch in flight per context).
+size_t fk_work_bytes(const irt_robot *rb, int64_t n);
 int fk_launch(irt_ctx *ctx, const irt_robot *rb, const double *d_states, int64_t n, int cap_pts,
-              const irt_fk_outputs &o, const int32_t *d_perm, cudaStream_t st,
-              const int64_t *d_row_off = nullptr);
+              const irt_fk_outputs &o, cudaStream_t st, const int64_t *d_row_off = nullptr,
+              const int32_t *d_range = nullptr, void *work = nullptr);
 int fk_row_counts(irt_ctx *ctx, const irt_robot *rb, const double *d_states, int64_t n,
                   int64_t *d_counts, cudaStream_t st);
+// same conventions for d_range / work (selfcol_work_bytes(n) bytes)
+size_t selfcol_work_bytes(int64_t n);
 int self_collision_launch(irt_ctx *ctx, const irt_robot *rb, const double *d_p,
                           const int32_t *d_npts, int64_t n, int cap_pts, uint32_t *d_flags,
-                          cudaStream_t st, const int64_t *d_row_off = nullptr);
+                          cudaStream_t st, const int64_t *d_row_off = nullptr,
+                          const int32_t *d_range = nullptr, void *work = nullptr);

@@ -1,6 +1,7 @@
 // ctx.cu -- context, robot constants / routing tables, grid helpers, FP64 peak probe.
 #include <cmath>
 #include <cstdarg>
+#include <cstdlib>
 #include <cstring>
 #include <limits>
 
@@ -17,6 +18,19 @@ int irt_fail(irt_ctx *ctx, int status, const char *fmt, ...) {
     ctx->last_error = buf;
   }
   return status;
+}
+
+void irt_launched(irt_ctx *ctx, const char *file, int line) {
+  ctx->launches.fetch_add(1, std::memory_order_relaxed);
+  if (ctx->debug_sync) {
+    cudaError_t e = cudaDeviceSynchronize();
+    if (e == cudaSuccess) e = cudaGetLastError();
+    if (e != cudaSuccess) {
+      std::fprintf(stderr, "[irt debug] kernel launched at %s:%d failed: %s\n", file, line, cudaGetErrorString(e));
+      std::fflush(stderr);
+      ctx->debug_sync = false;
+    }
+  }
 }
 
 void *ctx_scratch(irt_ctx *ctx, size_t bytes) {
@@ -45,8 +59,7 @@ void *ctx_arena(irt_ctx *ctx, size_t bytes) {
 
 void *ctx_io(irt_ctx *ctx, size_t bytes) {
   if (bytes <= ctx->io_bytes) return ctx->io;
-  if (ctx->io) cudaFree(ctx->io);
-  if (ctx->pinned) cudaFreeHost(ctx->pinned);
+  if (ctx->io) cudaFree(ctx->io);   // (the pinned host buffer is independent of this one: ctx_pinned owns it)
   ctx->io = nullptr;
   ctx->io_bytes = 0;
   if (cudaMalloc(&ctx->io, bytes) != cudaSuccess) return nullptr;
@@ -92,6 +105,12 @@ int irt_ctx_create(int device, irt_ctx **out) {
   if (cudaSetDevice(device) != cudaSuccess) return IRT_ERR_CUDA;
   irt_ctx *ctx = new irt_ctx();
   ctx->device = device;
+  {
+    const char *dbg = getenv("IRT_B200_DEBUG_SYNC");
+    ctx->debug_sync = dbg && dbg[0] == '1';
+    const char *fs = getenv("IRT_FK_SMEM");
+    ctx->fk_smem = fs && fs[0] == '1';
+  }
   cudaDeviceProp prop;
   if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) ctx->sm_count = prop.multiProcessorCount;
   if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess ||
@@ -268,6 +287,25 @@ int irt_robot_create(irt_ctx *ctx, const irt_robot_desc *desc, irt_robot **out) 
   d.n_tendons = N; d.n_c = desc->n_c; d.n_d = desc->n_d;
   d.enable_rotation = desc->enable_rotation ? 1 : 0;
   d.enable_retraction = desc->enable_retraction ? 1 : 0;
+  {
+    double tsum = 0.0;
+    for (int j = 0; j < N; j++) tsum += desc->max_tension[j];
+    d.tau_bin_scale = (tsum > 0.0) ? 8.0 / tsum : 0.0;   // FK_TAU_BINS bins over [0, sum(max_tension)]
+    d.simple_routing = (desc->n_c <= 2 && desc->n_d == 1) ? 1 : 0;
+    d.c1_uniform = d.simple_routing;
+    d.c1_abs = 0.0;
+    for (int j = 0; j < N && d.simple_routing; j++) {
+      const double c0 = desc->C[j * IRT_MAX_COEF];
+      const double c1 = (desc->n_c > 1) ? desc->C[j * IRT_MAX_COEF + 1] : 0.0;
+      d.sin_c0[j] = std::sin(c0);
+      d.cos_c0[j] = std::cos(c0);
+      d.c1_sign[j] = (c1 > 0.0) ? 1.0 : ((c1 < 0.0) ? -1.0 : 0.0);
+      if (c1 != 0.0) {
+        if (d.c1_abs == 0.0) d.c1_abs = std::fabs(c1);
+        else if (std::fabs(c1) != d.c1_abs) d.c1_uniform = 0;
+      }
+    }
+  }
   for (int j = 0; j < N; j++) {  // home_shape closed forms -- tendon/TendonRobot.cpp:281-310
     const double *C = desc->C + j * IRT_MAX_COEF, *D = desc->D + j * IRT_MAX_COEF;
     int rdeg = poly_degree(D, desc->n_d), tdeg = poly_degree(C, desc->n_c);

@@ -38,6 +38,12 @@ constexpr int FK_THREADS = FK_THREADS_PER_BLOCK;
 #ifndef FK_FAST_PRIMS
 #define FK_FAST_PRIMS 1
 #endif
+#ifndef FK_PERSIST
+#define FK_PERSIST 1
+#endif
+#ifndef FK_SMEM_VARIANT
+#define FK_SMEM_VARIANT 0
+#endif
 #if FK_FAST_PRIMS
 // Branch-free reciprocal / reciprocal square root: the hardware FP64 seed (MUFU.RCP64H /
 // MUFU.RSQ64H, ~20 bits) refined by two Newton steps (relative error ~1e-16, not correctly
@@ -99,6 +105,63 @@ __device__ __forceinline__ void routing_eval(const RobotDev &rb, double t, doubl
     o[3] = rho1 * cs + rho * (-sn * th1);
     o[4] = ((rho2 * sn + (2 * rho1) * (cs * th1)) - rho * (sn * th1 * th1)) + rho * (cs * th2);
     o[5] = ((rho2 * cs + (2 * rho1) * (-sn * th1)) - rho * (cs * th1 * th1)) + rho * (-sn * th2);
+  }
+}
+
+// Straight and helical routing (theta of degree <= 1, rho constant: exactly the tendons whose home length has a
+// closed form, TendonRobot.cpp:281-310): the power sums of get_r_info2 collapse to theta = C0 + C1 t,
+// theta' = C1, theta'' = 0, rho = D0, rho' = rho'' = 0, and every term of the general formulas that is
+// multiplied by one of the zeros drops out.  A double-precision sincos is ~200 instructions, and a shape with
+// retraction needs the routing of all tendons at 4 head times; when all tendons wind at the same rate |C1|
+// (rb.c1_uniform: helices of equal pitch, either handedness, and straight tendons) ONE sincos(|C1| t) per time
+// serves every tendon through the angle-addition formulas with sin(C0), cos(C0) tabulated by the host:
+// 4 sincos per shape instead of 4 N (within 2 ulp of the direct evaluation).
+template <int NT, int NEVAL>
+__device__ __forceinline__ void routing_eval_simple(const RobotDev &rb, const double (&t)[NEVAL],
+                                                    double *const (&out)[NEVAL]) {
+  if (rb.c1_uniform) {
+    double sw[NEVAL], cw[NEVAL];
+#pragma unroll
+    for (int k = 0; k < NEVAL; k++) {
+      sw[k] = 0.0; cw[k] = 1.0;
+      if (rb.c1_abs != 0.0) sincos(rb.c1_abs * t[k], &sw[k], &cw[k]);
+    }
+#pragma unroll 1
+    for (int j = 0; j < NT; j++) {
+      const double s0 = rb.sin_c0[j], c0 = rb.cos_c0[j], sg = rb.c1_sign[j];
+      const double c1 = sg * rb.c1_abs, rho = rb.D[j * IRT_MAX_COEF];
+#pragma unroll
+      for (int k = 0; k < NEVAL; k++) {
+        const double ssw = sg * sw[k];
+        const double cwk = (sg != 0.0) ? cw[k] : 1.0;   // a straight tendon beside helices does not wind
+        const double sn = fma(s0, cwk, c0 * ssw), cs = fma(c0, cwk, -s0 * ssw);
+        double *o = out[k] + 6 * j;
+        o[0] = rho * sn;
+        o[1] = rho * cs;
+        o[2] = rho * (cs * c1);
+        o[3] = rho * (-sn * c1);
+        o[4] = -(rho * (sn * c1 * c1));
+        o[5] = -(rho * (cs * c1 * c1));
+      }
+    }
+    return;
+  }
+#pragma unroll 1
+  for (int j = 0; j < NT; j++) {
+    const double c0 = rb.C[j * IRT_MAX_COEF], c1 = (rb.n_c > 1) ? rb.C[j * IRT_MAX_COEF + 1] : 0.0;
+    const double rho = rb.D[j * IRT_MAX_COEF];
+#pragma unroll 1
+    for (int k = 0; k < NEVAL; k++) {
+      double sn, cs;
+      sincos(fma(c1, t[k], c0), &sn, &cs);
+      double *o = out[k] + 6 * j;
+      o[0] = rho * sn;
+      o[1] = rho * cs;
+      o[2] = rho * (cs * c1);
+      o[3] = rho * (-sn * c1);
+      o[4] = -(rho * (sn * c1 * c1));
+      o[5] = -(rho * (cs * c1 * c1));
+    }
   }
 }
 
@@ -216,48 +279,57 @@ __device__ __forceinline__ void vu_dot(const double *__restrict__ rt, const doub
   vd[2] = fma(-idA, fma(y20, ud[0], fma(y21, ud[1], y22 * ud[2])), z2);
 }
 
-// FK_SMEM_ACC: the pure quadratures (L, L_i and optionally p) are only touched once per RK4
-// stage; keeping them in per-thread shared-memory slots (stride = block size, conflict-free)
-// frees registers for the scheduler.
-#ifndef FK_SMEM_ACC
-#define FK_SMEM_ACC 0
-#endif
+// Integration state of one configuration.  SM = false: registers (255 per thread, 8 warps per SM).
+// SM = true: per-thread slots in shared memory with stride SM_THREADS (conflict-free): the state proper AND the
+// RK4 stage scratch live there, so that the derivative evaluation -- the only register-hungry part -- runs at
+// 168 registers and 12 warps per SM (3 per scheduler instead of 2) hide each other's FP64 latencies.
+constexpr int FK_SM_THREADS = 384;
 template <int NT>
-struct FkState {
-  double R[9];  // column-major (R[i + 3 j]) like Eigen
-  double v[3], u[3];
-#if FK_SMEM_ACC >= 2
-  double *sm;   // slots: [0..2] p, [3] L, [4..4+NT) L_i
-  __device__ __forceinline__ double &P(int i) { return sm[i * FK_THREADS]; }
-  __device__ __forceinline__ const double &P(int i) const { return sm[i * FK_THREADS]; }
-#else
-  double p[3];
-  __device__ __forceinline__ double &P(int i) { return p[i]; }
-  __device__ __forceinline__ const double &P(int i) const { return p[i]; }
-#endif
-#if FK_SMEM_ACC >= 1
-#if FK_SMEM_ACC == 1
-  double *sm;
-#endif
-  __device__ __forceinline__ double &LB() { return sm[3 * FK_THREADS]; }
-  __device__ __forceinline__ const double &LB() const { return sm[3 * FK_THREADS]; }
-  __device__ __forceinline__ double &LI(int j) { return sm[(4 + j) * FK_THREADS]; }
-  __device__ __forceinline__ const double &LI(int j) const { return sm[(4 + j) * FK_THREADS]; }
-#else
-  double Lb;
-  double Li[NT];
-  __device__ __forceinline__ double &LB() { return Lb; }
-  __device__ __forceinline__ const double &LB() const { return Lb; }
-  __device__ __forceinline__ double &LI(int j) { return Li[j]; }
-  __device__ __forceinline__ const double &LI(int j) const { return Li[j]; }
-#endif
+constexpr int fk_sm_slots() { return 19 + NT + 9 + 9 + 3 + 3; }   // R v u p L Li | sR aR av au
+
+template <int NT, bool SM>
+struct FkState;
+template <int NT>
+struct FkState<NT, false> {
+  double R_[9];  // column-major (R[i + 3 j]) like Eigen
+  double v_[3], u_[3];
+  double p_[3];
+  double Lb_;
+  double Li_[NT];
+  __device__ __forceinline__ double &R(int i) { return R_[i]; }
+  __device__ __forceinline__ const double &R(int i) const { return R_[i]; }
+  __device__ __forceinline__ double &V(int i) { return v_[i]; }
+  __device__ __forceinline__ const double &V(int i) const { return v_[i]; }
+  __device__ __forceinline__ double &U(int i) { return u_[i]; }
+  __device__ __forceinline__ const double &U(int i) const { return u_[i]; }
+  __device__ __forceinline__ double &P(int i) { return p_[i]; }
+  __device__ __forceinline__ const double &P(int i) const { return p_[i]; }
+  __device__ __forceinline__ double &LB() { return Lb_; }
+  __device__ __forceinline__ const double &LB() const { return Lb_; }
+  __device__ __forceinline__ double &LI(int j) { return Li_[j]; }
+  __device__ __forceinline__ const double &LI(int j) const { return Li_[j]; }
+};
+template <int NT>
+struct FkState<NT, true> {
+  double *sm;   // this thread's slot 0
+  __device__ __forceinline__ double &S(int slot) const { return sm[slot * FK_SM_THREADS]; }
+  __device__ __forceinline__ double &R(int i) const { return S(i); }
+  __device__ __forceinline__ double &V(int i) const { return S(9 + i); }
+  __device__ __forceinline__ double &U(int i) const { return S(12 + i); }
+  __device__ __forceinline__ double &P(int i) const { return S(15 + i); }
+  __device__ __forceinline__ double &LB() const { return S(18); }
+  __device__ __forceinline__ double &LI(int j) const { return S(19 + j); }
+  __device__ __forceinline__ double &SR(int i) const { return S(19 + NT + i); }
+  __device__ __forceinline__ double &AR(int i) const { return S(28 + NT + i); }
+  __device__ __forceinline__ double &AV(int i) const { return S(37 + NT + i); }
+  __device__ __forceinline__ double &AU(int i) const { return S(40 + NT + i); }
 };
 
 // one classic RK4 step of size h; rt0/rt1/rt2 = routing at t, t+h/2, t+h.
 // The four stages are a real loop (not unrolled): the hot loop body is ONE copy of vu_dot, which
 // keeps the instruction footprint inside the SM's instruction cache.
 template <int NT>
-__device__ __forceinline__ void rk4_step(FkState<NT> &x, const double (&tau)[NT],
+__device__ __forceinline__ void rk4_step(FkState<NT, false> &x, const double (&tau)[NT],
                                          const double (&Kse)[3], const double (&Kbt)[3], double h,
                                          const double *rt0, const double *rt1, const double *rt2) {
   const double hh = 0.5 * h, w1 = h * (1.0 / 6.0), w2 = h * (1.0 / 3.0);
@@ -265,9 +337,9 @@ __device__ __forceinline__ void rk4_step(FkState<NT> &x, const double (&tau)[NT]
   double aR[9], av[3], au[3];      // k1 + 2 k2 + 2 k3 + k4
   double vd[3], ud[3], sig[NT], Rd[9];
 #pragma unroll
-  for (int i = 0; i < 3; i++) { sv[i] = x.v[i]; su[i] = x.u[i]; av[i] = 0.0; au[i] = 0.0; }
+  for (int i = 0; i < 3; i++) { sv[i] = x.V(i); su[i] = x.U(i); av[i] = 0.0; au[i] = 0.0; }
 #pragma unroll
-  for (int i = 0; i < 9; i++) { sR[i] = x.R[i]; aR[i] = 0.0; }
+  for (int i = 0; i < 9; i++) { sR[i] = x.R(i); aR[i] = 0.0; }
 
 #pragma unroll 1
   for (int stage = 0; stage < 4; stage++) {
@@ -299,17 +371,79 @@ __device__ __forceinline__ void rk4_step(FkState<NT> &x, const double (&tau)[NT]
       Rd[i + 6] = fma(sR[i], su[1], -sR[i + 3] * su[0]);
     }
 #pragma unroll
-    for (int i = 0; i < 9; i++) { aR[i] = fma(wk, Rd[i], aR[i]); sR[i] = fma(a, Rd[i], x.R[i]); }
+    for (int i = 0; i < 9; i++) { aR[i] = fma(wk, Rd[i], aR[i]); sR[i] = fma(a, Rd[i], x.R(i)); }
 #pragma unroll
     for (int i = 0; i < 3; i++) {
       av[i] = fma(wk, vd[i], av[i]); au[i] = fma(wk, ud[i], au[i]);
-      sv[i] = fma(a, vd[i], x.v[i]); su[i] = fma(a, ud[i], x.u[i]);
+      sv[i] = fma(a, vd[i], x.V(i)); su[i] = fma(a, ud[i], x.U(i));
     }
   }
 #pragma unroll
-  for (int i = 0; i < 9; i++) x.R[i] = fma(w1, aR[i], x.R[i]);
+  for (int i = 0; i < 9; i++) x.R(i) = fma(w1, aR[i], x.R(i));
 #pragma unroll
-  for (int i = 0; i < 3; i++) { x.v[i] = fma(w1, av[i], x.v[i]); x.u[i] = fma(w1, au[i], x.u[i]); }
+  for (int i = 0; i < 3; i++) { x.V(i) = fma(w1, av[i], x.V(i)); x.U(i) = fma(w1, au[i], x.U(i)); }
+}
+
+// the same step with the state and the stage scratch in shared memory (FkState<NT, true>): identical
+// arithmetic in identical order, so both variants give bit-identical results
+template <int NT>
+__device__ __forceinline__ void rk4_step(FkState<NT, true> &x, const double (&tau)[NT],
+                                         const double (&Kse)[3], const double (&Kbt)[3], double h,
+                                         const double *rt0, const double *rt1, const double *rt2) {
+  const double hh = 0.5 * h, w1 = h * (1.0 / 6.0), w2 = h * (1.0 / 3.0);
+  double sv[3], su[3];
+#pragma unroll
+  for (int i = 0; i < 3; i++) { sv[i] = x.V(i); su[i] = x.U(i); x.AV(i) = 0.0; x.AU(i) = 0.0; }
+#pragma unroll
+  for (int i = 0; i < 9; i++) { x.SR(i) = x.R(i); x.AR(i) = 0.0; }
+
+#pragma unroll 1
+  for (int stage = 0; stage < 4; stage++) {
+    const bool outer = (stage == 0) || (stage == 3);
+    const double *rt = (stage == 0) ? rt0 : ((stage == 3) ? rt2 : rt1);
+    const double wq = outer ? w1 : w2;     // quadrature weight
+    const double wk = outer ? 1.0 : 2.0;   // slope weight
+    const double a = (stage == 2) ? h : hh;
+    double vd[3], ud[3], sig[NT];
+    // compiler barriers: without them the stored stage values are forwarded in registers across the derivative
+    // evaluation (store-to-load forwarding), which is exactly the register pressure this variant is meant to shed
+    asm volatile("" ::: "memory");
+    vu_dot<NT>(rt, tau, Kse, Kbt, sv, su, vd, ud, sig);
+    asm volatile("" ::: "memory");
+    double sR[9], Rd[9];
+#pragma unroll
+    for (int i = 0; i < 9; i++) sR[i] = x.SR(i);
+#pragma unroll
+    for (int i = 0; i < 3; i++)
+      x.P(i) = fma(wq, fma(sR[i], sv[0], fma(sR[i + 3], sv[1], sR[i + 6] * sv[2])), x.P(i));
+    {
+      const double vv = fma(sv[0], sv[0], fma(sv[1], sv[1], sv[2] * sv[2]));
+#if FK_FAST_PRIMS
+      x.LB() = fma(wq, vv * rsqrt_fast(vv), x.LB());
+#else
+      x.LB() = fma(wq, sqrt(vv), x.LB());
+#endif
+    }
+#pragma unroll
+    for (int j = 0; j < NT; j++) x.LI(j) = fma(wq, sig[j], x.LI(j));
+#pragma unroll
+    for (int i = 0; i < 3; i++) {
+      Rd[i] = fma(sR[i + 3], su[2], -sR[i + 6] * su[1]);
+      Rd[i + 3] = fma(sR[i + 6], su[0], -sR[i] * su[2]);
+      Rd[i + 6] = fma(sR[i], su[1], -sR[i + 3] * su[0]);
+    }
+#pragma unroll
+    for (int i = 0; i < 9; i++) { x.AR(i) = fma(wk, Rd[i], x.AR(i)); x.SR(i) = fma(a, Rd[i], x.R(i)); }
+#pragma unroll
+    for (int i = 0; i < 3; i++) {
+      x.AV(i) = fma(wk, vd[i], x.AV(i)); x.AU(i) = fma(wk, ud[i], x.AU(i));
+      sv[i] = fma(a, vd[i], x.V(i)); su[i] = fma(a, ud[i], x.U(i));
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 9; i++) x.R(i) = fma(w1, x.AR(i), x.R(i));
+#pragma unroll
+  for (int i = 0; i < 3; i++) { x.V(i) = fma(w1, x.AV(i), x.V(i)); x.U(i) = fma(w1, x.AU(i), x.U(i)); }
 }
 
 struct RotZ {
@@ -317,9 +451,9 @@ struct RotZ {
   int on;
 };
 
-template <int NT>
+template <int NT, bool SM>
 __device__ __forceinline__ void emit_node(const irt_fk_outputs &o, int64_t row_base, int k,
-                                          double t, const FkState<NT> &x, const RotZ &rz) {
+                                          double t, const FkState<NT, SM> &x, const RotZ &rz) {
   const int64_t row = row_base + k;
   const double p0 = x.P(0), p1 = x.P(1), p2 = x.P(2);
   double px = p0, py = p1;
@@ -336,7 +470,7 @@ __device__ __forceinline__ void emit_node(const irt_fk_outputs &o, int64_t row_b
     double *dst = o.R + row * 9;
 #pragma unroll
     for (int j = 0; j < 3; j++) {
-      double r0 = x.R[3 * j], r1 = x.R[3 * j + 1];
+      double r0 = x.R(3 * j), r1 = x.R(3 * j + 1);
       if (rz.on) {
         dst[3 * j] = rz.c * r0 - rz.s * r1;
         dst[3 * j + 1] = rz.s * r0 + rz.c * r1;
@@ -344,40 +478,109 @@ __device__ __forceinline__ void emit_node(const irt_fk_outputs &o, int64_t row_b
         dst[3 * j] = r0;
         dst[3 * j + 1] = r1;
       }
-      dst[3 * j + 2] = x.R[3 * j + 2];
+      dst[3 * j + 2] = x.R(3 * j + 2);
     }
   }
 }
 
-// FK_MAXNREG (experiments, tools/time_fk_variants.py): an explicit register cap instead of the minimum-blocks
-// hint, which only ever yields 255 or 168 registers here.  Measured: 200 registers x 10 warps/SM and 224 x 9
-// are 7-16 % slower than 255 x 8 (profiles/README.md) -- the spills cost more than the warps bring.
-#ifdef FK_MAXNREG
-#define FK_KERNEL_BOUNDS __maxnreg__(FK_MAXNREG)
-#else
-#define FK_KERNEL_BOUNDS __launch_bounds__(FK_THREADS, FK_MIN_BLOCKS)
-#endif
-template <int NT, bool RETRACT>
-__global__ void FK_KERNEL_BOUNDS
-fk_rk4_fp64_kernel(const RobotDev rb, const double *__restrict__ states, int state_size, int64_t n,
-                   int cap_pts, const irt_fk_outputs o, const int32_t *__restrict__ perm,
-                   const int64_t *__restrict__ row_off) {
+// ---- bucket keys ------------------------------------------------------------------------------
+// Configurations are counting-sorted by (RK4 step count, tension bin) before the RK4 kernel so that the lanes
+// of a warp run the same number of steps (retraction) and about the same number of fixed-point iterations
+// (solve_initial_bending.cpp:41-70: the iteration count grows with the tension; binning sum(tau) brings the
+// warp-max of a C2 batch from 33 to 24 iterations at a mean of 17.5).  key = bucket | K << 16, where K is the
+// node count of util::range's accumulation (vector_ops.h:67-75) -- evaluated ONCE here, in a memory-bound
+// kernel, instead of as a latency-bound chain of dependent additions in front of every shape.
+constexpr int FK_TAU_BINS = 8;
+constexpr int FK_K_BAD = 0xFFFF;   // the grid would exceed max_points (s < 0 beyond the first gap)
+
+__device__ __forceinline__ int fk_bucket_key(const RobotDev &rb, const double *st, int state_size, int *K_out) {
+  int T = 0, K = 0;
+  if (rb.enable_retraction) {
+    const double s = st[state_size - 1];
+    if (s >= -rb.dL && s < rb.L) {
+      const double lim = rb.L - (rb.dL / 2);
+      for (double p = s; p <= lim; p += rb.dL) K++;
+      if (K > rb.Kfull) {
+        K = FK_K_BAD;   // flagged IRT_FLAG_BAD_STATE by the FK kernel
+      } else if (K >= 1) {
+        const double t1 = rb.node_t[K - 1];
+        const double h0 = fmin(rb.dL, t1 - s);
+        T = K - 1 + ((t1 - (s + h0) > 2.220446049250313e-16) ? 2 : 1);
+      }
+    }
+  } else {
+    K = rb.Kfull;
+    T = rb.Kfull - 1 + ((rb.n_head == 4) ? 2 : 1);
+  }
+  double ts = 0.0;
+  for (int j = 0; j < rb.n_tendons; j++) ts += st[j];
+  int bin = (int)(ts * rb.tau_bin_scale);
+  bin = (bin < 0 || !(ts == ts)) ? 0 : (bin >= FK_TAU_BINS ? FK_TAU_BINS - 1 : bin);
+  *K_out = K;
+  return T * FK_TAU_BINS + bin;
+}
+
+struct FkArgs {
+  const double *states;   // [.][state_size]; configuration i of this launch is row lo + i
+  int state_size;
+  int64_t n;              // number of configurations (d_range == nullptr) or an upper bound of it
+  const int32_t *range;   // device {lo, hi} or nullptr (lo = 0, hi = n)
+  int cap_pts;
+  irt_fk_outputs o;       // output arrays are indexed by the absolute row lo + i
+  const int32_t *perm;    // [n] bucket order (relative indices)
+  const int32_t *keys;    // [n] bucket | K << 16 (relative indices)
+  const int64_t *row_off; // packed rows (absolute index) or nullptr
+  int32_t *work;          // dynamic work counter (zero at launch)
+};
+
+#define FK_KERNEL_BOUNDS __launch_bounds__(SM ? FK_SM_THREADS : FK_THREADS, SM ? 1 : FK_MIN_BLOCKS)
+
+// Persistent kernel: FK_MIN_BLOCKS CTAs per SM stage the routing table once, then every WARP fetches the next
+// 32 configurations of the bucket order from a global counter until the batch is done (no CTA-wide barrier after
+// the staging, no tail of half-empty CTAs, and the batch size may live in device memory: K2's bisection rounds
+// launch this kernel without the host knowing how many samples a round has).
+template <int NT, bool RETRACT, bool SM>
+__global__ void FK_KERNEL_BOUNDS fk_rk4_fp64_kernel(const RobotDev rb, const FkArgs a) {
+  constexpr int THREADS = SM ? FK_SM_THREADS : FK_THREADS;
   extern __shared__ double smem[];
   double *tab = smem;                                // [n_table][NT][6]
   double *head = smem + (size_t)rb.n_table * NT * 6; // [4][NT][6]
-#if FK_SMEM_ACC >= 1
-  double *acc_smem = head + 4 * NT * 6;              // [4 + NT][FK_THREADS]
-#endif
+  int64_t lo = 0, n = a.n;
+  if (a.range) { lo = a.range[0]; n = (int64_t)a.range[1] - lo; }
+  if (n <= 0 || (int64_t)blockIdx.x * THREADS >= n) return;   // the other CTAs cover the batch
   for (int i = threadIdx.x; i < rb.n_table * NT * 6; i += blockDim.x) tab[i] = rb.table[i];
   for (int i = threadIdx.x; i < 4 * NT * 6; i += blockDim.x) head[i] = rb.head[i];
   __syncthreads();
+  const irt_fk_outputs &o = a.o;
+  const int state_size = a.state_size, cap_pts = a.cap_pts;
+  const double Kse[3] = {rb.Kse[0], rb.Kse[1], rb.Kse[2]};
+  const double Kbt[3] = {rb.Kbt[0], rb.Kbt[1], rb.Kbt[2]};
+  const int lane = threadIdx.x & 31;
 
-  const int64_t gi = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+#if FK_PERSIST
+  // every WARP fetches the next 32 configurations of the bucket order from a global counter
+#pragma unroll 1
+  for (;;) {
+  int64_t wbase = 0;
+  if (lane == 0) wbase = (int64_t)atomicAdd(a.work, 32);
+  wbase = __shfl_sync(0xffffffffu, wbase, 0);
+  if (wbase >= n) break;
+  const int64_t gi = wbase + lane;
+#else
+  // block-strided: with a host-known batch the grid has one CTA per 128 configurations (the hardware hands
+  // CTAs to SMs as slots free up, and the warps of a CTA walk the code in step: instruction-cache friendly);
+  // with a device-side batch size (K2) a resident grid strides over it
+#pragma unroll 1
+  for (int64_t blk = blockIdx.x; blk * THREADS < n; blk += gridDim.x) {
+  const int64_t gi = blk * THREADS + threadIdx.x;
+  (void)lane;
+#endif
   const bool in_range = gi < n;
-  const int64_t cfg = in_range ? (perm ? (int64_t)perm[gi] : gi) : 0;
-  const double *st = states + cfg * state_size;
+  const int64_t rel = in_range ? (a.perm ? (int64_t)a.perm[gi] : gi) : 0;
+  const int64_t cfg = lo + rel;
+  const double *st = a.states + cfg * state_size;
   // first output row of this configuration: dense [n][cap_pts] layout, or packed rows (row_off[cfg])
-  const int64_t row_base = row_off ? (in_range ? row_off[cfg] : 0) : cfg * cap_pts;
+  const int64_t row_base = a.row_off ? (in_range ? a.row_off[cfg] : 0) : cfg * cap_pts;
 
   double tau[NT];
 #pragma unroll
@@ -389,8 +592,6 @@ fk_rk4_fp64_kernel(const RobotDev rb, const double *__restrict__ states, int sta
   }
   double s_start = 0.0;
   if (RETRACT) s_start = in_range ? st[state_size - 1] : 0.0;
-  const double Kse[3] = {rb.Kse[0], rb.Kse[1], rb.Kse[2]};
-  const double Kbt[3] = {rb.Kbt[0], rb.Kbt[1], rb.Kbt[2]};
 
   uint32_t flags = 0;
   bool active = in_range;
@@ -405,13 +606,13 @@ fk_rk4_fp64_kernel(const RobotDev rb, const double *__restrict__ states, int sta
   }
   if (s_start > rb.L) s_start = rb.L;  // TendonRobot.cpp:359
 
-  // number of nodes K: util::range's accumulation (vector_ops.h:67-75), bit-for-bit
+  // number of nodes K: util::range's accumulation (vector_ops.h:67-75), bit-for-bit -- taken from the bucket
+  // key (fk_bucket_key ran the accumulation)
   int K = 0;
   if (active) {
     if (RETRACT) {
-      const double lim = rb.L - (rb.dL / 2);
-      for (double pacc = s_start; pacc <= lim; pacc += rb.dL) K++;
-      if (K > rb.Kfull) {   // only possible for s < 0: one grid point more than the outputs hold
+      K = (int)((uint32_t)a.keys[rel] >> 16);
+      if (K == FK_K_BAD) {   // only possible for s < 0: one grid point more than the outputs hold
         flags |= IRT_FLAG_BAD_STATE;
         active = false;
         K = 0;
@@ -422,36 +623,69 @@ fk_rk4_fp64_kernel(const RobotDev rb, const double *__restrict__ states, int sta
   }
   const bool degenerate = active && (s_start == rb.L);  // TendonRobot.cpp:361-372
 
-  FkState<NT> x;
-#if FK_SMEM_ACC >= 1
-  x.sm = acc_smem + threadIdx.x;
-#endif
+  FkState<NT, SM> x;
+  if constexpr (SM) x.sm = head + 4 * NT * 6 + threadIdx.x;   // [fk_sm_slots][FK_SM_THREADS] behind the tables
 #pragma unroll
-  for (int i = 0; i < 3; i++) { x.P(i) = 0; x.v[i] = 0; x.u[i] = 0; }
+  for (int i = 0; i < 3; i++) { x.P(i) = 0; x.V(i) = 0; x.U(i) = 0; }
 #pragma unroll
-  for (int i = 0; i < 9; i++) x.R[i] = 0;
-  x.R[0] = x.R[4] = x.R[8] = 1.0;
-  x.v[2] = 1.0;
+  for (int i = 0; i < 9; i++) x.R(i) = 0;
+  x.R(0) = x.R(4) = x.R(8) = 1.0;
+  x.V(2) = 1.0;
   x.LB() = 0;
 #pragma unroll
   for (int j = 0; j < NT; j++) x.LI(j) = 0;
 
   int iters = 0, nsteps = 0;
   double u0[3] = {0, 0, 0}, v0[3] = {0, 0, 1};
-  double rt_local[NT * 6];
+  double rt_local[NT * 6], rt_h1[NT * 6], rt_h2[NT * 6], rt_h3[NT * 6];
   const bool run = active && !degenerate;
   // L - dL/2 < s < L: the grid is the single point {s} (K == 0), nothing to integrate
   const bool integ = run && K >= 1;
 
+  // ---- head: the irregular first gap s -> node K-1 takes one or two steps (h = min(dL, t_next - t),
+  // repeated while t_next - t > eps, odeint integrate_times) -------------------------------------
+  int nhead = 0;
+  double hh0 = 0.0, hh1 = 0.0;
+  const double *hd0 = head, *hd1 = head + NT * 6, *hd2 = head + 2 * NT * 6, *hd3 = head + 3 * NT * 6;
+  if (RETRACT) {
+    double tc = s_start;
+    if (integ) {
+      const double eps = 2.220446049250313e-16;
+      const double t1 = rb.node_t[K - 1];
+      hh0 = fmin(rb.dL, t1 - s_start);
+      nhead = 1;
+      tc = s_start + hh0;
+      if (t1 - tc > eps) {
+        hh1 = fmin(rb.dL, t1 - tc);
+        nhead = 2;
+      }
+    }
+    if (run) {   // routing at s (initial condition) and at the stage times of the head steps
+      const double tt[4] = {s_start, s_start + 0.5 * hh0, tc, tc + 0.5 * hh1};
+      double *const oo[4] = {rt_local, rt_h1, rt_h2, rt_h3};
+      if (rb.simple_routing) {
+        routing_eval_simple<NT, 4>(rb, tt, oo);
+      } else {
+        routing_eval<NT>(rb, tt[0], rt_local);
+        if (integ) {
+          routing_eval<NT>(rb, tt[1], rt_h1);
+          if (nhead == 2) {
+            routing_eval<NT>(rb, tt[2], rt_h2);
+            routing_eval<NT>(rb, tt[3], rt_h3);
+          }
+        }
+      }
+    }
+    hd0 = rt_local; hd1 = rt_h1; hd2 = rt_h2; hd3 = rt_h3;
+  } else if (integ) {
+    nhead = (rb.n_head == 4) ? 2 : 1;
+    hh0 = rb.head_h[0];
+    hh1 = rb.head_h[1];
+  }
+
   if (run) {
     // ---- initial condition: solve_initial_bending.cpp:15-73 ------------------------------
-    const double *rt_s;
-    if (RETRACT) {
-      routing_eval<NT>(rb, s_start, rt_local);
-      rt_s = rt_local;
-    } else {
-      rt_s = head;
-    }
+    const double *rt_s = RETRACT ? rt_local : head;
     double v[3] = {0, 0, 1}, u[3] = {0, 0, 0};
     // Same iteration as the reference; the unit vectors use rsqrt and the three exit tests
     // compare squares (residual < thr <=> residual^2 < thr^2, |dv| < 1e-9 |v| <=> |dv|^2 <
@@ -488,7 +722,7 @@ fk_rk4_fp64_kernel(const RobotDev rb, const double *__restrict__ states, int sta
       u[0] = un0; u[1] = un1; u[2] = un2;
     }
 #pragma unroll
-    for (int i = 0; i < 3; i++) { x.v[i] = v0[i] = v[i]; x.u[i] = u0[i] = u[i]; }
+    for (int i = 0; i < 3; i++) { x.V(i) = v0[i] = v[i]; x.U(i) = u0[i] = u[i]; }
 
     // ---- convergence flag: calc_point_forces at the base, R = I (TendonRobot.cpp:188-217) --
     {
@@ -512,36 +746,10 @@ fk_rk4_fp64_kernel(const RobotDev rb, const double *__restrict__ states, int sta
   }
 
   // ---- integrate_times(runge_kutta4) over the grid {s} U {node K-1 .. node 0} --------------
-  // Head: the irregular first gap s -> node K-1 takes one or two steps (h = min(dL, t_next - t),
-  // repeated while t_next - t > eps).  Then the regular steps node q -> node q-1.  All steps run
-  // through ONE rk4_step call site in a loop that is end-aligned across the warp, so that every
-  // lane is at the same regular step q in the same iteration (table reads are broadcasts).
-  if (run) emit_node<NT>(o, row_base, 0, s_start, x, rz);
-  int nhead = 0;
-  double hh0 = 0.0, hh1 = 0.0;
-  const double *hd0 = head, *hd1 = head + NT * 6, *hd2 = head + 2 * NT * 6, *hd3 = head + 3 * NT * 6;
-  double rt_h1[NT * 6], rt_h2[NT * 6], rt_h3[NT * 6];
-  if (integ) {
-    if (RETRACT) {
-      const double eps = 2.220446049250313e-16;
-      const double t1 = rb.node_t[K - 1];
-      hh0 = fmin(rb.dL, t1 - s_start);
-      routing_eval<NT>(rb, s_start + 0.5 * hh0, rt_h1);
-      nhead = 1;
-      if (t1 - (s_start + hh0) > eps) {
-        const double tc = s_start + hh0;
-        hh1 = fmin(rb.dL, t1 - tc);
-        routing_eval<NT>(rb, tc, rt_h2);
-        routing_eval<NT>(rb, tc + 0.5 * hh1, rt_h3);
-        nhead = 2;
-      }
-      hd0 = rt_local; hd1 = rt_h1; hd2 = rt_h2; hd3 = rt_h3;
-    } else {
-      nhead = (rb.n_head == 4) ? 2 : 1;
-      hh0 = rb.head_h[0];
-      hh1 = rb.head_h[1];
-    }
-  }
+  // Head steps, then the regular steps node q -> node q-1.  All steps run through ONE rk4_step call site in
+  // a loop that is end-aligned across the warp, so that every lane is at the same regular step q in the
+  // same iteration (table reads are broadcasts).
+  if (run) emit_node<NT, SM>(o, row_base, 0, s_start, x, rz);
   {
     const int T = integ ? (K - 1 + nhead) : 0;
     int Tmax = T;
@@ -572,15 +780,15 @@ fk_rk4_fp64_kernel(const RobotDev rb, const double *__restrict__ states, int sta
         emit_idx = -1;
       }
       rk4_step<NT>(x, tau, Kse, Kbt, h, p0, p1, p2);
-      if (emit_idx >= 0) emit_node<NT>(o, row_base, emit_idx, rb.node_t[K - emit_idx], x, rz);
+      if (emit_idx >= 0) emit_node<NT, SM>(o, row_base, emit_idx, rb.node_t[K - emit_idx], x, rz);
     }
   }
 
-  if (!in_range) return;
+  if (!in_range) continue;
   int npts = 0;
   if (degenerate) {
     npts = 1;
-    emit_node<NT>(o, row_base, 0, s_start, x, rz);  // p = 0, R = I, v = e3, u = 0
+    emit_node<NT, SM>(o, row_base, 0, s_start, x, rz);  // p = 0, R = I, v = e3, u = 0
   } else if (run) {
     npts = K + 1;
   }
@@ -609,39 +817,30 @@ fk_rk4_fp64_kernel(const RobotDev rb, const double *__restrict__ states, int sta
   if (o.uv) {
     double *d = o.uv + cfg * 12;
 #pragma unroll
-    for (int i = 0; i < 3; i++) { d[i] = u0[i]; d[3 + i] = x.u[i]; d[6 + i] = v0[i]; d[9 + i] = x.v[i]; }
+    for (int i = 0; i < 3; i++) { d[i] = u0[i]; d[3 + i] = x.U(i); d[6 + i] = v0[i]; d[9 + i] = x.V(i); }
   }
   if (o.flags) o.flags[cfg] = flags;
   if (o.iters) o.iters[cfg] = iters;
   if (o.nsteps) o.nsteps[cfg] = nsteps;
+  }
 }
 
-// ---- bucket configurations by node count (descending) so warps stay converged --------------
-__global__ void fk_count_nodes_kernel(const RobotDev rb, const double *__restrict__ states,
-                                      int state_size, int64_t n, int32_t *__restrict__ keys,
-                                      int32_t *__restrict__ hist) {
+// ---- bucket configurations by (step count, tension bin), descending, so warps stay converged --------
+// grid-stride over the configurations [lo, hi) (device range or [0, n)); block-aggregated histogram
+__global__ void fk_count_nodes_kernel(const RobotDev rb, const double *__restrict__ states, int state_size,
+                                      int64_t n_host, const int32_t *__restrict__ range, int nb,
+                                      int32_t *__restrict__ keys, int32_t *__restrict__ hist) {
   extern __shared__ int32_t sh[];
-  const int nb = rb.Kfull + 2;
+  int64_t lo = 0, n = n_host;
+  if (range) { lo = range[0]; n = (int64_t)range[1] - lo; }
+  if ((int64_t)blockIdx.x * blockDim.x >= n) return;
   for (int i = threadIdx.x; i < nb; i += blockDim.x) sh[i] = 0;
   __syncthreads();
-  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) {
-    // bucket key = number of RK4 steps the configuration will take (K - 1 regular + 1 or 2 head)
-    double s = states[i * state_size + state_size - 1];
-    int T = 0;
-    if (s >= -rb.dL && s < rb.L) {
-      int K = 0;
-      const double lim = rb.L - (rb.dL / 2);
-      for (double p = s; p <= lim; p += rb.dL) K++;
-      if (K > rb.Kfull) K = 0;   // flagged IRT_FLAG_BAD_STATE by the FK kernel
-      if (K >= 1) {
-        const double t1 = rb.node_t[K - 1];
-        const double h0 = fmin(rb.dL, t1 - s);
-        T = K - 1 + ((t1 - (s + h0) > 2.220446049250313e-16) ? 2 : 1);
-      }
-    }
-    keys[i] = T;
-    atomicAdd(&sh[T], 1);
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    int K;
+    const int key = fk_bucket_key(rb, states + (lo + i) * state_size, state_size, &K);
+    keys[i] = key | (K << 16);
+    atomicAdd(&sh[key], 1);
   }
   __syncthreads();
   for (int k = threadIdx.x; k < nb; k += blockDim.x)
@@ -670,24 +869,20 @@ __global__ void fk_row_count_kernel(const RobotDev rb, const double *__restrict_
 
 // Scatter into buckets in DESCENDING key order.  hist[k] = number of configurations with key k (final: the
 // count kernel ran before on the same stream); cursor[k] = slots of bucket k handed out so far (zeroed).
-// Every block ranks its configurations per bucket in shared memory and reserves ONE contiguous run per
-// (block, bucket) with a single global atomic, so the ~n same-address atomics of a naive scatter become
-// ~n/256 * (occupied buckets); the bucket starts (an exclusive scan of <= a few hundred counts) are recomputed
+// Every block ranks the configurations of a tile per bucket in shared memory and reserves ONE contiguous run per
+// (tile, bucket) with a single global atomic, so the ~n same-address atomics of a naive scatter become
+// ~n/256 * (occupied buckets); the bucket starts (an exclusive scan of <= a few hundred counts) are computed
 // per block by warp 0 instead of by a kernel of their own.  Which slot inside its bucket a configuration gets
 // is arbitrary; results are written at the original index, so they do not depend on it.
-__global__ void fk_bucket_scatter_kernel(const int32_t *__restrict__ keys, int64_t n,
+__global__ void fk_bucket_scatter_kernel(const int32_t *__restrict__ keys, int64_t n_host,
+                                         const int32_t *__restrict__ range,
                                          const int32_t *__restrict__ hist, int32_t *__restrict__ cursor,
                                          int nb, int32_t *__restrict__ perm) {
   extern __shared__ int32_t sh[];
-  int32_t *cnt = sh, *base = sh + nb;   // per-bucket: configurations of this block, then first slot of its run
-  for (int k = threadIdx.x; k < nb; k += blockDim.x) cnt[k] = 0;
-  __syncthreads();
-  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  int key = 0, local = 0;
-  if (i < n) {
-    key = keys[i];
-    local = atomicAdd(&cnt[key], 1);
-  }
+  int32_t *cnt = sh, *base = sh + nb, *start = sh + 2 * nb;   // per bucket: tile count, run start, bucket start
+  int64_t n = n_host;
+  if (range) n = (int64_t)range[1] - range[0];
+  if ((int64_t)blockIdx.x * blockDim.x >= n) return;
   if (threadIdx.x < 32) {   // bucket starts: exclusive scan of hist from the highest key down
     const int lane = threadIdx.x;
     int32_t carry = 0;
@@ -700,40 +895,61 @@ __global__ void fk_bucket_scatter_kernel(const int32_t *__restrict__ keys, int64
         const int32_t t = __shfl_up_sync(0xffffffffu, incl, d);
         if (lane >= d) incl += t;
       }
-      if (k >= 0) base[k] = carry + incl - c;
+      if (k >= 0) start[k] = carry + incl - c;
       carry += __shfl_sync(0xffffffffu, incl, 31);
     }
   }
-  __syncthreads();
-  for (int k = threadIdx.x; k < nb; k += blockDim.x) {
-    const int32_t c = cnt[k];
-    if (c) base[k] += atomicAdd(&cursor[k], c);
+  for (int64_t t0 = (int64_t)blockIdx.x * blockDim.x; t0 < n; t0 += (int64_t)gridDim.x * blockDim.x) {
+    for (int k = threadIdx.x; k < nb; k += blockDim.x) cnt[k] = 0;
+    __syncthreads();
+    const int64_t i = t0 + threadIdx.x;
+    int key = 0, local = 0;
+    if (i < n) {
+      key = keys[i] & 0xFFFF;
+      local = atomicAdd(&cnt[key], 1);
+    }
+    __syncthreads();
+    for (int k = threadIdx.x; k < nb; k += blockDim.x) {
+      const int32_t c = cnt[k];
+      if (c) base[k] = start[k] + atomicAdd(&cursor[k], c);
+    }
+    __syncthreads();
+    if (i < n) perm[base[key] + local] = (int32_t)i;
+    __syncthreads();
   }
-  __syncthreads();
-  if (i < n) perm[base[key] + local] = (int32_t)i;
 }
 
-template <int NT>
-int launch_nt(irt_ctx *ctx, const irt_robot *rb, const double *d_states, int64_t n, int cap_pts,
-              const irt_fk_outputs &o, const int32_t *d_perm, const int64_t *d_row_off, cudaStream_t st) {
-  const RobotDev &d = rb->dev;
-  size_t smem = ((size_t)d.n_table + 4) * NT * 6 * sizeof(double);
-#if FK_SMEM_ACC >= 1
-  smem += (size_t)(4 + NT) * FK_THREADS * sizeof(double);
+template <int NT, bool RETRACT, bool SM>
+int launch_k(irt_ctx *ctx, const RobotDev &d, const FkArgs &a, size_t smem, cudaStream_t st) {
+  constexpr int THREADS = SM ? FK_SM_THREADS : FK_THREADS;
+  int64_t blocks = (a.n + THREADS - 1) / THREADS;
+  const int64_t resident = (int64_t)ctx->sm_count * (SM ? 1 : FK_MIN_BLOCKS);
+#if FK_PERSIST
+  if (blocks > resident) blocks = resident;
+#else
+  if (a.range && blocks > resident) blocks = resident;   // batch size only known on the device: strided grid
 #endif
-  const int64_t blocks = (n + FK_THREADS - 1) / FK_THREADS;
-  if (d.enable_retraction) {
-    auto k = fk_rk4_fp64_kernel<NT, true>;
-    IRT_CUDA(ctx, cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k<<<(unsigned)blocks, FK_THREADS, smem, st>>>(d, d_states, rb->state_size, n, cap_pts, o, d_perm, d_row_off);
-  } else {
-    auto k = fk_rk4_fp64_kernel<NT, false>;
-    IRT_CUDA(ctx, cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k<<<(unsigned)blocks, FK_THREADS, smem, st>>>(d, d_states, rb->state_size, n, cap_pts, o, d_perm, d_row_off);
-  }
+  auto k = fk_rk4_fp64_kernel<NT, RETRACT, SM>;
+  IRT_CUDA(ctx, cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  k<<<(unsigned)blocks, THREADS, smem, st>>>(d, a);
   IRT_LAUNCHED(ctx);
   IRT_CUDA(ctx, cudaGetLastError());
   return IRT_OK;
+}
+
+template <int NT>
+int launch_nt(irt_ctx *ctx, const irt_robot *rb, const FkArgs &a, cudaStream_t st) {
+  const RobotDev &d = rb->dev;
+  const size_t smem = ((size_t)d.n_table + 4) * NT * 6 * sizeof(double);
+#if FK_SMEM_VARIANT
+  // state in shared memory, 12 warps per SM: when the slots fit beside the routing table
+  const size_t smem_sm = smem + (size_t)fk_sm_slots<NT>() * FK_SM_THREADS * sizeof(double);
+  if (ctx->fk_smem && smem_sm <= 227 * 1024)
+    return d.enable_retraction ? launch_k<NT, true, true>(ctx, d, a, smem_sm, st)
+                               : launch_k<NT, false, true>(ctx, d, a, smem_sm, st);
+#endif
+  return d.enable_retraction ? launch_k<NT, true, false>(ctx, d, a, smem, st)
+                             : launch_k<NT, false, false>(ctx, d, a, smem, st);
 }
 
 }  // namespace
@@ -751,47 +967,76 @@ int fk_row_counts(irt_ctx *ctx, const irt_robot *rb, const double *d_states, int
   return IRT_OK;
 }
 
-// d_perm == nullptr: when retraction is enabled a bucket permutation is built in ctx scratch.
+static int fk_num_buckets(const irt_robot *rb) { return (rb->dev.Kfull + 2) * FK_TAU_BINS; }
+
+// device scratch one FK launch over up to n configurations needs: keys[n], perm[n], hist / cursor / work counter
+size_t fk_work_bytes(const irt_robot *rb, int64_t n) {
+  return (((size_t)n * 8 + 255) & ~(size_t)255) + (((size_t)fk_num_buckets(rb) * 8 + 64 + 255) & ~(size_t)255);
+}
+
+// K1 over configurations [0, n) of d_states -- or, d_range != nullptr, over rows [lo, hi) of d_states and of the
+// output arrays with {lo, hi} read from device memory at run time (n = an upper bound of hi - lo).  work:
+// fk_work_bytes(rb, n) bytes of device scratch, or nullptr to use the context's scratch buffer.
 int fk_launch(irt_ctx *ctx, const irt_robot *rb, const double *d_states, int64_t n, int cap_pts,
-              const irt_fk_outputs &o, const int32_t *d_perm, cudaStream_t st, const int64_t *d_row_off) {
+              const irt_fk_outputs &o, cudaStream_t st, const int64_t *d_row_off, const int32_t *d_range,
+              void *work) {
   if (n <= 0) return IRT_OK;
-  if (n > 0x7fffffffLL) return irt_fail(ctx, IRT_ERR_INVALID_ARGUMENT, "batch too large");
+  if (n > 0x7ff00000LL) return irt_fail(ctx, IRT_ERR_INVALID_ARGUMENT, "batch too large");
   const RobotDev &d = rb->dev;
   size_t smem = ((size_t)d.n_table + 4) * d.n_tendons * 6 * sizeof(double);
   if (smem > 200 * 1024)
     return irt_fail(ctx, IRT_ERR_CAPACITY, "routing table (%zu B) exceeds shared memory", smem);
-  if (d.enable_retraction && !d_perm) {
-    const int nb = d.Kfull + 2;
-    size_t bytes = (size_t)n * 4 * 2 + (size_t)nb * 4 * 2 + 256;
-    char *scr = (char *)ctx_scratch(ctx, bytes);
-    if (!scr) return irt_fail(ctx, IRT_ERR_CUDA, "scratch alloc of %zu bytes failed", bytes);
-    int32_t *keys = (int32_t *)scr;
-    int32_t *perm = keys + n;
-    int32_t *hist = perm + n;      // [nb] counts, then [nb] cursors
-    int32_t *cursor = hist + nb;
-    IRT_CUDA(ctx, cudaMemsetAsync(hist, 0, (size_t)nb * 4 * 2, st));
+  const int nb = fk_num_buckets(rb);
+  if (nb > 0xFFFF || (size_t)nb * 12 > 96 * 1024)
+    return irt_fail(ctx, IRT_ERR_CAPACITY, "too many step-count buckets (%d)", nb);
+  char *scr = (char *)work;
+  if (!scr) {
+    scr = (char *)ctx_scratch(ctx, fk_work_bytes(rb, n));
+    if (!scr) return irt_fail(ctx, IRT_ERR_CUDA, "scratch alloc of %zu bytes failed", fk_work_bytes(rb, n));
+  }
+  int32_t *keys = (int32_t *)scr;
+  int32_t *perm = keys + n;
+  int32_t *hist = (int32_t *)(scr + (((size_t)n * 8 + 255) & ~(size_t)255));   // [nb] counts, [nb] cursors, work
+  int32_t *cursor = hist + nb;
+  int32_t *workctr = cursor + nb;
+  IRT_CUDA(ctx, cudaMemsetAsync(hist, 0, (size_t)nb * 8 + 16, st));
+  FkArgs a;
+  a.states = d_states; a.state_size = rb->state_size; a.n = n; a.range = d_range; a.cap_pts = cap_pts;
+  a.o = o; a.perm = nullptr; a.keys = nullptr; a.row_off = d_row_off; a.work = workctr;
+  // Bucketing pays when warps would otherwise diverge: with retraction (step counts differ) always; without it
+  // only the fixed-point iteration counts differ, which a batch large enough to fill the GPU several times
+  // over amortises (small batches skip the two extra launches)
+  if (d.enable_retraction) {
     const int T = 256;
-    const unsigned B = (unsigned)((n + T - 1) / T);
-    fk_count_nodes_kernel<<<B, T, nb * sizeof(int32_t), st>>>(d, d_states, rb->state_size, n, keys, hist);
+    int64_t B = (n + T - 1) / T;
+    const int64_t maxB = (int64_t)ctx->sm_count * 8;
+    if (B > maxB) B = maxB;
+    fk_count_nodes_kernel<<<(unsigned)B, T, nb * sizeof(int32_t), st>>>(d, d_states, rb->state_size, n, d_range, nb,
+                                                                     keys, hist);
     IRT_LAUNCHED(ctx);
-    fk_bucket_scatter_kernel<<<B, T, 2 * nb * sizeof(int32_t), st>>>(keys, n, hist, cursor, nb, perm);
+    if ((size_t)nb * 12 > 48 * 1024)
+      IRT_CUDA(ctx, cudaFuncSetAttribute(fk_bucket_scatter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         nb * 12));
+    fk_bucket_scatter_kernel<<<(unsigned)B, T, 3 * nb * sizeof(int32_t), st>>>(keys, n, d_range, hist, cursor, nb,
+                                                                            perm);
     IRT_LAUNCHED(ctx);
     IRT_CUDA(ctx, cudaGetLastError());
-    d_perm = perm;
+    a.perm = perm;
+    a.keys = keys;
   }
   switch (d.n_tendons) {
-    case 1: return launch_nt<1>(ctx, rb, d_states, n, cap_pts, o, d_perm, d_row_off, st);
-    case 2: return launch_nt<2>(ctx, rb, d_states, n, cap_pts, o, d_perm, d_row_off, st);
-    case 3: return launch_nt<3>(ctx, rb, d_states, n, cap_pts, o, d_perm, d_row_off, st);
-    case 4: return launch_nt<4>(ctx, rb, d_states, n, cap_pts, o, d_perm, d_row_off, st);
-    case 5: return launch_nt<5>(ctx, rb, d_states, n, cap_pts, o, d_perm, d_row_off, st);
-    case 6: return launch_nt<6>(ctx, rb, d_states, n, cap_pts, o, d_perm, d_row_off, st);
-    case 7: return launch_nt<7>(ctx, rb, d_states, n, cap_pts, o, d_perm, d_row_off, st);
-    case 8: return launch_nt<8>(ctx, rb, d_states, n, cap_pts, o, d_perm, d_row_off, st);
-    case 9: return launch_nt<9>(ctx, rb, d_states, n, cap_pts, o, d_perm, d_row_off, st);
-    case 10: return launch_nt<10>(ctx, rb, d_states, n, cap_pts, o, d_perm, d_row_off, st);
-    case 11: return launch_nt<11>(ctx, rb, d_states, n, cap_pts, o, d_perm, d_row_off, st);
-    case 12: return launch_nt<12>(ctx, rb, d_states, n, cap_pts, o, d_perm, d_row_off, st);
+    case 1: return launch_nt<1>(ctx, rb, a, st);
+    case 2: return launch_nt<2>(ctx, rb, a, st);
+    case 3: return launch_nt<3>(ctx, rb, a, st);
+    case 4: return launch_nt<4>(ctx, rb, a, st);
+    case 5: return launch_nt<5>(ctx, rb, a, st);
+    case 6: return launch_nt<6>(ctx, rb, a, st);
+    case 7: return launch_nt<7>(ctx, rb, a, st);
+    case 8: return launch_nt<8>(ctx, rb, a, st);
+    case 9: return launch_nt<9>(ctx, rb, a, st);
+    case 10: return launch_nt<10>(ctx, rb, a, st);
+    case 11: return launch_nt<11>(ctx, rb, a, st);
+    case 12: return launch_nt<12>(ctx, rb, a, st);
     default:
       return irt_fail(ctx, IRT_ERR_UNSUPPORTED, "no fk kernel for %d tendons (1..%d supported)",
                       d.n_tendons, IRT_MAX_TENDONS);

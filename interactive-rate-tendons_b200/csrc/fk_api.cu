@@ -28,7 +28,8 @@ int check_fk_args(irt_ctx *ctx, const irt_robot *rb, const void *states, int sta
   if (state_size != rb->state_size)  // TendonRobot.h:107-109 std::invalid_argument
     return irt_fail(ctx, IRT_ERR_INVALID_ARGUMENT, "State is not the right size (%d != %d)",
                     state_size, rb->state_size);
-  if ((out->p || out->R || out->t) && cap_pts < rb->max_points)
+  // flags also need it: the self-collision test reads points staged at stride cap_pts
+  if ((out->p || out->R || out->t || out->flags) && cap_pts < rb->max_points)
     return irt_fail(ctx, IRT_ERR_CAPACITY, "cap_pts=%d < max_points=%d", cap_pts, rb->max_points);
   return IRT_OK;
 }
@@ -48,7 +49,7 @@ int irt_fk_batch_dev(irt_ctx *ctx, const irt_robot *rb, const double *d_states, 
   if (o.flags && !(o.p && o.npts))
     return irt_fail(ctx, IRT_ERR_INVALID_ARGUMENT,
                     "flags output needs p and npts outputs (self-collision reads the points)");
-  rc = fk_launch(ctx, rb, d_states, n, cap_pts, o, nullptr, st);
+  rc = fk_launch(ctx, rb, d_states, n, cap_pts, o, st);
   if (rc) return rc;
   if (o.flags) rc = self_collision_launch(ctx, rb, o.p, o.npts, n, cap_pts, o.flags, st);
   return rc;
@@ -124,7 +125,7 @@ int irt_fk_batch(irt_ctx *ctx, const irt_robot *rb, const double *states, int st
     if (o.p) IRT_CUDA(ctx, cudaMemsetAsync(o.p, 0, (size_t)m * cap_pts * 24, st));
     if (o.R) IRT_CUDA(ctx, cudaMemsetAsync(o.R, 0, (size_t)m * cap_pts * 72, st));
     if (o.t) IRT_CUDA(ctx, cudaMemsetAsync(o.t, 0, (size_t)m * cap_pts * 8, st));
-    rc = fk_launch(ctx, rb, s.states, m, cap_pts, o, nullptr, st);
+    rc = fk_launch(ctx, rb, s.states, m, cap_pts, o, st);
     if (rc) return rc;
     if (o.flags) {
       rc = self_collision_launch(ctx, rb, o.p, o.npts, m, cap_pts, o.flags, st);
@@ -250,7 +251,7 @@ int irt_fk_batch_packed(irt_ctx *ctx, const irt_robot *rb, const double *states,
     std::memset(&o, 0, sizeof(o));
     o.p = s.p; o.R = s.R; o.t = s.t; o.npts = s.npts; o.L = s.L; o.L_i = s.Li;
     o.tip = s.tip; o.uv = s.uv; o.flags = s.flags; o.iters = s.iters; o.nsteps = s.nsteps;
-    rc = fk_launch(ctx, rb, s.states, m, cap_pts, o, nullptr, st, s.off);
+    rc = fk_launch(ctx, rb, s.states, m, cap_pts, o, st, s.off);
     if (rc) return rc;
     if (o.flags) {
       rc = self_collision_launch(ctx, rb, o.p, o.npts, m, cap_pts, o.flags, st, s.off);

@@ -123,7 +123,7 @@ int irt_fk_tip_jacobian_batch_dev(irt_ctx *ctx, const irt_robot *rb, const doubl
   IRT_LAUNCHED(ctx);
   irt_fk_outputs o{};
   o.tip = tips;
-  int rc = fk_launch(ctx, rb, pert, m, rb->max_points, o, nullptr, st);
+  int rc = fk_launch(ctx, rb, pert, m, rb->max_points, o, st);
   if (rc) return rc;
   jac_diff_kernel<<<(unsigned)((n * S + T - 1) / T), T, 0, st>>>(
       d_states, pert, tips, S, n, mode, delta, evals, rb->desc.enable_retraction, rb->desc.L, d_tips, d_J);

@@ -82,24 +82,35 @@ __device__ bool capsules_collide(const P3 &a0, const P3 &a1, const P3 &b0, const
 // given to the same lane so that lanes carry equal work.
 constexpr int SC_FILTER_WARPS = 8;
 
+// LPS = lanes per shape: 32, or 16 when a shape has so few capsules that half a warp covers its pair rows
+// (P = 41: 15 row pairs) -- then a warp filters two shapes at once.  All warp-level operations use the group's
+// own lane mask, so the two halves may run different trip counts.
+template <int LPS>
 __global__ void __launch_bounds__(SC_FILTER_WARPS * 32)
-self_collision_filter_kernel(const double *__restrict__ p, const int32_t *__restrict__ npts, int64_t n,
-                             int cap_pts, double r, int32_t *__restrict__ cand, int32_t *__restrict__ n_cand,
+self_collision_filter_kernel(const double *__restrict__ p, const int32_t *__restrict__ npts, int64_t n_host,
+                             const int32_t *__restrict__ range, int cap_pts, double r,
+                             int32_t *__restrict__ cand, int32_t *__restrict__ n_cand,
                              const int64_t *__restrict__ row_off) {
   extern __shared__ float fsm[];
+  constexpr int GPW = 32 / LPS;                                  // groups (shapes) per warp
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  float4 *seg = reinterpret_cast<float4 *>(fsm) + (size_t)warp * cap_pts;  // (mid.x, mid.y, mid.z, half length)
+  const int grp = lane / LPS, gl = lane % LPS;
+  const unsigned gmask = (LPS == 32) ? 0xffffffffu : (0xffffu << (16 * grp));
+  float4 *seg = reinterpret_cast<float4 *>(fsm) + (size_t)(warp * GPW + grp) * cap_pts;  // (mid.x, mid.y, mid.z, half length)
   const float rr = (float)(2.0 * r) * 1.00001f + 1e-6f;
+  int64_t lo = 0, n = n_host;
+  if (range) { lo = range[0]; n = (int64_t)range[1] - lo; }   // rows [lo, hi) with the bounds in device memory
 
-  for (int64_t shape = (int64_t)blockIdx.x * SC_FILTER_WARPS + warp; shape < n;
-       shape += (int64_t)gridDim.x * SC_FILTER_WARPS) {
+  for (int64_t w = ((int64_t)blockIdx.x * SC_FILTER_WARPS + warp) * GPW + grp; w < n;
+       w += (int64_t)gridDim.x * SC_FILTER_WARPS * GPW) {
+    const int64_t shape = lo + w;
     const int N = npts[shape];
-    __syncwarp();
+    __syncwarp(gmask);
     if (N <= 3) continue;  // collision.cpp:14 and the loop bounds a < N-3
     const double *src = p + (row_off ? row_off[shape] : shape * (int64_t)cap_pts) * 3;   // packed or dense rows
     const int ncap = N - 1;
     float maxhl = 0.0f;
-    for (int i = lane; i < ncap; i += 32) {
+    for (int i = gl; i < ncap; i += LPS) {
       const double ax = src[3 * i], ay = src[3 * i + 1], az = src[3 * i + 2];
       const double bx = src[3 * i + 3], by = src[3 * i + 4], bz = src[3 * i + 5];
       const float dx = (float)(bx - ax), dy = (float)(by - ay), dz = (float)(bz - az);
@@ -107,15 +118,15 @@ self_collision_filter_kernel(const double *__restrict__ p, const int32_t *__rest
       seg[i] = make_float4((float)(0.5 * (ax + bx)), (float)(0.5 * (ay + by)), (float)(0.5 * (az + bz)), hl);
       maxhl = fmaxf(maxhl, hl);
     }
-    for (int o = 16; o > 0; o >>= 1) maxhl = fmaxf(maxhl, __shfl_xor_sync(0xffffffffu, maxhl, o));
-    __syncwarp();
+    for (int o = LPS / 2; o > 0; o >>= 1) maxhl = fmaxf(maxhl, __shfl_xor_sync(gmask, maxhl, o));
+    __syncwarp(gmask);
     // smallest index gap b - a - 1 that can reach 3r of arc length (maxhl over-estimates len/2)
     const float safe = (float)(3.0 * r) * 0.9999f;
     const int min_gap = (maxhl > 0.0f) ? (int)fminf(1e6f, floorf(safe / (2.0f * maxhl))) : 1000000;
     const int first = 1 + (min_gap < 1 ? 1 : min_gap);  // b >= a + first (and the reference's b >= a + 2)
     const int R = ncap - first;                         // rows a = 0 .. R-1 have at least one b
     bool found = false;
-    for (int k = lane; k < (R + 1) / 2; k += 32) {
+    for (int k = gl; k < (R + 1) / 2; k += LPS) {       // rows k and R-1-k: R + 1 pair tests per lane
       for (int half = 0; half < 2; half++) {
         const int a = half ? (R - 1 - k) : k;
         if (half && a == k) break;
@@ -129,14 +140,14 @@ self_collision_filter_kernel(const double *__restrict__ p, const int32_t *__rest
         }
       }
     }
-    if (__any_sync(0xffffffffu, found) && lane == 0) cand[atomicAdd(n_cand, 1)] = (int32_t)shape;
+    if (__any_sync(gmask, found) && gl == 0) cand[atomicAdd(n_cand, 1)] = (int32_t)w;
   }
 }
 
 // Stage 2 -- exact test, one warp per candidate shape (all shapes when cand == nullptr).
 __global__ void __launch_bounds__(SC_WARPS * 32)
 self_collision_kernel(const double *__restrict__ p, const int32_t *__restrict__ npts, int64_t n,
-                      int cap_pts, double r, uint32_t *__restrict__ flags,
+                      const int32_t *__restrict__ range, int cap_pts, double r, uint32_t *__restrict__ flags,
                       const int32_t *__restrict__ cand, const int32_t *__restrict__ n_cand,
                       const int64_t *__restrict__ row_off) {
   extern __shared__ double sm[];
@@ -148,9 +159,11 @@ self_collision_kernel(const double *__restrict__ p, const int32_t *__restrict__ 
   const double dist_to_consider = 3.0 * r;
   const double rr = r + r;
 
+  const int64_t lo = range ? range[0] : 0;
+  if (range) n = (int64_t)range[1] - lo;
   const int64_t n_work = cand ? (int64_t)*n_cand : n;
   for (int64_t w = (int64_t)blockIdx.x * SC_WARPS + warp; w < n_work; w += (int64_t)gridDim.x * SC_WARPS) {
-    const int64_t shape = cand ? (int64_t)cand[w] : w;
+    const int64_t shape = lo + (cand ? (int64_t)cand[w] : w);
     const int N = npts[shape];
     __syncwarp();
     if (N <= 2) continue;  // collision.cpp:14
@@ -248,9 +261,11 @@ self_collision_kernel(const double *__restrict__ p, const int32_t *__restrict__ 
 
 }  // namespace
 
+size_t selfcol_work_bytes(int64_t n) { return 256 + (((size_t)n * 4 + 255) & ~(size_t)255); }
+
 int self_collision_launch(irt_ctx *ctx, const irt_robot *rb, const double *d_p,
                           const int32_t *d_npts, int64_t n, int cap_pts, uint32_t *d_flags,
-                          cudaStream_t st, const int64_t *d_row_off) {
+                          cudaStream_t st, const int64_t *d_row_off, const int32_t *d_range, void *work) {
   if (n <= 0) return IRT_OK;
   if (n > 0x7fffffffLL) return irt_fail(ctx, IRT_ERR_INVALID_ARGUMENT, "batch too large");
   if (cap_pts > IRT_CAP_PTS_MAX) return irt_fail(ctx, IRT_ERR_CAPACITY, "cap_pts=%d too large", cap_pts);
@@ -259,30 +274,36 @@ int self_collision_launch(irt_ctx *ctx, const irt_robot *rb, const double *d_p,
   if (smem > 200 * 1024) return irt_fail(ctx, IRT_ERR_CAPACITY, "cap_pts=%d too large", cap_pts);
   IRT_CUDA(ctx, cudaFuncSetAttribute(self_collision_kernel,
                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  // candidate list lives behind the bucket permutation area of the context scratch
-  const size_t perm_bytes = (size_t)n * 8 + 8192 + 256;  // fk_launch: keys + perm + 2 x (Kfull + 2) counters
-  char *scr = (char *)ctx_scratch(ctx, perm_bytes + (size_t)n * 4 + 256);
-  if (!scr) return irt_fail(ctx, IRT_ERR_CUDA, "scratch alloc failed");
-  int32_t *d_ncand = (int32_t *)(scr + perm_bytes);
-  int32_t *d_cand = d_ncand + 64;
+  char *scr = (char *)work;
+  if (!scr) {   // behind the bucket permutation area of the context scratch
+    const size_t fk_bytes = fk_work_bytes(rb, n);
+    scr = (char *)ctx_scratch(ctx, fk_bytes + selfcol_work_bytes(n));
+    if (!scr) return irt_fail(ctx, IRT_ERR_CUDA, "scratch alloc failed");
+    scr += fk_bytes;
+  }
+  int32_t *d_ncand = (int32_t *)scr;
+  int32_t *d_cand = (int32_t *)(scr + 256);
   IRT_CUDA(ctx, cudaMemsetAsync(d_ncand, 0, 4, st));
   {
-    int64_t fb = (n + SC_FILTER_WARPS - 1) / SC_FILTER_WARPS;
+    // half a warp per shape while a shape's pair rows fit 16 lanes (up to ~48 points at the usual r / dL)
+    const bool half = cap_pts <= 48;
+    const int gpw = half ? 2 : 1;
+    int64_t fb = (n + SC_FILTER_WARPS * gpw - 1) / (SC_FILTER_WARPS * gpw);
     const int64_t fmax_blocks = (int64_t)ctx->sm_count * 16;
     if (fb > fmax_blocks) fb = fmax_blocks;
-    const size_t fsmem = (size_t)SC_FILTER_WARPS * cap_pts * sizeof(float4);
+    const size_t fsmem = (size_t)SC_FILTER_WARPS * gpw * cap_pts * sizeof(float4);
+    auto kf = half ? self_collision_filter_kernel<16> : self_collision_filter_kernel<32>;
     if (fsmem > 48 * 1024)
-      IRT_CUDA(ctx, cudaFuncSetAttribute(self_collision_filter_kernel,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem));
-    self_collision_filter_kernel<<<(unsigned)fb, SC_FILTER_WARPS * 32, fsmem, st>>>(d_p, d_npts, n, cap_pts,
-                                                                                  rb->dev.r, d_cand, d_ncand, d_row_off);
+      IRT_CUDA(ctx, cudaFuncSetAttribute(kf, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem));
+    kf<<<(unsigned)fb, SC_FILTER_WARPS * 32, fsmem, st>>>(d_p, d_npts, n, d_range, cap_pts, rb->dev.r, d_cand,
+                                                          d_ncand, d_row_off);
   }
   IRT_LAUNCHED(ctx);
   // stage 2 runs over however many candidates stage 1 found (count stays on the device)
   int64_t blocks = (n + SC_WARPS - 1) / SC_WARPS;
   const int64_t max_blocks = (int64_t)ctx->sm_count * 4;
   if (blocks > max_blocks) blocks = max_blocks;
-  self_collision_kernel<<<(unsigned)blocks, SC_WARPS * 32, smem, st>>>(d_p, d_npts, n, cap_pts, rb->dev.r,
+  self_collision_kernel<<<(unsigned)blocks, SC_WARPS * 32, smem, st>>>(d_p, d_npts, n, d_range, cap_pts, rb->dev.r,
                                                                       d_flags, d_cand, d_ncand, d_row_off);
   IRT_LAUNCHED(ctx);
   IRT_CUDA(ctx, cudaGetLastError());

@@ -69,8 +69,8 @@ __global__ void count_nonzero_kernel(const uint64_t *__restrict__ blocks, int64_
 // bitmap (atomicOr, only on a hit); after the stream thread t -- which owns set s0+t and holds its
 // leaf range [lo,hi) -- tests the bits of its range (1-2 words for a typical 20-60 leaf set), and a
 // __ballot_sync per warp is the verdict word.  No shuffles, no search and no per-set divergence in the
-// streaming loop; tiles with more leaves than the bitmap holds are streamed in chunks.  The bitmap is
-// double-buffered by tile parity so a chunk costs two __syncthreads.
+// streaming loop; tiles with more leaves than the bitmap holds are streamed in chunks.  Three hit bitmaps
+// rotate, so a chunk costs ONE __syncthreads (the buffer cleared during chunk k was last read two barriers ago).
 constexpr int K3_CHUNK_LEAVES = 32768;                      // hit-bitmap capacity per buffer (4 KiB)
 constexpr int K3_BM_WORDS = K3_CHUNK_LEAVES / 32 + 2;       // +1 straddle word, +1 pad
 constexpr int K3_GATHER_TILES = 256;                         // staged verdict words per CTA: 8 KiB
@@ -114,7 +114,7 @@ struct XchgDev {
   int flush_tiles;                // staged tiles per P2P flush (<= K3_GATHER_TILES)
   int64_t slot_words;             // words every rank contributes
   uint32_t epoch;
-  unsigned int *done;             // local CTA counter
+  unsigned int *done;             // local: [0] CTAs done, [1] error word, [2] dynamic tile counter
   // buffer layout (uint32): words[2][world][slot_words], flags[2][world]
   __device__ __forceinline__ uint32_t *words(int r) const {
     return peer[r] + ((int64_t)parity * world + rank) * slot_words;
@@ -122,22 +122,44 @@ struct XchgDev {
   __device__ __forceinline__ uint32_t *flag(int r) const {
     return peer[r] + (int64_t)2 * world * slot_words + parity * world + rank;
   }
+  // rank r's flag of this parity in THIS rank's buffer
+  __device__ __forceinline__ const uint32_t *flag_here(int r) const {
+    return peer[rank] + (int64_t)2 * world * slot_words + parity * world + r;
+  }
 };
 
-// last-CTA epilogue of a gathering kernel: data stores of all CTAs happen-before the flag stores
+// last-CTA epilogue of a gathering kernel: data stores of all CTAs happen-before the flag stores; the same CTA
+// then waits (bounded) until every peer's flag of this sweep has arrived in this rank's buffer, so that when
+// the kernel ends the gathered array is complete: no separate wait kernel.  (Every rank's kernel runs on its own
+// GPU; nothing here waits for another launch on the same device.)
 __device__ __forceinline__ void xchg_signal(const XchgDev &x) {
   // the CTA barrier orders every thread's peer stores before thread 0's system-scope fence (fences are
   // cumulative), so ONE fence per CTA publishes them all: 256 per-thread MEMBAR.SYS cost ~10 us per sweep
+  __shared__ int s_last;
   __syncthreads();
   if (threadIdx.x == 0) {
     __threadfence_system();
     const unsigned prev = atomicAdd(x.done, 1u);
-    if (prev == gridDim.x - 1) {
-      *x.done = 0;
+    s_last = (prev == gridDim.x - 1);
+    if (s_last) {
+      x.done[0] = 0;   // CTA counter and tile counter are ready for the next sweep
+      x.done[2] = 0;
       __threadfence_system();
       for (int r = 0; r < x.world; r++)
         asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(x.flag(r)), "r"(x.epoch) : "memory");
     }
+  }
+  __syncthreads();
+  if (s_last && threadIdx.x < x.world) {   // thread r waits for rank r's flag
+    const uint32_t *f = x.flag_here(threadIdx.x);
+    bool ok = false;
+    for (long it = 0; it < (1L << 22); it++) {
+      uint32_t v;
+      asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(f) : "memory");
+      if (v == x.epoch) { ok = true; break; }
+      __nanosleep(100);
+    }
+    if (!ok) atomicExch(x.done + 1, 1u + (unsigned)threadIdx.x);   // a peer that never arrives: reported, no hang
   }
 }
 
@@ -171,7 +193,22 @@ voxel_and_popc_kernel(const uint32_t *__restrict__ keys, const uint64_t *__restr
     if (tid == 0) cp_async8(dst + K3_THREADS, offsets + s0 + n_valid);
   };
 
-  if ((int64_t)blockIdx.x < ntiles) prefetch_offsets(blockIdx.x, 0);
+  // tile schedule.  Plain sweeps: static stride over a grid of up to 8 CTAs per SM.  GATHER: one resident wave
+  // whose CTAs take tile ids from a global counter (fetched two tiles ahead, so the id of the next tile is
+  // known when its offsets are prefetched): no tail of unevenly loaded CTAs, however many tiles a shard has.
+  __shared__ long long s_tile_id[2];
+  int64_t tile = blockIdx.x, tile_next = (int64_t)blockIdx.x + gridDim.x;
+  if (GATHER) {
+    if (tid == 0) {
+      s_tile_id[0] = (long long)atomicAdd(xd.done + 2, 1u);
+      s_tile_id[1] = (long long)atomicAdd(xd.done + 2, 1u);
+    }
+    __syncthreads();
+    tile = s_tile_id[0];
+    tile_next = s_tile_id[1];
+    __syncthreads();
+  }
+  if (tile < ntiles) prefetch_offsets(tile, 0);
   if (OCC_SMEM) {
     for (int i = tid; i < occ_words; i += K3_THREADS) s_mem[OCC_OFF + i] = occ[i];
   }
@@ -179,13 +216,14 @@ voxel_and_popc_kernel(const uint32_t *__restrict__ keys, const uint64_t *__restr
   cp_async_wait_all();
   __syncthreads();
   int hb = 0, mb = 0;   // current hit bitmap / offsets buffer
-  // GATHER: verdict words of the tiles this CTA has finished, [K3_GATHER_TILES][8]
+  // GATHER: verdict words of the tiles this CTA has finished, [K3_GATHER_TILES][8], and their tile ids
   uint32_t *s_gw = s_mem + OCC_OFF + (OCC_SMEM ? occ_words : 0);
-  int kt = 0, kt_base = 0;
-  auto flush_gathered = [&](int first_tile, int ntl) {   // block-uniform arguments
+  int32_t *s_gtile = reinterpret_cast<int32_t *>(s_gw + K3_GATHER_TILES * (K3_THREADS / 32));
+  int kt = 0;
+  auto flush_gathered = [&](int ntl) {   // block-uniform argument
     __syncthreads();
     for (int idx = tid; idx < ntl * (K3_THREADS / 32); idx += K3_THREADS) {
-      const int64_t t = (int64_t)blockIdx.x + (int64_t)(first_tile + idx / (K3_THREADS / 32)) * gridDim.x;
+      const int64_t t = (int64_t)s_gtile[idx / (K3_THREADS / 32)];
       const int64_t wi = t * (K3_THREADS / 32) + idx % (K3_THREADS / 32);
       if (wi < nwords_out) {
         const uint32_t v = s_gw[idx];
@@ -195,12 +233,14 @@ voxel_and_popc_kernel(const uint32_t *__restrict__ keys, const uint64_t *__restr
     __syncthreads();
   };
 
-  for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+  for (int it = 0; tile < ntiles; it++) {
     const uint64_t *my_off = s_off + mb * (K3_THREADS + 2);
     const uint64_t t_lo = my_off[0], t_hi = my_off[K3_THREADS];
     const uint64_t lo = my_off[tid], hi = my_off[tid + 1];
-    if (tile + gridDim.x < ntiles) prefetch_offsets(tile + gridDim.x, mb ^ 1);
+    if (tile_next < ntiles) prefetch_offsets(tile_next, mb ^ 1);
     mb ^= 1;
+    if (GATHER && tid == 0)   // id of the tile after next; the barrier(s) of this tile publish it
+      s_tile_id[it & 1] = (long long)atomicAdd(xd.done + 2, 1u);
     bool own = false;
     if (t_lo == t_hi) {   // a tile of empty sets: no chunk below, but the prefetch still needs its barrier
       cp_async_wait_all();
@@ -298,13 +338,17 @@ voxel_and_popc_kernel(const uint32_t *__restrict__ keys, const uint64_t *__restr
       // stage this CTA's words in shared memory; they go to the peers as 32-byte runs (one tile = 8
       // consecutive words) instead of one 4-byte NVLink write per warp
       if ((tid & 31) == 0) s_gw[kt * (K3_THREADS / 32) + (tid >> 5)] = word;
-      if (++kt == xd.flush_tiles) { flush_gathered(kt_base, kt); kt_base += kt; kt = 0; }
+      if (tid == 0) s_gtile[kt] = (int32_t)tile;
+      if (++kt == xd.flush_tiles) { flush_gathered(kt); kt = 0; }
     } else if ((tid & 31) == 0 && wi < nwords_out) {
       verdict[wi] = word;
     }
+    const int64_t tile_after = GATHER ? (int64_t)s_tile_id[it & 1] : tile_next + gridDim.x;
+    tile = tile_next;
+    tile_next = tile_after;
   }
   if (GATHER) {
-    flush_gathered(kt_base, kt);
+    flush_gathered(kt);
     // padding words of this rank's slot (sets beyond the shard) read as "no collision" everywhere
     for (int64_t wi = nwords_out + (int64_t)blockIdx.x * K3_THREADS + tid; wi < xd.slot_words;
          wi += (int64_t)gridDim.x * K3_THREADS)
@@ -329,22 +373,6 @@ __global__ void xchg_empty_shard_kernel(const XchgDev xd) {
        wi += (int64_t)gridDim.x * blockDim.x)
     for (int r = 0; r < xd.world; r++) xd.words(r)[wi] = 0u;
   xchg_signal(xd);
-}
-
-// one warp: lane r waits until rank r's flag of this parity shows `epoch`.  Bounded: a peer that never
-// arrives sets *err instead of hanging the GPU.
-__global__ void xchg_wait_kernel(const uint32_t *__restrict__ flags, int world, uint32_t epoch,
-                                 unsigned int *__restrict__ err) {
-  const int r = threadIdx.x;
-  if (r >= world) return;
-  const uint32_t *f = flags + r;
-  for (long it = 0; it < (1L << 24); it++) {
-    uint32_t v;
-    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(f) : "memory");
-    if (v == epoch) return;
-    __nanosleep(64);
-  }
-  atomicExch(err, 1u + (unsigned)r);
 }
 
 int ensure_store_capacity(irt_ctx *ctx, irt_setstore *s, int64_t n_sets, int64_t n_blocks) {
@@ -623,7 +651,9 @@ static int check_sets_impl(irt_ctx *ctx, const irt_setstore *store, const irt_en
   const int occ_words = (int)((env->n_blocks_total + 31) / 32);
   const bool occ_smem = (size_t)occ_words * 4 <= 64 * 1024;
   int64_t blocks = (n + K3_THREADS - 1) / K3_THREADS;     // one CTA per tile of 256 sets ...
-  const int64_t max_blocks = (int64_t)ctx->sm_count * 8;  // ... persistent over 8 CTAs per SM
+  // ... a grid of up to 8 CTAs per SM striding over the tiles: __launch_bounds__(256, 4) keeps 4 resident per
+  // SM, i.e. two waves (the second wave's early CTAs start while the first wave's late ones drain)
+  const int64_t max_blocks = (int64_t)ctx->sm_count * 8;
   if (blocks > max_blocks) blocks = max_blocks;
   const size_t smem = (size_t)K3_SMEM_FIXED_WORDS * 4 + (occ_smem ? (size_t)occ_words * 4 : 0);
 #define K3_LAUNCH(OS, ST)                                                                          \
@@ -638,7 +668,7 @@ static int check_sets_impl(irt_ctx *ctx, const irt_setstore *store, const irt_en
 #define K3_LAUNCH_GATHER(OS)                                                                       \
   do {                                                                                             \
     auto kfn = voxel_and_popc_kernel<OS, false, true>;                                             \
-    const size_t gsmem = smem + (size_t)K3_GATHER_TILES * (K3_THREADS / 32) * 4;                   \
+    const size_t gsmem = smem + (size_t)K3_GATHER_TILES * (K3_THREADS / 32 + 1) * 4;               \
     if (gsmem > 48 * 1024)                                                                         \
       IRT_CUDA(ctx, cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gsmem)); \
     kfn<<<(unsigned)blocks, K3_THREADS, gsmem, st>>>(store->d_keys, store->d_bits, store->d_offsets, \
@@ -646,13 +676,9 @@ static int check_sets_impl(irt_ctx *ctx, const irt_setstore *store, const irt_en
                                                     end, nullptr, nullptr, *xd);                   \
   } while (0)
   if (xd) {
-    // one resident wave: every CTA ends with a system-scope fence that holds its SM slot for the
-    // round trip of its peer stores; a second wave would pay that latency twice
-    {
-      const char *wv = getenv("IRT_K3_GATHER_WAVES");   // tuning knob (default 1)
-      const int64_t waves = (wv && atoi(wv) > 0) ? atoi(wv) : 1;
-      if (blocks > (int64_t)ctx->sm_count * 4 * waves) blocks = (int64_t)ctx->sm_count * 4 * waves;
-    }
+    // one resident wave with dynamic tile scheduling (the CTAs take tile ids from a counter): every CTA ends
+    // with ONE system-scope fence, and no CTA is left with an extra tile at the end of the sweep
+    if (blocks > (int64_t)ctx->sm_count * 4) blocks = (int64_t)ctx->sm_count * 4;
     if ((n + 31) / 32 > xd->slot_words)
       return irt_fail(ctx, IRT_ERR_CAPACITY, "shard of %lld sets exceeds the exchange slot (%lld words)",
                       (long long)n, (long long)xd->slot_words);
@@ -677,9 +703,10 @@ struct irt_xchg {
   uint32_t *local = nullptr;          // words[2][world][slot_words], flags[2][world]
   uint32_t *peer[IRT_MAX_PEERS] = {};  // peers' buffers mapped here (peer[rank] == local)
   bool opened[IRT_MAX_PEERS] = {};
-  unsigned int *d_done = nullptr;     // [0] CTA counter, [1] error word
+  unsigned int *d_done = nullptr;     // [0] CTA counter, [1] error word, [2] dynamic tile counter
   uint32_t epoch = 0;
   bool connected = false;
+  int flush_tiles = 4;                // staged tiles per P2P flush (IRT_K3_GATHER_FLUSH, read once at creation)
 };
 
 int irt_xchg_create(irt_ctx *ctx, int rank, int world, int64_t slot_words, irt_xchg **out) {
@@ -698,6 +725,13 @@ int irt_xchg_create(irt_ctx *ctx, int rank, int world, int64_t slot_words, irt_x
   cudaMemset(x->d_done, 0, 64);
   x->peer[rank] = x->local;
   x->connected = (world == 1);
+  {
+    // peer stores trickle out while the sweep runs (every flush_tiles tiles), so the fence at the end of
+    // a CTA only waits for its last few; tuning knob IRT_K3_GATHER_FLUSH
+    const char *fl = getenv("IRT_K3_GATHER_FLUSH");
+    const int f = (fl && atoi(fl) > 0) ? atoi(fl) : 4;
+    x->flush_tiles = f > K3_GATHER_TILES ? K3_GATHER_TILES : f;
+  }
   *out = x;
   return IRT_OK;
 }
@@ -760,19 +794,10 @@ int irt_check_sets_allgather_dev(irt_ctx *ctx, const irt_setstore *store, const 
   for (int r = 0; r < x->world; r++) xd.peer[r] = x->peer[r];
   xd.world = x->world; xd.rank = x->rank; xd.parity = (int)(x->epoch & 1u);
   xd.slot_words = x->slot_words; xd.epoch = x->epoch; xd.done = x->d_done;
-  {
-    // peer stores trickle out while the sweep runs (every flush_tiles tiles), so the fence at the end of
-    // a CTA only waits for its last few; tuning knob IRT_K3_GATHER_FLUSH
-    const char *fl = getenv("IRT_K3_GATHER_FLUSH");
-    int f = (fl && atoi(fl) > 0) ? atoi(fl) : 4;
-    xd.flush_tiles = f > K3_GATHER_TILES ? K3_GATHER_TILES : f;
-  }
+  xd.flush_tiles = x->flush_tiles;
   int rc = check_sets_impl(ctx, store, env, begin, end, nullptr, nullptr, st, &xd);
   if (rc) return rc;
-  const uint32_t *flags = x->local + (size_t)2 * x->world * x->slot_words + (size_t)xd.parity * x->world;
-  xchg_wait_kernel<<<1, 32, 0, st>>>(flags, x->world, x->epoch, x->d_done + 1);
-  IRT_LAUNCHED(ctx);
-  IRT_CUDA(ctx, cudaGetLastError());
+  // (the kernel's last CTA has waited for every peer's flag: the gathered array is complete when it ends)
   if (d_gathered) *d_gathered = x->local + (size_t)xd.parity * x->world * x->slot_words;
   return IRT_OK;
 }

@@ -48,6 +48,9 @@ struct Trace {
   }
 };
 
+#ifndef RS_FAST_TRAVERSAL
+#define RS_FAST_TRAVERSAL 1
+#endif
 constexpr int RS_WARPS = 4;
 constexpr int RS_HLOG_SMALL = 8;     // main pass: 256 hash entries per warp (a set rarely exceeds ~150 blocks)
 constexpr int RS_HLOG_BIG = 12;      // fallback pass for the sets that overflow it: 4096 entries, 1 warp per CTA
@@ -56,7 +59,7 @@ constexpr int RS_BIGSLOT = 1 << RS_HLOG_BIG;  // slot capacity of the fallback p
 constexpr int RS_MAX_OVF = 2048;     // fallback slots per raster launch
 constexpr uint32_t RS_EMPTY = 0xffffffffu;
 constexpr int RS_MAXS = 128;          // samples of one set handled by the flat segment walk
-constexpr int rs_warp_bytes(int hlog) { return (1 << hlog) * 18 + 16 + RS_MAXS * 8; }
+constexpr int rs_warp_bytes(int hlog) { return (1 << hlog) * 18 + 16 + RS_MAXS * 12; }
 constexpr uint32_t INVALID_MASK = IRT_FLAG_NONCONVERGED | IRT_FLAG_LENGTH_LIMIT |
                                   IRT_FLAG_SELF_COLLISION | IRT_FLAG_BAD_STATE | IRT_FLAG_ENV_COLLISION;
 
@@ -199,12 +202,68 @@ __device__ void add_line(const GridDev &g, Sink &sink, const D3 &a, const D3 &b)
   if (VOX_IN(Bxi, Byi, Bzi)) sink.cell(Bxi, Byi, Bzi);
   if (entered) sink.cell(Axi, Ayi, Azi);
   D3 U = {B.x - A.x, B.y - A.y, B.z - A.z};
+  const double z = (U.x * U.x + U.y * U.y) + U.z * U.z;  // Eigen normalized()
+#if RS_FAST_TRAVERSAL
+  // Division-free traversal.  The reference's ray parameters are t_axis(k) = (e_axis + k) * n / |U_axis| (U the
+  // un-normalised direction, n its norm, k the steps already taken on that axis), so every comparison between
+  // two of them is a comparison of cross products (e_x + k_x) |U_y| <> (e_y + k_y) |U_x|: no square root, no
+  // division (1 sqrt + 6 divisions per segment otherwise: ~200 of ~300 FP64 instructions).  The reference's
+  // own values carry a few ulp of rounding, so a decision is only taken here when the two sides differ by more
+  // than 1e-12 relative; a closer call, a direction component near the reference's 1e-10 validity threshold, or
+  // a path longer than the recorded 16 steps hands the segment to the literal code below.  The decisions are
+  // found in a dry run first and replayed with cell emission afterwards, so nothing is emitted twice.
   {
-    const double z = (U.x * U.x + U.y * U.y) + U.z * U.z;  // Eigen normalized()
-    if (z > 0.0) {
-      const double n = sqrt(z);
-      U.x /= n; U.y /= n; U.z /= n;
+    const double adx = fabs(U.x), ady = fabs(U.y), adz = fabs(U.z);
+    const double zhi = 1.0001e-20 * z;   // |U_axis| / n > 1e-10 with margin
+    bool ok = z > 0.0 && adx * adx > zhi && ady * ady > zhi && adz * adz > zhi;
+    if (ok) {
+      const int sx = 1 - 2 * (U.x < 0), sy = 1 - 2 * (U.y < 0), sz = 1 - 2 * (U.z < 0);
+      double Nx = fabs(A.x - (Axi + sx) * g.d[0]);
+      double Ny = fabs(A.y - (Ayi + sy) * g.d[1]);
+      double Nz = fabs(A.z - (Azi + sz) * g.d[2]);
+      uint32_t seq = 0;
+      int ns = 0;
+      {
+        int xi = Axi, yi = Ayi, zi = Azi;
+        bool ent = entered;
+        while (sx * (Bxi - xi) >= 0 && sy * (Byi - yi) >= 0 && sz * (Bzi - zi) >= 0) {
+          const double xy_l = Nx * ady, xy_r = Ny * adx, xz_l = Nx * adz, xz_r = Nz * adx, yz_l = Ny * adz, yz_r = Nz * ady;
+          const double tol = 1e-12;
+          if (fabs(xy_l - xy_r) <= tol * (xy_l + xy_r) || fabs(xz_l - xz_r) <= tol * (xz_l + xz_r) ||
+              fabs(yz_l - yz_r) <= tol * (yz_l + yz_r) || ns >= 16) {
+            ok = false;
+            break;
+          }
+          const bool tx_is_min = (xy_l < xy_r) && (xz_l < xz_r);
+          const bool ty_is_min = !(xy_l < xy_r) && (yz_l < yz_r);
+          const int axis = tx_is_min ? 0 : (ty_is_min ? 1 : 2);
+          seq |= (uint32_t)axis << (2 * ns);
+          ns++;
+          if (axis == 0) { xi += sx; if (ent && !IDX_IN(xi)) break; Nx += 1.0; }
+          else if (axis == 1) { yi += sy; if (ent && !IDX_IN(yi)) break; Ny += 1.0; }
+          else { zi += sz; if (ent && !IDX_IN(zi)) break; Nz += 1.0; }
+          if (!ent && VOX_IN(xi, yi, zi)) ent = true;
+        }
+      }
+      if (ok) {   // replay
+        int xi = Axi, yi = Ayi, zi = Azi;
+        for (int k = 0; k < ns; k++) {
+          const int axis = (seq >> (2 * k)) & 3;
+          if (axis == 0) { xi += sx; if (entered && !IDX_IN(xi)) break; }
+          else if (axis == 1) { yi += sy; if (entered && !IDX_IN(yi)) break; }
+          else { zi += sz; if (entered && !IDX_IN(zi)) break; }
+          if (!entered && VOX_IN(xi, yi, zi)) entered = true;
+          if (entered) sink.cell(xi, yi, zi);
+        }
+        sink.finish();
+        return;
+      }
     }
+  }
+#endif
+  if (z > 0.0) {
+    const double n = sqrt(z);
+    U.x /= n; U.y /= n; U.z /= n;
   }
   const int step_x = 1 - 2 * (U.x < 0), step_y = 1 - 2 * (U.y < 0), step_z = 1 - 2 * (U.z < 0);
   const double ex = fabs(A.x - (Axi + step_x) * g.d[0]);
@@ -241,22 +300,71 @@ __device__ void add_line(const GridDev &g, Sink &sink, const D3 &a, const D3 &b)
 #undef VOX_IN
 }
 
-// One warp per set.  A set is a linked list of FK samples (set_head / sample_next); a sample is
-// included iff t < tlimit[set] (edges) -- vertices have a single sample and no limit.
-// Output: the set's occupied leaf blocks, key-sorted, in its slot (slot_keys / slot_bits),
+// ---- sample pools ---------------------------------------------------------------------------------
+// Vertex pool: FK results of the edge endpoints (roadmap vertices), computed once and shared by all incident
+// edges.  Mid pool: the samples the bisection creates.  A sample is named, relative to its edge, by an int32
+// reference: >= 0 = index into the mid pool, -1 = endpoint a (t = 0), -2 = endpoint b (t = 1).
+struct EdgePool {
+  const double *v_state;    // [nv][S]
+  const double *v_p;        // [nv][cap_pts][3]
+  const int32_t *v_npts;    // [nv]
+  const uint32_t *v_flags;  // [nv]
+  int64_t nv;
+  int64_t *pairs;           // [E][2] endpoint vertices of this chunk's edges
+  double *thr;              // [E] rel_threshold
+  unsigned long long *first_invalid;  // [E] double bits (positive -> uint order == double order)
+  int32_t *head;            // [E] newest mid sample of the edge (linked through m_next) or -1
+  uint32_t *eflags;         // [E]
+  int32_t *m_edge, *m_next, *m_npts;
+  uint32_t *m_flags;
+  double *m_t, *m_state, *m_p;
+  int32_t cap_mid, cap_q, E;
+  int S, N, enable_rotation, enable_retraction, cap_pts;
+};
+__device__ __forceinline__ int64_t end_vertex(const EdgePool &P, int32_t edge, int32_t ref) {
+  return P.pairs[2 * (int64_t)edge + (-1 - ref)];
+}
+__device__ __forceinline__ const double *smp_pts(const EdgePool &P, int32_t edge, int32_t ref) {
+  return ref >= 0 ? P.m_p + (int64_t)ref * P.cap_pts * 3 : P.v_p + end_vertex(P, edge, ref) * P.cap_pts * 3;
+}
+__device__ __forceinline__ int smp_npts(const EdgePool &P, int32_t edge, int32_t ref) {
+  return ref >= 0 ? P.m_npts[ref] : P.v_npts[end_vertex(P, edge, ref)];
+}
+__device__ __forceinline__ uint32_t smp_flags(const EdgePool &P, int32_t edge, int32_t ref) {
+  return ref >= 0 ? P.m_flags[ref] : P.v_flags[end_vertex(P, edge, ref)];
+}
+__device__ __forceinline__ double smp_t(const EdgePool &P, int32_t ref) {
+  return ref >= 0 ? P.m_t[ref] : (ref == -1 ? 0.0 : 1.0);
+}
+
+// device-side counters of one in-flight chunk (int32 words): the host never reads them between rounds
+enum { C_NMID = 0, C_NPEND = 1, C_NQ0 = 2, C_NQ1 = 3, C_LO = 4, C_HI = 5, C_ERR = 6, C_WORDS = 16 };
+
+// what a raster launch reads its sets from
+struct SetSrc {
+  int edge_mode;
+  // vertex mode: set i = the single shape i (heads[i] < 0: invalid shape, empty set)
+  const double *pts;
+  const int32_t *npts;
+  const int32_t *heads;
+  int cap_pts;
+  // edge mode: set e = endpoints + mid samples of edge e with t < tlimit[e] (VoxelEnvironment.cpp:406-422)
+  EdgePool P;
+  const double *tlimit;
+};
+
+// One warp per set.  Output: the set's occupied leaf blocks, key-sorted, in its slot (slot_keys / slot_bits),
 // counts[set], optional t_last / nsamples.  A gather kernel then packs the slots into the CSR at
 // the scanned offsets.  Per-set cost is proportional to the number of occupied blocks: occupied
 // hash slots are kept in an append list, so neither the sort nor the clean-up scans the table.
-// HLOG = RS_HLOG_SMALL: main pass over all sets; a set that outgrows the small table is appended
-// to ovf_list and left for the HLOG = RS_HLOG_BIG pass, which works through that list (count on
-// the device) with one warp per CTA and writes into the big slots.
+// HLOG = RS_HLOG_SMALL: main pass over sets [set0, set0 + nsets); a set that outgrows the small table is
+// appended to ovf_list and left for the HLOG = RS_HLOG_BIG pass, which works through that list (count on
+// the device) with one warp per CTA and writes into the big slots.  Per-set arrays (counts, t_last,
+// nsamples, set_flags, ovf_slot) are indexed relative to set0.
 template <int HLOG, int WARPS>
 __global__ void __launch_bounds__(WARPS * 32)
-swept_voxel_raster_kernel(const GridDev g, const double *__restrict__ pts,
-                          const int32_t *__restrict__ npts, int cap_pts,
-                          const int32_t *__restrict__ set_head, const int32_t *__restrict__ sample_next,
-                          const double *__restrict__ sample_t, const double *__restrict__ tlimit,
-                          int64_t nsets, uint32_t *__restrict__ counts, double *__restrict__ t_last,
+swept_voxel_raster_kernel(const GridDev g, const SetSrc src, int64_t set0, int64_t nsets,
+                          uint32_t *__restrict__ counts, double *__restrict__ t_last,
                           int32_t *__restrict__ nsamples, uint32_t *__restrict__ slot_keys,
                           uint64_t *__restrict__ slot_bits, uint32_t *__restrict__ set_flags,
                           int32_t *__restrict__ ovf_list, int32_t *__restrict__ ovf_count,
@@ -275,38 +383,51 @@ swept_voxel_raster_kernel(const GridDev g, const double *__restrict__ pts,
   h.list = reinterpret_cast<uint16_t *>(wbase + H * 16);
   h.count = reinterpret_cast<uint32_t *>(wbase + H * 18);
   h.overflow = h.count + 1;
-  int32_t *ls = reinterpret_cast<int32_t *>(wbase + H * 18 + 16);  // sample ids
-  int32_t *lc = ls + RS_MAXS;                                      // first flat segment index
+  const double **lp = reinterpret_cast<const double **>(wbase + H * 18 + 16);   // sample point arrays
+  int32_t *lc = reinterpret_cast<int32_t *>(wbase + H * 18 + 16 + RS_MAXS * 8);  // first flat segment index
   for (int i = lane; i < H; i += 32) { h.keys[i] = RS_EMPTY; h.bits[i] = 0ull; }
   if (lane == 0) { *h.count = 0u; *h.overflow = 0u; }
   __syncwarp();
 
   const int64_t n_work = BIG ? (int64_t)min(*ovf_count, RS_MAX_OVF) : nsets;
   for (int64_t w = (int64_t)blockIdx.x * WARPS + warp; w < n_work; w += (int64_t)gridDim.x * WARPS) {
-    const int64_t set = BIG ? (int64_t)ovf_list[w] : w;
-    const double lim = tlimit ? tlimit[set] : 0.0;
+    const int64_t rel = BIG ? (int64_t)ovf_list[w] : w;
+    const int64_t set = set0 + rel;
     double tl = 0.0;
     int ns = 0, nsm = 0, total = 0;
     // pass 1: list the included samples with their cumulative segment counts (flat work list)
-    for (int smp = set_head[set]; smp >= 0; smp = sample_next ? sample_next[smp] : -1) {
-      ns++;
-      if (tlimit) {
-        const double t = sample_t[smp];
-        if (!(t < lim)) continue;  // VoxelEnvironment.cpp:409
-        if (tl < t) tl = t;        // :419-422 last valid t
-      }
-      const int P = npts[smp];
-      if (P < 2) continue;         // add_piecewise_line of fewer than 2 points adds nothing
+    auto take = [&](const double *sp, int P) {
+      if (P < 2) return;             // add_piecewise_line of fewer than 2 points adds nothing
       if (nsm < RS_MAXS) {
-        if (lane == 0) { ls[nsm] = smp; lc[nsm] = total; }
+        if (lane == 0) { lp[nsm] = sp; lc[nsm] = total; }
         nsm++;
         total += P - 1;
       } else {  // very long sample lists: the remainder goes sample by sample
-        const double *sp = pts + (int64_t)smp * cap_pts * 3;
         for (int i = 1 + lane; i < P; i += 32) {
           HashSink sink(h);
           add_line(g, sink, rotate_pt(g, sp + 3 * (i - 1)), rotate_pt(g, sp + 3 * i));
         }
+      }
+    };
+    if (!src.edge_mode) {
+      const int32_t smp = src.heads[set];
+      if (smp >= 0) {
+        ns = 1;
+        take(src.pts + (int64_t)smp * src.cap_pts * 3, src.npts[smp]);
+      }
+    } else {
+      const EdgePool &P = src.P;
+      const int32_t e = (int32_t)set;
+      const double lim = src.tlimit[e];
+      ns = 2;
+      if (0.0 < lim) take(smp_pts(P, e, -1), smp_npts(P, e, -1));   // VoxelEnvironment.cpp:409: t < first_invalid_t
+      if (1.0 < lim) { tl = 1.0; take(smp_pts(P, e, -2), smp_npts(P, e, -2)); }
+      for (int32_t m = P.head[e]; m >= 0; m = P.m_next[m]) {
+        ns++;
+        const double t = P.m_t[m];
+        if (!(t < lim)) continue;
+        if (tl < t) tl = t;          // :419-422 last valid t
+        take(P.m_p + (int64_t)m * P.cap_pts * 3, P.m_npts[m]);
       }
     }
     __syncwarp();
@@ -315,8 +436,8 @@ swept_voxel_raster_kernel(const GridDev g, const double *__restrict__ pts,
       int k = 0;
       for (int step = RS_MAXS >> 1; step > 0; step >>= 1)
         if (k + step < nsm && lc[k + step] <= f) k += step;
-      const int i = f - lc[k] + 1;  // segment (i-1, i) of sample ls[k]
-      const double *sp = pts + (int64_t)ls[k] * cap_pts * 3;
+      const int i = f - lc[k] + 1;  // segment (i-1, i) of sample k
+      const double *sp = lp[k];
       HashSink sink(h);
       add_line(g, sink, rotate_pt(g, sp + 3 * (i - 1)), rotate_pt(g, sp + 3 * i));
     }
@@ -324,19 +445,19 @@ swept_voxel_raster_kernel(const GridDev g, const double *__restrict__ pts,
     const bool over = *h.overflow != 0u;
     const int used = (int)min(*h.count, (uint32_t)H);
     int cnt = used;
-    int64_t slot_id = set;
+    int64_t slot_id = rel;
     if (!BIG && over) {
       // defer to the big-table pass (or give up with a flag when its slots are exhausted)
       cnt = 0;
       if (lane == 0) {
         const int32_t idx = atomicAdd(ovf_count, 1);
-        if (idx < RS_MAX_OVF) ovf_list[idx] = (int32_t)set;
-        else if (set_flags) set_flags[set] |= IRT_FLAG_CAPACITY;
+        if (idx < RS_MAX_OVF) ovf_list[idx] = (int32_t)rel;
+        else if (set_flags) set_flags[rel] |= IRT_FLAG_CAPACITY;
       }
     } else {
       if (BIG) {
         slot_id = w;
-        if (over && lane == 0 && set_flags) set_flags[set] |= IRT_FLAG_CAPACITY;
+        if (over && lane == 0 && set_flags) set_flags[rel] |= IRT_FLAG_CAPACITY;
       }
       for (int i = lane; i < cnt; i += 32) dk[i] = h.keys[h.list[i]];
       __syncwarp();
@@ -352,10 +473,10 @@ swept_voxel_raster_kernel(const GridDev g, const double *__restrict__ pts,
       }
     }
     if (lane == 0) {
-      counts[set] = (uint32_t)cnt;
-      if (BIG) ovf_slot[set] = (int32_t)w + 1;
-      if (t_last) t_last[set] = tl;
-      if (nsamples) nsamples[set] = ns;
+      counts[rel] = (uint32_t)cnt;
+      if (BIG) ovf_slot[rel] = (int32_t)w + 1;
+      if (t_last) t_last[rel] = tl;
+      if (nsamples) nsamples[rel] = ns;
     }
     __syncwarp();
     for (int i = lane; i < used; i += 32) {  // clean only what was used
@@ -371,33 +492,44 @@ swept_voxel_raster_kernel(const GridDev g, const double *__restrict__ pts,
 
 // voxelize_until_invalid: a sample is also invalid when its own backbone voxels hit the
 // environment (_vc->collides(shape), VoxelBackboneMotionValidator.cpp:83-91).  One warp per
-// sample; no set is built, the traversal just probes the environment grid.
+// sample of rows [lo, hi) (device range, or [0, n)); no set is built, the traversal just probes the grid.
 __global__ void sample_env_collision_kernel(const GridDev g, const double *__restrict__ pts,
-                                            const int32_t *__restrict__ npts, int cap_pts, int64_t n,
+                                            const int32_t *__restrict__ npts, int cap_pts, int64_t n_host,
+                                            const int32_t *__restrict__ range,
                                             const uint64_t *__restrict__ env, const uint32_t *__restrict__ occ,
                                             uint32_t *__restrict__ flags) {
   const int lane = threadIdx.x & 31;
-  const int64_t smp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  if (smp >= n) return;
-  if (flags[smp] & INVALID_MASK) return;  // is_valid_shape short-circuits the collision check
-  const int P = npts[smp];
-  const double *sp = pts + smp * (int64_t)cap_pts * 3;
-  EnvSink sink(env, occ);
-  for (int i = 1 + lane; i < P; i += 32) add_line(g, sink, rotate_pt(g, sp + 3 * (i - 1)), rotate_pt(g, sp + 3 * i));
-  if (__any_sync(0xffffffffu, sink.hit) && lane == 0) flags[smp] |= IRT_FLAG_ENV_COLLISION;
+  int64_t lo = 0, n = n_host;
+  if (range) { lo = range[0]; n = (int64_t)range[1] - lo; }
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t w = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; w < n; w += nwarps) {
+    const int64_t smp = lo + w;
+    if (flags[smp] & INVALID_MASK) continue;  // is_valid_shape short-circuits the collision check
+    const int P = npts[smp];
+    const double *sp = pts + smp * (int64_t)cap_pts * 3;
+    EnvSink sink(env, occ);
+    for (int i = 1 + lane; i < P; i += 32) add_line(g, sink, rotate_pt(g, sp + 3 * (i - 1)), rotate_pt(g, sp + 3 * i));
+    if (__any_sync(0xffffffffu, sink.hit) && lane == 0) flags[smp] |= IRT_FLAG_ENV_COLLISION;
+  }
 }
 
-// pack the slots into the CSR: one warp per set, coalesced copies
+// pack the slots into the CSR: one warp per set, coalesced copies.  A store that is too small for the
+// leaves raises *overflow and leaves the set out (the caller re-runs with the measured size).
 __global__ void raster_gather_kernel(const uint32_t *__restrict__ slot_keys, const uint64_t *__restrict__ slot_bits,
                                      const uint32_t *__restrict__ big_keys, const uint64_t *__restrict__ big_bits,
                                      const int32_t *__restrict__ ovf_slot,
                                      const uint32_t *__restrict__ counts, const uint64_t *__restrict__ offsets,
-                                     int64_t nsets, uint32_t *__restrict__ out_keys, uint64_t *__restrict__ out_bits) {
+                                     int64_t nsets, uint32_t *__restrict__ out_keys, uint64_t *__restrict__ out_bits,
+                                     uint64_t cap_blocks, int32_t *__restrict__ overflow) {
   const int lane = threadIdx.x & 31;
   const int64_t set = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (set >= nsets) return;
   const uint32_t n = counts[set];
   const uint64_t base = offsets[set];
+  if (base + n > cap_blocks) {
+    if (lane == 0 && n) *overflow = 1;
+    return;
+  }
   const int32_t ov = ovf_slot[set];
   const uint32_t *sk = ov ? big_keys + (int64_t)(ov - 1) * RS_BIGSLOT : slot_keys + set * RS_SLOT;
   const uint64_t *sb = ov ? big_bits + (int64_t)(ov - 1) * RS_BIGSLOT : slot_bits + set * RS_SLOT;
@@ -429,21 +561,23 @@ __global__ void scan_tile_sums_kernel(const uint32_t *__restrict__ in, int64_t n
   }
 }
 
-__global__ void scan_tile_offsets_kernel(uint64_t *tile_sums, int64_t ntiles, uint64_t *total) {
+// tile_sums[i] <- running + exclusive prefix; running += total  (running: leaves appended to the store so far;
+// chained on the device from raster launch to raster launch, the host only reads it at the very end)
+__global__ void scan_tile_offsets_kernel(uint64_t *tile_sums, int64_t ntiles, uint64_t *running) {
   if (threadIdx.x == 0 && blockIdx.x == 0) {
-    uint64_t acc = 0;
+    uint64_t acc = *running;
     for (int64_t i = 0; i < ntiles; i++) {
       const uint64_t c = tile_sums[i];
       tile_sums[i] = acc;
       acc += c;
     }
-    *total = acc;
+    *running = acc;
   }
 }
 
 __global__ void scan_apply_kernel(const uint32_t *__restrict__ in, int64_t n,
                                   const uint64_t *__restrict__ tile_sums,
-                                  const uint64_t *__restrict__ total, uint64_t base_off,
+                                  const uint64_t *__restrict__ running,
                                   uint64_t *__restrict__ out) {
   // thread t owns SCAN_ITEMS consecutive items of the tile
   __shared__ uint64_t sh[SCAN_T];
@@ -462,26 +596,25 @@ __global__ void scan_apply_kernel(const uint32_t *__restrict__ in, int64_t n,
     sh[threadIdx.x] += add;
     __syncthreads();
   }
-  uint64_t acc = base_off + tile_sums[blockIdx.x] + sh[threadIdx.x] - s;
+  uint64_t acc = tile_sums[blockIdx.x] + sh[threadIdx.x] - s;
   for (int k = 0; k < SCAN_ITEMS; k++) {
     if (base + k < n) out[base + k] = acc;
     acc += v[k];
   }
-  if (blockIdx.x == 0 && threadIdx.x == 0) out[n] = base_off + *total;
+  if (blockIdx.x == 0 && threadIdx.x == 0) out[n] = *running;
 }
 
-// offsets[0..n] = base_off + exclusive scan of counts[0..n); returns the chunk total on the host
-int exclusive_scan(irt_ctx *ctx, const uint32_t *d_counts, int64_t n, uint64_t base_off,
-                   uint64_t *d_offsets, uint64_t *d_tmp /* ntiles + 1 */, uint64_t *h_total,
-                   cudaStream_t st) {
+// offsets[0..n] = *d_running + exclusive scan of counts[0..n); *d_running += sum(counts).  No host sync.
+int exclusive_scan_chained(irt_ctx *ctx, const uint32_t *d_counts, int64_t n, uint64_t *d_running,
+                           uint64_t *d_offsets, uint64_t *d_tmp /* ntiles + 1 */, cudaStream_t st) {
   const int64_t ntiles = (n + SCAN_TILE - 1) / SCAN_TILE;
   scan_tile_sums_kernel<<<(unsigned)ntiles, SCAN_T, 0, st>>>(d_counts, n, d_tmp);
-  scan_tile_offsets_kernel<<<1, 32, 0, st>>>(d_tmp, ntiles, d_tmp + ntiles);
-  scan_apply_kernel<<<(unsigned)ntiles, SCAN_T, 0, st>>>(d_counts, n, d_tmp, d_tmp + ntiles, base_off, d_offsets);
-  ctx->launches.fetch_add(3);
+  IRT_LAUNCHED(ctx);
+  scan_tile_offsets_kernel<<<1, 32, 0, st>>>(d_tmp, ntiles, d_running);
+  IRT_LAUNCHED(ctx);
+  scan_apply_kernel<<<(unsigned)ntiles, SCAN_T, 0, st>>>(d_counts, n, d_tmp, d_running, d_offsets);
+  IRT_LAUNCHED(ctx);
   IRT_CUDA(ctx, cudaGetLastError());
-  IRT_CUDA(ctx, cudaMemcpyAsync(h_total, d_tmp + ntiles, 8, cudaMemcpyDeviceToHost, st));
-  IRT_CUDA(ctx, cudaStreamSynchronize(st));
   return IRT_OK;
 }
 
@@ -492,117 +625,13 @@ __global__ void vertex_heads_kernel(const uint32_t *__restrict__ flags, int64_t 
   if (i < n) heads[i] = (flags[i] & INVALID_MASK) ? -1 : (int32_t)i;
 }
 
-// ---- edge mode: level-synchronous bisection -----------------------------------------------------
+// ---- edge mode: level-synchronous bisection, driven from the device ----------------------------
 struct Interval {
-  int32_t edge, ia, ib;
+  int32_t edge, ia, ib;   // ia / ib: sample references (see EdgePool)
 };
 struct Pending {
   int32_t edge, ia, im, ib;
 };
-
-struct EdgePool {
-  // per edge
-  const double *a, *b;        // [E][S]
-  const double *thr;          // [E] rel_threshold
-  unsigned long long *first_invalid;  // [E] double bits (positive -> uint order == double order)
-  int32_t *head;              // [E]
-  uint32_t *eflags;           // [E]
-  // per sample
-  int32_t *s_edge, *s_next, *s_npts;
-  uint32_t *s_flags;
-  double *s_t, *s_state, *s_p;
-  int32_t cap_samples;
-  int S, N, enable_rotation, enable_retraction, cap_pts;
-};
-
-__global__ void edge_init_kernel(EdgePool P, int32_t E) {
-  const int32_t e = blockIdx.x * blockDim.x + threadIdx.x;
-  if (e >= E) return;
-  const int32_t i0 = 2 * e, i1 = 2 * e + 1;
-  P.s_edge[i0] = e; P.s_edge[i1] = e;
-  P.s_t[i0] = 0.0; P.s_t[i1] = 1.0;
-  for (int k = 0; k < P.S; k++) {
-    P.s_state[(int64_t)i0 * P.S + k] = P.a[(int64_t)e * P.S + k];
-    P.s_state[(int64_t)i1 * P.S + k] = P.b[(int64_t)e * P.S + k];
-  }
-  P.s_next[i0] = -1;
-  P.s_next[i1] = i0;
-  P.head[e] = i1;
-  P.first_invalid[e] = (unsigned long long)__double_as_longlong(10.0);  // VoxelEnvironment.cpp:261
-  P.eflags[e] = 0u;
-}
-
-// indexed form: the endpoints of edge e are roadmap vertices whose FK already exists in a vertex
-// pool; one warp per endpoint sample copies state, shape, point count and validity flags.
-__global__ void edge_init_indexed_kernel(EdgePool P, int32_t E, const int64_t *__restrict__ pairs,
-                                         const double *__restrict__ vstates, const double *__restrict__ vp,
-                                         const int32_t *__restrict__ vnpts, const uint32_t *__restrict__ vflags,
-                                         double *__restrict__ a_out, double *__restrict__ b_out) {
-  const int lane = threadIdx.x & 31;
-  const int64_t w = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  if (w >= 2 * (int64_t)E) return;
-  const int32_t e = (int32_t)(w >> 1), side = (int32_t)(w & 1);
-  const int64_t v = pairs[2 * (int64_t)e + side];
-  const int32_t smp = 2 * e + side;
-  const int np = vnpts[v];
-  const double *src = vp + v * (int64_t)P.cap_pts * 3;
-  double *dst = P.s_p + (int64_t)smp * P.cap_pts * 3;
-  for (int i = lane; i < np * 3; i += 32) dst[i] = src[i];
-  double *eo = (side ? b_out : a_out) + (int64_t)e * P.S;
-  for (int k = lane; k < P.S; k += 32) {
-    const double x = vstates[v * P.S + k];
-    P.s_state[(int64_t)smp * P.S + k] = x;
-    eo[k] = x;
-  }
-  if (lane == 0) {
-    P.s_edge[smp] = e;
-    P.s_t[smp] = side ? 1.0 : 0.0;
-    P.s_npts[smp] = np;
-    P.s_flags[smp] = vflags[v];
-    P.s_next[smp] = side ? (smp - 1) : -1;
-    if (side) {
-      P.head[e] = smp;
-      P.first_invalid[e] = (unsigned long long)__double_as_longlong(10.0);
-      P.eflags[e] = 0u;
-    }
-  }
-}
-
-// rel_threshold = 1 / validSegmentCount(a, b) (VoxelBackboneMotionValidator.cpp:55-56), the same
-// arithmetic as irt_valid_segment_count (this file is compiled without FMA contraction)
-__global__ void edge_threshold_kernel(EdgePool P, int32_t E, const double *__restrict__ a,
-                                      const double *__restrict__ b, double len_t, double len_r,
-                                      double len_s, double *__restrict__ thr) {
-  const int32_t e = blockIdx.x * blockDim.x + threadIdx.x;
-  if (e >= E) return;
-  const double pi = 3.14159265358979323846;
-  const double *ea = a + (int64_t)e * P.S, *eb = b + (int64_t)e * P.S;
-  double d2 = 0;
-  for (int i = 0; i < P.N; i++) d2 += (ea[i] - eb[i]) * (ea[i] - eb[i]);
-  unsigned sc = (unsigned)ceil(sqrt(d2) / len_t);
-  int idx = P.N;
-  if (P.enable_rotation) {
-    double d = fabs(ea[idx] - eb[idx]);
-    d = (d > pi) ? 2.0 * pi - d : d;
-    const unsigned c = (unsigned)ceil(d / len_r);
-    if (c > sc) sc = c;
-    idx++;
-  }
-  if (P.enable_retraction) {
-    const double d = sqrt((ea[idx] - eb[idx]) * (ea[idx] - eb[idx]));
-    const unsigned c = (unsigned)ceil(d / len_s);
-    if (c > sc) sc = c;
-  }
-  thr[e] = 1.0 / double(sc);
-}
-
-// after FK: invalid samples lower first_invalid_t of their edge (VoxelEnvironment.cpp:266-268)
-__global__ void edge_mark_kernel(EdgePool P, int32_t lo, int32_t hi) {
-  const int32_t i = lo + blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= hi) return;
-  if (P.s_flags[i] & INVALID_MASK)
-    atomicMin(&P.first_invalid[P.s_edge[i]], (unsigned long long)__double_as_longlong(P.s_t[i]));
-}
 
 // OMPL compound interpolate restated (RealVector linear, SO2 shortest arc + wrap), the `interp`
 // lambda of VoxelBackboneMotionValidator.cpp:58-66
@@ -628,30 +657,98 @@ __device__ void interpolate_state(const EdgePool &P, const double *a, const doub
   if (P.enable_retraction) out[idx] = a[idx] + (b[idx] - a[idx]) * t;
 }
 
-// one thread per open interval: VoxelEnvironment.cpp:369-384
-__global__ void edge_split_kernel(EdgePool P, const Interval *__restrict__ cur, int32_t ncur,
-                                  int32_t *__restrict__ n_samples, Pending *__restrict__ pend,
-                                  int32_t *__restrict__ n_pend) {
-  const int32_t q = blockIdx.x * blockDim.x + threadIdx.x;
-  if (q >= ncur) return;
-  const Interval iv = cur[q];
-  const double ta = P.s_t[iv.ia], tb = P.s_t[iv.ib];
-  if ((tb - ta) <= P.thr[iv.edge]) return;
-  const double fi = __longlong_as_double((long long)P.first_invalid[iv.edge]);
-  if (fi <= ta) return;
-  const int32_t m = atomicAdd(n_samples, 1);
-  if (m >= P.cap_samples) {
-    atomicOr(&P.eflags[iv.edge], IRT_FLAG_CAPACITY);
-    return;
+// one thread per edge of the chunk: validates / clamps the endpoint indices, rel_threshold =
+// 1 / validSegmentCount(a, b) (VoxelBackboneMotionValidator.cpp:55-56, the same arithmetic as
+// irt_valid_segment_count: this file is compiled without FMA contraction), first_invalid_t from the endpoint
+// validity (VoxelEnvironment.cpp:261-268), empty sample list
+__global__ void edge_init_kernel(EdgePool P, int32_t *__restrict__ C, double len_t, double len_r, double len_s) {
+  const int32_t e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= P.E) return;
+  int64_t va = P.pairs[2 * (int64_t)e], vb = P.pairs[2 * (int64_t)e + 1];
+  if (va < 0 || va >= P.nv || vb < 0 || vb >= P.nv) {   // reported as IRT_ERR_OUT_OF_RANGE by the host
+    atomicOr(&C[C_ERR], 1);
+    va = (va < 0 || va >= P.nv) ? 0 : va;
+    vb = (vb < 0 || vb >= P.nv) ? 0 : vb;
+    P.pairs[2 * (int64_t)e] = va;
+    P.pairs[2 * (int64_t)e + 1] = vb;
   }
-  const double tm = (ta + tb) / 2;
-  P.s_edge[m] = iv.edge;
-  P.s_t[m] = tm;
-  interpolate_state(P, P.a + (int64_t)iv.edge * P.S, P.b + (int64_t)iv.edge * P.S, tm,
-                    P.s_state + (int64_t)m * P.S);
-  P.s_next[m] = atomicExch(&P.head[iv.edge], m);
-  const int32_t k = atomicAdd(n_pend, 1);
-  pend[k] = Pending{iv.edge, iv.ia, m, iv.ib};
+  const double pi = 3.14159265358979323846;
+  const double *ea = P.v_state + va * P.S, *eb = P.v_state + vb * P.S;
+  double d2 = 0;
+  for (int i = 0; i < P.N; i++) d2 += (ea[i] - eb[i]) * (ea[i] - eb[i]);
+  unsigned sc = (unsigned)ceil(sqrt(d2) / len_t);
+  int idx = P.N;
+  if (P.enable_rotation) {
+    double d = fabs(ea[idx] - eb[idx]);
+    d = (d > pi) ? 2.0 * pi - d : d;
+    const unsigned c = (unsigned)ceil(d / len_r);
+    if (c > sc) sc = c;
+    idx++;
+  }
+  if (P.enable_retraction) {
+    const double d = sqrt((ea[idx] - eb[idx]) * (ea[idx] - eb[idx]));
+    const unsigned c = (unsigned)ceil(d / len_s);
+    if (c > sc) sc = c;
+  }
+  P.thr[e] = 1.0 / double(sc);
+  double fi = 10.0;                                       // VoxelEnvironment.cpp:261
+  if (P.v_flags[va] & INVALID_MASK) fi = 0.0;             // :266-268: the smallest invalid t
+  else if (P.v_flags[vb] & INVALID_MASK) fi = 1.0;
+  P.first_invalid[e] = (unsigned long long)__double_as_longlong(fi);
+  P.head[e] = -1;
+  P.eflags[e] = 0u;
+}
+
+// non-indexed entry points: the endpoints of edge e are vertices 2e and 2e+1 of the chunk's own vertex pool
+__global__ void edge_identity_pairs_kernel(int64_t *__restrict__ pairs, int32_t E) {
+  const int32_t e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e < E) { pairs[2 * (int64_t)e] = 2 * (int64_t)e; pairs[2 * (int64_t)e + 1] = 2 * (int64_t)e + 1; }
+}
+
+// start of a round: the samples created from here on are [lo, ...); the queue this round fills is empty
+__global__ void round_begin_kernel(int32_t *__restrict__ C, int32_t cap_mid, int q_next) {
+  if (threadIdx.x == 0) {
+    C[C_LO] = min(C[C_NMID], cap_mid);
+    C[C_NPEND] = 0;
+    C[C_NQ0 + q_next] = 0;
+  }
+}
+__global__ void round_mid_kernel(int32_t *__restrict__ C, int32_t cap_mid) {
+  if (threadIdx.x == 0) C[C_HI] = min(C[C_NMID], cap_mid);
+}
+
+// one thread per open interval: VoxelEnvironment.cpp:369-384
+__global__ void edge_split_kernel(EdgePool P, const Interval *__restrict__ cur, int32_t *__restrict__ C, int q_cur,
+                                  Pending *__restrict__ pend) {
+  const int32_t ncur = min(C[C_NQ0 + q_cur], P.cap_q);
+  for (int32_t q = blockIdx.x * blockDim.x + threadIdx.x; q < ncur; q += gridDim.x * blockDim.x) {
+    const Interval iv = cur[q];
+    const double ta = smp_t(P, iv.ia), tb = smp_t(P, iv.ib);
+    if ((tb - ta) <= P.thr[iv.edge]) continue;
+    const double fi = __longlong_as_double((long long)P.first_invalid[iv.edge]);
+    if (fi <= ta) continue;
+    const int32_t m = atomicAdd(&C[C_NMID], 1);
+    if (m >= P.cap_mid) {   // pool full: the host sees C_NMID > cap_mid and redoes the chunk in two halves
+      atomicOr(&P.eflags[iv.edge], IRT_FLAG_CAPACITY);
+      continue;
+    }
+    const double tm = (ta + tb) / 2;
+    P.m_edge[m] = iv.edge;
+    P.m_t[m] = tm;
+    interpolate_state(P, P.v_state + end_vertex(P, iv.edge, -1) * P.S, P.v_state + end_vertex(P, iv.edge, -2) * P.S,
+                      tm, P.m_state + (int64_t)m * P.S);
+    P.m_next[m] = atomicExch(&P.head[iv.edge], m);
+    const int32_t k = atomicAdd(&C[C_NPEND], 1);
+    pend[k] = Pending{iv.edge, iv.ia, m, iv.ib};
+  }
+}
+
+// after FK: invalid samples lower first_invalid_t of their edge (VoxelEnvironment.cpp:266-268)
+__global__ void edge_mark_kernel(EdgePool P, const int32_t *__restrict__ C) {
+  const int32_t lo = C[C_LO], hi = C[C_HI];
+  for (int32_t i = lo + blockIdx.x * blockDim.x + threadIdx.x; i < hi; i += gridDim.x * blockDim.x)
+    if (P.m_flags[i] & INVALID_MASK)
+      atomicMin(&P.first_invalid[P.m_edge[i]], (unsigned long long)__double_as_longlong(P.m_t[i]));
 }
 
 // find_cell -- collision/VoxelOctree.cpp:309-317 (+domain_check :1511-1521); false = domain error
@@ -659,6 +756,15 @@ __device__ __forceinline__ bool find_cell(const GridDev &g, const D3 &p, long lo
   if (p.x < g.lo[0] || g.hi[0] < p.x) return false;
   if (p.y < g.lo[1] || g.hi[1] < p.y) return false;
   if (p.z < g.lo[2] || g.hi[2] < p.z) return false;
+  // the quotient by the reciprocal differs from the reference's division by a few ulp (< 1e-13 cells): the
+  // truncation is the same unless the point is within 1e-9 of a cell face, where the division itself decides
+  const double qx = (p.x - g.lo[0]) * g.inv_d[0], qy = (p.y - g.lo[1]) * g.inv_d[1], qz = (p.z - g.lo[2]) * g.inv_d[2];
+  const double fx = qx - floor(qx), fy = qy - floor(qy), fz = qz - floor(qz);
+  const double m = 1e-9;
+  if (fx > m && fx < 1.0 - m && fy > m && fy < 1.0 - m && fz > m && fz < 1.0 - m) {
+    c[0] = (long long)qx; c[1] = (long long)qy; c[2] = (long long)qz;
+    return true;
+  }
   c[0] = (long long)((p.x - g.lo[0]) / g.d[0]);
   c[1] = (long long)((p.y - g.lo[1]) / g.d[1]);
   c[2] = (long long)((p.z - g.lo[2]) / g.d[2]);
@@ -667,13 +773,13 @@ __device__ __forceinline__ bool find_cell(const GridDev &g, const D3 &p, long lo
 
 // should_subdivide(a, b) -- VoxelEnvironment.cpp:304-341, warp-cooperative (lanes over points,
 // scanned from the tip like the reference so the first event found is the same one)
-__device__ bool should_subdivide(const GridDev &g, const EdgePool &P, int32_t ia, int32_t ib,
-                                 int32_t edge, int lane) {
-  if (P.s_flags[ia] & INVALID_MASK) return false;
-  const int na = P.s_npts[ia], nb = P.s_npts[ib];
+__device__ bool should_subdivide(const GridDev &g, const EdgePool &P, int32_t edge, int32_t ra, int32_t rb,
+                                 int lane) {
+  if (smp_flags(P, edge, ra) & INVALID_MASK) return false;
+  const int na = smp_npts(P, edge, ra), nb = smp_npts(P, edge, rb);
   if (na + 1 < nb || na > nb + 1) return true;
   const int Pn = min(na, nb);
-  const double *pa = P.s_p + (int64_t)ia * P.cap_pts * 3, *pb = P.s_p + (int64_t)ib * P.cap_pts * 3;
+  const double *pa = smp_pts(P, edge, ra), *pb = smp_pts(P, edge, rb);
   for (int top = Pn - 1; top >= 0; top -= 32) {
     const int i = top - lane;
     int ev = 0;  // 1 = far apart, 2 = domain error
@@ -701,45 +807,45 @@ __device__ bool should_subdivide(const GridDev &g, const EdgePool &P, int32_t ia
   return false;
 }
 
-// one warp per candidate: round 0 tests (2e, 2e+1); later rounds test both halves of a bisected
+// one warp per candidate: round 0 tests the whole edge (a, b); later rounds test both halves of a bisected
 // interval (VoxelEnvironment.cpp:350-353,386-397)
 __global__ void edge_subdivide_kernel(const GridDev g, EdgePool P, const Pending *__restrict__ pend,
-                                      int32_t npend, int32_t E_round0, Interval *__restrict__ next,
-                                      int32_t *__restrict__ n_next, int32_t cap_next) {
+                                      int32_t *__restrict__ C, Interval *__restrict__ next, int q_next) {
   const int lane = threadIdx.x & 31;
-  const int32_t w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int32_t total = pend ? npend : E_round0;
-  if (w >= total) return;
-  if (!pend) {
-    const int32_t e = w;
-    if (should_subdivide(g, P, 2 * e, 2 * e + 1, e, lane) && lane == 0) {
-      const int32_t k = atomicAdd(n_next, 1);
-      if (k < cap_next) next[k] = Interval{e, 2 * e, 2 * e + 1};
-      else atomicOr(&P.eflags[e], IRT_FLAG_CAPACITY);
+  const int32_t total = pend ? min(C[C_NPEND], P.cap_mid) : P.E;
+  const int32_t nwarps = (gridDim.x * blockDim.x) >> 5;
+  int32_t *n_next = &C[C_NQ0 + q_next];
+  for (int32_t w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; w < total; w += nwarps) {
+    if (!pend) {
+      const int32_t e = w;
+      if (should_subdivide(g, P, e, -1, -2, lane) && lane == 0) {
+        const int32_t k = atomicAdd(n_next, 1);
+        if (k < P.cap_q) next[k] = Interval{e, -1, -2};
+        else atomicOr(&P.eflags[e], IRT_FLAG_CAPACITY);
+      }
+      continue;
     }
-    return;
-  }
-  const Pending pd = pend[w];
-  const bool distal = should_subdivide(g, P, pd.im, pd.ib, pd.edge, lane);
-  const bool proximal = should_subdivide(g, P, pd.ia, pd.im, pd.edge, lane);
-  if (lane == 0) {
-    if (distal) {
-      const int32_t k = atomicAdd(n_next, 1);
-      if (k < cap_next) next[k] = Interval{pd.edge, pd.im, pd.ib};
-      else atomicOr(&P.eflags[pd.edge], IRT_FLAG_CAPACITY);
-    }
-    if (proximal) {
-      const int32_t k = atomicAdd(n_next, 1);
-      if (k < cap_next) next[k] = Interval{pd.edge, pd.ia, pd.im};
-      else atomicOr(&P.eflags[pd.edge], IRT_FLAG_CAPACITY);
+    const Pending pd = pend[w];
+    const bool distal = should_subdivide(g, P, pd.edge, pd.im, pd.ib, lane);
+    const bool proximal = should_subdivide(g, P, pd.edge, pd.ia, pd.im, lane);
+    if (lane == 0) {
+      if (distal) {
+        const int32_t k = atomicAdd(n_next, 1);
+        if (k < P.cap_q) next[k] = Interval{pd.edge, pd.im, pd.ib};
+        else atomicOr(&P.eflags[pd.edge], IRT_FLAG_CAPACITY);
+      }
+      if (proximal) {
+        const int32_t k = atomicAdd(n_next, 1);
+        if (k < P.cap_q) next[k] = Interval{pd.edge, pd.ia, pd.im};
+        else atomicOr(&P.eflags[pd.edge], IRT_FLAG_CAPACITY);
+      }
     }
   }
 }
 
-__global__ void edge_finish_kernel(EdgePool P, int32_t E, double *__restrict__ tlimit,
-                                   uint32_t *__restrict__ flags_out) {
+__global__ void edge_finish_kernel(EdgePool P, double *__restrict__ tlimit, uint32_t *__restrict__ flags_out) {
   const int32_t e = blockIdx.x * blockDim.x + threadIdx.x;
-  if (e >= E) return;
+  if (e >= P.E) return;
   const double fi = __longlong_as_double((long long)P.first_invalid[e]);
   tlimit[e] = fi;
   uint32_t f = P.eflags[e];
@@ -775,7 +881,7 @@ int arena_layout(irt_ctx *ctx, const F &layout) {
   return IRT_OK;
 }
 
-constexpr int64_t RS_CHUNK_SETS = 262144;  // sets rasterised per launch (slot scratch = 3 KiB per set)
+constexpr int64_t RS_CHUNK_SETS = 524288;  // sets rasterised per launch (slot scratch = 3 KiB per set)
 
 struct RasterScratch {
   uint32_t *slot_keys = nullptr, *big_keys = nullptr;
@@ -783,8 +889,10 @@ struct RasterScratch {
   uint32_t *counts = nullptr;
   uint64_t *scan_tmp = nullptr;
   int32_t *ovf_list = nullptr, *ovf_count = nullptr, *ovf_slot = nullptr;
+  int64_t chunk = 0;
   template <typename A>
-  bool layout(A &a, int64_t chunk) {
+  bool layout(A &a, int64_t chunk_sets) {
+    chunk = chunk_sets;
     const int64_t ntiles = (chunk + SCAN_TILE - 1) / SCAN_TILE;
     return a.alloc(&slot_keys, (size_t)chunk * RS_SLOT) && a.alloc(&slot_bits, (size_t)chunk * RS_SLOT) &&
            a.alloc(&big_keys, (size_t)RS_MAX_OVF * RS_BIGSLOT) && a.alloc(&big_bits, (size_t)RS_MAX_OVF * RS_BIGSLOT) &&
@@ -793,53 +901,73 @@ struct RasterScratch {
   }
 };
 
-// Rasterise sets [0, nsets) of one sample pool and APPEND them to the store: the sets become
-// store sets [set_base, set_base + nsets) and their leaves start at leaf_base.
-int raster_append(irt_ctx *ctx, const GridDev &g, const double *d_pts, const int32_t *d_npts,
-                  int cap_pts, const int32_t *d_heads, const int32_t *d_next, const double *d_st,
-                  const double *d_tlimit, int64_t nsets, double *d_tlast, int32_t *d_nsamples,
-                  uint32_t *d_setflags, RasterScratch &rs, irt_setstore *store, int64_t set_base,
-                  uint64_t leaf_base, uint64_t *leaf_total_out, cudaStream_t st) {
+// Rasterise sets [0, nsets) of `src` and APPEND them to the store: they become store sets
+// [set_base, set_base + nsets), their leaves follow the *d_running leaves already there (device-chained:
+// no host synchronisation; *d_running advances).  A store too small for the leaves raises *d_overflow.
+// Per-set outputs (d_tlast, d_nsamples, d_setflags) are indexed like the sets of `src`.
+int raster_append(irt_ctx *ctx, const GridDev &g, const SetSrc &src, int64_t nsets, double *d_tlast,
+                  int32_t *d_nsamples, uint32_t *d_setflags, RasterScratch &rs, irt_setstore *store,
+                  int64_t set_base, uint64_t *d_running, int32_t *d_overflow, cudaStream_t st) {
   auto k_small = swept_voxel_raster_kernel<RS_HLOG_SMALL, RS_WARPS>;
   auto k_big = swept_voxel_raster_kernel<RS_HLOG_BIG, 1>;
   const int smem_small = RS_WARPS * rs_warp_bytes(RS_HLOG_SMALL), smem_big = rs_warp_bytes(RS_HLOG_BIG);
   IRT_CUDA(ctx, cudaFuncSetAttribute(k_big, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_big));
-  uint64_t running = leaf_base;
-  for (int64_t c0 = 0; c0 < nsets; c0 += RS_CHUNK_SETS) {
-    const int64_t m = (nsets - c0 < RS_CHUNK_SETS) ? (nsets - c0) : RS_CHUNK_SETS;
+  for (int64_t c0 = 0; c0 < nsets; c0 += rs.chunk) {
+    const int64_t m = (nsets - c0 < rs.chunk) ? (nsets - c0) : rs.chunk;
     int64_t blocks = (m + RS_WARPS - 1) / RS_WARPS;
     const int64_t max_blocks = (int64_t)ctx->sm_count * 16;
     if (blocks > max_blocks) blocks = max_blocks;
     IRT_CUDA(ctx, cudaMemsetAsync(rs.ovf_count, 0, 4, st));
     IRT_CUDA(ctx, cudaMemsetAsync(rs.ovf_slot, 0, (size_t)m * 4, st));
     k_small<<<(unsigned)blocks, RS_WARPS * 32, smem_small, st>>>(
-        g, d_pts, d_npts, cap_pts, d_heads + c0, d_next, d_st, d_tlimit ? d_tlimit + c0 : nullptr, m, rs.counts,
-        d_tlast ? d_tlast + c0 : nullptr, d_nsamples ? d_nsamples + c0 : nullptr, rs.slot_keys, rs.slot_bits,
-        d_setflags ? d_setflags + c0 : nullptr, rs.ovf_list, rs.ovf_count, rs.ovf_slot);
+        g, src, c0, m, rs.counts, d_tlast ? d_tlast + c0 : nullptr, d_nsamples ? d_nsamples + c0 : nullptr,
+        rs.slot_keys, rs.slot_bits, d_setflags ? d_setflags + c0 : nullptr, rs.ovf_list, rs.ovf_count, rs.ovf_slot);
     IRT_LAUNCHED(ctx);
     // sets that outgrew the small table (normally none): big-table pass over the device-side list
     k_big<<<(unsigned)ctx->sm_count, 32, smem_big, st>>>(
-        g, d_pts, d_npts, cap_pts, d_heads + c0, d_next, d_st, d_tlimit ? d_tlimit + c0 : nullptr, m, rs.counts,
-        d_tlast ? d_tlast + c0 : nullptr, d_nsamples ? d_nsamples + c0 : nullptr, rs.big_keys, rs.big_bits,
-        d_setflags ? d_setflags + c0 : nullptr, rs.ovf_list, rs.ovf_count, rs.ovf_slot);
+        g, src, c0, m, rs.counts, d_tlast ? d_tlast + c0 : nullptr, d_nsamples ? d_nsamples + c0 : nullptr,
+        rs.big_keys, rs.big_bits, d_setflags ? d_setflags + c0 : nullptr, rs.ovf_list, rs.ovf_count, rs.ovf_slot);
     IRT_LAUNCHED(ctx);
     IRT_CUDA(ctx, cudaGetLastError());
-    uint64_t total = 0;
-    int rc = exclusive_scan(ctx, rs.counts, m, running, store->d_offsets + set_base + c0, rs.scan_tmp, &total, st);
-    if (rc) return rc;
-    rc = setstore_grow_blocks(ctx, store, (int64_t)(running + total), (int64_t)running, st);
+    int rc = exclusive_scan_chained(ctx, rs.counts, m, d_running, store->d_offsets + set_base + c0, rs.scan_tmp, st);
     if (rc) return rc;
     const int T = 256;
     raster_gather_kernel<<<(unsigned)((m * 32 + T - 1) / T), T, 0, st>>>(
         rs.slot_keys, rs.slot_bits, rs.big_keys, rs.big_bits, rs.ovf_slot, rs.counts,
-        store->d_offsets + set_base + c0, m, store->d_keys, store->d_bits);
+        store->d_offsets + set_base + c0, m, store->d_keys, store->d_bits, (uint64_t)store->cap_blocks - 4,
+        d_overflow);
     IRT_LAUNCHED(ctx);
     IRT_CUDA(ctx, cudaGetLastError());
-    running += total;
   }
-  *leaf_total_out = running - leaf_base;
   return IRT_OK;
 }
+
+// device words shared by the raster launches of one call: [0] running leaf total (u64), [1] overflow flag
+struct RasterTotals {
+  uint64_t *d_running = nullptr;
+  int32_t *d_overflow = nullptr;
+  template <typename A>
+  bool layout(A &a) {
+    uint64_t *w = nullptr;
+    if (!a.alloc(&w, 4)) return false;
+    d_running = w;
+    d_overflow = reinterpret_cast<int32_t *>(w + 1);
+    return true;
+  }
+  int reset(irt_ctx *ctx, cudaStream_t st) {
+    IRT_CUDA(ctx, cudaMemsetAsync(d_running, 0, 16, st));
+    return IRT_OK;
+  }
+  // total leaves / overflow flag after everything on `st` has run
+  int read(irt_ctx *ctx, cudaStream_t st, uint64_t *total, bool *overflow) {
+    uint64_t h[2] = {0, 0};
+    IRT_CUDA(ctx, cudaMemcpyAsync(h, d_running, 16, cudaMemcpyDeviceToHost, st));
+    IRT_CUDA(ctx, cudaStreamSynchronize(st));
+    *total = h[0];
+    *overflow = (h[1] & 0xffffffffull) != 0;
+    return IRT_OK;
+  }
+};
 
 }  // namespace
 
@@ -879,6 +1007,8 @@ uint32_t irt_valid_segment_count(const irt_robot_desc *rb, const irt_space *sp, 
   return sc;
 }
 
+}  // extern "C"
+
 static int store_begin(irt_ctx *ctx, irt_setstore *store, int64_t n, int64_t est_blocks, cudaStream_t st) {
   int rc = setstore_reserve(ctx, store, n, est_blocks);
   if (rc) return rc;
@@ -896,57 +1026,86 @@ static int check_dl_vs_grid(irt_ctx *ctx, const irt_robot *rb, const GridDev &g)
   return IRT_OK;
 }
 
+// vertex sets: FK + validity + raster, chunk by chunk; the leaf offsets chain on the device, so the only host
+// synchronisation is the one at the end (and per chunk when the caller wants flags / tips on the host).
+// A store that turns out too small is grown to the measured size and the call repeated (once).
+static int voxelize_vertices_impl(irt_ctx *ctx, const irt_robot *rb, const double *states, const double *p_in,
+                                  const int32_t *npts_in, int cap, int state_size, int64_t n, irt_setstore *store,
+                                  uint32_t *flags, double *tips, int64_t est_blocks) {
+  const GridDev &g = store->gd;
+  cudaStream_t st = ctx->stream;
+  int rc = store_begin(ctx, store, n, est_blocks, st);
+  if (rc) return rc;
+  if (n == 0) return setstore_finalize(ctx, store, 0, 0, st);
+  const int S = state_size;
+  const int64_t chunk = std::min<int64_t>(n, 262144);
+  double *d_states = nullptr, *d_p = nullptr, *d_tip = nullptr;
+  int32_t *d_npts = nullptr, *d_heads = nullptr;
+  uint32_t *d_flags = nullptr;
+  RasterScratch rs;
+  RasterTotals tot;
+  rc = arena_layout(ctx, [&](Arena &a) {
+    return a.alloc(&d_states, (size_t)chunk * (states ? S : 1)) && a.alloc(&d_p, (size_t)chunk * cap * 3) &&
+           a.alloc(&d_tip, (size_t)chunk * 3) && a.alloc(&d_npts, (size_t)chunk) &&
+           a.alloc(&d_heads, (size_t)chunk) && a.alloc(&d_flags, (size_t)chunk) && tot.layout(a) &&
+           rs.layout(a, std::min<int64_t>(chunk, RS_CHUNK_SETS));
+  });
+  if (rc) return rc;
+  rc = tot.reset(ctx, st);
+  if (rc) return rc;
+  const int T = 256;
+  for (int64_t off = 0; off < n; off += chunk) {
+    const int64_t m = std::min<int64_t>(chunk, n - off);
+    if (states) {
+      IRT_CUDA(ctx, cudaMemcpyAsync(d_states, states + off * S, (size_t)m * S * 8, cudaMemcpyHostToDevice, st));
+      irt_fk_outputs o;
+      std::memset(&o, 0, sizeof(o));
+      o.p = d_p; o.npts = d_npts; o.flags = d_flags; o.tip = d_tip;
+      rc = fk_launch(ctx, rb, d_states, m, cap, o, st);
+      if (rc) return rc;
+      rc = self_collision_launch(ctx, rb, d_p, d_npts, m, cap, d_flags, st);
+      if (rc) return rc;
+    } else {   // shapes given by the caller
+      IRT_CUDA(ctx, cudaMemcpyAsync(d_p, p_in + off * cap * 3, (size_t)m * cap * 24, cudaMemcpyHostToDevice, st));
+      IRT_CUDA(ctx, cudaMemcpyAsync(d_npts, npts_in + off, (size_t)m * 4, cudaMemcpyHostToDevice, st));
+      IRT_CUDA(ctx, cudaMemsetAsync(d_flags, 0, (size_t)m * 4, st));
+    }
+    vertex_heads_kernel<<<(unsigned)((m + T - 1) / T), T, 0, st>>>(d_flags, m, d_heads);
+    IRT_LAUNCHED(ctx);
+    SetSrc src;
+    std::memset(&src, 0, sizeof(src));
+    src.edge_mode = 0; src.pts = d_p; src.npts = d_npts; src.heads = d_heads; src.cap_pts = cap;
+    rc = raster_append(ctx, g, src, m, nullptr, nullptr, d_flags, rs, store, off, tot.d_running, tot.d_overflow, st);
+    if (rc) return rc;
+    if (flags) IRT_CUDA(ctx, cudaMemcpyAsync(flags + off, d_flags, (size_t)m * 4, cudaMemcpyDeviceToHost, st));
+    if (tips) IRT_CUDA(ctx, cudaMemcpyAsync(tips + off * 3, d_tip, (size_t)m * 24, cudaMemcpyDeviceToHost, st));
+    if ((flags || tips || !states) && off + chunk < n) IRT_CUDA(ctx, cudaStreamSynchronize(st));  // staging reused
+  }
+  uint64_t total = 0;
+  bool overflow = false;
+  rc = tot.read(ctx, st, &total, &overflow);
+  if (rc) return rc;
+  if (overflow) {
+    if ((int64_t)total <= est_blocks) return irt_fail(ctx, IRT_ERR_CAPACITY, "set store overflow");
+    return voxelize_vertices_impl(ctx, rb, states, p_in, npts_in, cap, state_size, n, store, flags, tips,
+                                  (int64_t)total);
+  }
+  return setstore_finalize(ctx, store, n, (int64_t)total, st);
+}
+
+extern "C" {
+
 int irt_voxelize_vertices(irt_ctx *ctx, const irt_robot *rb, const double *states, int state_size,
                           int64_t n, irt_setstore *store, uint32_t *flags, double *tips) {
   if (!ctx || !rb || !store || n < 0 || (n > 0 && !states)) return IRT_ERR_INVALID_ARGUMENT;
   if (state_size != rb->state_size)
     return irt_fail(ctx, IRT_ERR_INVALID_ARGUMENT, "State is not the right size (%d != %d)",
                     state_size, rb->state_size);
-  const GridDev &g = store->gd;
-  int rc = check_dl_vs_grid(ctx, rb, g);
+  int rc = check_dl_vs_grid(ctx, rb, store->gd);
   if (rc) return rc;
   IRT_CUDA(ctx, cudaSetDevice(ctx->device));
-  cudaStream_t st = ctx->stream;
-  rc = store_begin(ctx, store, n, n * 24, st);
-  if (rc) return rc;
-  if (n == 0) return setstore_finalize(ctx, store, 0, 0, st);
-  const int cap = rb->max_points, S = state_size;
-  const int64_t chunk = std::min<int64_t>(n, 262144);
-  double *d_states = nullptr, *d_p = nullptr, *d_tip = nullptr;
-  int32_t *d_npts = nullptr, *d_heads = nullptr;
-  uint32_t *d_flags = nullptr;
-  RasterScratch rs;
-  rc = arena_layout(ctx, [&](Arena &a) {
-    return a.alloc(&d_states, (size_t)chunk * S) && a.alloc(&d_p, (size_t)chunk * cap * 3) &&
-           a.alloc(&d_tip, (size_t)chunk * 3) && a.alloc(&d_npts, (size_t)chunk) &&
-           a.alloc(&d_heads, (size_t)chunk) && a.alloc(&d_flags, (size_t)chunk) &&
-           rs.layout(a, std::min<int64_t>(chunk, RS_CHUNK_SETS));
-  });
-  if (rc) return rc;
-  uint64_t running = 0;
-  const int T = 256;
-  for (int64_t off = 0; off < n; off += chunk) {
-    const int64_t m = std::min<int64_t>(chunk, n - off);
-    IRT_CUDA(ctx, cudaMemcpyAsync(d_states, states + off * S, (size_t)m * S * 8, cudaMemcpyHostToDevice, st));
-    irt_fk_outputs o;
-    std::memset(&o, 0, sizeof(o));
-    o.p = d_p; o.npts = d_npts; o.flags = d_flags; o.tip = d_tip;
-    rc = fk_launch(ctx, rb, d_states, m, cap, o, nullptr, st);
-    if (rc) return rc;
-    rc = self_collision_launch(ctx, rb, d_p, d_npts, m, cap, d_flags, st);
-    if (rc) return rc;
-    vertex_heads_kernel<<<(unsigned)((m + T - 1) / T), T, 0, st>>>(d_flags, m, d_heads);
-    IRT_LAUNCHED(ctx);
-    uint64_t total = 0;
-    rc = raster_append(ctx, g, d_p, d_npts, cap, d_heads, nullptr, nullptr, nullptr, m, nullptr, nullptr,
-                       d_flags, rs, store, off, running, &total, st);
-    if (rc) return rc;
-    running += total;
-    if (flags) IRT_CUDA(ctx, cudaMemcpyAsync(flags + off, d_flags, (size_t)m * 4, cudaMemcpyDeviceToHost, st));
-    if (tips) IRT_CUDA(ctx, cudaMemcpyAsync(tips + off * 3, d_tip, (size_t)m * 24, cudaMemcpyDeviceToHost, st));
-    IRT_CUDA(ctx, cudaStreamSynchronize(st));
-  }
-  return setstore_finalize(ctx, store, n, (int64_t)running, st);
+  return voxelize_vertices_impl(ctx, rb, states, nullptr, nullptr, rb->max_points, state_size, n, store, flags, tips,
+                                n * 24);
 }
 
 int irt_voxelize_shapes(irt_ctx *ctx, const double *p, const int32_t *npts, int cap_pts, int64_t n,
@@ -956,48 +1115,185 @@ int irt_voxelize_shapes(irt_ctx *ctx, const double *p, const int32_t *npts, int 
     if (npts[i] < 0 || npts[i] > cap_pts)
       return irt_fail(ctx, IRT_ERR_INVALID_ARGUMENT, "npts[%lld] out of range", (long long)i);
   IRT_CUDA(ctx, cudaSetDevice(ctx->device));
-  cudaStream_t st = ctx->stream;
-  const GridDev &g = store->gd;
-  int rc = store_begin(ctx, store, n, n * 24, st);
-  if (rc) return rc;
-  if (n == 0) return setstore_finalize(ctx, store, 0, 0, st);
-  const int64_t chunk = std::min<int64_t>(n, 262144);
-  double *d_p = nullptr;
-  int32_t *d_npts = nullptr, *d_heads = nullptr;
-  uint32_t *d_flags = nullptr;
-  RasterScratch rs;
-  rc = arena_layout(ctx, [&](Arena &a) {
-    return a.alloc(&d_p, (size_t)chunk * cap_pts * 3) && a.alloc(&d_npts, (size_t)chunk) &&
-           a.alloc(&d_heads, (size_t)chunk) && a.alloc(&d_flags, (size_t)chunk) &&
-           rs.layout(a, std::min<int64_t>(chunk, RS_CHUNK_SETS));
-  });
-  if (rc) return rc;
-  uint64_t running = 0;
-  const int T = 256;
-  for (int64_t off = 0; off < n; off += chunk) {
-    const int64_t m = std::min<int64_t>(chunk, n - off);
-    IRT_CUDA(ctx, cudaMemcpyAsync(d_p, p + off * cap_pts * 3, (size_t)m * cap_pts * 24, cudaMemcpyHostToDevice, st));
-    IRT_CUDA(ctx, cudaMemcpyAsync(d_npts, npts + off, (size_t)m * 4, cudaMemcpyHostToDevice, st));
-    IRT_CUDA(ctx, cudaMemsetAsync(d_flags, 0, (size_t)m * 4, st));
-    vertex_heads_kernel<<<(unsigned)((m + T - 1) / T), T, 0, st>>>(d_flags, m, d_heads);
-    IRT_LAUNCHED(ctx);
-    uint64_t total = 0;
-    rc = raster_append(ctx, g, d_p, d_npts, cap_pts, d_heads, nullptr, nullptr, nullptr, m, nullptr, nullptr,
-                       d_flags, rs, store, off, running, &total, st);
-    if (rc) return rc;
-    running += total;
-    IRT_CUDA(ctx, cudaStreamSynchronize(st));
-  }
-  return setstore_finalize(ctx, store, n, (int64_t)running, st);
+  return voxelize_vertices_impl(ctx, nullptr, nullptr, p, npts, cap_pts, 0, n, store, nullptr, nullptr, n * 24);
 }
 
 }  // extern "C"
+
+// ---- edges ------------------------------------------------------------------------------------------
+namespace {
+
+// one in-flight chunk of edges: its stream, its share of the arena, its device counters
+struct Lane {
+  cudaStream_t st = nullptr;
+  cudaEvent_t ev_bisect = nullptr;
+  EdgePool P{};
+  int32_t *C = nullptr;            // device counters
+  int32_t *h_C = nullptr;          // pinned host copy
+  Interval *q[2] = {nullptr, nullptr};
+  Pending *pend = nullptr;
+  double *tlimit = nullptr;
+  void *fk_work = nullptr, *sc_work = nullptr;
+  // non-indexed mode: this chunk's own vertex pool (2 endpoints per edge)
+  double *v_state = nullptr, *v_p = nullptr;
+  int32_t *v_npts = nullptr;
+  uint32_t *v_flags = nullptr;
+  RasterScratch rs;
+  int64_t off = 0;
+  int32_t E = 0;
+  int q_cur = 0;
+  int rounds = 0;
+};
+
+struct EdgeJob {
+  irt_ctx *ctx;
+  const irt_robot *rb;
+  const irt_env *env;
+  irt_setstore *store;
+  GridDev g;
+  int S, cap;
+  bool indexed;
+  const double *a, *b;          // host, non-indexed
+  const int64_t *pairs;         // host, indexed
+  int64_t *d_pairs_all = nullptr;   // device copy of all index pairs (indexed)
+  double len_t, len_r, len_s;
+  int static_rounds;
+  // whole-call device outputs (indexed by edge)
+  uint32_t *d_flags = nullptr;
+  double *d_tlast = nullptr;
+  int32_t *d_nsamp = nullptr;
+  RasterTotals tot;
+  cudaEvent_t ev_raster = nullptr;   // raster phases run in chunk order: each waits for the previous one
+  bool raster_pending = false;
+  int64_t mids_total = 0;
+};
+
+const int K2_T = 256;
+
+int issue_round(EdgeJob &J, Lane &L) {
+  irt_ctx *ctx = J.ctx;
+  cudaStream_t st = L.st;
+  const int qc = L.q_cur, qn = qc ^ 1;
+  const int G = ctx->sm_count * 4;
+  round_begin_kernel<<<1, 32, 0, st>>>(L.C, L.P.cap_mid, qn);
+  IRT_LAUNCHED(ctx);
+  edge_split_kernel<<<G, K2_T, 0, st>>>(L.P, L.q[qc], L.C, qc, L.pend);
+  IRT_LAUNCHED(ctx);
+  round_mid_kernel<<<1, 32, 0, st>>>(L.C, L.P.cap_mid);
+  IRT_LAUNCHED(ctx);
+  irt_fk_outputs o;
+  std::memset(&o, 0, sizeof(o));
+  o.p = L.P.m_p; o.npts = L.P.m_npts; o.flags = L.P.m_flags;
+  int rc = fk_launch(ctx, J.rb, L.P.m_state, L.P.cap_mid, J.cap, o, st, nullptr, L.C + C_LO, L.fk_work);
+  if (rc) return rc;
+  rc = self_collision_launch(ctx, J.rb, o.p, o.npts, L.P.cap_mid, J.cap, o.flags, st, nullptr, L.C + C_LO, L.sc_work);
+  if (rc) return rc;
+  if (J.env) {
+    sample_env_collision_kernel<<<G, K2_T, 0, st>>>(J.g, o.p, o.npts, J.cap, 0, L.C + C_LO, J.env->d_blocks,
+                                                    J.env->d_occ, o.flags);
+    IRT_LAUNCHED(ctx);
+  }
+  edge_mark_kernel<<<G, K2_T, 0, st>>>(L.P, L.C);
+  IRT_LAUNCHED(ctx);
+  edge_subdivide_kernel<<<G * 2, K2_T, 0, st>>>(J.g, L.P, L.pend, L.C, L.q[qn], qn);
+  IRT_LAUNCHED(ctx);
+  IRT_CUDA(ctx, cudaGetLastError());
+  L.q_cur = qn;
+  L.rounds++;
+  return IRT_OK;
+}
+
+// everything of a chunk up to (not including) the raster: uploads, endpoint FK (non-indexed), init, all rounds
+int issue_bisection(EdgeJob &J, Lane &L, int64_t off, int32_t E) {
+  irt_ctx *ctx = J.ctx;
+  cudaStream_t st = L.st;
+  L.off = off; L.E = E; L.P.E = E; L.q_cur = 0; L.rounds = 0;
+  IRT_CUDA(ctx, cudaMemsetAsync(L.C, 0, C_WORDS * 4, st));
+  if (J.indexed) {
+    L.P.pairs = J.d_pairs_all + 2 * off;
+  } else {
+    // this chunk's vertex pool: endpoint a of edge e = vertex 2e, endpoint b = vertex 2e + 1
+    const size_t row = (size_t)J.S * 8;
+    IRT_CUDA(ctx, cudaMemcpy2DAsync(L.v_state, 2 * row, J.a + off * J.S, row, row, E, cudaMemcpyHostToDevice, st));
+    IRT_CUDA(ctx, cudaMemcpy2DAsync(L.v_state + J.S, 2 * row, J.b + off * J.S, row, row, E, cudaMemcpyHostToDevice, st));
+    edge_identity_pairs_kernel<<<(E + K2_T - 1) / K2_T, K2_T, 0, st>>>(L.P.pairs, E);
+    IRT_LAUNCHED(ctx);
+    irt_fk_outputs o;
+    std::memset(&o, 0, sizeof(o));
+    o.p = L.v_p; o.npts = L.v_npts; o.flags = L.v_flags;
+    int rc = fk_launch(ctx, J.rb, L.v_state, 2 * (int64_t)E, J.cap, o, st, nullptr, nullptr, L.fk_work);
+    if (rc) return rc;
+    rc = self_collision_launch(ctx, J.rb, o.p, o.npts, 2 * (int64_t)E, J.cap, o.flags, st, nullptr, nullptr, L.sc_work);
+    if (rc) return rc;
+    if (J.env) {
+      sample_env_collision_kernel<<<ctx->sm_count * 4, K2_T, 0, st>>>(J.g, o.p, o.npts, J.cap, 2 * (int64_t)E, nullptr,
+                                                                      J.env->d_blocks, J.env->d_occ, o.flags);
+      IRT_LAUNCHED(ctx);
+    }
+    L.P.nv = 2 * (int64_t)E;
+  }
+  edge_init_kernel<<<(E + K2_T - 1) / K2_T, K2_T, 0, st>>>(L.P, L.C, J.len_t, J.len_r, J.len_s);
+  IRT_LAUNCHED(ctx);
+  edge_subdivide_kernel<<<ctx->sm_count * 8, K2_T, 0, st>>>(J.g, L.P, nullptr, L.C, L.q[0], 0);
+  IRT_LAUNCHED(ctx);
+  IRT_CUDA(ctx, cudaGetLastError());
+  for (int r = 0; r < J.static_rounds; r++) {
+    int rc = issue_round(J, L);
+    if (rc) return rc;
+  }
+  IRT_CUDA(ctx, cudaMemcpyAsync(L.h_C, L.C, C_WORDS * 4, cudaMemcpyDeviceToHost, st));
+  IRT_CUDA(ctx, cudaEventRecord(L.ev_bisect, st));
+  return IRT_OK;
+}
+
+// waits for the chunk's bisection; runs extra rounds while intervals are still open.
+// *overflow: the mid pool was too small (the chunk has to be redone in smaller pieces)
+int finish_bisection(EdgeJob &J, Lane &L, bool *overflow) {
+  irt_ctx *ctx = J.ctx;
+  for (;;) {
+    IRT_CUDA(ctx, cudaEventSynchronize(L.ev_bisect));
+    if (L.h_C[C_ERR] & 1)
+      return irt_fail(ctx, IRT_ERR_OUT_OF_RANGE, "edge endpoint index outside [0,%lld)", (long long)L.P.nv);
+    *overflow = L.h_C[C_NMID] > L.P.cap_mid;
+    const int32_t open = L.h_C[C_NQ0 + L.q_cur];
+    if (open > L.P.cap_q) *overflow = true;
+    if (*overflow || open == 0 || L.rounds >= 64) return IRT_OK;
+    for (int r = 0; r < 2; r++) {   // deeper than the static bound (states outside the space bounds): keep going
+      int rc = issue_round(J, L);
+      if (rc) return rc;
+    }
+    IRT_CUDA(ctx, cudaMemcpyAsync(L.h_C, L.C, C_WORDS * 4, cudaMemcpyDeviceToHost, L.st));
+    IRT_CUDA(ctx, cudaEventRecord(L.ev_bisect, L.st));
+  }
+}
+
+int issue_raster(EdgeJob &J, Lane &L) {
+  irt_ctx *ctx = J.ctx;
+  cudaStream_t st = L.st;
+  edge_finish_kernel<<<(L.E + K2_T - 1) / K2_T, K2_T, 0, st>>>(L.P, L.tlimit, J.d_flags + L.off);
+  IRT_LAUNCHED(ctx);
+  // the leaf offsets chain through *d_running: raster phases run in chunk order
+  if (J.raster_pending) IRT_CUDA(ctx, cudaStreamWaitEvent(st, J.ev_raster, 0));
+  SetSrc src;
+  std::memset(&src, 0, sizeof(src));
+  src.edge_mode = 1; src.P = L.P; src.tlimit = L.tlimit; src.cap_pts = J.cap;
+  // rasterise every sample below the first invalid t (VoxelEnvironment.cpp:406-422)
+  int rc = raster_append(ctx, J.g, src, L.E, J.d_tlast + L.off, J.d_nsamp + L.off, J.d_flags + L.off, L.rs, J.store,
+                         L.off, J.tot.d_running, J.tot.d_overflow, st);
+  if (rc) return rc;
+  IRT_CUDA(ctx, cudaEventRecord(J.ev_raster, st));
+  J.raster_pending = true;
+  J.mids_total += std::min(L.h_C[C_NMID], L.P.cap_mid);
+  return IRT_OK;
+}
+
+}  // namespace
 
 // a, b: per-edge endpoint states (host) -- or, indexed form: vstates[nv][S] + pairs[n][2]
 static int voxelize_edges_core(irt_ctx *ctx, const irt_robot *rb, const irt_space *space, const double *a,
                                const double *b, const double *vstates, int64_t nv, const int64_t *pairs,
                                int state_size, int64_t n, const irt_env *env, irt_setstore *store,
-                               uint32_t *flags, double *t_last, int32_t *nsamples) {
+                               uint32_t *flags, double *t_last, int32_t *nsamples, int64_t est_blocks = -1) {
   const bool indexed = pairs != nullptr;
   if (env && store && env->grid.Ng != store->grid.Ng)
     return irt_fail(ctx, IRT_ERR_INVALID_ARGUMENT, "voxel dimension mismatch (%d != %d)", env->grid.Ng,
@@ -1005,10 +1301,7 @@ static int voxelize_edges_core(irt_ctx *ctx, const irt_robot *rb, const irt_spac
   if (!ctx || !rb || !space || !store || n < 0) return IRT_ERR_INVALID_ARGUMENT;
   if (!indexed && n > 0 && (!a || !b)) return IRT_ERR_INVALID_ARGUMENT;
   if (indexed && (nv < 0 || (nv > 0 && !vstates))) return IRT_ERR_INVALID_ARGUMENT;
-  if (indexed)
-    for (int64_t i = 0; i < 2 * n; i++)
-      if (pairs[i] < 0 || pairs[i] >= nv)
-        return irt_fail(ctx, IRT_ERR_OUT_OF_RANGE, "edge endpoint %lld outside [0,%lld)", (long long)pairs[i], (long long)nv);
+  if (indexed && n > 0 && nv == 0) return irt_fail(ctx, IRT_ERR_OUT_OF_RANGE, "edges over an empty vertex list");
   if (state_size != rb->state_size)
     return irt_fail(ctx, IRT_ERR_INVALID_ARGUMENT, "State is not the right size (%d != %d)",
                     state_size, rb->state_size);
@@ -1016,224 +1309,222 @@ static int voxelize_edges_core(irt_ctx *ctx, const irt_robot *rb, const irt_spac
   int rc = check_dl_vs_grid(ctx, rb, g);
   if (rc) return rc;
   IRT_CUDA(ctx, cudaSetDevice(ctx->device));
-  cudaStream_t st = ctx->stream;
   const int S = state_size, cap = rb->max_points;
   if (n > (int64_t)0x3fffffff) return irt_fail(ctx, IRT_ERR_INVALID_ARGUMENT, "too many edges");
-  rc = store_begin(ctx, store, n, n * 32, st);
+  if (est_blocks < 0) est_blocks = n * 32;
+  rc = store_begin(ctx, store, n, est_blocks, ctx->stream);
   if (rc) return rc;
-  if (n == 0) return setstore_finalize(ctx, store, 0, 0, st);
-  Trace tr(st);
+  if (n == 0) return setstore_finalize(ctx, store, 0, 0, ctx->stream);
+  Trace tr(ctx->stream);
 
-  // chunk sizing: a sample costs cap*24 + S*8 + 72 bytes; budget ~6 GiB or 40% of free memory
-  size_t free_b = 0, total_b = 0;
-  IRT_CUDA(ctx, cudaMemGetInfo(&free_b, &total_b));
-  free_b += ctx->arena_bytes;  // the arena is ours to reuse
-  const size_t per_sample = (size_t)cap * 24 + (size_t)S * 8 + 72;
-  size_t budget = (size_t)16 << 30;
-  if (budget > free_b * 2 / 5) budget = free_b * 2 / 5;
-  int64_t cap_samples = (int64_t)(budget / per_sample);
-  if (cap_samples > 0x3fffffff) cap_samples = 0x3fffffff;
-  // typical roadmap edges need 4-15 FK samples; a chunk whose pool overflows is split and redone
-  int64_t chunk = cap_samples / 12;
-  if (chunk < 256) { chunk = 256; if (cap_samples < chunk * 8) cap_samples = chunk * 8; }
-  if (chunk > n) {
-    chunk = n;
-    cap_samples = std::min<int64_t>(cap_samples, std::max<int64_t>(chunk * 64, 4096));
-  }
-
-  // longest valid segment lengths of the three subspaces (Problem.cpp:118-144), as in
-  // irt_valid_segment_count; the per-edge count itself is evaluated on the device
-  double len_t, len_r, len_s;
+  EdgeJob J;
+  J.ctx = ctx; J.rb = rb; J.env = env; J.store = store; J.g = g; J.S = S; J.cap = cap;
+  J.indexed = indexed; J.a = a; J.b = b; J.pairs = pairs;
   {
+    // longest valid segment lengths of the three subspaces (Problem.cpp:118-144), as in
+    // irt_valid_segment_count; the per-edge count itself is evaluated on the device.  The deepest
+    // bisection any edge inside the space bounds can need gives the number of rounds launched blind.
     double ext2 = 0;
     for (int i = 0; i < rb->desc.n_tendons; i++) ext2 += rb->desc.max_tension[i] * rb->desc.max_tension[i];
     const double tendon_extent = std::sqrt(ext2);
-    len_t = tendon_extent * (space->min_tension_change / tendon_extent);
-    len_r = M_PI * (space->min_rotation_change / (2 * M_PI));
-    len_s = rb->desc.L * std::fmin(0.01, space->min_retraction_change / rb->desc.L);
+    J.len_t = tendon_extent * (space->min_tension_change / tendon_extent);
+    J.len_r = M_PI * (space->min_rotation_change / (2 * M_PI));
+    J.len_s = rb->desc.L * std::fmin(0.01, space->min_retraction_change / rb->desc.L);
+    double nmax = std::ceil(tendon_extent / J.len_t);
+    if (rb->desc.enable_rotation) nmax = std::fmax(nmax, std::ceil(M_PI / J.len_r));
+    if (rb->desc.enable_retraction) nmax = std::fmax(nmax, std::ceil(rb->desc.L / J.len_s));
+    int depth = 1;
+    while (depth < 40 && std::ldexp(1.0, depth) < nmax) depth++;
+    J.static_rounds = depth + 1;
   }
 
-  EdgePool P;
-  std::memset(&P, 0, sizeof(P));
-  double *d_a = nullptr, *d_b = nullptr, *d_thr = nullptr, *d_tlimit = nullptr, *d_tlast = nullptr;
-  int32_t *d_nsamp_set = nullptr, *d_counters = nullptr;
-  uint32_t *d_flags_out = nullptr;
-  Interval *d_q0 = nullptr, *d_q1 = nullptr;
-  Pending *d_pend = nullptr;
-  RasterScratch rs;
-  // indexed form: FK of every roadmap vertex once; edges gather their endpoint shapes from it
+  // ---- sizing: two lanes (chunks in flight) share the budget ------------------------------------
+  size_t free_b = 0, total_b = 0;
+  IRT_CUDA(ctx, cudaMemGetInfo(&free_b, &total_b));
+  free_b += ctx->arena_bytes;  // the arena is ours to reuse
+  size_t budget = (size_t)24 << 30;
+  if (budget > free_b * 2 / 5) budget = free_b * 2 / 5;
+  const size_t per_mid = (size_t)cap * 24 + (size_t)S * 8 + 24 /* edge, next, npts, flags, t */ +
+                         2 * 2 * sizeof(Interval) + sizeof(Pending) + 8 /* fk keys + perm */ + 12 /* selfcol lists */;
+  const size_t per_vertex = (size_t)cap * 24 + (size_t)S * 8 + 8;
+  const int64_t rs_sets = std::min<int64_t>(n, RS_CHUNK_SETS);
+  const size_t raster_fixed = (size_t)rs_sets * RS_SLOT * 12 + (size_t)RS_MAX_OVF * RS_BIGSLOT * 12 + ((size_t)8 << 20);
+  const size_t fixed = (size_t)n * 32 + (indexed ? (size_t)nv * (per_vertex + 12) : 0) + 2 * raster_fixed + ((size_t)64 << 20);
+  const size_t avail = (budget > fixed) ? budget - fixed : 0;
+  const int mids_per_edge = 3;   // roadmap edges need 2-3 mid samples on average; a chunk whose pool overflows is split
+  const size_t per_edge = mids_per_edge * per_mid + 64 + (indexed ? 0 : 2 * (per_vertex + 20));
+  int64_t chunk = (int64_t)(avail / 2 / per_edge);
+  if (chunk < 256) chunk = 256;
+  int64_t nchunks = (n + chunk - 1) / chunk;
+  if (nchunks > 1 && (nchunks & 1)) nchunks++;   // an even number of chunks keeps both lanes busy to the end
+  chunk = (n + nchunks - 1) / nchunks;
+  const int nlanes = nchunks > 1 ? 2 : 1;
+  int64_t cap_mid = chunk * mids_per_edge;
+  if (n <= 65536) {   // small calls: room for long edges (dozens of samples each) as far as the budget goes
+    const int64_t room = (int64_t)(avail / nlanes / per_mid);
+    cap_mid = std::max<int64_t>(cap_mid, std::min<int64_t>(std::max<int64_t>(chunk * 64, 4096), room));
+  }
+  if (cap_mid > 0x3fffffff) cap_mid = 0x3fffffff;
+  const int64_t cap_q = std::max<int64_t>(chunk, 2 * cap_mid);
+  const int64_t fkn = std::max<int64_t>(cap_mid, indexed ? 0 : 2 * chunk);
+
+  Lane lanes[2];
   double *d_vstates = nullptr, *d_vp = nullptr;
   int32_t *d_vnpts = nullptr;
   uint32_t *d_vflags = nullptr;
-  int64_t *d_pairs = nullptr;
+  int64_t *d_pairs_all = nullptr;
+  void *v_fk_work = nullptr, *v_sc_work = nullptr;
+  const int64_t vchunk = std::min<int64_t>(nv, 1048576);
   rc = arena_layout(ctx, [&](Arena &A) {
-    if (indexed &&
-        !(A.alloc(&d_vstates, (size_t)nv * S) && A.alloc(&d_vp, (size_t)nv * cap * 3) &&
-          A.alloc(&d_vnpts, (size_t)nv) && A.alloc(&d_vflags, (size_t)nv) && A.alloc(&d_pairs, (size_t)chunk * 2)))
+    if (!(A.alloc(&J.d_flags, (size_t)n) && A.alloc(&J.d_tlast, (size_t)n) && A.alloc(&J.d_nsamp, (size_t)n) &&
+          J.tot.layout(A)))
       return false;
-    return A.alloc(&d_a, (size_t)chunk * S) && A.alloc(&d_b, (size_t)chunk * S) &&
-           A.alloc(&d_thr, (size_t)chunk) && A.alloc(&d_tlimit, (size_t)chunk) &&
-           A.alloc(&d_tlast, (size_t)chunk) && A.alloc(&d_nsamp_set, (size_t)chunk) &&
-           A.alloc(&d_flags_out, (size_t)chunk) && A.alloc(&P.first_invalid, (size_t)chunk) &&
-           A.alloc(&P.head, (size_t)chunk) && A.alloc(&P.eflags, (size_t)chunk) &&
-           A.alloc(&P.s_edge, (size_t)cap_samples) && A.alloc(&P.s_next, (size_t)cap_samples) &&
-           A.alloc(&P.s_npts, (size_t)cap_samples) && A.alloc(&P.s_flags, (size_t)cap_samples) &&
-           A.alloc(&P.s_t, (size_t)cap_samples) && A.alloc(&P.s_state, (size_t)cap_samples * S) &&
-           A.alloc(&P.s_p, (size_t)cap_samples * cap * 3) && A.alloc(&d_q0, (size_t)cap_samples) &&
-           A.alloc(&d_q1, (size_t)cap_samples) && A.alloc(&d_pend, (size_t)cap_samples) &&
-           A.alloc(&d_counters, 8) && rs.layout(A, std::min<int64_t>(chunk, RS_CHUNK_SETS));
+    if (indexed) {
+      char *w1 = nullptr, *w2 = nullptr;
+      if (!(A.alloc(&d_pairs_all, (size_t)n * 2) && A.alloc(&d_vstates, (size_t)nv * S) && A.alloc(&d_vp, (size_t)nv * cap * 3) &&
+            A.alloc(&d_vnpts, (size_t)nv) && A.alloc(&d_vflags, (size_t)nv) &&
+            A.alloc(&w1, fk_work_bytes(rb, vchunk)) && A.alloc(&w2, selfcol_work_bytes(vchunk))))
+        return false;
+      v_fk_work = w1; v_sc_work = w2;
+    }
+    for (int l = 0; l < nlanes; l++) {
+      Lane &L = lanes[l];
+      EdgePool &P = L.P;
+      char *w1 = nullptr, *w2 = nullptr;
+      if (!((indexed || A.alloc(&P.pairs, (size_t)chunk * 2)) && A.alloc(&P.thr, (size_t)chunk) &&
+            A.alloc(&P.first_invalid, (size_t)chunk) && A.alloc(&P.head, (size_t)chunk) &&
+            A.alloc(&P.eflags, (size_t)chunk) && A.alloc(&L.tlimit, (size_t)chunk) &&
+            A.alloc(&P.m_edge, (size_t)cap_mid) && A.alloc(&P.m_next, (size_t)cap_mid) &&
+            A.alloc(&P.m_npts, (size_t)cap_mid) && A.alloc(&P.m_flags, (size_t)cap_mid) &&
+            A.alloc(&P.m_t, (size_t)cap_mid) && A.alloc(&P.m_state, (size_t)cap_mid * S) &&
+            A.alloc(&P.m_p, (size_t)cap_mid * cap * 3) && A.alloc(&L.q[0], (size_t)cap_q) &&
+            A.alloc(&L.q[1], (size_t)cap_q) && A.alloc(&L.pend, (size_t)cap_mid) && A.alloc(&L.C, (size_t)C_WORDS) &&
+            A.alloc(&w1, fk_work_bytes(rb, fkn)) && A.alloc(&w2, selfcol_work_bytes(fkn)) &&
+            L.rs.layout(A, std::min<int64_t>(chunk, RS_CHUNK_SETS))))
+        return false;
+      L.fk_work = w1; L.sc_work = w2;
+      if (!indexed &&
+          !(A.alloc(&L.v_state, (size_t)chunk * 2 * S) && A.alloc(&L.v_p, (size_t)chunk * 2 * cap * 3) &&
+            A.alloc(&L.v_npts, (size_t)chunk * 2) && A.alloc(&L.v_flags, (size_t)chunk * 2)))
+        return false;
+    }
+    return true;
   });
   if (rc) return rc;
-  tr.point("thr + pool layout", cap_samples);
-  P.a = d_a; P.b = d_b; P.thr = d_thr;
-  P.cap_samples = (int32_t)cap_samples;
-  P.S = S; P.N = rb->desc.n_tendons; P.cap_pts = cap;
-  P.enable_rotation = rb->desc.enable_rotation ? 1 : 0;
-  P.enable_retraction = rb->desc.enable_retraction ? 1 : 0;
+  int32_t *h_C = (int32_t *)ctx_pinned(ctx, 2 * C_WORDS * 4 + 64);
+  if (!h_C) return irt_fail(ctx, IRT_ERR_CUDA, "pinned staging allocation failed");
+  for (int l = 0; l < nlanes; l++) {
+    Lane &L = lanes[l];
+    L.st = l == 0 ? ctx->stream : ctx->copy_stream;
+    L.ev_bisect = ctx->ev_computed[l];
+    L.h_C = h_C + l * C_WORDS;
+    EdgePool &P = L.P;
+    P.cap_mid = (int32_t)cap_mid; P.cap_q = (int32_t)cap_q;
+    P.S = S; P.N = rb->desc.n_tendons; P.cap_pts = cap;
+    P.enable_rotation = rb->desc.enable_rotation ? 1 : 0;
+    P.enable_retraction = rb->desc.enable_retraction ? 1 : 0;
+    if (indexed) { P.v_state = d_vstates; P.v_p = d_vp; P.v_npts = d_vnpts; P.v_flags = d_vflags; P.nv = nv; }
+    else { P.v_state = L.v_state; P.v_p = L.v_p; P.v_npts = L.v_npts; P.v_flags = L.v_flags; P.nv = 0; }
+  }
+  J.ev_raster = ctx->ev_copied[0];
+  J.d_pairs_all = d_pairs_all;
+  cudaStream_t s0 = ctx->stream;
+  rc = J.tot.reset(ctx, s0);
+  if (rc) return rc;
+  tr.point("layout", cap_mid);
 
-  uint64_t grand_total = 0;
-  const int T = 256;
-  if (indexed && nv > 0) {
-    IRT_CUDA(ctx, cudaMemcpyAsync(d_vstates, vstates, (size_t)nv * S * 8, cudaMemcpyHostToDevice, st));
-    for (int64_t v0 = 0; v0 < nv; v0 += 1048576) {
-      const int64_t m = std::min<int64_t>(1048576, nv - v0);
+  // ---- indexed form: FK of every roadmap vertex once; edges read their endpoint shapes from it ------
+  if (indexed) {
+    IRT_CUDA(ctx, cudaMemcpyAsync(d_vstates, vstates, (size_t)nv * S * 8, cudaMemcpyHostToDevice, s0));
+    for (int64_t v0 = 0; v0 < nv; v0 += vchunk) {
+      const int64_t m = std::min<int64_t>(vchunk, nv - v0);
       irt_fk_outputs o;
       std::memset(&o, 0, sizeof(o));
       o.p = d_vp + v0 * cap * 3; o.npts = d_vnpts + v0; o.flags = d_vflags + v0;
-      rc = fk_launch(ctx, rb, d_vstates + v0 * S, m, cap, o, nullptr, st);
+      rc = fk_launch(ctx, rb, d_vstates + v0 * S, m, cap, o, s0, nullptr, nullptr, v_fk_work);
       if (rc) return rc;
-      rc = self_collision_launch(ctx, rb, o.p, o.npts, m, cap, o.flags, st);
+      rc = self_collision_launch(ctx, rb, o.p, o.npts, m, cap, o.flags, s0, nullptr, nullptr, v_sc_work);
       if (rc) return rc;
       if (env) {
-        sample_env_collision_kernel<<<(unsigned)((m * 32 + T - 1) / T), T, 0, st>>>(
-            g, o.p, o.npts, cap, m, env->d_blocks, env->d_occ, o.flags);
+        sample_env_collision_kernel<<<ctx->sm_count * 4, K2_T, 0, s0>>>(g, o.p, o.npts, cap, m, nullptr, env->d_blocks,
+                                                                        env->d_occ, o.flags);
         IRT_LAUNCHED(ctx);
       }
     }
-    tr.point("vertex fk", nv);
+    // all index pairs in ONE upload, on the second stream, issued after the vertex FK so that the (pageable,
+    // host-blocking) copy runs beside it; no per-chunk copies: they would block the host behind everything
+    // already queued on their stream
+    cudaStream_t sp = lanes[nlanes - 1].st;
+    IRT_CUDA(ctx, cudaMemcpyAsync(d_pairs_all, pairs, (size_t)n * 16, cudaMemcpyHostToDevice, sp));
+    IRT_CUDA(ctx, cudaEventRecord(ctx->ev_copied[1], sp));
+    IRT_CUDA(ctx, cudaStreamWaitEvent(s0, ctx->ev_copied[1], 0));
   }
-  // work list of edge ranges in index order; a range whose sample pool overflows is split in two
-  std::vector<std::pair<int64_t, int64_t>> work;
-  for (int64_t off = n - ((n - 1) % chunk + 1); off >= 0; off -= chunk)
-    work.emplace_back(off, std::min<int64_t>(chunk, n - off));
-  while (!work.empty()) {
-    const int64_t off = work.back().first;
-    const int32_t E = (int32_t)work.back().second;
-    work.pop_back();
-    bool pool_overflow = false;
-    IRT_CUDA(ctx, cudaMemsetAsync(d_counters, 0, 32, st));
-    if (indexed) {
-      IRT_CUDA(ctx, cudaMemcpyAsync(d_pairs, pairs + 2 * off, (size_t)E * 16, cudaMemcpyHostToDevice, st));
-      const int64_t threads = (int64_t)E * 2 * 32;
-      edge_init_indexed_kernel<<<(unsigned)((threads + T - 1) / T), T, 0, st>>>(
-          P, E, d_pairs, d_vstates, d_vp, d_vnpts, d_vflags, d_a, d_b);
-    } else {
-      IRT_CUDA(ctx, cudaMemcpyAsync(d_a, a + off * S, (size_t)E * S * 8, cudaMemcpyHostToDevice, st));
-      IRT_CUDA(ctx, cudaMemcpyAsync(d_b, b + off * S, (size_t)E * S * 8, cudaMemcpyHostToDevice, st));
-      edge_init_kernel<<<(E + T - 1) / T, T, 0, st>>>(P, E);
-    }
-    IRT_LAUNCHED(ctx);
-    edge_threshold_kernel<<<(E + T - 1) / T, T, 0, st>>>(P, E, d_a, d_b, len_t, len_r, len_s, d_thr);
-    IRT_LAUNCHED(ctx);
-    int32_t n_samples = 2 * E;
-    IRT_CUDA(ctx, cudaMemcpyAsync(d_counters, &n_samples, 4, cudaMemcpyHostToDevice, st));
+  // the second lane starts after the vertex pool and the resets above
+  IRT_CUDA(ctx, cudaEventRecord(ctx->ev_offsets[0], s0));
+  if (nlanes > 1) IRT_CUDA(ctx, cudaStreamWaitEvent(lanes[1].st, ctx->ev_offsets[0], 0));
+  tr.point("vertex fk issued", nv);
 
-    auto run_fk = [&](int32_t lo, int32_t hi) -> int {
-      if (hi <= lo) return IRT_OK;
-      irt_fk_outputs o;
-      std::memset(&o, 0, sizeof(o));
-      o.p = P.s_p + (int64_t)lo * cap * 3;
-      o.npts = P.s_npts + lo;
-      o.flags = P.s_flags + lo;
-      int r = fk_launch(ctx, rb, P.s_state + (int64_t)lo * S, hi - lo, cap, o, nullptr, st);
-      if (r) return r;
-      r = self_collision_launch(ctx, rb, o.p, o.npts, hi - lo, cap, o.flags, st);
-      if (r) return r;
-      if (env) {
-        sample_env_collision_kernel<<<(unsigned)(((int64_t)(hi - lo) * 32 + T - 1) / T), T, 0, st>>>(
-            g, o.p, o.npts, cap, hi - lo, env->d_blocks, env->d_occ, o.flags);
-        IRT_LAUNCHED(ctx);
-      }
-      edge_mark_kernel<<<(hi - lo + T - 1) / T, T, 0, st>>>(P, lo, hi);
-      IRT_LAUNCHED(ctx);
-      return IRT_OK;
-    };
-    tr.point("h2d + init");
-    if (indexed) {  // endpoint shapes came from the vertex pool: only mark the invalid ones
-      edge_mark_kernel<<<(n_samples + T - 1) / T, T, 0, st>>>(P, 0, n_samples);
-      IRT_LAUNCHED(ctx);
-    } else {
-      rc = run_fk(0, n_samples);
-      if (rc) return rc;
+  // ---- chunks: up to two in flight, rastered in index order ----------------------------------------
+  std::vector<std::pair<int64_t, int64_t>> todo;   // (offset, count), lowest offset LAST (a stack)
+  for (int64_t off = n - ((n - 1) % chunk + 1); off >= 0; off -= chunk)
+    todo.emplace_back(off, std::min<int64_t>(chunk, n - off));
+  std::vector<Lane *> inflight;                    // sorted by offset
+  std::vector<Lane *> idle;
+  for (int l = nlanes - 1; l >= 0; l--) idle.push_back(&lanes[l]);
+  auto fail = [&](int code) {
+    cudaStreamSynchronize(ctx->stream);
+    cudaStreamSynchronize(ctx->copy_stream);
+    return code;
+  };
+  for (;;) {
+    while (!idle.empty() && !todo.empty()) {
+      Lane *L = idle.back();
+      idle.pop_back();
+      const auto w = todo.back();
+      todo.pop_back();
+      rc = issue_bisection(J, *L, w.first, (int32_t)w.second);
+      if (rc) return fail(rc);
+      auto it = inflight.begin();
+      while (it != inflight.end() && (*it)->off < L->off) ++it;
+      inflight.insert(it, L);
     }
-    tr.point("round 0 fk", n_samples);
-    Interval *cur = d_q0, *nxt = d_q1;
-    int32_t *n_cur = d_counters + 2, *n_nxt = d_counters + 3;
-    {
-      const int64_t threads = (int64_t)E * 32;
-      edge_subdivide_kernel<<<(unsigned)((threads + T - 1) / T), T, 0, st>>>(
-          g, P, nullptr, 0, E, cur, n_cur, (int32_t)cap_samples);
-      IRT_LAUNCHED(ctx);
-    }
-    for (int round = 0; round < 64; round++) {
-      int32_t h_cnt[4];
-      IRT_CUDA(ctx, cudaMemcpyAsync(h_cnt, d_counters, 16, cudaMemcpyDeviceToHost, st));
-      IRT_CUDA(ctx, cudaStreamSynchronize(st));
-      const int32_t ncur_raw = *(cur == d_q0 ? &h_cnt[2] : &h_cnt[3]);
-      if (ncur_raw > (int32_t)cap_samples) pool_overflow = true;
-      const int32_t ncur = std::min(ncur_raw, (int32_t)cap_samples);
-      if (ncur == 0) break;
-      const int32_t s_lo = std::min(h_cnt[0], (int32_t)cap_samples);
-      IRT_CUDA(ctx, cudaMemsetAsync(d_counters + 1, 0, 4, st));  // n_pend
-      IRT_CUDA(ctx, cudaMemsetAsync(n_nxt, 0, 4, st));
-      edge_split_kernel<<<(ncur + T - 1) / T, T, 0, st>>>(P, cur, ncur, d_counters, d_pend, d_counters + 1);
-      IRT_LAUNCHED(ctx);
-      IRT_CUDA(ctx, cudaMemcpyAsync(h_cnt, d_counters, 8, cudaMemcpyDeviceToHost, st));
-      IRT_CUDA(ctx, cudaStreamSynchronize(st));
-      const int32_t s_hi = std::min(h_cnt[0], (int32_t)cap_samples);
-      const int32_t npend = h_cnt[1];
-      if (h_cnt[0] > (int32_t)cap_samples) {  // keep the counter in range
-        int32_t capv = (int32_t)cap_samples;
-        IRT_CUDA(ctx, cudaMemcpyAsync(d_counters, &capv, 4, cudaMemcpyHostToDevice, st));
-        pool_overflow = true;
-      }
-      rc = run_fk(s_lo, s_hi);
-      if (rc) return rc;
-      if (npend > 0) {
-        const int64_t threads = (int64_t)npend * 32;
-        edge_subdivide_kernel<<<(unsigned)((threads + T - 1) / T), T, 0, st>>>(
-            g, P, d_pend, npend, 0, nxt, n_nxt, (int32_t)cap_samples);
-        IRT_LAUNCHED(ctx);
-      }
-      std::swap(cur, nxt);
-      std::swap(n_cur, n_nxt);
-      tr.point("bisection round", s_hi - s_lo);
-    }
-    if (pool_overflow && E > 256) {  // redo this range as two halves (nothing was appended yet)
-      const int64_t h1 = E / 2;
-      work.emplace_back(off + h1, E - h1);
-      work.emplace_back(off, h1);
-      tr.point("pool overflow -> split");
+    if (inflight.empty()) break;
+    Lane *L = inflight.front();
+    inflight.erase(inflight.begin());
+    bool overflow = false;
+    rc = finish_bisection(J, *L, &overflow);
+    if (rc) return fail(rc);
+    tr.point("bisection done", L->h_C[C_NMID]);
+    if (overflow && L->E > 256) {   // redo this range as two halves, before anything that follows it
+      const int64_t h1 = L->E / 2;
+      todo.emplace_back(L->off + h1, L->E - h1);
+      todo.emplace_back(L->off, h1);
+      idle.push_back(L);
       continue;
     }
-    edge_finish_kernel<<<(E + T - 1) / T, T, 0, st>>>(P, E, d_tlimit, d_flags_out);
-    IRT_LAUNCHED(ctx);
-    // rasterise every sample below the first invalid t (VoxelEnvironment.cpp:406-422)
-    uint64_t total = 0;
-    rc = raster_append(ctx, g, P.s_p, P.s_npts, cap, P.head, P.s_next, P.s_t, d_tlimit, E, d_tlast,
-                       d_nsamp_set, d_flags_out, rs, store, off, grand_total, &total, st);
-    if (rc) return rc;
-    tr.point("raster + scan + gather", (long long)total);
-    if (flags) IRT_CUDA(ctx, cudaMemcpyAsync(flags + off, d_flags_out, (size_t)E * 4, cudaMemcpyDeviceToHost, st));
-    if (t_last) IRT_CUDA(ctx, cudaMemcpyAsync(t_last + off, d_tlast, (size_t)E * 8, cudaMemcpyDeviceToHost, st));
-    if (nsamples) IRT_CUDA(ctx, cudaMemcpyAsync(nsamples + off, d_nsamp_set, (size_t)E * 4, cudaMemcpyDeviceToHost, st));
-    IRT_CUDA(ctx, cudaStreamSynchronize(st));
-    grand_total += total;
-    tr.point("chunk d2h");
+    rc = issue_raster(J, *L);
+    if (rc) return fail(rc);
+    idle.push_back(L);
   }
-  rc = setstore_finalize(ctx, store, n, (int64_t)grand_total, st);
-  tr.point("finalize");
-  return rc;
+  // everything is issued; the lanes' streams join on the context stream
+  if (nlanes > 1) {
+    IRT_CUDA(ctx, cudaEventRecord(ctx->ev_offsets[1], lanes[1].st));
+    IRT_CUDA(ctx, cudaStreamWaitEvent(s0, ctx->ev_offsets[1], 0));
+  }
+  if (flags) IRT_CUDA(ctx, cudaMemcpyAsync(flags, J.d_flags, (size_t)n * 4, cudaMemcpyDeviceToHost, s0));
+  if (t_last) IRT_CUDA(ctx, cudaMemcpyAsync(t_last, J.d_tlast, (size_t)n * 8, cudaMemcpyDeviceToHost, s0));
+  if (nsamples) IRT_CUDA(ctx, cudaMemcpyAsync(nsamples, J.d_nsamp, (size_t)n * 4, cudaMemcpyDeviceToHost, s0));
+  uint64_t total = 0;
+  bool overflow = false;
+  rc = J.tot.read(ctx, s0, &total, &overflow);
+  if (rc) return fail(rc);
+  tr.point("raster + d2h done", (long long)total);
+  if (overflow) {   // the store was too small for the leaves: now their number is known, run again
+    if ((int64_t)total <= est_blocks) return irt_fail(ctx, IRT_ERR_CAPACITY, "set store overflow");
+    return voxelize_edges_core(ctx, rb, space, a, b, vstates, nv, pairs, state_size, n, env, store, flags, t_last,
+                               nsamples, (int64_t)total);
+  }
+  return setstore_finalize(ctx, store, n, (int64_t)total, s0);
 }
 
 extern "C" {

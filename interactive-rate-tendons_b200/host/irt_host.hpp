@@ -27,7 +27,9 @@
 #include <cstring>
 #include <functional>
 #include <map>
+#include <limits>
 #include <memory>
+#include <queue>
 #include <random>
 #include <set>
 #include <stdexcept>
@@ -916,6 +918,7 @@ public:
   void setRoadmap(std::vector<std::vector<double>> states, std::vector<std::pair<size_t, size_t>> edges) {
     states_ = std::move(states); edges_ = std::move(edges);
     vflags_.clear(); eflags_.clear();
+    adj_edges_ = (size_t)-1; vertex_removed_.clear(); edge_removed_.clear();
     clearValidity();
   }
   // ---- createRoadmap (VoxelCachedLazyPRM.h:468-495, .cpp:1380-1561) -------------------------------------
@@ -980,6 +983,7 @@ public:
   void createRoadmap(size_t N, unsigned opt = LazyRoadmap) {
     const size_t Nv = states_.size();
     if (N <= Nv) return;  // "Graph is already at or bigger than N, skipping roadmap creation"
+    adj_edges_ = (size_t)-1; vertex_removed_.clear(); edge_removed_.clear();   // the graph changes: adjacency is rebuilt
     const bool validate_verts = opt & ValidateVertices, validate_edges = opt & ValidateEdges;
     const bool voxelize_verts = validate_verts || (opt & VoxelizeVertices);
     const bool voxelize_edges = validate_edges || (opt & VoxelizeEdges);
@@ -1094,15 +1098,112 @@ public:
     if (vflags_.size() != states_.size()) precomputeVertexVoxelCache();
     sweep(vstore_, vflags_, IRT_FLAG_NONCONVERGED | IRT_FLAG_LENGTH_LIMIT | IRT_FLAG_SELF_COLLISION | IRT_FLAG_BAD_STATE,
           vertex_validity_);
+    vertex_swept_ = true;
+    sweeps_++;
   }
   void precomputeEdgeValidity() {  // .cpp:1600-1647
     if (eflags_.size() != edges_.size()) precomputeEdgeVoxelCache();
     sweep(estore_, eflags_, IRT_FLAG_PARTIAL, edge_validity_);
+    edge_swept_ = true;
+    sweeps_++;
   }
   void precomputeValidity() { precomputeVertexValidity(); precomputeEdgeValidity(); }
   void clearValidity() {  // .cpp:1656-1663
     vertex_validity_.assign(states_.size(), VALIDITY_UNKNOWN);
     edge_validity_.assign(edges_.size(), VALIDITY_UNKNOWN);
+    vertex_swept_ = edge_swept_ = false;
+  }
+
+  // ---- lazy-path consumers: the query side of the planner --------------------------
+  /// computeVertexValidity (.cpp:2607-2618).  The reference checks ONE vertex here (voxelise if needed +
+  /// collides); with the verdict words of a full sweep on the host it is a table look-up.  The first query
+  /// after clearValidity() runs the sweep (one K3 launch over all cached sets), later ones only read.
+  bool computeVertexValidity(size_t v) {
+    if (!vertex_swept_) precomputeVertexValidity();
+    lookups_++;
+    return (vertex_validity_[v] & VALIDITY_TRUE) != 0;
+  }
+  /// computeEdgeValidity (.cpp:2620-2631): is_fully_valid (no IRT_FLAG_PARTIAL) and no hit
+  bool computeEdgeValidity(size_t e) {
+    if (!edge_swept_) precomputeEdgeValidity();
+    lookups_++;
+    return (edge_validity_[e] & VALIDITY_TRUE) != 0;
+  }
+  size_t sweepCount() const { return sweeps_; }
+  size_t lookupCount() const { return lookups_; }
+  const std::vector<char> &removedVertices() const { return vertex_removed_; }
+  const std::vector<char> &removedEdges() const { return edge_removed_; }
+  void restoreRemoved() { vertex_removed_.assign(states_.size(), 0); edge_removed_.assign(edges_.size(), 0); }
+  long edgeIndex(size_t a, size_t b) {
+    build_adjacency();
+    for (size_t k = adj_ptr_[a]; k < adj_ptr_[a + 1]; k++)
+      if (adj_nbr_[k] == b) return (long)adj_eid_[k];
+    return -1;
+  }
+  /// astarSearch (.cpp:2950-2976): A* over the current graph (removed vertices / edges left out), motion cost as
+  /// edge weight and heuristic.  Host code in the reference (Boost.Graph) and here.  Empty = no path.
+  std::vector<size_t> astarSearch(size_t start, size_t goal) {
+    build_adjacency();
+    std::vector<size_t> path;
+    if (vertex_removed_[start] || vertex_removed_[goal]) return path;
+    const size_t n = states_.size();
+    std::vector<double> dist(n, std::numeric_limits<double>::infinity());
+    std::vector<size_t> prev(n, n);
+    std::vector<char> done(n, 0);
+    using QE = std::pair<double, size_t>;
+    std::priority_queue<QE, std::vector<QE>, std::greater<QE>> heap;
+    dist[start] = 0.0; prev[start] = start;
+    heap.push({distance(states_[start], states_[goal]), start});
+    while (!heap.empty()) {
+      const size_t u = heap.top().second;
+      heap.pop();
+      if (done[u]) continue;
+      if (u == goal) {
+        for (size_t v = goal; ; v = prev[v]) { path.push_back(v); if (v == start) break; }
+        std::reverse(path.begin(), path.end());
+        return path;
+      }
+      done[u] = 1;
+      for (size_t k = adj_ptr_[u]; k < adj_ptr_[u + 1]; k++) {
+        const size_t v = adj_nbr_[k];
+        if (edge_removed_[adj_eid_[k]] || vertex_removed_[v] || done[v]) continue;
+        const double nd = dist[u] + distance(states_[u], states_[v]);
+        if (nd < dist[v]) {
+          dist[v] = nd; prev[v] = u;
+          heap.push({nd + distance(states_[v], states_[goal]), v});
+        }
+      }
+    }
+    return path;
+  }
+  /// constructSolution (.cpp:2689-2771): A* path, then the lazy checks along it -- every intermediate vertex
+  /// first (ALL invalid ones are removed), then the edges from the goal side (the FIRST invalid one is
+  /// removed).  Returns the validated path, or an empty one when something was removed / no path exists.
+  std::vector<size_t> constructSolution(size_t start, size_t goal) {
+    if (start == goal) return {start};
+    std::vector<size_t> path = astarSearch(start, goal);
+    if (path.empty()) return path;
+    bool removed = false;
+    for (size_t i = path.size() - 1; i-- > 1;)          // intermediate vertices, goal side first
+      if (!computeVertexValidity(path[i])) { vertex_removed_[path[i]] = 1; removed = true; }
+    if (removed) return {};
+    for (size_t i = path.size() - 1; i >= 1; i--) {     // edges, goal side first
+      const long e = edgeIndex(path[i - 1], path[i]);
+      if (e < 0 || !computeEdgeValidity((size_t)e)) {
+        if (e >= 0) edge_removed_[(size_t)e] = 1;
+        return {};
+      }
+    }
+    return path;
+  }
+  /// the remove-and-retry loop of solveWithRoadmap (.cpp:1977-2096) around constructSolution
+  std::vector<size_t> solveWithRoadmap(size_t start, size_t goal, size_t *iterations = nullptr) {
+    for (size_t it = 1;; it++) {
+      const size_t before = removed_count();
+      std::vector<size_t> path = constructSolution(start, goal);
+      if (iterations) *iterations = it;
+      if (!path.empty() || removed_count() == before) return path;   // solved, or A* found no path
+    }
   }
   /// environment replacement (the reference rebuilds its validators, Problem.h:175-216)
   void setEnvironment(const collision::VoxelOctree &env_voxels) {
@@ -1118,6 +1219,28 @@ public:
   const std::vector<uint32_t> &edgeFlags() const { return eflags_; }
 
 private:
+  size_t removed_count() const {
+    size_t c = 0;
+    for (char x : vertex_removed_) c += x != 0;
+    for (char x : edge_removed_) c += x != 0;
+    return c;
+  }
+  void build_adjacency() {
+    const size_t n = states_.size(), m = edges_.size();
+    if (adj_edges_ == m && adj_ptr_.size() == n + 1) return;
+    adj_ptr_.assign(n + 1, 0);
+    for (auto &e : edges_) { adj_ptr_[e.first + 1]++; adj_ptr_[e.second + 1]++; }
+    for (size_t i = 0; i < n; i++) adj_ptr_[i + 1] += adj_ptr_[i];
+    adj_nbr_.assign(2 * m, 0); adj_eid_.assign(2 * m, 0);
+    std::vector<size_t> cur(adj_ptr_.begin(), adj_ptr_.end() - 1);
+    for (size_t i = 0; i < m; i++) {
+      adj_nbr_[cur[edges_[i].first]] = edges_[i].second; adj_eid_[cur[edges_[i].first]++] = i;
+      adj_nbr_[cur[edges_[i].second]] = edges_[i].first; adj_eid_[cur[edges_[i].second]++] = i;
+    }
+    adj_edges_ = m;
+    if (vertex_removed_.size() != n) vertex_removed_.assign(n, 0);
+    if (edge_removed_.size() != m) edge_removed_.assign(m, 0);
+  }
   void clear_store(irt_setstore *st) {
     const uint64_t off = 0;
     const uint32_t key = 0;
@@ -1157,6 +1280,11 @@ private:
   std::vector<uint32_t> vflags_, eflags_;
   std::vector<double> tips_;
   std::vector<unsigned> vertex_validity_, edge_validity_;
+  bool vertex_swept_ = false, edge_swept_ = false;
+  size_t sweeps_ = 0, lookups_ = 0;
+  std::vector<char> vertex_removed_, edge_removed_;
+  std::vector<size_t> adj_ptr_, adj_nbr_, adj_eid_;
+  size_t adj_edges_ = (size_t)-1;
   Sampler sampler_;
   std::function<std::vector<size_t>(size_t)> connection_;
   std::mt19937 gen_{20220801u};

@@ -52,6 +52,8 @@ def gather_verdict_words(local_words, dist=None, group=None):
 def assemble_verdicts(all_words, n, world, align=64):
     """global bool[n] (True = collides) from the gathered words of `world` aligned shards."""
     w = shard_words(n, world, align)
+    if n == 0:
+        return np.zeros(0, dtype=bool)
     words = np.ascontiguousarray(all_words, dtype=np.uint32).reshape(world, w)
     out = np.zeros(n, dtype=bool)
     for r in range(world):
@@ -83,6 +85,13 @@ class VoxelCachedLazyPRM:
         self.range = None            # maxDistance_; None = configurePlannerRange's 20 % of the maximum extent
         self.fused_gather = True     # multi-GPU sweeps: fuse the verdict all-gather into K3 (peer memory)
         self._xchg = {}
+        self._sampler_calls = 0      # createRoadmap calls so far: every call draws from its own Philox stream
+        # lazy-path consumers (computeVertexValidity / computeEdgeValidity / constructSolution)
+        self._vertex_swept = self._edge_swept = False   # a full sweep ran since the last clearValidity
+        self.vertex_removed = np.zeros(0, dtype=bool)   # removeVertices / removeEdge of constructSolution
+        self.edge_removed = np.zeros(0, dtype=bool)
+        self._adj = None
+        self.lookups = {"vertex": 0, "edge": 0, "sweeps": 0}
 
     def _exchange(self, store, slot_words):
         """one exchange buffer per (store, slot size); creating it is collective (IPC handle all-gather)"""
@@ -97,6 +106,9 @@ class VoxelCachedLazyPRM:
         self.states = np.ascontiguousarray(states, dtype=np.float64)
         self.edges = np.ascontiguousarray(edges, dtype=np.int64).reshape(-1, 2)
         self._have_vcache = self._have_ecache = False
+        self._adj = None
+        self.vertex_removed = np.zeros(len(self.states), dtype=bool)
+        self.edge_removed = np.zeros(len(self.edges), dtype=bool)
         self.clearValidity()
 
     def distance(self, a, b):
@@ -137,7 +149,8 @@ class VoxelCachedLazyPRM:
         """TendonRobot::random_state (tendon/TendonRobot.cpp:219-247) for a batch, seeded: tensions
         U[0, max_tension], rotation U[-pi, pi], retraction U[0, L], in state order"""
         d = self.robot.spec
-        g = np.random.Generator(np.random.Philox(key=[self.seed, rnd]))
+        # one stream per (createRoadmap call, round): growing the roadmap never replays old candidates
+        g = np.random.Generator(np.random.Philox(key=[self.seed, (self._sampler_calls << 32) + rnd]))
         N = len(d["C"])
         cols = [g.uniform(0.0, d["max_tension"][j], count) for j in range(N)]
         if d.get("enable_rotation"):
@@ -168,7 +181,11 @@ class VoxelCachedLazyPRM:
         if n_vertices <= nv0:
             return self      # "Graph is already at or bigger than N, skipping roadmap creation"
         sampler = sampler or self.random_states
+        self._sampler_calls += 1
         kept, total = [], 0
+        # addMilestone's duplicate rejection (the was_added loop of createRoadmap): a candidate equal to an
+        # existing or already kept state is dropped and resampled
+        seen = set(r.tobytes() for r in np.ascontiguousarray(self.states, dtype=np.float64))
         scratch = SetStore(self.ctx, self.grid) if validate_verts else None
         for rnd in range(max_rounds):
             need = n_vertices - nv0 - total
@@ -181,7 +198,15 @@ class VoxelCachedLazyPRM:
                 ok = ((flags & INVALID_MASK) == 0) & ~scratch.check(self.env)
             elif voxelize_verts:
                 ok = (self.robot.shape_batch(cand, want=("flags",))["flags"] & INVALID_MASK) == 0
-            good = cand[ok][:need]
+            good = []
+            for r in cand[ok]:
+                key = r.tobytes()
+                if key not in seen:
+                    seen.add(key)
+                    good.append(r)
+                    if len(good) == need:
+                        break
+            good = np.asarray(good, dtype=np.float64).reshape(-1, cand.shape[1])
             kept.append(good)
             total += len(good)
         if total < n_vertices - nv0:
@@ -233,6 +258,13 @@ class VoxelCachedLazyPRM:
             self.vertex_validity[nv0:] = VALIDITY_TRUE
         if validate_edges:
             self.edge_validity[ne0:] = VALIDITY_TRUE
+        self._adj = None
+        self._vertex_swept = self._edge_swept = False
+        vr, er = self.vertex_removed, self.edge_removed
+        self.vertex_removed = np.zeros(len(self.states), dtype=bool)
+        self.vertex_removed[:min(nv0, len(vr))] = vr[:nv0]
+        self.edge_removed = np.zeros(len(self.edges), dtype=bool)
+        self.edge_removed[:min(ne0, len(er))] = er[:ne0]
         return self
 
     def shard(self, n):
@@ -287,6 +319,8 @@ class VoxelCachedLazyPRM:
     # ---- validity sweeps ------------------------------------------------------------------------
     def _sweep(self, store, n_total, flags):
         import torch
+        if n_total == 0:        # a roadmap without edges (or vertices): nothing collides
+            return np.zeros(0, dtype=bool)
         lo, hi = self.shard(n_total)
         w = shard_words(n_total, self.world)
         use_cuda = torch.cuda.is_available()
@@ -323,6 +357,8 @@ class VoxelCachedLazyPRM:
         collides = self._sweep(self.vertex_store, n, self.vertex_flags)
         invalid = self._gather_flags(self.vertex_flags, n, INVALID_MASK)
         self.vertex_validity = np.where(~collides & ~invalid, VALIDITY_TRUE, VALIDITY_UNKNOWN).astype(np.uint8)
+        self._vertex_swept = True
+        self.lookups["sweeps"] += 1
         return self.vertex_validity
 
     def precomputeEdgeValidity(self):
@@ -333,6 +369,8 @@ class VoxelCachedLazyPRM:
         collides = self._sweep(self.edge_store, n, self.edge_flags)
         invalid = self._gather_flags(self.edge_flags, n, FLAG_PARTIAL)
         self.edge_validity = np.where(~collides & ~invalid, VALIDITY_TRUE, VALIDITY_UNKNOWN).astype(np.uint8)
+        self._edge_swept = True
+        self.lookups["sweeps"] += 1
         return self.edge_validity
 
     def precomputeValidity(self):
@@ -340,12 +378,130 @@ class VoxelCachedLazyPRM:
         self.precomputeEdgeValidity()
 
     def clearValidity(self):
+        """clearValidity (VoxelCachedLazyPRM.cpp:1656-1663): every validity word back to VALIDITY_UNKNOWN"""
         self.vertex_validity = np.zeros(len(self.states), dtype=np.uint8)
         self.edge_validity = np.zeros(len(self.edges), dtype=np.uint8)
+        self._vertex_swept = self._edge_swept = False
+
+    # ---- lazy-path consumers: what the planner's query side calls (SURVEY 8(f) row 2) --------------------
+    def computeVertexValidity(self, v):
+        """computeVertexValidity (VoxelCachedLazyPRM.cpp:2607-2618).  The reference checks ONE vertex here
+        (voxelise if needed + collides); with the verdict words of a full sweep on the host this is a table
+        look-up.  The first query after clearValidity() triggers the sweep (one K3 launch over every cached
+        set + the gather), every later one only reads the table."""
+        if not self._vertex_swept:
+            self.precomputeVertexValidity()
+        self.lookups["vertex"] += 1
+        return bool(self.vertex_validity[v] & VALIDITY_TRUE)
+
+    def computeEdgeValidity(self, e):
+        """computeEdgeValidity (VoxelCachedLazyPRM.cpp:2620-2631): is_fully_valid (no IRT_FLAG_PARTIAL) and the
+        swept volume misses the environment -- a look-up into the gathered words, as above."""
+        if not self._edge_swept:
+            self.precomputeEdgeValidity()
+        self.lookups["edge"] += 1
+        return bool(self.edge_validity[e] & VALIDITY_TRUE)
+
+    def _adjacency(self):
+        """CSR adjacency (neighbour vertex, edge id) of the undirected roadmap; rebuilt when the edge list changes"""
+        if self._adj is None or self._adj[3] != len(self.edges):
+            n, m = len(self.states), len(self.edges)
+            src = np.concatenate([self.edges[:, 0], self.edges[:, 1]])
+            dst = np.concatenate([self.edges[:, 1], self.edges[:, 0]])
+            eid = np.concatenate([np.arange(m), np.arange(m)])
+            order = np.argsort(src, kind="stable")
+            ptr = np.zeros(n + 1, dtype=np.int64)
+            np.add.at(ptr, src + 1, 1)
+            self._adj = (np.cumsum(ptr), dst[order], eid[order], m)
+            if len(self.vertex_removed) != n:
+                self.vertex_removed = np.zeros(n, dtype=bool)
+            if len(self.edge_removed) != m:
+                self.edge_removed = np.zeros(m, dtype=bool)
+        return self._adj[:3]
+
+    def astarSearch(self, start, goal):
+        """astarSearch (VoxelCachedLazyPRM.cpp:2950-2976): A* over the current graph (removed vertices / edges
+        left out) with the motion cost as edge weight and as heuristic.  Host code in the reference (Boost.Graph)
+        and here; it never touches the device.  Returns the vertex list start..goal or None."""
+        import heapq
+        ptr, nbr, eid = self._adjacency()
+        if self.vertex_removed[start] or self.vertex_removed[goal]:
+            return None
+        gs = self.states[goal]
+        dist = {start: 0.0}
+        prev = {start: start}
+        done = set()
+        heap = [(float(self.distance(self.states[start], gs[None])[0]), start)]
+        while heap:
+            _, u = heapq.heappop(heap)
+            if u in done:
+                continue
+            if u == goal:
+                path = [goal]
+                while path[-1] != start:
+                    path.append(prev[path[-1]])
+                return path[::-1]
+            done.add(u)
+            lo, hi = int(ptr[u]), int(ptr[u + 1])
+            ok = ~(self.edge_removed[eid[lo:hi]] | self.vertex_removed[nbr[lo:hi]])
+            vs = nbr[lo:hi][ok]
+            if not len(vs):
+                continue
+            w = self.distance(self.states[u], self.states[vs])
+            h = self.distance(gs, self.states[vs])
+            for v, wi, hi_ in zip(vs.tolist(), w.tolist(), h.tolist()):
+                nd = dist[u] + wi
+                if v not in done and nd < dist.get(v, np.inf):
+                    dist[v] = nd
+                    prev[v] = u
+                    heapq.heappush(heap, (nd + hi_, v))
+        return None
+
+    def edge_index(self, a, b):
+        ptr, nbr, eid = self._adjacency()
+        lo, hi = int(ptr[a]), int(ptr[a + 1])
+        hit = np.nonzero(nbr[lo:hi] == b)[0]
+        return int(eid[lo + hit[0]]) if len(hit) else -1
+
+    def constructSolution(self, start, goal):
+        """constructSolution (VoxelCachedLazyPRM.cpp:2689-2771): A* path, then the lazy validity checks along it --
+        every intermediate vertex first (ALL invalid ones are removed), then the edges from the goal side (the
+        FIRST invalid one is removed).  Returns the vertex list of a fully validated path, or None when
+        something was removed (the caller searches again) or no path exists."""
+        if start == goal:
+            return [start]
+        path = self.astarSearch(start, goal)
+        if path is None:
+            return None
+        bad = [v for v in path[-2:0:-1] if not self.computeVertexValidity(v)]   # from the goal side, ends excluded
+        if bad:
+            self.vertex_removed[bad] = True          # removeVertices(milestonesToRemove)
+            return None
+        for i in range(len(path) - 1, 0, -1):        # edge (path[i-1], path[i]), goal side first
+            e = self.edge_index(path[i - 1], path[i])
+            if not self.computeEdgeValidity(e):
+                self.edge_removed[e] = True          # removeEdge(e): the first invalid edge only
+                return None
+        return path
+
+    def solveWithRoadmap(self, start, goal, max_iterations=10000):
+        """the remove-and-retry loop of solveWithRoadmap (VoxelCachedLazyPRM.cpp:1977-2096) around
+        constructSolution: search again while something was removed and the two ends stay connected.
+        Returns (path or None, number of constructSolution calls)."""
+        for it in range(1, max_iterations + 1):
+            nv, ne = int(self.vertex_removed.sum()), int(self.edge_removed.sum())
+            path = self.constructSolution(start, goal)
+            if path is not None:
+                return path, it
+            if nv == int(self.vertex_removed.sum()) and ne == int(self.edge_removed.sum()):
+                return None, it                       # nothing removed: A* found no path
+        return None, max_iterations
 
     def _gather_flags(self, local_flags, n_total, mask):
         """validity flags of all shards as a global bool array (1 bit per item on the wire)."""
         import torch
+        if n_total == 0:
+            return np.zeros(0, dtype=bool)
         lo, hi = self.shard(n_total)
         w = shard_words(n_total, self.world)
         bits = np.zeros(w * 32, dtype=np.uint8)

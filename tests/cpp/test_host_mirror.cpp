@@ -359,6 +359,36 @@ int main() {
     orc_octree_free(ov);
   }
   std::printf("roadmap: %d/%zu edges valid\n", valid_edges, edges.size());
+  {  // lazy-path consumers (VoxelCachedLazyPRM.cpp:2607-2631, 2689-2771): look-ups into the swept table
+    const std::vector<unsigned> vt = prm.vertexValidity(), et = prm.edgeValidity();   // checked against the oracle above
+    const size_t sweeps0 = prm.sweepCount();
+    int solved = 0, blocked_n = 0;
+    for (size_t a = 0; a + 8 < verts.size(); a += 8) {
+      size_t it = 0;
+      auto path = prm.solveWithRoadmap(a, a + 8, &it);
+      if (!path.empty()) {
+        solved++;
+        CHECK(path.front() == a && path.back() == a + 8);
+        for (size_t k = 1; k + 1 < path.size(); k++) CHECK(vt[path[k]] == 1u);
+        for (size_t k = 0; k + 1 < path.size(); k++) {
+          const long e = prm.edgeIndex(path[k], path[k + 1]);
+          CHECK(e >= 0 && et[(size_t)e] == 1u);
+        }
+      } else {  // a chain graph: no path <=> an intermediate vertex or an edge of the chain is invalid
+        bool blocked = false;
+        for (size_t k = a; k < a + 8; k++) blocked = blocked || et[k] != 1u || (k > a && vt[k] != 1u);
+        CHECK(blocked);
+        blocked_n++;
+      }
+    }
+    CHECK(prm.sweepCount() == sweeps0 && prm.lookupCount() > 0);   // however many look-ups: no further sweep
+    for (size_t i = 0; i < verts.size(); i++) if (prm.removedVertices()[i]) CHECK(vt[i] != 1u);
+    for (size_t i = 0; i < edges.size(); i++) if (prm.removedEdges()[i]) CHECK(et[i] != 1u);
+    CHECK(prm.computeVertexValidity(3) == (vt[3] == 1u) && prm.computeEdgeValidity(5) == (et[5] == 1u));
+    std::printf("lazy consumers: %d paths validated, %d blocked, %zu look-ups, %zu sweeps\n", solved, blocked_n,
+                prm.lookupCount(), prm.sweepCount());
+    prm.restoreRemoved();
+  }
   prm.clearValidity();
   for (auto v : prm.edgeValidity()) CHECK(v == 0);
   // environment swap: empty environment -> everything with a valid shape becomes valid

@@ -921,3 +921,96 @@ def test_env_voxelize_lung_capsules_and_dilate(irt, ctx, orc, wl):
         assert np.array_equal(env.download(), want.dense_morton())
     with pytest.raises(irt.IrtError):
         irt.Env(ctx, grid).add_primitives(capsules=caps, dilate=-1.0)
+
+
+def test_fused_verdict_exchange_single_rank_and_empty_shard(irt, ctx, orc, wl):
+    """The verdict all-gather fused into K3 (voxel_and_popc_kernel<..., GATHER> + its last-CTA flag wait, and
+    xchg_empty_shard_kernel), exercised on ONE GPU as a self-exchange (world = 1: the rank's own buffer is the
+    only peer): the gathered words equal irt_check_sets' on full ranges, sub-ranges, ranges that end inside a
+    verdict word, an empty shard, and over several sweeps (the two alternating buffers and the epoch flags)."""
+    import torch
+    spec = wl.robot_b(0.003)
+    g = wl.workspace_grid(spec)
+    grid = irt.make_grid(g["Ng"], g["lim"], g["inv_rot"])
+    rb = irt.Robot(ctx, spec)
+    states = wl.sample_states(spec, 5000, stream=41)
+    store = irt.SetStore(ctx, grid)
+    store.voxelize_vertices(rb, states)
+    env = irt.Env(ctx, grid)
+    env_blocks = wl.dense_to_morton_blocks(wl.lung_like_env_dense(spec, g))
+    env.update(env_blocks)
+    n = store.num_sets
+    want = store.check(env)
+    assert 0.05 < want.mean() < 0.95
+    slot = (n + 63) // 64 * 2
+    x = irt.VerdictExchange(ctx, 0, 1, slot)
+    for sweep, (b, e) in enumerate([(0, n), (0, n), (0, 1000), (64, 64 + 777), (0, 0), (128, 128), (0, n), (4992, n)]):
+        words = x.check(store, env, b, e).cpu().numpy().view(np.uint32)
+        ctx.synchronize()
+        assert len(words) == slot and x.status() == 0
+        got = irt.unpack_verdicts(words, e - b) if e > b else np.zeros(0, dtype=bool)
+        assert np.array_equal(got, want[b:e]), "sweep %d [%d, %d)" % (sweep, b, e)
+        assert not words[(e - b + 31) // 32:].any(), "padding words of the slot must read 'no collision'"
+    # a changed environment between sweeps (the replanning tick): the next gathered table follows it
+    env.update(np.zeros_like(env_blocks))
+    assert not irt.unpack_verdicts(x.check(store, env, 0, n).cpu().numpy().view(np.uint32), n).any()
+    # an empty STORE is an empty shard too
+    empty = irt.SetStore(ctx, grid)
+    x2 = irt.VerdictExchange(ctx, 0, 1, 4)
+    assert not x2.check(empty, env, 0, 0).cpu().numpy().any() and x2.status() == 0
+
+
+def test_pinned_staging_survives_io_growth(irt, ctx, wl):
+    """packed(small) -> dense(large) -> packed(small) on ONE context.  Growing the device
+    staging buffer used to free the pinned row-offset buffer and leave the dangling pointer in the context."""
+    spec = wl.robot_b(0.005)
+    rb = irt.Robot(ctx, spec)
+    small = wl.sample_states(spec, 300, stream=51)
+    big = wl.sample_states(spec, 300_000, stream=52)
+    a = rb.shape_batch_packed(small, want=("p", "npts", "flags"))
+    dense = rb.shape_batch(big, want=("p", "npts", "L_i", "flags"))
+    b = rb.shape_batch_packed(small, want=("p", "npts", "flags"))
+    assert np.array_equal(a["row_offsets"], b["row_offsets"]) and np.array_equal(a["p"], b["p"])
+    assert np.array_equal(a["npts"], b["npts"]) and int(a["row_offsets"][-1]) == int(a["npts"].sum())
+    assert dense["npts"].shape == (300_000,)
+
+
+def test_lazy_path_consumers_on_device_tables(irt, ctx, orc, wl):
+    """SURVEY 8(f) row 2 on the real library: constructSolution / solveWithRoadmap validate A* paths by look-ups
+    into the verdict words of ONE vertex sweep and ONE edge sweep (D2H included); paths are valid by the oracle's
+    per-item checks, removed items are invalid ones (collisions and IRT_FLAG_PARTIAL edges)."""
+    from irt_b200 import roadmap as R
+    spec = wl.robot_b(0.003)
+    g = wl.workspace_grid(spec)
+    grid = irt.make_grid(g["Ng"], g["lim"], g["inv_rot"])
+    rb = irt.Robot(ctx, spec)
+    prm = R.VoxelCachedLazyPRM(ctx, rb, grid)
+    n = 400
+    prm.createRoadmap(n, lambda cnt, rnd: wl.sample_states(spec, cnt, stream=700 + rnd),
+                      lambda st: wl.knn_edges(spec, st, k=6), opt=R.VoxelizeVertices)
+    prm.precomputeEdgeVoxelCache()
+    ogrid, osp = orc.grid(g["Ng"], g["lim"]), orc.space()
+    oenv = orc.octree(ogrid)
+    oenv.add_sphere([0.04, 0.0, 0.13], 0.035)
+    oenv.add_sphere([-0.05, 0.03, 0.10], 0.03)
+    env = irt.Env(ctx, grid)
+    env.add_primitives(spheres=[[0.04, 0.0, 0.13, 0.035], [-0.05, 0.03, 0.10, 0.03]], clear=True)
+    prm.setEnvironment(env.download())
+    orb = orc.robot(spec)
+    vs, vf = orc.voxelize_vertices_batch(orb, ogrid, prm.states)
+    v_ok = (vf == 0) & ~orc.check_sets_batch(vs, oenv).astype(bool)
+    es, einfo = orc.voxelize_edges_batch(orb, ogrid, osp, prm.states[prm.edges[:, 0]], prm.states[prm.edges[:, 1]])
+    e_ok = ((einfo["flags"] & 16) == 0) & ~orc.check_sets_batch(es, oenv).astype(bool)
+    rng = np.random.default_rng(5)
+    solved = 0
+    for _ in range(10):
+        a, b = (int(x) for x in rng.choice(np.nonzero(v_ok)[0], 2, replace=False))
+        path, _ = prm.solveWithRoadmap(a, b)
+        if path is None:
+            continue
+        solved += 1
+        assert path[0] == a and path[-1] == b and all(v_ok[v] for v in path[1:-1])
+        assert all(e_ok[prm.edge_index(u, v)] for u, v in zip(path[:-1], path[1:]))
+    assert solved >= 5 and prm.lookups["sweeps"] == 2
+    assert np.array_equal(prm.vertex_validity.astype(bool), v_ok) and np.array_equal(prm.edge_validity.astype(bool), e_ok)
+    assert not v_ok[prm.vertex_removed].any() and not e_ok[prm.edge_removed].any()

@@ -132,6 +132,104 @@ def test_create_roadmap_options_host_logic(orc, wl, monkeypatch):
     # every new edge has a new vertex as its source and none is a duplicate
     new = prm.edges[len(edges0):]
     assert np.all(new[:, 0] >= n) and len(set(map(tuple, np.sort(prm.edges, axis=1).tolist()))) == len(prm.edges)
+    # growing by EQUAL increments never replays the candidate stream: all states stay distinct
+    prm.createRoadmap(n + 80, opt=R.LazyRoadmap)
+    assert len(prm.states) == n + 80
+    assert len(set(r.tobytes() for r in prm.states)) == len(prm.states), "duplicate vertices after growth"
+    assert len(prm.edges) and not np.any(prm.edges[:, 0] == prm.edges[:, 1])
+
+
+def _shortest_valid_path_cost(prm, start, goal, v_ok, e_ok):
+    """Dijkstra over the sub-graph of valid vertices / edges (start and goal always kept); inf if unreachable"""
+    import heapq
+    n = len(prm.states)
+    adj = [[] for _ in range(n)]
+    for e, (a, b) in enumerate(prm.edges.tolist()):
+        if e_ok[e] and (v_ok[a] or a in (start, goal)) and (v_ok[b] or b in (start, goal)):
+            w = float(prm.distance(prm.states[a], prm.states[b][None])[0])
+            adj[a].append((b, w))
+            adj[b].append((a, w))
+    dist = {start: 0.0}
+    heap = [(0.0, start)]
+    while heap:
+        d, u = heapq.heappop(heap)
+        if u == goal:
+            return d
+        if d > dist.get(u, np.inf):
+            continue
+        for v, w in adj[u]:
+            if d + w < dist.get(v, np.inf):
+                dist[v] = d + w
+                heapq.heappush(heap, (d + w, v))
+    return np.inf
+
+
+def test_lazy_path_consumers_are_lookups(orc, wl, monkeypatch):
+    """computeVertexValidity / computeEdgeValidity / constructSolution / the remove-and-retry
+    loop (VoxelCachedLazyPRM.cpp:2607-2631, 2689-2771, 1977-2096) over the verdict table of ONE sweep per kind:
+    the paths returned are fully valid by the oracle's per-item checks and as short as the shortest path of
+    the valid sub-graph, invalid vertices / edges (collisions and IRT_FLAG_PARTIAL) met on the way are removed,
+    and however many look-ups the search makes, only two sweeps run until clearValidity()."""
+    from irt_b200 import roadmap as R
+    spec = wl.robot_b(0.003)
+    g = wl.workspace_grid(spec)
+    ogrid, osp = orc.grid(g["Ng"], g["lim"]), orc.space()
+    oenv = orc.octree(ogrid)
+    oenv.add_sphere([0.04, 0.0, 0.13], 0.035)
+    oenv.add_sphere([-0.05, 0.03, 0.10], 0.03)
+    prm = _prm(R, orc, wl, spec, g, oenv, monkeypatch)
+    n = 160
+    prm.createRoadmap(n, lambda cnt, rnd: wl.sample_states(spec, cnt, stream=700 + rnd),
+                      lambda st: wl.knn_edges(spec, st, k=6), opt=R.VoxelizeVertices)
+    prm.precomputeEdgeVoxelCache()
+    # per-item truth from the oracle
+    vs, vf = orc.voxelize_vertices_batch(prm.robot.orb, ogrid, prm.states)
+    v_ok = (vf == 0) & ~orc.check_sets_batch(vs, oenv).astype(bool)
+    es, einfo = orc.voxelize_edges_batch(prm.robot.orb, ogrid, osp, prm.states[prm.edges[:, 0]], prm.states[prm.edges[:, 1]])
+    e_ok = ((einfo["flags"] & 16) == 0) & ~orc.check_sets_batch(es, oenv).astype(bool)
+    assert 0.05 < 1 - v_ok.mean() and 0.05 < 1 - e_ok.mean(), "fixture needs invalid vertices and edges"
+    rng = np.random.default_rng(5)
+    solved = unsolved = 0
+    for _ in range(12):
+        a, b = (int(x) for x in rng.choice(np.nonzero(v_ok)[0], 2, replace=False))
+        path, iters = prm.solveWithRoadmap(a, b)
+        want = _shortest_valid_path_cost(prm, a, b, v_ok, e_ok)
+        if path is None:
+            assert not np.isfinite(want)
+            unsolved += 1
+            continue
+        solved += 1
+        assert path[0] == a and path[-1] == b and all(v_ok[v] for v in path[1:-1])
+        eids = [prm.edge_index(u, v) for u, v in zip(path[:-1], path[1:])]
+        assert all(e >= 0 and e_ok[e] for e in eids)
+        cost = sum(float(prm.distance(prm.states[u], prm.states[v][None])[0]) for u, v in zip(path[:-1], path[1:]))
+        assert abs(cost - want) <= 1e-9 * max(1.0, want)
+    assert solved >= 6
+    assert prm.lookups["sweeps"] == 2 and prm.lookups["vertex"] + prm.lookups["edge"] > 20
+    # everything that was removed was invalid; single-item queries agree with the oracle
+    assert not v_ok[prm.vertex_removed].any() and not e_ok[prm.edge_removed].any()
+    assert prm.vertex_removed.any() or prm.edge_removed.any()
+    assert all(prm.computeVertexValidity(v) == bool(v_ok[v]) for v in range(0, n, 7))
+    assert all(prm.computeEdgeValidity(e) == bool(e_ok[e]) for e in range(0, len(prm.edges), 11))
+    # clearValidity: the next query sweeps again (a changed environment answers differently)
+    prm.env.oenv = orc.octree(ogrid)
+    prm.clearValidity()
+    assert prm.computeVertexValidity(int(np.nonzero(~v_ok & (vf == 0))[0][0]))
+    assert prm.lookups["sweeps"] == 3
+
+
+def test_sweeps_on_edgeless_roadmap(orc, wl, monkeypatch):
+    """precompute*Validity on a roadmap without edges / vertices returns empty arrays (the 1-word
+    device buffer used to be reshaped to (world, 0))"""
+    from irt_b200 import roadmap as R
+    spec = wl.robot_a(0.003)
+    g = wl.workspace_grid(spec)
+    oenv = orc.octree(orc.grid(g["Ng"], g["lim"]))
+    prm = R.VoxelCachedLazyPRM.__new__(R.VoxelCachedLazyPRM)
+    prm.rank, prm.world, prm.dist, prm.ctx = 0, 1, None, _Ctx()
+    assert R.VoxelCachedLazyPRM._sweep(prm, None, 0, None).shape == (0,)
+    assert R.VoxelCachedLazyPRM._gather_flags(prm, np.zeros(0, np.uint32), 0, 1).shape == (0,)
+    assert R.assemble_verdicts(np.zeros(0, np.uint32), 0, 2).shape == (0,)
 
 
 def test_create_roadmap_lazy_and_custom_callbacks(orc, wl, monkeypatch):

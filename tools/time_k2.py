@@ -10,7 +10,8 @@ g = wl.workspace_grid(spec)
 grid = irt_b200.make_grid(g["Ng"], g["lim"])
 nv = int(sys.argv[1]) if len(sys.argv) > 1 else 100000
 st = wl.sample_states(spec, nv, stream=200)
-pairs = knn_edges_gpu(torch, st, spec, 10, torch.device("cuda"))
+k = int(sys.argv[2]) if len(sys.argv) > 2 and sys.argv[2].isdigit() else 10
+pairs = knn_edges_gpu(torch, st, spec, k, torch.device("cuda"))
 store = irt_b200.SetStore(ctx, grid)
 for rep in range(2):
     t0 = time.perf_counter()
