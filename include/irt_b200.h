@@ -187,6 +187,11 @@ int irt_fk_tip_jacobian_batch(irt_ctx *ctx, const irt_robot *rb, const double *s
 int irt_fk_tip_jacobian_batch_dev(irt_ctx *ctx, const irt_robot *rb, const double *d_states,
                                   int state_size, int64_t n, int mode, double delta, double *d_tips,
                                   double *d_J, void *stream);
+/* collision::collides_self(CapsuleSequence{points, r}) (collision/collision.cpp:6-46) = TendonRobot::collides_self
+ * (tendon/TendonRobot.cpp:955-974) for n given backbones: p[n][cap_pts][3], npts[n] (host); collides[i] = 0 / 1.
+ * The validity epilogue of irt_fk_batch runs the same kernels on the shapes it has just computed. */
+int irt_self_collision_shapes(irt_ctx *ctx, const double *p, const int32_t *npts, int cap_pts, int64_t n,
+                              double r, uint8_t *collides);
 /* TendonRobot::home_shape(state).L_i (tendon/TendonRobot.cpp:249-314), host arrays */
 int irt_home_lengths_batch(irt_ctx *ctx, const irt_robot *rb, const double *states,
                            int state_size, int64_t n, double *L_i);

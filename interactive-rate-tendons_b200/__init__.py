@@ -94,7 +94,7 @@ ABI_SYMBOLS = [
     "irt_abi_version", "irt_status_string", "irt_ctx_create", "irt_ctx_destroy", "irt_last_error",
     "irt_ctx_device", "irt_ctx_synchronize", "irt_ctx_launch_count", "irt_measure_fp64_peak",
     "irt_robot_create", "irt_robot_destroy", "irt_robot_state_size", "irt_robot_max_points",
-    "irt_fk_batch", "irt_fk_batch_dev", "irt_fk_batch_packed", "irt_home_lengths_batch",
+    "irt_fk_batch", "irt_fk_batch_dev", "irt_fk_batch_packed", "irt_home_lengths_batch", "irt_self_collision_shapes",
     "irt_fk_tip_jacobian_batch", "irt_fk_tip_jacobian_batch_dev",
     "irt_env_create", "irt_env_destroy", "irt_env_update", "irt_env_update_dev",
     "irt_env_update_sparse", "irt_env_nblocks",
@@ -144,6 +144,7 @@ def lib():
         "irt_fk_batch_dev": (i32, [vp, vp, vp, i32, i64, i32, C.POINTER(FkOutputs), vp]),
         "irt_fk_batch_packed": (i32, [vp, vp, vp, i32, i64, C.POINTER(FkOutputs), i64, vp]),
         "irt_home_lengths_batch": (i32, [vp, vp, vp, i32, i64, vp]),
+        "irt_self_collision_shapes": (i32, [vp, vp, vp, i32, i64, C.c_double, vp]),
         "irt_fk_tip_jacobian_batch": (i32, [vp, vp, vp, i32, i64, i32, C.c_double, vp, vp]),
         "irt_fk_tip_jacobian_batch_dev": (i32, [vp, vp, vp, i32, i64, i32, C.c_double, vp, vp, vp]),
         "irt_env_create": (i32, [vp, C.POINTER(Grid), C.POINTER(vp)]),
@@ -288,6 +289,15 @@ class Context:
         v = C.c_double()
         self.check(self.L.irt_measure_fp64_peak(self.h, C.byref(v)))
         return v.value
+
+
+def self_collision_shapes(ctx, p, npts, r):
+    """collides_self(CapsuleSequence{points, r}) (collision/collision.cpp:6-46) for backbones p[n][cap][3], npts[n]"""
+    p, npts = _np(p, np.float64), _np(npts, np.int32)
+    n, cap = p.shape[0], p.shape[1]
+    out = np.zeros(n, dtype=np.uint8)
+    ctx.check(ctx.L.irt_self_collision_shapes(ctx.h, _ptr(p), _ptr(npts), cap, n, float(r), _ptr(out)))
+    return out.astype(bool)
 
 
 class Robot:

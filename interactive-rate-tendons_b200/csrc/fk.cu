@@ -758,29 +758,30 @@ __global__ void FK_KERNEL_BOUNDS fk_rk4_fp64_kernel(const RobotDev rb, const FkA
 #pragma unroll 1
     for (int j = 0; j < Tmax; j++) {
       const int q = Tmax - j;  // regular step q: node q -> node q-1 (1 <= q <= K-1)
-      if (!integ || q > K - 1 + nhead) continue;
-      const double *p0, *p1, *p2;
-      double h;
-      int emit_idx;
-      if (q <= K - 1) {
-        p0 = tab + (size_t)(2 * q) * NT * 6;
-        p1 = p0 - NT * 6;
-        p2 = p0 - 2 * NT * 6;
-        h = rb.dL;
-        emit_idx = K - q + 1;
-      } else if (q == K) {  // the head step that lands on node K-1
-        p0 = (nhead == 2) ? hd2 : hd0;
-        p1 = (nhead == 2) ? hd3 : hd1;
-        p2 = tab + (size_t)(2 * (K - 1)) * NT * 6;
-        h = (nhead == 2) ? hh1 : hh0;
-        emit_idx = 1;
-      } else {  // q == K + 1: first of two head steps, lands between grid points (not observed)
-        p0 = hd0; p1 = hd1; p2 = hd2;
-        h = hh0;
-        emit_idx = -1;
+      if (integ && q <= K - 1 + nhead) {
+        const double *p0, *p1, *p2;
+        double h;
+        int emit_idx;
+        if (q <= K - 1) {
+          p0 = tab + (size_t)(2 * q) * NT * 6;
+          p1 = p0 - NT * 6;
+          p2 = p0 - 2 * NT * 6;
+          h = rb.dL;
+          emit_idx = K - q + 1;
+        } else if (q == K) {  // the head step that lands on node K-1
+          p0 = (nhead == 2) ? hd2 : hd0;
+          p1 = (nhead == 2) ? hd3 : hd1;
+          p2 = tab + (size_t)(2 * (K - 1)) * NT * 6;
+          h = (nhead == 2) ? hh1 : hh0;
+          emit_idx = 1;
+        } else {  // q == K + 1: first of two head steps, lands between grid points (not observed)
+          p0 = hd0; p1 = hd1; p2 = hd2;
+          h = hh0;
+          emit_idx = -1;
+        }
+        rk4_step<NT>(x, tau, Kse, Kbt, h, p0, p1, p2);
+        if (emit_idx >= 0) emit_node<NT, SM>(o, row_base, emit_idx, rb.node_t[K - emit_idx], x, rz);
       }
-      rk4_step<NT>(x, tau, Kse, Kbt, h, p0, p1, p2);
-      if (emit_idx >= 0) emit_node<NT, SM>(o, row_base, emit_idx, rb.node_t[K - emit_idx], x, rz);
     }
   }
 

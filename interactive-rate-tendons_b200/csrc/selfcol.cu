@@ -1,4 +1,7 @@
 // selfcol.cu -- validity epilogue of K1: collision::collides_self(CapsuleSequence)
+// (compiled with -fmad=false: the exact stage repeats the reference's operations one by one, and a contracted
+// multiply-add moves a capsule distance by an ulp -- enough to flip a pair that sits exactly at 2r; the FP32
+// filter spells its fused operations out)
 // (collision/collision.cpp:6-46) with closest_st_segment (collision_primitives.cpp:10-102)
 // and the capsule/sphere tests of collision.hxx:65-68,102-108.
 //
@@ -109,7 +112,7 @@ self_collision_filter_kernel(const double *__restrict__ p, const int32_t *__rest
     if (N <= 3) continue;  // collision.cpp:14 and the loop bounds a < N-3
     const double *src = p + (row_off ? row_off[shape] : shape * (int64_t)cap_pts) * 3;   // packed or dense rows
     const int ncap = N - 1;
-    float maxhl = 0.0f;
+    float maxhl = 0.0f, tsum = 0.0f, tmax = 0.0f;
     for (int i = gl; i < ncap; i += LPS) {
       const double ax = src[3 * i], ay = src[3 * i + 1], az = src[3 * i + 2];
       const double bx = src[3 * i + 3], by = src[3 * i + 4], bz = src[3 * i + 5];
@@ -117,9 +120,26 @@ self_collision_filter_kernel(const double *__restrict__ p, const int32_t *__rest
       const float hl = 0.5f * sqrtf(dx * dx + dy * dy + dz * dz) * 1.00001f + 1e-9f;
       seg[i] = make_float4((float)(0.5 * (ax + bx)), (float)(0.5 * (ay + by)), (float)(0.5 * (az + bz)), hl);
       maxhl = fmaxf(maxhl, hl);
+      if (i + 1 < ncap) {   // turning angle between capsule i and capsule i + 1 (over-estimated)
+        const float ex = (float)(src[3 * i + 6] - bx), ey = (float)(src[3 * i + 7] - by), ez = (float)(src[3 * i + 8] - bz);
+        const float cx = dy * ez - dz * ey, cy = dz * ex - dx * ez, cz = dx * ey - dy * ex;
+        const float th = atan2f(sqrtf(cx * cx + cy * cy + cz * cz), dx * ex + dy * ey + dz * ez) * 1.001f + 1e-6f;
+        tsum += th;
+        tmax = fmaxf(tmax, th);
+      }
     }
-    for (int o = LPS / 2; o > 0; o >>= 1) maxhl = fmaxf(maxhl, __shfl_xor_sync(gmask, maxhl, o));
+    for (int o = LPS / 2; o > 0; o >>= 1) {
+      maxhl = fmaxf(maxhl, __shfl_xor_sync(gmask, maxhl, o));
+      tsum += __shfl_xor_sync(gmask, tsum, o);
+      tmax = fmaxf(tmax, __shfl_xor_sync(gmask, tmax, o));
+    }
     __syncwarp(gmask);
+    // A backbone that turns too little cannot touch itself: between any two points x, y on capsules a < b every
+    // segment direction lies within phi = turning(a..b) / 2 + (largest single turn) of one of them (the one where
+    // the running turn passes half), so |x - y| >= (arc length between them) * cos(phi); pairs the reference does
+    // not skip have arc length >= 3r (collision.cpp:37-39), and a collision needs |x - y| <= 2r: impossible while
+    // cos(phi) > 2/3.  tsum over-estimates every turning(a..b).
+    if (0.5f * tsum + tmax < 0.83f) continue;   // acos(2/3) = 0.8411
     // smallest index gap b - a - 1 that can reach 3r of arc length (maxhl over-estimates len/2)
     const float safe = (float)(3.0 * r) * 0.9999f;
     const int min_gap = (maxhl > 0.0f) ? (int)fminf(1e6f, floorf(safe / (2.0f * maxhl))) : 1000000;
@@ -136,7 +156,7 @@ self_collision_filter_kernel(const double *__restrict__ p, const int32_t *__rest
           const float4 sb = seg[b];
           const float dx = sa.x - sb.x, dy = sa.y - sb.y, dz = sa.z - sb.z;
           const float reach = rr + sa.w + sb.w;
-          if (dx * dx + dy * dy + dz * dz <= reach * reach) found = true;
+          if (fmaf(dx, dx, fmaf(dy, dy, dz * dz)) <= reach * reach) found = true;
         }
       }
     }
@@ -263,9 +283,21 @@ self_collision_kernel(const double *__restrict__ p, const int32_t *__restrict__ 
 
 size_t selfcol_work_bytes(int64_t n) { return 256 + (((size_t)n * 4 + 255) & ~(size_t)255); }
 
+static int selfcol_run(irt_ctx *ctx, double radius, size_t scratch_offset, const double *d_p,
+                       const int32_t *d_npts, int64_t n, int cap_pts, uint32_t *d_flags,
+                       cudaStream_t st, const int64_t *d_row_off, const int32_t *d_range, void *work);
+
 int self_collision_launch(irt_ctx *ctx, const irt_robot *rb, const double *d_p,
                           const int32_t *d_npts, int64_t n, int cap_pts, uint32_t *d_flags,
                           cudaStream_t st, const int64_t *d_row_off, const int32_t *d_range, void *work) {
+  // without private scratch: behind the bucket permutation area of the context scratch
+  return selfcol_run(ctx, rb->dev.r, work ? 0 : fk_work_bytes(rb, n), d_p, d_npts, n, cap_pts, d_flags, st, d_row_off,
+                     d_range, work);
+}
+
+static int selfcol_run(irt_ctx *ctx, double radius, size_t scratch_offset, const double *d_p,
+                       const int32_t *d_npts, int64_t n, int cap_pts, uint32_t *d_flags,
+                       cudaStream_t st, const int64_t *d_row_off, const int32_t *d_range, void *work) {
   if (n <= 0) return IRT_OK;
   if (n > 0x7fffffffLL) return irt_fail(ctx, IRT_ERR_INVALID_ARGUMENT, "batch too large");
   if (cap_pts > IRT_CAP_PTS_MAX) return irt_fail(ctx, IRT_ERR_CAPACITY, "cap_pts=%d too large", cap_pts);
@@ -275,11 +307,10 @@ int self_collision_launch(irt_ctx *ctx, const irt_robot *rb, const double *d_p,
   IRT_CUDA(ctx, cudaFuncSetAttribute(self_collision_kernel,
                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   char *scr = (char *)work;
-  if (!scr) {   // behind the bucket permutation area of the context scratch
-    const size_t fk_bytes = fk_work_bytes(rb, n);
-    scr = (char *)ctx_scratch(ctx, fk_bytes + selfcol_work_bytes(n));
+  if (!scr) {
+    scr = (char *)ctx_scratch(ctx, scratch_offset + selfcol_work_bytes(n));
     if (!scr) return irt_fail(ctx, IRT_ERR_CUDA, "scratch alloc failed");
-    scr += fk_bytes;
+    scr += scratch_offset;
   }
   int32_t *d_ncand = (int32_t *)scr;
   int32_t *d_cand = (int32_t *)(scr + 256);
@@ -295,7 +326,7 @@ int self_collision_launch(irt_ctx *ctx, const irt_robot *rb, const double *d_p,
     auto kf = half ? self_collision_filter_kernel<16> : self_collision_filter_kernel<32>;
     if (fsmem > 48 * 1024)
       IRT_CUDA(ctx, cudaFuncSetAttribute(kf, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem));
-    kf<<<(unsigned)fb, SC_FILTER_WARPS * 32, fsmem, st>>>(d_p, d_npts, n, d_range, cap_pts, rb->dev.r, d_cand,
+    kf<<<(unsigned)fb, SC_FILTER_WARPS * 32, fsmem, st>>>(d_p, d_npts, n, d_range, cap_pts, radius, d_cand,
                                                           d_ncand, d_row_off);
   }
   IRT_LAUNCHED(ctx);
@@ -303,9 +334,39 @@ int self_collision_launch(irt_ctx *ctx, const irt_robot *rb, const double *d_p,
   int64_t blocks = (n + SC_WARPS - 1) / SC_WARPS;
   const int64_t max_blocks = (int64_t)ctx->sm_count * 4;
   if (blocks > max_blocks) blocks = max_blocks;
-  self_collision_kernel<<<(unsigned)blocks, SC_WARPS * 32, smem, st>>>(d_p, d_npts, n, d_range, cap_pts, rb->dev.r,
+  self_collision_kernel<<<(unsigned)blocks, SC_WARPS * 32, smem, st>>>(d_p, d_npts, n, d_range, cap_pts, radius,
                                                                       d_flags, d_cand, d_ncand, d_row_off);
   IRT_LAUNCHED(ctx);
   IRT_CUDA(ctx, cudaGetLastError());
+  return IRT_OK;
+}
+
+// collision::collides_self(CapsuleSequence{points, r}) (collision/collision.cpp:6-46; TendonRobot::collides_self,
+// tendon/TendonRobot.cpp:955-974) for n given backbones: p[n][cap_pts][3], npts[n] (host); collides[i] = 0 / 1
+extern "C" int irt_self_collision_shapes(irt_ctx *ctx, const double *p, const int32_t *npts, int cap_pts, int64_t n,
+                                         double r, uint8_t *collides) {
+  if (!ctx || n < 0 || cap_pts < 1 || (n > 0 && (!p || !npts || !collides))) return IRT_ERR_INVALID_ARGUMENT;
+  if (!(r >= 0.0)) return irt_fail(ctx, IRT_ERR_INVALID_ARGUMENT, "negative radius");
+  for (int64_t i = 0; i < n; i++)
+    if (npts[i] < 0 || npts[i] > cap_pts)
+      return irt_fail(ctx, IRT_ERR_INVALID_ARGUMENT, "npts[%lld] out of range", (long long)i);
+  if (n == 0) return IRT_OK;
+  IRT_CUDA(ctx, cudaSetDevice(ctx->device));
+  cudaStream_t st = ctx->stream;
+  const size_t b_p = ((size_t)n * cap_pts * 24 + 255) & ~(size_t)255, b_n = ((size_t)n * 4 + 255) & ~(size_t)255;
+  char *io = (char *)ctx_io(ctx, b_p + 2 * b_n);
+  if (!io) return irt_fail(ctx, IRT_ERR_CUDA, "device staging allocation failed");
+  double *d_p = (double *)io;
+  int32_t *d_npts = (int32_t *)(io + b_p);
+  uint32_t *d_flags = (uint32_t *)(io + b_p + b_n);
+  IRT_CUDA(ctx, cudaMemcpyAsync(d_p, p, (size_t)n * cap_pts * 24, cudaMemcpyHostToDevice, st));
+  IRT_CUDA(ctx, cudaMemcpyAsync(d_npts, npts, (size_t)n * 4, cudaMemcpyHostToDevice, st));
+  IRT_CUDA(ctx, cudaMemsetAsync(d_flags, 0, (size_t)n * 4, st));
+  int rc = selfcol_run(ctx, r, 0, d_p, d_npts, n, cap_pts, d_flags, st, nullptr, nullptr, nullptr);
+  if (rc) return rc;
+  std::vector<uint32_t> h((size_t)n);
+  IRT_CUDA(ctx, cudaMemcpyAsync(h.data(), d_flags, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
+  IRT_CUDA(ctx, cudaStreamSynchronize(st));
+  for (int64_t i = 0; i < n; i++) collides[i] = (h[(size_t)i] & IRT_FLAG_SELF_COLLISION) ? 1 : 0;
   return IRT_OK;
 }

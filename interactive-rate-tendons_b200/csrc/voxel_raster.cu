@@ -26,6 +26,7 @@
 #include <vector>
 
 #include <chrono>
+#include <thread>
 
 #include "common.cuh"
 
@@ -108,7 +109,10 @@ __device__ __forceinline__ void hash_insert(const WarpHash &h, uint32_t key, uns
       if (idx >= (H >> 2) * 3) *h.overflow = 1u;  // keep the load factor below 3/4
     }
     if (old == RS_EMPTY || old == key) {
-      atomicOr(&h.bits[slot], mask);
+      // bits are only ever OR-ed: two native 32-bit shared-memory ORs instead of a 64-bit CAS loop
+      uint32_t *w = reinterpret_cast<uint32_t *>(&h.bits[slot]);
+      if ((uint32_t)mask) atomicOr(w, (uint32_t)mask);
+      if ((uint32_t)(mask >> 32)) atomicOr(w + 1, (uint32_t)(mask >> 32));
       return;
     }
     slot = (slot + 1) & (H - 1);
@@ -145,6 +149,60 @@ struct HashSink {
   __device__ __forceinline__ void cell(int ix, int iy, int iz) { set_cell(h, acc, ix, iy, iz); }
   __device__ __forceinline__ void finish() { flush_block(h, acc); }
 };
+// Collects the {block key, bit mask} pairs of ONE segment in registers (a backbone segment is shorter than a
+// voxel: it touches one or two 4x4x4 blocks, three at a corner).  The warp then inserts the pairs of its 32
+// segments together (warp_insert_pairs): consecutive segments of a backbone mostly fall into the same block, so
+// lanes with equal keys merge their masks with a shuffle reduction and ONE lane per distinct key touches the
+// hash -- instead of 4-8 lanes contending for the same shared-memory word with atomicCAS / atomicOr.
+constexpr int RS_PAIRS = 3;
+struct PairSink {
+  const WarpHash &h;
+  BlockAcc acc;
+  uint32_t key[RS_PAIRS];
+  unsigned long long mask[RS_PAIRS];
+  int n = 0;
+  __device__ __forceinline__ explicit PairSink(const WarpHash &hh) : h(hh) {
+#pragma unroll
+    for (int i = 0; i < RS_PAIRS; i++) { key[i] = RS_EMPTY; mask[i] = 0ull; }
+  }
+  __device__ __forceinline__ void push() {
+    if (!acc.mask) return;
+    const uint32_t k = morton_key((uint32_t)acc.bx, (uint32_t)acc.by, (uint32_t)acc.bz);
+    bool placed = false;
+#pragma unroll
+    for (int i = 0; i < RS_PAIRS; i++) {
+      if (!placed && (key[i] == k || key[i] == RS_EMPTY)) {
+        key[i] = k;
+        mask[i] |= acc.mask;
+        placed = true;
+      }
+    }
+    if (!placed) hash_insert(h, k, acc.mask);   // more blocks than slots (a long segment): straight to the hash
+    acc.mask = 0ull;
+  }
+  __device__ __forceinline__ void cell(int ix, int iy, int iz) {
+    const int bx = ix >> 2, by = iy >> 2, bz = iz >> 2;
+    if (bx != acc.bx || by != acc.by || bz != acc.bz) {
+      push();
+      acc.bx = bx; acc.by = by; acc.bz = bz;
+    }
+    acc.mask |= 1ull << ((ix & 3) * 16 + (iy & 3) * 4 + (iz & 3));
+  }
+  __device__ __forceinline__ void finish() { push(); }
+};
+// all 32 lanes (converged): insert every lane's pairs, one hash access per distinct key and round
+__device__ __forceinline__ void warp_insert_pairs(const WarpHash &h, const PairSink &ps) {
+#pragma unroll
+  for (int r = 0; r < RS_PAIRS; r++) {
+    const uint32_t k = ps.key[r];
+    if (!__any_sync(0xffffffffu, k != RS_EMPTY)) break;
+    const unsigned peers = __match_any_sync(0xffffffffu, k);
+    const uint32_t lo = __reduce_or_sync(peers, (uint32_t)ps.mask[r]);
+    const uint32_t hi = __reduce_or_sync(peers, (uint32_t)(ps.mask[r] >> 32));
+    if (k != RS_EMPTY && (__ffs(peers) - 1) == (int)(threadIdx.x & 31))
+      hash_insert(h, k, ((unsigned long long)hi << 32) | lo);
+  }
+}
 struct EnvSink {
   const uint64_t *env;
   const uint32_t *occ;
@@ -362,7 +420,7 @@ struct SetSrc {
 // the device) with one warp per CTA and writes into the big slots.  Per-set arrays (counts, t_last,
 // nsamples, set_flags, ovf_slot) are indexed relative to set0.
 template <int HLOG, int WARPS>
-__global__ void __launch_bounds__(WARPS * 32)
+__global__ void __launch_bounds__(WARPS * 32, WARPS == 1 ? 1 : 5)
 swept_voxel_raster_kernel(const GridDev g, const SetSrc src, int64_t set0, int64_t nsets,
                           uint32_t *__restrict__ counts, double *__restrict__ t_last,
                           int32_t *__restrict__ nsamples, uint32_t *__restrict__ slot_keys,
@@ -431,15 +489,21 @@ swept_voxel_raster_kernel(const GridDev g, const SetSrc src, int64_t set0, int64
       }
     }
     __syncwarp();
-    // pass 2: lanes take consecutive segments of the concatenated polylines
-    for (int f = lane; f < total; f += 32) {
-      int k = 0;
-      for (int step = RS_MAXS >> 1; step > 0; step >>= 1)
-        if (k + step < nsm && lc[k + step] <= f) k += step;
-      const int i = f - lc[k] + 1;  // segment (i-1, i) of sample k
-      const double *sp = lp[k];
-      HashSink sink(h);
-      add_line(g, sink, rotate_pt(g, sp + 3 * (i - 1)), rotate_pt(g, sp + 3 * i));
+    // pass 2: lanes take consecutive segments of the concatenated polylines; the warp inserts the blocks of
+    // its 32 segments together
+    {
+      int k = 0;   // sample cursor: f only grows, so the sample a lane's segment belongs to only moves forward
+      for (int f0 = 0; f0 < total; f0 += 32) {
+        const int f = f0 + lane;
+        PairSink sink(h);
+        if (f < total) {
+          while (k + 1 < nsm && lc[k + 1] <= f) k++;
+          const int i = f - lc[k] + 1;  // segment (i-1, i) of sample k
+          const double *sp = lp[k];
+          add_line(g, sink, rotate_pt(g, sp + 3 * (i - 1)), rotate_pt(g, sp + 3 * i));
+        }
+        warp_insert_pairs(h, sink);
+      }
     }
     __syncwarp();
     const bool over = *h.overflow != 0u;
@@ -786,9 +850,18 @@ __device__ bool should_subdivide(const GridDev &g, const EdgePool &P, int32_t ed
     if (i >= 0) {
       long long s[3], e[3];
       const D3 qa = rotate_pt(g, pa + 3 * i), qb = rotate_pt(g, pb + 3 * i);
-      if (!find_cell(g, qa, s) || !find_cell(g, qb, e)) {
+      const bool in_a = !(qa.x < g.lo[0] || g.hi[0] < qa.x || qa.y < g.lo[1] || g.hi[1] < qa.y || qa.z < g.lo[2] || g.hi[2] < qa.z);
+      const bool in_b = !(qb.x < g.lo[0] || g.hi[0] < qb.x || qb.y < g.lo[1] || g.hi[1] < qb.y || qb.z < g.lo[2] || g.hi[2] < qb.z);
+      const double tight = 1.0 - 1e-9;
+      if (!in_a || !in_b) {
         ev = 2;
+      } else if (fabs(qa.x - qb.x) < g.d[0] * tight && fabs(qa.y - qb.y) < g.d[1] * tight &&
+                 fabs(qa.z - qb.z) < g.d[2] * tight) {
+        // two points less than one cell apart on every axis: their cells differ by at most 1 (the common case at
+        // the last bisection level) -- no need to locate them
       } else {
+        find_cell(g, qa, s);
+        find_cell(g, qb, e);
         const long long dx = llabs(s[0] - e[0]), dy = llabs(s[1] - e[1]), dz = llabs(s[2] - e[2]);
         if (dx > 1 || dy > 1 || dz > 1) ev = 1;
       }
@@ -1123,6 +1196,31 @@ int irt_voxelize_shapes(irt_ctx *ctx, const double *p, const int32_t *npts, int 
 // ---- edges ------------------------------------------------------------------------------------------
 namespace {
 
+// host-side copy between pageable user arrays and the context's pinned staging, on a few threads (one core
+// moves ~8-10 GB/s; the roadmap's index pairs and per-edge outputs are 160 MB each at 10M edges)
+void par_memcpy(void *dst, const void *src, size_t bytes) {
+  const int nt = bytes >= ((size_t)16 << 20) ? 4 : 1;
+  if (nt == 1) { std::memcpy(dst, src, bytes); return; }
+  std::thread th[3];
+  const size_t part = ((bytes / nt) + 4095) & ~(size_t)4095;
+  for (int t = 1; t < nt; t++) {
+    const size_t b = (size_t)t * part, e = std::min(bytes, b + part);
+    if (b < e) th[t - 1] = std::thread([=] { std::memcpy((char *)dst + b, (const char *)src + b, e - b); });
+  }
+  std::memcpy(dst, src, std::min(bytes, part));
+  for (int t = 1; t < nt; t++)
+    if (th[t - 1].joinable()) th[t - 1].join();
+}
+
+// per-edge outputs of a finished chunk on their way to the caller's arrays: device -> pinned staging (async, on
+// the chunk's stream) -> caller memory (host copy, done while the GPU works on later chunks)
+struct OutJob {
+  int64_t off;
+  int32_t E;
+  cudaEvent_t ev;
+  bool done;
+};
+
 // one in-flight chunk of edges: its stream, its share of the arena, its device counters
 struct Lane {
   cudaStream_t st = nullptr;
@@ -1166,9 +1264,33 @@ struct EdgeJob {
   cudaEvent_t ev_raster = nullptr;   // raster phases run in chunk order: each waits for the previous one
   bool raster_pending = false;
   int64_t mids_total = 0;
+  // caller's output arrays (may be null) and their pinned staging
+  uint32_t *u_flags = nullptr, *h_flags = nullptr;
+  double *u_tlast = nullptr, *h_tlast = nullptr;
+  int32_t *u_nsamp = nullptr, *h_nsamp = nullptr;
+  std::vector<OutJob> outs;
 };
 
+// copies finished chunks' outputs from the staging to the caller's arrays; block = wait for all of them
+int drain_outputs(EdgeJob &J, bool block) {
+  for (auto &o : J.outs) {
+    if (o.done) continue;
+    if (block) IRT_CUDA(J.ctx, cudaEventSynchronize(o.ev));
+    else if (cudaEventQuery(o.ev) != cudaSuccess) {
+      (void)cudaGetLastError();   // cudaErrorNotReady is recorded as the thread's last error: clear it
+      continue;
+    }
+    if (J.u_flags) std::memcpy(J.u_flags + o.off, J.h_flags + o.off, (size_t)o.E * 4);
+    if (J.u_tlast) std::memcpy(J.u_tlast + o.off, J.h_tlast + o.off, (size_t)o.E * 8);
+    if (J.u_nsamp) std::memcpy(J.u_nsamp + o.off, J.h_nsamp + o.off, (size_t)o.E * 4);
+    o.done = true;
+  }
+  return IRT_OK;
+}
+
+
 const int K2_T = 256;
+
 
 int issue_round(EdgeJob &J, Lane &L) {
   irt_ctx *ctx = J.ctx;
@@ -1284,6 +1406,15 @@ int issue_raster(EdgeJob &J, Lane &L) {
   IRT_CUDA(ctx, cudaEventRecord(J.ev_raster, st));
   J.raster_pending = true;
   J.mids_total += std::min(L.h_C[C_NMID], L.P.cap_mid);
+  if (J.u_flags || J.u_tlast || J.u_nsamp) {
+    if (J.u_flags) IRT_CUDA(ctx, cudaMemcpyAsync(J.h_flags + L.off, J.d_flags + L.off, (size_t)L.E * 4, cudaMemcpyDeviceToHost, st));
+    if (J.u_tlast) IRT_CUDA(ctx, cudaMemcpyAsync(J.h_tlast + L.off, J.d_tlast + L.off, (size_t)L.E * 8, cudaMemcpyDeviceToHost, st));
+    if (J.u_nsamp) IRT_CUDA(ctx, cudaMemcpyAsync(J.h_nsamp + L.off, J.d_nsamp + L.off, (size_t)L.E * 4, cudaMemcpyDeviceToHost, st));
+    OutJob o{L.off, L.E, nullptr, false};
+    IRT_CUDA(ctx, cudaEventCreateWithFlags(&o.ev, cudaEventDisableTiming));
+    IRT_CUDA(ctx, cudaEventRecord(o.ev, st));
+    J.outs.push_back(o);
+  }
   return IRT_OK;
 }
 
@@ -1411,8 +1542,20 @@ static int voxelize_edges_core(irt_ctx *ctx, const irt_robot *rb, const irt_spac
     return true;
   });
   if (rc) return rc;
-  int32_t *h_C = (int32_t *)ctx_pinned(ctx, 2 * C_WORDS * 4 + 64);
-  if (!h_C) return irt_fail(ctx, IRT_ERR_CUDA, "pinned staging allocation failed");
+  // pinned host staging (grow-only, owned by the context): chunk counters, the caller's per-edge outputs, and
+  // (indexed form) the vertex states and index pairs -- so every transfer is a real asynchronous DMA
+  const size_t pin_c = 256, pin_out = ((size_t)n * 16 + 255) & ~(size_t)255;
+  const size_t pin_pairs = indexed ? (((size_t)n * 16 + 255) & ~(size_t)255) : 0;
+  const size_t pin_vs = indexed ? (((size_t)nv * S * 8 + 255) & ~(size_t)255) : 0;
+  char *pin = (char *)ctx_pinned(ctx, pin_c + pin_out + pin_pairs + pin_vs);
+  if (!pin) return irt_fail(ctx, IRT_ERR_CUDA, "pinned staging allocation failed");
+  int32_t *h_C = (int32_t *)pin;
+  J.u_flags = flags; J.u_tlast = t_last; J.u_nsamp = nsamples;
+  J.h_tlast = (double *)(pin + pin_c);
+  J.h_flags = (uint32_t *)(pin + pin_c + (size_t)n * 8);
+  J.h_nsamp = (int32_t *)(pin + pin_c + (size_t)n * 12);
+  int64_t *h_pairs = (int64_t *)(pin + pin_c + pin_out);
+  double *h_vstates = (double *)(pin + pin_c + pin_out + pin_pairs);
   for (int l = 0; l < nlanes; l++) {
     Lane &L = lanes[l];
     L.st = l == 0 ? ctx->stream : ctx->copy_stream;
@@ -1435,7 +1578,8 @@ static int voxelize_edges_core(irt_ctx *ctx, const irt_robot *rb, const irt_spac
 
   // ---- indexed form: FK of every roadmap vertex once; edges read their endpoint shapes from it ------
   if (indexed) {
-    IRT_CUDA(ctx, cudaMemcpyAsync(d_vstates, vstates, (size_t)nv * S * 8, cudaMemcpyHostToDevice, s0));
+    par_memcpy(h_vstates, vstates, (size_t)nv * S * 8);
+    IRT_CUDA(ctx, cudaMemcpyAsync(d_vstates, h_vstates, (size_t)nv * S * 8, cudaMemcpyHostToDevice, s0));
     for (int64_t v0 = 0; v0 < nv; v0 += vchunk) {
       const int64_t m = std::min<int64_t>(vchunk, nv - v0);
       irt_fk_outputs o;
@@ -1451,11 +1595,11 @@ static int voxelize_edges_core(irt_ctx *ctx, const irt_robot *rb, const irt_spac
         IRT_LAUNCHED(ctx);
       }
     }
-    // all index pairs in ONE upload, on the second stream, issued after the vertex FK so that the (pageable,
-    // host-blocking) copy runs beside it; no per-chunk copies: they would block the host behind everything
-    // already queued on their stream
+    // all index pairs in ONE upload on the second stream; the host-side copy into the staging runs while the
+    // GPU computes the vertex shapes
     cudaStream_t sp = lanes[nlanes - 1].st;
-    IRT_CUDA(ctx, cudaMemcpyAsync(d_pairs_all, pairs, (size_t)n * 16, cudaMemcpyHostToDevice, sp));
+    par_memcpy(h_pairs, pairs, (size_t)n * 16);
+    IRT_CUDA(ctx, cudaMemcpyAsync(d_pairs_all, h_pairs, (size_t)n * 16, cudaMemcpyHostToDevice, sp));
     IRT_CUDA(ctx, cudaEventRecord(ctx->ev_copied[1], sp));
     IRT_CUDA(ctx, cudaStreamWaitEvent(s0, ctx->ev_copied[1], 0));
   }
@@ -1474,9 +1618,12 @@ static int voxelize_edges_core(irt_ctx *ctx, const irt_robot *rb, const irt_spac
   auto fail = [&](int code) {
     cudaStreamSynchronize(ctx->stream);
     cudaStreamSynchronize(ctx->copy_stream);
+    for (auto &o : J.outs) cudaEventDestroy(o.ev);
     return code;
   };
   for (;;) {
+    rc = drain_outputs(J, false);   // finished chunks' outputs go to the caller while the GPU works on
+    if (rc) return fail(rc);
     while (!idle.empty() && !todo.empty()) {
       Lane *L = idle.back();
       idle.pop_back();
@@ -1511,9 +1658,10 @@ static int voxelize_edges_core(irt_ctx *ctx, const irt_robot *rb, const irt_spac
     IRT_CUDA(ctx, cudaEventRecord(ctx->ev_offsets[1], lanes[1].st));
     IRT_CUDA(ctx, cudaStreamWaitEvent(s0, ctx->ev_offsets[1], 0));
   }
-  if (flags) IRT_CUDA(ctx, cudaMemcpyAsync(flags, J.d_flags, (size_t)n * 4, cudaMemcpyDeviceToHost, s0));
-  if (t_last) IRT_CUDA(ctx, cudaMemcpyAsync(t_last, J.d_tlast, (size_t)n * 8, cudaMemcpyDeviceToHost, s0));
-  if (nsamples) IRT_CUDA(ctx, cudaMemcpyAsync(nsamples, J.d_nsamp, (size_t)n * 4, cudaMemcpyDeviceToHost, s0));
+  rc = drain_outputs(J, true);
+  if (rc) return fail(rc);
+  for (auto &o : J.outs) cudaEventDestroy(o.ev);
+  J.outs.clear();
   uint64_t total = 0;
   bool overflow = false;
   rc = J.tot.read(ctx, s0, &total, &overflow);

@@ -63,6 +63,80 @@ def assemble_verdicts(all_words, n, world, align=64):
     return out
 
 
+class LockstepFk:
+    """Batching layer under k IK solvers that run side by side: every solver asks for the tip and
+    the finite-difference tip Jacobian of ONE state at a time, like the reference's ikController_ does through
+    fk_wrap (tip-control/tip_control.cpp:92-122); the requests of all solvers that are still running are answered
+    by ONE K1 launch (irt_fk_tip_jacobian_batch over n (2S+1) states).  The solvers themselves stay what they
+    are -- e.g. the reference's levmar driver, sequential host code -- and run in one host thread each."""
+
+    def __init__(self, robot, n_workers, mode=None, delta=1e-6):
+        import threading
+        from . import JAC_LEVMAR_CENTRAL
+        self.robot, self.mode, self.delta = robot, (JAC_LEVMAR_CENTRAL if mode is None else mode), delta
+        self.cv = threading.Condition()
+        self.active, self.pending, self.results, self.generation = n_workers, {}, {}, 0
+        self.batches = self.evaluations = 0
+
+    def _flush(self):       # called with the lock held by the thread that completed the round
+        ids = sorted(self.pending)
+        states = np.stack([self.pending[i] for i in ids])
+        tips, J = self.robot.tip_jacobian_batch(states, mode=self.mode, delta=self.delta)
+        self.results = {i: (tips[k].copy(), J[k].copy()) for k, i in enumerate(ids)}
+        self.pending = {}
+        self.batches += 1
+        self.evaluations += len(ids)
+        self.generation += 1
+        self.cv.notify_all()
+
+    def evaluate(self, worker, state):
+        """tip [3] and Jacobian [3][S] at `state`; blocks until every running solver has asked"""
+        with self.cv:
+            self.pending[worker] = np.array(state, dtype=np.float64)
+            gen = self.generation
+            if len(self.pending) == self.active:
+                self._flush()
+            else:
+                while self.generation == gen:
+                    self.cv.wait()
+            return self.results[worker]
+
+    def finished(self, worker):
+        with self.cv:
+            self.active -= 1
+            if self.active > 0 and len(self.pending) == self.active:
+                self._flush()
+
+
+def solve_ik_lockstep(robot, solver, starts, request, mode=None, delta=1e-6):
+    """runs solver(start, request, fk) for every start state side by side, fk(state) -> (tip, J) answered in
+    lockstep batches.  Returns (final states [k][S], LockstepFk with its batch statistics)."""
+    import threading
+    starts = np.asarray(starts, dtype=np.float64)
+    k = len(starts)
+    fk = LockstepFk(robot, k, mode, delta)
+    out, errors = [None] * k, [None] * k
+
+    def run(i):
+        try:
+            out[i] = np.asarray(solver(starts[i].copy(), np.asarray(request, dtype=np.float64),
+                                       lambda st, _i=i: fk.evaluate(_i, st)), dtype=np.float64)
+        except BaseException as e:   # noqa: a failing solver must not leave the others waiting for it
+            errors[i] = e
+        finally:
+            fk.finished(i)
+
+    threads = [threading.Thread(target=run, args=(i,)) for i in range(k)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    for e in errors:
+        if e is not None:
+            raise e
+    return np.stack(out), fk
+
+
 class VoxelCachedLazyPRM:
     """Roadmap with device-resident voxel caches and batch validity sweeps."""
 
@@ -411,8 +485,8 @@ class VoxelCachedLazyPRM:
             eid = np.concatenate([np.arange(m), np.arange(m)])
             order = np.argsort(src, kind="stable")
             ptr = np.zeros(n + 1, dtype=np.int64)
-            np.add.at(ptr, src + 1, 1)
-            self._adj = (np.cumsum(ptr), dst[order], eid[order], m)
+            ptr[1:] = np.cumsum(np.bincount(src, minlength=n))
+            self._adj = (ptr, dst[order], eid[order], m)
             if len(self.vertex_removed) != n:
                 self.vertex_removed = np.zeros(n, dtype=bool)
             if len(self.edge_removed) != m:
@@ -496,6 +570,110 @@ class VoxelCachedLazyPRM:
             if nv == int(self.vertex_removed.sum()) and ne == int(self.edge_removed.sum()):
                 return None, it                       # nothing removed: A* found no path
         return None, max_iterations
+
+    def restoreRemoved(self):
+        """forget the removals of constructSolution / roadmapIk (the reference reloads its roadmap instead)"""
+        self.vertex_removed[:] = False
+        self.edge_removed[:] = False
+
+    # ---- roadmapIk as a batch (VoxelCachedLazyPRM.cpp:3095-3420) -----------------------------------------------
+    def nearest_tips(self, request, k):
+        """nnTip_->nearestK: the k vertices whose cached tip positions are nearest to `request` (exact)"""
+        if self.tips is None or len(self.tips) != len(self.states):
+            self.precomputeVertexVoxelCache()
+        d = np.linalg.norm(self.tips - np.asarray(request, dtype=np.float64)[None], axis=1)
+        d = np.where(self.vertex_removed[:len(d)] if len(self.vertex_removed) == len(d) else False, np.inf, d)
+        order = np.lexsort((np.arange(len(d)), d))[:k]
+        return order[np.isfinite(d[order])]
+
+    def roadmapIk(self, request, tolerance, k, solver, auto_add=False, mode=None, delta=1e-6):
+        """roadmapIk(request, tolerance, k, opt) of the reference with its per-neighbour loop turned into batches:
+          1. the k nearest VALID neighbours in tip space (invalid ones are removed and the query repeated,
+             .cpp:3112-3137; validity = table look-ups),
+          2. the k IK problems solved side by side, their FK / Jacobian requests answered in lockstep by single
+             K1 launches (solve_ik_lockstep; `solver(start, request, fk)` is the reference's ikController_),
+          3. ONE FK + is_valid_shape + voxelise + collides call over the k results (.cpp:3182-3192),
+          4. RMAP_IK_AUTO_ADD: ONE voxelize_until_invalid call over the edges neighbour -> result of every result
+             within tolerance (.cpp:3214-3292),
+          5. the reference's order of acceptance: the FIRST neighbour (nearest first) whose result it would have
+             returned; without auto_add, failing that, the closest valid result, and failing that the closest
+             last-valid state of the edges neighbour -> result (.cpp:3298-3420, one more until-invalid batch).
+        Returns dict(controls, tip_position, neighbor, error, index, vertex, lockstep_batches, ...) or None."""
+        if self.world != 1:
+            raise NotImplementedError("roadmapIk runs on the full roadmap of one rank")
+        request = np.asarray(request, dtype=np.float64)
+        while True:
+            nb = self.nearest_tips(request, k)
+            if not len(nb):
+                raise RuntimeError("roadmapIk(): No neighbors were able to be found")
+            bad = [int(v) for v in nb if not self.computeVertexValidity(int(v))]
+            if not bad:
+                break
+            self._adjacency()
+            self.vertex_removed[bad] = True
+        starts = self.states[nb]
+        finals, fk = solve_ik_lockstep(self.robot, solver, starts, request, mode, delta)
+        scratch = SetStore(self.ctx, self.grid)
+        flags, tips = scratch.voxelize_vertices(self.robot, finals)
+        collides = scratch.check(self.env)
+        valid = ((flags & INVALID_MASK) == 0) & ~collides
+        err = np.linalg.norm(tips - request[None], axis=1)
+        info = dict(lockstep_batches=fk.batches, fk_requests=fk.evaluations, neighbors=nb, errors=err, valid=valid)
+
+        def result(i, controls=None, tip=None, error=None, **kw):
+            return dict(controls=finals[i] if controls is None else controls,
+                        tip_position=tips[i] if tip is None else tip, neighbor=starts[i],
+                        error=float(err[i] if error is None else error), index=int(i), vertex=int(nb[i]), **info, **kw)
+
+        if not auto_add:
+            for i in range(len(nb)):
+                if valid[i] and err[i] < tolerance:
+                    return result(i)
+            ok = np.nonzero(valid)[0]
+            if len(ok):          # "All IKs rejected, returning closest valid one"
+                return result(int(ok[np.argmin(err[ok])]), accepted=False)
+            # "All IKs are in collision, stepping them backwards": last valid state of neighbour -> result
+            est = SetStore(self.ctx, self.grid)
+            pe = est.voxelize_edges_until_invalid(self.robot, self.space, starts, finals, self.env)
+            t = pe["t_last"][:, None]
+            last_valid = self._interpolate(starts, finals, t)
+            lt = self.robot.shape_batch(last_valid, want=("tip",))["tip"]
+            lerr = np.linalg.norm(lt - request[None], axis=1)
+            j = int(np.argmin(lerr))
+            return result(j, controls=last_valid[j], tip=lt[j], error=lerr[j], accepted=False, stepped_back=True)
+        cand = [i for i in range(len(nb)) if err[i] < tolerance]
+        if not cand:
+            return None
+        est = SetStore(self.ctx, self.grid)
+        pe = est.voxelize_edges_until_invalid(self.robot, self.space, starts[cand], finals[cand], self.env)
+        for c, i in enumerate(cand):
+            if (pe["flags"][c] & FLAG_PARTIAL) == 0:      # is_fully_valid: connect neighbour -- new vertex
+                v = len(self.states)
+                self.states = np.ascontiguousarray(np.concatenate([self.states, finals[i:i + 1]], axis=0))
+                self.edges = np.ascontiguousarray(np.concatenate([self.edges, [[int(nb[i]), v]]], axis=0))
+                self.vertex_validity = np.append(self.vertex_validity, np.uint8(VALIDITY_TRUE))
+                self.edge_validity = np.append(self.edge_validity, np.uint8(VALIDITY_TRUE))
+                self.vertex_removed = np.append(self.vertex_removed, False)
+                self.edge_removed = np.append(self.edge_removed, False)
+                self.tips = np.concatenate([self.tips, tips[i:i + 1]], axis=0)
+                self._adj = None
+                self._have_vcache = self._have_ecache = False     # the caches lack the new vertex / edge
+                return result(i, added_vertex=v)
+        return None
+
+    def _interpolate(self, a, b, t):
+        """OMPL compound interpolate of the space of Problem.cpp:101-163 (RealVector linear, SO2 shortest arc)"""
+        d = self.robot.spec
+        out = a + (b - a) * t
+        if d.get("enable_rotation"):
+            k = len(d["C"])
+            diff = b[:, k] - a[:, k]
+            wrap = np.abs(diff) > np.pi
+            dd = np.where(diff > 0, 2 * np.pi - diff, -2 * np.pi - diff)
+            v = a[:, k] - dd * t[:, 0]
+            v = np.where(v > np.pi, v - 2 * np.pi, np.where(v < -np.pi, v + 2 * np.pi, v))
+            out[:, k] = np.where(wrap, v, out[:, k])
+        return out
 
     def _gather_flags(self, local_flags, n_total, mask):
         """validity flags of all shards as a global bool array (1 bit per item on the wire)."""

@@ -970,7 +970,8 @@ def test_pinned_staging_survives_io_growth(irt, ctx, wl):
     a = rb.shape_batch_packed(small, want=("p", "npts", "flags"))
     dense = rb.shape_batch(big, want=("p", "npts", "L_i", "flags"))
     b = rb.shape_batch_packed(small, want=("p", "npts", "flags"))
-    assert np.array_equal(a["row_offsets"], b["row_offsets"]) and np.array_equal(a["p"], b["p"])
+    rows = int(a["row_offsets"][-1])
+    assert np.array_equal(a["row_offsets"], b["row_offsets"]) and np.array_equal(a["p"][:rows], b["p"][:rows])
     assert np.array_equal(a["npts"], b["npts"]) and int(a["row_offsets"][-1]) == int(a["npts"].sum())
     assert dense["npts"].shape == (300_000,)
 
@@ -1014,3 +1015,89 @@ def test_lazy_path_consumers_on_device_tables(irt, ctx, orc, wl):
     assert solved >= 5 and prm.lookups["sweeps"] == 2
     assert np.array_equal(prm.vertex_validity.astype(bool), v_ok) and np.array_equal(prm.edge_validity.astype(bool), e_ok)
     assert not v_ok[prm.vertex_removed].any() and not e_ok[prm.edge_removed].any()
+
+
+def _adversarial_backbones(rng, r, cap):
+    """polylines that sit on the decision boundaries of collides_self (collision/collision.cpp:6-46)"""
+    shapes = []
+
+    def put(pts):
+        pts = np.asarray(pts, dtype=np.float64)
+        if 2 <= len(pts) <= cap:
+            shapes.append(pts)
+
+    def rigid(pts):
+        q, _ = np.linalg.qr(rng.normal(size=(3, 3)))
+        return np.asarray(pts) @ q.T + rng.uniform(-0.15, 0.15, 3)
+
+    dl = 0.005
+    # (1) hairpins: two parallel runs D apart, D = 2r +- a few ulp and +- small relative steps (parallel-segment
+    #     branch of closest_st_segment; the FP32 filter must keep every D <= 2r)
+    for j in list(range(-4, 5)) + [-1000, 1000, -10 ** 6, 10 ** 6]:
+        D = np.nextafter(2 * r, np.inf) if j == 0 else 2 * r * (1 + j * 2.2e-16)
+        for nleg in (10, 14, 20):
+            out = [[i * dl, 0.0, 0.0] for i in range(nleg)]
+            nb = 6
+            bend = [[(nleg - 1) * dl + 0.5 * D * np.sin(np.pi * k / nb), 0.5 * D * (1 - np.cos(np.pi * k / nb)), 0.0]
+                    for k in range(1, nb)]
+            back = [[(nleg - 1 - i) * dl, D, 0.0] for i in range(nleg)]
+            put(out + bend + back)
+            put(rigid(out + bend + back))
+    # (2) V shapes: legs of n segments, turning theta at the corner; arc gaps around the 3r rule, distances around 2r
+    for theta in np.linspace(0.3, 3.1, 29):
+        for n1 in (3, 5, 8, 9, 10, 12):
+            for scale in (1.0, 1.0 - 1e-12, 1.0 + 1e-12, 0.9, 1.1):
+                d2 = np.array([np.cos(np.pi - theta), np.sin(np.pi - theta), 0.0])
+                a = [[-(n1 - i) * dl * scale, 0.0, 0.0] for i in range(n1)] + [[0.0, 0.0, 0.0]]
+                b = [list(d2 * (i + 1) * dl * scale) for i in range(n1)]
+                put(rigid(a + b))
+    # (3) arcs and spirals: constant and growing curvature, turning from below the early-out to several turns
+    for turn in np.concatenate([np.linspace(1.2, 2.2, 21), np.linspace(2.5, 14.0, 24)]):
+        for n in (20, 40, cap - 1):
+            s = np.arange(n + 1) * dl
+            for grow in (0.0, 1.0):
+                kappa = turn / s[-1] * (1 + grow * s / s[-1]) / (1 + grow / 2)
+                ang = np.concatenate([[0], np.cumsum(kappa[:-1] * dl)])
+                pts = np.concatenate([[[0, 0, 0]], np.cumsum(np.stack([np.cos(ang[:-1]), np.sin(ang[:-1]),
+                                                                         0.02 * np.ones(n)], 1) * dl, 0)])
+                put(rigid(pts))
+    # (4) random walks with bounded turning per step (many true collisions, many near misses)
+    for _ in range(3000):
+        n = int(rng.integers(8, cap))
+        d = rng.normal(size=3)
+        d /= np.linalg.norm(d)
+        pts = [np.zeros(3)]
+        for _k in range(n - 1):
+            d = d + rng.normal(size=3) * rng.uniform(0.05, 0.6)
+            d /= np.linalg.norm(d)
+            pts.append(pts[-1] + d * dl * rng.uniform(0.6, 1.2))
+        put(rigid(pts))
+    # (5) degenerate: repeated points, very short shapes
+    put(np.zeros((10, 3)))
+    put([[0, 0, 0], [dl, 0, 0]])
+    put([[0, 0, 0], [dl, 0, 0], [0, 0, 0], [dl, 0, 0], [0, 0, 0], [dl, 0, 0]])
+    return shapes
+
+
+def test_self_collision_adversarial_boundaries(irt, ctx, orc, wl):
+    """collides_self on backbones built to sit on its decision boundaries: capsule pairs at 2r +- ulps (parallel
+    and skew), arc gaps at the 3r skip rule, sharp corners, arcs around the turning bound of the filter's early
+    out, spirals, random walks.  The FP32 pair filter and the turning early-out must never drop a true hit, and
+    the exact stage must reproduce the reference's arithmetic: verdicts identical to the oracle on every shape."""
+    r, cap = 0.015, 68
+    shapes = _adversarial_backbones(np.random.default_rng(11), r, cap)
+    n = len(shapes)
+    p = np.zeros((n, cap, 3))
+    npts = np.zeros(n, dtype=np.int32)
+    for i, s in enumerate(shapes):
+        p[i, :len(s)] = s
+        npts[i] = len(s)
+    got = irt.self_collision_shapes(ctx, p, npts, r)
+    want = np.array([orc.collides_self(np.ascontiguousarray(s), r) for s in shapes])
+    assert n > 4000 and 0.1 < want.mean() < 0.9
+    bad = np.nonzero(got != want)[0]
+    assert len(bad) == 0, "verdict differs on %d shapes, first: %s" % (len(bad), bad[:5])
+    # the same shapes through a narrower layout (cap 41 -> half a warp per shape in the filter)
+    short = np.nonzero(npts <= 41)[0]
+    got41 = irt.self_collision_shapes(ctx, np.ascontiguousarray(p[short, :41]), npts[short], r)
+    assert np.array_equal(got41, want[short]) and want[short].any() and not want[short].all()

@@ -294,3 +294,69 @@ def test_k1_vs_reference_tendon_robot_shape(irt, ctx, wl, name):
         assert seen & 1
     if name == "a003soft":
         assert seen & 2 and seen & 4
+
+
+@pytest.mark.skipif(not ref.RefLevmar.available(), reason="oracle/_ref/liblevmar_ref.so was not shipped")
+def test_roadmap_ik_lockstep_with_the_reference_levmar(irt, ctx, orc, wl):
+    """roadmapIk as a batch (VoxelCachedLazyPRM.cpp:3095-3205): the k seeds' IK problems run the reference's own
+    optimiser (levmar-2.6 dlevmar_bc_der, one host thread per seed) while every FK / Jacobian request of the k
+    solvers is answered in lockstep by single K1 launches; results and the order of acceptance equal the
+    reference's sequential loop (dlevmar_bc_dif over a CPU FK, neighbour by neighbour)."""
+    from irt_b200 import roadmap as R
+    spec = wl.robot_b(0.003)       # voxel caches at 128^3 need dL <= the voxel size
+    g = wl.workspace_grid(spec)
+    grid = irt.make_grid(g["Ng"], g["lim"], g["inv_rot"])
+    rb = irt.Robot(ctx, spec)
+    orb = orc.robot(spec)
+    L = spec["L"]
+    delta = 1e-6
+    prm = R.VoxelCachedLazyPRM(ctx, rb, grid)
+    prm.createRoadmap(300, lambda cnt, rnd: wl.sample_states(spec, cnt, stream=950 + rnd),
+                      lambda st: wl.knn_edges(spec, st, k=4), opt=R.VoxelizeVertices)
+    env = irt.Env(ctx, grid)
+    env.add_primitives(spheres=[[0.06, 0.0, 0.12, 0.025]], clear=True)
+    prm.setEnvironment(env.download())
+    ogrid = orc.grid(g["Ng"], g["lim"])
+    oenv = orc.octree(ogrid)
+    oenv.add_sphere([0.06, 0.0, 0.12], 0.025)
+    lb, ub = np.zeros(7), np.array([20.0] * 6 + [L])
+    opts = [0.1, 1e-9, 1e-8, 1e-8]
+
+    def f_cpu(p):
+        if p[-1] > L:
+            return np.array([0.0, 0.0, L - p[-1]])
+        return orc.shape(orb, p)["p"][-1]
+
+    def solver(start, request, fk):
+        last = {}
+
+        def both(p):
+            key = p.tobytes()
+            if last.get("k") != key:
+                last["k"], last["v"] = key, fk(p)
+            return last["v"]
+
+        p, info, _ = ref.RefLevmar.bc_der(lambda q: both(q)[0], lambda q: both(q)[1], start, request, lb, ub, 100, opts)
+        return p
+
+    rng = np.random.default_rng(8)
+    accepted = 0
+    for trial in range(3):
+        goal = np.clip(prm.states[rng.integers(300)] + rng.normal(size=7) * [0.8, 0.8, 0.8, 0.8, 0.8, 0.8, 0.003], lb, ub)
+        request = f_cpu(goal)
+        got = prm.roadmapIk(request, 5e-4, 4, solver, delta=delta)
+        assert got["lockstep_batches"] < got["fk_requests"]
+        want = None
+        for i, v in enumerate(got["neighbors"]):
+            p_ref, info_ref, _ = ref.RefLevmar.bc_dif(f_cpu, prm.states[v].copy(), request, lb, ub, 100, opts + [-delta])
+            st_, fl_ = orc.voxelize_vertices_batch(orb, ogrid, p_ref[None])
+            ok = fl_[0] == 0 and not orc.check_sets_batch(st_, oenv)[0]
+            err = float(np.linalg.norm(f_cpu(p_ref) - request))
+            assert bool(got["valid"][i]) == bool(ok)
+            assert abs(got["errors"][i] - err) < 2e-5
+            if want is None and ok and err < 5e-4:
+                want = (i, p_ref)
+        if want is not None:
+            accepted += 1
+            assert got["index"] == want[0] and np.abs(got["controls"] - want[1]).max() < 1e-6 * 20.0
+    assert accepted >= 1

@@ -14,7 +14,13 @@ class _Robot:
         self.state_size = wl.state_size(spec)
 
     def shape_batch(self, states, want=("flags",)):
-        return dict(flags=self.orc.fk_batch(self.orb, states, 128, want_p=False)["flags"])
+        out = self.orc.fk_batch(self.orb, np.ascontiguousarray(states), 128, want_p=False)
+        return {k: out[k] for k in want}
+
+    def tip_jacobian_batch(self, states, mode=2, delta=1e-6):
+        self.jac_calls = getattr(self, "jac_calls", 0) + 1
+        res = [self.orc.tip_jacobian(self.orb, np.ascontiguousarray(s), mode, delta) for s in states]
+        return np.stack([r[0] for r in res]), np.stack([r[1] for r in res])
 
 
 class _Env:
@@ -32,8 +38,16 @@ class _Store:
 
     def voxelize_vertices(self, robot, states):
         self.calls += 1
+        states = np.ascontiguousarray(states)
         self.store, flags = self.orc.voxelize_vertices_batch(robot.orb, self.ogrid, states)
-        return flags, None
+        return flags, self.orc.fk_batch(robot.orb, states, 128, want_p=False)["tip"]
+
+    def voxelize_edges_until_invalid(self, robot, space, a, b, env):
+        self.calls += 1
+        res = [self.orc.voxelize_edge(robot.orb, self.ogrid, self.orc.space(), np.ascontiguousarray(x),
+                                      np.ascontiguousarray(y), env=env.oenv) for x, y in zip(a, b)]
+        return dict(flags=np.array([0 if r[1]["is_fully_valid"] else 16 for r in res], dtype=np.uint32),
+                    t_last=np.array([r[1]["t"] for r in res]))
 
     def voxelize_edges_indexed(self, robot, space, vertex_states, pairs):
         self.calls += 1
@@ -216,6 +230,88 @@ def test_lazy_path_consumers_are_lookups(orc, wl, monkeypatch):
     prm.clearValidity()
     assert prm.computeVertexValidity(int(np.nonzero(~v_ok & (vf == 0))[0][0]))
     assert prm.lookups["sweeps"] == 3
+
+
+def _dls_solver(lb, ub, iters=25):
+    """a small damped-least-squares IK with box clamping: stands in for the reference's ikController_ (the
+    levmar driver); all it sees of the robot is fk(state) -> (tip, J)"""
+    def solve(start, request, fk):
+        x = start.copy()
+        for _ in range(iters):
+            tip, J = fk(x)
+            e = request - tip
+            if np.linalg.norm(e) < 1e-7:
+                break
+            dx = J.T @ np.linalg.solve(J @ J.T + 1e-8 * np.eye(3), e)
+            x = np.clip(x + dx, lb, ub)
+        return x
+    return solve
+
+
+def test_roadmap_ik_batch_host_logic(orc, wl, monkeypatch):
+    """roadmapIk as a batch (VoxelCachedLazyPRM.cpp:3095-3420): k IK problems solved side by side with their FK /
+    Jacobian requests coalesced into lockstep batches, one validity call over the k results, the reference's order
+    of acceptance.  Checked against the reference's sequential per-neighbour loop restated over the oracle."""
+    from irt_b200 import roadmap as R
+    spec = wl.robot_b(0.003)
+    g = wl.workspace_grid(spec)
+    ogrid = orc.grid(g["Ng"], g["lim"])
+    oenv = orc.octree(ogrid)
+    oenv.add_sphere([0.05, 0.0, 0.12], 0.03)
+    prm = _prm(R, orc, wl, spec, g, oenv, monkeypatch)
+    prm.world = 1
+    prm.createRoadmap(80, lambda cnt, rnd: wl.sample_states(spec, cnt, stream=900 + rnd),
+                      lambda st: wl.knn_edges(spec, st, k=4), opt=R.VoxelizeVertices)
+    rb = prm.robot
+    lb, ub = np.zeros(7), np.array([20.0] * 6 + [spec["L"]])
+    solver = _dls_solver(lb, ub)
+    rng = np.random.default_rng(3)
+    accepted = fallback = 0
+    for trial in range(6):
+        goal = np.clip(prm.states[rng.integers(80)] + rng.normal(size=7) * [1, 1, 1, 1, 1, 1, 0.004], lb, ub)
+        request = orc.fk_batch(rb.orb, goal[None], 128, want_p=False)["tip"][0]
+        k = 4
+        got = prm.roadmapIk(request, 1e-4, k, solver)
+        # the reference's loop, one neighbour at a time, nearest first
+        nb = got["neighbors"]
+        assert np.array_equal(nb, prm.nearest_tips(request, k))
+        want = None
+        seq = []
+        for i, v in enumerate(nb):
+            fin = solver(prm.states[v].copy(), request, lambda st: orc.tip_jacobian(rb.orb, st, 2, 1e-6))
+            st_, fl_ = orc.voxelize_vertices_batch(rb.orb, ogrid, fin[None])
+            ok = fl_[0] == 0 and not orc.check_sets_batch(st_, oenv)[0]
+            tip = orc.fk_batch(rb.orb, fin[None], 128, want_p=False)["tip"][0]
+            err = float(np.linalg.norm(tip - request))
+            seq.append((fin, ok, err))
+            if want is None and ok and err < 1e-4:
+                want = i
+        for i, (fin, ok, err) in enumerate(seq):      # lockstep batching does not change a single iterate
+            assert bool(got["valid"][i]) == bool(ok) and abs(got["errors"][i] - err) < 1e-12
+        if want is not None:
+            accepted += 1
+            assert got["index"] == want and np.array_equal(got["controls"], seq[want][0])
+        else:
+            fallback += 1
+            oks = [i for i, (_, ok, _) in enumerate(seq) if ok]
+            if oks:
+                best = min(oks, key=lambda i: seq[i][2])
+                assert got["index"] == best and got.get("accepted") is False
+            else:
+                assert got.get("stepped_back")
+        assert got["lockstep_batches"] < got["fk_requests"], "requests of the k solvers must share launches"
+    assert accepted >= 3
+    # auto_add: the accepted result joins the roadmap through a collision-free edge from its IK neighbour
+    nv, ne = len(prm.states), len(prm.edges)
+    goal = np.clip(prm.states[5] + 0.3, lb, ub)
+    request = orc.fk_batch(rb.orb, goal[None], 128, want_p=False)["tip"][0]
+    res = prm.roadmapIk(request, 1e-4, 3, solver, auto_add=True)
+    if res is not None:
+        assert len(prm.states) == nv + 1 and len(prm.edges) == ne + 1 and res["added_vertex"] == nv
+        assert tuple(prm.edges[-1]) == (res["vertex"], nv) and np.array_equal(prm.states[-1], res["controls"])
+        e_store, e_info = orc.voxelize_edge(rb.orb, ogrid, orc.space(), prm.states[res["vertex"]].copy(),
+                                            res["controls"].copy(), env=oenv)
+        assert e_info["is_fully_valid"]
 
 
 def test_sweeps_on_edgeless_roadmap(orc, wl, monkeypatch):

@@ -18,6 +18,36 @@ if which == "fk":
     for _ in range(3):
         rb.shape_batch_dev(st, n, outs)
         ctx.synchronize()
+elif which == "fkv":      # the headline step: FK + validity epilogue (flags)
+    spec = wl.robot_b(0.005)
+    rb = irt_b200.Robot(ctx, spec)
+    n = 1_000_000
+    st = torch.from_numpy(wl.sample_states(spec, n, stream=100)).cuda()
+    outs = dict(p=torch.zeros(n, rb.max_points, 3, dtype=torch.float64, device="cuda"),
+                npts=torch.zeros(n, dtype=torch.int32, device="cuda"),
+                L=torch.zeros(n, dtype=torch.float64, device="cuda"),
+                L_i=torch.zeros(n, 6, dtype=torch.float64, device="cuda"),
+                flags=torch.zeros(n, dtype=torch.int32, device="cuda"))
+    for _ in range(3):
+        rb.shape_batch_dev(st, n, outs)
+        ctx.synchronize()
+elif which == "peak":     # the FP64 roofline denominator: the DFMA-chain probe
+    print("fp64 peak", ctx.fp64_peak() / 1e12, "TFLOP/s")
+elif which == "k2":       # K2 over a small k-NN roadmap (numpy k-NN: no torch kernels in the launch list)
+    spec = wl.robot_b(0.003)
+    rb = irt_b200.Robot(ctx, spec)
+    g = wl.workspace_grid(spec)
+    grid = irt_b200.make_grid(g["Ng"], g["lim"])
+    nv = int(sys.argv[2]) if len(sys.argv) > 2 else 40000
+    st = wl.sample_states(spec, nv, stream=200)
+    pairs = wl.knn_edges(spec, st, k=10)
+    store = irt_b200.SetStore(ctx, grid)
+    import time
+    for rep in range(2):
+        t0 = time.perf_counter()
+        info = store.voxelize_edges_indexed(rb, irt_b200.make_space(), st, pairs)
+        print("k2 edges", len(pairs), "%.1f ms" % ((time.perf_counter() - t0) * 1e3), "samples/edge",
+              info["nsamples"].mean(), "blocks/edge", store.num_blocks / len(pairs))
 elif which == "k3real":
     # K3 over a roadmap store built by the real pipeline (bench.py's edge_check at 300k vertices)
     sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
