@@ -100,6 +100,45 @@ class ClockSampler(threading.Thread):
                 "reasons": sorted(self.reasons)}
 
 
+def bind_rank_to_gpu_numa(local_rank, world):
+    """N > 1: pin this rank's host threads (and therefore the first-touch placement of its pinned buffers) to
+    the CPUs of the NUMA node its GPU hangs off, split evenly between the ranks that share the node.  Reporting
+    only when the topology cannot be read (containers often expose a single node)."""
+    info = {"numa_node": None, "cpus": None}
+    try:
+        import torch
+        bus = torch.cuda.get_device_properties(local_rank).pci_bus_id if hasattr(
+            torch.cuda.get_device_properties(local_rank), "pci_bus_id") else None
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(local_rank)
+        bus = pynvml.nvmlDeviceGetPciInfo(h).busId
+        bus = bus.decode() if isinstance(bus, bytes) else bus
+        path = "/sys/bus/pci/devices/%s/numa_node" % bus.lower()[-12:]
+        node = int(open(path).read().strip())
+        info["numa_node"] = node
+        if node < 0:
+            return info
+        cl = open("/sys/devices/system/node/node%d/cpulist" % node).read().strip()
+        cpus = []
+        for part in cl.split(","):
+            a, _, b = part.partition("-")
+            cpus += list(range(int(a), int(b or a) + 1))
+        allowed = sorted(set(cpus) & os.sched_getaffinity(0))
+        if world > 1 and len(allowed) >= 2:
+            # the ranks of one node share its CPUs: an even slice each (rank order)
+            peers = [r for r in range(world)]
+            share = max(1, len(allowed) // max(1, len(peers)))
+            mine = allowed[(local_rank * share) % len(allowed):][:share] or allowed
+            os.sched_setaffinity(0, mine)
+            info["cpus"] = len(mine)
+        else:
+            info["cpus"] = len(allowed)
+    except Exception as e:
+        info["error"] = repr(e)[:120]
+    return info
+
+
 def cpu_fk_rate(spec, n_tendons, seconds, threads=None, stream=900, batch=20000, variant="fast"):
     """oracle (restatement of the reference CPU path, -O3 -march=native -fopenmp) timed on a
     bounded sample of the SAME workload; loop shape = apps/estimate_length_discretization.cpp:62-71.
@@ -336,6 +375,7 @@ def main():
         raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    affinity = bind_rank_to_gpu_numa(local_rank, world) if world > 1 else None
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         # NCCL prints its version banner (NCCL_DEBUG=VERSION/INFO) on STDOUT when the communicator is
@@ -846,7 +886,7 @@ def main():
             "clocks": sampler.result(), "e2e": e2e, "gpu_launches": int(launches),
             "roofline": roofline, "cpu_baseline": cpu, "edge_check": edge_check,
             "wall_s_timed_region": t_wall, "host_vs_device_path_equal": same,
-            "valid_shape_fraction": valid_fraction,
+            "valid_shape_fraction": valid_fraction, "host_affinity_rank0": affinity,
         }
         print(json.dumps(line), flush=True)
     if world > 1:

@@ -283,7 +283,13 @@ __device__ __forceinline__ void vu_dot(const double *__restrict__ rt, const doub
 // SM = true: per-thread slots in shared memory with stride SM_THREADS (conflict-free): the state proper AND the
 // RK4 stage scratch live there, so that the derivative evaluation -- the only register-hungry part -- runs at
 // 168 registers and 12 warps per SM (3 per scheduler instead of 2) hide each other's FP64 latencies.
-constexpr int FK_SM_THREADS = 384;
+#ifndef FK_SM_THREADS_PER_BLOCK
+#define FK_SM_THREADS_PER_BLOCK 384
+#endif
+#ifndef FK_SM_MIN_BLOCKS
+#define FK_SM_MIN_BLOCKS 1
+#endif
+constexpr int FK_SM_THREADS = FK_SM_THREADS_PER_BLOCK;
 template <int NT>
 constexpr int fk_sm_slots() { return 19 + NT + 9 + 9 + 3 + 3; }   // R v u p L Li | sR aR av au
 
@@ -533,7 +539,7 @@ struct FkArgs {
   int32_t *work;          // dynamic work counter (zero at launch)
 };
 
-#define FK_KERNEL_BOUNDS __launch_bounds__(SM ? FK_SM_THREADS : FK_THREADS, SM ? 1 : FK_MIN_BLOCKS)
+#define FK_KERNEL_BOUNDS __launch_bounds__(SM ? FK_SM_THREADS : FK_THREADS, SM ? FK_SM_MIN_BLOCKS : FK_MIN_BLOCKS)
 
 // Persistent kernel: FK_MIN_BLOCKS CTAs per SM stage the routing table once, then every WARP fetches the next
 // 32 configurations of the bucket order from a global counter until the batch is done (no CTA-wide barrier after
@@ -924,7 +930,7 @@ template <int NT, bool RETRACT, bool SM>
 int launch_k(irt_ctx *ctx, const RobotDev &d, const FkArgs &a, size_t smem, cudaStream_t st) {
   constexpr int THREADS = SM ? FK_SM_THREADS : FK_THREADS;
   int64_t blocks = (a.n + THREADS - 1) / THREADS;
-  const int64_t resident = (int64_t)ctx->sm_count * (SM ? 1 : FK_MIN_BLOCKS);
+  const int64_t resident = (int64_t)ctx->sm_count * (SM ? FK_SM_MIN_BLOCKS : FK_MIN_BLOCKS);
 #if FK_PERSIST
   if (blocks > resident) blocks = resident;
 #else
@@ -945,7 +951,7 @@ int launch_nt(irt_ctx *ctx, const irt_robot *rb, const FkArgs &a, cudaStream_t s
 #if FK_SMEM_VARIANT
   // state in shared memory, 12 warps per SM: when the slots fit beside the routing table
   const size_t smem_sm = smem + (size_t)fk_sm_slots<NT>() * FK_SM_THREADS * sizeof(double);
-  if (ctx->fk_smem && smem_sm <= 227 * 1024)
+  if (ctx->fk_smem && smem_sm * FK_SM_MIN_BLOCKS <= 226 * 1024)
     return d.enable_retraction ? launch_k<NT, true, true>(ctx, d, a, smem_sm, st)
                                : launch_k<NT, false, true>(ctx, d, a, smem_sm, st);
 #endif

@@ -1,8 +1,6 @@
 // fk_api.cu -- C-ABI entry points of the FK path (host-pointer and device-pointer forms).
 #include <cstring>
 
-#include <cub/device/device_scan.cuh>
-
 #include "common.cuh"
 
 namespace {
@@ -14,6 +12,31 @@ struct DevBuf {
   }
   bool alloc(size_t bytes) { return cudaMalloc(&p, bytes ? bytes : 1) == cudaSuccess; }
 };
+
+// off[0] = 0, off[i + 1] = cnt[0] + ... + cnt[i] for one chunk (m <= ~100k rows counts): one CTA, every thread
+// sums a contiguous segment, the 1024 partial sums are scanned in shared memory, then the segments are written
+__global__ void __launch_bounds__(1024) row_offsets_kernel(const int64_t *__restrict__ cnt, int64_t *__restrict__ off,
+                                                           int64_t m) {
+  __shared__ int64_t part[1024];
+  const int t = threadIdx.x;
+  const int64_t per = (m + 1023) / 1024, b = (int64_t)t * per, e = (b + per < m) ? b + per : m;
+  int64_t s = 0;
+  for (int64_t i = b; i < e; i++) s += cnt[i];
+  part[t] = s;
+  __syncthreads();
+  for (int d = 1; d < 1024; d <<= 1) {   // Hillis-Steele inclusive scan
+    const int64_t add = (t >= d) ? part[t - d] : 0;
+    __syncthreads();
+    part[t] += add;
+    __syncthreads();
+  }
+  int64_t acc = part[t] - s;
+  if (t == 0) off[0] = 0;
+  for (int64_t i = b; i < e; i++) {
+    acc += cnt[i];
+    off[i + 1] = acc;
+  }
+}
 
 __global__ void copy_i64_kernel(int64_t *__restrict__ dst, const int64_t *__restrict__ src, int64_t n) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -177,7 +200,6 @@ int irt_fk_batch_packed(irt_ctx *ctx, const irt_robot *rb, const double *states,
   struct Stage {
     double *states, *p, *R, *t, *L, *Li, *tip, *uv;
     int64_t *cnt, *off;
-    void *cub_tmp;
     int32_t *npts, *iters, *nsteps;
     uint32_t *flags;
     int64_t *h_off;  // pinned host copy of off[0..m]
@@ -185,9 +207,6 @@ int irt_fk_batch_packed(irt_ctx *ctx, const irt_robot *rb, const double *states,
   } stage[2];
   std::memset(stage, 0, sizeof(stage));
   const int nstage = (n > chunk) ? 2 : 1;
-  size_t cub_bytes = 0;
-  IRT_CUDA(ctx, cub::DeviceScan::InclusiveSum(nullptr, cub_bytes, (int64_t *)nullptr, (int64_t *)nullptr,
-                                              (int)chunk, st));
   {
     auto carve = [&](char *base, size_t *total) {
       size_t used = 0;
@@ -201,7 +220,6 @@ int irt_fk_batch_packed(irt_ctx *ctx, const irt_robot *rb, const double *states,
         s.states = (double *)take((size_t)chunk * state_size * 8);
         s.cnt = (int64_t *)take((size_t)chunk * 8);
         s.off = (int64_t *)take((size_t)(chunk + 1) * 8);
-        s.cub_tmp = take(cub_bytes + 256);
         s.p = need_p ? (double *)take((size_t)chunk * cap_pts * 24) : nullptr;
         s.R = out->R ? (double *)take((size_t)chunk * cap_pts * 72) : nullptr;
         s.t = out->t ? (double *)take((size_t)chunk * cap_pts * 8) : nullptr;
@@ -237,9 +255,7 @@ int irt_fk_batch_packed(irt_ctx *ctx, const irt_robot *rb, const double *states,
                                   cudaMemcpyHostToDevice, st));
     rc = fk_row_counts(ctx, rb, s.states, m, s.cnt, st);
     if (rc) return rc;
-    IRT_CUDA(ctx, cudaMemsetAsync(s.off, 0, 8, st));
-    size_t tmp_bytes = cub_bytes + 256;
-    IRT_CUDA(ctx, cub::DeviceScan::InclusiveSum(s.cub_tmp, tmp_bytes, s.cnt, s.off + 1, (int)m, st));
+    row_offsets_kernel<<<1, 1024, 0, st>>>(s.cnt, s.off, m);
     IRT_LAUNCHED(ctx);
     // the offsets go to the host through SM stores into page-locked memory, not through the D2H copy
     // engine: a small cudaMemcpyAsync would queue behind the previous chunk's large p copy and hold back

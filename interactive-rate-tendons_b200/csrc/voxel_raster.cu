@@ -127,8 +127,16 @@ struct BlockAcc {
   int bx = -1, by = 0, bz = 0;
   unsigned long long mask = 0ull;
 };
+// Inside the hash a block is keyed by its packed coordinates (two shifts); the Morton key (36 bit operations)
+// is only formed for the occupied blocks of a finished set, ~23 per set instead of ~2 per segment.
+__device__ __forceinline__ uint32_t linear_key(int bx, int by, int bz) {
+  return ((uint32_t)bx << 16) | ((uint32_t)by << 8) | (uint32_t)bz;
+}
+__device__ __forceinline__ uint32_t morton_of_linear(uint32_t k) {
+  return morton_key(k >> 16, (k >> 8) & 0xffu, k & 0xffu);
+}
 __device__ __forceinline__ void flush_block(const WarpHash &h, BlockAcc &acc) {
-  if (acc.mask) hash_insert(h, morton_key((uint32_t)acc.bx, (uint32_t)acc.by, (uint32_t)acc.bz), acc.mask);
+  if (acc.mask) hash_insert(h, linear_key(acc.bx, acc.by, acc.bz), acc.mask);
   acc.mask = 0ull;
 }
 __device__ __forceinline__ void set_cell(const WarpHash &h, BlockAcc &acc, int ix, int iy, int iz) {
@@ -167,7 +175,7 @@ struct PairSink {
   }
   __device__ __forceinline__ void push() {
     if (!acc.mask) return;
-    const uint32_t k = morton_key((uint32_t)acc.bx, (uint32_t)acc.by, (uint32_t)acc.bz);
+    const uint32_t k = linear_key(acc.bx, acc.by, acc.bz);
     bool placed = false;
 #pragma unroll
     for (int i = 0; i < RS_PAIRS; i++) {
@@ -190,17 +198,24 @@ struct PairSink {
   }
   __device__ __forceinline__ void finish() { push(); }
 };
-// all 32 lanes (converged): insert every lane's pairs, one hash access per distinct key and round
+// all 32 lanes (converged): insert every lane's pairs.  Lanes hold consecutive segments, so equal keys sit in
+// adjacent lanes: a segmented OR scan over the lanes (5 shuffle steps) leaves the union of a run of equal keys in
+// its last lane, and only that lane touches the hash.
 __device__ __forceinline__ void warp_insert_pairs(const WarpHash &h, const PairSink &ps) {
+  const int lane = threadIdx.x & 31;
 #pragma unroll
   for (int r = 0; r < RS_PAIRS; r++) {
     const uint32_t k = ps.key[r];
     if (!__any_sync(0xffffffffu, k != RS_EMPTY)) break;
-    const unsigned peers = __match_any_sync(0xffffffffu, k);
-    const uint32_t lo = __reduce_or_sync(peers, (uint32_t)ps.mask[r]);
-    const uint32_t hi = __reduce_or_sync(peers, (uint32_t)(ps.mask[r] >> 32));
-    if (k != RS_EMPTY && (__ffs(peers) - 1) == (int)(threadIdx.x & 31))
-      hash_insert(h, k, ((unsigned long long)hi << 32) | lo);
+    uint32_t lo = (uint32_t)ps.mask[r], hi = (uint32_t)(ps.mask[r] >> 32);
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const uint32_t ok = __shfl_up_sync(0xffffffffu, k, d);
+      const uint32_t olo = __shfl_up_sync(0xffffffffu, lo, d), ohi = __shfl_up_sync(0xffffffffu, hi, d);
+      if (lane >= d && ok == k) { lo |= olo; hi |= ohi; }
+    }
+    const uint32_t nk = __shfl_down_sync(0xffffffffu, k, 1);
+    if (k != RS_EMPTY && (lane == 31 || nk != k)) hash_insert(h, k, ((unsigned long long)hi << 32) | lo);
   }
 }
 struct EnvSink {
@@ -523,7 +538,7 @@ swept_voxel_raster_kernel(const GridDev g, const SetSrc src, int64_t set0, int64
         slot_id = w;
         if (over && lane == 0 && set_flags) set_flags[rel] |= IRT_FLAG_CAPACITY;
       }
-      for (int i = lane; i < cnt; i += 32) dk[i] = h.keys[h.list[i]];
+      for (int i = lane; i < cnt; i += 32) dk[i] = morton_of_linear(h.keys[h.list[i]]);
       __syncwarp();
       // rank sort by key == the reference's visit_leaves order
       uint32_t *sk = slot_keys + slot_id * H;

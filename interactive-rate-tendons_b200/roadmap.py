@@ -397,8 +397,10 @@ class VoxelCachedLazyPRM:
             return np.zeros(0, dtype=bool)
         lo, hi = self.shard(n_total)
         w = shard_words(n_total, self.world)
-        use_cuda = torch.cuda.is_available()
-        dev = torch.device("cuda", self.ctx.device) if use_cuda else torch.device("cpu")
+        # the verdict words live where the store's K3 writes them: on this rank's GPU (a store may name another
+        # device through `words_device`; the product's SetStore does not)
+        dev = torch.device(getattr(store, "words_device", None) or ("cuda:%d" % self.ctx.device))
+        use_cuda = dev.type == "cuda"
         fused = (use_cuda and self.world > 1 and self.dist is not None and self.dist.is_initialized()
                  and self.dist.get_backend() == "nccl" and self.fused_gather)
         if fused:
@@ -680,6 +682,8 @@ class VoxelCachedLazyPRM:
         import torch
         if n_total == 0:
             return np.zeros(0, dtype=bool)
+        if self.dist is None or self.world == 1:     # one rank holds everything: nothing to pack or exchange
+            return (np.asarray(local_flags) & mask) != 0
         lo, hi = self.shard(n_total)
         w = shard_words(n_total, self.world)
         bits = np.zeros(w * 32, dtype=np.uint8)
@@ -688,8 +692,8 @@ class VoxelCachedLazyPRM:
         if self.dist is None or self.world == 1:
             allw = words
         else:
-            use_cuda = torch.cuda.is_available() and self.dist.get_backend() == "nccl"
-            dev = torch.device("cuda", self.ctx.device) if use_cuda else torch.device("cpu")
+            # the flag bits travel over the process group's own transport (NCCL: device tensors)
+            dev = torch.device("cuda", self.ctx.device) if self.dist.get_backend() == "nccl" else torch.device("cpu")
             t = torch.from_numpy(words.view(np.int32).copy()).to(dev)
             allw = gather_verdict_words(t, self.dist).cpu().numpy().view(np.uint32)
         return assemble_verdicts(allw, n_total, self.world)

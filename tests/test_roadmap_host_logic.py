@@ -29,6 +29,8 @@ class _Env:
 
 
 class _Store:
+    words_device = "cpu"     # this stand-in's "K3" writes its verdict words into host tensors
+
     def __init__(self, orc, ogrid):
         self.orc, self.ogrid, self.store, self.calls = orc, ogrid, None, 0
 
