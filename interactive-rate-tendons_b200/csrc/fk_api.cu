@@ -13,28 +13,41 @@ struct DevBuf {
   bool alloc(size_t bytes) { return cudaMalloc(&p, bytes ? bytes : 1) == cudaSuccess; }
 };
 
-// off[0] = 0, off[i + 1] = cnt[0] + ... + cnt[i] for one chunk (m <= ~100k rows counts): one CTA, every thread
-// sums a contiguous segment, the 1024 partial sums are scanned in shared memory, then the segments are written
+// off[0] = 0, off[i + 1] = cnt[0] + ... + cnt[i] for one chunk (m <= ~100k row counts): one CTA walks the array
+// in tiles of 1024 (coalesced loads), scans a tile with warp shuffles and carries the running total
 __global__ void __launch_bounds__(1024) row_offsets_kernel(const int64_t *__restrict__ cnt, int64_t *__restrict__ off,
                                                            int64_t m) {
-  __shared__ int64_t part[1024];
-  const int t = threadIdx.x;
-  const int64_t per = (m + 1023) / 1024, b = (int64_t)t * per, e = (b + per < m) ? b + per : m;
-  int64_t s = 0;
-  for (int64_t i = b; i < e; i++) s += cnt[i];
-  part[t] = s;
+  __shared__ int64_t wsum[32];
+  __shared__ int64_t carry_s;
+  const int t = threadIdx.x, lane = t & 31, w = t >> 5;
+  if (t == 0) { off[0] = 0; carry_s = 0; }
   __syncthreads();
-  for (int d = 1; d < 1024; d <<= 1) {   // Hillis-Steele inclusive scan
-    const int64_t add = (t >= d) ? part[t - d] : 0;
+  for (int64_t base = 0; base < m; base += 1024) {
+    const int64_t i = base + t;
+    int64_t v = (i < m) ? cnt[i] : 0;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {          // inclusive scan inside the warp
+      const int64_t o = __shfl_up_sync(0xffffffffu, v, d);
+      if (lane >= d) v += o;
+    }
+    if (lane == 31) wsum[w] = v;
     __syncthreads();
-    part[t] += add;
+    if (w == 0) {                               // scan of the 32 warp totals
+      int64_t s = wsum[lane];
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        const int64_t o = __shfl_up_sync(0xffffffffu, s, d);
+        if (lane >= d) s += o;
+      }
+      wsum[lane] = s;
+    }
     __syncthreads();
-  }
-  int64_t acc = part[t] - s;
-  if (t == 0) off[0] = 0;
-  for (int64_t i = b; i < e; i++) {
-    acc += cnt[i];
-    off[i + 1] = acc;
+    const int64_t carry = carry_s;
+    const int64_t incl = carry + v + (w ? wsum[w - 1] : 0);
+    if (i < m) off[i + 1] = incl;
+    __syncthreads();
+    if (t == 1023) carry_s = incl;
+    __syncthreads();
   }
 }
 

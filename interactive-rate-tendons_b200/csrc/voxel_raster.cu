@@ -256,19 +256,21 @@ __device__ bool segment_aabox_intersect(const D3 &A, const D3 &B, const D3 &C, c
 template <typename Sink>
 __device__ void add_line(const GridDev &g, Sink &sink, const D3 &a, const D3 &b) {
   const D3 ll = {g.lo[0], g.lo[1], g.lo[2]}, ur = {g.hi[0], g.hi[1], g.hi[2]};
-  // A segment whose endpoints both lie inside the grid box (by a safety margin of a ten-thousandth
-  // of a cell) intersects it: the reference's separating-axis test cannot report otherwise, so it
-  // is only evaluated for segments that touch or leave the box.
-  const double mx = 1e-4 * g.d[0], my = 1e-4 * g.d[1], mz = 1e-4 * g.d[2];
-  const bool inside = a.x > ll.x + mx && a.x < ur.x - mx && b.x > ll.x + mx && b.x < ur.x - mx &&
-                      a.y > ll.y + my && a.y < ur.y - my && b.y > ll.y + my && b.y < ur.y - my &&
-                      a.z > ll.z + mz && a.z < ur.z - mz && b.z > ll.z + mz && b.z < ur.z - mz;
-  if (!inside && !segment_aabox_intersect(a, b, ll, ur)) return;
+  // A segment whose endpoints both lie well inside the grid box intersects it: the reference's
+  // separating-axis test cannot report otherwise, so it is only evaluated for segments near or outside the faces.
   const D3 A = {(a.x - ll.x) * g.inv_d[0], (a.y - ll.y) * g.inv_d[1], (a.z - ll.z) * g.inv_d[2]};
   const D3 B = {(b.x - ll.x) * g.inv_d[0], (b.y - ll.y) * g.inv_d[1], (b.z - ll.z) * g.inv_d[2]};
   const int Axi = (int)A.x - (A.x < 0), Ayi = (int)A.y - (A.y < 0), Azi = (int)A.z - (A.z < 0);
   const int Bxi = (int)B.x - (B.x < 0), Byi = (int)B.y - (B.y < 0), Bzi = (int)B.z - (B.z < 0);
   const int N = g.Ng;
+  {
+    // both endpoints in INTERIOR cells (not the outermost layer): the segment lies inside the grid box by a
+    // whole cell, so it intersects it (integer compares instead of 12 FP64 ones)
+    const unsigned lim = (unsigned)(N - 2);
+    const bool inside = (unsigned)(Axi - 1) < lim && (unsigned)(Ayi - 1) < lim && (unsigned)(Azi - 1) < lim &&
+                        (unsigned)(Bxi - 1) < lim && (unsigned)(Byi - 1) < lim && (unsigned)(Bzi - 1) < lim;
+    if (!inside && !segment_aabox_intersect(a, b, ll, ur)) return;
+  }
 #define IDX_IN(v) (0 <= (v) && (v) < N)
 #define VOX_IN(x, y, z) (IDX_IN(x) && IDX_IN(y) && IDX_IN(z))
   bool entered = VOX_IN(Axi, Ayi, Azi);
@@ -1506,9 +1508,12 @@ static int voxelize_edges_core(irt_ctx *ctx, const irt_robot *rb, const irt_spac
   chunk = (n + nchunks - 1) / nchunks;
   const int nlanes = nchunks > 1 ? 2 : 1;
   int64_t cap_mid = chunk * mids_per_edge;
-  if (n <= 65536) {   // small calls: room for long edges (dozens of samples each) as far as the budget goes
-    const int64_t room = (int64_t)(avail / nlanes / per_mid);
-    cap_mid = std::max<int64_t>(cap_mid, std::min<int64_t>(std::max<int64_t>(chunk * 64, 4096), room));
+  {
+    // calls that do not need the whole budget take more room per edge: up to 8 mid samples per edge (sparse
+    // roadmaps have long edges), 64 for small calls (single long edges need dozens of samples)
+    const int64_t room = (int64_t)((avail - std::min(avail, (size_t)nlanes * chunk * per_edge)) / nlanes / per_mid) + cap_mid;
+    const int64_t want = (n <= 65536) ? std::max<int64_t>(chunk * 64, 4096) : chunk * 8;
+    cap_mid = std::max<int64_t>(cap_mid, std::min<int64_t>(want, room));
   }
   if (cap_mid > 0x3fffffff) cap_mid = 0x3fffffff;
   const int64_t cap_q = std::max<int64_t>(chunk, 2 * cap_mid);
@@ -1636,14 +1641,22 @@ static int voxelize_edges_core(irt_ctx *ctx, const irt_robot *rb, const irt_spac
     for (auto &o : J.outs) cudaEventDestroy(o.ev);
     return code;
   };
+  // Chunks are sized by the sample pool: est_mpe = mid samples an edge needs (3 to begin with, then what the
+  // finished chunks needed); a chunk whose pool overflows anyway is re-cut by what it turned out to need.
+  double est_mpe = (double)mids_per_edge;
   for (;;) {
     rc = drain_outputs(J, false);   // finished chunks' outputs go to the caller while the GPU works on
     if (rc) return fail(rc);
     while (!idle.empty() && !todo.empty()) {
       Lane *L = idle.back();
       idle.pop_back();
-      const auto w = todo.back();
+      auto w = todo.back();
       todo.pop_back();
+      const int64_t fit = std::max<int64_t>(256, (int64_t)((double)cap_mid / (est_mpe * 1.1)));
+      if (w.second > fit && w.second > 256) {   // more edges than the pool is expected to hold: take a part
+        todo.emplace_back(w.first + fit, w.second - fit);
+        w.second = fit;
+      }
       rc = issue_bisection(J, *L, w.first, (int32_t)w.second);
       if (rc) return fail(rc);
       auto it = inflight.begin();
@@ -1657,10 +1670,14 @@ static int voxelize_edges_core(irt_ctx *ctx, const irt_robot *rb, const irt_spac
     rc = finish_bisection(J, *L, &overflow);
     if (rc) return fail(rc);
     tr.point("bisection done", L->h_C[C_NMID]);
-    if (overflow && L->E > 256) {   // redo this range as two halves, before anything that follows it
-      const int64_t h1 = L->E / 2;
-      todo.emplace_back(L->off + h1, L->E - h1);
-      todo.emplace_back(L->off, h1);
+    {
+      // C_NMID keeps counting past the pool size, so an overflowed chunk still tells (a lower bound of) its need
+      const double seen = (double)L->h_C[C_NMID] / (double)std::max<int32_t>(L->E, 1);
+      est_mpe = overflow ? std::max(est_mpe, seen) * 1.3 : std::max(0.5 * est_mpe, seen);
+      if (est_mpe < 0.25) est_mpe = 0.25;
+    }
+    if (overflow && L->E > 256) {   // redo this range (the issue loop re-cuts it), before anything that follows it
+      todo.emplace_back(L->off, L->E);
       idle.push_back(L);
       continue;
     }

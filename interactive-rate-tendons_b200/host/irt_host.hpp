@@ -27,9 +27,13 @@
 #include <cstring>
 #include <functional>
 #include <map>
+#include <condition_variable>
 #include <limits>
 #include <memory>
+#include <mutex>
+#include <optional>
 #include <queue>
+#include <thread>
 #include <random>
 #include <set>
 #include <stdexcept>
@@ -356,6 +360,87 @@ inline std::vector<std::vector<double>> levmar_jacobian_batch(const tendon::Tend
                                                               const std::vector<std::vector<double>> &states,
                                                               std::vector<collision::Point> *tips = nullptr) {
   return Jacobian_batch(robot, delta, states, tips, IRT_JAC_LEVMAR_CENTRAL);
+}
+
+/// Batching layer under k IK solvers that run side by side: every solver asks for the tip and the
+/// finite-difference tip Jacobian of ONE state at a time, like the reference's ikController_ does through fk_wrap
+/// (tip-control/tip_control.cpp:92-122); the requests of all solvers that are still running are answered by ONE
+/// irt_fk_tip_jacobian_batch call.  The solvers stay sequential host code, one thread each.
+class LockstepFk {
+public:
+  struct Eval { collision::Point tip; std::vector<double> J; };   // J row-major 3 x S
+  LockstepFk(const tendon::TendonRobot &robot, size_t workers, int mode, double delta)
+      : robot_(robot), mode_(mode), delta_(delta), active_(workers), results_(workers), asked_(workers, 0) {}
+  Eval evaluate(size_t worker, const std::vector<double> &state) {
+    std::unique_lock<std::mutex> lk(mu_);
+    pending_.emplace_back(worker, state);
+    const size_t gen = generation_;
+    if (pending_.size() == active_) flush();
+    else cv_.wait(lk, [&] { return generation_ != gen; });
+    return results_[worker];
+  }
+  void finished(size_t) {
+    std::unique_lock<std::mutex> lk(mu_);
+    active_--;
+    if (active_ > 0 && pending_.size() == active_) flush();
+  }
+  size_t batches() const { return batches_; }
+  size_t requests() const { return requests_; }
+
+private:
+  void flush() {   // lock held
+    std::vector<std::vector<double>> states;
+    for (auto &p : pending_) states.push_back(p.second);
+    std::vector<collision::Point> tips;
+    auto Js = Jacobian_batch(robot_, delta_, states, &tips, mode_);
+    for (size_t i = 0; i < pending_.size(); i++) results_[pending_[i].first] = Eval{tips[i], Js[i]};
+    requests_ += pending_.size();
+    batches_++;
+    pending_.clear();
+    generation_++;
+    cv_.notify_all();
+  }
+  const tendon::TendonRobot &robot_;
+  int mode_;
+  double delta_;
+  size_t active_;
+  std::vector<Eval> results_;
+  std::vector<char> asked_;
+  std::vector<std::pair<size_t, std::vector<double>>> pending_;
+  std::mutex mu_;
+  std::condition_variable cv_;
+  size_t generation_ = 0, batches_ = 0, requests_ = 0;
+};
+
+/// the reference's ikController_: (start state, requested tip, fk) -> final state; fk(state) -> tip + Jacobian
+using IkSolver = std::function<std::vector<double>(const std::vector<double> &, const collision::Point &,
+                                                   const std::function<LockstepFk::Eval(const std::vector<double> &)> &)>;
+
+/// runs the solver for every start state side by side (one host thread each), FK requests answered in lockstep
+inline std::vector<std::vector<double>> solve_ik_lockstep(const tendon::TendonRobot &robot, const IkSolver &solver,
+                                                          const std::vector<std::vector<double>> &starts,
+                                                          const collision::Point &request, int mode, double delta,
+                                                          size_t *batches = nullptr, size_t *requests = nullptr) {
+  const size_t k = starts.size();
+  LockstepFk fk(robot, k, mode, delta);
+  std::vector<std::vector<double>> out(k);
+  std::vector<std::exception_ptr> err(k);
+  std::vector<std::thread> th;
+  for (size_t i = 0; i < k; i++)
+    th.emplace_back([&, i] {
+      try {
+        out[i] = solver(starts[i], request, [&fk, i](const std::vector<double> &st) { return fk.evaluate(i, st); });
+      } catch (...) {
+        err[i] = std::current_exception();   // a failing solver must not leave the others waiting for it
+      }
+      fk.finished(i);
+    });
+  for (auto &t : th) t.join();
+  for (auto &e : err)
+    if (e) std::rethrow_exception(e);
+  if (batches) *batches = fk.batches();
+  if (requests) *requests = fk.requests();
+  return out;
 }
 
 }  // namespace tip_control
@@ -1217,6 +1302,86 @@ public:
   collision::VoxelOctree edgeVoxels(size_t i) const { return collision::VoxelOctree::from_store(ctx_, estore_, (int64_t)i, env_voxels_); }
   const std::vector<uint32_t> &vertexFlags() const { return vflags_; }
   const std::vector<uint32_t> &edgeFlags() const { return eflags_; }
+
+  // ---- roadmapIk as a batch (.cpp:3095-3420) ---------------------------------------------------------------
+  struct IKResult {                 // VoxelCachedLazyPRM.h:356-362
+    std::vector<double> controls;   // valid state at or close to the desired tip position
+    collision::Point tip_position;  // tip position obtained by controls
+    std::vector<double> neighbor;   // where IK started from
+    double error = 0.0;             // achieved tip-position error
+    size_t index = 0, vertex = 0;   // which of the k neighbours (nearest first) / its roadmap vertex
+    size_t lockstep_batches = 0, fk_requests = 0;
+    bool accepted = true;           // false: no result within tolerance, the closest valid one is returned
+  };
+  /// nnTip_->nearestK: the k vertices whose cached tip positions are nearest to the request (exact)
+  std::vector<size_t> nearestTips(const collision::Point &request, size_t k) {
+    if (tips_.size() != 3 * states_.size()) precomputeVertexVoxelCache();
+    build_adjacency();
+    std::vector<std::pair<double, size_t>> d;
+    for (size_t v = 0; v < states_.size(); v++) {
+      if (vertex_removed_[v]) continue;
+      double s = 0.0;
+      for (int c = 0; c < 3; c++) s += (tips_[3 * v + c] - request[c]) * (tips_[3 * v + c] - request[c]);
+      d.emplace_back(std::sqrt(s), v);
+    }
+    k = std::min(k, d.size());
+    std::partial_sort(d.begin(), d.begin() + k, d.end());
+    std::vector<size_t> out;
+    for (size_t i = 0; i < k; i++) out.push_back(d[i].second);
+    return out;
+  }
+  /// roadmapIk(request, tolerance, k) of the reference (RMAP_IK_SIMPLE) with its per-neighbour loop turned into
+  /// batches: the k nearest VALID neighbours in tip space (invalid ones are removed and the query repeated;
+  /// validity = table look-ups), the k IK problems solved side by side with their FK requests answered in
+  /// lockstep (tip_control::solve_ik_lockstep), ONE FK + is_valid_shape + voxelise + collides call over the k
+  /// results, acceptance in the reference's order: the first neighbour (nearest first) whose result is valid and
+  /// within tolerance; failing that the closest valid result; std::nullopt when every result is invalid (the
+  /// reference then steps back along the edges; see the Python mirror for that branch and for RMAP_IK_AUTO_ADD).
+  std::optional<IKResult> roadmapIk(const collision::Point &request, double tolerance, size_t k,
+                                    const tip_control::IkSolver &solver, int mode = IRT_JAC_LEVMAR_CENTRAL,
+                                    double delta = 1e-6) {
+    std::vector<size_t> nb;
+    for (;;) {
+      nb = nearestTips(request, k);
+      if (nb.empty()) throw std::runtime_error("roadmapIk(): No neighbors were able to be found");
+      bool removed = false;
+      for (size_t v : nb)
+        if (!computeVertexValidity(v)) { vertex_removed_[v] = 1; removed = true; }
+      if (!removed) break;
+    }
+    std::vector<std::vector<double>> starts;
+    for (size_t v : nb) starts.push_back(states_[v]);
+    size_t batches = 0, requests = 0;
+    auto finals = tip_control::solve_ik_lockstep(robot_, solver, starts, request, mode, delta, &batches, &requests);
+    // one validity call over the k results
+    const size_t S = robot_.state_size(), m = finals.size();
+    std::vector<double> flat(m * S), tips(3 * m);
+    for (size_t i = 0; i < m; i++) std::copy(finals[i].begin(), finals[i].end(), flat.begin() + i * S);
+    std::vector<uint32_t> flags(m), words((m + 31) / 32 + 1, 0);
+    irt_setstore *scratch = nullptr;
+    irt_grid g = env_voxels_.grid(venv_.inv_rotation);
+    irt::check(ctx_, irt_setstore_create(ctx_, &g, &scratch));
+    std::shared_ptr<irt_setstore> guard(scratch, [](irt_setstore *x) { irt_setstore_destroy(x); });
+    irt::check(ctx_, irt_voxelize_vertices(ctx_, robot_.handle(), flat.data(), (int)S, (int64_t)m, scratch,
+                                           flags.data(), tips.data()));
+    irt::check(ctx_, irt_check_sets(ctx_, scratch, env_, 0, (int64_t)m, words.data()));
+    const uint32_t bad = IRT_FLAG_NONCONVERGED | IRT_FLAG_LENGTH_LIMIT | IRT_FLAG_SELF_COLLISION | IRT_FLAG_BAD_STATE;
+    std::optional<IKResult> best;
+    for (size_t i = 0; i < m; i++) {
+      const bool valid = !(flags[i] & bad) && !((words[i >> 5] >> (i & 31)) & 1u);
+      double e2 = 0.0;
+      for (int c = 0; c < 3; c++) e2 += (tips[3 * i + c] - request[c]) * (tips[3 * i + c] - request[c]);
+      IKResult r;
+      r.controls = finals[i]; r.tip_position = {tips[3 * i], tips[3 * i + 1], tips[3 * i + 2]};
+      r.neighbor = starts[i]; r.error = std::sqrt(e2); r.index = i; r.vertex = nb[i];
+      r.lockstep_batches = batches; r.fk_requests = requests;
+      if (!valid) continue;
+      if (r.error < tolerance) return r;                       // "we've found a good one!"
+      r.accepted = false;
+      if (!best || r.error < best->error) best = r;            // "returning closest valid one"
+    }
+    return best;
+  }
 
 private:
   size_t removed_count() const {

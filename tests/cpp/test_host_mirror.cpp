@@ -389,6 +389,79 @@ int main() {
                 prm.lookupCount(), prm.sweepCount());
     prm.restoreRemoved();
   }
+  {  // roadmapIk as a batch (VoxelCachedLazyPRM.cpp:3095-3205): k IK solvers side by side, FK requests in lockstep
+    const double Lr = robot.specs.L, delta = 1e-6;
+    tip_control::IkSolver dls = [&](const std::vector<double> &start, const collision::Point &req,
+                                    const std::function<tip_control::LockstepFk::Eval(const std::vector<double> &)> &fk) {
+      std::vector<double> x = start;   // damped least squares with box clamping (stands in for ikController_)
+      for (int it = 0; it < 20; it++) {
+        auto ev = fk(x);
+        double e[3] = {req[0] - ev.tip[0], req[1] - ev.tip[1], req[2] - ev.tip[2]};
+        if (std::sqrt(e[0] * e[0] + e[1] * e[1] + e[2] * e[2]) < 1e-7) break;
+        double A[3][3];
+        for (int r = 0; r < 3; r++)
+          for (int c = 0; c < 3; c++) {
+            A[r][c] = (r == c) ? 1e-8 : 0.0;
+            for (int j = 0; j < 8; j++) A[r][c] += ev.J[r * 8 + j] * ev.J[c * 8 + j];
+          }
+        const double det = A[0][0] * (A[1][1] * A[2][2] - A[1][2] * A[2][1]) - A[0][1] * (A[1][0] * A[2][2] - A[1][2] * A[2][0]) +
+                           A[0][2] * (A[1][0] * A[2][1] - A[1][1] * A[2][0]);
+        double y[3];
+        for (int c = 0; c < 3; c++) {   // Cramer
+          double B[3][3];
+          for (int r = 0; r < 3; r++) for (int q = 0; q < 3; q++) B[r][q] = (q == c) ? e[r] : A[r][q];
+          y[c] = (B[0][0] * (B[1][1] * B[2][2] - B[1][2] * B[2][1]) - B[0][1] * (B[1][0] * B[2][2] - B[1][2] * B[2][0]) +
+                  B[0][2] * (B[1][0] * B[2][1] - B[1][1] * B[2][0])) / det;
+        }
+        for (int j = 0; j < 8; j++) {
+          x[j] += ev.J[0 * 8 + j] * y[0] + ev.J[1 * 8 + j] * y[1] + ev.J[2 * 8 + j] * y[2];
+          const double lo = (j == 6) ? -M_PI : 0.0, hi = (j < 6) ? 20.0 : (j == 6 ? M_PI : Lr);
+          x[j] = std::min(hi, std::max(lo, x[j]));
+        }
+      }
+      return x;
+    };
+    std::vector<double> goal = verts[10];
+    for (int j = 0; j < 6; j++) goal[j] = std::min(20.0, goal[j] + 0.4);
+    collision::Point request = robot.forward_kinematics(goal).back();
+    auto res = prm.roadmapIk(request, 1e-4, 4, dls, IRT_JAC_LEVMAR_CENTRAL, delta);
+    CHECK(res.has_value());
+    if (res) {
+      CHECK(res->lockstep_batches > 0 && res->lockstep_batches < res->fk_requests);   // requests shared launches
+      // the reference's loop: neighbour by neighbour, nearest first, the same solver over single-state FK calls
+      auto nb = prm.nearestTips(request, 4);
+      long want = -1, best = -1;
+      double best_err = 0.0;
+      std::vector<std::vector<double>> seq;
+      for (size_t i = 0; i < nb.size(); i++) {
+        auto fin = dls(verts[nb[i]], request, [&](const std::vector<double> &st) {
+          std::vector<collision::Point> tp;
+          auto J = tip_control::Jacobian_batch(robot, delta, {st}, &tp, IRT_JAC_LEVMAR_CENTRAL);
+          return tip_control::LockstepFk::Eval{tp[0], J[0]};
+        });
+        seq.push_back(fin);
+        std::vector<double> t(512), p(512 * 3);
+        orc_fk_out fo;
+        int n = orc_shape(&orb, fin.data(), 512, t.data(), p.data(), nullptr, &fo);
+        uint32_t f = orc_validity_flags(&orb, fin.data(), &fo, p.data());
+        orc_octree *ov = orc_octree_new(&og);
+        if (f == 0) orc_voxelize_shape(&og, p.data(), n, ov);
+        const bool ok = (f == 0) && orc_octree_collides(oenv, ov) != 1;
+        orc_octree_free(ov);
+        double err = 0.0;
+        for (int c = 0; c < 3; c++) err += (p[3 * (n - 1) + c] - request[c]) * (p[3 * (n - 1) + c] - request[c]);
+        err = std::sqrt(err);
+        if (ok && err < 1e-4 && want < 0) want = (long)i;
+        if (ok && (best < 0 || err < best_err)) { best = (long)i; best_err = err; }
+      }
+      const long expect = want >= 0 ? want : best;
+      CHECK(expect >= 0 && (long)res->index == expect && res->accepted == (want >= 0));
+      if (expect >= 0) CHECK(res->controls == seq[(size_t)expect]);   // lockstep batching changes no iterate
+      std::printf("roadmapIk: neighbour #%zu accepted=%d error %.3g, %zu lockstep batches for %zu FK requests\n",
+                  res->index, (int)res->accepted, res->error, res->lockstep_batches, res->fk_requests);
+    }
+    prm.restoreRemoved();
+  }
   prm.clearValidity();
   for (auto v : prm.edgeValidity()) CHECK(v == 0);
   // environment swap: empty environment -> everything with a valid shape becomes valid
