@@ -432,7 +432,7 @@ class VoxelCachedLazyPRM:
         n = len(self.states)
         collides = self._sweep(self.vertex_store, n, self.vertex_flags)
         invalid = self._gather_flags(self.vertex_flags, n, INVALID_MASK)
-        self.vertex_validity = np.where(~collides & ~invalid, VALIDITY_TRUE, VALIDITY_UNKNOWN).astype(np.uint8)
+        self.vertex_validity = np.logical_not(collides | invalid).view(np.uint8)   # VALIDITY_TRUE = 1, UNKNOWN = 0
         self._vertex_swept = True
         self.lookups["sweeps"] += 1
         return self.vertex_validity
@@ -444,7 +444,7 @@ class VoxelCachedLazyPRM:
         n = len(self.edges)
         collides = self._sweep(self.edge_store, n, self.edge_flags)
         invalid = self._gather_flags(self.edge_flags, n, FLAG_PARTIAL)
-        self.edge_validity = np.where(~collides & ~invalid, VALIDITY_TRUE, VALIDITY_UNKNOWN).astype(np.uint8)
+        self.edge_validity = np.logical_not(collides | invalid).view(np.uint8)     # VALIDITY_TRUE = 1, UNKNOWN = 0
         self._edge_swept = True
         self.lookups["sweeps"] += 1
         return self.edge_validity
