@@ -18,6 +18,11 @@
  *     must be serialised by the caller (the reference calls its validators from many OpenMP
  *     threads, one item each -- here one call carries the whole batch).  Different contexts,
  *     robots, stores and environments can be used from different host threads concurrently.
+ *     The "_dev" calls keep their per-call temporaries (bucket keys and order of K1, perturbed states
+ *     of the Jacobian batch, candidate lists of the self-collision test) in that per-context scratch:
+ *     all "_dev" calls on one context must therefore be STREAM-ORDERED with each other (same stream,
+ *     or an event between them); two of them running concurrently on different streams would share
+ *     the temporaries.  Use one context per concurrent stream.
  *   - there is NO CPU fallback: without a CUDA device irt_ctx_create fails with
  *     IRT_ERR_NO_DEVICE and nothing else can be called.
  *   - per-item problems (non-convergence, limits, ...) are NOT errors: they are reported in a
@@ -318,8 +323,9 @@ int irt_check_sets_popcount(irt_ctx *ctx, const irt_setstore *store, const irt_e
 /* ---- multi-GPU: verdict all-gather fused into K3 over peer memory (NVLink / NVSwitch) -----------
  * One process per GPU.  Every rank creates an exchange buffer, publishes its handle (host-side
  * all-gather of irt_xchg_handle_size() bytes, e.g. with torch.distributed / MPI) and connects.  A
- * sweep then stores every verdict word straight into all peers' copies of the gathered array and
- * raises a per-rank epoch flag; a one-warp kernel on the same stream waits for all flags.  Replaces
+ * sweep then stores every verdict word straight into all peers' copies of the gathered array; its
+ * last CTA raises this rank's epoch flag on every peer and waits (bounded) for the peers' flags, so
+ * the gathered array is complete when the sweep kernel ends -- ONE launch per sweep.  Replaces
  * K3 + ncclAllGather of the verdict words (VoxelCachedLazyPRM.cpp:1584-1591 sharded over GPUs).
  * slot_words = words every rank contributes (the same on all ranks, >= ceil(shard sets / 32)). */
 typedef struct irt_xchg irt_xchg;

@@ -108,6 +108,12 @@ __device__ __forceinline__ ulonglong2 ld_stream(const ulonglong2 *p) {
 // every peer's copy; the last CTA to finish raises this rank's epoch flag on every peer.  No NCCL call,
 // no extra kernel between the sweep and its consumers except a one-warp flag wait.
 constexpr int IRT_MAX_PEERS = 16;
+// 1: a CTA publishes its peer stores towards the LAST CTA with a gpu-scope fence and only the last CTA pays a
+// system-scope fence before the flags (-6 us per sweep: MEMBAR.SYS twice in a row on the critical path was ~10 us);
+// 0: every CTA fences at system scope
+#ifndef K3_CTA_FENCE_GPU
+#define K3_CTA_FENCE_GPU 1
+#endif
 struct XchgDev {
   uint32_t *peer[IRT_MAX_PEERS];  // base of every rank's buffer as mapped in THIS process (own: local)
   int world, rank, parity;
@@ -128,25 +134,34 @@ struct XchgDev {
   }
 };
 
-// last-CTA epilogue of a gathering kernel: data stores of all CTAs happen-before the flag stores; the same CTA
-// then waits (bounded) until every peer's flag of this sweep has arrived in this rank's buffer, so that when
-// the kernel ends the gathered array is complete: no separate wait kernel.  (Every rank's kernel runs on its own
-// GPU; nothing here waits for another launch on the same device.)
+// last-CTA epilogue of a gathering kernel.  Ordering (PTX memory model, causality order is transitive across
+// scopes): a CTA's peer stores -> CTA barrier -> thread 0: fence.gpu + atomicAdd(done)  [release at gpu scope]
+// -> last CTA: atomicAdd observes all + fence.sys  [acquire at gpu scope, and the fence is cumulative]
+// -> st.relaxed.sys flags  [release at sys scope] -> a peer's ld.acquire.sys of the flag.  The same CTA then waits
+// (bounded) until every peer's flag of this sweep has arrived in this rank's buffer, so that when the kernel ends
+// the gathered array is complete: no separate wait kernel.  (Every rank's kernel runs on its own GPU; nothing here
+// waits for another launch on the same device.)
 __device__ __forceinline__ void xchg_signal(const XchgDev &x) {
-  // the CTA barrier orders every thread's peer stores before thread 0's system-scope fence (fences are
-  // cumulative), so ONE fence per CTA publishes them all: 256 per-thread MEMBAR.SYS cost ~10 us per sweep
+  // the CTA barrier orders every thread's peer stores before thread 0's fence (fences are cumulative), so ONE
+  // fence per CTA publishes them all
   __shared__ int s_last;
   __syncthreads();
   if (threadIdx.x == 0) {
+#if K3_CTA_FENCE_GPU
+    __threadfence();
+#else
     __threadfence_system();
+#endif
     const unsigned prev = atomicAdd(x.done, 1u);
     s_last = (prev == gridDim.x - 1);
     if (s_last) {
       x.done[0] = 0;   // CTA counter and tile counter are ready for the next sweep
       x.done[2] = 0;
+      // release pattern with ONE fence: fence.sys, then relaxed system-scope flag stores.  (st.release.sys is a
+      // fence per store: with 8 peers the last CTA would sit through 7 more NVLink round trips.)
       __threadfence_system();
       for (int r = 0; r < x.world; r++)
-        asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(x.flag(r)), "r"(x.epoch) : "memory");
+        asm volatile("st.relaxed.sys.global.u32 [%0], %1;" ::"l"(x.flag(r)), "r"(x.epoch) : "memory");
     }
   }
   __syncthreads();

@@ -49,6 +49,33 @@ struct Trace {
   }
 };
 
+// IRT_B200_TRACE=2: device timeline of the K2 pipeline -- timing events recorded on the lanes' streams (nothing
+// synchronises until the call is over), printed relative to the first mark (debugging / profiling only)
+struct Timeline {
+  struct Mark { cudaEvent_t ev; const char *label; int lane; long long v; };
+  bool on;
+  std::vector<Mark> marks;
+  Timeline() { const char *e = getenv("IRT_B200_TRACE"); on = e && e[0] == '2'; }
+  void mark(cudaStream_t st, const char *label, int lane, long long v = -1) {
+    if (!on) return;
+    cudaEvent_t ev;
+    if (cudaEventCreate(&ev) != cudaSuccess) return;
+    cudaEventRecord(ev, st);
+    marks.push_back({ev, label, lane, v});
+  }
+  void print() {
+    if (!on || marks.empty()) return;
+    cudaDeviceSynchronize();
+    for (auto &m : marks) {
+      float ms = 0.f;
+      cudaEventElapsedTime(&ms, marks[0].ev, m.ev);
+      std::fprintf(stderr, "[irt timeline] %9.3f ms  lane %d  %-18s %lld\n", ms, m.lane, m.label, m.v);
+    }
+    for (auto &m : marks) cudaEventDestroy(m.ev);
+    marks.clear();
+  }
+};
+
 #ifndef RS_FAST_TRAVERSAL
 #define RS_FAST_TRAVERSAL 1
 #endif
@@ -1258,6 +1285,7 @@ struct Lane {
   int32_t E = 0;
   int q_cur = 0;
   int rounds = 0;
+  int id = 0;
 };
 
 struct EdgeJob {
@@ -1286,6 +1314,7 @@ struct EdgeJob {
   double *u_tlast = nullptr, *h_tlast = nullptr;
   int32_t *u_nsamp = nullptr, *h_nsamp = nullptr;
   std::vector<OutJob> outs;
+  Timeline tl;
 };
 
 // copies finished chunks' outputs from the staging to the caller's arrays; block = wait for all of them
@@ -1339,6 +1368,7 @@ int issue_round(EdgeJob &J, Lane &L) {
   IRT_CUDA(ctx, cudaGetLastError());
   L.q_cur = qn;
   L.rounds++;
+  J.tl.mark(st, "round end", L.id, L.rounds);
   return IRT_OK;
 }
 
@@ -1347,6 +1377,7 @@ int issue_bisection(EdgeJob &J, Lane &L, int64_t off, int32_t E) {
   irt_ctx *ctx = J.ctx;
   cudaStream_t st = L.st;
   L.off = off; L.E = E; L.P.E = E; L.q_cur = 0; L.rounds = 0;
+  J.tl.mark(st, "bisection begin", L.id, off);
   IRT_CUDA(ctx, cudaMemsetAsync(L.C, 0, C_WORDS * 4, st));
   if (J.indexed) {
     L.P.pairs = J.d_pairs_all + 2 * off;
@@ -1413,6 +1444,7 @@ int issue_raster(EdgeJob &J, Lane &L) {
   IRT_LAUNCHED(ctx);
   // the leaf offsets chain through *d_running: raster phases run in chunk order
   if (J.raster_pending) IRT_CUDA(ctx, cudaStreamWaitEvent(st, J.ev_raster, 0));
+  J.tl.mark(st, "raster begin", L.id, L.off);
   SetSrc src;
   std::memset(&src, 0, sizeof(src));
   src.edge_mode = 1; src.P = L.P; src.tlimit = L.tlimit; src.cap_pts = J.cap;
@@ -1421,6 +1453,7 @@ int issue_raster(EdgeJob &J, Lane &L) {
                          L.off, J.tot.d_running, J.tot.d_overflow, st);
   if (rc) return rc;
   IRT_CUDA(ctx, cudaEventRecord(J.ev_raster, st));
+  J.tl.mark(st, "raster end", L.id, L.h_C[C_NMID]);
   J.raster_pending = true;
   J.mids_total += std::min(L.h_C[C_NMID], L.P.cap_mid);
   if (J.u_flags || J.u_tlast || J.u_nsamp) {
@@ -1578,6 +1611,7 @@ static int voxelize_edges_core(irt_ctx *ctx, const irt_robot *rb, const irt_spac
   double *h_vstates = (double *)(pin + pin_c + pin_out + pin_pairs);
   for (int l = 0; l < nlanes; l++) {
     Lane &L = lanes[l];
+    L.id = l;
     L.st = l == 0 ? ctx->stream : ctx->copy_stream;
     L.ev_bisect = ctx->ev_computed[l];
     L.h_C = h_C + l * C_WORDS;
@@ -1595,6 +1629,7 @@ static int voxelize_edges_core(irt_ctx *ctx, const irt_robot *rb, const irt_spac
   rc = J.tot.reset(ctx, s0);
   if (rc) return rc;
   tr.point("layout", cap_mid);
+  J.tl.mark(s0, "start", 0, n);
 
   // ---- indexed form: FK of every roadmap vertex once; edges read their endpoint shapes from it ------
   if (indexed) {
@@ -1627,6 +1662,7 @@ static int voxelize_edges_core(irt_ctx *ctx, const irt_robot *rb, const irt_spac
   IRT_CUDA(ctx, cudaEventRecord(ctx->ev_offsets[0], s0));
   if (nlanes > 1) IRT_CUDA(ctx, cudaStreamWaitEvent(lanes[1].st, ctx->ev_offsets[0], 0));
   tr.point("vertex fk issued", nv);
+  J.tl.mark(s0, "vertex fk end", 0, nv);
 
   // ---- chunks: up to two in flight, rastered in index order ----------------------------------------
   std::vector<std::pair<int64_t, int64_t>> todo;   // (offset, count), lowest offset LAST (a stack)
@@ -1699,6 +1735,8 @@ static int voxelize_edges_core(irt_ctx *ctx, const irt_robot *rb, const irt_spac
   rc = J.tot.read(ctx, s0, &total, &overflow);
   if (rc) return fail(rc);
   tr.point("raster + d2h done", (long long)total);
+  J.tl.mark(s0, "all done", 0, (long long)total);
+  J.tl.print();
   if (overflow) {   // the store was too small for the leaves: now their number is known, run again
     if ((int64_t)total <= est_blocks) return irt_fail(ctx, IRT_ERR_CAPACITY, "set store overflow");
     return voxelize_edges_core(ctx, rb, space, a, b, vstates, nv, pairs, state_size, n, env, store, flags, t_last,

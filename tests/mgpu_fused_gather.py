@@ -96,6 +96,26 @@ def main():
         res[name + "_sum"] = int(out.to(torch.int64).abs().sum().item())
     assert x.status() == 0
     assert torch.equal(fused().cpu(), nccl().cpu())
+    # stress of the flag protocol: back-to-back sweeps against three rotating environments (so the slot of this
+    # parity holds a DIFFERENT environment's words from two sweeps ago), the gathered table read on the device
+    # right behind every sweep, no host synchronisation in between; a peer store that became visible after its
+    # flag would leave a stale word
+    envs, expect = [], []
+    for i in range(3):
+        e = irt_b200.Env(ctx, grid)
+        e.update(wl.toggle_blob(env0, g, np.array([0.03 * (i - 1), 0.0, 0.1]), 0.015 + 0.004 * i))
+        envs.append(e)
+        prm.edge_store.check_dev(e, d_words, 0, hi - lo, stream=stream.cuda_stream)
+        expect.append(gather_verdict_words(d_words, dist).clone())
+    assert not torch.equal(expect[0], expect[1]) and not torch.equal(expect[1], expect[2])
+    bad = torch.zeros((), dtype=torch.int64, device=dev)
+    sweeps = int(os.environ.get("MGPU_STRESS_SWEEPS", "600"))
+    for k in range(sweeps):
+        out = x.check(prm.edge_store, envs[k % 3], 0, hi - lo, stream=stream.cuda_stream)
+        bad += (out != expect[k % 3]).sum()
+    torch.cuda.synchronize()
+    assert x.status() == 0
+    assert int(bad.item()) == 0, "stale verdict words in %d places over %d sweeps" % (int(bad.item()), sweeps)
     if rank == 0:
         print("MGPU_OK world=%d vertices=%d edges=%d fused %.4f ms nccl %.4f ms per edge sweep"
               % (world, nv, ne, res["fused"], res["nccl"]), flush=True)
