@@ -743,8 +743,8 @@ def write_rmp(path, d):
 
 
 def unpack_verdicts(words, n):
-    bits = np.unpackbits(np.ascontiguousarray(words, dtype=np.uint32).view(np.uint8), bitorder="little")
-    return bits[:n].astype(bool)
+    w8 = np.ascontiguousarray(words, dtype=np.uint32).view(np.uint8)
+    return np.unpackbits(w8, count=n, bitorder="little").view(bool)   # bytes 0 / 1: a bool view, no copy
 
 
 def shard_range(n, rank, world, align=64):

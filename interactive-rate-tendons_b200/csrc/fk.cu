@@ -41,6 +41,9 @@ constexpr int FK_THREADS = FK_THREADS_PER_BLOCK;
 #ifndef FK_PERSIST
 #define FK_PERSIST 1
 #endif
+#ifndef FK_PIPELINE_TENDONS
+#define FK_PIPELINE_TENDONS 0
+#endif
 #ifndef FK_SMEM_VARIANT
 #define FK_SMEM_VARIANT 0
 #endif
@@ -177,17 +180,43 @@ __device__ __forceinline__ void vu_dot(const double *__restrict__ rt, const doub
   double h00 = 0, h01 = 0, h02 = 0, h11 = 0, h12 = 0, h22 = 0;
   double av0 = 0, av1 = 0, av2 = 0, bv0 = 0, bv1 = 0, bv2 = 0;
   double esum = 0, erx = 0, ery = 0, exx = 0, eyy = 0, exy = 0;
+#if FK_PIPELINE_TENDONS
+  // software pipeline over the tendons: the latency chain of tendon j+1 (q -> |q|^2 -> rsqrt seed -> two Newton
+  // steps, ~12 dependent FP64 operations) is started BEFORE the ~70 independent accumulations of tendon j, so the
+  // two overlap inside one warp (with 2 warps per scheduler there is nobody else to hide it)
+  double nqx, nqy, nqz, ns2, nrs;
+  {
+    const double rx = rt[0], ry = rt[1], dx = rt[2], dy = rt[3];
+    nqx = fma(-u[2], ry, dx + v[0]);
+    nqy = fma(u[2], rx, dy + v[1]);
+    nqz = fma(u[0], ry, fma(-u[1], rx, v[2]));
+    ns2 = fma(nqx, nqx, fma(nqy, nqy, nqz * nqz));
+    nrs = rsqrt_fast(ns2);
+  }
+#endif
 #pragma unroll
   for (int j = 0; j < NT; j++) {
     const double rx = rt[6 * j + 0], ry = rt[6 * j + 1];
     const double dx = rt[6 * j + 2], dy = rt[6 * j + 3];
     const double ddx = rt[6 * j + 4], ddy = rt[6 * j + 5];
+#if FK_PIPELINE_TENDONS
+    const double qx = nqx, qy = nqy, qz = nqz, s2 = ns2, rs = nrs;
+    if (j + 1 < NT) {
+      const double rx1 = rt[6 * j + 6], ry1 = rt[6 * j + 7], dx1 = rt[6 * j + 8], dy1 = rt[6 * j + 9];
+      nqx = fma(-u[2], ry1, dx1 + v[0]);
+      nqy = fma(u[2], rx1, dy1 + v[1]);
+      nqz = fma(u[0], ry1, fma(-u[1], rx1, v[2]));
+      ns2 = fma(nqx, nqx, fma(nqy, nqy, nqz * nqz));
+      nrs = rsqrt_fast(ns2);
+    }
+#else
     // q = u x r + r' + v        (r_z = r'_z = r''_z = 0)
     const double qx = fma(-u[2], ry, dx + v[0]);
     const double qy = fma(u[2], rx, dy + v[1]);
     const double qz = fma(u[0], ry, fma(-u[1], rx, v[2]));
     const double s2 = fma(qx, qx, fma(qy, qy, qz * qz));
     const double rs = rsqrt_fast(s2);
+#endif
     sig[j] = s2 * rs;
     const double e = tau[j] * rs;        // tau / sigma
     const double c3 = e * (rs * rs);     // tau / sigma^3

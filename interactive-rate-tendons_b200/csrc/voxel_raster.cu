@@ -37,7 +37,7 @@ struct Trace {
   bool on;
   cudaStream_t st;
   std::chrono::steady_clock::time_point t0;
-  explicit Trace(cudaStream_t s) : on(getenv("IRT_B200_TRACE") != nullptr), st(s), t0(std::chrono::steady_clock::now()) {}
+  explicit Trace(cudaStream_t s) : on(getenv("IRT_B200_TRACE") && getenv("IRT_B200_TRACE")[0] == '1'), st(s), t0(std::chrono::steady_clock::now()) {}
   void point(const char *name, long long count = -1) {
     if (!on) return;
     cudaStreamSynchronize(st);
@@ -55,7 +55,13 @@ struct Timeline {
   struct Mark { cudaEvent_t ev; const char *label; int lane; long long v; };
   bool on;
   std::vector<Mark> marks;
+  std::chrono::steady_clock::time_point h0 = std::chrono::steady_clock::now();
   Timeline() { const char *e = getenv("IRT_B200_TRACE"); on = e && e[0] == '2'; }
+  void host(const char *label) {   // host wall-clock since the timeline was created
+    if (!on) return;
+    std::fprintf(stderr, "[irt timeline host] %9.3f ms  %s\n",
+                 std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - h0).count(), label);
+  }
   void mark(cudaStream_t st, const char *label, int lane, long long v = -1) {
     if (!on) return;
     cudaEvent_t ev;
@@ -80,6 +86,9 @@ struct Timeline {
 #define RS_FAST_TRAVERSAL 1
 #endif
 constexpr int RS_WARPS = 4;
+#ifndef RS_MINB
+#define RS_MINB 6   // resident CTAs per SM the main raster pass is compiled for (80 registers; 5 -> 6: -10 %, 7 and 8: no further gain)
+#endif
 constexpr int RS_HLOG_SMALL = 8;     // main pass: 256 hash entries per warp (a set rarely exceeds ~150 blocks)
 constexpr int RS_HLOG_BIG = 12;      // fallback pass for the sets that overflow it: 4096 entries, 1 warp per CTA
 constexpr int RS_SLOT = 1 << RS_HLOG_SMALL;   // slot capacity of the main pass
@@ -190,6 +199,9 @@ struct HashSink {
 // lanes with equal keys merge their masks with a shuffle reduction and ONE lane per distinct key touches the
 // hash -- instead of 4-8 lanes contending for the same shared-memory word with atomicCAS / atomicOr.
 constexpr int RS_PAIRS = 3;
+#ifndef RS_SEGS
+#define RS_SEGS 2   // consecutive segments a lane handles per warp iteration
+#endif
 struct PairSink {
   const WarpHash &h;
   BlockAcc acc;
@@ -201,19 +213,19 @@ struct PairSink {
     for (int i = 0; i < RS_PAIRS; i++) { key[i] = RS_EMPTY; mask[i] = 0ull; }
   }
   __device__ __forceinline__ void push() {
-    if (!acc.mask) return;
+    const unsigned long long m = acc.mask;
+    if (!m) return;
+    acc.mask = 0ull;
     const uint32_t k = linear_key(acc.bx, acc.by, acc.bz);
     bool placed = false;
 #pragma unroll
-    for (int i = 0; i < RS_PAIRS; i++) {
-      if (!placed && (key[i] == k || key[i] == RS_EMPTY)) {
-        key[i] = k;
-        mask[i] |= acc.mask;
-        placed = true;
-      }
+    for (int i = 0; i < RS_PAIRS; i++) {   // selects, not branches: lanes change blocks at different times
+      const bool hit = !placed && (key[i] == k || key[i] == RS_EMPTY);
+      key[i] = hit ? k : key[i];
+      mask[i] |= hit ? m : 0ull;
+      placed = placed || hit;
     }
-    if (!placed) hash_insert(h, k, acc.mask);   // more blocks than slots (a long segment): straight to the hash
-    acc.mask = 0ull;
+    if (!placed) hash_insert(h, k, m);   // more blocks than slots (a long segment): straight to the hash
   }
   __device__ __forceinline__ void cell(int ix, int iy, int iz) {
     const int bx = ix >> 2, by = iy >> 2, bz = iz >> 2;
@@ -300,8 +312,11 @@ __device__ void add_line(const GridDev &g, Sink &sink, const D3 &a, const D3 &b)
   }
 #define IDX_IN(v) (0 <= (v) && (v) < N)
 #define VOX_IN(x, y, z) (IDX_IN(x) && IDX_IN(y) && IDX_IN(z))
-  bool entered = VOX_IN(Axi, Ayi, Azi);
-  if (VOX_IN(Bxi, Byi, Bzi)) sink.cell(Bxi, Byi, Bzi);
+  // cells are emitted in path order A, steps, B (the result is a set; the reference adds B, A, steps): along a
+  // monotone path the 4x4x4 block only changes when a block face is crossed, which keeps the sinks' block
+  // accumulators in registers
+  const bool entered = VOX_IN(Axi, Ayi, Azi);
+  const bool b_in = VOX_IN(Bxi, Byi, Bzi);
   if (entered) sink.cell(Axi, Ayi, Azi);
   D3 U = {B.x - A.x, B.y - A.y, B.z - A.z};
   const double z = (U.x * U.x + U.y * U.y) + U.z * U.z;  // Eigen normalized()
@@ -311,58 +326,49 @@ __device__ void add_line(const GridDev &g, Sink &sink, const D3 &a, const D3 &b)
   // two of them is a comparison of cross products (e_x + k_x) |U_y| <> (e_y + k_y) |U_x|: no square root, no
   // division (1 sqrt + 6 divisions per segment otherwise: ~200 of ~300 FP64 instructions).  The reference's
   // own values carry a few ulp of rounding, so a decision is only taken here when the two sides differ by more
-  // than 1e-12 relative; a closer call, a direction component near the reference's 1e-10 validity threshold, or
-  // a path longer than the recorded 16 steps hands the segment to the literal code below.  The decisions are
-  // found in a dry run first and replayed with cell emission afterwards, so nothing is emitted twice.
+  // than 1e-12 relative; a closer call or a direction component near the reference's 1e-10 validity threshold
+  // hands the segment to the literal code below.  Cells are emitted as the path advances: up to a close call the
+  // decisions are the reference's, so the cells emitted before a hand-over are cells the literal code adds too.
   {
     const double adx = fabs(U.x), ady = fabs(U.y), adz = fabs(U.z);
     const double zhi = 1.0001e-20 * z;   // |U_axis| / n > 1e-10 with margin
-    bool ok = z > 0.0 && adx * adx > zhi && ady * ady > zhi && adz * adz > zhi;
-    if (ok) {
+    if (z > 0.0 && adx * adx > zhi && ady * ady > zhi && adz * adz > zhi) {
       const int sx = 1 - 2 * (U.x < 0), sy = 1 - 2 * (U.y < 0), sz = 1 - 2 * (U.z < 0);
       double Nx = fabs(A.x - (Axi + sx) * g.d[0]);
       double Ny = fabs(A.y - (Ayi + sy) * g.d[1]);
       double Nz = fabs(A.z - (Azi + sz) * g.d[2]);
-      uint32_t seq = 0;
-      int ns = 0;
-      {
-        int xi = Axi, yi = Ayi, zi = Azi;
-        bool ent = entered;
-        while (sx * (Bxi - xi) >= 0 && sy * (Byi - yi) >= 0 && sz * (Bzi - zi) >= 0) {
-          const double xy_l = Nx * ady, xy_r = Ny * adx, xz_l = Nx * adz, xz_r = Nz * adx, yz_l = Ny * adz, yz_r = Nz * ady;
-          const double tol = 1e-12;
-          if (fabs(xy_l - xy_r) <= tol * (xy_l + xy_r) || fabs(xz_l - xz_r) <= tol * (xz_l + xz_r) ||
-              fabs(yz_l - yz_r) <= tol * (yz_l + yz_r) || ns >= 16) {
-            ok = false;
-            break;
-          }
-          const bool tx_is_min = (xy_l < xy_r) && (xz_l < xz_r);
-          const bool ty_is_min = !(xy_l < xy_r) && (yz_l < yz_r);
-          const int axis = tx_is_min ? 0 : (ty_is_min ? 1 : 2);
-          seq |= (uint32_t)axis << (2 * ns);
-          ns++;
-          if (axis == 0) { xi += sx; if (ent && !IDX_IN(xi)) break; Nx += 1.0; }
-          else if (axis == 1) { yi += sy; if (ent && !IDX_IN(yi)) break; Ny += 1.0; }
-          else { zi += sz; if (ent && !IDX_IN(zi)) break; Nz += 1.0; }
-          if (!ent && VOX_IN(xi, yi, zi)) ent = true;
+      int xi = Axi, yi = Ayi, zi = Azi;
+      // steps left on every axis until the path has passed B's cell (the loop runs while none is negative)
+      int rx = sx * (Bxi - Axi), ry = sy * (Byi - Ayi), rz = sz * (Bzi - Azi);
+      bool ent = entered, ok = true;
+      while ((rx | ry | rz) >= 0) {
+        const double xy_l = Nx * ady, xy_r = Ny * adx, xz_l = Nx * adz, xz_r = Nz * adx, yz_l = Ny * adz, yz_r = Nz * ady;
+        const double tol = 1e-12;
+        if (fabs(xy_l - xy_r) <= tol * (xy_l + xy_r) || fabs(xz_l - xz_r) <= tol * (xz_l + xz_r) ||
+            fabs(yz_l - yz_r) <= tol * (yz_l + yz_r)) {
+          ok = false;
+          break;
         }
+        const bool ax0 = (xy_l < xy_r) && (xz_l < xz_r);            // tx is the minimum
+        const bool ax1 = !ax0 && !(xy_l < xy_r) && (yz_l < yz_r);   // ty is
+        const bool ax2 = !ax0 && !ax1;
+        xi += ax0 ? sx : 0; yi += ax1 ? sy : 0; zi += ax2 ? sz : 0;
+        rx -= ax0 ? 1 : 0; ry -= ax1 ? 1 : 0; rz -= ax2 ? 1 : 0;
+        const int moved = ax0 ? xi : (ax1 ? yi : zi);
+        if (ent && !IDX_IN(moved)) break;
+        Nx = ax0 ? Nx + 1.0 : Nx; Ny = ax1 ? Ny + 1.0 : Ny; Nz = ax2 ? Nz + 1.0 : Nz;
+        if (!ent) ent = VOX_IN(xi, yi, zi);
+        if (ent) sink.cell(xi, yi, zi);
       }
-      if (ok) {   // replay
-        int xi = Axi, yi = Ayi, zi = Azi;
-        for (int k = 0; k < ns; k++) {
-          const int axis = (seq >> (2 * k)) & 3;
-          if (axis == 0) { xi += sx; if (entered && !IDX_IN(xi)) break; }
-          else if (axis == 1) { yi += sy; if (entered && !IDX_IN(yi)) break; }
-          else { zi += sz; if (entered && !IDX_IN(zi)) break; }
-          if (!entered && VOX_IN(xi, yi, zi)) entered = true;
-          if (entered) sink.cell(xi, yi, zi);
-        }
+      if (ok) {
+        if (b_in) sink.cell(Bxi, Byi, Bzi);
         sink.finish();
         return;
       }
     }
   }
 #endif
+  bool entered_l = entered;
   if (z > 0.0) {
     const double n = sqrt(z);
     U.x /= n; U.y /= n; U.z /= n;
@@ -383,20 +389,21 @@ __device__ void add_line(const GridDev &g, Sink &sink, const D3 &a, const D3 &b)
     const bool ty_is_min = !(tx < ty) && (ty < tz);
     if (tx_is_min) {
       xi += step_x;
-      if (entered && !IDX_IN(xi)) break;
+      if (entered_l && !IDX_IN(xi)) break;
       tx += tx_delta;
     } else if (ty_is_min) {
       yi += step_y;
-      if (entered && !IDX_IN(yi)) break;
+      if (entered_l && !IDX_IN(yi)) break;
       ty += ty_delta;
     } else {
       zi += step_z;
-      if (entered && !IDX_IN(zi)) break;
+      if (entered_l && !IDX_IN(zi)) break;
       tz += tz_delta;
     }
-    if (!entered && VOX_IN(xi, yi, zi)) entered = true;
-    if (entered) sink.cell(xi, yi, zi);
+    if (!entered_l && VOX_IN(xi, yi, zi)) entered_l = true;
+    if (entered_l) sink.cell(xi, yi, zi);
   }
+  if (b_in) sink.cell(Bxi, Byi, Bzi);
   sink.finish();
 #undef IDX_IN
 #undef VOX_IN
@@ -464,7 +471,7 @@ struct SetSrc {
 // the device) with one warp per CTA and writes into the big slots.  Per-set arrays (counts, t_last,
 // nsamples, set_flags, ovf_slot) are indexed relative to set0.
 template <int HLOG, int WARPS>
-__global__ void __launch_bounds__(WARPS * 32, WARPS == 1 ? 1 : 5)
+__global__ void __launch_bounds__(WARPS * 32, WARPS == 1 ? 1 : RS_MINB)
 swept_voxel_raster_kernel(const GridDev g, const SetSrc src, int64_t set0, int64_t nsets,
                           uint32_t *__restrict__ counts, double *__restrict__ t_last,
                           int32_t *__restrict__ nsamples, uint32_t *__restrict__ slot_keys,
@@ -533,18 +540,28 @@ swept_voxel_raster_kernel(const GridDev g, const SetSrc src, int64_t set0, int64
       }
     }
     __syncwarp();
-    // pass 2: lanes take consecutive segments of the concatenated polylines; the warp inserts the blocks of
-    // its 32 segments together
+    // pass 2: a lane takes RS_SEGS consecutive segments of the concatenated polylines per iteration (the point
+    // two segments of one sample share is transformed once; the block accumulator runs across both), then the
+    // warp inserts the blocks of its 32 * RS_SEGS segments together
     {
       int k = 0;   // sample cursor: f only grows, so the sample a lane's segment belongs to only moves forward
-      for (int f0 = 0; f0 < total; f0 += 32) {
-        const int f = f0 + lane;
+      for (int f0 = 0; f0 < total; f0 += 32 * RS_SEGS) {
         PairSink sink(h);
-        if (f < total) {
-          while (k + 1 < nsm && lc[k + 1] <= f) k++;
-          const int i = f - lc[k] + 1;  // segment (i-1, i) of sample k
-          const double *sp = lp[k];
-          add_line(g, sink, rotate_pt(g, sp + 3 * (i - 1)), rotate_pt(g, sp + 3 * i));
+        D3 prev = {0.0, 0.0, 0.0};
+        bool have_prev = false;
+#pragma unroll 1
+        for (int sgm = 0; sgm < RS_SEGS; sgm++) {
+          const int f = f0 + RS_SEGS * lane + sgm;
+          if (f < total) {
+            while (k + 1 < nsm && lc[k + 1] <= f) { k++; have_prev = false; }
+            const int i = f - lc[k] + 1;  // segment (i-1, i) of sample k
+            const double *sp = lp[k];
+            const D3 a = have_prev ? prev : rotate_pt(g, sp + 3 * (i - 1));
+            const D3 b = rotate_pt(g, sp + 3 * i);
+            add_line(g, sink, a, b);
+            prev = b;
+            have_prev = true;
+          }
         }
         warp_insert_pairs(h, sink);
       }
@@ -1629,6 +1646,7 @@ static int voxelize_edges_core(irt_ctx *ctx, const irt_robot *rb, const irt_spac
   rc = J.tot.reset(ctx, s0);
   if (rc) return rc;
   tr.point("layout", cap_mid);
+  J.tl.host("layout done");
   J.tl.mark(s0, "start", 0, n);
 
   // ---- indexed form: FK of every roadmap vertex once; edges read their endpoint shapes from it ------
@@ -1663,6 +1681,7 @@ static int voxelize_edges_core(irt_ctx *ctx, const irt_robot *rb, const irt_spac
   if (nlanes > 1) IRT_CUDA(ctx, cudaStreamWaitEvent(lanes[1].st, ctx->ev_offsets[0], 0));
   tr.point("vertex fk issued", nv);
   J.tl.mark(s0, "vertex fk end", 0, nv);
+  J.tl.host("vertex fk + pair upload issued");
 
   // ---- chunks: up to two in flight, rastered in index order ----------------------------------------
   std::vector<std::pair<int64_t, int64_t>> todo;   // (offset, count), lowest offset LAST (a stack)
@@ -1726,8 +1745,10 @@ static int voxelize_edges_core(irt_ctx *ctx, const irt_robot *rb, const irt_spac
     IRT_CUDA(ctx, cudaEventRecord(ctx->ev_offsets[1], lanes[1].st));
     IRT_CUDA(ctx, cudaStreamWaitEvent(s0, ctx->ev_offsets[1], 0));
   }
+  J.tl.host("everything issued");
   rc = drain_outputs(J, true);
   if (rc) return fail(rc);
+  J.tl.host("outputs drained");
   for (auto &o : J.outs) cudaEventDestroy(o.ev);
   J.outs.clear();
   uint64_t total = 0;
@@ -1736,6 +1757,7 @@ static int voxelize_edges_core(irt_ctx *ctx, const irt_robot *rb, const irt_spac
   if (rc) return fail(rc);
   tr.point("raster + d2h done", (long long)total);
   J.tl.mark(s0, "all done", 0, (long long)total);
+  J.tl.host("totals read");
   J.tl.print();
   if (overflow) {   // the store was too small for the leaves: now their number is known, run again
     if ((int64_t)total <= est_blocks) return irt_fail(ctx, IRT_ERR_CAPACITY, "set store overflow");

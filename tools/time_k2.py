@@ -23,5 +23,6 @@ if "--pairwise" in sys.argv:
     t0 = time.perf_counter(); store.voxelize_edges(rb, irt_b200.make_space(), a, b); dt = time.perf_counter() - t0
     print("pairwise edges %d: %.3f s" % (len(pairs), dt))
 vs = irt_b200.SetStore(ctx, grid)
-t0 = time.perf_counter(); vs.voxelize_vertices(rb, st); dt = time.perf_counter() - t0
-print("vertices %d: %.3f s" % (nv, dt))
+for rep in range(2):
+    t0 = time.perf_counter(); vs.voxelize_vertices(rb, st); dt = time.perf_counter() - t0
+    print("vertices %d: %.3f s" % (nv, dt))
