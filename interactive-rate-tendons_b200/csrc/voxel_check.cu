@@ -104,9 +104,10 @@ __device__ __forceinline__ ulonglong2 ld_stream(const ulonglong2 *p) {
 }
 
 // Verdict exchange fused into K3 (multi-GPU): every rank holds the gathered verdict array of ALL ranks
-// in a buffer its peers can write (CUDA IPC over NVLink).  A warp stores its verdict word straight into
-// every peer's copy; the last CTA to finish raises this rank's epoch flag on every peer.  No NCCL call,
-// no extra kernel between the sweep and its consumers except a one-warp flag wait.
+// in a buffer its peers can write (CUDA IPC over NVLink).  A CTA stages the verdict words of its finished tiles
+// and stores them as 32-byte runs straight into every peer's copy; the last CTA to finish raises this rank's
+// epoch flag on every peer and waits for the peers' flags.  No NCCL call, no extra kernel between the sweep and
+// its consumers.
 constexpr int IRT_MAX_PEERS = 16;
 // 1: a CTA publishes its peer stores towards the LAST CTA with a gpu-scope fence and only the last CTA pays a
 // system-scope fence before the flags (-6 us per sweep: MEMBAR.SYS twice in a row on the critical path was ~10 us);
