@@ -960,6 +960,78 @@ def test_fused_verdict_exchange_single_rank_and_empty_shard(irt, ctx, orc, wl):
     assert not x2.check(empty, env, 0, 0).cpu().numpy().any() and x2.status() == 0
 
 
+def test_raster_arbitrary_segments_vs_oracle(irt, ctx, orc, wl):
+    """K2's rasteriser on polylines that are NOT backbones (irt_voxelize_shapes): the golden segments of every kind
+    (short, long across / past the grid, axis-aligned, zero-length, on cell faces, near-degenerate directions:
+    tests/golden/reference_vectors.npz, generated with the reference's own add_line) as two-point shapes, and random
+    polylines of long steps that cross many blocks (division-free traversal over paths of any length, hand-over to
+    the literal code on close calls, block accumulator across segments, hash overflow into the big-table pass).
+    Leaves and bits equal to the oracle's add_piecewise_line, in visit_leaves order."""
+    import os
+    gold = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "reference_vectors.npz"))
+    lim = gold["vo_lim"].tolist()
+    Ng, Nb = 128, 32
+    rng = np.random.default_rng(77)
+    shapes = [np.array(sg) for sg in gold["vo_segs"]]
+    dxv = (lim[1] - lim[0]) / Ng
+    for i in range(400):
+        crossing = i >= 380                      # the last 20: 20-30 long steps through the grid, > 192 blocks
+        n = int(rng.integers(20, 31)) if crossing else int(rng.integers(2, 13))
+        pts = [rng.uniform(-0.24, 0.24, 3)]
+        for _ in range(n - 1):
+            kind = 1 if crossing else int(rng.integers(0, 6))
+            a = pts[-1]
+            if kind == 0:
+                b = a + rng.normal(size=3) * 0.004
+            elif kind == 1:
+                b = rng.uniform(-0.3, 0.3, 3)
+            elif kind == 2:
+                b = a.copy(); b[rng.integers(0, 3)] += rng.uniform(-0.2, 0.2)
+            elif kind == 3:
+                b = a.copy()
+            elif kind == 4:
+                b = np.round(a / dxv) * dxv + rng.integers(-6, 7, 3) * dxv
+            else:
+                b = a + rng.uniform(-1, 1, 3) * np.array([1e-12, 0.08, 1e-11])[rng.permutation(3)]
+            pts.append(b)
+        shapes.append(np.array(pts))
+    cap = max(len(sh) for sh in shapes)
+    p = np.zeros((len(shapes), cap, 3))
+    npts = np.zeros(len(shapes), dtype=np.int32)
+    for i, sh in enumerate(shapes):
+        p[i, :len(sh)] = sh
+        npts[i] = len(sh)
+    store = irt.SetStore(ctx, irt.make_grid(Ng, lim))
+    store.voxelize_shapes(p, npts)
+    off, keys, bits = store.export_csr()
+    og = orc.grid(Ng, lim)
+    flips = 0
+    for i, sh in enumerate(shapes):
+        t = orc.octree(og)
+        t.add_piecewise_line(sh)
+        xyz, rbits = t.export()
+        rkeys = wl.morton_key(xyz[:, 0].astype(np.int64), xyz[:, 1].astype(np.int64), xyz[:, 2].astype(np.int64), Nb) \
+            if len(xyz) else np.zeros(0, dtype=np.uint32)
+        gk, gb = keys[int(off[i]):int(off[i + 1])], bits[int(off[i]):int(off[i + 1])]
+        if not (np.array_equal(gk, np.asarray(rkeys, dtype=np.uint32)) and np.array_equal(gb, rbits)):
+            flips += 1
+    assert flips == 0, "%d of %d polylines differ from the oracle's add_piecewise_line" % (flips, len(shapes))
+    nblk = np.diff(off.astype(np.int64))
+    assert nblk.max() > 192, "no shape reached the big-table pass (%d blocks at most)" % nblk.max()
+    # the golden groups (three segments per tree, leaves written by the reference's add_line): union of the three
+    # single-segment sets
+    goff = gold["vo_leaf_off"]
+    for k in range(0, 600, 3):
+        acc = {}
+        for i in range(k, k + 3):
+            for kk, bb in zip(keys[int(off[i]):int(off[i + 1])], bits[int(off[i]):int(off[i + 1])]):
+                acc[int(kk)] = acc.get(int(kk), 0) | int(bb)
+        xyz = gold["vo_leaf_xyz"][goff[k // 3]:goff[k // 3 + 1]].astype(np.int64)
+        want = dict(zip(wl.morton_key(xyz[:, 0], xyz[:, 1], xyz[:, 2], Nb).tolist() if len(xyz) else [],
+                        gold["vo_leaf_bits"][goff[k // 3]:goff[k // 3 + 1]].tolist()))
+        assert acc == want, "golden group %d" % (k // 3)
+
+
 def test_pinned_staging_survives_io_growth(irt, ctx, wl):
     """packed(small) -> dense(large) -> packed(small) on ONE context.  Growing the device
     staging buffer used to free the pinned row-offset buffer and leave the dangling pointer in the context."""
