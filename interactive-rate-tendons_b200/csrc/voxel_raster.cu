@@ -86,6 +86,9 @@ struct Timeline {
 #define RS_FAST_TRAVERSAL 1
 #endif
 constexpr int RS_WARPS = 4;
+#ifndef ES_MINB
+#define ES_MINB 4   // resident CTAs per SM of the subdivision test
+#endif
 #ifndef RS_MINB
 #define RS_MINB 6   // resident CTAs per SM the main raster pass is compiled for (80 registers; 5 -> 6: -10 %, 7 and 8: no further gain)
 #endif
@@ -896,55 +899,96 @@ __device__ __forceinline__ bool find_cell(const GridDev &g, const D3 &p, long lo
   return true;
 }
 
-// should_subdivide(a, b) -- VoxelEnvironment.cpp:304-341, warp-cooperative (lanes over points,
-// scanned from the tip like the reference so the first event found is the same one)
-__device__ bool should_subdivide(const GridDev &g, const EdgePool &P, int32_t edge, int32_t ra, int32_t rb,
-                                 int lane) {
-  if (smp_flags(P, edge, ra) & INVALID_MASK) return false;
-  const int na = smp_npts(P, edge, ra), nb = smp_npts(P, edge, rb);
-  if (na + 1 < nb || na > nb + 1) return true;
-  const int Pn = min(na, nb);
-  const double *pa = smp_pts(P, edge, ra), *pb = smp_pts(P, edge, rb);
-  for (int top = Pn - 1; top >= 0; top -= 32) {
-    const int i = top - lane;
-    int ev = 0;  // 1 = far apart, 2 = domain error
-    if (i >= 0) {
-      long long s[3], e[3];
-      const D3 qa = rotate_pt(g, pa + 3 * i), qb = rotate_pt(g, pb + 3 * i);
-      const bool in_a = !(qa.x < g.lo[0] || g.hi[0] < qa.x || qa.y < g.lo[1] || g.hi[1] < qa.y || qa.z < g.lo[2] || g.hi[2] < qa.z);
-      const bool in_b = !(qb.x < g.lo[0] || g.hi[0] < qb.x || qb.y < g.lo[1] || g.hi[1] < qb.y || qb.z < g.lo[2] || g.hi[2] < qb.z);
-      const double tight = 1.0 - 1e-9;
-      if (!in_a || !in_b) {
-        ev = 2;
-      } else if (fabs(qa.x - qb.x) < g.d[0] * tight && fabs(qa.y - qb.y) < g.d[1] * tight &&
-                 fabs(qa.z - qb.z) < g.d[2] * tight) {
-        // two points less than one cell apart on every axis: their cells differ by at most 1 (the common case at
-        // the last bisection level) -- no need to locate them
-      } else {
-        find_cell(g, qa, s);
-        find_cell(g, qb, e);
-        const long long dx = llabs(s[0] - e[0]), dy = llabs(s[1] - e[1]), dz = llabs(s[2] - e[2]);
-        if (dx > 1 || dy > 1 || dz > 1) ev = 1;
-      }
+// should_subdivide(a, b) -- VoxelEnvironment.cpp:304-341, warp-cooperative: lanes over points, scanned from the
+// tip like the reference so the first event found is the same one.  A bisected interval needs TWO such tests
+// (a, m) and (m, b) (VoxelEnvironment.cpp:350-353, 386-397); the kernel is bound by memory latency (a chain of
+// sample header -> points of the top 32 nodes -> next 32 ...), so both tests of an interval run in ONE loop with
+// all their loads issued together: 3 dependent rounds per interval instead of 6.
+struct SmpView {
+  const double *p;
+  int n;
+  uint32_t flags;
+};
+__device__ __forceinline__ SmpView smp_view(const EdgePool &P, int32_t edge, int32_t ref) {
+  SmpView s;
+  if (ref >= 0) {
+    s.p = P.m_p + (int64_t)ref * P.cap_pts * 3; s.n = P.m_npts[ref]; s.flags = P.m_flags[ref];
+  } else {
+    const int64_t v = end_vertex(P, edge, ref);
+    s.p = P.v_p + v * P.cap_pts * 3; s.n = P.v_npts[v]; s.flags = P.v_flags[v];
+  }
+  return s;
+}
+// event of one point pair: 0 = cells at most 1 apart, 1 = far apart, 2 = domain error (a point outside the grid)
+__device__ __forceinline__ int pair_event(const GridDev &g, const D3 &ra, const D3 &rb) {
+  const double pa[3] = {ra.x, ra.y, ra.z}, pb[3] = {rb.x, rb.y, rb.z};
+  const D3 qa = rotate_pt(g, pa), qb = rotate_pt(g, pb);
+  const bool in_a = !(qa.x < g.lo[0] || g.hi[0] < qa.x || qa.y < g.lo[1] || g.hi[1] < qa.y || qa.z < g.lo[2] || g.hi[2] < qa.z);
+  const bool in_b = !(qb.x < g.lo[0] || g.hi[0] < qb.x || qb.y < g.lo[1] || g.hi[1] < qb.y || qb.z < g.lo[2] || g.hi[2] < qb.z);
+  const double tight = 1.0 - 1e-9;
+  if (!in_a || !in_b) return 2;
+  // two points less than one cell apart on every axis: their cells differ by at most 1 (the common case at the
+  // last bisection level) -- no need to locate them
+  if (fabs(qa.x - qb.x) < g.d[0] * tight && fabs(qa.y - qb.y) < g.d[1] * tight && fabs(qa.z - qb.z) < g.d[2] * tight)
+    return 0;
+  long long s[3], e[3];
+  find_cell(g, qa, s);
+  find_cell(g, qb, e);
+  const long long dx = llabs(s[0] - e[0]), dy = llabs(s[1] - e[1]), dz = llabs(s[2] - e[2]);
+  return (dx > 1 || dy > 1 || dz > 1) ? 1 : 0;
+}
+// up to two tests at once: test 0 = (x0, y0), test 1 = (x1, y1); run[t] selects; res[t] = should_subdivide
+__device__ __forceinline__ void should_subdivide2(const GridDev &g, const EdgePool &P, int32_t edge, const SmpView &x0,
+                                                  const SmpView &y0, const SmpView &x1, const SmpView &y1, bool run0,
+                                                  bool run1, int lane, bool &res0, bool &res1) {
+  res0 = res1 = false;
+  bool live0 = run0 && !(x0.flags & INVALID_MASK), live1 = run1 && !(x1.flags & INVALID_MASK);
+  if (live0 && (x0.n + 1 < y0.n || x0.n > y0.n + 1)) { res0 = true; live0 = false; }
+  if (live1 && (x1.n + 1 < y1.n || x1.n > y1.n + 1)) { res1 = true; live1 = false; }
+  int top0 = min(x0.n, y0.n) - 1, top1 = min(x1.n, y1.n) - 1;
+  if (top0 < 0) live0 = false;
+  if (top1 < 0) live1 = false;
+  while (live0 || live1) {   // warp-uniform
+    const int i0 = top0 - lane, i1 = top1 - lane;
+    // all twelve coordinates of this round are requested before any of them is looked at
+    const bool act0 = live0 && i0 >= 0, act1 = live1 && i1 >= 0;
+    const D3 zero = {0.0, 0.0, 0.0};
+    D3 xa = zero, ya = zero, xb = zero, yb = zero;
+    if (act0) {
+      const double *px = x0.p + 3 * i0, *py = y0.p + 3 * i0;
+      xa = {px[0], px[1], px[2]}; ya = {py[0], py[1], py[2]};
     }
-    const unsigned m = __ballot_sync(0xffffffffu, ev != 0);
-    if (m) {
-      const int first = __ffs(m) - 1;  // lane 0 holds the highest index
-      const int fev = __shfl_sync(0xffffffffu, ev, first);
-      if (fev == 2) {
-        if (lane == 0) atomicOr(&P.eflags[edge], IRT_FLAG_OUT_OF_DOMAIN);
-        return false;
-      }
-      return true;
+    if (act1) {
+      const double *px = x1.p + 3 * i1, *py = y1.p + 3 * i1;
+      xb = {px[0], px[1], px[2]}; yb = {py[0], py[1], py[2]};
+    }
+    const int ev0 = act0 ? pair_event(g, xa, ya) : 0;
+    const int ev1 = act1 ? pair_event(g, xb, yb) : 0;
+    const unsigned m0 = __ballot_sync(0xffffffffu, ev0 != 0), m1 = __ballot_sync(0xffffffffu, ev1 != 0);
+    if (live0) {
+      if (m0) {
+        const int fev = __shfl_sync(0xffffffffu, ev0, __ffs(m0) - 1);   // lane 0 holds the highest index
+        if (fev == 2) { if (lane == 0) atomicOr(&P.eflags[edge], IRT_FLAG_OUT_OF_DOMAIN); }
+        else res0 = true;
+        live0 = false;
+      } else if ((top0 -= 32) < 0) live0 = false;
+    }
+    if (live1) {
+      if (m1) {
+        const int fev = __shfl_sync(0xffffffffu, ev1, __ffs(m1) - 1);
+        if (fev == 2) { if (lane == 0) atomicOr(&P.eflags[edge], IRT_FLAG_OUT_OF_DOMAIN); }
+        else res1 = true;
+        live1 = false;
+      } else if ((top1 -= 32) < 0) live1 = false;
     }
   }
-  return false;
 }
 
 // one warp per candidate: round 0 tests the whole edge (a, b); later rounds test both halves of a bisected
 // interval (VoxelEnvironment.cpp:350-353,386-397)
-__global__ void edge_subdivide_kernel(const GridDev g, EdgePool P, const Pending *__restrict__ pend,
-                                      int32_t *__restrict__ C, Interval *__restrict__ next, int q_next) {
+__global__ void __launch_bounds__(256, ES_MINB)
+edge_subdivide_kernel(const GridDev g, EdgePool P, const Pending *__restrict__ pend,
+                      int32_t *__restrict__ C, Interval *__restrict__ next, int q_next) {
   const int lane = threadIdx.x & 31;
   const int32_t total = pend ? min(C[C_NPEND], P.cap_mid) : P.E;
   const int32_t nwarps = (gridDim.x * blockDim.x) >> 5;
@@ -952,7 +996,10 @@ __global__ void edge_subdivide_kernel(const GridDev g, EdgePool P, const Pending
   for (int32_t w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; w < total; w += nwarps) {
     if (!pend) {
       const int32_t e = w;
-      if (should_subdivide(g, P, e, -1, -2, lane) && lane == 0) {
+      const SmpView a = smp_view(P, e, -1), b = smp_view(P, e, -2);
+      bool whole, unused;
+      should_subdivide2(g, P, e, a, b, a, b, true, false, lane, whole, unused);
+      if (whole && lane == 0) {
         const int32_t k = atomicAdd(n_next, 1);
         if (k < P.cap_q) next[k] = Interval{e, -1, -2};
         else atomicOr(&P.eflags[e], IRT_FLAG_CAPACITY);
@@ -960,8 +1007,9 @@ __global__ void edge_subdivide_kernel(const GridDev g, EdgePool P, const Pending
       continue;
     }
     const Pending pd = pend[w];
-    const bool distal = should_subdivide(g, P, pd.edge, pd.im, pd.ib, lane);
-    const bool proximal = should_subdivide(g, P, pd.edge, pd.ia, pd.im, lane);
+    const SmpView a = smp_view(P, pd.edge, pd.ia), m = smp_view(P, pd.edge, pd.im), b = smp_view(P, pd.edge, pd.ib);
+    bool distal, proximal;
+    should_subdivide2(g, P, pd.edge, m, b, a, m, true, true, lane, distal, proximal);
     if (lane == 0) {
       if (distal) {
         const int32_t k = atomicAdd(n_next, 1);
