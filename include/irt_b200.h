@@ -146,6 +146,10 @@ int irt_ctx_synchronize(irt_ctx *ctx);
 int64_t irt_ctx_launch_count(const irt_ctx *ctx);
 /* measured FP64 DFMA-chain peak of this device in FLOP/s (roofline denominator for K1) */
 int irt_measure_fp64_peak(irt_ctx *ctx, double *flops_per_s);
+/* the same probe with other operand patterns: mode 0 = the peak probe (a = fma(a, m, c): m and c stay in the
+ * operand reuse cache), 1 = two new register pairs per DFMA, 2 = three distinct register pairs per DFMA (the
+ * register file serves two per issue slot: what bounds K1's stage loop) */
+int irt_measure_fp64_rate(irt_ctx *ctx, int mode, double *flops_per_s);
 
 /* ---- robot: replaces tendon::TendonRobot (tendon/TendonRobot.h:52-355) ------------------ */
 int irt_robot_create(irt_ctx *ctx, const irt_robot_desc *desc, irt_robot **out);

@@ -92,7 +92,7 @@ class FkOutputs(C.Structure):
 # every symbol include/irt_b200.h declares (tests check the library exports each one)
 ABI_SYMBOLS = [
     "irt_abi_version", "irt_status_string", "irt_ctx_create", "irt_ctx_destroy", "irt_last_error",
-    "irt_ctx_device", "irt_ctx_synchronize", "irt_ctx_launch_count", "irt_measure_fp64_peak",
+    "irt_ctx_device", "irt_ctx_synchronize", "irt_ctx_launch_count", "irt_measure_fp64_peak", "irt_measure_fp64_rate",
     "irt_robot_create", "irt_robot_destroy", "irt_robot_state_size", "irt_robot_max_points",
     "irt_fk_batch", "irt_fk_batch_dev", "irt_fk_batch_packed", "irt_home_lengths_batch", "irt_self_collision_shapes",
     "irt_fk_tip_jacobian_batch", "irt_fk_tip_jacobian_batch_dev",
@@ -136,6 +136,7 @@ def lib():
         "irt_ctx_synchronize": (i32, [vp]),
         "irt_ctx_launch_count": (i64, [vp]),
         "irt_measure_fp64_peak": (i32, [vp, C.POINTER(C.c_double)]),
+        "irt_measure_fp64_rate": (i32, [vp, i32, C.POINTER(C.c_double)]),
         "irt_robot_create": (i32, [vp, C.POINTER(RobotDesc), C.POINTER(vp)]),
         "irt_robot_destroy": (None, [vp]),
         "irt_robot_state_size": (i32, [vp]),
@@ -288,6 +289,13 @@ class Context:
     def fp64_peak(self):
         v = C.c_double()
         self.check(self.L.irt_measure_fp64_peak(self.h, C.byref(v)))
+        return v.value
+
+    def fp64_rate(self, mode):
+        """DFMA rate (FLOP/s) of the probe with 0 / 2 / 3 register pairs per instruction that the operand reuse
+        cache does not serve (mode 0 / 1 / 2)"""
+        v = C.c_double()
+        self.check(self.L.irt_measure_fp64_rate(self.h, int(mode), C.byref(v)))
         return v.value
 
 

@@ -67,6 +67,7 @@ struct RobotDev {
 
 struct irt_robot {
   irt_ctx *ctx = nullptr;
+  unsigned long long uid = 0;   // process-unique (the constant-memory copy of the routing table is tagged with it)
   irt_robot_desc desc;
   RobotDev dev;
   int state_size = 0;

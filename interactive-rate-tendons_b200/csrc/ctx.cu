@@ -5,6 +5,8 @@
 #include <cstring>
 #include <limits>
 
+#include <atomic>
+
 #include "common.cuh"
 
 int irt_fail(irt_ctx *ctx, int status, const char *fmt, ...) {
@@ -265,6 +267,10 @@ int irt_robot_create(irt_ctx *ctx, const irt_robot_desc *desc, irt_robot **out) 
   IRT_CUDA(ctx, cudaSetDevice(ctx->device));
 
   irt_robot *rb = new irt_robot();
+  {
+    static std::atomic<unsigned long long> next_uid{1};
+    rb->uid = next_uid.fetch_add(1);
+  }
   rb->ctx = ctx;
   rb->desc = *desc;
   rb->state_size = N + (desc->enable_rotation ? 1 : 0) + (desc->enable_retraction ? 1 : 0);
@@ -402,8 +408,35 @@ __global__ void __launch_bounds__(256) dfma_peak_kernel(double *out, int iters, 
   if (s == 123.456) out[0] = s;  // keep the chains alive
 }
 
-extern "C" int irt_measure_fp64_peak(irt_ctx *ctx, double *flops_per_s) {
-  if (!ctx || !flops_per_s) return IRT_ERR_INVALID_ARGUMENT;
+// The same probe with other operand patterns (irt_measure_fp64_rate): what a DFMA costs when its sources are not
+// served by the operand reuse cache.  MODE 1: a_k = fma(a_k, m, c_k) -- two new register pairs per instruction
+// (m stays in the reuse cache); MODE 2: a_k = fma(a_k, b_k, c_k) -- three distinct register pairs, none shared with
+// the previous instruction.  K1's stage loop has 245 of 445 DFMAs of the second kind.
+template <int MODE>
+__global__ void __launch_bounds__(256) dfma_operand_kernel(double *out, int iters, double seed) {
+  double a[8], b[8], c[8];
+#pragma unroll
+  for (int k = 0; k < 8; k++) {
+    a[k] = seed + threadIdx.x + k;
+    b[k] = 1.0000001 + 1e-12 * seed * (threadIdx.x + k + 1);   // per thread: not a uniform-register operand
+    c[k] = 1e-9 * seed * (threadIdx.x + k + 1);
+  }
+#pragma unroll 1
+  for (int i = 0; i < iters; i++) {
+#pragma unroll
+    for (int r = 0; r < 8; r++) {
+#pragma unroll
+      for (int k = 0; k < 8; k++) a[k] = (MODE == 1) ? fma(a[k], b[0], c[k]) : fma(a[k], b[k], c[k]);
+    }
+  }
+  double s = 0;
+#pragma unroll
+  for (int k = 0; k < 8; k++) s += a[k];
+  if (s == 123.456) out[0] = s;
+}
+
+extern "C" int irt_measure_fp64_rate(irt_ctx *ctx, int mode, double *flops_per_s) {
+  if (!ctx || !flops_per_s || mode < 0 || mode > 2) return IRT_ERR_INVALID_ARGUMENT;
   IRT_CUDA(ctx, cudaSetDevice(ctx->device));
   double *d_out = (double *)ctx_scratch(ctx, 256);
   if (!d_out) return irt_fail(ctx, IRT_ERR_CUDA, "scratch alloc failed");
@@ -414,7 +447,9 @@ extern "C" int irt_measure_fp64_peak(irt_ctx *ctx, double *flops_per_s) {
   double best = 0;
   for (int rep = 0; rep < 5; rep++) {
     IRT_CUDA(ctx, cudaEventRecord(e0, ctx->stream));
-    dfma_peak_kernel<<<blocks, threads, 0, ctx->stream>>>(d_out, iters, 1.0);
+    if (mode == 0) dfma_peak_kernel<<<blocks, threads, 0, ctx->stream>>>(d_out, iters, 1.0);
+    else if (mode == 1) dfma_operand_kernel<1><<<blocks, threads, 0, ctx->stream>>>(d_out, iters, 1.0);
+    else dfma_operand_kernel<2><<<blocks, threads, 0, ctx->stream>>>(d_out, iters, 1.0);
     IRT_LAUNCHED(ctx);
     IRT_CUDA(ctx, cudaEventRecord(e1, ctx->stream));
     IRT_CUDA(ctx, cudaEventSynchronize(e1));
@@ -428,4 +463,8 @@ extern "C" int irt_measure_fp64_peak(irt_ctx *ctx, double *flops_per_s) {
   cudaEventDestroy(e1);
   *flops_per_s = best;
   return IRT_OK;
+}
+
+extern "C" int irt_measure_fp64_peak(irt_ctx *ctx, double *flops_per_s) {
+  return irt_measure_fp64_rate(ctx, 0, flops_per_s);
 }

@@ -21,6 +21,7 @@
 //     using adjugates, so a derivative evaluation needs 2 reciprocals and N+1 rsqrt only.
 //   * configurations are bucketed by node count (retraction) so warps stay converged.
 #include <cmath>
+#include <mutex>
 #include <limits>
 
 #include "common.cuh"
@@ -168,9 +169,30 @@ __device__ __forceinline__ void routing_eval_simple(const RobotDev &rb, const do
   }
 }
 
-// (v', u', sigma_i) at one RK4 stage.  rt: [NT][6] routing (shared table or local array).
-template <int NT>
-__device__ __forceinline__ void vu_dot(const double *__restrict__ rt, const double (&tau)[NT],
+// Where a stage reads its routing row from.  RtPtr: a pointer (the shared-memory table, or the per-thread rows of the
+// irregular first gap).  RtConst: a row of the copy of the table in CONSTANT memory, named by a warp-uniform index:
+// the values arrive through the uniform datapath (LDCU -> uniform registers) and enter the FP64 instructions as
+// uniform-register operands.  That matters because the FP64 pipe's issue rate is bounded by register-file reads:
+// a DFMA with three distinct register pairs costs 3 issue cycles instead of 2 (irt_measure_fp64_rate mode 2:
+// 0.68 of the DFMA peak), and every routing value that comes from a uniform register is one pair less -- and the 36
+// values of a row no longer occupy 72 registers of every thread.
+#ifndef FK_CONST_TABLE
+#define FK_CONST_TABLE 1
+#endif
+constexpr int FK_CT_DOUBLES = 7680;   // 60 KB of the 64 KB constant bank: 213 rows of a 6-tendon robot
+__constant__ double c_fk_tab[FK_CT_DOUBLES];
+struct RtPtr {
+  const double *p;
+  __device__ __forceinline__ double operator[](int i) const { return p[i]; }
+};
+struct RtConst {
+  int base;
+  __device__ __forceinline__ double operator[](int i) const { return c_fk_tab[base + i]; }
+};
+
+// (v', u', sigma_i) at one RK4 stage.  rt: [NT][6] routing (RtPtr or RtConst).
+template <int NT, typename RT>
+__device__ __forceinline__ void vu_dot(const RT &rt, const double (&tau)[NT],
                                        const double (&Kse)[3], const double (&Kbt)[3],
                                        const double (&v)[3], const double (&u)[3],
                                        double (&vd)[3], double (&ud)[3], double (&sig)[NT]) {
@@ -178,8 +200,11 @@ __device__ __forceinline__ void vu_dot(const double *__restrict__ rt, const doub
   double a00 = 0, a01 = 0, a02 = 0, a11 = 0, a12 = 0, a22 = 0;
   double b00 = 0, b01 = 0, b02 = 0, b10 = 0, b11 = 0, b12 = 0, b20 = 0, b21 = 0, b22 = 0;
   double h00 = 0, h01 = 0, h02 = 0, h11 = 0, h12 = 0, h22 = 0;
-  double av0 = 0, av1 = 0, av2 = 0, bv0 = 0, bv1 = 0, bv2 = 0;
-  double esum = 0, erx = 0, ery = 0, exx = 0, eyy = 0, exy = 0;
+  // sums that are built with plain additions start from -0.0: (-0.0) + x == x for every x, so the first tendon's
+  // "0 + x" folds away (with +0.0 it may not: 0 + (-0) is +0), one FP64 instruction less per sum and stage; the
+  // value of a sum can differ from the +0.0 start only in the sign of an exact zero
+  double av0 = -0.0, av1 = -0.0, av2 = -0.0, bv0 = 0, bv1 = 0, bv2 = -0.0;
+  double esum = -0.0, erx = -0.0, ery = -0.0, exx = 0, eyy = 0, exy = 0;
 #if FK_PIPELINE_TENDONS
   // software pipeline over the tendons: the latency chain of tendon j+1 (q -> |q|^2 -> rsqrt seed -> two Newton
   // steps, ~12 dependent FP64 operations) is started BEFORE the ~70 independent accumulations of tendon j, so the
@@ -363,10 +388,10 @@ struct FkState<NT, true> {
 // one classic RK4 step of size h; rt0/rt1/rt2 = routing at t, t+h/2, t+h.
 // The four stages are a real loop (not unrolled): the hot loop body is ONE copy of vu_dot, which
 // keeps the instruction footprint inside the SM's instruction cache.
-template <int NT>
+template <int NT, typename RT>
 __device__ __forceinline__ void rk4_step(FkState<NT, false> &x, const double (&tau)[NT],
                                          const double (&Kse)[3], const double (&Kbt)[3], double h,
-                                         const double *rt0, const double *rt1, const double *rt2) {
+                                         const RT &rt0, const RT &rt1, const RT &rt2) {
   const double hh = 0.5 * h, w1 = h * (1.0 / 6.0), w2 = h * (1.0 / 3.0);
   double sv[3], su[3], sR[9];      // stage values
   double aR[9], av[3], au[3];      // k1 + 2 k2 + 2 k3 + k4
@@ -379,11 +404,11 @@ __device__ __forceinline__ void rk4_step(FkState<NT, false> &x, const double (&t
 #pragma unroll 1
   for (int stage = 0; stage < 4; stage++) {
     const bool outer = (stage == 0) || (stage == 3);
-    const double *rt = (stage == 0) ? rt0 : ((stage == 3) ? rt2 : rt1);
+    const RT rt = (stage == 0) ? rt0 : ((stage == 3) ? rt2 : rt1);
     const double wq = outer ? w1 : w2;     // quadrature weight
     const double wk = outer ? 1.0 : 2.0;   // slope weight
     const double a = (stage == 2) ? h : hh;
-    vu_dot<NT>(rt, tau, Kse, Kbt, sv, su, vd, ud, sig);
+    vu_dot<NT, RT>(rt, tau, Kse, Kbt, sv, su, vd, ud, sig);
     // p' = R v ; L' = |v| ; L_i' = sigma_i : pure quadratures, accumulate in place
 #pragma unroll
     for (int i = 0; i < 3; i++)
@@ -421,10 +446,10 @@ __device__ __forceinline__ void rk4_step(FkState<NT, false> &x, const double (&t
 
 // the same step with the state and the stage scratch in shared memory (FkState<NT, true>): identical
 // arithmetic in identical order, so both variants give bit-identical results
-template <int NT>
+template <int NT, typename RT>
 __device__ __forceinline__ void rk4_step(FkState<NT, true> &x, const double (&tau)[NT],
                                          const double (&Kse)[3], const double (&Kbt)[3], double h,
-                                         const double *rt0, const double *rt1, const double *rt2) {
+                                         const RT &rt0, const RT &rt1, const RT &rt2) {
   const double hh = 0.5 * h, w1 = h * (1.0 / 6.0), w2 = h * (1.0 / 3.0);
   double sv[3], su[3];
 #pragma unroll
@@ -435,7 +460,7 @@ __device__ __forceinline__ void rk4_step(FkState<NT, true> &x, const double (&ta
 #pragma unroll 1
   for (int stage = 0; stage < 4; stage++) {
     const bool outer = (stage == 0) || (stage == 3);
-    const double *rt = (stage == 0) ? rt0 : ((stage == 3) ? rt2 : rt1);
+    const RT rt = (stage == 0) ? rt0 : ((stage == 3) ? rt2 : rt1);
     const double wq = outer ? w1 : w2;     // quadrature weight
     const double wk = outer ? 1.0 : 2.0;   // slope weight
     const double a = (stage == 2) ? h : hh;
@@ -443,7 +468,7 @@ __device__ __forceinline__ void rk4_step(FkState<NT, true> &x, const double (&ta
     // compiler barriers: without them the stored stage values are forwarded in registers across the derivative
     // evaluation (store-to-load forwarding), which is exactly the register pressure this variant is meant to shed
     asm volatile("" ::: "memory");
-    vu_dot<NT>(rt, tau, Kse, Kbt, sv, su, vd, ud, sig);
+    vu_dot<NT, RT>(rt, tau, Kse, Kbt, sv, su, vd, ud, sig);
     asm volatile("" ::: "memory");
     double sR[9], Rd[9];
 #pragma unroll
@@ -566,6 +591,7 @@ struct FkArgs {
   const int32_t *keys;    // [n] bucket | K << 16 (relative indices)
   const int64_t *row_off; // packed rows (absolute index) or nullptr
   int32_t *work;          // dynamic work counter (zero at launch)
+  int use_const;          // c_fk_tab holds this robot's routing table
 };
 
 #define FK_KERNEL_BOUNDS __launch_bounds__(SM ? FK_SM_THREADS : FK_THREADS, SM ? FK_SM_MIN_BLOCKS : FK_MIN_BLOCKS)
@@ -787,12 +813,23 @@ __global__ void FK_KERNEL_BOUNDS fk_rk4_fp64_kernel(const RobotDev rb, const FkA
   if (run) emit_node<NT, SM>(o, row_base, 0, s_start, x, rz);
   {
     const int T = integ ? (K - 1 + nhead) : 0;
-    int Tmax = T;
-    if (RETRACT) Tmax = __reduce_max_sync(0xffffffffu, T);
+    // the warp's step count: every lane runs the loop the same number of times (lanes that do not integrate idle
+    // in it), so the warp-wide vote of the fast path below is reached by all 32 lanes, and q is warp-uniform
+    const int Tmax = __reduce_max_sync(0xffffffffu, T);
     nsteps = T;
 #pragma unroll 1
     for (int j = 0; j < Tmax; j++) {
       const int q = Tmax - j;  // regular step q: node q -> node q-1 (1 <= q <= K-1)
+#if FK_CONST_TABLE
+      // every lane of the warp takes the regular step q (the common case: buckets are warps of equal step
+      // counts): the routing rows come from constant memory by a warp-uniform index, the step size is uniform
+      if (!SM && a.use_const && __all_sync(0xffffffffu, integ && q <= K - 1)) {
+        const int b0 = 2 * q * NT * 6;
+        rk4_step<NT, RtConst>(x, tau, Kse, Kbt, rb.dL, RtConst{b0}, RtConst{b0 - NT * 6}, RtConst{b0 - 2 * NT * 6});
+        emit_node<NT, SM>(o, row_base, K - q + 1, rb.node_t[q - 1], x, rz);
+        continue;
+      }
+#endif
       if (integ && q <= K - 1 + nhead) {
         const double *p0, *p1, *p2;
         double h;
@@ -814,7 +851,7 @@ __global__ void FK_KERNEL_BOUNDS fk_rk4_fp64_kernel(const RobotDev rb, const FkA
           h = hh0;
           emit_idx = -1;
         }
-        rk4_step<NT>(x, tau, Kse, Kbt, h, p0, p1, p2);
+        rk4_step<NT, RtPtr>(x, tau, Kse, Kbt, h, RtPtr{p0}, RtPtr{p1}, RtPtr{p2});
         if (emit_idx >= 0) emit_node<NT, SM>(o, row_base, emit_idx, rb.node_t[K - emit_idx], x, rz);
       }
     }
@@ -1060,6 +1097,28 @@ int fk_launch(irt_ctx *ctx, const irt_robot *rb, const double *d_states, int64_t
     a.perm = perm;
     a.keys = keys;
   }
+  a.use_const = 0;
+#if FK_CONST_TABLE
+  // The kernel's fast path reads the routing table from constant memory, which is ONE array per device and process:
+  // it is tagged with the robot it holds.  A launch for another robot waits for everything that may still read the
+  // old table (device-wide, rare: applications use one robot), uploads, and the lock is held across the launch so
+  // that no other host thread swaps the table between the check and the launch.
+  static std::mutex ct_mutex;
+  static unsigned long long ct_owner[64] = {};
+  std::unique_lock<std::mutex> ct_lock(ct_mutex, std::defer_lock);
+  const size_t tab_doubles = (size_t)d.n_table * d.n_tendons * 6;
+  if (tab_doubles <= (size_t)FK_CT_DOUBLES && ctx->device >= 0 && ctx->device < 64 && !ctx->fk_smem) {
+    ct_lock.lock();
+    if (ct_owner[ctx->device] != rb->uid) {
+      IRT_CUDA(ctx, cudaDeviceSynchronize());
+      IRT_CUDA(ctx, cudaMemcpyToSymbolAsync(c_fk_tab, rb->d_table, tab_doubles * sizeof(double), 0,
+                                            cudaMemcpyDeviceToDevice, st));
+      IRT_CUDA(ctx, cudaStreamSynchronize(st));
+      ct_owner[ctx->device] = rb->uid;
+    }
+    a.use_const = 1;
+  }
+#endif
   switch (d.n_tendons) {
     case 1: return launch_nt<1>(ctx, rb, a, st);
     case 2: return launch_nt<2>(ctx, rb, a, st);
