@@ -15,3 +15,7 @@ try:
     print('cpu',d['cpu_baseline']['value'], ec['cpu_baseline']['value'], ec['cpu_baseline']['verdicts_equal_gpu'], ec['cpu_baseline']['k2_vs_oracle'])
 except Exception as e: print('parse error',e)
 PY
+timeout 200 ncu --set full --clock-control none --import-source on -k regex:fk_rk4 -s 2 -c 1 -o gpurun_out/r2_k1_final python tools/ncu_fk.py fkv > gpurun_out/r2_k1_ncu.log 2>&1
+K='regex:fk_|self_coll|voxel_and|swept|edge_|raster_|scan_|round_|vertex_heads|env_|dfma|copy_i64|row_offsets|xchg'
+timeout 400 ncu --metrics gpu__time_duration.sum --clock-control none -k "$K" --csv --log-file gpurun_out/r2_launches.csv python bench.py --steps 2 --warmup 3 --cpu-seconds 0 > gpurun_out/r2_launches_bench.log 2>&1
+ls -la gpurun_out/r2_k1_final.ncu-rep gpurun_out/r2_launches.csv

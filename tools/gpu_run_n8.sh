@@ -1,8 +1,6 @@
 #!/bin/bash
 mkdir -p gpurun_out
 nvidia-smi -L | wc -l
-MGPU_VERTICES=400000 MGPU_STRESS_SWEEPS=3000 timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29519 tests/mgpu_fused_gather.py > gpurun_out/r2_mgpu_stress_N8.log 2>&1; echo "stress n8 rc=$?"
-grep -a "MGPU_OK\|Error\|assert" gpurun_out/r2_mgpu_stress_N8.log | head
 timeout 1500 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29517 bench.py --gpus 8 --steps 5 --warmup 3 > gpurun_out/r2_bench_N8.json 2> gpurun_out/r2_bench_N8.err; echo "bench n8 rc=$?"
 tail -c 600 gpurun_out/r2_bench_N8.err
 python - <<'PY'
