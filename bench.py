@@ -504,6 +504,17 @@ def main():
                             "achieved": achieved_fkonly, "frac": achieved_fkonly / peak_tf,
                             "note": "same step without flags (FK kernels only), for comparison with round 1"}}
 
+    try:    # what bounds the FP64 pipe for K1's instruction stream: register-file reads
+        rates = [ctx.fp64_rate(m) / 1e12 for m in (0, 1, 2)]
+        roofline["operand_read_bound"] = {
+            "dfma_tflops_operands_in_reuse_cache": rates[0], "dfma_tflops_two_new_register_pairs": rates[1],
+            "dfma_tflops_three_distinct_register_pairs": rates[2],
+            "note": "DFMA rate of the peak probe by register pairs per instruction that the operand reuse cache "
+                    "does not serve; K1's stage loop: 187 of its 445 DFMAs read three (tools/sass_fp64_rf_model.py: "
+                    "ceiling of pipe_fp64_cycles_active 89 %, ncu 84 %)"}
+    except Exception as e:
+        roofline["operand_read_bound"] = {"error": repr(e)[:200]}
+
     # ---------------- e2e: host-pointer C ABI, pinned buffers, H2D + D2H inside ----------------
     import ctypes as C
     h_states = torch.from_numpy(states).pin_memory()

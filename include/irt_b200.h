@@ -23,6 +23,9 @@
  *     all "_dev" calls on one context must therefore be STREAM-ORDERED with each other (same stream,
  *     or an event between them); two of them running concurrently on different streams would share
  *     the temporaries.  Use one context per concurrent stream.
+ *   - robots: K1 keeps the routing table of the robot it last ran in the device's constant memory (one copy per
+ *     device and process, shared by all contexts); a call for another robot on the same device drains the device
+ *     and re-uploads (correct, but slow when two robots alternate).
  *   - there is NO CPU fallback: without a CUDA device irt_ctx_create fails with
  *     IRT_ERR_NO_DEVICE and nothing else can be called.
  *   - per-item problems (non-convergence, limits, ...) are NOT errors: they are reported in a
