@@ -9,8 +9,11 @@
 
 #ifdef __CUDACC__
 #define RL_HD __device__
+#define RL_HDI __device__ __forceinline__
 #else
+#include <stdlib.h>
 #define RL_HD inline
+#define RL_HDI inline
 #endif
 #ifndef RS_FAST_TRAVERSAL
 #define RS_FAST_TRAVERSAL 1
@@ -166,4 +169,48 @@ RL_HD void add_line(const Grid &g, Sink &sink, const D3 &a, const D3 &b) {
   sink.finish();
 #undef IDX_IN
 #undef VOX_IN
+}
+
+// find_cell -- collision/VoxelOctree.cpp:309-317 (+domain_check :1511-1521); false = domain error
+template <typename Grid>
+RL_HDI bool find_cell(const Grid &g, const D3 &p, long long *c) {
+  if (p.x < g.lo[0] || g.hi[0] < p.x) return false;
+  if (p.y < g.lo[1] || g.hi[1] < p.y) return false;
+  if (p.z < g.lo[2] || g.hi[2] < p.z) return false;
+  // the quotient by the reciprocal differs from the reference's division by a few ulp (< 1e-13 cells): the
+  // truncation is the same unless the point is within 1e-9 of a cell face, where the division itself decides
+  const double qx = (p.x - g.lo[0]) * g.inv_d[0], qy = (p.y - g.lo[1]) * g.inv_d[1], qz = (p.z - g.lo[2]) * g.inv_d[2];
+  const double fx = qx - floor(qx), fy = qy - floor(qy), fz = qz - floor(qz);
+  const double m = 1e-9;
+  if (fx > m && fx < 1.0 - m && fy > m && fy < 1.0 - m && fz > m && fz < 1.0 - m) {
+    c[0] = (long long)qx; c[1] = (long long)qy; c[2] = (long long)qz;
+    return true;
+  }
+  c[0] = (long long)((p.x - g.lo[0]) / g.d[0]);
+  c[1] = (long long)((p.y - g.lo[1]) / g.d[1]);
+  c[2] = (long long)((p.z - g.lo[2]) / g.d[2]);
+  return true;
+}
+
+// event of one point pair of should_subdivide (VoxelEnvironment.cpp:304-341), points already in grid coordinates:
+// 0 = cells at most 1 apart, 1 = far apart, 2 = domain error (a point outside the grid: find_cell would throw)
+template <typename Grid>
+RL_HDI int pair_event_core(const Grid &g, const D3 &qa, const D3 &qb) {
+  const bool in_a = !(qa.x < g.lo[0] || g.hi[0] < qa.x || qa.y < g.lo[1] || g.hi[1] < qa.y || qa.z < g.lo[2] || g.hi[2] < qa.z);
+  const bool in_b = !(qb.x < g.lo[0] || g.hi[0] < qb.x || qb.y < g.lo[1] || g.hi[1] < qb.y || qb.z < g.lo[2] || g.hi[2] < qb.z);
+  const double tight = 1.0 - 1e-9;
+  if (!in_a || !in_b) return 2;
+  // two points less than one cell apart on every axis: their cells differ by at most 1 (the common case at the
+  // last bisection level) -- no need to locate them
+  if (fabs(qa.x - qb.x) < g.d[0] * tight && fabs(qa.y - qb.y) < g.d[1] * tight && fabs(qa.z - qb.z) < g.d[2] * tight)
+    return 0;
+#ifdef __CUDACC__
+  long long s[3], e[3];
+#else
+  long long s[3] = {0, 0, 0}, e[3] = {0, 0, 0};   // both points are in the domain here: find_cell fills them (gcc cannot see it)
+#endif
+  find_cell(g, qa, s);
+  find_cell(g, qb, e);
+  const long long dx = llabs(s[0] - e[0]), dy = llabs(s[1] - e[1]), dz = llabs(s[2] - e[2]);
+  return (dx > 1 || dy > 1 || dz > 1) ? 1 : 0;
 }

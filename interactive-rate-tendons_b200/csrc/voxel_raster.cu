@@ -732,26 +732,6 @@ __global__ void edge_mark_kernel(EdgePool P, const int32_t *__restrict__ C) {
       atomicMin(&P.first_invalid[P.m_edge[i]], (unsigned long long)__double_as_longlong(P.m_t[i]));
 }
 
-// find_cell -- collision/VoxelOctree.cpp:309-317 (+domain_check :1511-1521); false = domain error
-__device__ __forceinline__ bool find_cell(const GridDev &g, const D3 &p, long long *c) {
-  if (p.x < g.lo[0] || g.hi[0] < p.x) return false;
-  if (p.y < g.lo[1] || g.hi[1] < p.y) return false;
-  if (p.z < g.lo[2] || g.hi[2] < p.z) return false;
-  // the quotient by the reciprocal differs from the reference's division by a few ulp (< 1e-13 cells): the
-  // truncation is the same unless the point is within 1e-9 of a cell face, where the division itself decides
-  const double qx = (p.x - g.lo[0]) * g.inv_d[0], qy = (p.y - g.lo[1]) * g.inv_d[1], qz = (p.z - g.lo[2]) * g.inv_d[2];
-  const double fx = qx - floor(qx), fy = qy - floor(qy), fz = qz - floor(qz);
-  const double m = 1e-9;
-  if (fx > m && fx < 1.0 - m && fy > m && fy < 1.0 - m && fz > m && fz < 1.0 - m) {
-    c[0] = (long long)qx; c[1] = (long long)qy; c[2] = (long long)qz;
-    return true;
-  }
-  c[0] = (long long)((p.x - g.lo[0]) / g.d[0]);
-  c[1] = (long long)((p.y - g.lo[1]) / g.d[1]);
-  c[2] = (long long)((p.z - g.lo[2]) / g.d[2]);
-  return true;
-}
-
 // should_subdivide(a, b) -- VoxelEnvironment.cpp:304-341, warp-cooperative: lanes over points, scanned from the
 // tip like the reference so the first event found is the same one.  A bisected interval needs TWO such tests
 // (a, m) and (m, b) (VoxelEnvironment.cpp:350-353, 386-397); the kernel is bound by memory latency (a chain of
@@ -775,20 +755,7 @@ __device__ __forceinline__ SmpView smp_view(const EdgePool &P, int32_t edge, int
 // event of one point pair: 0 = cells at most 1 apart, 1 = far apart, 2 = domain error (a point outside the grid)
 __device__ __forceinline__ int pair_event(const GridDev &g, const D3 &ra, const D3 &rb) {
   const double pa[3] = {ra.x, ra.y, ra.z}, pb[3] = {rb.x, rb.y, rb.z};
-  const D3 qa = rotate_pt(g, pa), qb = rotate_pt(g, pb);
-  const bool in_a = !(qa.x < g.lo[0] || g.hi[0] < qa.x || qa.y < g.lo[1] || g.hi[1] < qa.y || qa.z < g.lo[2] || g.hi[2] < qa.z);
-  const bool in_b = !(qb.x < g.lo[0] || g.hi[0] < qb.x || qb.y < g.lo[1] || g.hi[1] < qb.y || qb.z < g.lo[2] || g.hi[2] < qb.z);
-  const double tight = 1.0 - 1e-9;
-  if (!in_a || !in_b) return 2;
-  // two points less than one cell apart on every axis: their cells differ by at most 1 (the common case at the
-  // last bisection level) -- no need to locate them
-  if (fabs(qa.x - qb.x) < g.d[0] * tight && fabs(qa.y - qb.y) < g.d[1] * tight && fabs(qa.z - qb.z) < g.d[2] * tight)
-    return 0;
-  long long s[3], e[3];
-  find_cell(g, qa, s);
-  find_cell(g, qb, e);
-  const long long dx = llabs(s[0] - e[0]), dy = llabs(s[1] - e[1]), dz = llabs(s[2] - e[2]);
-  return (dx > 1 || dy > 1 || dz > 1) ? 1 : 0;
+  return pair_event_core(g, rotate_pt(g, pa), rotate_pt(g, pb));   // raster_line.h
 }
 // up to two tests at once: test 0 = (x0, y0), test 1 = (x1, y1); run[t] selects; res[t] = should_subdivide
 __device__ __forceinline__ void should_subdivide2(const GridDev &g, const EdgePool &P, int32_t edge, const SmpView &x0,

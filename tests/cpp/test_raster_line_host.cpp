@@ -5,8 +5,10 @@
 // segments that took the hand-over path, so that both paths are known to be exercised.  Compile with
 // -ffp-contract=off (the device file is built with -fmad=false).  The oracle is linked as the checker only.
 // Built and run by tests/test_abi_and_host.py.
+#include <cmath>
 #include <cstdint>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <random>
@@ -127,6 +129,71 @@ static long long run(int Ng, const double *lim, unsigned seed, int nseg, long lo
   return bad;
 }
 
+// find_cell (reciprocal multiply, exact division next to a cell face) and the point-pair event of should_subdivide
+// against the oracle's find_cell (VoxelOctree.cpp:309-317, domain_check :1511-1521): points anywhere, on cell
+// faces +- a few ulp, on and just beyond the limits; pairs near and far
+static long long run_cells(int Ng, const double *lim, unsigned seed, int npts, long long *n_exact_div) {
+  orc_grid og;
+  std::memset(&og, 0, sizeof(og));
+  og.Ng = Ng;
+  std::memcpy(og.lim, lim, sizeof(og.lim));
+  og.inv_rot[0] = og.inv_rot[4] = og.inv_rot[8] = 1;
+  Grid g;
+  g.Ng = Ng;
+  double ext[3];
+  for (int a = 0; a < 3; a++) {
+    g.lo[a] = lim[2 * a];
+    g.hi[a] = lim[2 * a + 1];
+    g.d[a] = (lim[2 * a + 1] - lim[2 * a]) / Ng;
+    g.inv_d[a] = 1 / g.d[a];
+    ext[a] = g.hi[a] - g.lo[a];
+  }
+  std::mt19937_64 gen(seed);
+  std::uniform_real_distribution<double> U(0.0, 1.0);
+  long long bad = 0;
+  auto make = [&](double *p, int kind) {
+    for (int c = 0; c < 3; c++) {
+      switch (kind) {
+        case 0: p[c] = g.lo[c] + ext[c] * (-0.02 + 1.04 * U(gen)); break;                       // anywhere
+        case 1: {                                                                               // on a face +- ulps
+          double v = g.lo[c] + g.d[c] * (double)(int)(U(gen) * (Ng + 1));
+          const int k = (int)(U(gen) * 7) - 3;
+          for (int i = 0; i < (k < 0 ? -k : k); i++) v = std::nextafter(v, k < 0 ? -1e300 : 1e300);
+          p[c] = v;
+          break;
+        }
+        case 2: p[c] = g.lo[c] + g.d[c] * ((double)(int)(U(gen) * Ng) + (U(gen) < 0.5 ? 1e-10 : 1 - 1e-10)); break;
+        default: {                                                                              // the limits
+          const double pick[4] = {g.lo[c], g.hi[c], std::nextafter(g.hi[c], 1e300), std::nextafter(g.lo[c], -1e300)};
+          p[c] = (U(gen) < 0.7) ? g.lo[c] + ext[c] * U(gen) : pick[(int)(U(gen) * 4) % 4];
+        }
+      }
+    }
+  };
+  for (int i = 0; i < npts; i++) {
+    double a[3], b[3];
+    make(a, i % 4);
+    if (i % 3 == 0) make(b, (i / 4) % 4);
+    else for (int c = 0; c < 3; c++) b[c] = a[c] + g.d[c] * (U(gen) - 0.5) * ((i % 3 == 1) ? 1.9 : 5.0);
+    const D3 A = {a[0], a[1], a[2]}, B = {b[0], b[1], b[2]};
+    long long ca[3] = {0, 0, 0}, cb[3] = {0, 0, 0};
+    int64_t wa[3], wb[3];
+    const bool oka = find_cell(g, A, ca), okb = find_cell(g, B, cb);
+    const int ea = orc_find_cell(&og, a, wa), eb = orc_find_cell(&og, b, wb);
+    if (oka != (ea == 0) || okb != (eb == 0)) { bad++; continue; }
+    if (oka && (ca[0] != wa[0] || ca[1] != wa[1] || ca[2] != wa[2])) bad++;
+    if (okb && (cb[0] != wb[0] || cb[1] != wb[1] || cb[2] != wb[2])) bad++;
+    int want = 2;
+    if (ea == 0 && eb == 0) {
+      const long long dx = std::llabs(wa[0] - wb[0]), dy = std::llabs(wa[1] - wb[1]), dz = std::llabs(wa[2] - wb[2]);
+      want = (dx > 1 || dy > 1 || dz > 1) ? 1 : 0;
+    }
+    if (pair_event_core(g, A, B) != want) bad++;
+    if (i % 4 == 1 || i % 4 == 2) ++*n_exact_div;
+  }
+  return bad;
+}
+
 int main() {
   const double lung[6] = {-0.21, 0.21, -0.21, 0.21, -0.21, 0.21};
   const double skew[6] = {-0.1, 0.3, 0.05, 0.25, -0.4, 0.0};
@@ -138,6 +205,15 @@ int main() {
     long long cells = 0;
     const long long bad = run(c.Ng, c.lim, c.seed, c.nseg, &cells);
     std::printf("Ng %3d: %d segments, %lld cells emitted, %lld groups differ\n", c.Ng, c.nseg, cells, bad);
+    all_bad += bad;
+  }
+  {
+    long long near_face = 0, bad = 0;
+    bad += run_cells(128, lung, 11, 3000000, &near_face);
+    bad += run_cells(128, skew, 12, 1500000, &near_face);
+    bad += run_cells(512, unit, 13, 1500000, &near_face);
+    std::printf("find_cell / pair events: 6000000 point pairs (%lld with a point within ulps of a cell face), %lld differ\n",
+                near_face, bad);
     all_bad += bad;
   }
   std::printf("division-free path %lld segments, literal path %lld (close calls, near-degenerate directions, "
