@@ -601,19 +601,103 @@ class VoxelCachedLazyPRM:
         order = np.lexsort((np.arange(len(d)), d))[:k]
         return order[np.isfinite(d[order])]
 
-    def roadmapIk(self, request, tolerance, k, solver, auto_add=False, mode=None, delta=1e-6):
-        """roadmapIk(request, tolerance, k, opt) of the reference with its per-neighbour loop turned into batches:
+    def _enforce_bounds(self, x):
+        """CompoundStateSpace::enforceBounds of the space of Problem.cpp:101-163: tensions clamped to
+        [0, max_tension], rotation wrapped into [-pi, pi] (SO2StateSpace::enforceBounds: fmod + one wrap), retraction
+        clamped to [0, L]"""
+        d = self.robot.spec
+        N = len(d["C"])
+        x = np.array(x, dtype=np.float64)
+        x[:N] = np.clip(x[:N], 0.0, np.asarray(d["max_tension"], dtype=np.float64)[:N])
+        kk = N
+        if d.get("enable_rotation"):
+            v = np.fmod(x[kk], 2.0 * np.pi)
+            x[kk] = v + 2.0 * np.pi if v < -np.pi else (v - 2.0 * np.pi if v >= np.pi else v)
+            kk += 1
+        if d.get("enable_retraction"):
+            x[kk] = min(max(x[kk], 0.0), d["L"])
+        return x
+
+    def _find_state(self, x):
+        """tryAddToGraph (VoxelCachedLazyPRM.cpp:2777-2801): the vertex whose state equals x (si_->equalStates:
+        every component within 2 epsilon), else -1"""
+        if not len(self.states):
+            return -1
+        same = np.all(np.abs(self.states - x[None]) <= 2.0 * np.finfo(np.float64).eps, axis=1)
+        if len(self.vertex_removed) == len(same):
+            same &= ~self.vertex_removed
+        hit = np.nonzero(same)[0]
+        return int(hit[0]) if len(hit) else -1
+
+    def _out_degree(self, v):
+        ptr, nbr, eid = self._adjacency()
+        lo, hi = int(ptr[v]), int(ptr[v + 1])
+        return int((~(self.edge_removed[eid[lo:hi]] | self.vertex_removed[nbr[lo:hi]])).sum())
+
+    def _ik_nearest(self, x, own, ik_neighbor, accurate, removed):
+        """the would-be edge sources of an IK result x (`nearest` of VoxelCachedLazyPRM.cpp:3238-3246, 3340-3349,
+        3470-3478): its IK neighbour only, or with RMAP_IK_ACCURATE connectionStrategy_(vertex) -- the k nearest
+        milestones within the range, the (temporarily added) vertex itself among them since it is in nn_ by then
+        -- plus the IK neighbour when it is not one of them.  The result's own vertex is `own` when the state was
+        already in the roadmap, else -1 (a vertex that only exists for the duration of the query)."""
+        if not accurate:
+            return [int(ik_neighbor)]
+        bound = self.range or 0.2 * self.maximum_extent()
+        d = self.distance(x, self.states)
+        d = np.where(removed, np.inf, d)
+        ids = np.arange(len(d))
+        if own < 0:                       # the temporary vertex: distance 0, the highest index
+            d, ids = np.append(d, 0.0), np.append(ids, -1)
+        order = np.lexsort((np.arange(len(d)), d))[:self.max_nearest_neighbors]
+        out = [int(ids[j]) for j in order if d[j] <= bound]
+        if int(ik_neighbor) not in out:
+            out.append(int(ik_neighbor))
+        return out
+
+    def _append_vertex(self, state, tip):
+        v = len(self.states)
+        self._adjacency()
+        self.states = np.ascontiguousarray(np.concatenate([self.states, state[None]], axis=0))
+        self.vertex_validity = np.append(self.vertex_validity, np.uint8(VALIDITY_TRUE))
+        self.vertex_removed = np.append(self.vertex_removed, False)
+        self.tips = np.concatenate([self.tips, np.asarray(tip, dtype=np.float64)[None]], axis=0)
+        self._adj = None
+        self._have_vcache = False         # the cache lacks the new vertex
+        return v
+
+    def _append_edges(self, pairs, validity):
+        self._adjacency()
+        pairs = np.asarray(pairs, dtype=np.int64).reshape(-1, 2)
+        self.edges = np.ascontiguousarray(np.concatenate([self.edges, pairs], axis=0))
+        self.edge_validity = np.append(self.edge_validity, np.full(len(pairs), validity, dtype=np.uint8))
+        self.edge_removed = np.append(self.edge_removed, np.zeros(len(pairs), dtype=bool))
+        self._adj = None
+        self._have_ecache = False
+
+    def roadmapIk(self, request, tolerance, k, solver, auto_add=False, mode=None, delta=1e-6, accurate=False,
+                  lazy_add=False):
+        """roadmapIk(request, tolerance, k, opt) of the reference (VoxelCachedLazyPRM.cpp:3095-3565) with its
+        per-neighbour loop turned into batches; auto_add / accurate / lazy_add are RMAP_IK_AUTO_ADD / _ACCURATE /
+        _LAZY_ADD (VoxelCachedLazyPRM.h:364-381):
           1. the k nearest VALID neighbours in tip space (invalid ones are removed and the query repeated,
              .cpp:3112-3137; validity = table look-ups),
           2. the k IK problems solved side by side, their FK / Jacobian requests answered in lockstep by single
              K1 launches (solve_ik_lockstep; `solver(start, request, fk)` is the reference's ikController_),
           3. ONE FK + is_valid_shape + voxelise + collides call over the k results (.cpp:3182-3192),
-          4. RMAP_IK_AUTO_ADD: ONE voxelize_until_invalid call over the edges neighbour -> result of every result
-             within tolerance (.cpp:3214-3292),
-          5. the reference's order of acceptance: the FIRST neighbour (nearest first) whose result it would have
-             returned; without auto_add, failing that, the closest valid result, and failing that the closest
-             last-valid state of the edges neighbour -> result (.cpp:3298-3420, one more until-invalid batch).
-        Returns dict(controls, tip_position, neighbor, error, index, vertex, lockstep_batches, ...) or None."""
+          4. ONE voxelize_until_invalid call over every would-be edge source -> result that the branches below can
+             ask for (the reference computes them one at a time where it needs them; an edge it would not have
+             reached costs device time here but changes nothing), sources per result as _ik_nearest says,
+          5. the reference's order of acceptance, walked over those tables:
+             without auto_add the FIRST neighbour (nearest first) whose result is valid and within tolerance; failing
+             that the closest valid result; failing that the closest last-valid state of the edges source -> result
+             ("stepping them backwards", .cpp:3298-3428);
+             with auto_add the first result within tolerance that a fully valid edge connects to a valid source
+             (the result joins the roadmap with that edge, .cpp:3212-3292); failing that the closest last-valid state
+             over the edges of ALL results joins the roadmap, connected to its source and, lazily, to its
+             connection-strategy neighbours, whose edges are validated unless lazy_add (.cpp:3430-3565).
+        Sources found invalid on the way are removed like removeVertices does (vertex_removed).  Returns
+        dict(controls, tip_position, neighbor, error, index, vertex, lockstep_batches, ...) or None (where the
+        reference would index an empty list: no valid source anywhere)."""
         if self.world != 1:
             raise NotImplementedError("roadmapIk runs on the full roadmap of one rank")
         request = np.asarray(request, dtype=np.float64)
@@ -634,47 +718,156 @@ class VoxelCachedLazyPRM:
         valid = ((flags & INVALID_MASK) == 0) & ~collides
         err = np.linalg.norm(tips - request[None], axis=1)
         info = dict(lockstep_batches=fk.batches, fk_requests=fk.evaluations, neighbors=nb, errors=err, valid=valid)
+        m = len(nb)
 
-        def result(i, controls=None, tip=None, error=None, **kw):
+        def result(i, controls=None, tip=None, error=None, neighbor=None, **kw):
             return dict(controls=finals[i] if controls is None else controls,
-                        tip_position=tips[i] if tip is None else tip, neighbor=starts[i],
+                        tip_position=tips[i] if tip is None else tip, neighbor=starts[i] if neighbor is None else neighbor,
                         error=float(err[i] if error is None else error), index=int(i), vertex=int(nb[i]), **info, **kw)
 
         if not auto_add:
-            for i in range(len(nb)):
+            for i in range(m):
                 if valid[i] and err[i] < tolerance:
                     return result(i)
             ok = np.nonzero(valid)[0]
             if len(ok):          # "All IKs rejected, returning closest valid one"
                 return result(int(ok[np.argmin(err[ok])]), accepted=False)
-            # "All IKs are in collision, stepping them backwards": last valid state of neighbour -> result
+
+        # ---- the would-be edges: sources per result in the reference's order, validity look-ups and removals
+        # replayed on a copy first so that ONE until-invalid batch can answer every edge the walk may ask for
+        self._adjacency()
+        bounded = np.stack([self._enforce_bounds(x) for x in finals])   # space->enforceBounds(state)
+        own = [self._find_state(x) for x in bounded]                    # addMilestone: was_added == (own < 0)
+        removed = self.vertex_removed.copy()
+        first_pass = [i for i in range(m) if err[i] < tolerance] if auto_add else list(range(m))
+
+        def plan_result(i):
+            rows = []                  # (source, is_self, valid) in the reference's order
+            for s in self._ik_nearest(bounded[i], own[i], nb[i], accurate, removed):
+                is_self = s < 0 or s == own[i]
+                ok_s = bool(valid[i]) if s < 0 else self.computeVertexValidity(s)
+                if not ok_s and not is_self:
+                    removed[s] = True
+                rows.append((s, is_self, ok_s))
+            return rows
+
+        plan1, plan3 = {}, {}
+        for i in first_pass:
+            if not (auto_add and own[i] >= 0 and self._out_degree(own[i]) > 0):   # else returned before any edge
+                plan1[i] = plan_result(i)
+        jobs = [(i, s) for i, rows in plan1.items() for (s, is_self, ok_s) in rows if ok_s and not (auto_add and is_self)]
+        if auto_add:                   # the fallback asks again for the results the loop above left without sources
+            for i in range(m):
+                if own[i] < 0 and not any(ok_s and not is_self for (_, is_self, ok_s) in plan1.get(i, [])):
+                    plan3[i] = plan_result(i)
+                    jobs += [(i, s) for (s, _, ok_s) in plan3[i] if ok_s and (i, s) not in jobs]
+        pe_of = {}
+        if jobs:
+            src = np.stack([bounded[i] if s < 0 else self.states[s] for i, s in jobs])
+            dst = np.stack([finals[i] for i, _ in jobs])
             est = SetStore(self.ctx, self.grid)
-            pe = est.voxelize_edges_until_invalid(self.robot, self.space, starts, finals, self.env)
-            t = pe["t_last"][:, None]
-            last_valid = self._interpolate(starts, finals, t)
-            lt = self.robot.shape_batch(last_valid, want=("tip",))["tip"]
+            pe = est.voxelize_edges_until_invalid(self.robot, self.space, src, dst, self.env)
+            last_valid = self._interpolate(src, dst, pe["t_last"][:, None])
+            lt = self.robot.shape_batch(last_valid, want=("tip",))["tip"]       # last_backbone.back()
             lerr = np.linalg.norm(lt - request[None], axis=1)
-            j = int(np.argmin(lerr))
-            return result(j, controls=last_valid[j], tip=lt[j], error=lerr[j], accepted=False, stepped_back=True)
-        cand = [i for i in range(len(nb)) if err[i] < tolerance]
-        if not cand:
+            for j, key in enumerate(jobs):
+                pe_of[key] = dict(fully_valid=(pe["flags"][j] & FLAG_PARTIAL) == 0, last_valid=last_valid[j],
+                                  tip=lt[j], error=float(lerr[j]))
+
+        def walk(rows):
+            """the valid sources of a result in order; applies the removals the reference makes on the way"""
+            for s, is_self, ok_s in rows:
+                if not ok_s:
+                    if not is_self:
+                        self.vertex_removed[s] = True
+                    continue
+                yield s, is_self
+
+        if not auto_add:
+            # "All IKs are in collision, stepping them backwards"
+            best = None
+            for i in range(m):
+                for s, _ in walk(plan1[i]):
+                    e = pe_of[(i, s)]
+                    if best is None or e["error"] < best[0]["error"]:
+                        best = (e, i, s)
+            if best is None:
+                return None
+            e, i, s = best
+            return result(i, controls=e["last_valid"], tip=e["tip"], error=e["error"], accepted=False,
+                          stepped_back=True, source=int(s))
+
+        nearest = {}                   # res.nearest: the sources whose partial edge was computed
+        for i in first_pass:
+            if own[i] >= 0 and self._out_degree(own[i]) > 0:
+                return result(i, added_vertex=None, already_in_roadmap=True)
+            nearest[i] = []
+            for s, is_self in walk(plan1[i]):
+                if is_self:            # "State already in the roadmap, returning it."
+                    v = own[i]
+                    if v < 0:          # the vertex addMilestone created stays, without an edge
+                        v = self._append_vertex(bounded[i], tips[i])
+                    else:
+                        self.tips[v] = tips[i]
+                        self.vertex_validity[v] = VALIDITY_TRUE
+                    return result(i, added_vertex=v if own[i] < 0 else None, already_in_roadmap=own[i] >= 0)
+                nearest[i].append(s)
+                if pe_of[(i, s)]["fully_valid"]:          # connect source -- result vertex
+                    v = own[i]
+                    if v < 0:
+                        v = self._append_vertex(bounded[i], tips[i])
+                    else:
+                        self.tips[v] = tips[i]
+                        self.vertex_validity[v] = VALIDITY_TRUE
+                    self._append_edges([[int(s), v]], VALIDITY_TRUE)
+                    return result(i, added_vertex=v if own[i] < 0 else None, source=int(s))
+        # "All IKs rejected, finding closest collision-free connection"
+        best = None
+        for i in range(m):
+            if not nearest.get(i):
+                if own[i] >= 0:    # "already part of the roadmap, no need to connect it"
+                    continue
+                nearest[i] = [s for s, _ in walk(plan3[i])]
+            for s in nearest[i]:
+                e = pe_of[(i, s)]
+                if best is None or e["error"] < best[0]["error"]:
+                    best = (e, i, s)
+        if best is None:
             return None
-        est = SetStore(self.ctx, self.grid)
-        pe = est.voxelize_edges_until_invalid(self.robot, self.space, starts[cand], finals[cand], self.env)
-        for c, i in enumerate(cand):
-            if (pe["flags"][c] & FLAG_PARTIAL) == 0:      # is_fully_valid: connect neighbour -- new vertex
-                v = len(self.states)
-                self.states = np.ascontiguousarray(np.concatenate([self.states, finals[i:i + 1]], axis=0))
-                self.edges = np.ascontiguousarray(np.concatenate([self.edges, [[int(nb[i]), v]]], axis=0))
-                self.vertex_validity = np.append(self.vertex_validity, np.uint8(VALIDITY_TRUE))
-                self.edge_validity = np.append(self.edge_validity, np.uint8(VALIDITY_TRUE))
-                self.vertex_removed = np.append(self.vertex_removed, False)
-                self.edge_removed = np.append(self.edge_removed, False)
-                self.tips = np.concatenate([self.tips, tips[i:i + 1]], axis=0)
-                self._adj = None
-                self._have_vcache = self._have_ecache = False     # the caches lack the new vertex / edge
-                return result(i, added_vertex=v)
-        return None
+        e, i, s = best
+        src_state = bounded[i] if s < 0 else self.states[s].copy()
+        v = self._find_state(e["last_valid"])
+        added = v < 0
+        if added:
+            # addMilestone(state, true): connected lazily to its connection-strategy neighbours (itself not yet in nn_)
+            d = np.where(self.vertex_removed, np.inf, self.distance(e["last_valid"], self.states))
+            order = np.lexsort((np.arange(len(d)), d))[:self.max_nearest_neighbors]
+            conn = [int(j) for j in order if d[j] <= (self.range or 0.2 * self.maximum_extent())]
+            v = self._append_vertex(e["last_valid"], tips[i])      # the reference caches the IK RESULT's tip here
+            if conn:
+                self._append_edges([[v, n] for n in conn], VALIDITY_UNKNOWN)
+        else:
+            self.tips[v] = tips[i]
+            self.vertex_validity[v] = VALIDITY_TRUE
+        if s >= 0 and v != s:
+            eid = self.edge_index(int(s), v)
+            if eid < 0:
+                self._append_edges([[int(s), v]], VALIDITY_TRUE)
+            else:
+                self.edge_validity[eid] = VALIDITY_TRUE
+            if not lazy_add:           # every edge of the vertex is validated now, the invalid ones removed
+                ptr, nbr, eids = self._adjacency()
+                mine = [int(x) for x in eids[int(ptr[v]):int(ptr[v + 1])] if not self.edge_removed[x]]
+                todo = [x for x in mine if not self.edge_validity[x] & VALIDITY_TRUE]
+                if todo:
+                    vs = SetStore(self.ctx, self.grid)
+                    einfo = vs.voxelize_edges_indexed(self.robot, self.space, self.states, self.edges[todo])
+                    hit = vs.check(self.env)
+                    good = ((einfo["flags"] & FLAG_PARTIAL) == 0) & ~hit
+                    self.edge_validity[np.asarray(todo)[good]] = VALIDITY_TRUE
+                    self.edge_removed[np.asarray(todo)[~good]] = True
+        return result(i, controls=e["last_valid"], tip=e["tip"], error=e["error"], neighbor=src_state, accepted=False,
+                      stepped_back=True, source=int(s), added_vertex=v if added else None)
 
     def _interpolate(self, a, b, t):
         """OMPL compound interpolate of the space of Problem.cpp:101-163 (RealVector linear, SO2 shortest arc)"""

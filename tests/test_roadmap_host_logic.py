@@ -419,3 +419,279 @@ def test_create_roadmap_two_ranks_gloo(tmp_path, orc, wl, monkeypatch):
     prm.createRoadmap(70, opt=R.VoxelizeVertices | R.ValidateVertices | R.VoxelizeEdges | R.ValidateEdges)
     assert np.array_equal(prm.states, r0["states"]) and np.array_equal(prm.edges, r0["edges"])
     assert np.all(r0["vv"] == R.VALIDITY_TRUE) and np.all(r0["ev"] == R.VALIDITY_TRUE) and len(r0["ev"]) > 50
+
+
+class _SeqPlanner:
+    """The reference's roadmapIk (VoxelCachedLazyPRM.cpp:3095-3565) restated the way the reference runs it: one
+    neighbour, one IK, one vertex check, one voxelize_until_invalid at a time, with its early returns, temporary
+    vertices and removals -- over plain lists and the oracle.  The checker for the batched mirror."""
+
+    def __init__(self, orc, rb, ogrid, oenv, prm, solver):
+        self.orc, self.rb, self.ogrid, self.oenv, self.solver = orc, rb, ogrid, oenv, solver
+        self.dist = lambda a, b: float(prm.distance(np.asarray(a), np.asarray(b)[None])[0])
+        self.bound, self.kconn = prm.range or 0.2 * prm.maximum_extent(), prm.max_nearest_neighbors
+        self.states = [s.copy() for s in prm.states]
+        self.alive = [not r for r in prm.vertex_removed.tolist()] if len(prm.vertex_removed) else [True] * len(self.states)
+        self.edges = {}        # frozenset({a, b}) -> validity
+        for e, (a, b) in enumerate(prm.edges.tolist()):
+            if not prm.edge_removed[e]:
+                self.edges[frozenset((a, b))] = int(prm.edge_validity[e])
+        self.tips = [t.copy() for t in prm.tips]
+        self.edge_calls = 0
+
+    def fk_tip(self, x):
+        return self.orc.fk_batch(self.rb.orb, np.ascontiguousarray(x)[None], 128, want_p=False)["tip"][0]
+
+    def state_valid(self, x):
+        st, fl = self.orc.voxelize_vertices_batch(self.rb.orb, self.ogrid, np.ascontiguousarray(x)[None])
+        return fl[0] == 0 and not self.orc.check_sets_batch(st, self.oenv)[0]
+
+    def until_invalid(self, a, b):
+        self.edge_calls += 1
+        _, info = self.orc.voxelize_edge(self.rb.orb, self.ogrid, self.orc.space(), a.copy(), b.copy(), env=self.oenv)
+        lv = a + (b - a) * info["t"]
+        return dict(fully=info["is_fully_valid"], last_valid=lv, tip=self.fk_tip(lv))
+
+    def find(self, x):
+        for v, s in enumerate(self.states):
+            if self.alive[v] and np.all(np.abs(s - x) <= 2 * np.finfo(float).eps):
+                return v
+        return -1
+
+    def add(self, x):          # addMilestone(state, false, &was_added)
+        v = self.find(x)
+        if v >= 0:
+            return v, False
+        self.states.append(x.copy())
+        self.alive.append(True)
+        self.tips.append(np.zeros(3))
+        return len(self.states) - 1, True
+
+    def remove(self, v):
+        self.alive[v] = False
+        for e in [e for e in self.edges if v in e]:
+            del self.edges[e]
+
+    def degree(self, v):
+        return sum(1 for e in self.edges if v in e)
+
+    def conn(self, v, skip_self=False):     # connectionStrategy_(v) = KBoundedStrategy over nn_
+        cand = [(self.dist(self.states[v], self.states[u]), u) for u in range(len(self.states))
+                if self.alive[u] and not (skip_self and u == v)]
+        return [u for d, u in sorted(cand)[:self.kconn] if d <= self.bound]
+
+    def nearest_of(self, vertex, ik_nb, accurate):
+        if not accurate:
+            return [ik_nb]
+        out = self.conn(vertex)
+        return out if ik_nb in out else out + [ik_nb]
+
+    def run(self, request, tol, k, auto_add=False, accurate=False, lazy_add=False):
+        while True:
+            cand = sorted((float(np.linalg.norm(self.tips[v] - request)), v) for v in range(len(self.states)) if self.alive[v])
+            nbs = [v for _, v in cand[:k]]
+            bad = [v for v in nbs if not self.state_valid(self.states[v])]
+            for v in bad:
+                self.remove(v)
+            if not bad:
+                break
+        res = []
+        for i, nbv in enumerate(nbs):
+            fin = self.solver(self.states[nbv].copy(), request, lambda st: self.orc.tip_jacobian(self.rb.orb, st, 2, 1e-6))
+            tip = self.fk_tip(fin)
+            r = dict(i=i, nbv=nbv, fin=fin, tip=tip, err=float(np.linalg.norm(tip - request)), ok=self.state_valid(fin),
+                     nearest=[], pes=[])
+            res.append(r)
+            if r["ok"] and r["err"] < tol and not auto_add:
+                return dict(kind="accepted", i=i, controls=fin, tip=tip, error=r["err"])
+            if r["err"] < tol and auto_add:
+                vertex, was_added = self.add(fin)
+                if self.degree(vertex) > 0:
+                    return dict(kind="already", i=i, controls=fin, tip=tip, error=r["err"])
+                for src in self.nearest_of(vertex, nbv, accurate):
+                    if not self.state_valid(self.states[src]):
+                        if src != vertex:
+                            self.remove(src)
+                        continue
+                    if src == vertex:
+                        self.tips[vertex] = tip
+                        return dict(kind="self", i=i, controls=fin, tip=tip, error=r["err"], vertex=vertex)
+                    r["nearest"].append(src)
+                    r["pes"].append(self.until_invalid(self.states[src], fin))
+                    if r["pes"][-1]["fully"]:
+                        self.edges[frozenset((src, vertex))] = 1
+                        self.tips[vertex] = tip
+                        return dict(kind="connected", i=i, controls=fin, tip=tip, error=r["err"], vertex=vertex, source=src)
+                if was_added:
+                    self.remove(vertex)
+        if not auto_add:
+            oks = [r for r in res if r["ok"]]
+            if oks:
+                best = oks[0]
+                for r in oks[1:]:
+                    if r["err"] < best["err"]:
+                        best = r
+                return dict(kind="closest_valid", i=best["i"], controls=best["fin"], tip=best["tip"], error=best["err"])
+            best = None
+            for r in res:
+                vertex, was_added = self.add(r["fin"])
+                for src in self.nearest_of(vertex, r["nbv"], accurate):
+                    if not self.state_valid(self.states[src]):
+                        if src != vertex:
+                            self.remove(src)
+                        continue
+                    pe = self.until_invalid(self.states[src], r["fin"])
+                    e = float(np.linalg.norm(pe["tip"] - request))
+                    if best is None or e < best[0]:
+                        best = (e, r, pe, src)
+                if was_added:
+                    self.remove(vertex)
+            if best is None:
+                return None
+            return dict(kind="stepped_back", i=best[1]["i"], controls=best[2]["last_valid"], tip=best[2]["tip"], error=best[0],
+                        source=best[3])
+        best = None
+        for r in res:
+            if not r["nearest"]:
+                vertex, was_added = self.add(r["fin"])
+                if not was_added:
+                    continue
+                for src in self.nearest_of(vertex, r["nbv"], accurate):
+                    if not self.state_valid(self.states[src]):
+                        if src != vertex:
+                            self.remove(src)
+                        continue
+                    r["nearest"].append(src if src != vertex else -1)
+                    r["pes"].append(self.until_invalid(self.states[src], r["fin"]))
+                self.remove(vertex)
+            for src, pe in zip(r["nearest"], r["pes"]):
+                e = float(np.linalg.norm(pe["tip"] - request))
+                if best is None or e < best[0]:
+                    best = (e, r, pe, src)
+        if best is None:
+            return None
+        e, r, pe, src = best
+        vertex = self.find(pe["last_valid"])
+        added = vertex < 0
+        if added:
+            self.states.append(pe["last_valid"].copy())
+            self.alive.append(True)
+            self.tips.append(r["tip"].copy())
+            vertex = len(self.states) - 1
+            for n in self.conn(vertex, skip_self=True):          # addMilestone(state, true): not yet in nn_
+                self.edges.setdefault(frozenset((vertex, n)), 0)
+        if src >= 0 and vertex != src:
+            self.edges[frozenset((src, vertex))] = 1
+            if not lazy_add:
+                for ed in [ed for ed in self.edges if vertex in ed]:
+                    if self.edges[ed] != 1:
+                        a, b = sorted(ed)
+                        # computeEdgeValidity: voxelizeEdge (stored source -> target) + collides
+                        u, w = (vertex, b if a == vertex else a)
+                        st, info = self.orc.voxelize_edges_batch(self.rb.orb, self.ogrid, self.orc.space(),
+                                                                 self.states[u][None], self.states[w][None])
+                        if (info["flags"][0] & 16) == 0 and not self.orc.check_sets_batch(st, self.oenv)[0]:
+                            self.edges[ed] = 1
+                        else:
+                            del self.edges[ed]
+        return dict(kind="fallback", i=r["i"], controls=pe["last_valid"], tip=pe["tip"], error=e, source=src,
+                    vertex=vertex if added else None)
+
+
+def _graph_of(prm):
+    alive = ~prm.vertex_removed if len(prm.vertex_removed) == len(prm.states) else np.ones(len(prm.states), bool)
+    edges = {}
+    for e, (a, b) in enumerate(prm.edges.tolist()):
+        if not prm.edge_removed[e] and alive[a] and alive[b]:
+            edges[frozenset((a, b))] = int(prm.edge_validity[e])
+    return alive.tolist(), edges
+
+
+@pytest.mark.parametrize("accurate", [False, True])
+def test_roadmap_ik_every_branch_vs_sequential_reference(orc, wl, monkeypatch, accurate):
+    """Every branch of roadmapIk (VoxelCachedLazyPRM.cpp:3095-3565) -- accepted, closest valid, stepping back, auto_add
+    connected / the closest collision-free connection with and without RMAP_IK_LAZY_ADD, each with and without
+    RMAP_IK_ACCURATE -- against the reference's sequential loop restated over the oracle (_SeqPlanner): the same
+    result (which neighbour, controls, tip, error), the same vertices removed, the same vertices and edges added
+    with the same validity; and the batched mirror answered every edge with ONE until-invalid call."""
+    from irt_b200 import roadmap as R
+    spec = wl.robot_b(0.003)
+    g = wl.workspace_grid(spec)
+    ogrid = orc.grid(g["Ng"], g["lim"])
+    oenv = orc.octree(ogrid)
+    oenv.add_sphere([0.05, 0.0, 0.12], 0.03)
+    oenv.add_sphere([-0.04, 0.03, 0.14], 0.025)
+    lb, ub = np.zeros(7), np.array([20.0] * 6 + [spec["L"]])
+    solver = _dls_solver(lb, ub)
+    seen, stats = set(), {}
+
+    def fresh():
+        prm = _prm(R, orc, wl, spec, g, oenv, monkeypatch)
+        prm.world = 1
+        prm.createRoadmap(90, lambda cnt, rnd: wl.sample_states(spec, cnt, stream=1200 + rnd),
+                          lambda st: wl.knn_edges(spec, st, k=4), opt=R.VoxelizeVertices)
+        prm.precomputeVertexVoxelCache()
+        return prm
+
+    base = fresh()
+    rng = np.random.default_rng(11)
+    requests = []
+    for _ in range(5):                                     # reachable tips near roadmap vertices
+        goal = np.clip(base.states[rng.integers(90)] + rng.normal(size=7) * [1, 1, 1, 1, 1, 1, 0.004], lb, ub)
+        requests.append(orc.fk_batch(base.robot.orb, goal[None], 128, want_p=False)["tip"][0])
+    requests.append(np.array([0.05, 0.0, 0.12]))           # the centre of an obstacle: every result collides
+    requests.append(np.array([-0.04, 0.03, 0.14]))
+    requests.append(np.array([0.12, 0.12, 0.19]))          # out of reach: no result within tolerance
+    for request in requests:
+        for auto_add, lazy_add in ((False, False), (True, False), (True, True)):
+            prm = fresh()
+            seq = _SeqPlanner(orc, prm.robot, ogrid, oenv, prm, solver)
+            nv = len(prm.states)
+            want = seq.run(request, 1e-4, 4, auto_add=auto_add, accurate=accurate, lazy_add=lazy_add)
+            calls0 = []
+            orig = _Store.voxelize_edges_until_invalid
+
+            def counted(self, *a, **kw):
+                calls0.append(1)
+                return orig(self, *a, **kw)
+            monkeypatch.setattr(_Store, "voxelize_edges_until_invalid", counted)
+            got = prm.roadmapIk(request, 1e-4, 4, solver, auto_add=auto_add, accurate=accurate, lazy_add=lazy_add)
+            monkeypatch.setattr(_Store, "voxelize_edges_until_invalid", orig)
+            assert len(calls0) <= 1, "every until-invalid edge of a query belongs in one batch"
+            if want is None:
+                assert got is None
+                seen.add("none")
+                continue
+            seen.add(want["kind"])
+            assert got is not None and got["index"] == want["i"], (want["kind"], got["index"], want["i"])
+            assert np.array_equal(got["controls"], want["controls"]) and np.array_equal(got["tip_position"], want["tip"])
+            assert got["error"] == want["error"]
+            assert bool(got.get("stepped_back")) == (want["kind"] in ("stepped_back", "fallback"))
+            if "source" in want and want["source"] >= 0:
+                assert got["source"] == want["source"]
+            # the graph afterwards: same vertices alive, same states, same edges with the same validity
+            alive, edges = _graph_of(prm)
+            # the sequential planner appends temporary vertices and kills them again: compare the living ones in order
+            live_seq = [v for v in range(len(seq.states)) if seq.alive[v]]
+            live_got = [v for v in range(len(prm.states)) if alive[v]]
+            assert len(live_seq) == len(live_got)
+            remap = dict(zip(live_seq, live_got))
+            for a, b in remap.items():
+                assert np.array_equal(seq.states[a], prm.states[b])
+            assert live_got[:len([v for v in live_got if v < nv])] == [v for v in live_seq if v < nv], "removed vertices differ"
+            want_edges = {frozenset(remap[x] for x in ed): val for ed, val in seq.edges.items()}
+            assert want_edges == edges, (want["kind"], set(want_edges) ^ set(edges))
+            if want["kind"] in ("connected", "fallback") and want.get("vertex") is not None:
+                assert got["added_vertex"] == remap[want["vertex"]]
+                assert np.array_equal(prm.tips[got["added_vertex"]], seq.tips[want["vertex"]])
+                mine = [val for ed, val in edges.items() if got["added_vertex"] in ed]
+                stats[(want["kind"], lazy_add)] = stats.get((want["kind"], lazy_add), []) + [(len(mine), sum(mine))]
+    # with RMAP_IK_ACCURATE the result's own (temporary) vertex is the first of its nearest milestones -- it is in
+    # nn_ by then -- so the reference returns at "State already in the roadmap" before it connects anything
+    need = {"accepted", "closest_valid", "stepped_back", "self" if accurate else "connected", "fallback"}
+    assert need <= seen, "fixture must reach every branch: missing %s" % (need - seen)
+    # the closest collision-free connection joins the roadmap with several lazily connected edges: unknown validity
+    # with RMAP_IK_LAZY_ADD, else all validated (the invalid ones removed, so fewer remain)
+    lazy, eager = stats[("fallback", True)], stats[("fallback", False)]
+    assert any(n > 1 and valid == 1 for n, valid in lazy) and all(n == valid for n, valid in eager)
+    assert sum(n for n, _ in eager) < sum(n for n, _ in lazy), "no lazily connected edge was found invalid"
