@@ -891,6 +891,24 @@ private:
   tendon::TendonResult home_;
 };
 
+/// OMPL compound interpolate of the space of Problem.cpp:101-163 restated (RealVector linear, SO2 shortest arc + wrap)
+inline std::vector<double> interpolate_states(const tendon::TendonRobot &robot, const std::vector<double> &a,
+                                              const std::vector<double> &b, double t) {
+  std::vector<double> out(a.size());
+  const size_t N = robot.tendons.size();
+  for (size_t i = 0; i < a.size(); i++) out[i] = a[i] + (b[i] - a[i]) * t;
+  if (robot.enable_rotation) {
+    double diff = b[N] - a[N];
+    if (std::fabs(diff) > M_PI) {
+      diff = (diff > 0.0) ? 2.0 * M_PI - diff : -2.0 * M_PI - diff;
+      double v = a[N] - diff * t;
+      if (v > M_PI) v -= 2.0 * M_PI; else if (v < -M_PI) v += 2.0 * M_PI;
+      out[N] = v;
+    }
+  }
+  return out;
+}
+
 /// AbstractVoxelMotionValidator / VoxelBackboneMotionValidator (AbstractVoxelMotionValidator.h:32-193,
 /// VoxelBackboneMotionValidator.cpp:19-91); the OMPL space constants come from irt_space
 class VoxelBackboneMotionValidator {
@@ -956,21 +974,8 @@ public:
     irt_robot_desc d = robot_.desc();
     return irt_valid_segment_count(&d, &space_, a.data(), b.data());
   }
-  /// OMPL compound interpolate restated (RealVector linear, SO2 shortest arc + wrap)
   std::vector<double> interpolate(const std::vector<double> &a, const std::vector<double> &b, double t) const {
-    std::vector<double> out(a.size());
-    const size_t N = robot_.tendons.size();
-    for (size_t i = 0; i < a.size(); i++) out[i] = a[i] + (b[i] - a[i]) * t;
-    if (robot_.enable_rotation) {
-      double diff = b[N] - a[N];
-      if (std::fabs(diff) > M_PI) {
-        diff = (diff > 0.0) ? 2.0 * M_PI - diff : -2.0 * M_PI - diff;
-        double v = a[N] - diff * t;
-        if (v > M_PI) v -= 2.0 * M_PI; else if (v < -M_PI) v += 2.0 * M_PI;
-        out[N] = v;
-      }
-    }
-    return out;
+    return interpolate_states(robot_, a, b, t);
   }
 
 private:
@@ -1312,6 +1317,10 @@ public:
     size_t index = 0, vertex = 0;   // which of the k neighbours (nearest first) / its roadmap vertex
     size_t lockstep_batches = 0, fk_requests = 0;
     bool accepted = true;           // false: no result within tolerance, the closest valid one is returned
+    bool stepped_back = false;      // controls = the last valid state of the edge source -> result
+    long source = -1;               // the roadmap vertex that edge starts from (-1: none, or the result itself)
+    long added_vertex = -1;         // RMAP_IK_AUTO_ADD: the vertex that joined the roadmap (-1: none)
+    bool already_in_roadmap = false;
   };
   /// nnTip_->nearestK: the k vertices whose cached tip positions are nearest to the request (exact)
   std::vector<size_t> nearestTips(const collision::Point &request, size_t k) {
@@ -1330,16 +1339,45 @@ public:
     for (size_t i = 0; i < k; i++) out.push_back(d[i].second);
     return out;
   }
-  /// roadmapIk(request, tolerance, k) of the reference (RMAP_IK_SIMPLE) with its per-neighbour loop turned into
-  /// batches: the k nearest VALID neighbours in tip space (invalid ones are removed and the query repeated;
+  enum RoadmapIkOpts : unsigned {   // VoxelCachedLazyPRM.h:364-381
+    RMAP_IK_SIMPLE = 0x0,     // no extra features
+    RMAP_IK_AUTO_ADD = 0x1,   // add the IK result to the roadmap, only return one that connects
+    RMAP_IK_ACCURATE = 0x2,   // try to connect from the connection-strategy neighbours, not only the IK neighbour
+    RMAP_IK_LAZY_ADD = 0x4,   // do not validate the lazily connected edges of the added vertex
+  };
+  /// CompoundStateSpace::enforceBounds of the space of Problem.cpp:101-163
+  std::vector<double> enforceBounds(std::vector<double> x) const {
+    const size_t N = robot_.tendons.size();
+    for (size_t j = 0; j < N; j++) x[j] = std::min(robot_.tendons[j].max_tension, std::max(0.0, x[j]));
+    size_t kk = N;
+    if (robot_.enable_rotation) {   // SO2StateSpace::enforceBounds
+      double v = std::fmod(x[kk], 2.0 * M_PI);
+      if (v < -M_PI) v += 2.0 * M_PI; else if (v >= M_PI) v -= 2.0 * M_PI;
+      x[kk++] = v;
+    }
+    if (robot_.enable_retraction) x[kk] = std::min(robot_.specs.L, std::max(0.0, x[kk]));
+    return x;
+  }
+  /// roadmapIk(request, tolerance, k, opt) of the reference (.cpp:3095-3565) with its per-neighbour loop turned
+  /// into batches: the k nearest VALID neighbours in tip space (invalid ones are removed and the query repeated;
   /// validity = table look-ups), the k IK problems solved side by side with their FK requests answered in
   /// lockstep (tip_control::solve_ik_lockstep), ONE FK + is_valid_shape + voxelise + collides call over the k
-  /// results, acceptance in the reference's order: the first neighbour (nearest first) whose result is valid and
-  /// within tolerance; failing that the closest valid result; std::nullopt when every result is invalid (the
-  /// reference then steps back along the edges; see the Python mirror for that branch and for RMAP_IK_AUTO_ADD).
+  /// results, ONE voxelize_until_invalid call over every would-be edge source -> result that the branches below
+  /// can ask for, then the reference's order of acceptance walked over those tables:
+  ///  * without RMAP_IK_AUTO_ADD the first neighbour (nearest first) whose result is valid and within tolerance;
+  ///    failing that the closest valid result; failing that the closest last-valid state of the edges
+  ///    source -> result ("stepping them backwards", .cpp:3298-3428);
+  ///  * with it the first result within tolerance that a fully valid edge connects to a valid source joins the
+  ///    roadmap with that edge (.cpp:3212-3292); failing that the closest last-valid state over the edges of ALL
+  ///    results joins it, connected to its source and, lazily, to its connection-strategy neighbours, whose
+  ///    edges are validated unless RMAP_IK_LAZY_ADD (.cpp:3430-3565).
+  /// Sources per result: the IK neighbour, or with RMAP_IK_ACCURATE connectionStrategy_(vertex) -- the result's
+  /// own temporary vertex among them, it is in nn_ by then -- plus the IK neighbour.  Sources found invalid on
+  /// the way are removed (removeVertices).  std::nullopt where the reference would index an empty list.
   std::optional<IKResult> roadmapIk(const collision::Point &request, double tolerance, size_t k,
                                     const tip_control::IkSolver &solver, int mode = IRT_JAC_LEVMAR_CENTRAL,
-                                    double delta = 1e-6) {
+                                    double delta = 1e-6, unsigned opt = RMAP_IK_SIMPLE) {
+    const bool auto_add = opt & RMAP_IK_AUTO_ADD, accurate = opt & RMAP_IK_ACCURATE, lazy_add = opt & RMAP_IK_LAZY_ADD;
     std::vector<size_t> nb;
     for (;;) {
       nb = nearestTips(request, k);
@@ -1366,24 +1404,264 @@ public:
                                            flags.data(), tips.data()));
     irt::check(ctx_, irt_check_sets(ctx_, scratch, env_, 0, (int64_t)m, words.data()));
     const uint32_t bad = IRT_FLAG_NONCONVERGED | IRT_FLAG_LENGTH_LIMIT | IRT_FLAG_SELF_COLLISION | IRT_FLAG_BAD_STATE;
-    std::optional<IKResult> best;
-    for (size_t i = 0; i < m; i++) {
-      const bool valid = !(flags[i] & bad) && !((words[i >> 5] >> (i & 31)) & 1u);
+    auto tip_error = [&](const double *t) {
       double e2 = 0.0;
-      for (int c = 0; c < 3; c++) e2 += (tips[3 * i + c] - request[c]) * (tips[3 * i + c] - request[c]);
+      for (int c = 0; c < 3; c++) e2 += (t[c] - request[c]) * (t[c] - request[c]);
+      return std::sqrt(e2);
+    };
+    std::vector<char> valid(m);
+    std::vector<double> err(m);
+    auto result = [&](size_t i) {
       IKResult r;
       r.controls = finals[i]; r.tip_position = {tips[3 * i], tips[3 * i + 1], tips[3 * i + 2]};
-      r.neighbor = starts[i]; r.error = std::sqrt(e2); r.index = i; r.vertex = nb[i];
+      r.neighbor = starts[i]; r.error = err[i]; r.index = i; r.vertex = nb[i];
       r.lockstep_batches = batches; r.fk_requests = requests;
-      if (!valid) continue;
-      if (r.error < tolerance) return r;                       // "we've found a good one!"
-      r.accepted = false;
-      if (!best || r.error < best->error) best = r;            // "returning closest valid one"
+      return r;
+    };
+    for (size_t i = 0; i < m; i++) {
+      valid[i] = !(flags[i] & bad) && !((words[i >> 5] >> (i & 31)) & 1u);
+      err[i] = tip_error(&tips[3 * i]);
+    }
+    if (!auto_add) {
+      std::optional<IKResult> best;
+      for (size_t i = 0; i < m; i++) {
+        if (!valid[i]) continue;
+        if (err[i] < tolerance) return result(i);                // "we've found a good one!"
+        if (!best || err[i] < best->error) { best = result(i); best->accepted = false; }
+      }
+      if (best) return best;                                     // "returning closest valid one"
+    }
+
+    // ---- the would-be edges: sources per result in the reference's order; the validity look-ups and removals
+    // are replayed on a copy first so that ONE until-invalid batch answers every edge the walk may ask for
+    build_adjacency();
+    struct Row { long s; bool is_self, ok; };   // s = -1: the result's own temporary vertex
+    std::vector<std::vector<double>> bounded(m);
+    std::vector<long> own(m);
+    for (size_t i = 0; i < m; i++) { bounded[i] = enforceBounds(finals[i]); own[i] = findState(bounded[i]); }
+    std::vector<char> removed = vertex_removed_;
+    std::vector<char> in_first(m, 0);
+    for (size_t i = 0; i < m; i++) in_first[i] = !auto_add || err[i] < tolerance;
+    auto plan_result = [&](size_t i) {
+      std::vector<Row> rows;
+      for (long s : ikNearest(bounded[i], own[i], nb[i], accurate, removed)) {
+        const bool is_self = s < 0 || s == own[i];
+        const bool ok = s < 0 ? (bool)valid[i] : computeVertexValidity((size_t)s);
+        if (!ok && !is_self) removed[(size_t)s] = 1;
+        rows.push_back({s, is_self, ok});
+      }
+      return rows;
+    };
+    std::vector<std::vector<Row>> plan1(m), plan3(m);
+    std::vector<std::pair<size_t, long>> jobs;
+    auto add_job = [&](size_t i, long s) {
+      if (std::find(jobs.begin(), jobs.end(), std::make_pair(i, s)) == jobs.end()) jobs.emplace_back(i, s);
+    };
+    for (size_t i = 0; i < m; i++) {
+      if (!in_first[i] || (auto_add && own[i] >= 0 && outDegree((size_t)own[i]) > 0)) continue;
+      plan1[i] = plan_result(i);
+      for (auto &r : plan1[i]) if (r.ok && !(auto_add && r.is_self)) add_job(i, r.s);
+    }
+    if (auto_add)   // the fallback asks again for the results the loop above left without sources
+      for (size_t i = 0; i < m; i++) {
+        bool any = false;
+        for (auto &r : plan1[i]) any = any || (r.ok && !r.is_self);
+        if (own[i] < 0 && !any) {
+          plan3[i] = plan_result(i);
+          for (auto &r : plan3[i]) if (r.ok) add_job(i, r.s);
+        }
+      }
+    struct Partial { bool fully_valid; std::vector<double> last_valid; collision::Point tip; double error; };
+    std::map<std::pair<size_t, long>, Partial> pe_of;
+    if (!jobs.empty()) {
+      const size_t nj = jobs.size();
+      std::vector<double> a(nj * S), b(nj * S), t_last(nj);
+      std::vector<uint32_t> fl(nj);
+      for (size_t j = 0; j < nj; j++) {
+        const std::vector<double> &src = jobs[j].second < 0 ? bounded[jobs[j].first] : states_[(size_t)jobs[j].second];
+        std::copy(src.begin(), src.end(), a.begin() + j * S);
+        std::copy(finals[jobs[j].first].begin(), finals[jobs[j].first].end(), b.begin() + j * S);
+      }
+      irt::check(ctx_, irt_voxelize_edges_until_invalid(ctx_, robot_.handle(), &space_, a.data(), b.data(), (int)S,
+                                                        (int64_t)nj, env_, scratch, fl.data(), t_last.data(), nullptr));
+      std::vector<std::vector<double>> lv(nj);
+      for (size_t j = 0; j < nj; j++)
+        lv[j] = interpolate_states(robot_, std::vector<double>(a.begin() + j * S, a.begin() + (j + 1) * S),
+                                   std::vector<double>(b.begin() + j * S, b.begin() + (j + 1) * S), t_last[j]);
+      auto shapes = robot_.shape_batch(lv);                      // last_backbone.back()
+      for (size_t j = 0; j < nj; j++) {
+        const collision::Point tip = shapes[j].p.back();
+        pe_of[jobs[j]] = Partial{!(fl[j] & IRT_FLAG_PARTIAL), lv[j], tip, tip_error(tip.data())};
+      }
+    }
+    // the valid sources of a result in order, with the removals the reference makes on the way; fn returns true
+    // where the reference returns (nothing after that point is looked at)
+    auto walk = [&](const std::vector<Row> &rows, const std::function<bool(long, bool)> &fn) {
+      for (auto &r : rows) {
+        if (!r.ok) { if (!r.is_self) vertex_removed_[(size_t)r.s] = 1; continue; }
+        if (fn(r.s, r.is_self)) return true;
+      }
+      return false;
+    };
+    auto stepped = [&](size_t i, long s, const Partial &e) {
+      IKResult r = result(i);
+      r.controls = e.last_valid; r.tip_position = e.tip; r.error = e.error;
+      r.accepted = false; r.stepped_back = true; r.source = s;
+      return r;
+    };
+    if (!auto_add) {   // "All IKs are in collision, stepping them backwards"
+      std::optional<IKResult> best;
+      for (size_t i = 0; i < m; i++)
+        walk(plan1[i], [&](long s, bool) {
+          const Partial &e = pe_of.at({i, s});
+          if (!best || e.error < best->error) best = stepped(i, s, e);
+          return false;
+        });
+      return best;
+    }
+    auto keep_vertex = [&](size_t i) {   // the result's vertex stays in the roadmap with its caches
+      if (own[i] >= 0) {
+        for (int c = 0; c < 3; c++) tips_[3 * (size_t)own[i] + c] = tips[3 * i + c];
+        vertex_validity_[(size_t)own[i]] = VALIDITY_TRUE;
+        return (size_t)own[i];
+      }
+      return appendVertex(bounded[i], &tips[3 * i]);
+    };
+    std::vector<std::vector<long>> nearest(m);
+    for (size_t i = 0; i < m; i++) {
+      if (!in_first[i]) continue;
+      if (own[i] >= 0 && outDegree((size_t)own[i]) > 0) {       // "IK result already part of the roadmap"
+        IKResult r = result(i); r.already_in_roadmap = true;
+        return r;
+      }
+      IKResult r = result(i);
+      const bool done = walk(plan1[i], [&](long s, bool is_self) {
+        if (is_self) {                                           // "State already in the roadmap, returning it."
+          const size_t v = keep_vertex(i);
+          if (own[i] < 0) r.added_vertex = (long)v; else r.already_in_roadmap = true;
+          return true;
+        }
+        nearest[i].push_back(s);
+        if (pe_of.at({i, s}).fully_valid) {                      // connect source -- result vertex
+          const size_t v = keep_vertex(i);
+          appendEdge((size_t)s, v, VALIDITY_TRUE);
+          if (own[i] < 0) r.added_vertex = (long)v;
+          r.source = s;
+          return true;
+        }
+        return false;
+      });
+      if (done) return r;
+    }
+    // "All IKs rejected, finding closest collision-free connection"
+    std::optional<IKResult> best;
+    const Partial *best_pe = nullptr;
+    for (size_t i = 0; i < m; i++) {
+      if (nearest[i].empty()) {
+        if (own[i] >= 0) continue;                               // "already part of the roadmap, no need to connect it"
+        walk(plan3[i], [&](long s, bool) { nearest[i].push_back(s); return false; });
+      }
+      for (long s : nearest[i]) {
+        const Partial &e = pe_of.at({i, s});
+        if (!best || e.error < best->error) { best = stepped(i, s, e); best_pe = &e; }
+      }
+    }
+    if (!best) return best;
+    const size_t bi = best->index;
+    const long s = best->source;
+    best->neighbor = s < 0 ? bounded[bi] : states_[(size_t)s];
+    long v = findState(best_pe->last_valid);
+    if (v < 0) {
+      // addMilestone(state, true): connected lazily to its connection-strategy neighbours (itself not yet in nn_)
+      std::vector<std::pair<double, size_t>> d;
+      for (size_t u = 0; u < states_.size(); u++)
+        if (!vertex_removed_[u]) d.emplace_back(distance(best_pe->last_valid, states_[u]), u);
+      const size_t kk = std::min(k_, d.size());
+      std::partial_sort(d.begin(), d.begin() + kk, d.end());
+      v = (long)appendVertex(best_pe->last_valid, &tips[3 * bi]);   // the reference caches the IK RESULT's tip here
+      for (size_t j = 0; j < kk && d[j].first <= getRange(); j++) appendEdge((size_t)v, d[j].second, VALIDITY_UNKNOWN);
+      best->added_vertex = v;
+    } else {
+      for (int c = 0; c < 3; c++) tips_[3 * (size_t)v + c] = tips[3 * bi + c];
+      vertex_validity_[(size_t)v] = VALIDITY_TRUE;
+    }
+    if (s >= 0 && v != s) {
+      const long e = edgeIndex((size_t)s, (size_t)v);
+      if (e < 0) appendEdge((size_t)s, (size_t)v, VALIDITY_TRUE); else edge_validity_[(size_t)e] = VALIDITY_TRUE;
+      if (!lazy_add) {   // every edge of the vertex is validated now, the invalid ones removed
+        build_adjacency();
+        std::vector<size_t> todo;
+        for (size_t q = adj_ptr_[(size_t)v]; q < adj_ptr_[(size_t)v + 1]; q++)
+          if (!edge_removed_[adj_eid_[q]] && !(edge_validity_[adj_eid_[q]] & VALIDITY_TRUE)) todo.push_back(adj_eid_[q]);
+        if (!todo.empty()) {
+          const size_t nt = todo.size();
+          std::vector<double> a(nt * S), b(nt * S);
+          for (size_t j = 0; j < nt; j++) {
+            std::copy(states_[edges_[todo[j]].first].begin(), states_[edges_[todo[j]].first].end(), a.begin() + j * S);
+            std::copy(states_[edges_[todo[j]].second].begin(), states_[edges_[todo[j]].second].end(), b.begin() + j * S);
+          }
+          std::vector<uint32_t> fl(nt), w((nt + 31) / 32 + 1, 0);
+          irt::check(ctx_, irt_voxelize_edges(ctx_, robot_.handle(), &space_, a.data(), b.data(), (int)S, (int64_t)nt,
+                                              scratch, fl.data(), nullptr, nullptr));
+          irt::check(ctx_, irt_check_sets(ctx_, scratch, env_, 0, (int64_t)nt, w.data()));
+          for (size_t j = 0; j < nt; j++) {
+            if (!(fl[j] & IRT_FLAG_PARTIAL) && !((w[j >> 5] >> (j & 31)) & 1u)) edge_validity_[todo[j]] = VALIDITY_TRUE;
+            else edge_removed_[todo[j]] = 1;
+          }
+        }
+      }
     }
     return best;
   }
 
 private:
+  /// tryAddToGraph (.cpp:2777-2801): the vertex whose state equals x (si_->equalStates), else -1
+  long findState(const std::vector<double> &x) const {
+    const double tol = 2.0 * std::numeric_limits<double>::epsilon();
+    for (size_t v = 0; v < states_.size(); v++) {
+      if (v < vertex_removed_.size() && vertex_removed_[v]) continue;
+      bool same = true;
+      for (size_t c = 0; c < x.size() && same; c++) same = std::fabs(states_[v][c] - x[c]) <= tol;
+      if (same) return (long)v;
+    }
+    return -1;
+  }
+  size_t outDegree(size_t v) {
+    build_adjacency();
+    size_t c = 0;
+    for (size_t q = adj_ptr_[v]; q < adj_ptr_[v + 1]; q++) c += !edge_removed_[adj_eid_[q]] && !vertex_removed_[adj_nbr_[q]];
+    return c;
+  }
+  /// `nearest` of .cpp:3238-3246, 3340-3349, 3470-3478; -1 stands for the result's own temporary vertex
+  std::vector<long> ikNearest(const std::vector<double> &x, long own, size_t ik_neighbor, bool accurate,
+                              const std::vector<char> &removed) const {
+    if (!accurate) return {(long)ik_neighbor};
+    std::vector<std::pair<double, size_t>> d;
+    for (size_t u = 0; u < states_.size(); u++)
+      if (!removed[u]) d.emplace_back(distance(x, states_[u]), u);
+    if (own < 0) d.emplace_back(0.0, states_.size());            // the temporary vertex: distance 0, the highest index
+    const size_t kk = std::min(k_, d.size());
+    std::partial_sort(d.begin(), d.begin() + kk, d.end());
+    std::vector<long> out;
+    for (size_t j = 0; j < kk && d[j].first <= getRange(); j++)
+      out.push_back(d[j].second == states_.size() ? -1L : (long)d[j].second);
+    if (std::find(out.begin(), out.end(), (long)ik_neighbor) == out.end()) out.push_back((long)ik_neighbor);
+    return out;
+  }
+  size_t appendVertex(const std::vector<double> &state, const double *tip) {
+    build_adjacency();
+    states_.push_back(state);
+    vertex_validity_.push_back(VALIDITY_TRUE);
+    vertex_removed_.push_back(0);
+    tips_.insert(tips_.end(), tip, tip + 3);
+    return states_.size() - 1;                                   // vflags_ is now shorter: the cache lacks the vertex
+  }
+  void appendEdge(size_t a, size_t b, unsigned validity) {
+    build_adjacency();
+    edges_.emplace_back(a, b);
+    edge_validity_.push_back(validity);
+    edge_removed_.push_back(0);
+  }
   size_t removed_count() const {
     size_t c = 0;
     for (char x : vertex_removed_) c += x != 0;

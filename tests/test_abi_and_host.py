@@ -205,6 +205,26 @@ def test_cpp_host_mirror_host_logic(tmp_path, orc):
     assert "host mirror ok" in out.stdout and "createRoadmap: 120 vertices" in out.stdout
 
 
+def test_cpp_roadmap_ik_every_branch(tmp_path, orc):
+    """roadmapIk of the C++ host mirror, every branch (accepted, closest valid, stepping back, RMAP_IK_AUTO_ADD connected
+    / the closest collision-free connection with and without RMAP_IK_LAZY_ADD, each with and without RMAP_IK_ACCURATE),
+    against the reference's sequential loop (VoxelCachedLazyPRM.cpp:3095-3565) restated over the oracle in
+    tests/cpp/test_roadmap_ik_host.cpp: the same result, removals, added vertices / edges and validity.  Host logic:
+    linked against the test-only stand-in of the C ABI."""
+    exe = str(tmp_path / "test_roadmap_ik_host")
+    cpp = os.path.join(ROOT, "tests", "cpp")
+    subprocess.check_call(["g++", "-std=c++17", "-O1", "-Wall", "-Wextra", "-Werror", "-DIRT_TEST_OVER_STANDIN",
+                           os.path.join(cpp, "test_roadmap_ik_host.cpp"),
+                           os.path.join(cpp, "abi_standin_over_oracle.cpp"), "-o", exe,
+                           "-L" + os.path.join(ROOT, "oracle"), "-loracle",
+                           "-Wl,-rpath," + os.path.join(ROOT, "oracle"), "-fopenmp"])
+    out = subprocess.run([exe], capture_output=True, text=True, timeout=900)
+    assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-2000:]
+    assert "roadmap ik ok" in out.stdout
+    for kind in ("accepted", "closest_valid", "stepped_back", "connected", "self", "fallback"):
+        assert kind in out.stdout
+
+
 def test_env_primitive_arithmetic_on_host(tmp_path, orc):
     """The per-leaf-block arithmetic the device kernel env_add_primitives_kernel runs (csrc/env_prims.h: voxel
     centres inside spheres / capsules, add_point cells) compiled for the host with -ffp-contract=off and
