@@ -856,7 +856,10 @@ def main():
             edge_check["low_collision_env"] = {
                 "occupied_block_fraction": float(np.count_nonzero(env_lo)) / env_lo.size,
                 "collision_fraction": float(lw.mean()), "ms_per_sweep": ms_lo,
-                "value": ne / (ms_lo * 1e-3), "roofline_frac": (alg_bytes / (ms_lo * 1e-3) / 1e9) / hbm_peak if world == 1 else None}
+                "value": ne / (ms_lo * 1e-3), "roofline_frac": (alg_bytes / (ms_lo * 1e-3) / 1e9) / hbm_peak if world == 1 else None,
+                "note": "same store, fewer hits: the sweep is a read-only stream and the peak is a COPY bandwidth (reads "
+                        "and writes share the bus), so a fraction a few percent above 1 is the read-only margin, not "
+                        "skipped work; every verdict is still compared with the NCCL / unsharded path"}
             prm.setEnvironment(env_blocks)
             k3_step_nccl()
             torch.cuda.synchronize()
