@@ -859,7 +859,7 @@ def main():
                 "value": ne / (ms_lo * 1e-3), "roofline_frac": (alg_bytes / (ms_lo * 1e-3) / 1e9) / hbm_peak if world == 1 else None,
                 "note": "same store, fewer hits: the sweep is a read-only stream and the peak is a COPY bandwidth (reads "
                         "and writes share the bus), so a fraction a few percent above 1 is the read-only margin, not "
-                        "skipped work; every verdict is still compared with the NCCL / unsharded path"}
+                        "skipped work (the sweep streams the same leaves whatever the environment holds)"}
             prm.setEnvironment(env_blocks)
             k3_step_nccl()
             torch.cuda.synchronize()
