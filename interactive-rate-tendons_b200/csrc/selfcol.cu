@@ -10,71 +10,11 @@
 // chunk pairs whose spheres come within 2r (+margin) have their 64 capsule pairs examined
 // with the reference's arithmetic.  The verdict (any pair collides) is unchanged.
 #include "common.cuh"
+#include "capsule_pair.h"
 
 namespace {
 
 constexpr int SC_WARPS = 4;
-constexpr int SC_CHUNK = 8;
-
-struct P3 {
-  double x, y, z;
-};
-__device__ __forceinline__ P3 sub3(const P3 &a, const P3 &b) { return {a.x - b.x, a.y - b.y, a.z - b.z}; }
-__device__ __forceinline__ double dot3(const P3 &a, const P3 &b) { return (a.x * b.x + a.y * b.y) + a.z * b.z; }
-__device__ __forceinline__ double bound01(double t) { return fmax(0.0, fmin(1.0, t)); }
-
-// closest_st_segment -- collision/collision_primitives.cpp:10-102
-__device__ void closest_st(const P3 &A, const P3 &B, const P3 &C, const P3 &D, double &s, double &t) {
-  const double eps = 2.220446049250313e-16;
-  const double eps2 = eps * eps;
-  const P3 AB = sub3(B, A), CD = sub3(D, C);
-  const double a = dot3(AB, AB), c = dot3(CD, CD);
-  if (a <= eps2) {
-    s = 0.0;
-    t = (c <= eps2) ? 0.0 : bound01(dot3(CD, sub3(A, C)) / c);
-    return;
-  }
-  if (c <= eps2) {
-    s = bound01(dot3(AB, sub3(C, A)) / a);
-    t = 0.0;
-    return;
-  }
-  const P3 AC = sub3(C, A);
-  const double b = dot3(AB, CD), d = dot3(AC, AB), e = dot3(AC, CD);
-  const double denom = fmax(0.0, a * c - b * b);
-  if (denom <= eps2) {
-    double tt = dot3(CD, sub3(A, C)) / c;
-    if (0.0 <= tt && tt <= 1.0) { s = 0.0; t = tt; return; }
-    tt = dot3(CD, sub3(B, C)) / c;
-    if (0.0 <= tt && tt <= 1.0) { s = 1.0; t = tt; return; }
-    double ss = dot3(AB, sub3(C, A)) / a;
-    if (0.0 <= ss && ss <= 1.0) { s = ss; t = 0.0; return; }
-    const P3 AD = sub3(D, A), BC = sub3(C, B), BD = sub3(D, B);
-    const double ac2 = dot3(AC, AC), ad2 = dot3(AD, AD), bc2 = dot3(BC, BC), bd2 = dot3(BD, BD);
-    if (ac2 <= ad2 && ac2 <= bc2 && ac2 <= bd2) { s = 0.0; t = 0.0; return; }
-    if (ad2 <= bc2 && ad2 <= bd2) { s = 0.0; t = 1.0; return; }
-    if (bc2 <= bd2) { s = 1.0; t = 0.0; return; }
-    s = 1.0; t = 1.0;
-    return;
-  }
-  const double ss = (c * d - b * e) / denom;
-  const double tt = (b * d - a * e) / denom;
-  if (0.0 <= tt && tt <= 1.0) { s = bound01(ss); t = tt; return; }
-  if (tt < 0.0) { s = bound01(-c / a); t = 0.0; return; }
-  s = bound01((b - c) / a);
-  t = 1.0;
-}
-
-// collides(Capsule, Capsule) -- collision/collision.hxx:102-108
-__device__ bool capsules_collide(const P3 &a0, const P3 &a1, const P3 &b0, const P3 &b1, double rr) {
-  double s, t;
-  closest_st(a0, a1, b0, b1, s, t);
-  const P3 dA = sub3(a1, a0), dB = sub3(b1, b0);
-  const P3 c1 = {a0.x + dA.x * s, a0.y + dA.y * s, a0.z + dA.z * s};
-  const P3 c2 = {b0.x + dB.x * t, b0.y + dB.y * t, b0.z + dB.z * t};
-  const P3 diff = sub3(c1, c2);
-  return dot3(diff, diff) <= (rr * rr);
-}
 
 // Stage 1 -- conservative FP32 pair filter, one warp per shape.  Every capsule pair (a, b) that can
 // survive the reference's 3r arc-length rule (exact index bound from the longest segment:
@@ -194,22 +134,13 @@ self_collision_kernel(const double *__restrict__ p, const int32_t *__restrict__ 
     // turned into the running sum (same sequential order as the reference) if it is ever needed
     double maxlen = 0.0;
     for (int i = lane; i < N; i += 32) {
-      double len = 0.0;
-      if (i > 0) {
-        const double dx = px[3 * i] - px[3 * i - 3], dy = px[3 * i + 1] - px[3 * i - 2],
-                     dz = px[3 * i + 2] - px[3 * i - 1];
-        len = sqrt((dx * dx + dy * dy) + dz * dz);
-      }
+      const double len = sc_segment_len(px, i);
       acc[i] = len;
       maxlen = fmax(maxlen, len);
     }
     for (int o = 16; o > 0; o >>= 1) maxlen = fmax(maxlen, __shfl_xor_sync(0xffffffffu, maxlen, o));
-    // Index pre-filter, exact: acc[b] - acc[a+1] is a sum of (b - a - 1) segment lengths, so it is
-    // below 3r whenever (b - a - 1) * maxlen is (with a 1e-9 safety factor for the rounding of the
-    // running sum): such pairs are skipped by the reference's own rule (collision.cpp:37-39).
-    // min_gap = smallest b - a - 1 that can survive the rule.
-    const double safe = dist_to_consider * (1.0 - 1e-9);
-    const int min_gap = (maxlen > 0.0) ? (int)fmin(1e6, floor(safe / maxlen)) : 1000000;
+    // min_gap = smallest b - a - 1 that can survive the reference's arc-length rule (capsule_pair.h)
+    const int min_gap = sc_min_gap(maxlen, dist_to_consider);
     __syncwarp();
     // chunk bounding spheres over capsules [c*8, c*8+8) i.e. points [c*8, min(c*8+8, N-1)]
     const int ncap = N - 1;

@@ -225,6 +225,23 @@ def test_cpp_roadmap_ik_every_branch(tmp_path, orc):
         assert kind in out.stdout
 
 
+def test_capsule_pair_arithmetic_on_host(tmp_path, orc):
+    """The arithmetic of the exact stage of the device self-collision test (csrc/capsule_pair.h: closest_st,
+    capsules_collide, segment lengths, the index-gap rule -- the file selfcol.cu includes) compiled for the host with
+    -ffp-contract=off: (s, t) of closest_st bit-equal to the oracle's closest_st_segment on 6 M segment pairs of every
+    kind, and the kernel's decision procedure composed serially (chunk bounding spheres, chunk-pair pruning, loop bounds,
+    arc-length rule, capsule test) equal to the oracle's collides_self on 61 k backbones that sit on its decision
+    boundaries (hairpins at 2r +- ulps, corners around the 3r rule, arcs, spirals, random walks)."""
+    exe = str(tmp_path / "test_capsule_pair_host")
+    subprocess.check_call(["g++", "-std=c++17", "-O2", "-ffp-contract=off", "-Wall", "-Wextra", "-Werror",
+                           os.path.join(ROOT, "tests", "cpp", "test_capsule_pair_host.cpp"), "-o", exe,
+                           "-L" + os.path.join(ROOT, "oracle"), "-loracle",
+                           "-Wl,-rpath," + os.path.join(ROOT, "oracle"), "-fopenmp"])
+    out = subprocess.run([exe], capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
+    assert "capsule pair ok" in out.stdout and ", 0 differ" in out.stdout and " 0 verdicts differ" in out.stdout
+
+
 def test_env_primitive_arithmetic_on_host(tmp_path, orc):
     """The per-leaf-block arithmetic the device kernel env_add_primitives_kernel runs (csrc/env_prims.h: voxel
     centres inside spheres / capsules, add_point cells) compiled for the host with -ffp-contract=off and
