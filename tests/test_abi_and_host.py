@@ -230,8 +230,9 @@ def test_capsule_pair_arithmetic_on_host(tmp_path, orc):
     capsules_collide, segment lengths, the index-gap rule -- the file selfcol.cu includes) compiled for the host with
     -ffp-contract=off: (s, t) of closest_st bit-equal to the oracle's closest_st_segment on 6 M segment pairs of every
     kind, and the kernel's decision procedure composed serially (chunk bounding spheres, chunk-pair pruning, loop bounds,
-    arc-length rule, capsule test) equal to the oracle's collides_self on 61 k backbones that sit on its decision
-    boundaries (hairpins at 2r +- ulps, corners around the 3r rule, arcs, spirals, random walks)."""
+    arc-length rule, capsule test) equal to the oracle's collides_self on 92 k backbones that sit on its decision
+    boundaries (hairpins at 2r +- ulps, corners around the 3r rule, arcs, spirals, random walks); the FP32 filter in
+    front of it, restated, never lets a backbone go that the oracle finds colliding."""
     exe = str(tmp_path / "test_capsule_pair_host")
     subprocess.check_call(["g++", "-std=c++17", "-O2", "-ffp-contract=off", "-Wall", "-Wextra", "-Werror",
                            os.path.join(ROOT, "tests", "cpp", "test_capsule_pair_host.cpp"), "-o", exe,
@@ -240,6 +241,7 @@ def test_capsule_pair_arithmetic_on_host(tmp_path, orc):
     out = subprocess.run([exe], capture_output=True, text=True, timeout=600)
     assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
     assert "capsule pair ok" in out.stdout and ", 0 differ" in out.stdout and " 0 verdicts differ" in out.stdout
+    assert "; 0 true hits dropped" in out.stdout
 
 
 def test_env_primitive_arithmetic_on_host(tmp_path, orc):
