@@ -178,6 +178,10 @@ class VoxelCachedLazyPRM:
         self.edge_removed = np.zeros(0, dtype=bool)
         self._adj = None
         self.lookups = {"vertex": 0, "edge": 0, "sweeps": 0}
+        # vertices / edges that joined the roadmap after the last sweep with VALIDITY_UNKNOWN (addMilestone's lazy
+        # connections): checked one at a time when a query first asks, like the reference's lazy checks
+        self._vertex_unchecked, self._edge_unchecked = set(), set()
+        self.max_uncached = 4096     # more items than this without a cached set: the next sweep rebuilds the cache
         self._flag_tables = {}
 
     def _exchange(self, store, slot_words):
@@ -440,24 +444,30 @@ class VoxelCachedLazyPRM:
     def precomputeVertexValidity(self):
         """vertexValidity = VALIDITY_TRUE iff the shape is valid and its voxels miss the
         environment (computeVertexValidity, VoxelCachedLazyPRM.cpp:2607-2618)."""
-        if not self._have_vcache:
+        if not self._have_vcache or self._tail(self.vertex_flags, len(self.states)) > self.max_uncached:
             self.precomputeVertexVoxelCache()
-        n = len(self.states)
+        n = len(self.states) - self._tail(self.vertex_flags, len(self.states))   # the sets the store holds
         collides = self._sweep(self.vertex_store, n, self.vertex_flags)
         invalid = self._gather_flags(self.vertex_flags, n, INVALID_MASK)
         self.vertex_validity = _validity_table(collides, invalid)
+        if n < len(self.states):     # vertices that joined since (roadmapIk / addMilestone): one small batch
+            self.vertex_validity = np.concatenate([self.vertex_validity, self._check_vertices_now(np.arange(n, len(self.states)))])
+        self._vertex_unchecked.clear()
         self._vertex_swept = True
         self.lookups["sweeps"] += 1
         return self.vertex_validity
 
     def precomputeEdgeValidity(self):
         """computeEdgeValidity (VoxelCachedLazyPRM.cpp:2620-2631): is_fully_valid and no hit."""
-        if not self._have_ecache:
+        if not self._have_ecache or self._tail(self.edge_flags, len(self.edges)) > self.max_uncached:
             self.precomputeEdgeVoxelCache()
-        n = len(self.edges)
+        n = len(self.edges) - self._tail(self.edge_flags, len(self.edges))
         collides = self._sweep(self.edge_store, n, self.edge_flags)
         invalid = self._gather_flags(self.edge_flags, n, FLAG_PARTIAL)
         self.edge_validity = _validity_table(collides, invalid)
+        if n < len(self.edges):
+            self.edge_validity = np.concatenate([self.edge_validity, self._check_edges_now(np.arange(n, len(self.edges)))])
+        self._edge_unchecked.clear()
         self._edge_swept = True
         self.lookups["sweeps"] += 1
         return self.edge_validity
@@ -471,6 +481,31 @@ class VoxelCachedLazyPRM:
         self.vertex_validity = np.zeros(len(self.states), dtype=np.uint8)
         self.edge_validity = np.zeros(len(self.edges), dtype=np.uint8)
         self._vertex_swept = self._edge_swept = False
+        self._vertex_unchecked.clear()
+        self._edge_unchecked.clear()
+
+    def _tail(self, flags, n_items):
+        """items that joined the roadmap after its voxel cache was built (roadmapIk / addMilestone, one rank): they
+        have no cached set; sweeps and look-ups answer them from small scratch batches until the cache is rebuilt"""
+        if self.world != 1 or flags is None:
+            return 0
+        return max(0, n_items - len(flags))
+
+    def _check_vertices_now(self, ids):
+        """voxelizeVertex + collides for a few vertices (VoxelCachedLazyPRM.cpp:2607-2618, 2803-2837): uint8 validity"""
+        ids = np.asarray(ids, dtype=np.int64)
+        scratch = SetStore(self.ctx, self.grid)
+        flags, _ = scratch.voxelize_vertices(self.robot, self.states[ids])
+        ok = ((flags & INVALID_MASK) == 0) & ~scratch.check(self.env)
+        return ok.astype(np.uint8) * np.uint8(VALIDITY_TRUE)
+
+    def _check_edges_now(self, ids):
+        """voxelizeEdge + collides for a few edges (VoxelCachedLazyPRM.cpp:2620-2631, 2879-2902): uint8 validity"""
+        ids = np.asarray(ids, dtype=np.int64)
+        scratch = SetStore(self.ctx, self.grid)
+        info = scratch.voxelize_edges_indexed(self.robot, self.space, self.states, self.edges[ids])
+        ok = ((info["flags"] & FLAG_PARTIAL) == 0) & ~scratch.check(self.env)
+        return ok.astype(np.uint8) * np.uint8(VALIDITY_TRUE)
 
     # ---- lazy-path consumers: what the planner's query side calls (SURVEY 8(f) row 2) --------------------
     def computeVertexValidity(self, v):
@@ -481,6 +516,10 @@ class VoxelCachedLazyPRM:
         if not self._vertex_swept:
             self.precomputeVertexValidity()
         self.lookups["vertex"] += 1
+        if v in self._vertex_unchecked:      # joined the roadmap after the sweep, never checked: the reference's lazy check
+            self._vertex_unchecked.discard(v)
+            self.vertex_validity[v] = self._check_vertices_now([v])[0]
+            self.lookups["single"] = self.lookups.get("single", 0) + 1
         return bool(self.vertex_validity[v] & VALIDITY_TRUE)
 
     def computeEdgeValidity(self, e):
@@ -489,6 +528,10 @@ class VoxelCachedLazyPRM:
         if not self._edge_swept:
             self.precomputeEdgeValidity()
         self.lookups["edge"] += 1
+        if e in self._edge_unchecked:
+            self._edge_unchecked.discard(e)
+            self.edge_validity[e] = self._check_edges_now([e])[0]
+            self.lookups["single"] = self.lookups.get("single", 0) + 1
         return bool(self.edge_validity[e] & VALIDITY_TRUE)
 
     def _adjacency(self):
@@ -654,15 +697,16 @@ class VoxelCachedLazyPRM:
             out.append(int(ik_neighbor))
         return out
 
-    def _append_vertex(self, state, tip):
+    def _append_vertex(self, state, tip, validity=VALIDITY_TRUE):
         v = len(self.states)
         self._adjacency()
         self.states = np.ascontiguousarray(np.concatenate([self.states, state[None]], axis=0))
-        self.vertex_validity = np.append(self.vertex_validity, np.uint8(VALIDITY_TRUE))
+        self.vertex_validity = np.append(self.vertex_validity, np.uint8(validity))
+        if not validity & VALIDITY_TRUE:
+            self._vertex_unchecked.add(v)
         self.vertex_removed = np.append(self.vertex_removed, False)
         self.tips = np.concatenate([self.tips, np.asarray(tip, dtype=np.float64)[None]], axis=0)
-        self._adj = None
-        self._have_vcache = False         # the cache lacks the new vertex
+        self._adj = None                  # the voxel cache lacks the new vertex: sweeps treat it as the tail (_tail)
         return v
 
     def _append_edges(self, pairs, validity):
@@ -671,8 +715,68 @@ class VoxelCachedLazyPRM:
         self.edges = np.ascontiguousarray(np.concatenate([self.edges, pairs], axis=0))
         self.edge_validity = np.append(self.edge_validity, np.full(len(pairs), validity, dtype=np.uint8))
         self.edge_removed = np.append(self.edge_removed, np.zeros(len(pairs), dtype=bool))
+        if not validity & VALIDITY_TRUE:
+            self._edge_unchecked.update(range(len(self.edges) - len(pairs), len(self.edges)))
         self._adj = None
-        self._have_ecache = False
+
+    def addMilestone(self, state, connect=True):
+        """addMilestone(state, connect) (VoxelCachedLazyPRM.cpp:1854-1885): the vertex of an equal state when the
+        roadmap has one (tryAddToGraph), else a new vertex with VALIDITY_UNKNOWN, lazily connected -- edges of unknown
+        validity -- to its connection-strategy neighbours (the k nearest milestones within the range; the vertex itself
+        is not in nn_ yet).  Nothing is voxelised here: queries check the new items when they first ask for them.
+        Returns (vertex, was_added)."""
+        if self.world != 1:
+            raise NotImplementedError("addMilestone runs on the full roadmap of one rank")
+        x = np.ascontiguousarray(state, dtype=np.float64)
+        self._adjacency()
+        v = self._find_state(x)
+        if v >= 0:
+            return v, False
+        conn = []
+        if connect and len(self.states):
+            d = np.where(self.vertex_removed, np.inf, self.distance(x, self.states))
+            order = np.lexsort((np.arange(len(d)), d))[:self.max_nearest_neighbors]
+            conn = [int(j) for j in order if d[j] <= (self.range or 0.2 * self.maximum_extent())]
+        if self.tips is None or len(self.tips) != len(self.states):
+            self.precomputeVertexVoxelCache()
+        tip = self.robot.shape_batch(x[None], want=("tip",))["tip"][0]
+        v = self._append_vertex(x, tip, VALIDITY_UNKNOWN)
+        if conn:
+            self._append_edges([[v, n] for n in conn], VALIDITY_UNKNOWN)
+        return v, True
+
+    def chainedPlan(self, start_state, requests, tolerance, k, solver, auto_add=True, accurate=False, lazy_add=False,
+                    mode=None, delta=1e-6, common_start=False):
+        """The milestone loop of apps/roadmap_chained_plan.cpp:535-679: for every requested tip position roadmapIk
+        gives the goal configuration, start and goal join the roadmap as milestones (solvePrep,
+        VoxelCachedLazyPRM.cpp:2978-3025), solveWithRoadmap plans between them, and the plan's last state is where the
+        next milestone starts (unless common_start).  Everything the loop asks of the device is a batch or a look-up:
+        the IK's lockstep FK launches, one validity call and one until-invalid call per request, table look-ups
+        along the A* path, and single checks only for the few items that joined the roadmap since the last sweep.
+        Returns one dict per request: ik (roadmapIk's result), status ('exact' / 'empty': no path, the plan stays
+        put), path (vertex list or None), plan (states), searches, tip_error of the plan's last state."""
+        current = np.ascontiguousarray(start_state, dtype=np.float64)
+        first = current.copy()
+        out = []
+        for request in requests:
+            request = np.asarray(request, dtype=np.float64)
+            ik = self.roadmapIk(request, tolerance, k, solver, auto_add=auto_add, mode=mode, delta=delta,
+                                accurate=accurate, lazy_add=lazy_add)
+            if ik is None:
+                raise RuntimeError("no IK results returned")
+            start_v, _ = self.addMilestone(first if common_start else current)
+            goal_v, _ = self.addMilestone(np.ascontiguousarray(ik["controls"], dtype=np.float64))
+            path, searches = self.solveWithRoadmap(start_v, goal_v)
+            if path is None:     # "Could not reach goal, no solution": make plan to just stay put
+                plan, status = self.states[[start_v]].copy(), "empty"
+            else:
+                plan, status = self.states[path].copy(), "exact"
+            tip = self.robot.shape_batch(plan[-1:], want=("tip",))["tip"][0]
+            out.append(dict(ik=ik, status=status, path=path, plan=plan, searches=searches, start_vertex=start_v,
+                            goal_vertex=goal_v, tip_error=float(np.linalg.norm(tip - request))))
+            if not common_start:
+                current = plan[-1].copy()
+        return out
 
     def roadmapIk(self, request, tolerance, k, solver, auto_add=False, mode=None, delta=1e-6, accurate=False,
                   lazy_add=False):
@@ -860,10 +964,8 @@ class VoxelCachedLazyPRM:
                 mine = [int(x) for x in eids[int(ptr[v]):int(ptr[v + 1])] if not self.edge_removed[x]]
                 todo = [x for x in mine if not self.edge_validity[x] & VALIDITY_TRUE]
                 if todo:
-                    vs = SetStore(self.ctx, self.grid)
-                    einfo = vs.voxelize_edges_indexed(self.robot, self.space, self.states, self.edges[todo])
-                    hit = vs.check(self.env)
-                    good = ((einfo["flags"] & FLAG_PARTIAL) == 0) & ~hit
+                    good = self._check_edges_now(todo) != 0
+                    self._edge_unchecked.difference_update(todo)
                     self.edge_validity[np.asarray(todo)[good]] = VALIDITY_TRUE
                     self.edge_removed[np.asarray(todo)[~good]] = True
         return result(i, controls=e["last_valid"], tip=e["tip"], error=e["error"], neighbor=src_state, accepted=False,

@@ -695,3 +695,96 @@ def test_roadmap_ik_every_branch_vs_sequential_reference(orc, wl, monkeypatch, a
     lazy, eager = stats[("fallback", True)], stats[("fallback", False)]
     assert any(n > 1 and valid == 1 for n, valid in lazy) and all(n == valid for n, valid in eager)
     assert sum(n for n, _ in eager) < sum(n for n, _ in lazy), "no lazily connected edge was found invalid"
+
+
+def test_chained_plan_host_logic(orc, wl, monkeypatch):
+    """The milestone loop of apps/roadmap_chained_plan.cpp:535-679 (roadmapIk -> start / goal milestones ->
+    solveWithRoadmap -> next start) over the batch mirror: every plan starts where the last one ended, ends at the IK
+    result, is valid item by item by the oracle and as short as the shortest path of the oracle-valid sub-graph of the
+    roadmap as it is then (milestones and lazy connections included); the items that joined the roadmap on the way are
+    checked one at a time when a query first asks (the reference's lazy checks), the two sweeps at the start stay the
+    only ones, and after an environment change the next sweeps cover the newcomers from a small scratch batch instead
+    of re-voxelising the roadmap (addMilestone: VoxelCachedLazyPRM.cpp:1854-1885, solvePrep: 2978-3025)."""
+    from irt_b200 import roadmap as R
+    spec = wl.robot_b(0.003)
+    g = wl.workspace_grid(spec)
+    ogrid, osp = orc.grid(g["Ng"], g["lim"]), orc.space()
+    oenv = orc.octree(ogrid)
+    oenv.add_sphere([0.05, 0.0, 0.12], 0.03)
+    prm = _prm(R, orc, wl, spec, g, oenv, monkeypatch)
+    prm.world = 1
+    prm.createRoadmap(140, lambda cnt, rnd: wl.sample_states(spec, cnt, stream=1500 + rnd),
+                      lambda st: wl.knn_edges(spec, st, k=5), opt=R.VoxelizeVertices | R.ValidateVertices)
+    prm.precomputeVoxelCache()
+    nv0, ne0 = len(prm.states), len(prm.edges)
+    calls0 = (prm.vertex_store.calls, prm.edge_store.calls)
+    lb, ub = np.zeros(7), np.array([20.0] * 6 + [spec["L"]])
+    solver = _dls_solver(lb, ub)
+    rng = np.random.default_rng(21)
+    requests = []
+    for _ in range(6):
+        goal = np.clip(prm.states[rng.integers(nv0)] + rng.normal(size=7) * [1, 1, 1, 1, 1, 1, 0.004], lb, ub)
+        requests.append(orc.fk_batch(prm.robot.orb, goal[None], 128, want_p=False)["tip"][0])
+    start = np.clip(prm.states[3] + 0.05, lb, ub)          # off the roadmap: becomes a milestone
+    assert prm._find_state(start) < 0
+
+    def oracle_truth():
+        vs, vf = orc.voxelize_vertices_batch(prm.robot.orb, ogrid, prm.states)
+        v_ok = (vf == 0) & ~orc.check_sets_batch(vs, prm.env.oenv).astype(bool)
+        es, ei = orc.voxelize_edges_batch(prm.robot.orb, ogrid, osp, prm.states[prm.edges[:, 0]], prm.states[prm.edges[:, 1]])
+        e_ok = ((ei["flags"] & 16) == 0) & ~orc.check_sets_batch(es, prm.env.oenv).astype(bool)
+        return v_ok, e_ok
+
+    def check_chain(start_state, chain):
+        current = start_state
+        exact = 0
+        for m in chain:
+            v_ok, e_ok = oracle_truth()          # the graph only grows / loses invalid items after this milestone
+            ctl = np.asarray(m["ik"]["controls"])
+            assert v_ok[m["goal_vertex"]] and np.array_equal(prm.states[m["goal_vertex"]], ctl)
+            assert np.array_equal(prm.states[m["start_vertex"]], current)
+            want = _shortest_valid_path_cost(prm, m["start_vertex"], m["goal_vertex"], v_ok, e_ok & ~prm.edge_removed)
+            if m["status"] == "exact":
+                exact += 1
+                path = m["path"]
+                assert path[0] == m["start_vertex"] and path[-1] == m["goal_vertex"]
+                assert np.array_equal(m["plan"], prm.states[path]) and all(v_ok[v] for v in path[1:-1])
+                eids = [prm.edge_index(u, v) for u, v in zip(path[:-1], path[1:])]
+                assert all(e >= 0 and e_ok[e] for e in eids)
+                cost = sum(float(prm.distance(prm.states[u], prm.states[v][None])[0]) for u, v in zip(path[:-1], path[1:]))
+                assert abs(cost - want) <= 1e-9 * max(1.0, want)
+                assert m["tip_error"] == pytest.approx(m["ik"]["error"], abs=1e-12)
+            else:
+                assert m["path"] is None and len(m["plan"]) == 1 and not np.isfinite(want)
+            current = m["plan"][-1]
+        return exact
+
+    prm.precomputeValidity()                               # the tick's two sweeps; the chain runs on their tables
+    chain = prm.chainedPlan(start, requests, 1e-4, 4, solver, auto_add=True)
+    assert len(chain) == len(requests)
+    assert check_chain(start, chain) >= 4
+    assert len(prm.states) > nv0 and len(prm.edges) > ne0, "milestones and their lazy connections joined the roadmap"
+    assert prm.lookups["sweeps"] == 2, "one vertex and one edge sweep for the whole chain"
+    singles = prm.lookups.get("single", 0)
+    assert 0 < singles <= (len(prm.states) - nv0) + (len(prm.edges) - ne0)
+    assert (prm.vertex_store.calls, prm.edge_store.calls) == calls0, "the caches were not rebuilt"
+    # the environment changes: the next chain sweeps again -- the cached sets by K3, the newcomers from a scratch batch
+    oenv2 = orc.octree(ogrid)
+    oenv2.add_sphere([-0.05, 0.02, 0.13], 0.03)
+    prm.env.oenv = oenv2
+    prm.clearValidity()
+    prm.restoreRemoved()
+    chain2 = prm.chainedPlan(chain[-1]["plan"][-1], requests[:3], 1e-4, 4, solver, auto_add=False)
+    assert check_chain(chain[-1]["plan"][-1], chain2) >= 1
+    assert prm.lookups["sweeps"] == 4 and (prm.vertex_store.calls, prm.edge_store.calls) == calls0
+    v_ok, e_ok = oracle_truth()
+    n_swept_v, n_swept_e = len(v_ok), len(e_ok)     # everything present at the sweep has its validity in the table
+    live = [e for e in range(n_swept_e) if e not in prm._edge_unchecked]
+    assert all(bool(prm.edge_validity[e]) == bool(e_ok[e]) for e in live if not prm.edge_removed[e])
+    assert all(bool(prm.vertex_validity[v]) == bool(v_ok[v]) for v in range(n_swept_v) if v not in prm._vertex_unchecked)
+    # too many newcomers: the next sweep rebuilds the cache instead
+    prm.max_uncached = 0
+    prm.clearValidity()
+    prm.precomputeValidity()
+    assert prm.vertex_store.calls == calls0[0] + 1 and prm.edge_store.calls == calls0[1] + 1
+    assert len(prm.vertex_flags) == len(prm.states) and len(prm.edge_flags) == len(prm.edges)
