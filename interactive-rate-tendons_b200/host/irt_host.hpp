@@ -1184,16 +1184,36 @@ public:
   void clearVoxelCache() { clearVertexVoxelCache(); clearEdgeVoxelCache(); }
   size_t vertexVoxelCacheSize() const { return (size_t)irt_setstore_num_sets(vstore_); }
   size_t edgeVoxelCacheSize() const { return (size_t)irt_setstore_num_sets(estore_); }
+  /// Items that joined the roadmap after its voxel cache was built (roadmapIk / addMilestone) have no cached set:
+  /// a sweep covers the cached sets with K3 and the few newcomers with one small scratch batch; only when there
+  /// are more than maxUncached() of them is the cache rebuilt.
+  void setMaxUncached(size_t n) { max_uncached_ = n; }
   void precomputeVertexValidity() {  // .cpp:1563-1598 with warm caches
-    if (vflags_.size() != states_.size()) precomputeVertexVoxelCache();
+    if (vflags_.size() != states_.size() &&
+        (vflags_.empty() || vflags_.size() > states_.size() || states_.size() - vflags_.size() > max_uncached_))
+      precomputeVertexVoxelCache();
     sweep(vstore_, vflags_, IRT_FLAG_NONCONVERGED | IRT_FLAG_LENGTH_LIMIT | IRT_FLAG_SELF_COLLISION | IRT_FLAG_BAD_STATE,
           vertex_validity_);
+    if (vertex_validity_.size() < states_.size()) {
+      std::vector<size_t> ids;
+      for (size_t v = vertex_validity_.size(); v < states_.size(); v++) ids.push_back(v);
+      for (unsigned x : checkVerticesNow(ids)) vertex_validity_.push_back(x);
+    }
+    vertex_unchecked_.clear();
     vertex_swept_ = true;
     sweeps_++;
   }
   void precomputeEdgeValidity() {  // .cpp:1600-1647
-    if (eflags_.size() != edges_.size()) precomputeEdgeVoxelCache();
+    if (eflags_.size() != edges_.size() &&
+        (eflags_.empty() || eflags_.size() > edges_.size() || edges_.size() - eflags_.size() > max_uncached_))
+      precomputeEdgeVoxelCache();
     sweep(estore_, eflags_, IRT_FLAG_PARTIAL, edge_validity_);
+    if (edge_validity_.size() < edges_.size()) {
+      std::vector<size_t> ids;
+      for (size_t e = edge_validity_.size(); e < edges_.size(); e++) ids.push_back(e);
+      for (unsigned x : checkEdgesNow(ids)) edge_validity_.push_back(x);
+    }
+    edge_unchecked_.clear();
     edge_swept_ = true;
     sweeps_++;
   }
@@ -1202,6 +1222,7 @@ public:
     vertex_validity_.assign(states_.size(), VALIDITY_UNKNOWN);
     edge_validity_.assign(edges_.size(), VALIDITY_UNKNOWN);
     vertex_swept_ = edge_swept_ = false;
+    vertex_unchecked_.clear(); edge_unchecked_.clear();
   }
 
   // ---- lazy-path consumers: the query side of the planner --------------------------
@@ -1211,16 +1232,25 @@ public:
   bool computeVertexValidity(size_t v) {
     if (!vertex_swept_) precomputeVertexValidity();
     lookups_++;
+    if (vertex_unchecked_.erase(v)) {   // joined the roadmap after the sweep, never checked: the reference's lazy check
+      vertex_validity_[v] = checkVerticesNow({v})[0];
+      single_checks_++;
+    }
     return (vertex_validity_[v] & VALIDITY_TRUE) != 0;
   }
   /// computeEdgeValidity (.cpp:2620-2631): is_fully_valid (no IRT_FLAG_PARTIAL) and no hit
   bool computeEdgeValidity(size_t e) {
     if (!edge_swept_) precomputeEdgeValidity();
     lookups_++;
+    if (edge_unchecked_.erase(e)) {
+      edge_validity_[e] = checkEdgesNow({e})[0];
+      single_checks_++;
+    }
     return (edge_validity_[e] & VALIDITY_TRUE) != 0;
   }
   size_t sweepCount() const { return sweeps_; }
   size_t lookupCount() const { return lookups_; }
+  size_t singleCheckCount() const { return single_checks_; }   // look-ups answered by checking one newcomer
   const std::vector<char> &removedVertices() const { return vertex_removed_; }
   const std::vector<char> &removedEdges() const { return edge_removed_; }
   void restoreRemoved() { vertex_removed_.assign(states_.size(), 0); edge_removed_.assign(edges_.size(), 0); }
@@ -1594,24 +1624,78 @@ public:
         for (size_t q = adj_ptr_[(size_t)v]; q < adj_ptr_[(size_t)v + 1]; q++)
           if (!edge_removed_[adj_eid_[q]] && !(edge_validity_[adj_eid_[q]] & VALIDITY_TRUE)) todo.push_back(adj_eid_[q]);
         if (!todo.empty()) {
-          const size_t nt = todo.size();
-          std::vector<double> a(nt * S), b(nt * S);
-          for (size_t j = 0; j < nt; j++) {
-            std::copy(states_[edges_[todo[j]].first].begin(), states_[edges_[todo[j]].first].end(), a.begin() + j * S);
-            std::copy(states_[edges_[todo[j]].second].begin(), states_[edges_[todo[j]].second].end(), b.begin() + j * S);
-          }
-          std::vector<uint32_t> fl(nt), w((nt + 31) / 32 + 1, 0);
-          irt::check(ctx_, irt_voxelize_edges(ctx_, robot_.handle(), &space_, a.data(), b.data(), (int)S, (int64_t)nt,
-                                              scratch, fl.data(), nullptr, nullptr));
-          irt::check(ctx_, irt_check_sets(ctx_, scratch, env_, 0, (int64_t)nt, w.data()));
-          for (size_t j = 0; j < nt; j++) {
-            if (!(fl[j] & IRT_FLAG_PARTIAL) && !((w[j >> 5] >> (j & 31)) & 1u)) edge_validity_[todo[j]] = VALIDITY_TRUE;
+          const std::vector<unsigned> val = checkEdgesNow(todo);
+          for (size_t j = 0; j < todo.size(); j++) {
+            edge_unchecked_.erase(todo[j]);
+            if (val[j] & VALIDITY_TRUE) edge_validity_[todo[j]] = VALIDITY_TRUE;
             else edge_removed_[todo[j]] = 1;
           }
         }
       }
     }
     return best;
+  }
+
+  /// addMilestone(state, connect) (.cpp:1854-1885): the vertex of an equal state when the roadmap has one
+  /// (tryAddToGraph), else a new vertex with VALIDITY_UNKNOWN, lazily connected -- edges of unknown validity -- to
+  /// its connection-strategy neighbours (the vertex itself is not in nn_ yet).  Nothing is voxelised here: queries
+  /// check the new items when they first ask for them.  Returns (vertex, was_added).
+  std::pair<size_t, bool> addMilestone(const std::vector<double> &state, bool connect = true) {
+    if (state.size() != robot_.state_size()) throw std::invalid_argument("State is not the right size");
+    build_adjacency();
+    const long have = findState(state);
+    if (have >= 0) return {(size_t)have, false};
+    std::vector<std::pair<double, size_t>> d;
+    if (connect)
+      for (size_t u = 0; u < states_.size(); u++)
+        if (!vertex_removed_[u]) d.emplace_back(distance(state, states_[u]), u);
+    const size_t kk = std::min(k_, d.size());
+    std::partial_sort(d.begin(), d.begin() + kk, d.end());
+    if (tips_.size() != 3 * states_.size()) precomputeVertexVoxelCache();
+    const collision::Point tip = robot_.forward_kinematics(state).back();
+    const size_t v = appendVertex(state, tip.data(), VALIDITY_UNKNOWN);
+    for (size_t j = 0; j < kk && d[j].first <= getRange(); j++) appendEdge(v, d[j].second, VALIDITY_UNKNOWN);
+    return {v, true};
+  }
+  struct ChainedStep {
+    IKResult ik;                              // roadmapIk's result for the request
+    bool exact = false;                       // false: no path, the plan stays put ("Could not reach goal, no solution")
+    std::vector<size_t> path;                 // roadmap vertices start .. goal
+    std::vector<std::vector<double>> plan;    // their states
+    size_t searches = 0, start_vertex = 0, goal_vertex = 0;
+    size_t n_vertices = 0, n_edges = 0;       // size of the roadmap the search ran on
+    double tip_error = 0.0;                   // of the plan's last state
+  };
+  /// The milestone loop of apps/roadmap_chained_plan.cpp:535-679: for every requested tip position roadmapIk gives
+  /// the goal configuration, start and goal join the roadmap as milestones (solvePrep, .cpp:2978-3025),
+  /// solveWithRoadmap plans between them, and the plan's last state is where the next milestone starts (unless
+  /// common_start).  Everything it asks of the device is a batch or a look-up.
+  std::vector<ChainedStep> chainedPlan(const std::vector<double> &start_state, const std::vector<collision::Point> &requests,
+                                       double tolerance, size_t k, const tip_control::IkSolver &solver,
+                                       unsigned opt = RMAP_IK_AUTO_ADD, int mode = IRT_JAC_LEVMAR_CENTRAL,
+                                       double delta = 1e-6, bool common_start = false) {
+    std::vector<double> current = start_state;
+    std::vector<ChainedStep> out;
+    for (const collision::Point &request : requests) {
+      auto ik = roadmapIk(request, tolerance, k, solver, mode, delta, opt);
+      if (!ik) throw std::runtime_error("no IK results returned");
+      ChainedStep st;
+      st.ik = *ik;
+      st.start_vertex = addMilestone(common_start ? start_state : current).first;
+      st.goal_vertex = addMilestone(ik->controls).first;
+      st.n_vertices = states_.size(); st.n_edges = edges_.size();
+      st.path = solveWithRoadmap(st.start_vertex, st.goal_vertex, &st.searches);
+      st.exact = !st.path.empty();
+      if (st.exact) for (size_t v : st.path) st.plan.push_back(states_[v]);
+      else st.plan.push_back(states_[st.start_vertex]);
+      const collision::Point tip = robot_.forward_kinematics(st.plan.back()).back();
+      double e2 = 0.0;
+      for (int c = 0; c < 3; c++) e2 += (tip[c] - request[c]) * (tip[c] - request[c]);
+      st.tip_error = std::sqrt(e2);
+      if (!common_start) current = st.plan.back();
+      out.push_back(std::move(st));
+    }
+    return out;
   }
 
 private:
@@ -1648,12 +1732,13 @@ private:
     if (std::find(out.begin(), out.end(), (long)ik_neighbor) == out.end()) out.push_back((long)ik_neighbor);
     return out;
   }
-  size_t appendVertex(const std::vector<double> &state, const double *tip) {
+  size_t appendVertex(const std::vector<double> &state, const double *tip, unsigned validity = VALIDITY_TRUE) {
     build_adjacency();
     states_.push_back(state);
-    vertex_validity_.push_back(VALIDITY_TRUE);
+    vertex_validity_.push_back(validity);
     vertex_removed_.push_back(0);
     tips_.insert(tips_.end(), tip, tip + 3);
+    if (!(validity & VALIDITY_TRUE)) vertex_unchecked_.insert(states_.size() - 1);
     return states_.size() - 1;                                   // vflags_ is now shorter: the cache lacks the vertex
   }
   void appendEdge(size_t a, size_t b, unsigned validity) {
@@ -1661,6 +1746,45 @@ private:
     edges_.emplace_back(a, b);
     edge_validity_.push_back(validity);
     edge_removed_.push_back(0);
+    if (!(validity & VALIDITY_TRUE)) edge_unchecked_.insert(edges_.size() - 1);
+  }
+  /// voxelizeVertex + collides for a few vertices (.cpp:2607-2618, 2803-2837)
+  std::vector<unsigned> checkVerticesNow(const std::vector<size_t> &ids) {
+    const size_t S = robot_.state_size(), m = ids.size();
+    std::vector<double> flat(m * S);
+    for (size_t i = 0; i < m; i++) std::copy(states_[ids[i]].begin(), states_[ids[i]].end(), flat.begin() + i * S);
+    std::vector<uint32_t> fl(m), w((m + 31) / 32 + 1, 0);
+    irt_setstore *scratch = nullptr;
+    irt_grid g = env_voxels_.grid(venv_.inv_rotation);
+    irt::check(ctx_, irt_setstore_create(ctx_, &g, &scratch));
+    std::shared_ptr<irt_setstore> guard(scratch, [](irt_setstore *x) { irt_setstore_destroy(x); });
+    irt::check(ctx_, irt_voxelize_vertices(ctx_, robot_.handle(), flat.data(), (int)S, (int64_t)m, scratch, fl.data(), nullptr));
+    irt::check(ctx_, irt_check_sets(ctx_, scratch, env_, 0, (int64_t)m, w.data()));
+    const uint32_t bad = IRT_FLAG_NONCONVERGED | IRT_FLAG_LENGTH_LIMIT | IRT_FLAG_SELF_COLLISION | IRT_FLAG_BAD_STATE;
+    std::vector<unsigned> out(m);
+    for (size_t i = 0; i < m; i++) out[i] = (!(fl[i] & bad) && !((w[i >> 5] >> (i & 31)) & 1u)) ? VALIDITY_TRUE : VALIDITY_UNKNOWN;
+    return out;
+  }
+  /// voxelizeEdge + collides for a few edges (.cpp:2620-2631, 2879-2902)
+  std::vector<unsigned> checkEdgesNow(const std::vector<size_t> &ids) {
+    const size_t S = robot_.state_size(), m = ids.size();
+    std::vector<double> a(m * S), b(m * S);
+    for (size_t i = 0; i < m; i++) {
+      std::copy(states_[edges_[ids[i]].first].begin(), states_[edges_[ids[i]].first].end(), a.begin() + i * S);
+      std::copy(states_[edges_[ids[i]].second].begin(), states_[edges_[ids[i]].second].end(), b.begin() + i * S);
+    }
+    std::vector<uint32_t> fl(m), w((m + 31) / 32 + 1, 0);
+    irt_setstore *scratch = nullptr;
+    irt_grid g = env_voxels_.grid(venv_.inv_rotation);
+    irt::check(ctx_, irt_setstore_create(ctx_, &g, &scratch));
+    std::shared_ptr<irt_setstore> guard(scratch, [](irt_setstore *x) { irt_setstore_destroy(x); });
+    irt::check(ctx_, irt_voxelize_edges(ctx_, robot_.handle(), &space_, a.data(), b.data(), (int)S, (int64_t)m, scratch,
+                                        fl.data(), nullptr, nullptr));
+    irt::check(ctx_, irt_check_sets(ctx_, scratch, env_, 0, (int64_t)m, w.data()));
+    std::vector<unsigned> out(m);
+    for (size_t i = 0; i < m; i++)
+      out[i] = (!(fl[i] & IRT_FLAG_PARTIAL) && !((w[i >> 5] >> (i & 31)) & 1u)) ? VALIDITY_TRUE : VALIDITY_UNKNOWN;
+    return out;
   }
   size_t removed_count() const {
     size_t c = 0;
@@ -1724,7 +1848,8 @@ private:
   std::vector<double> tips_;
   std::vector<unsigned> vertex_validity_, edge_validity_;
   bool vertex_swept_ = false, edge_swept_ = false;
-  size_t sweeps_ = 0, lookups_ = 0;
+  size_t sweeps_ = 0, lookups_ = 0, single_checks_ = 0, max_uncached_ = 4096;
+  std::set<size_t> vertex_unchecked_, edge_unchecked_;   // joined after the last sweep with VALIDITY_UNKNOWN
   std::vector<char> vertex_removed_, edge_removed_;
   std::vector<size_t> adj_ptr_, adj_nbr_, adj_eid_;
   size_t adj_edges_ = (size_t)-1;

@@ -754,7 +754,8 @@ class VoxelCachedLazyPRM:
         the IK's lockstep FK launches, one validity call and one until-invalid call per request, table look-ups
         along the A* path, and single checks only for the few items that joined the roadmap since the last sweep.
         Returns one dict per request: ik (roadmapIk's result), status ('exact' / 'empty': no path, the plan stays
-        put), path (vertex list or None), plan (states), searches, tip_error of the plan's last state."""
+        put), path (vertex list or None), plan (states), searches, n_vertices / n_edges of the roadmap the search ran on,
+        tip_error of the plan's last state."""
         current = np.ascontiguousarray(start_state, dtype=np.float64)
         first = current.copy()
         out = []
@@ -766,6 +767,7 @@ class VoxelCachedLazyPRM:
                 raise RuntimeError("no IK results returned")
             start_v, _ = self.addMilestone(first if common_start else current)
             goal_v, _ = self.addMilestone(np.ascontiguousarray(ik["controls"], dtype=np.float64))
+            n_v, n_e = len(self.states), len(self.edges)      # the roadmap the search runs on
             path, searches = self.solveWithRoadmap(start_v, goal_v)
             if path is None:     # "Could not reach goal, no solution": make plan to just stay put
                 plan, status = self.states[[start_v]].copy(), "empty"
@@ -773,7 +775,8 @@ class VoxelCachedLazyPRM:
                 plan, status = self.states[path].copy(), "exact"
             tip = self.robot.shape_batch(plan[-1:], want=("tip",))["tip"][0]
             out.append(dict(ik=ik, status=status, path=path, plan=plan, searches=searches, start_vertex=start_v,
-                            goal_vertex=goal_v, tip_error=float(np.linalg.norm(tip - request))))
+                            goal_vertex=goal_v, n_vertices=n_v, n_edges=n_e,
+                            tip_error=float(np.linalg.norm(tip - request))))
             if not common_start:
                 current = plan[-1].copy()
         return out

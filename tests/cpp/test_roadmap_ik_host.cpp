@@ -386,6 +386,93 @@ int main() {
             CHECK(prm.tipPositions()[3 * (size_t)got->added_vertex + c] == seq.tips[(size_t)want->vertex][c]);
         }
       }
+  // ---- chainedPlan: the milestone loop of apps/roadmap_chained_plan.cpp:535-679 ----------------------------------
+  {
+    PRM prm(robot, venv, env_vox);
+    fresh(prm);
+    prm.precomputeEdgeVoxelCache();
+    prm.precomputeValidity();                       // the tick's two sweeps; the chain runs on their tables
+    const size_t nv0 = prm.states().size(), ne0 = prm.edges().size(), sweeps0 = prm.sweepCount();
+    const size_t cache_v = prm.vertexVoxelCacheSize(), cache_e = prm.edgeVoxelCacheSize();
+    State start = prm.states()[3];
+    for (int j = 0; j < 6; j++) start[j] = std::min(20.0, start[j] + 0.05);   // off the roadmap: becomes a milestone
+    std::vector<Point> reqs(requests.begin(), requests.begin() + 5);
+    auto chain = prm.chainedPlan(start, reqs, 1e-4, 4, dls, PRM::RMAP_IK_AUTO_ADD, IRT_JAC_LEVMAR_CENTRAL, delta);
+    CHECK(chain.size() == reqs.size());
+    SeqPlanner orc_check{robot, orb, og, oenv, osp, prm, dls, delta, {}, {}, {}, {}};
+    // truth of the roadmap as it is now, item by item by the oracle
+    std::vector<char> v_ok(prm.states().size()), e_ok(prm.edges().size());
+    for (size_t v = 0; v < v_ok.size(); v++) v_ok[v] = orc_check.state_valid(prm.states()[v]);
+    for (size_t e = 0; e < e_ok.size(); e++)
+      e_ok[e] = !prm.removedEdges()[e] && orc_check.edge_valid(prm.states()[prm.edges()[e].first], prm.states()[prm.edges()[e].second]);
+    // Dijkstra over the valid sub-graph (ends always kept) of the roadmap as it was when the search ran
+    auto shortest = [&](size_t a, size_t b, size_t n, size_t n_edges) {
+      std::vector<double> dist(n, 1e300);
+      std::vector<char> done(n, 0);
+      dist[a] = 0.0;
+      for (;;) {
+        size_t u = n;
+        for (size_t v = 0; v < n; v++) if (!done[v] && dist[v] < 1e300 && (u == n || dist[v] < dist[u])) u = v;
+        if (u == n || u == b) break;
+        done[u] = 1;
+        for (size_t e = 0; e < n_edges; e++) {
+          if (!e_ok[e]) continue;
+          const auto &ed = prm.edges()[e];
+          if (ed.first != u && ed.second != u) continue;
+          const size_t w = ed.first == u ? ed.second : ed.first;
+          if (!(v_ok[w] || w == a || w == b) || prm.removedVertices()[w]) continue;
+          dist[w] = std::min(dist[w], dist[u] + prm.distance(prm.states()[u], prm.states()[w]));
+        }
+      }
+      return dist[b];
+    };
+    State current = start;
+    int exact = 0;
+    for (auto &m : chain) {
+      CHECK(prm.states()[m.start_vertex] == current && prm.states()[m.goal_vertex] == m.ik.controls);
+      CHECK(v_ok[m.goal_vertex]);
+      const double want = shortest(m.start_vertex, m.goal_vertex, m.n_vertices, m.n_edges);
+      if (m.exact) {
+        exact++;
+        CHECK(m.path.front() == m.start_vertex && m.path.back() == m.goal_vertex && m.plan.size() == m.path.size());
+        double cost = 0.0;
+        for (size_t q = 1; q < m.path.size(); q++) {
+          const long e = prm.edgeIndex(m.path[q - 1], m.path[q]);
+          CHECK(e >= 0 && e_ok[(size_t)e]);
+          if (q + 1 < m.path.size()) CHECK(v_ok[m.path[q]]);
+          cost += prm.distance(prm.states()[m.path[q - 1]], prm.states()[m.path[q]]);
+        }
+        CHECK(std::fabs(cost - want) <= 1e-9 * std::max(1.0, want));
+        CHECK(std::fabs(m.tip_error - m.ik.error) < 1e-12);
+      } else {
+        CHECK(m.path.empty() && m.plan.size() == 1 && want >= 1e300);
+      }
+      current = m.plan.back();
+    }
+    CHECK(exact >= 3);
+    CHECK(prm.states().size() > nv0 && prm.edges().size() > ne0);         // milestones and lazy connections joined
+    CHECK(prm.sweepCount() == sweeps0);                                   // no further sweep during the chain
+    CHECK(prm.singleCheckCount() > 0 && prm.singleCheckCount() <= (prm.states().size() - nv0) + (prm.edges().size() - ne0));
+    // an environment change: the next sweeps cover the newcomers from a scratch batch, the caches stay
+    prm.setEnvironment(env_vox.empty_copy());
+    prm.restoreRemoved();
+    prm.precomputeValidity();
+    CHECK(prm.vertexVoxelCacheSize() == cache_v && prm.edgeVoxelCacheSize() == cache_e);
+    CHECK(prm.vertexValidity().size() == prm.states().size() && prm.edgeValidity().size() == prm.edges().size());
+    orc_octree *empty = orc_octree_new(&og);
+    SeqPlanner free_check{robot, orb, og, empty, osp, prm, dls, delta, {}, {}, {}, {}};
+    for (size_t v = nv0; v < prm.states().size(); v++)
+      CHECK((prm.vertexValidity()[v] == 1u) == free_check.state_valid(prm.states()[v]));
+    for (size_t e = ne0; e < prm.edges().size(); e++)
+      CHECK((prm.edgeValidity()[e] == 1u) == free_check.edge_valid(prm.states()[prm.edges()[e].first], prm.states()[prm.edges()[e].second]));
+    orc_octree_free(empty);
+    prm.setMaxUncached(0);                          // too many newcomers: the next sweep rebuilds the caches
+    prm.clearValidity();
+    prm.precomputeValidity();
+    CHECK(prm.vertexVoxelCacheSize() == prm.states().size() && prm.edgeVoxelCacheSize() == prm.edges().size());
+    std::printf("chainedPlan: %d of %zu milestones reached exactly, %zu newcomers checked one at a time, %zu vertices / %zu edges joined\n",
+                exact, chain.size(), prm.singleCheckCount(), prm.states().size() - nv0, prm.edges().size() - ne0);
+  }
   for (const char *kind : {"accepted", "closest_valid", "stepped_back", "connected", "self", "fallback"})
     if (!seen.count(kind)) { std::printf("branch never reached: %s\n", kind); failures++; }
   CHECK(eager_edges < lazy_edges);   // validation removed some of the lazily connected edges

@@ -209,8 +209,10 @@ def test_cpp_roadmap_ik_every_branch(tmp_path, orc):
     """roadmapIk of the C++ host mirror, every branch (accepted, closest valid, stepping back, RMAP_IK_AUTO_ADD connected
     / the closest collision-free connection with and without RMAP_IK_LAZY_ADD, each with and without RMAP_IK_ACCURATE),
     against the reference's sequential loop (VoxelCachedLazyPRM.cpp:3095-3565) restated over the oracle in
-    tests/cpp/test_roadmap_ik_host.cpp: the same result, removals, added vertices / edges and validity.  Host logic:
-    linked against the test-only stand-in of the C ABI."""
+    tests/cpp/test_roadmap_ik_host.cpp: the same result, removals, added vertices / edges and validity; and chainedPlan
+    (the milestone loop of apps/roadmap_chained_plan.cpp:535-679: addMilestone's lazy connections checked on first use,
+    paths valid and shortest by the oracle, no further sweep, no cache rebuild).  Host logic: linked against the
+    test-only stand-in of the C ABI."""
     exe = str(tmp_path / "test_roadmap_ik_host")
     cpp = os.path.join(ROOT, "tests", "cpp")
     subprocess.check_call(["g++", "-std=c++17", "-O1", "-Wall", "-Wextra", "-Werror", "-DIRT_TEST_OVER_STANDIN",
@@ -220,7 +222,7 @@ def test_cpp_roadmap_ik_every_branch(tmp_path, orc):
                            "-Wl,-rpath," + os.path.join(ROOT, "oracle"), "-fopenmp"])
     out = subprocess.run([exe], capture_output=True, text=True, timeout=900)
     assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-2000:]
-    assert "roadmap ik ok" in out.stdout
+    assert "roadmap ik ok" in out.stdout and "chainedPlan:" in out.stdout
     for kind in ("accepted", "closest_valid", "stepped_back", "connected", "self", "fallback"):
         assert kind in out.stdout
 

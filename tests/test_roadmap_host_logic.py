@@ -743,7 +743,9 @@ def test_chained_plan_host_logic(orc, wl, monkeypatch):
             ctl = np.asarray(m["ik"]["controls"])
             assert v_ok[m["goal_vertex"]] and np.array_equal(prm.states[m["goal_vertex"]], ctl)
             assert np.array_equal(prm.states[m["start_vertex"]], current)
-            want = _shortest_valid_path_cost(prm, m["start_vertex"], m["goal_vertex"], v_ok, e_ok & ~prm.edge_removed)
+            e_then = e_ok & ~prm.edge_removed
+            e_then[m["n_edges"]:] = False          # the roadmap the search ran on: what joined later is not part of it
+            want = _shortest_valid_path_cost(prm, m["start_vertex"], m["goal_vertex"], v_ok, e_then)
             if m["status"] == "exact":
                 exact += 1
                 path = m["path"]
