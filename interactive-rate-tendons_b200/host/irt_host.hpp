@@ -1256,9 +1256,9 @@ public:
   void restoreRemoved() { vertex_removed_.assign(states_.size(), 0); edge_removed_.assign(edges_.size(), 0); }
   long edgeIndex(size_t a, size_t b) {
     build_adjacency();
-    for (size_t k = adj_ptr_[a]; k < adj_ptr_[a + 1]; k++)
-      if (adj_nbr_[k] == b) return (long)adj_eid_[k];
-    return -1;
+    long found = -1;
+    for_neighbors(a, [&](size_t nbr, size_t eid) { if (found < 0 && nbr == b) found = (long)eid; });
+    return found;
   }
   /// astarSearch (.cpp:2950-2976): A* over the current graph (removed vertices / edges left out), motion cost as
   /// edge weight and heuristic.  Host code in the reference (Boost.Graph) and here.  Empty = no path.
@@ -1284,15 +1284,14 @@ public:
         return path;
       }
       done[u] = 1;
-      for (size_t k = adj_ptr_[u]; k < adj_ptr_[u + 1]; k++) {
-        const size_t v = adj_nbr_[k];
-        if (edge_removed_[adj_eid_[k]] || vertex_removed_[v] || done[v]) continue;
+      for_neighbors(u, [&](size_t v, size_t eid) {
+        if (edge_removed_[eid] || vertex_removed_[v] || done[v]) return;
         const double nd = dist[u] + distance(states_[u], states_[v]);
         if (nd < dist[v]) {
           dist[v] = nd; prev[v] = u;
           heap.push({nd + distance(states_[v], states_[goal]), v});
         }
-      }
+      });
     }
     return path;
   }
@@ -1621,8 +1620,9 @@ public:
       if (!lazy_add) {   // every edge of the vertex is validated now, the invalid ones removed
         build_adjacency();
         std::vector<size_t> todo;
-        for (size_t q = adj_ptr_[(size_t)v]; q < adj_ptr_[(size_t)v + 1]; q++)
-          if (!edge_removed_[adj_eid_[q]] && !(edge_validity_[adj_eid_[q]] & VALIDITY_TRUE)) todo.push_back(adj_eid_[q]);
+        for_neighbors((size_t)v, [&](size_t, size_t eid) {
+          if (!edge_removed_[eid] && !(edge_validity_[eid] & VALIDITY_TRUE)) todo.push_back(eid);
+        });
         if (!todo.empty()) {
           const std::vector<unsigned> val = checkEdgesNow(todo);
           for (size_t j = 0; j < todo.size(); j++) {
@@ -1713,7 +1713,7 @@ private:
   size_t outDegree(size_t v) {
     build_adjacency();
     size_t c = 0;
-    for (size_t q = adj_ptr_[v]; q < adj_ptr_[v + 1]; q++) c += !edge_removed_[adj_eid_[q]] && !vertex_removed_[adj_nbr_[q]];
+    for_neighbors(v, [&](size_t nbr, size_t eid) { c += !edge_removed_[eid] && !vertex_removed_[nbr]; });
     return c;
   }
   /// `nearest` of .cpp:3238-3246, 3340-3349, 3470-3478; -1 stands for the result's own temporary vertex
@@ -1746,6 +1746,9 @@ private:
     edges_.emplace_back(a, b);
     edge_validity_.push_back(validity);
     edge_removed_.push_back(0);
+    adj_extra_[a].emplace_back(b, edges_.size() - 1);
+    adj_extra_[b].emplace_back(a, edges_.size() - 1);
+    adj_extra_count_++;
     if (!(validity & VALIDITY_TRUE)) edge_unchecked_.insert(edges_.size() - 1);
   }
   /// voxelizeVertex + collides for a few vertices (.cpp:2607-2618, 2803-2837)
@@ -1794,7 +1797,12 @@ private:
   }
   void build_adjacency() {
     const size_t n = states_.size(), m = edges_.size();
-    if (adj_edges_ == m && adj_ptr_.size() == n + 1) return;
+    // edges appended one query at a time (roadmapIk / addMilestone) live in per-vertex lists next to the CSR
+    // (adj_extra_) instead of costing a rebuild each; folded in when their share passes 1/64
+    if (adj_edges_ != (size_t)-1 && adj_edges_ <= m && m - adj_edges_ == adj_extra_count_ &&
+        m - adj_edges_ <= std::max<size_t>(1024, adj_edges_ / 64))
+      return;
+    adj_extra_.clear(); adj_extra_count_ = 0;
     adj_ptr_.assign(n + 1, 0);
     for (auto &e : edges_) { adj_ptr_[e.first + 1]++; adj_ptr_[e.second + 1]++; }
     for (size_t i = 0; i < n; i++) adj_ptr_[i + 1] += adj_ptr_[i];
@@ -1807,6 +1815,15 @@ private:
     adj_edges_ = m;
     if (vertex_removed_.size() != n) vertex_removed_.assign(n, 0);
     if (edge_removed_.size() != m) edge_removed_.assign(m, 0);
+  }
+  /// fn(neighbour, edge id) for every edge at v: its CSR row, then the edges appended since the CSR was built
+  template <class F>
+  void for_neighbors(size_t v, F &&fn) const {
+    if (v + 1 < adj_ptr_.size())
+      for (size_t q = adj_ptr_[v]; q < adj_ptr_[v + 1]; q++) fn(adj_nbr_[q], adj_eid_[q]);
+    auto it = adj_extra_.find(v);
+    if (it != adj_extra_.end())
+      for (auto &ne : it->second) fn(ne.first, ne.second);
   }
   void clear_store(irt_setstore *st) {
     const uint64_t off = 0;
@@ -1852,7 +1869,8 @@ private:
   std::set<size_t> vertex_unchecked_, edge_unchecked_;   // joined after the last sweep with VALIDITY_UNKNOWN
   std::vector<char> vertex_removed_, edge_removed_;
   std::vector<size_t> adj_ptr_, adj_nbr_, adj_eid_;
-  size_t adj_edges_ = (size_t)-1;
+  size_t adj_edges_ = (size_t)-1, adj_extra_count_ = 0;
+  std::map<size_t, std::vector<std::pair<size_t, size_t>>> adj_extra_;   // vertex -> (neighbour, edge id) appended since
   Sampler sampler_;
   std::function<std::vector<size_t>(size_t)> connection_;
   std::mt19937 gen_{20220801u};

@@ -177,6 +177,8 @@ class VoxelCachedLazyPRM:
         self.vertex_removed = np.zeros(0, dtype=bool)   # removeVertices / removeEdge of constructSolution
         self.edge_removed = np.zeros(0, dtype=bool)
         self._adj = None
+        self._adj_extra, self._adj_extra_count = {}, 0   # edges appended since the CSR adjacency was built
+        self._bufs = {}                                  # growth buffers of the arrays queries append to (_grow)
         self.lookups = {"vertex": 0, "edge": 0, "sweeps": 0}
         # vertices / edges that joined the roadmap after the last sweep with VALIDITY_UNKNOWN (addMilestone's lazy
         # connections): checked one at a time when a query first asks, like the reference's lazy checks
@@ -535,9 +537,13 @@ class VoxelCachedLazyPRM:
         return bool(self.edge_validity[e] & VALIDITY_TRUE)
 
     def _adjacency(self):
-        """CSR adjacency (neighbour vertex, edge id) of the undirected roadmap; rebuilt when the edge list changes"""
-        if self._adj is None or self._adj[3] != len(self.edges):
-            n, m = len(self.states), len(self.edges)
+        """CSR adjacency (neighbour vertex, edge id) of the undirected roadmap.  Edges appended one query at a time
+        (roadmapIk / addMilestone) go to per-vertex lists next to it (_adj_extra) instead of costing a rebuild each;
+        it is rebuilt when the edge list was replaced or the appended share passes 1/64.  Use _neighbors(v)."""
+        m = len(self.edges)
+        base = -1 if self._adj is None else self._adj[3]
+        if base < 0 or base > m or m - base != self._adj_extra_count or m - base > max(1024, base // 64):
+            n = len(self.states)
             src = np.concatenate([self.edges[:, 0], self.edges[:, 1]])
             dst = np.concatenate([self.edges[:, 1], self.edges[:, 0]])
             eid = np.concatenate([np.arange(m), np.arange(m)])
@@ -545,18 +551,33 @@ class VoxelCachedLazyPRM:
             ptr = np.zeros(n + 1, dtype=np.int64)
             ptr[1:] = np.cumsum(np.bincount(src, minlength=n))
             self._adj = (ptr, dst[order], eid[order], m)
+            self._adj_extra, self._adj_extra_count = {}, 0
             if len(self.vertex_removed) != n:
                 self.vertex_removed = np.zeros(n, dtype=bool)
             if len(self.edge_removed) != m:
                 self.edge_removed = np.zeros(m, dtype=bool)
         return self._adj[:3]
 
+    def _neighbors(self, v):
+        """(neighbour vertices, edge ids) of v: its CSR row plus the edges appended since the CSR was built"""
+        ptr, nbr, eid = self._adjacency()
+        if v + 1 < len(ptr):
+            lo, hi = int(ptr[v]), int(ptr[v + 1])
+            bn, be = nbr[lo:hi], eid[lo:hi]
+        else:                                   # a vertex that joined after the CSR was built
+            bn = be = np.zeros(0, dtype=np.int64)
+        extra = self._adj_extra.get(int(v))
+        if extra:
+            ex = np.asarray(extra, dtype=np.int64)
+            bn, be = np.concatenate([bn, ex[:, 0]]), np.concatenate([be, ex[:, 1]])
+        return bn, be
+
     def astarSearch(self, start, goal):
         """astarSearch (VoxelCachedLazyPRM.cpp:2950-2976): A* over the current graph (removed vertices / edges
         left out) with the motion cost as edge weight and as heuristic.  Host code in the reference (Boost.Graph)
         and here; it never touches the device.  Returns the vertex list start..goal or None."""
         import heapq
-        ptr, nbr, eid = self._adjacency()
+        self._adjacency()
         if self.vertex_removed[start] or self.vertex_removed[goal]:
             return None
         gs = self.states[goal]
@@ -574,9 +595,9 @@ class VoxelCachedLazyPRM:
                     path.append(prev[path[-1]])
                 return path[::-1]
             done.add(u)
-            lo, hi = int(ptr[u]), int(ptr[u + 1])
-            ok = ~(self.edge_removed[eid[lo:hi]] | self.vertex_removed[nbr[lo:hi]])
-            vs = nbr[lo:hi][ok]
+            nb_u, eid_u = self._neighbors(u)
+            ok = ~(self.edge_removed[eid_u] | self.vertex_removed[nb_u])
+            vs = nb_u[ok]
             if not len(vs):
                 continue
             w = self.distance(self.states[u], self.states[vs])
@@ -590,10 +611,9 @@ class VoxelCachedLazyPRM:
         return None
 
     def edge_index(self, a, b):
-        ptr, nbr, eid = self._adjacency()
-        lo, hi = int(ptr[a]), int(ptr[a + 1])
-        hit = np.nonzero(nbr[lo:hi] == b)[0]
-        return int(eid[lo + hit[0]]) if len(hit) else -1
+        nb_a, eid_a = self._neighbors(a)
+        hit = np.nonzero(nb_a == b)[0]
+        return int(eid_a[hit[0]]) if len(hit) else -1
 
     def constructSolution(self, start, goal):
         """constructSolution (VoxelCachedLazyPRM.cpp:2689-2771): A* path, then the lazy validity checks along it --
@@ -673,9 +693,8 @@ class VoxelCachedLazyPRM:
         return int(hit[0]) if len(hit) else -1
 
     def _out_degree(self, v):
-        ptr, nbr, eid = self._adjacency()
-        lo, hi = int(ptr[v]), int(ptr[v + 1])
-        return int((~(self.edge_removed[eid[lo:hi]] | self.vertex_removed[nbr[lo:hi]])).sum())
+        nb_v, eid_v = self._neighbors(v)
+        return int((~(self.edge_removed[eid_v] | self.vertex_removed[nb_v])).sum())
 
     def _ik_nearest(self, x, own, ik_neighbor, accurate, removed):
         """the would-be edge sources of an IK result x (`nearest` of VoxelCachedLazyPRM.cpp:3238-3246, 3340-3349,
@@ -697,27 +716,44 @@ class VoxelCachedLazyPRM:
             out.append(int(ik_neighbor))
         return out
 
+    def _grow(self, name, rows):
+        """append rows to the array attribute `name` in amortised O(rows): the attribute is a view of the leading rows
+        of a buffer with spare capacity (a 10M-edge roadmap is 160 MB of index pairs; a query appends a handful)"""
+        cur = getattr(self, name)
+        rows = np.asarray(rows, dtype=cur.dtype).reshape((-1,) + cur.shape[1:])
+        n, k = len(cur), len(rows)
+        buf = self._bufs.get(name)
+        if buf is None or cur.base is not buf or n + k > len(buf) or (n and cur.ctypes.data != buf.ctypes.data):
+            buf = np.empty((max(2 * n, n + k + 1024),) + cur.shape[1:], dtype=cur.dtype)
+            buf[:n] = cur
+            self._bufs[name] = buf
+        buf[n:n + k] = rows
+        setattr(self, name, buf[:n + k])
+
     def _append_vertex(self, state, tip, validity=VALIDITY_TRUE):
         v = len(self.states)
         self._adjacency()
-        self.states = np.ascontiguousarray(np.concatenate([self.states, state[None]], axis=0))
-        self.vertex_validity = np.append(self.vertex_validity, np.uint8(validity))
+        self._grow("states", np.asarray(state, dtype=np.float64)[None])
+        self._grow("vertex_validity", [validity])
         if not validity & VALIDITY_TRUE:
             self._vertex_unchecked.add(v)
-        self.vertex_removed = np.append(self.vertex_removed, False)
-        self.tips = np.concatenate([self.tips, np.asarray(tip, dtype=np.float64)[None]], axis=0)
-        self._adj = None                  # the voxel cache lacks the new vertex: sweeps treat it as the tail (_tail)
-        return v
+        self._grow("vertex_removed", [False])
+        self._grow("tips", np.asarray(tip, dtype=np.float64)[None])
+        return v                          # the voxel cache lacks the new vertex: sweeps treat it as the tail (_tail)
 
     def _append_edges(self, pairs, validity):
         self._adjacency()
         pairs = np.asarray(pairs, dtype=np.int64).reshape(-1, 2)
-        self.edges = np.ascontiguousarray(np.concatenate([self.edges, pairs], axis=0))
-        self.edge_validity = np.append(self.edge_validity, np.full(len(pairs), validity, dtype=np.uint8))
-        self.edge_removed = np.append(self.edge_removed, np.zeros(len(pairs), dtype=bool))
+        e0 = len(self.edges)
+        self._grow("edges", pairs)
+        self._grow("edge_validity", np.full(len(pairs), validity, dtype=np.uint8))
+        self._grow("edge_removed", np.zeros(len(pairs), dtype=bool))
         if not validity & VALIDITY_TRUE:
-            self._edge_unchecked.update(range(len(self.edges) - len(pairs), len(self.edges)))
-        self._adj = None
+            self._edge_unchecked.update(range(e0, e0 + len(pairs)))
+        for j, (a, b) in enumerate(pairs.tolist()):
+            self._adj_extra.setdefault(a, []).append((b, e0 + j))
+            self._adj_extra.setdefault(b, []).append((a, e0 + j))
+        self._adj_extra_count += len(pairs)
 
     def addMilestone(self, state, connect=True):
         """addMilestone(state, connect) (VoxelCachedLazyPRM.cpp:1854-1885): the vertex of an equal state when the
@@ -963,8 +999,7 @@ class VoxelCachedLazyPRM:
             else:
                 self.edge_validity[eid] = VALIDITY_TRUE
             if not lazy_add:           # every edge of the vertex is validated now, the invalid ones removed
-                ptr, nbr, eids = self._adjacency()
-                mine = [int(x) for x in eids[int(ptr[v]):int(ptr[v + 1])] if not self.edge_removed[x]]
+                mine = [int(x) for x in self._neighbors(v)[1] if not self.edge_removed[x]]
                 todo = [x for x in mine if not self.edge_validity[x] & VALIDITY_TRUE]
                 if todo:
                     good = self._check_edges_now(todo) != 0

@@ -790,3 +790,52 @@ def test_chained_plan_host_logic(orc, wl, monkeypatch):
     prm.precomputeValidity()
     assert prm.vertex_store.calls == calls0[0] + 1 and prm.edge_store.calls == calls0[1] + 1
     assert len(prm.vertex_flags) == len(prm.states) and len(prm.edge_flags) == len(prm.edges)
+
+
+def test_appends_keep_adjacency_and_arrays_incremental(orc, wl, monkeypatch):
+    """A query appends a handful of vertices / edges to a roadmap of millions: the arrays grow in place (amortised) and
+    the CSR adjacency is kept, the newcomers living in per-vertex lists next to it until their share passes 1/64;
+    neighbours, edge_index, degrees and A* see the same graph as a rebuild from scratch."""
+    from irt_b200 import roadmap as R
+    spec = wl.robot_b(0.003)
+    g = wl.workspace_grid(spec)
+    oenv = orc.octree(orc.grid(g["Ng"], g["lim"]))
+    prm = _prm(R, orc, wl, spec, g, oenv, monkeypatch)
+    rng = np.random.default_rng(31)
+    n, m = 200_000, 1_000_000
+    states = wl.sample_states(spec, 2000, stream=77)[rng.integers(0, 2000, n)] + rng.normal(size=(n, 7)) * 1e-3
+    edges = np.stack([rng.integers(0, n, m), rng.integers(0, n, m)], axis=1)
+    prm.set_roadmap(states, edges)
+    prm.tips = np.zeros((n, 3))
+    prm._vertex_swept = prm._edge_swept = True            # tables as after a sweep: the appends below carry their own validity
+    prm.vertex_validity[:] = 1
+    prm.edge_validity[:] = 1
+    prm._adjacency()
+    base = prm._adj
+    added_e = []
+    for q in range(150):
+        v = prm._append_vertex(states[q] + 0.5, np.zeros(3))
+        pairs = [[v, int(rng.integers(0, n))] for _ in range(4)] + [[int(rng.integers(0, n)), int(rng.integers(0, n))]]
+        e0 = len(prm.edges)
+        prm._append_edges(pairs, R.VALIDITY_TRUE)
+        added_e += [(e0 + j, a, b) for j, (a, b) in enumerate(pairs)]
+        assert prm.edge_index(v, pairs[2][1]) in range(e0, e0 + 4) and prm._out_degree(v) >= 4
+    assert prm._adj is base, "the CSR adjacency was rebuilt by an append"
+    assert prm.states.base is prm._bufs["states"] and prm.edges.base is prm._bufs["edges"], "arrays grow inside their buffers"
+    assert len(prm.states) == n + 150 and len(prm.edges) == m + 750 == len(prm.edge_validity) == len(prm.edge_removed)
+    # the same graph as a rebuild from scratch
+    probe = [int(v) for v in rng.integers(0, n, 50)] + [n + 3, n + 149] + [a for _, a, _ in added_e[:20]]
+    got = {v: sorted(zip(*[x.tolist() for x in prm._neighbors(v)])) for v in probe}
+    path_inc = prm.astarSearch(n + 5, n + 140)
+    prm._adj = None
+    prm._adjacency()
+    assert prm._adj_extra_count == 0 and prm._adj[3] == m + 750
+    for v in probe:
+        assert got[v] == sorted(zip(*[x.tolist() for x in prm._neighbors(v)]))
+    assert path_inc == prm.astarSearch(n + 5, n + 140)
+    for e, a, b in added_e[::37]:
+        assert prm.edges[e].tolist() == [a, b] and prm.edge_index(a, b) >= 0
+    # past 1/64 of the edges the lists are folded into a new CSR
+    prm._append_edges(np.stack([rng.integers(0, n, 20000), rng.integers(0, n, 20000)], axis=1), R.VALIDITY_TRUE)
+    prm._adjacency()
+    assert prm._adj_extra_count == 0 and prm._adj[3] == len(prm.edges)
